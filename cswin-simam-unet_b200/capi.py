@@ -1,0 +1,99 @@
+"""ctypes binding of libcsb200.so (include/csb200.h) — the only door between PyTorch host code and
+the sm_100a kernels.  There is NO CPU fallback: a missing library or a CPU tensor raises."""
+import ctypes
+import os
+import threading
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcsb200.so")
+
+OK, ERR_INVALID, ERR_UNSUPPORTED, ERR_CUDA, ERR_WORKSPACE = 0, 1, 2, 3, 4
+F32, BF16 = 0, 1
+NCHW, NLC = 0, 1
+ENGINE_AUTO, ENGINE_SIMT, ENGINE_TCGEN05 = 0, 1, 2
+
+_DTYPES = {torch.float32: F32, torch.bfloat16: BF16}
+
+
+class StripeDesc(ctypes.Structure):
+    """Mirror of csb200_stripe_desc."""
+    _fields_ = [("dtype", ctypes.c_int32), ("batch", ctypes.c_int32), ("height", ctypes.c_int32),
+                ("width", ctypes.c_int32), ("h_sp", ctypes.c_int32), ("w_sp", ctypes.c_int32),
+                ("heads", ctypes.c_int32), ("head_dim", ctypes.c_int32), ("scale", ctypes.c_float),
+                ("engine", ctypes.c_int32)] + [
+        (n, ctypes.c_int64) for n in ("q_sb", "q_sl", "k_sb", "k_sl", "v_sb", "v_sl", "o_sb", "o_sl",
+                                      "dq_sb", "dq_sl", "dk_sb", "dk_sl", "dv_sb", "dv_sl")]
+
+
+_lib = None
+_lock = threading.Lock()
+
+EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_count", "csb200_simam_fwd",
+           "csb200_simam_bwd", "csb200_stripe_attn_engine", "csb200_stripe_attn_fwd",
+           "csb200_stripe_attn_bwd_workspace_bytes", "csb200_stripe_attn_bwd")
+
+
+def lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(or `make -C cswin-simam-unet_b200/csrc`). There is no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        vp, i64, f32p = ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p
+        L.csb200_abi_version.restype = ctypes.c_int
+        L.csb200_last_error_string.restype = ctypes.c_char_p
+        L.csb200_launch_count.restype = ctypes.c_uint64
+        L.csb200_simam_fwd.argtypes = [vp, vp, f32p, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp]
+        L.csb200_simam_bwd.argtypes = [vp, vp, f32p, vp, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp]
+        dp = ctypes.POINTER(StripeDesc)
+        L.csb200_stripe_attn_engine.argtypes = [dp, ctypes.c_int]
+        L.csb200_stripe_attn_fwd.argtypes = [dp, vp, vp, vp, f32p, f32p, vp, f32p, vp]
+        L.csb200_stripe_attn_bwd_workspace_bytes.argtypes = [dp]
+        L.csb200_stripe_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
+        L.csb200_stripe_attn_bwd.argtypes = [dp] + [vp] * 15 + [ctypes.c_size_t, vp]
+        for fn in ("csb200_simam_fwd", "csb200_simam_bwd", "csb200_stripe_attn_engine",
+                   "csb200_stripe_attn_fwd", "csb200_stripe_attn_bwd"):
+            getattr(L, fn).restype = ctypes.c_int
+        if L.csb200_abi_version() != 1:
+            raise RuntimeError("libcsb200.so ABI version mismatch; rebuild")
+        _lib = L
+    return _lib
+
+
+def last_error() -> str:
+    return lib().csb200_last_error_string().decode()
+
+
+def launch_count() -> int:
+    return int(lib().csb200_launch_count())
+
+
+def check(rc: int, what: str):
+    """Shape errors surface as RuntimeError, like the view() failure of the reference (C:204)."""
+    if rc != OK:
+        raise RuntimeError(f"{what} failed (csb200 status {rc}): {last_error()}")
+
+
+def dtype_code(t: torch.Tensor) -> int:
+    try:
+        return _DTYPES[t.dtype]
+    except KeyError:
+        raise TypeError(f"csb200 kernels take float32 or bfloat16 tensors, got {t.dtype}") from None
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("csb200 kernels run on sm_100a only: got a CPU tensor and there is no CPU fallback")
+
+
+def stream_of(t: torch.Tensor) -> int:
+    return torch.cuda.current_stream(t.device).cuda_stream

@@ -1,0 +1,775 @@
+// SimAM forward / backward for sm_100a.
+//
+// SimAM is not in the reference checkout; the arithmetic follows the public module
+// (Yang et al., ICML 2021) restated in oracle/simam_oracle.py.  Both passes are HBM-bound: the design
+// goal is algorithmic traffic only — forward 1 read + 1 write, backward 2 reads + 1 write — which
+// means a plane must stay on chip between the statistics and the rescale.
+//
+// Fast paths ("resident"): every thread keeps its share of the plane in REGISTERS as 16-byte
+// vectors, all loads are issued before the first use (deep memory-level parallelism), the mean and
+// the centred second moment are reduced by warp shuffles -> shared memory -> (for planes larger than
+// one CTA can hold) DSMEM across a thread-block cluster of 2/4/8 CTAs, and the result is written
+// straight from the same registers.  The variance is the exact two-pass form sum((x-mean)^2) — the
+// second pass costs nothing because the data is already in registers — so large-mean inputs keep
+// the 1e-5 fp32 parity target.
+//
+//   NCHW (UNet, U:177-250): a plane is H*W contiguous elements.
+//   NLC  (CSWin tokens, C:349): a plane is a column of a (L, C) matrix; a CTA cluster owns a slab of
+//        32/64/128-byte-wide row segments and reduces per channel.
+//
+// Generic paths: any shape / alignment, three sweeps (the 2nd and 3rd normally hit L2).
+
+#include "common.cuh"
+
+namespace csb200 {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// shared arithmetic
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct Sig {
+  // fp32: ex2.approx + rcp.approx based; ~3e-7 relative error, well inside the 1e-5 target
+  static __device__ __forceinline__ float f(float y) { return __fdividef(1.f, 1.f + __expf(-y)); }
+};
+template <>
+struct Sig<__nv_bfloat16> {
+  // bf16 output has 8 mantissa bits; a single MUFU.TANH (2^-11 abs error) is 4x below its rounding
+  static __device__ __forceinline__ float f(float y) {
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(0.5f * y));
+    return fmaf(0.5f, t, 0.5f);
+  }
+};
+
+struct FwdCoef {
+  float mean, inv4v;
+};
+template <typename T>
+__device__ __forceinline__ float simam_fwd_elem(float x, const FwdCoef& c) {
+  float t = x - c.mean;
+  return x * Sig<T>::f(fmaf(t * t, c.inv4v, 0.5f));
+}
+
+// ------------------------------------------------------------------------------------------------
+// block / cluster reduction of NV scalars held by every thread (NCHW: one plane per CTA/cluster)
+// ------------------------------------------------------------------------------------------------
+template <int THREADS, int CLUSTER, int NV>
+__device__ __forceinline__ void plane_reduce(float (&v)[NV], float* s_warp /*[NV][32]*/,
+                                             float* s_cta /*[NV]*/) {
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = warp_sum(v[i]);
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < NV; ++i) s_warp[i * 32 + warp] = v[i];
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) a += s_warp[i * 32 + w];  // broadcast reads, fixed order
+    v[i] = a;
+  }
+  if constexpr (CLUSTER > 1) {
+    if (threadIdx.x == 0) {
+#pragma unroll
+      for (int i = 0; i < NV; ++i) s_cta[i] = v[i];
+    }
+    cluster_sync_all();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < CLUSTER; ++r) a += dsmem_ld_f32(&s_cta[i], r);  // same order everywhere
+      v[i] = a;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// NCHW resident forward.  WARP_PLANE: one warp per plane (small planes), else one CTA / cluster.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int VPT, int THREADS, int CLUSTER, bool WARP_PLANE>
+__global__ void __launch_bounds__(THREADS)
+    simam_nchw_fwd_resident(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats,
+                            int64_t planes, int nvec, float S, float e_lambda) {
+  constexpr int VE = Vec16<T>::N;
+  __shared__ float s_warp[2 * 32];
+  __shared__ float s_cta[2];
+
+  int64_t plane;
+  int v0, vstride;
+  if constexpr (WARP_PLANE) {
+    plane = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    v0 = threadIdx.x & 31;
+    vstride = 32;
+    if (plane >= planes) return;  // whole warp leaves; no block-level sync on this path
+  } else {
+    plane = blockIdx.x / CLUSTER;
+    const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    v0 = rank * (THREADS * VPT) + threadIdx.x;
+    vstride = THREADS;
+  }
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + plane * nvec;
+  uint4* yp = reinterpret_cast<uint4*>(y) + plane * nvec;
+
+  uint4 d[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int vi = v0 + i * vstride;
+    d[i] = (vi < nvec) ? ld_stream(xp + vi) : make_uint4(0, 0, 0, 0);
+  }
+  // pass A: sum (zero padding of invalid slots is harmless)
+  float red[1] = {0.f};
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    float f[VE];
+    unpack<T>(d[i], f);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) red[0] += f[e];
+  }
+  if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
+  else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp, s_cta);
+  const float mean = red[0] / S;
+
+  // pass B: centred second moment
+  red[0] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    if (v0 + i * vstride < nvec) {
+      float f[VE];
+      unpack<T>(d[i], f);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        float t = f[e] - mean;
+        red[0] = fmaf(t, t, red[0]);
+      }
+    }
+  }
+  if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
+  else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp + 32, s_cta + 1);
+  const float v = red[0] / (S - 1.f) + e_lambda;
+  FwdCoef c{mean, 1.f / (4.f * v)};
+
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int vi = v0 + i * vstride;
+    if (vi < nvec) {
+      float f[VE];
+      unpack<T>(d[i], f);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) f[e] = simam_fwd_elem<T>(f[e], c);
+      st_stream(yp + vi, pack<T>(f));
+    }
+  }
+  if (stats != nullptr && v0 == 0) {
+    stats[2 * plane] = mean;
+    stats[2 * plane + 1] = v;
+  }
+  if constexpr (CLUSTER > 1) cluster_sync_all();  // keep s_cta alive until every peer has read it
+}
+
+// NCHW resident backward: holds x and grad_y; one reduction of (R1, R2').
+template <typename T, int VPT, int THREADS, int CLUSTER, bool WARP_PLANE>
+__global__ void __launch_bounds__(THREADS)
+    simam_nchw_bwd_resident(const T* __restrict__ x, const T* __restrict__ gy,
+                            const float* __restrict__ stats, T* __restrict__ gx, int64_t planes,
+                            int nvec, float S) {
+  constexpr int VE = Vec16<T>::N;
+  __shared__ float s_warp[2 * 32];
+  __shared__ float s_cta[2];
+
+  int64_t plane;
+  int v0, vstride;
+  if constexpr (WARP_PLANE) {
+    plane = (int64_t)blockIdx.x * (THREADS / 32) + (threadIdx.x >> 5);
+    v0 = threadIdx.x & 31;
+    vstride = 32;
+    if (plane >= planes) return;
+  } else {
+    plane = blockIdx.x / CLUSTER;
+    const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+    v0 = rank * (THREADS * VPT) + threadIdx.x;
+    vstride = THREADS;
+  }
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + plane * nvec;
+  const uint4* gp = reinterpret_cast<const uint4*>(gy) + plane * nvec;
+  uint4* op = reinterpret_cast<uint4*>(gx) + plane * nvec;
+
+  uint4 dx[VPT], dg[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int vi = v0 + i * vstride;
+    bool ok = vi < nvec;
+    dx[i] = ok ? ld_stream(xp + vi) : make_uint4(0, 0, 0, 0);
+    dg[i] = ok ? ld_stream(gp + vi) : make_uint4(0, 0, 0, 0);
+  }
+  const float mean = __ldg(stats + 2 * plane), v = __ldg(stats + 2 * plane + 1);
+  const float inv4v = 1.f / (4.f * v);
+
+  float red[2] = {0.f, 0.f};  // R1 = sum a*d, R2' = sum a*t  (grad of zero-padded slots is 0 -> a = 0)
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    float fx[VE], fg[VE];
+    unpack<T>(dx[i], fx);
+    unpack<T>(dg[i], fg);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      float t = fx[e] - mean, dd = t * t;
+      float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+      float a = fg[e] * fx[e] * s * (1.f - s);
+      red[0] = fmaf(a, dd, red[0]);
+      red[1] = fmaf(a, t, red[1]);
+    }
+  }
+  if constexpr (WARP_PLANE) {
+    red[0] = warp_sum(red[0]);
+    red[1] = warp_sum(red[1]);
+  } else {
+    plane_reduce<THREADS, CLUSTER, 2>(red, s_warp, s_cta);
+  }
+  const float c1 = red[0] * inv4v / (v * (S - 1.f));  // R1 / (4 v^2 n)
+  const float c2 = 2.f / S * red[1] * inv4v;          // (2/HW) R2
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int vi = v0 + i * vstride;
+    if (vi < nvec) {
+      float fx[VE], fg[VE];
+      unpack<T>(dx[i], fx);
+      unpack<T>(dg[i], fg);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        float t = fx[e] - mean, dd = t * t;
+        float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+        float a = fg[e] * fx[e] * s * (1.f - s);
+        fx[e] = fmaf(fg[e], s, 2.f * t * fmaf(a, inv4v, -c1)) - c2;
+      }
+      st_stream(op + vi, pack<T>(fx));
+    }
+  }
+  if constexpr (CLUSTER > 1) cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// NLC resident: a cluster owns (image b, slab of CWV 16-byte vectors per row); per-channel reduce.
+// Thread t holds column vector t % CWV of rows  (rank*VPT + i) * (THREADS/CWV) + t / CWV.
+// ------------------------------------------------------------------------------------------------
+template <int VE, int CWV, int THREADS, int CLUSTER, int NQ>
+__device__ __forceinline__ void slab_reduce(float (&acc)[NQ][VE], float* s_red /*[WARPS][NQ*CW]*/,
+                                            float* s_part /*[NQ*CW]*/, float* s_fin /*[NQ*CW]*/) {
+  constexpr int CW = CWV * VE;  // channels in the slab
+  constexpr int WARPS = THREADS / 32;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int e = 0; e < VE; ++e)
+#pragma unroll
+      for (int o = 16; o >= CWV; o >>= 1) acc[q][e] += __shfl_xor_sync(0xffffffffu, acc[q][e], o);
+  if (lane < CWV) {
+#pragma unroll
+    for (int q = 0; q < NQ; ++q)
+#pragma unroll
+      for (int e = 0; e < VE; ++e) s_red[warp * (NQ * CW) + q * CW + lane * VE + e] = acc[q][e];
+  }
+  __syncthreads();
+  if (threadIdx.x < NQ * CW) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < WARPS; ++w) a += s_red[w * (NQ * CW) + threadIdx.x];
+    if constexpr (CLUSTER > 1) s_part[threadIdx.x] = a;
+    else s_fin[threadIdx.x] = a;
+  }
+  if constexpr (CLUSTER > 1) {
+    cluster_sync_all();
+    if (threadIdx.x < NQ * CW) {
+      float a = 0.f;
+#pragma unroll
+      for (int r = 0; r < CLUSTER; ++r) a += dsmem_ld_f32(&s_part[threadIdx.x], r);
+      s_fin[threadIdx.x] = a;
+    }
+  }
+  __syncthreads();
+  const int cv = threadIdx.x % CWV;
+#pragma unroll
+  for (int q = 0; q < NQ; ++q)
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc[q][e] = s_fin[q * CW + cv * VE + e];
+}
+
+template <typename T, int VPT, int CWV, int THREADS, int CLUSTER>
+__global__ void __launch_bounds__(THREADS)
+    simam_nlc_fwd_resident(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats,
+                           int L, int C, int slabs, float e_lambda) {
+  constexpr int VE = Vec16<T>::N;
+  constexpr int CW = CWV * VE;
+  constexpr int RPI = THREADS / CWV;  // rows per iteration
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_red[WARPS * CW];
+  __shared__ float s_part[2][CW];
+  __shared__ float s_fin[CW];
+
+  const int group = blockIdx.x / CLUSTER;  // (b, slab)
+  const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  const int b = group / slabs, slab = group % slabs;
+  const int cv = threadIdx.x % CWV;
+  const int r0 = rank * VPT * RPI + threadIdx.x / CWV;
+  const int cvec = C / VE;  // vectors per row
+  const int64_t base = (int64_t)b * L * cvec + slab * CWV + cv;
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + base;
+  uint4* yp = reinterpret_cast<uint4*>(y) + base;
+
+  uint4 d[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int r = r0 + i * RPI;
+    d[i] = (r < L) ? ld_stream(xp + (int64_t)r * cvec) : make_uint4(0, 0, 0, 0);
+  }
+  float acc[1][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    float f[VE];
+    unpack<T>(d[i], f);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc[0][e] += f[e];
+  }
+  slab_reduce<VE, CWV, THREADS, CLUSTER, 1>(acc, s_red, s_part[0], s_fin);
+  float mean[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) {
+    mean[e] = acc[0][e] / (float)L;
+    acc[0][e] = 0.f;
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    if (r0 + i * RPI < L) {
+      float f[VE];
+      unpack<T>(d[i], f);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        float t = f[e] - mean[e];
+        acc[0][e] = fmaf(t, t, acc[0][e]);
+      }
+    }
+  }
+  __syncthreads();  // s_fin is re-used by the second reduction
+  slab_reduce<VE, CWV, THREADS, CLUSTER, 1>(acc, s_red, s_part[1], s_fin);
+  FwdCoef c[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) {
+    float v = acc[0][e] / ((float)L - 1.f) + e_lambda;
+    c[e].mean = mean[e];
+    c[e].inv4v = 1.f / (4.f * v);
+    acc[0][e] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int r = r0 + i * RPI;
+    if (r < L) {
+      float f[VE];
+      unpack<T>(d[i], f);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) f[e] = simam_fwd_elem<T>(f[e], c[e]);
+      st_stream(yp + (int64_t)r * cvec, pack<T>(f));
+    }
+  }
+  if (stats != nullptr && rank == 0 && threadIdx.x < CWV) {
+    const int64_t p0 = (int64_t)b * C + slab * CW + cv * VE;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      stats[2 * (p0 + e)] = mean[e];
+      stats[2 * (p0 + e) + 1] = acc[0][e];
+    }
+  }
+  if constexpr (CLUSTER > 1) cluster_sync_all();
+}
+
+template <typename T, int VPT, int CWV, int THREADS, int CLUSTER>
+__global__ void __launch_bounds__(THREADS)
+    simam_nlc_bwd_resident(const T* __restrict__ x, const T* __restrict__ gy,
+                           const float* __restrict__ stats, T* __restrict__ gx, int L, int C,
+                           int slabs) {
+  constexpr int VE = Vec16<T>::N;
+  constexpr int CW = CWV * VE;
+  constexpr int RPI = THREADS / CWV;
+  constexpr int WARPS = THREADS / 32;
+  __shared__ float s_red[WARPS * 2 * CW];
+  __shared__ float s_part[2 * CW];
+  __shared__ float s_fin[2 * CW];
+
+  const int group = blockIdx.x / CLUSTER;
+  const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  const int b = group / slabs, slab = group % slabs;
+  const int cv = threadIdx.x % CWV;
+  const int r0 = rank * VPT * RPI + threadIdx.x / CWV;
+  const int cvec = C / VE;
+  const int64_t base = (int64_t)b * L * cvec + slab * CWV + cv;
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + base;
+  const uint4* gp = reinterpret_cast<const uint4*>(gy) + base;
+  uint4* op = reinterpret_cast<uint4*>(gx) + base;
+
+  uint4 dx[VPT], dg[VPT];
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int r = r0 + i * RPI;
+    bool ok = r < L;
+    dx[i] = ok ? ld_stream(xp + (int64_t)r * cvec) : make_uint4(0, 0, 0, 0);
+    dg[i] = ok ? ld_stream(gp + (int64_t)r * cvec) : make_uint4(0, 0, 0, 0);
+  }
+  float mean[VE], v[VE], inv4v[VE];
+  {
+    const int64_t p0 = (int64_t)b * C + slab * CW + cv * VE;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      mean[e] = __ldg(stats + 2 * (p0 + e));
+      v[e] = __ldg(stats + 2 * (p0 + e) + 1);
+      inv4v[e] = 1.f / (4.f * v[e]);
+    }
+  }
+  float acc[2][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    float fx[VE], fg[VE];
+    unpack<T>(dx[i], fx);
+    unpack<T>(dg[i], fg);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      float t = fx[e] - mean[e], dd = t * t;
+      float s = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
+      float a = fg[e] * fx[e] * s * (1.f - s);
+      acc[0][e] = fmaf(a, dd, acc[0][e]);
+      acc[1][e] = fmaf(a, t, acc[1][e]);
+    }
+  }
+  slab_reduce<VE, CWV, THREADS, CLUSTER, 2>(acc, s_red, s_part, s_fin);
+  float c1[VE], c2[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) {
+    c1[e] = acc[0][e] * inv4v[e] / (v[e] * ((float)L - 1.f));
+    c2[e] = 2.f / (float)L * acc[1][e] * inv4v[e];
+  }
+#pragma unroll
+  for (int i = 0; i < VPT; ++i) {
+    int r = r0 + i * RPI;
+    if (r < L) {
+      float fx[VE], fg[VE];
+      unpack<T>(dx[i], fx);
+      unpack<T>(dg[i], fg);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        float t = fx[e] - mean[e], dd = t * t;
+        float s = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
+        float a = fg[e] * fx[e] * s * (1.f - s);
+        fx[e] = fmaf(fg[e], s, 2.f * t * fmaf(a, inv4v[e], -c1[e])) - c2[e];
+      }
+      st_stream(op + (int64_t)r * cvec, pack<T>(fx));
+    }
+  }
+  if constexpr (CLUSTER > 1) cluster_sync_all();
+}
+
+// ------------------------------------------------------------------------------------------------
+// generic (any shape, any alignment): element (plane p, position i) at  base(p) + i * istride.
+//   NCHW: base = p*S, istride = 1, 256 threads per plane, one plane per CTA.
+//   NLC : blockDim = (32 channels, 8 row groups); a CTA covers 32 adjacent channels of one image.
+// ------------------------------------------------------------------------------------------------
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256)
+    simam_generic(const T* __restrict__ x, const T* __restrict__ gy, float* __restrict__ stats_out,
+                  const float* __restrict__ stats_in, T* __restrict__ out, int64_t S, int64_t C,
+                  int layout, float e_lambda) {
+  __shared__ float s_red[2][8][33];
+  // lane = which plane inside the CTA (NLC) / always 0 (NCHW); grp = which row group
+  int lane, grp, ngrp;
+  int64_t plane, base, istride;
+  bool active = true;
+  if (layout == CSB200_NCHW) {
+    lane = 0;
+    grp = threadIdx.x;
+    ngrp = 256;
+    plane = blockIdx.x;
+    base = plane * S;
+    istride = 1;
+  } else {
+    lane = threadIdx.x & 31;
+    grp = threadIdx.x >> 5;
+    ngrp = 8;
+    const int64_t cblocks = (C + 31) / 32;
+    const int64_t b = blockIdx.x / cblocks, c = (blockIdx.x % cblocks) * 32 + lane;
+    active = c < C;
+    plane = b * C + (active ? c : 0);
+    base = b * S * C + (active ? c : 0);
+    istride = C;
+  }
+  auto reduce2 = [&](float& a, float& b2) {
+    if (layout == CSB200_NCHW) {
+      a = warp_sum(a);
+      b2 = warp_sum(b2);
+      if ((threadIdx.x & 31) == 0) {
+        s_red[0][threadIdx.x >> 5][0] = a;
+        s_red[1][threadIdx.x >> 5][0] = b2;
+      }
+      __syncthreads();
+      a = b2 = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        a += s_red[0][w][0];
+        b2 += s_red[1][w][0];
+      }
+    } else {
+      s_red[0][grp][lane] = a;
+      s_red[1][grp][lane] = b2;
+      __syncthreads();
+      a = b2 = 0.f;
+      for (int w = 0; w < 8; ++w) {
+        a += s_red[0][w][lane];
+        b2 += s_red[1][w][lane];
+      }
+    }
+    __syncthreads();
+  };
+  const float Sf = (float)S;
+  float mean, v;
+  if constexpr (!BWD) {
+    float sum = 0.f, dummy = 0.f;
+    if (active)
+      for (int64_t i = grp; i < S; i += ngrp) sum += to_f32(x[base + i * istride]);
+    reduce2(sum, dummy);
+    mean = sum / Sf;
+    float m2 = 0.f;
+    if (active)
+      for (int64_t i = grp; i < S; i += ngrp) {
+        float t = to_f32(x[base + i * istride]) - mean;
+        m2 = fmaf(t, t, m2);
+      }
+    reduce2(m2, dummy);
+    v = m2 / (Sf - 1.f) + e_lambda;
+    FwdCoef c{mean, 1.f / (4.f * v)};
+    if (active) {
+      for (int64_t i = grp; i < S; i += ngrp)
+        out[base + i * istride] = from_f32<T>(simam_fwd_elem<T>(to_f32(x[base + i * istride]), c));
+      if (stats_out != nullptr && grp == 0) {
+        stats_out[2 * plane] = mean;
+        stats_out[2 * plane + 1] = v;
+      }
+    }
+  } else {
+    mean = stats_in[2 * plane];
+    v = stats_in[2 * plane + 1];
+    const float inv4v = 1.f / (4.f * v);
+    float r1 = 0.f, r2 = 0.f;
+    if (active)
+      for (int64_t i = grp; i < S; i += ngrp) {
+        float xv = to_f32(x[base + i * istride]), g = to_f32(gy[base + i * istride]);
+        float t = xv - mean, dd = t * t;
+        float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+        float a = g * xv * s * (1.f - s);
+        r1 = fmaf(a, dd, r1);
+        r2 = fmaf(a, t, r2);
+      }
+    reduce2(r1, r2);
+    const float c1 = r1 * inv4v / (v * (Sf - 1.f)), c2 = 2.f / Sf * r2 * inv4v;
+    if (active)
+      for (int64_t i = grp; i < S; i += ngrp) {
+        float xv = to_f32(x[base + i * istride]), g = to_f32(gy[base + i * istride]);
+        float t = xv - mean, dd = t * t;
+        float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+        float a = g * xv * s * (1.f - s);
+        out[base + i * istride] = from_f32<T>(fmaf(g, s, 2.f * t * fmaf(a, inv4v, -c1)) - c2);
+      }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// launch helpers
+// ------------------------------------------------------------------------------------------------
+template <typename K, typename... Args>
+int launch(K kernel, int64_t grid, int threads, int cluster, cudaStream_t st, const char* name,
+           Args... args) {
+  if (grid <= 0) return CSB200_OK;
+  if (grid > 0x7fffffffLL) return fail(CSB200_ERR_INVALID, "%s: grid too large", name);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(threads);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cluster;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = cluster > 1 ? 1 : 0;
+  cudaError_t e = cudaLaunchKernelEx(&cfg, kernel, args...);
+  if (e != cudaSuccess) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return fail(CSB200_ERR_CUDA, "%s: %s", name, cudaGetErrorString(e));
+  }
+  return check_launch(name);
+}
+
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+// NCHW resident dispatch.  Returns -1 if no resident configuration fits.
+template <typename T, bool BWD>
+int nchw_resident(const T* x, const T* gy, float* stats_out, const float* stats_in, T* out,
+                  int64_t planes, int64_t S, float e_lambda, cudaStream_t st) {
+  constexpr int VE = Vec16<T>::N;
+  if (S % VE != 0 || !aligned16(x) || !aligned16(out) || (BWD && !aligned16(gy))) return -1;
+  const int64_t nvec64 = S / VE;
+  if (nvec64 > 32768) return -1;
+  const int nvec = (int)nvec64;
+  const float Sf = (float)S;
+#define CSB_NCHW(VPT, THREADS, CLUSTER, WARP)                                                     \
+  do {                                                                                            \
+    const int64_t grid = (WARP) ? (planes + (THREADS) / 32 - 1) / ((THREADS) / 32)                \
+                                : planes * (CLUSTER);                                             \
+    if constexpr (BWD)                                                                            \
+      return launch(simam_nchw_bwd_resident<T, VPT, THREADS, CLUSTER, WARP>, grid, THREADS,       \
+                    CLUSTER, st, "simam_nchw_bwd_resident", x, gy, stats_in, out, planes, nvec,   \
+                    Sf);                                                                          \
+    else                                                                                          \
+      return launch(simam_nchw_fwd_resident<T, VPT, THREADS, CLUSTER, WARP>, grid, THREADS,       \
+                    CLUSTER, st, "simam_nchw_fwd_resident", x, out, stats_out, planes, nvec, Sf,  \
+                    e_lambda);                                                                    \
+  } while (0)
+  if constexpr (!BWD) {
+    if (nvec <= 32) CSB_NCHW(1, 256, 1, true);
+    if (nvec <= 64) CSB_NCHW(2, 256, 1, true);
+    if (nvec <= 128) CSB_NCHW(4, 256, 1, true);
+    if (nvec <= 256) CSB_NCHW(8, 256, 1, true);
+    if (nvec <= 512) CSB_NCHW(4, 128, 1, false);
+    if (nvec <= 1024) CSB_NCHW(4, 256, 1, false);
+    if (nvec <= 2048) CSB_NCHW(8, 256, 1, false);
+    if (nvec <= 4096) CSB_NCHW(8, 512, 1, false);
+    if (nvec <= 8192) CSB_NCHW(8, 512, 2, false);
+    if (nvec <= 16384) CSB_NCHW(8, 512, 4, false);
+    CSB_NCHW(8, 512, 8, false);
+  } else {
+    if (nvec <= 32) CSB_NCHW(1, 256, 1, true);
+    if (nvec <= 64) CSB_NCHW(2, 256, 1, true);
+    if (nvec <= 128) CSB_NCHW(4, 256, 1, true);
+    if (nvec <= 512) CSB_NCHW(4, 128, 1, false);
+    if (nvec <= 1024) CSB_NCHW(4, 256, 1, false);
+    if (nvec <= 2048) CSB_NCHW(4, 512, 1, false);
+    if (nvec <= 4096) CSB_NCHW(4, 512, 2, false);
+    if (nvec <= 8192) CSB_NCHW(4, 512, 4, false);
+    if (nvec <= 16384) CSB_NCHW(4, 512, 8, false);
+    CSB_NCHW(8, 512, 8, false);
+  }
+#undef CSB_NCHW
+}
+
+// NLC resident dispatch: widest slab (128/64/32 B per row) whose L rows fit a cluster of <= 8 CTAs.
+template <typename T, bool BWD>
+int nlc_resident(const T* x, const T* gy, float* stats_out, const float* stats_in, T* out,
+                 int64_t B, int64_t C, int64_t L, float e_lambda, cudaStream_t st) {
+  constexpr int VE = Vec16<T>::N;
+  constexpr int THREADS = 512;
+  if (C % VE != 0 || !aligned16(x) || !aligned16(out) || (BWD && !aligned16(gy))) return -1;
+  if (L > 0x7fffffff / 64 || B * C > 0x7fffffff) return -1;
+  const int cvec = (int)(C / VE);
+#define CSB_NLC(VPT, CWV, CLUSTER)                                                                    \
+  do {                                                                                            \
+    const int slabs = cvec / (CWV);                                                               \
+    const int64_t grid = B * slabs * (CLUSTER);                                                   \
+    if constexpr (BWD)                                                                            \
+      return launch(simam_nlc_bwd_resident<T, VPT, CWV, THREADS, CLUSTER>, grid, THREADS,         \
+                    CLUSTER, st, "simam_nlc_bwd_resident", x, gy, stats_in, out, (int)L, (int)C,  \
+                    slabs);                                                                       \
+    else                                                                                          \
+      return launch(simam_nlc_fwd_resident<T, VPT, CWV, THREADS, CLUSTER>, grid, THREADS,         \
+                    CLUSTER, st, "simam_nlc_fwd_resident", x, out, stats_out, (int)L, (int)C,     \
+                    slabs, e_lambda);                                                             \
+  } while (0)
+#define CSB_NLC_TRY(VPT, CWV)                                                                     \
+  if (cvec % (CWV) == 0) {                                                                        \
+    const int64_t rows1 = (int64_t)(VPT) * (THREADS / (CWV)); /* rows one CTA can hold */         \
+    if (L <= rows1) CSB_NLC(VPT, CWV, 1);                                                         \
+    if (L <= 2 * rows1) CSB_NLC(VPT, CWV, 2);                                                     \
+    if (L <= 4 * rows1) CSB_NLC(VPT, CWV, 4);                                                     \
+    if (L <= 8 * rows1) CSB_NLC(VPT, CWV, 8);                                                     \
+  }
+  if constexpr (BWD) {
+    CSB_NLC_TRY(4, 8)
+    CSB_NLC_TRY(4, 4)
+    CSB_NLC_TRY(4, 2)
+    CSB_NLC_TRY(8, 2)
+  } else {
+    CSB_NLC_TRY(8, 8)
+    CSB_NLC_TRY(8, 4)
+    CSB_NLC_TRY(8, 2)
+  }
+#undef CSB_NLC_TRY
+#undef CSB_NLC
+  return -1;
+}
+
+template <typename T, bool BWD>
+int simam_dispatch(const void* x_, const void* gy_, float* stats_out, const float* stats_in,
+                   void* out_, int64_t B, int64_t C, int64_t S, int layout, float e_lambda,
+                   cudaStream_t st) {
+  const T* x = static_cast<const T*>(x_);
+  const T* gy = static_cast<const T*>(gy_);
+  T* out = static_cast<T*>(out_);
+  int rc = (layout == CSB200_NCHW)
+               ? nchw_resident<T, BWD>(x, gy, stats_out, stats_in, out, B * C, S, e_lambda, st)
+               : nlc_resident<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, st);
+  if (rc >= 0) return rc;
+  const int64_t grid = (layout == CSB200_NCHW) ? B * C : B * ((C + 31) / 32);
+  return launch(simam_generic<T, BWD>, grid, 256, 1, st, "simam_generic", x, gy, stats_out,
+                stats_in, out, S, C, layout, e_lambda);
+}
+
+int simam_check(const void* x, const void* out, int64_t B, int64_t C, int64_t S, int layout,
+                int dtype) {
+  if (B < 0 || C < 0 || S < 0) return fail(CSB200_ERR_INVALID, "simam: negative size");
+  if (layout != CSB200_NCHW && layout != CSB200_NLC)
+    return fail(CSB200_ERR_INVALID, "simam: unknown layout %d", layout);
+  if (dtype != CSB200_F32 && dtype != CSB200_BF16)
+    return fail(CSB200_ERR_INVALID, "simam: unknown dtype %d", dtype);
+  if (B * C * S > 0 && (x == nullptr || out == nullptr))
+    return fail(CSB200_ERR_INVALID, "simam: null pointer");
+  return CSB200_OK;
+}
+
+}  // namespace
+}  // namespace csb200
+
+using namespace csb200;
+
+extern "C" int csb200_simam_fwd(const void* x, void* y, float* stats, int64_t batch,
+                                int64_t channels, int64_t spatial, int layout, int dtype,
+                                float e_lambda, void* stream) {
+  int rc = simam_check(x, y, batch, channels, spatial, layout, dtype);
+  if (rc != CSB200_OK) return rc;
+  if (batch * channels * spatial == 0) return CSB200_OK;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == CSB200_F32)
+    return simam_dispatch<float, false>(x, nullptr, stats, nullptr, y, batch, channels, spatial,
+                                        layout, e_lambda, st);
+  return simam_dispatch<__nv_bfloat16, false>(x, nullptr, stats, nullptr, y, batch, channels,
+                                              spatial, layout, e_lambda, st);
+}
+
+extern "C" int csb200_simam_bwd(const void* x, const void* grad_y, const float* stats,
+                                void* grad_x, int64_t batch, int64_t channels, int64_t spatial,
+                                int layout, int dtype, float e_lambda, void* stream) {
+  int rc = simam_check(x, grad_x, batch, channels, spatial, layout, dtype);
+  if (rc != CSB200_OK) return rc;
+  if (batch * channels * spatial == 0) return CSB200_OK;
+  if (grad_y == nullptr || stats == nullptr)
+    return fail(CSB200_ERR_INVALID, "simam_bwd: grad_y and stats are required");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (dtype == CSB200_F32)
+    return simam_dispatch<float, true>(x, grad_y, nullptr, stats, grad_x, batch, channels, spatial,
+                                       layout, e_lambda, st);
+  return simam_dispatch<__nv_bfloat16, true>(x, grad_y, nullptr, stats, grad_x, batch, channels,
+                                             spatial, layout, e_lambda, st);
+}

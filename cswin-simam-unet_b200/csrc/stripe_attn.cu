@@ -1,0 +1,156 @@
+// C-ABI entry points of the stripe attention (include/csb200.h): validation, engine choice,
+// workspace carving.  The arithmetic lives in stripe_attn_simt.cu / stripe_attn_tc.cu.
+
+#include "stripe_attn.cuh"
+
+namespace csb200 {
+
+thread_local char g_err[512] = "";
+std::atomic<uint64_t> g_launches{0};
+
+namespace {
+
+size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// Mirrors the failures of the reference: a resolution that the stripe does not divide raises
+// RuntimeError from view() in img2windows (C:204); here it is CSB200_ERR_INVALID + message.
+int make_geom(const csb200_stripe_desc* d, bool backward, StripeGeom* g) {
+  if (d == nullptr) return fail(CSB200_ERR_INVALID, "stripe_attn: null descriptor");
+  if (d->dtype != CSB200_F32 && d->dtype != CSB200_BF16)
+    return fail(CSB200_ERR_INVALID, "stripe_attn: unknown dtype %d", d->dtype);
+  if (d->batch < 0 || d->height <= 0 || d->width <= 0 || d->h_sp <= 0 || d->w_sp <= 0 ||
+      d->heads <= 0)
+    return fail(CSB200_ERR_INVALID, "stripe_attn: non-positive size");
+  if (d->height % d->h_sp != 0 || d->width % d->w_sp != 0)
+    return fail(CSB200_ERR_INVALID,
+                "stripe_attn: token grid %dx%d is not divisible by the stripe %dx%d "
+                "(the reference raises from view() in img2windows for the same input)",
+                d->height, d->width, d->h_sp, d->w_sp);
+  if (d->head_dim != 32)
+    return fail(CSB200_ERR_UNSUPPORTED, "stripe_attn: head_dim %d (only 32 is built)",
+                d->head_dim);
+  if ((int64_t)d->height * d->width > 0x7fffffff / 4)
+    return fail(CSB200_ERR_INVALID, "stripe_attn: token grid too large");
+  const int64_t strides[] = {d->q_sb, d->q_sl, d->k_sb, d->k_sl, d->v_sb, d->v_sl, d->o_sb, d->o_sl};
+  for (int64_t s : strides)
+    if (s % 8 != 0 || s < 0)
+      return fail(CSB200_ERR_INVALID, "stripe_attn: strides must be non-negative multiples of 8");
+  if (backward) {
+    const int64_t gs[] = {d->dq_sb, d->dq_sl, d->dk_sb, d->dk_sl, d->dv_sb, d->dv_sl};
+    for (int64_t s : gs)
+      if (s % 8 != 0 || s < 0)
+        return fail(CSB200_ERR_INVALID, "stripe_attn: gradient strides must be multiples of 8");
+  }
+  g->B = d->batch;
+  g->H = d->height;
+  g->W = d->width;
+  g->L = d->height * d->width;
+  g->hs = d->h_sp;
+  g->ws = d->w_sp;
+  g->N = d->h_sp * d->w_sp;
+  g->nwy = d->height / d->h_sp;
+  g->nwx = d->width / d->w_sp;
+  g->heads = d->heads;
+  g->scale = d->scale;
+  g->q_sb = d->q_sb; g->q_sl = d->q_sl;
+  g->k_sb = d->k_sb; g->k_sl = d->k_sl;
+  g->v_sb = d->v_sb; g->v_sl = d->v_sl;
+  g->o_sb = d->o_sb; g->o_sl = d->o_sl;
+  g->dq_sb = d->dq_sb; g->dq_sl = d->dq_sl;
+  g->dk_sb = d->dk_sb; g->dk_sl = d->dk_sl;
+  g->dv_sb = d->dv_sb; g->dv_sl = d->dv_sl;
+  return CSB200_OK;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+int pick_engine(const csb200_stripe_desc* d, const StripeGeom& g, bool backward) {
+  const bool tc_ok = backward ? tc_bwd_supported(g, d->dtype) : tc_fwd_supported(g, d->dtype);
+  switch (d->engine) {
+    case CSB200_ENGINE_AUTO:
+      return tc_ok ? CSB200_ENGINE_TCGEN05 : CSB200_ENGINE_SIMT;
+    case CSB200_ENGINE_SIMT:
+      return CSB200_ENGINE_SIMT;
+    case CSB200_ENGINE_TCGEN05:
+      if (!tc_ok)
+        return -fail(CSB200_ERR_UNSUPPORTED,
+                     "stripe_attn: the tcgen05 engine does not tile this shape (N=%d, dtype=%d)",
+                     g.N, d->dtype);
+      return CSB200_ENGINE_TCGEN05;
+    default:
+      return -fail(CSB200_ERR_INVALID, "stripe_attn: unknown engine %d", d->engine);
+  }
+}
+
+}  // namespace
+}  // namespace csb200
+
+using namespace csb200;
+
+extern "C" int csb200_abi_version(void) { return CSB200_ABI_VERSION; }
+extern "C" const char* csb200_last_error_string(void) { return g_err; }
+extern "C" uint64_t csb200_launch_count(void) { return g_launches.load(); }
+
+extern "C" int csb200_stripe_attn_engine(const csb200_stripe_desc* d, int backward) {
+  StripeGeom g;
+  int rc = make_geom(d, backward != 0, &g);
+  if (rc != CSB200_OK) return -rc;
+  return pick_engine(d, g, backward != 0);
+}
+
+extern "C" int csb200_stripe_attn_fwd(const csb200_stripe_desc* d, const void* q, const void* k,
+                                      const void* v, const float* lepe_w, const float* lepe_b,
+                                      void* out, float* lse, void* stream) {
+  StripeGeom g;
+  int rc = make_geom(d, false, &g);
+  if (rc != CSB200_OK) return rc;
+  if (g.B == 0) return CSB200_OK;
+  if (!q || !k || !v || !lepe_w || !lepe_b || !out || !lse)
+    return fail(CSB200_ERR_INVALID, "stripe_attn_fwd: null pointer");
+  if (!aligned(q, 16) || !aligned(k, 16) || !aligned(v, 16) || !aligned(out, 16))
+    return fail(CSB200_ERR_INVALID, "stripe_attn_fwd: q/k/v/out must be 16-byte aligned");
+  const int engine = pick_engine(d, g, false);
+  if (engine < 0) return -engine;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (engine == CSB200_ENGINE_TCGEN05) return tc_fwd(g, q, k, v, lepe_w, lepe_b, out, lse, st);
+  return simt_fwd(g, d->dtype, q, k, v, lepe_w, lepe_b, out, lse, st);
+}
+
+extern "C" size_t csb200_stripe_attn_bwd_workspace_bytes(const csb200_stripe_desc* d) {
+  StripeGeom g;
+  if (make_geom(d, true, &g) != CSB200_OK) return 0;
+  const size_t delta = align_up((size_t)g.B * g.heads * g.L * sizeof(float), 256);
+  const size_t partial = align_up((size_t)wgrad_blocks(g) * g.heads * 32 * 10 * sizeof(float), 256);
+  return delta + partial;
+}
+
+extern "C" int csb200_stripe_attn_bwd(const csb200_stripe_desc* d, const void* q, const void* k,
+                                      const void* v, const float* lepe_w, const float* lepe_b,
+                                      const void* out, const void* grad_out, const float* lse,
+                                      void* dq, void* dk, void* dv, float* grad_lepe_w,
+                                      float* grad_lepe_b, void* workspace, size_t workspace_bytes,
+                                      void* stream) {
+  StripeGeom g;
+  int rc = make_geom(d, true, &g);
+  if (rc != CSB200_OK) return rc;
+  if (g.B == 0) return CSB200_OK;
+  if (!q || !k || !v || !lepe_w || !lepe_b || !out || !grad_out || !lse || !dq || !dk || !dv ||
+      !grad_lepe_w || !grad_lepe_b || !workspace)
+    return fail(CSB200_ERR_INVALID, "stripe_attn_bwd: null pointer");
+  const void* ptrs[] = {q, k, v, out, grad_out, dq, dk, dv, workspace};
+  for (const void* p : ptrs)
+    if (!aligned(p, 16))
+      return fail(CSB200_ERR_INVALID, "stripe_attn_bwd: tensors must be 16-byte aligned");
+  const size_t need = csb200_stripe_attn_bwd_workspace_bytes(d);
+  if (workspace_bytes < need)
+    return fail(CSB200_ERR_WORKSPACE, "stripe_attn_bwd: workspace %zu < %zu bytes",
+                workspace_bytes, need);
+  const int engine = pick_engine(d, g, true);
+  if (engine < 0) return -engine;
+  float* delta = static_cast<float*>(workspace);
+  float* partial = reinterpret_cast<float*>(
+      static_cast<char*>(workspace) + align_up((size_t)g.B * g.heads * g.L * sizeof(float), 256));
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return simt_bwd(g, d->dtype, q, k, v, lepe_w, lepe_b, out, grad_out, lse, dq, dk, dv,
+                  grad_lepe_w, grad_lepe_b, delta, partial, st);
+}

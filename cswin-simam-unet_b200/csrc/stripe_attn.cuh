@@ -1,0 +1,37 @@
+// Internal interface between the C-ABI entry points (stripe_attn.cu) and the attention engines.
+#pragma once
+#include "common.cuh"
+
+namespace csb200 {
+
+// Validated, kernel-friendly copy of csb200_stripe_desc (passed by value to the kernels).
+struct StripeGeom {
+  int B, H, W, L;      // batch, token grid, L = H*W
+  int hs, ws, N;       // stripe extent, N = hs*ws tokens per stripe
+  int nwy, nwx;        // stripes per image along y / x
+  int heads;           // heads of this branch (head_dim is 32)
+  float scale;
+  int64_t q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl;
+  int64_t dq_sb, dq_sl, dk_sb, dk_sl, dv_sb, dv_sl;
+};
+
+// ---- CUDA-core engine (stripe_attn_simt.cu) ---------------------------------------------------
+int simt_fwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,
+             const float* lepe_w, const float* lepe_b, void* out, float* lse, cudaStream_t st);
+int simt_bwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,
+             const float* lepe_w, const float* lepe_b, const void* out, const void* gout,
+             const float* lse, void* dq, void* dk, void* dv, float* gw, float* gb, float* delta,
+             float* partial, cudaStream_t st);
+// depthwise-3x3 weight / bias gradient (shared by both engines); partial: [wgrad_blocks][C'][10]
+int wgrad_blocks(const StripeGeom& g);
+template <typename T>
+int lepe_wgrad(const StripeGeom& g, const T* v, const T* gout, float* gw, float* gb,
+               float* partial, cudaStream_t st);
+
+// ---- tcgen05 engine (stripe_attn_tc.cu) -------------------------------------------------------
+bool tc_fwd_supported(const StripeGeom& g, int dtype);
+bool tc_bwd_supported(const StripeGeom& g, int dtype);
+int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
+           const float* lepe_b, void* out, float* lse, cudaStream_t st);
+
+}  // namespace csb200

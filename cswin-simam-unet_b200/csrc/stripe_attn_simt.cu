@@ -1,0 +1,534 @@
+// Cross-shaped stripe attention with LePE — CUDA-core engine (fp32 accumulate, any stripe shape).
+//
+// Replaces the body of LePEAttention.forward (reference C:271-298).  The stripe partition
+// (img2windows / windows2img, C:199-217; im2cswin, C:248-254; get_lepe, C:256-269) is pure index
+// arithmetic here: q/k/v are read in place from the token-major qkv buffer and the result is written
+// in place at the branch's channel offset, so none of the reference's 12 full-tensor copies exist.
+//
+//   token l = y*W + x  ->  stripe (y / h_sp, x / w_sp), in-stripe index n = (y % h_sp)*w_sp + x % w_sp
+//
+// This engine is the fp32 parity anchor (<= 1e-5 relative vs the reference) and the fallback for
+// stripe lengths the tcgen05 engine does not tile (N = 49, 56, 98 at 224^2).  One thread owns one
+// query (or key) row of 32 channels in registers; the other operand streams through shared memory
+// in 64-row chunks read as warp-wide broadcasts; softmax is the online (running max / sum) form.
+// Backward recomputes the probabilities from the saved log-sum-exp (no N x N tensor ever exists).
+
+#include "stripe_attn.cuh"
+
+namespace csb200 {
+namespace {
+
+constexpr int HD = 32;      // head_dim (dim // num_heads is 32 in every stage)
+constexpr int ROWS = 128;   // query (key) rows per CTA == threads per CTA
+constexpr int CHUNK = 64;   // rows of the streamed operand per shared-memory chunk
+
+template <typename T>
+struct Exp {
+  static __device__ __forceinline__ float f(float x) { return expf(x); }  // fp32: full precision
+};
+template <>
+struct Exp<__nv_bfloat16> {
+  static __device__ __forceinline__ float f(float x) { return __expf(x); }
+};
+
+// 4 consecutive channels of one token row -> fp32
+template <typename T>
+__device__ __forceinline__ float4 ld4(const T* p);
+template <>
+__device__ __forceinline__ float4 ld4<float>(const float* p) {
+  return __ldg(reinterpret_cast<const float4*>(p));
+}
+template <>
+__device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+template <typename T>
+__device__ __forceinline__ void st4(T* p, float4 v);
+template <>
+__device__ __forceinline__ void st4<float>(float* p, float4 v) {
+  *reinterpret_cast<float4*>(p) = v;
+}
+template <>
+__device__ __forceinline__ void st4<__nv_bfloat16>(__nv_bfloat16* p, float4 v) {
+  *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+}
+
+template <typename T>
+__device__ __forceinline__ void load_row(const T* p, float (&r)[HD]) {
+#pragma unroll
+  for (int i = 0; i < HD / 4; ++i) {
+    float4 f = ld4<T>(p + 4 * i);
+    r[4 * i] = f.x;
+    r[4 * i + 1] = f.y;
+    r[4 * i + 2] = f.z;
+    r[4 * i + 3] = f.w;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store_row(T* p, const float (&r)[HD]) {
+#pragma unroll
+  for (int i = 0; i < HD / 4; ++i)
+    st4<T>(p + 4 * i, make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]));
+}
+
+// Which (batch, stripe, head, row tile) a CTA works on, and the token index of in-stripe row n.
+struct Work {
+  int b, head, wy, wx, tile;
+};
+__device__ __forceinline__ Work decode_work(const StripeGeom& g, int tiles) {
+  int id = blockIdx.x;
+  Work w;
+  w.tile = id % tiles;
+  id /= tiles;
+  w.head = id % g.heads;
+  id /= g.heads;
+  w.wx = id % g.nwx;
+  id /= g.nwx;
+  w.wy = id % g.nwy;
+  w.b = id / g.nwy;
+  return w;
+}
+__device__ __forceinline__ int token_of(const StripeGeom& g, const Work& w, int n) {
+  return (w.wy * g.hs + n / g.ws) * g.W + w.wx * g.ws + n % g.ws;
+}
+
+// Cooperative load of `cnt` stripe rows [n0, n0+cnt) of one operand into smem (fp32, [CHUNK][HD]).
+template <typename T>
+__device__ __forceinline__ void load_chunk(float* dst, const T* base, int64_t sl,
+                                           const StripeGeom& g, const Work& w, int n0, int cnt,
+                                           float mul) {
+  for (int idx = threadIdx.x; idx < cnt * (HD / 4); idx += ROWS) {
+    int r = idx / (HD / 4), c4 = idx % (HD / 4);
+    float4 f = ld4<T>(base + (int64_t)token_of(g, w, n0 + r) * sl + 4 * c4);
+    f.x *= mul; f.y *= mul; f.z *= mul; f.w *= mul;
+    *reinterpret_cast<float4*>(dst + r * HD + 4 * c4) = f;
+  }
+}
+
+__device__ __forceinline__ float dot_smem(const float (&a)[HD], const float* row) {
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < HD / 4; ++i) {
+    float4 k = *reinterpret_cast<const float4*>(row + 4 * i);  // warp-wide broadcast
+    s = fmaf(a[4 * i], k.x, s);
+    s = fmaf(a[4 * i + 1], k.y, s);
+    s = fmaf(a[4 * i + 2], k.z, s);
+    s = fmaf(a[4 * i + 3], k.w, s);
+  }
+  return s;
+}
+__device__ __forceinline__ void axpy_smem(float (&acc)[HD], float a, const float* row) {
+#pragma unroll
+  for (int i = 0; i < HD / 4; ++i) {
+    float4 v = *reinterpret_cast<const float4*>(row + 4 * i);
+    acc[4 * i] = fmaf(a, v.x, acc[4 * i]);
+    acc[4 * i + 1] = fmaf(a, v.y, acc[4 * i + 1]);
+    acc[4 * i + 2] = fmaf(a, v.z, acc[4 * i + 2]);
+    acc[4 * i + 3] = fmaf(a, v.w, acc[4 * i + 3]);
+  }
+}
+
+// LePE taps for the 32 channels of one head: s_w[tap][c] (tap = ky*3+kx), s_b[c]
+__device__ __forceinline__ void load_lepe_weights(float* s_w, float* s_b, const float* lepe_w,
+                                                  const float* lepe_b, int head) {
+  for (int i = threadIdx.x; i < 9 * HD; i += ROWS) {
+    int tap = i / HD, c = i % HD;
+    s_w[i] = __ldg(lepe_w + (head * HD + c) * 9 + tap);
+  }
+  if (threadIdx.x < HD && s_b != nullptr)
+    s_b[threadIdx.x] = lepe_b ? __ldg(lepe_b + head * HD + threadIdx.x) : 0.f;
+}
+
+// acc[c] += sum over the 3x3 neighbourhood (zero padding at the STRIPE border, C:244,263-265) of
+// w[c][tap] * src[neighbour][c].  FLIP selects the transposed stencil used for grad_v.
+template <typename T, bool FLIP>
+__device__ __forceinline__ void lepe_stencil(float (&acc)[HD], const T* src_bh, int64_t sl,
+                                             const StripeGeom& g, const Work& w, int n,
+                                             const float* s_w) {
+  const int yy = n / g.ws, xx = n % g.ws;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    const int ny = FLIP ? yy - ky + 1 : yy + ky - 1;
+    if (ny < 0 || ny >= g.hs) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      const int nx = FLIP ? xx - kx + 1 : xx + kx - 1;
+      if (nx < 0 || nx >= g.ws) continue;
+      const T* p = src_bh + (int64_t)token_of(g, w, ny * g.ws + nx) * sl;
+      const float* wt = s_w + (ky * 3 + kx) * HD;
+#pragma unroll
+      for (int i = 0; i < HD / 4; ++i) {
+        float4 f = ld4<T>(p + 4 * i);
+        acc[4 * i] = fmaf(wt[4 * i], f.x, acc[4 * i]);
+        acc[4 * i + 1] = fmaf(wt[4 * i + 1], f.y, acc[4 * i + 1]);
+        acc[4 * i + 2] = fmaf(wt[4 * i + 2], f.z, acc[4 * i + 2]);
+        acc[4 * i + 3] = fmaf(wt[4 * i + 3], f.w, acc[4 * i + 3]);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward: out = softmax(scale q k^T) v + lepe(v),  lse = log sum exp (scaled scores)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ROWS)
+    stripe_fwd_simt(StripeGeom g, const T* __restrict__ q, const T* __restrict__ k,
+                    const T* __restrict__ v, const float* __restrict__ lepe_w,
+                    const float* __restrict__ lepe_b, T* __restrict__ out,
+                    float* __restrict__ lse, int tiles) {
+  __shared__ __align__(16) float s_k[CHUNK * HD];
+  __shared__ __align__(16) float s_v[CHUNK * HD];
+  __shared__ __align__(16) float s_w[9 * HD];
+  __shared__ float s_b[HD];
+  const Work w = decode_work(g, tiles);
+  const int n = w.tile * ROWS + threadIdx.x;
+  const bool valid = n < g.N;
+  const int co = w.head * HD;
+  const T* qb = q + (int64_t)w.b * g.q_sb + co;
+  const T* kb = k + (int64_t)w.b * g.k_sb + co;
+  const T* vb = v + (int64_t)w.b * g.v_sb + co;
+
+  load_lepe_weights(s_w, s_b, lepe_w, lepe_b, w.head);
+  const int tok = valid ? token_of(g, w, n) : 0;
+  float qs[HD], acc[HD];
+  if (valid) {
+    load_row<T>(qb + (int64_t)tok * g.q_sl, qs);
+#pragma unroll
+    for (int c = 0; c < HD; ++c) qs[c] *= g.scale;  // q = q * scale, C:287
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; ++c) qs[c] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < HD; ++c) acc[c] = 0.f;
+  float m = -INFINITY, l = 0.f;
+
+  for (int j0 = 0; j0 < g.N; j0 += CHUNK) {
+    const int cnt = min(CHUNK, g.N - j0);
+    __syncthreads();
+    load_chunk<T>(s_k, kb, g.k_sl, g, w, j0, cnt, 1.f);
+    load_chunk<T>(s_v, vb, g.v_sl, g, w, j0, cnt, 1.f);
+    __syncthreads();
+    for (int j = 0; j < cnt; j += 8) {
+      float s[8];
+      float mx = m;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        s[u] = (j + u < cnt) ? dot_smem(qs, s_k + (j + u) * HD) : -INFINITY;
+        mx = fmaxf(mx, s[u]);
+      }
+      const float corr = Exp<T>::f(m - mx);  // exp(-inf) = 0 on the first group
+      l *= corr;
+#pragma unroll
+      for (int c = 0; c < HD; ++c) acc[c] *= corr;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (j + u < cnt) {
+          const float p = Exp<T>::f(s[u] - mx);
+          l += p;
+          axpy_smem(acc, p, s_v + (j + u) * HD);
+        }
+      }
+      m = mx;
+    }
+  }
+  if (!valid) return;
+  const float inv_l = 1.f / l;
+  float o[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) o[c] = s_b[c];
+  lepe_stencil<T, false>(o, vb, g.v_sl, g, w, n, s_w);
+#pragma unroll
+  for (int c = 0; c < HD; ++c) o[c] = fmaf(acc[c], inv_l, o[c]);  // attn @ v + lepe, C:292
+  store_row<T>(out + (int64_t)w.b * g.o_sb + (int64_t)tok * g.o_sl + co, o);
+  lse[((int64_t)w.b * g.heads + w.head) * g.L + tok] = m + logf(l);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, step 1: delta[b,h,l] = sum_c grad_out * (out - lepe)   (= sum_j P_ij dP_ij)
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ROWS)
+    stripe_bwd_delta_simt(StripeGeom g, const T* __restrict__ v, const float* __restrict__ lepe_w,
+                          const float* __restrict__ lepe_b, const T* __restrict__ out,
+                          const T* __restrict__ gout, float* __restrict__ delta, int tiles) {
+  __shared__ __align__(16) float s_w[9 * HD];
+  __shared__ float s_b[HD];
+  const Work w = decode_work(g, tiles);
+  const int n = w.tile * ROWS + threadIdx.x;
+  const int co = w.head * HD;
+  load_lepe_weights(s_w, s_b, lepe_w, lepe_b, w.head);
+  __syncthreads();
+  if (n >= g.N) return;
+  const int tok = token_of(g, w, n);
+  float lp[HD], o[HD], go[HD];
+#pragma unroll
+  for (int c = 0; c < HD; ++c) lp[c] = s_b[c];
+  lepe_stencil<T, false>(lp, v + (int64_t)w.b * g.v_sb + co, g.v_sl, g, w, n, s_w);
+  load_row<T>(out + (int64_t)w.b * g.o_sb + (int64_t)tok * g.o_sl + co, o);
+  load_row<T>(gout + (int64_t)w.b * g.o_sb + (int64_t)tok * g.o_sl + co, go);
+  float d = 0.f;
+#pragma unroll
+  for (int c = 0; c < HD; ++c) d = fmaf(go[c], o[c] - lp[c], d);
+  delta[((int64_t)w.b * g.heads + w.head) * g.L + tok] = d;
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, step 2: grad_q.  Thread = query row; K and V stream through smem.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ROWS)
+    stripe_bwd_dq_simt(StripeGeom g, const T* __restrict__ q, const T* __restrict__ k,
+                       const T* __restrict__ v, const T* __restrict__ gout,
+                       const float* __restrict__ lse, const float* __restrict__ delta,
+                       T* __restrict__ dq, int tiles) {
+  __shared__ __align__(16) float s_k[CHUNK * HD];
+  __shared__ __align__(16) float s_v[CHUNK * HD];
+  const Work w = decode_work(g, tiles);
+  const int n = w.tile * ROWS + threadIdx.x;
+  const bool valid = n < g.N;
+  const int co = w.head * HD;
+  const int tok = valid ? token_of(g, w, n) : 0;
+  float qs[HD], go[HD], acc[HD];
+  float lse_i = 0.f, delta_i = 0.f;
+  if (valid) {
+    load_row<T>(q + (int64_t)w.b * g.q_sb + (int64_t)tok * g.q_sl + co, qs);
+    load_row<T>(gout + (int64_t)w.b * g.o_sb + (int64_t)tok * g.o_sl + co, go);
+    const int64_t si = ((int64_t)w.b * g.heads + w.head) * g.L + tok;
+    lse_i = lse[si];
+    delta_i = delta[si];
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; ++c) qs[c] = go[c] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < HD; ++c) {
+    qs[c] *= g.scale;
+    acc[c] = 0.f;
+  }
+  const T* kb = k + (int64_t)w.b * g.k_sb + co;
+  const T* vb = v + (int64_t)w.b * g.v_sb + co;
+  for (int j0 = 0; j0 < g.N; j0 += CHUNK) {
+    const int cnt = min(CHUNK, g.N - j0);
+    __syncthreads();
+    load_chunk<T>(s_k, kb, g.k_sl, g, w, j0, cnt, 1.f);
+    load_chunk<T>(s_v, vb, g.v_sl, g, w, j0, cnt, 1.f);
+    __syncthreads();
+    for (int j = 0; j < cnt; ++j) {
+      const float s = dot_smem(qs, s_k + j * HD);
+      const float p = Exp<T>::f(s - lse_i);
+      const float dp = dot_smem(go, s_v + j * HD);
+      axpy_smem(acc, p * (dp - delta_i), s_k + j * HD);
+    }
+  }
+  if (!valid) return;
+#pragma unroll
+  for (int c = 0; c < HD; ++c) acc[c] *= g.scale;
+  store_row<T>(dq + (int64_t)w.b * g.dq_sb + (int64_t)tok * g.dq_sl + co, acc);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, step 3: grad_k and grad_v (attention part + transposed LePE stencil on grad_out).
+// Thread = key row; Q (pre-scaled) and grad_out stream through smem with their lse / delta.
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(ROWS)
+    stripe_bwd_dkv_simt(StripeGeom g, const T* __restrict__ q, const T* __restrict__ k,
+                        const T* __restrict__ v, const float* __restrict__ lepe_w,
+                        const T* __restrict__ gout, const float* __restrict__ lse,
+                        const float* __restrict__ delta, T* __restrict__ dk, T* __restrict__ dv,
+                        int tiles) {
+  __shared__ __align__(16) float s_q[CHUNK * HD];
+  __shared__ __align__(16) float s_g[CHUNK * HD];
+  __shared__ __align__(16) float s_w[9 * HD];
+  __shared__ float s_lse[CHUNK], s_delta[CHUNK];
+  const Work w = decode_work(g, tiles);
+  const int n = w.tile * ROWS + threadIdx.x;
+  const bool valid = n < g.N;
+  const int co = w.head * HD;
+  const int tok = valid ? token_of(g, w, n) : 0;
+  load_lepe_weights(s_w, nullptr, lepe_w, nullptr, w.head);
+  float kr[HD], vr[HD], ak[HD], av[HD];
+  if (valid) {
+    load_row<T>(k + (int64_t)w.b * g.k_sb + (int64_t)tok * g.k_sl + co, kr);
+    load_row<T>(v + (int64_t)w.b * g.v_sb + (int64_t)tok * g.v_sl + co, vr);
+  } else {
+#pragma unroll
+    for (int c = 0; c < HD; ++c) kr[c] = vr[c] = 0.f;
+  }
+#pragma unroll
+  for (int c = 0; c < HD; ++c) ak[c] = av[c] = 0.f;
+  const T* qb = q + (int64_t)w.b * g.q_sb + co;
+  const T* gb = gout + (int64_t)w.b * g.o_sb + co;
+  const int64_t sbase = ((int64_t)w.b * g.heads + w.head) * g.L;
+  for (int i0 = 0; i0 < g.N; i0 += CHUNK) {
+    const int cnt = min(CHUNK, g.N - i0);
+    __syncthreads();
+    load_chunk<T>(s_q, qb, g.q_sl, g, w, i0, cnt, g.scale);
+    load_chunk<T>(s_g, gb, g.o_sl, g, w, i0, cnt, 1.f);
+    if (threadIdx.x < cnt) {
+      const int t = token_of(g, w, i0 + threadIdx.x);
+      s_lse[threadIdx.x] = lse[sbase + t];
+      s_delta[threadIdx.x] = delta[sbase + t];
+    }
+    __syncthreads();
+    for (int i = 0; i < cnt; ++i) {
+      const float s = dot_smem(kr, s_q + i * HD);
+      const float p = Exp<T>::f(s - s_lse[i]);
+      axpy_smem(av, p, s_g + i * HD);
+      const float dp = dot_smem(vr, s_g + i * HD);
+      axpy_smem(ak, p * (dp - s_delta[i]), s_q + i * HD);
+    }
+  }
+  if (!valid) return;
+  lepe_stencil<T, true>(av, gb, g.o_sl, g, w, n, s_w);
+  store_row<T>(dk + (int64_t)w.b * g.dk_sb + (int64_t)tok * g.dk_sl + co, ak);
+  store_row<T>(dv + (int64_t)w.b * g.dv_sb + (int64_t)tok * g.dv_sl + co, av);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward, step 4: grad of the depthwise 3x3 weights and bias (get_v, C:244).
+//   gw[c][tap] = sum_tokens grad_out[l][c] * v[neighbour_tap(l)][c];  gb[c] = sum grad_out[l][c]
+// Deterministic two-stage reduction: per-CTA partials [blocks][C'][10] then a column sum.
+// blockDim = (32 channels, 8 token lanes); grid = (token tiles, C'/32).
+// ------------------------------------------------------------------------------------------------
+constexpr int WG_TOK = 512;  // tokens per CTA
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+    lepe_wgrad_partial(StripeGeom g, const T* __restrict__ v, const T* __restrict__ gout,
+                       float* __restrict__ partial) {
+  __shared__ float s_red[8][10][33];
+  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int c = blockIdx.y * 32 + cx;
+  const int cp = g.heads * HD;
+  const int64_t total = (int64_t)g.B * g.L;
+  const int64_t t0 = (int64_t)blockIdx.x * WG_TOK;
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+  for (int t = ty; t < WG_TOK; t += 8) {
+    const int64_t gt = t0 + t;
+    if (gt >= total) break;
+    const int b = (int)(gt / g.L), l = (int)(gt % g.L);
+    const int y = l / g.W, x = l % g.W;
+    const int yy = y % g.hs, xx = x % g.ws;
+    const float go = to_f32(gout[(int64_t)b * g.o_sb + (int64_t)l * g.o_sl + c]);
+    acc[9] += go;
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      if (yy + ky - 1 < 0 || yy + ky - 1 >= g.hs) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        if (xx + kx - 1 < 0 || xx + kx - 1 >= g.ws) continue;
+        const int ln = (y + ky - 1) * g.W + (x + kx - 1);
+        acc[ky * 3 + kx] =
+            fmaf(go, to_f32(v[(int64_t)b * g.v_sb + (int64_t)ln * g.v_sl + c]), acc[ky * 3 + kx]);
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) s_red[ty][i][cx] = acc[i];
+  __syncthreads();
+  for (int i = threadIdx.x; i < 320; i += 256) {
+    const int tap = i / 32, cc = i % 32;
+    float a = 0.f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) a += s_red[r][tap][cc];
+    partial[((int64_t)blockIdx.x * cp + blockIdx.y * 32 + cc) * 10 + tap] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    lepe_wgrad_final(const float* __restrict__ partial, int blocks, int cp,
+                     float* __restrict__ gw, float* __restrict__ gb) {
+  const int i = blockIdx.x * 256 + threadIdx.x;  // (c, tap)
+  if (i >= cp * 10) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += partial[(int64_t)b * cp * 10 + i];
+  const int c = i / 10, tap = i % 10;
+  if (tap == 9) gb[c] = a;
+  else gw[c * 9 + tap] = a;
+}
+
+template <typename T>
+int fwd_t(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
+          const float* lepe_b, void* out, float* lse, cudaStream_t st) {
+  const int tiles = (g.N + ROWS - 1) / ROWS;
+  const int64_t grid = (int64_t)g.B * g.nwy * g.nwx * g.heads * tiles;
+  if (grid > 0x7fffffffLL) return fail(CSB200_ERR_INVALID, "stripe_attn: grid too large");
+  stripe_fwd_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(
+      g, static_cast<const T*>(q), static_cast<const T*>(k), static_cast<const T*>(v), lepe_w,
+      lepe_b, static_cast<T*>(out), lse, tiles);
+  return check_launch("stripe_fwd_simt");
+}
+
+template <typename T>
+int bwd_t(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
+          const float* lepe_b, const void* out, const void* gout, const float* lse, void* dq,
+          void* dk, void* dv, float* gw, float* gb, float* delta, float* partial,
+          cudaStream_t st) {
+  const int tiles = (g.N + ROWS - 1) / ROWS;
+  const int64_t grid = (int64_t)g.B * g.nwy * g.nwx * g.heads * tiles;
+  if (grid > 0x7fffffffLL) return fail(CSB200_ERR_INVALID, "stripe_attn: grid too large");
+  const T* qt = static_cast<const T*>(q);
+  const T* kt = static_cast<const T*>(k);
+  const T* vt = static_cast<const T*>(v);
+  const T* ot = static_cast<const T*>(out);
+  const T* gt = static_cast<const T*>(gout);
+  int rc;
+  stripe_bwd_delta_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(g, vt, lepe_w, lepe_b, ot, gt, delta,
+                                                            tiles);
+  if ((rc = check_launch("stripe_bwd_delta_simt")) != CSB200_OK) return rc;
+  stripe_bwd_dq_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(g, qt, kt, vt, gt, lse, delta,
+                                                         static_cast<T*>(dq), tiles);
+  if ((rc = check_launch("stripe_bwd_dq_simt")) != CSB200_OK) return rc;
+  stripe_bwd_dkv_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(
+      g, qt, kt, vt, lepe_w, gt, lse, delta, static_cast<T*>(dk), static_cast<T*>(dv), tiles);
+  if ((rc = check_launch("stripe_bwd_dkv_simt")) != CSB200_OK) return rc;
+  return lepe_wgrad<T>(g, vt, gt, gw, gb, partial, st);
+}
+
+}  // namespace
+
+int wgrad_blocks(const StripeGeom& g) {
+  return (int)(((int64_t)g.B * g.L + WG_TOK - 1) / WG_TOK);
+}
+
+template <typename T>
+int lepe_wgrad(const StripeGeom& g, const T* v, const T* gout, float* gw, float* gb,
+               float* partial, cudaStream_t st) {
+  const int cp = g.heads * HD;
+  const int blocks = wgrad_blocks(g);
+  lepe_wgrad_partial<T><<<dim3(blocks, cp / 32), 256, 0, st>>>(g, v, gout, partial);
+  int rc = check_launch("lepe_wgrad_partial");
+  if (rc != CSB200_OK) return rc;
+  lepe_wgrad_final<<<(cp * 10 + 255) / 256, 256, 0, st>>>(partial, blocks, cp, gw, gb);
+  return check_launch("lepe_wgrad_final");
+}
+template int lepe_wgrad<float>(const StripeGeom&, const float*, const float*, float*, float*,
+                               float*, cudaStream_t);
+template int lepe_wgrad<__nv_bfloat16>(const StripeGeom&, const __nv_bfloat16*,
+                                       const __nv_bfloat16*, float*, float*, float*, cudaStream_t);
+
+int simt_fwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,
+             const float* lepe_w, const float* lepe_b, void* out, float* lse, cudaStream_t st) {
+  return dtype == CSB200_F32 ? fwd_t<float>(g, q, k, v, lepe_w, lepe_b, out, lse, st)
+                             : fwd_t<__nv_bfloat16>(g, q, k, v, lepe_w, lepe_b, out, lse, st);
+}
+
+int simt_bwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,
+             const float* lepe_w, const float* lepe_b, const void* out, const void* gout,
+             const float* lse, void* dq, void* dk, void* dv, float* gw, float* gb, float* delta,
+             float* partial, cudaStream_t st) {
+  return dtype == CSB200_F32
+             ? bwd_t<float>(g, q, k, v, lepe_w, lepe_b, out, gout, lse, dq, dk, dv, gw, gb, delta,
+                            partial, st)
+             : bwd_t<__nv_bfloat16>(g, q, k, v, lepe_w, lepe_b, out, gout, lse, dq, dk, dv, gw,
+                                    gb, delta, partial, st);
+}
+
+}  // namespace csb200

@@ -1,0 +1,117 @@
+"""Batch-sharded data parallelism: one process per GPU, gradients-only all-reduce.
+
+The reference has no distributed code at all.  Every op of both models is per-sample independent
+(BatchNorm in the UNet uses per-rank batch statistics), so the only exchange per step
+is the gradient average: 23.6 M values for the CSWin-UNet.  Gradients live as views into a few flat
+buckets (no pack/unpack copies); a bucket's all-reduce is launched asynchronously as soon as autograd
+has produced its last gradient, so communication overlaps the rest of backward on NCCL's own stream;
+NVSwitch makes the cost latency- rather than link-bound, hence few large buckets.
+"""
+from typing import Iterable, List, Optional
+
+import torch
+import torch.distributed as dist
+
+
+def shard_of_global_batch(global_batch: int, rank: int, world_size: int) -> range:
+    """Contiguous shard [lo, hi) of the global batch owned by `rank`."""
+    if global_batch % world_size != 0:
+        raise ValueError(f"global batch {global_batch} is not divisible by world size {world_size}")
+    per = global_batch // world_size
+    return range(rank * per, (rank + 1) * per)
+
+
+class _Bucket:
+    def __init__(self, params: List[torch.nn.Parameter]):
+        self.params = params
+        p0 = params[0]
+        self.flat = torch.zeros(sum(p.numel() for p in params), dtype=p0.dtype, device=p0.device)
+        off = 0
+        for p in params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)  # gradient IS a bucket view
+            off += p.numel()
+        self.pending = len(params)
+        self.work = None
+
+
+class GradientAllReducer:
+    """Averages gradients over the process group, bucket by bucket, overlapped with backward.
+
+    Usage per step:  ``begin_step()`` -> forward / ``loss.backward()`` -> ``finish_step()`` ->
+    ``optimizer.step()``.  With world_size == 1 it only manages the flat gradient buffers.
+    """
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], bucket_bytes: int = 32 << 20,
+                 process_group: Optional[dist.ProcessGroup] = None, overlap: bool = True):
+        self.group = process_group
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        self.overlap = overlap
+        params = [p for p in params if p.requires_grad]
+        # backward produces gradients roughly in reverse registration order (decoder first)
+        self.buckets: List[_Bucket] = []
+        cur, cur_bytes, cur_key = [], 0, None
+        for p in reversed(params):
+            key = (p.dtype, p.device)
+            if cur and (key != cur_key or cur_bytes + p.numel() * p.element_size() > bucket_bytes):
+                self.buckets.append(_Bucket(cur))
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_key = key
+            cur_bytes += p.numel() * p.element_size()
+        if cur:
+            self.buckets.append(_Bucket(cur))
+        self._handles = []
+        if self.world > 1:
+            for b in self.buckets:
+                for p in b.params:
+                    self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+        # the backend may lack a native average (gloo): sum, then scale once in finish_step
+        self._avg = dist.ReduceOp.AVG if self.world > 1 and dist.get_backend(process_group) == "nccl" else None
+
+    def _launch(self, b: _Bucket):
+        op = self._avg if self._avg is not None else dist.ReduceOp.SUM
+        b.work = dist.all_reduce(b.flat, op=op, group=self.group, async_op=True)
+
+    def _make_hook(self, b: _Bucket):
+        def hook(_param):
+            b.pending -= 1
+            if b.pending == 0 and self.overlap:
+                self._launch(b)
+        return hook
+
+    def begin_step(self):
+        for b in self.buckets:
+            b.flat.zero_()
+            b.pending = len(b.params)
+            b.work = None
+            for p in b.params:  # an optimizer / user may have replaced .grad (set_to_none=True)
+                if p.grad is None or p.grad.data_ptr() < b.flat.data_ptr() or \
+                        p.grad.data_ptr() >= b.flat.data_ptr() + b.flat.numel() * b.flat.element_size():
+                    self._rebind(b)
+                    break
+
+    @staticmethod
+    def _rebind(b: _Bucket):
+        off = 0
+        for p in b.params:
+            p.grad = b.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def finish_step(self):
+        if self.world == 1:
+            return
+        for b in self.buckets:
+            if b.work is None:  # overlap off, or a parameter took no part in this backward
+                self._launch(b)
+        for b in self.buckets:
+            b.work.wait()
+            if self._avg is None:
+                b.flat.div_(self.world)
+
+    def gradient_bytes(self) -> int:
+        return sum(b.flat.numel() * b.flat.element_size() for b in self.buckets)
+
+    def close(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

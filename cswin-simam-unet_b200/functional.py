@@ -1,0 +1,199 @@
+"""torch.autograd bindings of the csb200 kernels.
+
+Tensors stay ``torch.Tensor``; device pointers come from ``data_ptr()`` and kernels are enqueued on
+torch's current stream.  Nothing here computes on the host or falls back to ATen.
+"""
+import ctypes
+from typing import Optional, Sequence, Tuple
+
+import torch
+
+from . import capi
+
+_vp = ctypes.c_void_p
+
+
+def _ptr(t: Optional[torch.Tensor], elem_offset: int = 0):
+    if t is None:
+        return None
+    return _vp(t.data_ptr() + elem_offset * t.element_size())
+
+
+# ------------------------------------------------------------------------------------------------
+# SimAM
+# ------------------------------------------------------------------------------------------------
+def _simam_dims(x: torch.Tensor, layout: str) -> Tuple[int, int, int, int]:
+    if layout == "NCHW":
+        if x.dim() != 4:
+            raise ValueError("SimAM NCHW expects (B, C, H, W)")
+        B, C, H, W = x.shape
+        return B, C, H * W, capi.NCHW
+    if layout == "NLC":
+        if x.dim() != 3:
+            raise ValueError("SimAM NLC expects (B, L, C)")
+        B, L, C = x.shape
+        return B, C, L, capi.NLC
+    raise ValueError(f"unknown SimAM layout {layout!r}")
+
+
+def _simam_plan(x: torch.Tensor, layout: str):
+    """Pick the physical kernel layout.  A channels-last (B, C, H, W) tensor IS a (B, H*W, C) token
+    matrix in memory, so it takes the NLC kernel in place instead of a transposing copy."""
+    if layout == "NCHW" and x.dim() == 4 and not x.is_contiguous() \
+            and x.is_contiguous(memory_format=torch.channels_last):
+        B, C, H, W = x.shape
+        return x, (B, C, H * W, capi.NLC), torch.channels_last
+    x = x.contiguous()
+    return x, _simam_dims(x, layout), torch.contiguous_format
+
+
+class _SimAMFn(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, e_lambda, layout):
+        capi.require_cuda(x)
+        x, (B, C, S, lay), fmt = _simam_plan(x, layout)
+        y = torch.empty_like(x, memory_format=fmt)
+        stats = torch.empty((B * C, 2), dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            capi.check(capi.lib().csb200_simam_fwd(_ptr(x), _ptr(y), _ptr(stats), B, C, S, lay,
+                                                   capi.dtype_code(x), float(e_lambda), _vp(capi.stream_of(x))),
+                       "csb200_simam_fwd")
+        ctx.save_for_backward(x, stats)
+        ctx.cfg = (B, C, S, lay, float(e_lambda), fmt)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        x, stats = ctx.saved_tensors
+        B, C, S, lay, e_lambda, fmt = ctx.cfg
+        gy = gy.contiguous(memory_format=fmt)
+        if gy.dtype != x.dtype:
+            gy = gy.to(x.dtype)
+        gx = torch.empty_like(x, memory_format=fmt)
+        with torch.cuda.device(x.device):
+            capi.check(capi.lib().csb200_simam_bwd(_ptr(x), _ptr(gy), _ptr(stats), _ptr(gx), B, C, S, lay,
+                                                   capi.dtype_code(x), e_lambda, _vp(capi.stream_of(x))),
+                       "csb200_simam_bwd")
+        return gx, None, None
+
+
+def simam(x: torch.Tensor, e_lambda: float = 1e-4, layout: str = "NCHW") -> torch.Tensor:
+    """Fused SimAM: ``x * sigmoid((x-mean)^2 / (4 (var_n + e_lambda)) + 0.5)`` per (image, channel).
+
+    layout "NCHW": x (B, C, H, W); "NLC": x (B, L, C) tokens.  float32 or bfloat16, CUDA only.
+    """
+    return _SimAMFn.apply(x, e_lambda, layout)
+
+
+# ------------------------------------------------------------------------------------------------
+# stripe attention
+# ------------------------------------------------------------------------------------------------
+class Branch:
+    """Geometry of one LePEAttention branch inside a (B, L, C_total) channel layout."""
+    __slots__ = ("h_sp", "w_sp", "heads", "chan0", "chans")
+
+    def __init__(self, h_sp: int, w_sp: int, heads: int, chan0: int, chans: int):
+        self.h_sp, self.w_sp, self.heads, self.chan0, self.chans = h_sp, w_sp, heads, chan0, chans
+
+
+def _desc(dtype_code, B, H, W, br: Branch, scale, engine, qkv_strides, o_strides, g_strides=None):
+    d = capi.StripeDesc()
+    d.dtype, d.batch, d.height, d.width = dtype_code, B, H, W
+    d.h_sp, d.w_sp, d.heads, d.head_dim = br.h_sp, br.w_sp, br.heads, br.chans // br.heads
+    d.scale, d.engine = float(scale), engine
+    (d.q_sb, d.q_sl), (d.k_sb, d.k_sl), (d.v_sb, d.v_sl) = qkv_strides
+    d.o_sb, d.o_sl = o_strides
+    if g_strides is not None:
+        (d.dq_sb, d.dq_sl), (d.dk_sb, d.dk_sl), (d.dv_sb, d.dv_sl) = g_strides
+    return d
+
+
+_ENGINE = {"auto": capi.ENGINE_AUTO, "simt": capi.ENGINE_SIMT, "tcgen05": capi.ENGINE_TCGEN05}
+
+
+class _CrossStripeFn(torch.autograd.Function):
+    """All branches of one CSWinBlock on the packed (B, L, 3C) qkv buffer -> (B, L, C).
+
+    Fuses what the reference does with slicing, 12 copies per branch and a torch.cat (C:358-363):
+    every branch reads q/k/v in place through strides and writes its channel range of ``out``;
+    backward writes one packed grad_qkv, so the qkv Linear sees a single contiguous gradient.
+    """
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, qkv, H, W, branches, scale, engine, *wb):
+        capi.require_cuda(qkv)
+        qkv = qkv.contiguous()
+        B, L, C3 = qkv.shape
+        C = C3 // 3
+        if L != H * W:
+            raise AssertionError("flatten img_tokens has wrong size")  # C:281, C:356
+        code = capi.dtype_code(qkv)
+        out = torch.empty((B, L, C), dtype=qkv.dtype, device=qkv.device)
+        lses = [torch.empty((B, b.heads, L), dtype=torch.float32, device=qkv.device) for b in branches]
+        ws = [w.detach().float().contiguous() for w in wb]
+        lib = capi.lib()
+        st = _vp(capi.stream_of(qkv))
+        with torch.cuda.device(qkv.device):
+            for i, br in enumerate(branches):
+                d = _desc(code, B, H, W, br, scale, engine, [(L * C3, C3)] * 3, (L * C, C))
+                capi.check(lib.csb200_stripe_attn_fwd(
+                    ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
+                    _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(lses[i]), st),
+                    "csb200_stripe_attn_fwd")
+        ctx.save_for_backward(qkv, out, *lses, *ws)
+        ctx.cfg = (H, W, branches, scale, engine)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        H, W, branches, scale, engine = ctx.cfg
+        qkv, out, *rest = ctx.saved_tensors
+        lses, ws = rest[:len(branches)], rest[len(branches):]
+        B, L, C3 = qkv.shape
+        C = C3 // 3
+        code = capi.dtype_code(qkv)
+        gout = gout.contiguous()
+        if gout.dtype != qkv.dtype:
+            gout = gout.to(qkv.dtype)
+        gqkv = torch.empty_like(qkv)
+        lib = capi.lib()
+        st = _vp(capi.stream_of(qkv))
+        grads = []
+        with torch.cuda.device(qkv.device):
+            for i, br in enumerate(branches):
+                s3 = [(L * C3, C3)] * 3
+                d = _desc(code, B, H, W, br, scale, engine, s3, (L * C, C), s3)
+                nbytes = lib.csb200_stripe_attn_bwd_workspace_bytes(ctypes.byref(d))
+                wsp = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv.device)
+                gw = torch.empty_like(ws[2 * i])
+                gb = torch.empty_like(ws[2 * i + 1])
+                capi.check(lib.csb200_stripe_attn_bwd(
+                    ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
+                    _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(gout, br.chan0), _ptr(lses[i]),
+                    _ptr(gqkv, br.chan0), _ptr(gqkv, C + br.chan0), _ptr(gqkv, 2 * C + br.chan0),
+                    _ptr(gw), _ptr(gb), _ptr(wsp), nbytes, st), "csb200_stripe_attn_bwd")
+                grads += [gw, gb]
+        return (gqkv, None, None, None, None, None, *grads)
+
+
+def cross_stripe_attention(qkv: torch.Tensor, H: int, W: int, branches: Sequence[Branch], scale: float,
+                           weights_and_biases: Sequence[torch.Tensor], engine: str = "auto") -> torch.Tensor:
+    """qkv: (B, L, 3C) packed as [q | k | v] along channels (the output of CSWinBlock.qkv, C:358).
+
+    ``branches`` partition the C channels; ``weights_and_biases`` = [w0, b0, w1, b1, ...] are the
+    get_v parameters ((C',1,3,3), (C',)) of each branch.  Returns (B, L, C).
+    """
+    out = _CrossStripeFn.apply(qkv, H, W, tuple(branches), scale, _ENGINE[engine], *weights_and_biases)
+    return out
+
+
+def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, h_sp, w_sp, heads, scale=None, engine="auto"):
+    """One branch on separate (B, L, C') q, k, v (any strides) — LePEAttention.forward, C:271-298."""
+    Cb = q.shape[-1]
+    scale = (Cb // heads) ** -0.5 if scale is None else scale
+    qkv = torch.cat([q, k, v], dim=-1)  # generic-stride entry: one packing copy, then the fused path
+    return cross_stripe_attention(qkv, H, W, [Branch(h_sp, w_sp, heads, 0, Cb)], scale, [lepe_w, lepe_b], engine)

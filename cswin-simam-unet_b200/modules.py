@@ -1,0 +1,249 @@
+"""Drop-in ``nn.Module`` building blocks of the CSWin-UNet, re-designed around the csb200 kernels.
+
+Constructor signatures, attribute names and therefore ``state_dict`` keys follow the reference
+(train_cswinunet_segmentation.py = "C:") so a constructor swap is all a user needs; the forward
+passes are new: token tensors stay (B, L, C) == NHWC end to end, stripe attention runs in one fused
+kernel per branch on the packed qkv buffer, and convolutions see channels-last views instead of
+transposed copies.
+"""
+import math
+from typing import Optional
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as csbF
+
+
+def _side(L: int) -> int:
+    s = math.isqrt(L)
+    if s * s != L:
+        raise ValueError(f"token count {L} is not a square grid (the reference assumes H == W, C:250)")
+    return s
+
+
+def tokens_as_image(x: torch.Tensor, H: int, W: int) -> torch.Tensor:
+    """(B, L, C) tokens -> logical (B, C, H, W) with channels-last strides; a view, never a copy."""
+    B, L, C = x.shape
+    return x.reshape(B, H, W, C).permute(0, 3, 1, 2)
+
+
+def image_as_tokens(img: torch.Tensor) -> torch.Tensor:
+    """(B, C, H, W) -> (B, H*W, C); free when `img` is channels-last."""
+    B, C, H, W = img.shape
+    return img.permute(0, 2, 3, 1).reshape(B, H * W, C)
+
+
+class SimAM(nn.Module):
+    """Parameter-free SimAM attention (Yang et al., ICML 2021) as ONE fused kernel per direction.
+
+    Not part of the reference checkout; adds no ``state_dict`` keys.
+    ``layout="NCHW"`` for (B, C, H, W) feature maps, ``"NLC"`` for (B, L, C) tokens.
+    """
+
+    def __init__(self, e_lambda: float = 1e-4, layout: str = "NCHW"):
+        super().__init__()
+        self.e_lambda = e_lambda
+        self.layout = layout
+
+    def extra_repr(self):
+        return f"e_lambda={self.e_lambda}, layout={self.layout}"
+
+    def forward(self, x):
+        return csbF.simam(x, self.e_lambda, self.layout)
+
+
+class DropPath(nn.Module):
+    """Per-sample stochastic depth (the reference takes it from timm, C:14, C:344)."""
+
+    def __init__(self, drop_prob: float = 0.0):
+        super().__init__()
+        self.drop_prob = float(drop_prob)
+
+    def forward(self, x):
+        if self.drop_prob == 0.0 or not self.training:
+            return x
+        keep = 1.0 - self.drop_prob
+        mask = torch.empty((x.shape[0],) + (1,) * (x.dim() - 1), dtype=x.dtype, device=x.device).bernoulli_(keep)
+        return x * (mask / keep)
+
+
+class Mlp(nn.Module):
+    """Linear -> act -> drop -> Linear -> drop (C:180-196); dense GEMMs stay on cuBLAS."""
+
+    def __init__(self, in_features, hidden_features=None, out_features=None, act_layer=nn.GELU, drop=0.):
+        super().__init__()
+        self.fc1 = nn.Linear(in_features, hidden_features or in_features)
+        self.act = act_layer()
+        self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
+        self.drop = nn.Dropout(drop)
+
+    def forward(self, x):
+        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+
+
+class LePEAttention(nn.Module):
+    """One stripe-attention branch with the LePE depthwise term (C:220-298), fused.
+
+    ``idx``: -1 full window, 0 vertical stripes (H_sp = resolution, W_sp = split_size), 1 horizontal.
+    ``forward(qkv)`` accepts anything indexable as qkv[0], qkv[1], qkv[2] with (B, L, C') entries of
+    arbitrary strides, as in the reference; CSWinBlock bypasses it and feeds the packed buffer to
+    the kernel directly.  ``get_v`` only stores the depthwise weights: the convolution itself is
+    evaluated inside the attention kernel from the V tile it already holds.
+    """
+
+    def __init__(self, dim, resolution, idx, split_size, dim_out=None, num_heads=9, attn_drop=0., proj_drop=0.,
+                 qk_scale=None):
+        super().__init__()
+        if idx == -1:
+            h_sp, w_sp = resolution, resolution
+        elif idx == 0:
+            h_sp, w_sp = resolution, split_size
+        elif idx == 1:
+            h_sp, w_sp = split_size, resolution
+        else:  # the reference prints and calls exit(0) here (C:238-240); raising is the library-safe form
+            raise ValueError(f"LePEAttention: idx must be -1, 0 or 1, got {idx}")
+        self.dim, self.dim_out = dim, dim_out or dim
+        self.resolution, self.split_size, self.num_heads = resolution, split_size, num_heads
+        self.scale = qk_scale or (dim // num_heads) ** -0.5
+        self.H_sp, self.W_sp = h_sp, w_sp
+        self.get_v = nn.Conv2d(dim, dim, kernel_size=3, stride=1, padding=1, groups=dim)
+        self.attn_drop = nn.Dropout(attn_drop)
+        self.engine = "auto"
+
+    def check_dropout(self):
+        if self.training and self.attn_drop.p > 0:
+            raise NotImplementedError(
+                "attn_drop > 0 in training mode is not implemented by the fused stripe-attention kernel; "
+                "use attn_drop_rate=0 (the constructor default, C:495)")
+
+    def branch(self, chan0: int) -> csbF.Branch:
+        return csbF.Branch(self.H_sp, self.W_sp, self.num_heads, chan0, self.dim)
+
+    def forward(self, qkv):
+        q, k, v = qkv[0], qkv[1], qkv[2]
+        B, L, C = q.shape
+        if L != self.resolution * self.resolution:
+            raise AssertionError("flatten img_tokens has wrong size")
+        self.check_dropout()
+        return csbF.stripe_attention(q, k, v, self.get_v.weight, self.get_v.bias, self.resolution, self.resolution,
+                                     self.H_sp, self.W_sp, self.num_heads, self.scale, self.engine)
+
+
+class CSWinBlock(nn.Module):
+    """pre-LN -> qkv -> cross-shaped stripe attention (2 branches, or 1 full window) -> proj ->
+    residual -> LN -> Mlp -> residual (C:301-370)."""
+
+    def __init__(self, dim, reso, num_heads, split_size, mlp_ratio=4., qkv_bias=False, qk_scale=None,
+                 drop=0., attn_drop=0., drop_path=0., act_layer=nn.GELU, norm_layer=nn.LayerNorm,
+                 last_stage=False):
+        super().__init__()
+        self.dim, self.num_heads = dim, num_heads
+        self.patches_resolution, self.split_size, self.mlp_ratio = reso, split_size, mlp_ratio
+        self.qkv = nn.Linear(dim, dim * 3, bias=qkv_bias)
+        self.norm1 = norm_layer(dim)
+        last_stage = last_stage or reso == split_size  # C:317-318
+        self.branch_num = 1 if last_stage else 2
+        self.proj = nn.Linear(dim, dim)
+        self.proj_drop = nn.Dropout(drop)
+        if last_stage:
+            branches = [LePEAttention(dim, resolution=reso, idx=-1, split_size=split_size, num_heads=num_heads,
+                                      dim_out=dim, qk_scale=qk_scale, attn_drop=attn_drop, proj_drop=drop)]
+        else:
+            branches = [LePEAttention(dim // 2, resolution=reso, idx=i, split_size=split_size,
+                                      num_heads=num_heads // 2, dim_out=dim // 2, qk_scale=qk_scale,
+                                      attn_drop=attn_drop, proj_drop=drop) for i in range(2)]
+        self.attns = nn.ModuleList(branches)
+        self.drop_path = DropPath(drop_path) if drop_path > 0. else nn.Identity()
+        self.mlp = Mlp(in_features=dim, hidden_features=int(dim * mlp_ratio), out_features=dim,
+                       act_layer=act_layer, drop=drop)
+        self.norm2 = norm_layer(dim)
+        self._scale = self.attns[0].scale
+
+    def attend(self, qkv: torch.Tensor) -> torch.Tensor:
+        """qkv: packed (B, L, 3C) -> (B, L, C); no slicing copies and no cat (cf. C:358-363)."""
+        reso = self.patches_resolution
+        width = self.dim // self.branch_num
+        branches, params = [], []
+        for i, att in enumerate(self.attns):
+            att.check_dropout()
+            branches.append(att.branch(i * width))
+            params += [att.get_v.weight, att.get_v.bias]
+        return csbF.cross_stripe_attention(qkv, reso, reso, branches, self._scale, params, self.attns[0].engine)
+
+    def forward(self, x):
+        B, L, C = x.shape
+        if L != self.patches_resolution ** 2:
+            raise AssertionError("flatten img_tokens has wrong size")
+        attended = self.proj(self.attend(self.qkv(self.norm1(x))))
+        x = x + self.drop_path(attended)  # proj_drop exists but is never applied in the reference (C:366-367)
+        return x + self.drop_path(self.mlp(self.norm2(x)))
+
+
+class Merge_Block(nn.Module):
+    """Stride-2 3x3 conv between stages + LayerNorm (C:373-388) on channels-last views."""
+
+    def __init__(self, dim, dim_out, norm_layer=nn.LayerNorm):
+        super().__init__()
+        self.conv = nn.Conv2d(dim, dim_out, 3, 2, 1)
+        self.norm = norm_layer(dim_out)
+
+    def forward(self, x):
+        side = _side(x.shape[1])
+        return self.norm(image_as_tokens(self.conv(tokens_as_image(x, side, side))))
+
+
+def carafe_kernels(img: torch.Tensor, down: nn.Conv2d, encoder: nn.Conv2d, up: int) -> torch.Tensor:
+    """Kernel-prediction half of CARAFE (C:406-411): softmax over the k*k taps, (B, k*k, H*up, W*up)."""
+    return torch.softmax(F.pixel_shuffle(encoder(down(img)), up), dim=1)
+
+
+def carafe_reassemble(low: torch.Tensor, kern: torch.Tensor, up: int, k: int = 3) -> torch.Tensor:
+    """out[b,c,h*up+y,w*up+x] = sum_tap kern[b,tap,h*up+y,w*up+x] * low[b,c,h+ky-k//2,w+kx-k//2]
+    with zero padding (the content-aware reassembly, C:413-431).  low: (B, C, H, W)."""
+    B, C, H, W = low.shape
+    nb = F.unfold(low, k, padding=k // 2).reshape(B, C, k * k, H, W)
+    kv = kern.reshape(B, k * k, H, up, W, up)
+    out = torch.einsum("bcthw,bthywx->bchywx", nb, kv.to(nb.dtype))
+    return out.reshape(B, C, H * up, W * up)
+
+
+class CARAFE(nn.Module):
+    """Content-aware upsampling (C:391-437): predict a softmax 3x3 kernel per output pixel, then
+    reassemble each output pixel from the 3x3 neighbourhood of its source pixel, then a 1x1 conv.
+
+    Re-ordered, not re-defined: reassembly acts on every channel with the same spatial weights and
+    ``out`` is a 1x1 convolution, so the two commute —  out(reassemble(x)) == reassemble(W x) + b.
+    Applying ``W`` at LOW resolution cuts its FLOPs by up^2 and (dim_out = dim/2) halves the
+    channels that get upsampled; the bias is added after reassembly exactly as in the reference.
+    """
+
+    def __init__(self, dim, dim_out, kernel_size=3, up_factor=2):
+        super().__init__()
+        self.kernel_size, self.up_factor = kernel_size, up_factor
+        self.down = nn.Conv2d(dim, dim // 4, 1)
+        self.encoder = nn.Conv2d(dim // 4, up_factor ** 2 * kernel_size ** 2, kernel_size, 1, kernel_size // 2)
+        self.out = nn.Conv2d(dim, dim_out, 1)
+
+    def forward(self, x):
+        side = _side(x.shape[1])
+        img = tokens_as_image(x, side, side)
+        kern = carafe_kernels(img, self.down, self.encoder, self.up_factor)
+        low = F.conv2d(img, self.out.weight)  # bias deferred past the reassembly
+        up = carafe_reassemble(low, kern, self.up_factor, self.kernel_size)
+        return image_as_tokens(up + self.out.bias.to(up.dtype).view(1, -1, 1, 1))
+
+
+class CARAFE4(CARAFE):
+    """CARAFE with up_factor 4 (C:440-486; identical to CARAFE except for the default)."""
+
+    def __init__(self, dim, dim_out, kernel_size=3, up_factor=4):
+        super().__init__(dim, dim_out, kernel_size, up_factor)
+
+
+class ConvEmbedTokens(nn.Module):
+    """'b c h w -> b (h w) c' (the einops Rearrange at C:506), parameter-free."""
+
+    def forward(self, x):
+        return image_as_tokens(x)

@@ -1,0 +1,130 @@
+/*
+ * csb200.h — C ABI of the B200 (sm_100a) kernels behind the CSWin-SimAM-UNet training hot path.
+ *
+ * The reference (TrungMasterChef/CSWin-SimAM-UNet) has no FFI of its own: its only seam is the
+ * nn.Module surface in train_cswinunet_segmentation.py ("C:") and train_unet_segmentation.py ("U:").
+ * Each entry point below names the reference code it replaces.  The Python host side
+ * (cswin-simam-unet_b200/capi.py) binds these with ctypes; INTEGRATION.md shows the stub a reference
+ * maintainer would add.
+ *
+ * Conventions
+ *   - every function returns an int status (CSB200_OK == 0); nothing throws, nothing calls exit()
+ *     (the reference's exit(0) on a bad idx, C:239-240, is deliberately not reproduced);
+ *   - all data pointers are DEVICE pointers owned by the caller; no allocation happens inside;
+ *   - `stream` is a cudaStream_t passed as void*; kernels are enqueued and the call returns at once;
+ *   - strides are in ELEMENTS; the channel stride of every token-major operand is 1;
+ *   - thread safe: no mutable global state except atomically-updated counters and an error string
+ *     that is thread-local.
+ */
+#ifndef CSB200_H_
+#define CSB200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CSB200_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define CSB200_API __attribute__((visibility("default")))
+#else
+#define CSB200_API
+#endif
+
+/* status codes */
+#define CSB200_OK 0
+#define CSB200_ERR_INVALID 1     /* bad shape / divisibility / null pointer — mirrors the RuntimeError
+                                    the reference raises from view() in img2windows, C:204 */
+#define CSB200_ERR_UNSUPPORTED 2 /* valid but not built (e.g. head_dim != 32) */
+#define CSB200_ERR_CUDA 3        /* a CUDA runtime / driver call failed */
+#define CSB200_ERR_WORKSPACE 4   /* workspace too small */
+
+/* element types of activations */
+#define CSB200_F32 0
+#define CSB200_BF16 1
+
+/* SimAM memory layouts */
+#define CSB200_NCHW 0 /* (B, C, H, W): a plane is H*W contiguous elements — UNet, U:177-250 */
+#define CSB200_NLC 1  /* (B, L, C) token-major: a plane is a column of stride C — CSWin, C:349 */
+
+/* attention engines (see csb200_stripe_attn_engine) */
+#define CSB200_ENGINE_AUTO 0
+#define CSB200_ENGINE_SIMT 1    /* fp32-accumulate CUDA-core kernels, any shape */
+#define CSB200_ENGINE_TCGEN05 2 /* bf16 tcgen05/TMEM/TMA kernels, shapes listed in DESIGN.md */
+
+CSB200_API int csb200_abi_version(void);
+/* Thread-local text of the last error raised on this thread ("" if none). */
+CSB200_API const char* csb200_last_error_string(void);
+/* Number of kernels this library has launched since load (all threads). bench.py's gpu_launches. */
+CSB200_API uint64_t csb200_launch_count(void);
+
+/* ------------------------------------------------------------------------------------------------
+ * SimAM — NOT present in the reference checkout; restates the public SimAM module
+ * (Yang et al., ICML 2021):  n = H*W - 1;  d = (x - mean)^2;  v = sum(d)/n + e_lambda;
+ *                            y = x * sigmoid(d / (4 v) + 0.5)
+ * stats (optional in fwd, required in bwd): float[2 * B * C] = {mean, v} per (b, c), index b*C + c.
+ * `spatial` = H*W (NCHW) or L (NLC).
+ * ---------------------------------------------------------------------------------------------- */
+CSB200_API int csb200_simam_fwd(const void* x, void* y, float* stats, int64_t batch, int64_t channels,
+                     int64_t spatial, int layout, int dtype, float e_lambda, void* stream);
+CSB200_API int csb200_simam_bwd(const void* x, const void* grad_y, const float* stats, void* grad_x,
+                     int64_t batch, int64_t channels, int64_t spatial, int layout, int dtype,
+                     float e_lambda, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Cross-shaped stripe attention with LePE — replaces the body of LePEAttention.forward (C:271-298)
+ * including im2cswin (C:248-254), get_lepe (C:256-269), img2windows / windows2img (C:199-217) and, on
+ * the caller's side, the torch.cat of the two branches (C:363): q/k/v are read in place from the
+ * (B, L, 3C) qkv buffer through strides and `out` is written at the branch's channel offset.
+ *
+ *   token l = y*width + x belongs to stripe (y / h_sp, x / w_sp), position (y % h_sp)*w_sp + x % w_sp
+ *   channel c of the branch belongs to head c / head_dim
+ *   out[b,l,:] = softmax(scale * q k^T) v  +  depthwise3x3(v; lepe_w, lepe_b) with ZERO padding at
+ *   the STRIPE border (C:244,263-265)
+ *
+ * lepe_w: float[C'][3][3] (the get_v.weight parameter, (C',1,3,3)), lepe_b: float[C'] — always fp32.
+ * lse:    float[B][heads][L], log-sum-exp of the scaled scores per query row (saved for backward).
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct csb200_stripe_desc {
+  int32_t dtype;          /* CSB200_F32 / CSB200_BF16: type of q, k, v, out and their gradients */
+  int32_t batch;          /* B */
+  int32_t height, width;  /* token grid; L = height * width (C:276-281) */
+  int32_t h_sp, w_sp;     /* stripe extent (C:232-242); height % h_sp == 0 and width % w_sp == 0 */
+  int32_t heads;          /* heads of THIS branch */
+  int32_t head_dim;       /* channels per head; C' = heads * head_dim */
+  float scale;            /* qk scale, head_dim^-0.5 unless qk_scale was given (C:231) */
+  int32_t engine;         /* CSB200_ENGINE_* request; AUTO picks tcgen05 when the shape allows */
+  int64_t q_sb, q_sl;     /* batch / token strides of q (elements) */
+  int64_t k_sb, k_sl;
+  int64_t v_sb, v_sl;
+  int64_t o_sb, o_sl;     /* out and grad_out */
+  int64_t dq_sb, dq_sl;   /* gradients (backward only) */
+  int64_t dk_sb, dk_sl;
+  int64_t dv_sb, dv_sl;
+} csb200_stripe_desc;
+
+/* Which engine a descriptor resolves to (CSB200_ENGINE_SIMT / _TCGEN05), or a negative status. */
+CSB200_API int csb200_stripe_attn_engine(const csb200_stripe_desc* d, int backward);
+
+CSB200_API int csb200_stripe_attn_fwd(const csb200_stripe_desc* d, const void* q, const void* k, const void* v,
+                           const float* lepe_w, const float* lepe_b, void* out, float* lse,
+                           void* stream);
+
+/* Bytes of scratch csb200_stripe_attn_bwd needs for this descriptor. */
+CSB200_API size_t csb200_stripe_attn_bwd_workspace_bytes(const csb200_stripe_desc* d);
+
+/* grad_lepe_w: float[C'][3][3], grad_lepe_b: float[C'] — overwritten (not accumulated).
+ * dq/dk/dv are overwritten. `out` is the forward result (needed for the softmax-gradient row term). */
+CSB200_API int csb200_stripe_attn_bwd(const csb200_stripe_desc* d, const void* q, const void* k, const void* v,
+                           const float* lepe_w, const float* lepe_b, const void* out,
+                           const void* grad_out, const float* lse, void* dq, void* dk, void* dv,
+                           float* grad_lepe_w, float* grad_lepe_b, void* workspace,
+                           size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CSB200_H_ */
