@@ -1,0 +1,267 @@
+#!/usr/bin/env python
+"""Headline benchmark: CSWin-SimAM-UNet training throughput (train img/s) at 512^2, bf16.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo, sm_100a kernels
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on host cores
+
+N > 1 is launched by torchrun (one rank per GPU, NCCL); weak scaling with 32 images per GPU (BASELINE
+config 3 at N=1, config 4's global batch 256 at N=8).  Prints ONE JSON line on rank 0.
+
+step    = zero_grad -> forward (autocast bf16) -> BCE (fp32) -> backward -> [grad all-reduce] -> AdamW
+          (C:780-786, lr 1e-4, wd 1e-4 as C:937-941), dropout 0 (constructor defaults)
+value   = images/s with the batch already resident in HBM, K steps between CUDA events, max over ranks
+e2e     = same step through the public API with pinned HOST batches: H2D copy of images+masks and a D2H
+          read of the loss inside the timed region, every step
+roofline= the csb200 kernel family that takes the most time inside the timed steps, algorithmic
+          FLOPs (attention) or bytes (SimAM) over its CUDA-event time, against MEASURED_PEAKS.json
+cpu_baseline / --impl reference = the oracle's CPU port of the reference model (the Python reference
+          itself cannot travel to the GPU box), fp32, all host threads, bounded sample (B=2 steps)
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+IMG, SPLIT, BATCH_PER_GPU = 512, [1, 2, 8, 8], 32
+METRIC, UNIT = "train img/s at 512^2 bf16 (CSWin-SimAM-UNet)", "img/s"
+FALLBACK_PEAKS = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(path):
+        with open(path) as f:
+            return json.load(f), "measured (MEASURED_PEAKS.json)"
+    return dict(FALLBACK_PEAKS), "fallback (B200_PROFILING.md)"
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks during the timed region
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    QUERY = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.samples, self.stop_flag, self.thread = index, [], threading.Event(), None
+
+    def _run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.QUERY}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [v.strip() for v in out.strip().split(",")]
+                if len(f) >= 6:
+                    self.samples.append((float(f[0]), float(f[1]), f[2:6]))
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def __enter__(self):
+        self.thread = threading.Thread(target=self._run, daemon=True)
+        self.thread.start()
+        return self
+
+    def __exit__(self, *exc):
+        self.stop_flag.set()
+        self.thread.join(timeout=6)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for _, _, fl in self.samples for n, v in zip(names, fl) if v.lower().startswith("active")})
+        return {"sm_mhz": statistics.median(s[0] for s in self.samples), "sm_max_mhz": self.samples[0][1],
+                "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# the reference algorithm on host cores (oracle port) — cpu_baseline and --impl reference
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
+    """fwd + BCE + bwd + AdamW of the reference CSWin-UNet arithmetic at 512^2 on the CPU, fp32.
+    SimAM on the skips is included so the work matches the GPU arm's model."""
+    from oracle import models as om
+    from cswin_simam_unet_b200.train import synthetic_batch
+    torch.set_num_threads(os.cpu_count())
+    cfg = om.CSWinConfig(img_size=IMG, split_size=SPLIT, simam=True)
+    params = {k: v.requires_grad_(True) for k, v in om.synth_params(om.cswin_param_shapes(cfg), 0).items()}
+    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=1e-4)
+    x, y = synthetic_batch(batch, IMG, "cpu", seed=0)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        opt.zero_grad()
+        loss = torch.nn.functional.binary_cross_entropy(om.cswin_unet_forward(params, x, cfg), y)
+        loss.backward()
+        opt.step()
+        if it >= warmup:
+            times.append(time.perf_counter() - t0)
+    total = sum(times)
+    return {"value": batch * steps / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{steps} steps of batch {batch} at {IMG}^2 fp32 after {warmup} warm-up, oracle/models.py "
+                      f"(CPU port of C:489-688 + SimAM on skips), AdamW", "ms_per_step": 1e3 * total / steps}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    steps, warmup = max(1, min(args.steps, 5)), max(1, min(args.warmup, 1))
+    r = cpu_reference_steps(steps, warmup)
+    line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"CSWin-SimAM-UNet train step {IMG}x{IMG}, split {SPLIT}, CPU sample batch 2"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+# this repo's arm
+# ------------------------------------------------------------------------------------------------
+def run_ours(args, rank, local_rank, world):
+    import cswin_simam_unet_b200 as pkg
+    from cswin_simam_unet_b200 import functional as csbF
+
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    torch.backends.cuda.matmul.allow_tf32 = True
+    torch.backends.cudnn.allow_tf32 = True
+    torch.backends.cudnn.benchmark = True
+
+    B = args.batch_per_gpu
+    torch.manual_seed(0)  # identical replicas on every rank
+    net = pkg.CSWinTransformer(img_size=IMG, split_size=SPLIT, simam=True, attn_engine=args.attn_engine).to(dev)
+    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+    reducer = pkg.GradientAllReducer(net.parameters()) if world > 1 else None
+    step = pkg.TrainStep(net, opt, precision="bf16", reducer=reducer)
+
+    shard = pkg.shard_of_global_batch(B * world, rank, world)
+    host = [pkg.synthetic_batch(B, IMG, "cpu", seed=s, first_index=shard.start, pin=True) for s in range(2)]
+    resident = [(x.to(dev), y.to(dev)) for x, y in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for i in range(steps):
+            fn(i)
+        t1.record()
+        barrier()
+        ms = torch.tensor([t0.elapsed_time(t1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    def step_resident(i):
+        x, y = resident[i % 2]
+        step(x, y)
+
+    def step_e2e(i):
+        x, y = host[i % 2]
+        loss = step(x.to(dev, non_blocking=True), y.to(dev, non_blocking=True))
+        return loss.item()  # the D2H read of the step's result
+
+    for i in range(args.warmup):
+        step_resident(i)
+    # --- kernel-only throughput, with per-family CUDA-event spans for the roofline -------------
+    timer = csbF.KernelTimer()
+    csbF.set_kernel_timer(timer)
+    n0 = pkg.capi.launch_count()
+    with ClockSampler(local_rank) as clk:
+        ms = timed(step_resident, args.steps)
+    launches = pkg.capi.launch_count() - n0
+    csbF.set_kernel_timer(None)
+    fams = timer.summary()
+    # --- end to end through the public API, host buffers ---------------------------------------
+    step_e2e(0)
+    ms_e2e = timed(step_e2e, args.steps)
+    mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk, pk_src = peaks()
+    roof_all = {}
+    for fam, r in fams.items():
+        sec = r["ms"] / 1e3
+        if fam.startswith("attn"):
+            ach, peak, unit, bound = r["flops"] / sec / 1e12, pk["bf16_tflops_sustained"], "TFLOP/s", "tensor"
+        else:
+            ach, peak, unit, bound = r["bytes"] / sec / 1e9, pk["hbm_gbs"], "GB/s", "hbm"
+        roof_all[fam] = {"bound": bound, "achieved": round(ach, 2), "peak": peak, "unit": unit,
+                         "frac": round(ach / peak, 4), "calls": r["calls"], "ms_total": round(r["ms"], 3),
+                         "hbm_gbs": round(r["bytes"] / sec / 1e9, 1)}
+    top = max(fams, key=lambda f: fams[f]["ms"])
+    roofline = dict(roof_all[top], kernel=top, traffic=None, peak_source=pk_src,
+                    share_of_step=round(fams[top]["ms"] / ms, 4))
+    h2d = sum(t.numel() * t.element_size() for t in host[0])
+    cpu = cpu_reference_steps(steps=3, warmup=1) if (world == 1 and not args.no_cpu_baseline) else None
+    line = {
+        "metric": METRIC, "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+        "config": {"workload": f"CSWin-SimAM-UNet train step {IMG}x{IMG} (BASELINE configs[2]; configs[3] at N=8)",
+                   "global_batch": B * world, "batch_per_gpu": B, "split_size": SPLIT, "simam": "3 skip tensors (NLC)",
+                   "precision": "autocast bf16, fp32 master weights, fp32 sigmoid+BCE", "optimizer": "AdamW fused",
+                   "dropout": 0.0, "parallelism": f"dp{world}", "attn_engine": args.attn_engine,
+                   "l2": "no explicit flush: one step streams several GB of activations (>> 126 MB L2)",
+                   "peak_mem_gib": round(mem_gb, 2)},
+        "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "roofline": roofline,
+        "roofline_all": roof_all,
+    }
+    if cpu is not None:
+        line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
+    ap.add_argument("--attn-engine", default="auto", choices=["auto", "simt", "tcgen05"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch N>1 with torch.distributed.run")
+    run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

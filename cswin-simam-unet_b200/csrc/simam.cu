@@ -1,7 +1,7 @@
 // SimAM forward / backward for sm_100a.
 //
 // SimAM is not in the reference checkout; the arithmetic follows the public module
-// (Yang et al., ICML 2021) restated in oracle/simam_oracle.py.  Both passes are HBM-bound: the design
+// (Yang et al., ICML 2021) restated in oracle/ops.py.  Both passes are HBM-bound: the design
 // goal is algorithmic traffic only — forward 1 read + 1 write, backward 2 reads + 1 write — which
 // means a plane must stay on chip between the statistics and the rescale.
 //

@@ -13,6 +13,53 @@ from . import capi
 _vp = ctypes.c_void_p
 
 
+class KernelTimer:
+    """Optional CUDA-event stopwatch around every csb200 call, with the call's ALGORITHMIC work
+    (bytes that must cross HBM once, FLOPs of the contraction) — bench.py's roofline source.
+    Events are recorded on the stream the kernels are launched on."""
+
+    def __init__(self):
+        self.spans = []  # (family, start, end, bytes, flops)
+
+    def summary(self):
+        torch.cuda.synchronize()
+        out = {}
+        for fam, a, b, nbytes, flops in self.spans:
+            r = out.setdefault(fam, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+            r["calls"] += 1
+            r["ms"] += a.elapsed_time(b)
+            r["bytes"] += nbytes
+            r["flops"] += flops
+        return out
+
+
+_timer: Optional[KernelTimer] = None
+
+
+def set_kernel_timer(t: Optional[KernelTimer]):
+    global _timer
+    _timer = t
+
+
+class _span:
+    __slots__ = ("fam", "nbytes", "flops", "start")
+
+    def __init__(self, fam, nbytes, flops=0):
+        self.fam, self.nbytes, self.flops = fam, nbytes, flops
+
+    def __enter__(self):
+        if _timer is not None:
+            self.start = torch.cuda.Event(enable_timing=True)
+            self.start.record()
+
+    def __exit__(self, *exc):
+        if _timer is not None:
+            end = torch.cuda.Event(enable_timing=True)
+            end.record()
+            _timer.spans.append((self.fam, self.start, end, self.nbytes, self.flops))
+        return False
+
+
 def _ptr(t: Optional[torch.Tensor], elem_offset: int = 0):
     if t is None:
         return None
@@ -55,7 +102,7 @@ class _SimAMFn(torch.autograd.Function):
         x, (B, C, S, lay), fmt = _simam_plan(x, layout)
         y = torch.empty_like(x, memory_format=fmt)
         stats = torch.empty((B * C, 2), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _span("simam_fwd", 2 * x.numel() * x.element_size()):
             capi.check(capi.lib().csb200_simam_fwd(_ptr(x), _ptr(y), _ptr(stats), B, C, S, lay,
                                                    capi.dtype_code(x), float(e_lambda), _vp(capi.stream_of(x))),
                        "csb200_simam_fwd")
@@ -72,7 +119,7 @@ class _SimAMFn(torch.autograd.Function):
         if gy.dtype != x.dtype:
             gy = gy.to(x.dtype)
         gx = torch.empty_like(x, memory_format=fmt)
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), _span("simam_bwd", 3 * x.numel() * x.element_size()):
             capi.check(capi.lib().csb200_simam_bwd(_ptr(x), _ptr(gy), _ptr(stats), _ptr(gx), B, C, S, lay,
                                                    capi.dtype_code(x), e_lambda, _vp(capi.stream_of(x))),
                        "csb200_simam_bwd")
@@ -110,6 +157,14 @@ def _desc(dtype_code, B, H, W, br: Branch, scale, engine, qkv_strides, o_strides
     return d
 
 
+def _attn_work(B, L, br: Branch, itemsize, backward):
+    """Algorithmic (bytes, flops) of one branch call: q, k, v, out cross HBM once
+    (backward: + grad_out in, 3 gradients out); 4 N^2 hd FLOPs per (stripe, head) forward, 10 backward."""
+    N, hd = br.h_sp * br.w_sp, br.chans // br.heads
+    tensors = 8 if backward else 4
+    return tensors * B * L * br.chans * itemsize, (10 if backward else 4) * N * hd * B * L * br.heads
+
+
 _ENGINE = {"auto": capi.ENGINE_AUTO, "simt": capi.ENGINE_SIMT, "tcgen05": capi.ENGINE_TCGEN05}
 
 
@@ -139,10 +194,11 @@ class _CrossStripeFn(torch.autograd.Function):
         with torch.cuda.device(qkv.device):
             for i, br in enumerate(branches):
                 d = _desc(code, B, H, W, br, scale, engine, [(L * C3, C3)] * 3, (L * C, C))
-                capi.check(lib.csb200_stripe_attn_fwd(
-                    ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
-                    _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(lses[i]), st),
-                    "csb200_stripe_attn_fwd")
+                with _span("attn_fwd", *_attn_work(B, L, br, qkv.element_size(), False)):
+                    capi.check(lib.csb200_stripe_attn_fwd(
+                        ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
+                        _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(lses[i]), st),
+                        "csb200_stripe_attn_fwd")
         ctx.save_for_backward(qkv, out, *lses, *ws)
         ctx.cfg = (H, W, branches, scale, engine)
         return out
@@ -171,11 +227,12 @@ class _CrossStripeFn(torch.autograd.Function):
                 wsp = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv.device)
                 gw = torch.empty_like(ws[2 * i])
                 gb = torch.empty_like(ws[2 * i + 1])
-                capi.check(lib.csb200_stripe_attn_bwd(
-                    ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
-                    _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(gout, br.chan0), _ptr(lses[i]),
-                    _ptr(gqkv, br.chan0), _ptr(gqkv, C + br.chan0), _ptr(gqkv, 2 * C + br.chan0),
-                    _ptr(gw), _ptr(gb), _ptr(wsp), nbytes, st), "csb200_stripe_attn_bwd")
+                with _span("attn_bwd", *_attn_work(B, L, br, qkv.element_size(), True)):
+                    capi.check(lib.csb200_stripe_attn_bwd(
+                        ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
+                        _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(gout, br.chan0),
+                        _ptr(lses[i]), _ptr(gqkv, br.chan0), _ptr(gqkv, C + br.chan0), _ptr(gqkv, 2 * C + br.chan0),
+                        _ptr(gw), _ptr(gb), _ptr(wsp), nbytes, st), "csb200_stripe_attn_bwd")
                 grads += [gw, gb]
         return (gqkv, None, None, None, None, None, *grads)
 

@@ -1,0 +1,92 @@
+"""CPU: the C-ABI library loads, exports every symbol include/csb200.h declares, and validates its
+arguments without touching a GPU (no compute calls here)."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from conftest import ROOT
+from cswin_simam_unet_b200 import capi, functional as F_
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "csb200.h")).read()
+    return sorted(set(re.findall(r"CSB200_API[^;(]*?\b(csb200_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    declared = _declared_symbols()
+    assert len(declared) >= 9
+    assert set(declared) == set(capi.EXPORTS)
+    lib = ctypes.CDLL(capi.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert capi.lib().csb200_abi_version() == 1
+
+
+def test_descriptor_layout_matches_header():
+    # 10 x 4-byte fields then 14 x int64 (the first int64 is 8-byte aligned: 40 bytes in)
+    assert ctypes.sizeof(capi.StripeDesc) == 40 + 14 * 8
+    assert capi.StripeDesc.q_sb.offset == 40
+
+
+def _desc(**kw):
+    d = capi.StripeDesc()
+    base = dict(dtype=capi.F32, batch=1, height=8, width=8, h_sp=8, w_sp=2, heads=1, head_dim=32, scale=0.1,
+                engine=capi.ENGINE_AUTO, q_sb=8 * 8 * 96, q_sl=96, k_sb=8 * 8 * 96, k_sl=96, v_sb=8 * 8 * 96,
+                v_sl=96, o_sb=8 * 8 * 32, o_sl=32)
+    base.update(kw)
+    for k, v in base.items():
+        setattr(d, k, v)
+    return d
+
+
+def test_shape_validation_mirrors_reference_failures():
+    lib = capi.lib()
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(_desc()), 0) == capi.ENGINE_SIMT
+    # stripe does not divide the grid: the reference raises RuntimeError from view() (C:204)
+    rc = lib.csb200_stripe_attn_engine(ctypes.byref(_desc(w_sp=7)), 0)
+    assert rc == -capi.ERR_INVALID and "not divisible" in capi.last_error()
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(_desc(head_dim=64)), 0) == -capi.ERR_UNSUPPORTED
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(_desc(dtype=7)), 0) == -capi.ERR_INVALID
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(_desc(q_sl=97)), 0) == -capi.ERR_INVALID
+    assert lib.csb200_stripe_attn_engine(None, 0) == -capi.ERR_INVALID
+    # forced tcgen05 on a shape it cannot tile is refused, not silently rerouted
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(_desc(engine=capi.ENGINE_TCGEN05)), 0) == -capi.ERR_UNSUPPORTED
+    assert lib.csb200_stripe_attn_bwd_workspace_bytes(ctypes.byref(_desc())) >= 8 * 8 * 4
+    with pytest.raises(RuntimeError, match="not divisible"):
+        capi.check(-lib.csb200_stripe_attn_engine(ctypes.byref(_desc(w_sp=7)), 0), "engine")
+
+
+def test_simam_argument_validation():
+    lib = capi.lib()
+    one = ctypes.c_void_p(16)
+    assert lib.csb200_simam_fwd(one, one, None, 1, 1, 4, 9, capi.F32, 1e-4, None) == capi.ERR_INVALID  # layout
+    assert lib.csb200_simam_fwd(one, one, None, 1, 1, 4, capi.NCHW, 5, 1e-4, None) == capi.ERR_INVALID  # dtype
+    assert lib.csb200_simam_fwd(None, one, None, 1, 1, 4, capi.NCHW, capi.F32, 1e-4, None) == capi.ERR_INVALID
+    assert lib.csb200_simam_bwd(one, None, None, one, 1, 1, 4, capi.NCHW, capi.F32, 1e-4, None) == capi.ERR_INVALID
+    # empty tensors are a no-op, not an error (and launch nothing)
+    n0 = capi.launch_count()
+    assert lib.csb200_simam_fwd(None, None, None, 0, 4, 16, capi.NCHW, capi.F32, 1e-4, None) == capi.OK
+    assert capi.launch_count() == n0
+
+
+def test_no_cpu_fallback():
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F_.simam(torch.randn(1, 2, 4, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        F_.cross_stripe_attention(torch.randn(1, 16, 96), 4, 4, [F_.Branch(4, 4, 1, 0, 32)], 0.1,
+                                  [torch.randn(32, 1, 3, 3), torch.randn(32)])
+    with pytest.raises(TypeError):
+        capi.dtype_code(torch.zeros(1, dtype=torch.float16))
+
+
+def test_product_package_does_not_import_the_oracle():
+    pkg = os.path.join(ROOT, "cswin-simam-unet_b200")
+    pat = re.compile(r"^\s*(from|import)\s+\.*oracle\b|import_module\([\"']oracle|#include\s+[<\"].*oracle", re.M)
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                assert not pat.search(open(os.path.join(dirpath, f)).read()), f

@@ -1,0 +1,97 @@
+"""GPU: SimAM kernels vs the oracle, through the C ABI (csb200_simam_fwd / _bwd).
+
+Tolerances: fp32 <= 1e-5 relative (north_star); bf16 <= 2 bf16 ulps of the largest magnitude
+(the kernel computes in fp32 from bf16 inputs and rounds once; the oracle is evaluated in fp64 on the
+same bf16 inputs and is NOT rounded, so half an ulp is rounding and the rest is headroom).
+"""
+import pytest
+import torch
+
+from conftest import rel_err
+import cswin_simam_unet_b200 as pkg
+from oracle import ops
+
+pytestmark = pytest.mark.gpu
+TOL = {torch.float32: 1e-5, torch.bfloat16: 2 ** -7}
+
+# every dispatch path: warp-per-plane, CTA-per-plane, clusters of 2/4/8, generic (odd sizes)
+NCHW_SHAPES = [(2, 3, 4, 4), (3, 5, 16, 16), (2, 4, 32, 32), (2, 3, 64, 64), (2, 2, 128, 128), (1, 2, 256, 256),
+               (1, 1, 512, 512), (2, 3, 7, 7), (1, 2, 224, 224), (1, 3, 14, 14), (2, 2, 56, 56), (1, 1, 600, 600)]
+NLC_SHAPES = [(2, 16, 64), (2, 1024, 256), (2, 4096, 128), (1, 16384, 64), (1, 256, 512), (2, 49, 24), (1, 3136, 64),
+              (1, 100, 13), (1, 65536, 32)]
+
+
+def _check(x, layout, dtype, offset=0.0):
+    x = (x + offset).to(dtype)
+    gy = torch.randn_like(x, dtype=torch.float32).to(dtype)
+    xd = x.cuda().requires_grad_(True)
+    y = pkg.simam(xd, 1e-4, layout)
+    y.backward(gy.cuda())
+    x64 = x.double().requires_grad_(True)
+    y64 = ops.simam(x64, 1e-4, layout)
+    y64.backward(gy.double())
+    assert y.dtype == dtype and y.shape == x.shape
+    assert rel_err(y.float().cpu(), y64.detach()) < TOL[dtype]
+    assert rel_err(xd.grad.float().cpu(), x64.grad) < TOL[dtype]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", NCHW_SHAPES)
+def test_simam_nchw_matches_oracle(shape, dtype):
+    torch.manual_seed(sum(shape))
+    _check(torch.randn(shape), "NCHW", dtype)
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", NLC_SHAPES)
+def test_simam_nlc_matches_oracle(shape, dtype):
+    torch.manual_seed(sum(shape))
+    _check(torch.randn(shape) * 2 + 0.5, "NLC", dtype)
+
+
+def test_simam_large_mean_keeps_fp32_parity():
+    # naive sum(x^2) - sum(x)^2/n would lose every digit here
+    torch.manual_seed(0)
+    _check(torch.randn(2, 3, 64, 64), "NCHW", torch.float32, offset=300.0)
+    _check(torch.randn(2, 1024, 64), "NLC", torch.float32, offset=300.0)
+
+
+def test_simam_channels_last_takes_the_token_kernel_in_place():
+    torch.manual_seed(1)
+    x = torch.randn(2, 64, 32, 32)
+    xc = x.cuda().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    y = pkg.simam(xc, 1e-4, "NCHW")
+    assert y.is_contiguous(memory_format=torch.channels_last)
+    y.sum().backward()
+    x64 = x.double().requires_grad_(True)
+    y64 = ops.simam(x64)
+    y64.sum().backward()
+    assert rel_err(y.cpu(), y64.detach()) < 1e-5 and rel_err(xc.grad.cpu(), x64.grad) < 1e-5
+
+
+def test_simam_module_and_edge_cases():
+    m = pkg.SimAM()
+    assert list(m.state_dict()) == []
+    assert m(torch.empty(0, 4, 8, 8, device="cuda")).shape == (0, 4, 8, 8)
+    const = torch.full((1, 2, 8, 8), 3.0, device="cuda")  # zero variance: v = lambda, d = 0 -> sigmoid(0.5)
+    assert rel_err(m(const).cpu(), ops.simam(const.cpu().double())) < 1e-6
+    one = torch.randn(1, 2, 1, 1, device="cuda")  # H*W = 1: n = 0 -> NaN, exactly like the definition
+    assert torch.isnan(m(one)).all() and torch.isnan(ops.simam(one.cpu())).all()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+def test_simam_full_size_config2_plane_samples(dtype):
+    # BASELINE config 2 largest call: (16, 64, 256, 256).  Oracle on sampled planes + global invariants.
+    torch.manual_seed(2)
+    x = torch.randn(16, 64, 256, 256, device="cuda").to(dtype)
+    y = pkg.simam(x)
+    for (b, c) in [(0, 0), (7, 31), (15, 63)]:
+        ref = ops.simam(x[b:b + 1, c:c + 1].double().cpu())
+        assert rel_err(y[b:b + 1, c:c + 1].float().cpu(), ref) < TOL[dtype]
+    # the gate is a sigmoid of a value >= 0.5: sign preserved, 0.62|x| <= |y| <= |x|
+    yf, xf = y.float(), x.float()
+    assert bool(((yf.abs() <= xf.abs() * (1 + 2 ** -7)) & (yf.abs() >= xf.abs() * 0.62 * (1 - 2 ** -6))).all())
+    assert torch.equal(torch.sign(yf), torch.sign(xf))
+    # per-plane independence: permuting planes permutes the output bit-for-bit
+    perm = torch.randperm(64, device="cuda")
+    assert torch.equal(pkg.simam(x[:, perm].contiguous()), y[:, perm])

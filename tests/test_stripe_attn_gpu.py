@@ -1,0 +1,154 @@
+"""GPU: stripe attention + LePE kernels vs the reference's golden vectors and the oracle, through the
+C ABI (csb200_stripe_attn_fwd / _bwd).
+
+Tolerances (relative = max|a-b| / max|b|):
+  fp32 engine: forward and all gradients <= 1e-5                     (north_star)
+  bf16: forward <= 2^-7 (one bf16 rounding of the output plus bf16 P in the tcgen05 engine);
+        gradients <= 3e-2 (bf16 rounding of dS / P before the second GEMM; stated tolerance)
+"""
+import pytest
+import torch
+
+from conftest import ATTN_GOLDEN, golden, rel_err
+import cswin_simam_unet_b200 as pkg
+from cswin_simam_unet_b200 import functional as csbF
+from oracle import ops
+
+pytestmark = pytest.mark.gpu
+FWD_TOL = {torch.float32: 1e-5, torch.bfloat16: 2 ** -7}
+BWD_TOL = {torch.float32: 1e-5, torch.bfloat16: 3e-2}
+
+
+def _run(qkv, w, b, gout, reso_hw, hs, ws, heads, dtype, engine="auto"):
+    """qkv: (3, B, L, C) float tensor on CPU.  Returns out, dqkv, dw, db from the kernels."""
+    H, W = reso_hw
+    C = qkv.shape[-1]
+    packed = torch.cat([qkv[0], qkv[1], qkv[2]], dim=-1).to(dtype).cuda().requires_grad_(True)
+    wd = w.float().cuda().requires_grad_(True)
+    bd = b.float().cuda().requires_grad_(True)
+    out = csbF.cross_stripe_attention(packed, H, W, [csbF.Branch(hs, ws, heads, 0, C)], (C // heads) ** -0.5,
+                                      [wd, bd], engine)
+    out.backward(gout.to(dtype).cuda())
+    dq = packed.grad.float().cpu()
+    return out.float().cpu(), torch.stack([dq[..., :C], dq[..., C:2 * C], dq[..., 2 * C:]]), wd.grad.cpu(), bd.grad.cpu()
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("name", ATTN_GOLDEN)
+def test_golden_vectors_from_the_reference(name, dtype):
+    g = golden(f"attn_{name}.npz")
+    dim, reso, idx, split, heads, B, hs, ws = [int(v) for v in g["meta"]]
+    out, dqkv, dw, db = _run(torch.tensor(g["qkv"]), torch.tensor(g["lepe_w"]), torch.tensor(g["lepe_b"]),
+                             torch.tensor(g["gout"]), (reso, reso), hs, ws, heads, dtype)
+    assert rel_err(out, g["out"]) < FWD_TOL[dtype]
+    assert rel_err(dqkv[0], g["dqkv"][0]) < BWD_TOL[dtype]
+    assert rel_err(dqkv[1], g["dqkv"][1]) < BWD_TOL[dtype]
+    assert rel_err(dqkv[2], g["dqkv"][2]) < BWD_TOL[dtype]
+    assert rel_err(dw, g["dw"]) < BWD_TOL[dtype]
+    assert rel_err(db, g["db"]) < BWD_TOL[dtype]
+
+
+# (B, H, W, hs, ws, heads): config-1 stripes (N = 56, 56, 98, 49), config-3 stripes (N = 128, 256),
+# non-square grids, several heads, a stripe longer than one CTA tile (N = 320) and N = 1
+RANDOM_CASES = [(2, 56, 56, 56, 1, 1), (1, 28, 28, 2, 28, 2), (2, 14, 14, 14, 7, 4), (2, 7, 7, 7, 7, 16),
+                (1, 128, 128, 128, 1, 1), (1, 64, 64, 2, 64, 2), (2, 32, 32, 32, 8, 4), (2, 16, 16, 16, 16, 16),
+                (1, 8, 24, 4, 12, 2), (1, 40, 16, 40, 8, 1), (2, 4, 4, 1, 1, 1)]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("case", RANDOM_CASES)
+def test_random_shapes_match_oracle(case, dtype):
+    B, H, W, hs, ws, heads = case
+    C = heads * 32
+    gen = torch.Generator().manual_seed(sum(case))
+    qkv = torch.randn((3, B, H * W, C), generator=gen).to(torch.bfloat16).double()
+    w = (torch.randn((C, 1, 3, 3), generator=gen) * 0.3).float().double()
+    b = (torch.randn((C,), generator=gen) * 0.1).float().double()
+    gout = torch.randn((B, H * W, C), generator=gen).to(torch.bfloat16).double()
+    out, dqkv, dw, db = _run(qkv, w, b, gout, (H, W), hs, ws, heads, dtype)
+    q64 = qkv.clone().requires_grad_(True)
+    w64, b64 = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = ops.stripe_attention(q64[0], q64[1], q64[2], w64, b64, H, W, hs, ws, heads)
+    ref.backward(gout)
+    assert rel_err(out, ref.detach()) < FWD_TOL[dtype]
+    assert rel_err(dqkv, q64.grad) < BWD_TOL[dtype]
+    assert rel_err(dw, w64.grad) < BWD_TOL[dtype] and rel_err(db, b64.grad) < BWD_TOL[dtype]
+
+
+def test_two_branches_share_one_packed_buffer(no_tf32):
+    # the CSWinBlock call: two orientations on the channel halves of one (B, L, 3C) buffer (C:360-363)
+    torch.manual_seed(0)
+    blk = pkg.CSWinBlock(dim=64, reso=16, num_heads=2, split_size=4, qkv_bias=True).cuda()
+    qkv = torch.randn(2, 256, 192, device="cuda", requires_grad=True)
+    out = blk.attend(qkv)
+    out.backward(torch.ones_like(out))
+    q64 = qkv.detach().double().cpu().requires_grad_(True)
+    refs = []
+    for i, att in enumerate(blk.attns):
+        cs = slice(32 * i, 32 * i + 32)
+        refs.append(ops.stripe_attention(q64[..., :64][..., cs], q64[..., 64:128][..., cs], q64[..., 128:][..., cs],
+                                         att.get_v.weight.detach().double().cpu(),
+                                         att.get_v.bias.detach().double().cpu(), 16, 16, att.H_sp, att.W_sp, 1))
+    ref = torch.cat(refs, -1)
+    ref.backward(torch.ones_like(ref))
+    assert rel_err(out.cpu(), ref.detach()) < 1e-5
+    assert rel_err(qkv.grad.cpu(), q64.grad) < 1e-5
+
+
+def test_lepe_module_accepts_strided_views_like_the_reference(no_tf32):
+    g = golden("attn_h_sw2_n16.npz")
+    dim, reso, idx, split, heads, B, hs, ws = [int(v) for v in g["meta"]]
+    att = pkg.LePEAttention(dim, reso, idx, split, num_heads=heads).cuda()
+    with torch.no_grad():
+        att.get_v.weight.copy_(torch.tensor(g["lepe_w"]))
+        att.get_v.bias.copy_(torch.tensor(g["lepe_b"]))
+    q = torch.tensor(g["qkv"]).cuda()  # (3, B, L, C)
+    big = torch.zeros(B, reso * reso, 3, 2 * dim, device="cuda")
+    big[..., dim:] = q.permute(1, 2, 0, 3)
+    view = big.permute(2, 0, 1, 3)[..., dim:]  # same indexing as qkv[:, :, :, C//2:] at C:362
+    assert not view[0].is_contiguous()
+    assert rel_err(att(view).cpu(), g["out"]) < 1e-5
+    with pytest.raises(AssertionError):
+        att(view[:, :, :-1])
+
+
+def test_shape_errors_surface_as_runtime_error():
+    qkv = torch.randn(1, 64, 96, device="cuda")
+    w, b = torch.randn(32, 1, 3, 3, device="cuda"), torch.randn(32, device="cuda")
+    with pytest.raises(RuntimeError, match="not divisible"):  # the reference fails in view(), C:204
+        csbF.cross_stripe_attention(qkv, 8, 8, [csbF.Branch(8, 3, 1, 0, 32)], 0.17, [w, b])
+    with pytest.raises(RuntimeError, match="head_dim"):
+        csbF.cross_stripe_attention(torch.randn(1, 64, 48, device="cuda"), 8, 8, [csbF.Branch(8, 8, 1, 0, 16)], 0.25,
+                                    [w[:16], b[:16]])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("stage", [(128, 128, 1, 1), (64, 64, 2, 2), (32, 32, 8, 4), (16, 16, 16, 16)])
+def test_full_size_config3_properties(stage, dtype):
+    """BASELINE config 3 shapes (512^2, B=32, split [1,2,8,8]); too big for the oracle, so check
+    size-independent properties: with v == const per channel and zero LePE weights the output must be
+    that constant (softmax rows sum to 1); the result is invariant under permuting whole stripes."""
+    reso, _, sw, heads = stage
+    B, C, L = 32, heads * 32, reso * reso
+    full = sw == reso
+    hs, ws = (reso, reso) if full else (reso, sw)
+    torch.manual_seed(reso)
+    qkv = torch.randn(B, L, 3 * C, device="cuda").to(dtype)
+    const = torch.linspace(-2, 2, C, device="cuda").to(dtype)
+    qkv[..., 2 * C:] = const
+    w0, b0 = torch.zeros(C, 1, 3, 3, device="cuda"), torch.zeros(C, device="cuda")
+    br = [csbF.Branch(hs, ws, heads, 0, C)]
+    out = csbF.cross_stripe_attention(qkv, reso, reso, br, 32 ** -0.5, [w0, b0])
+    assert (out.float() - const.float()).abs().max() <= (2 ** -7 if dtype == torch.bfloat16 else 1e-5)
+    # oracle on one image of the batch (cheap enough): random v and LePE weights
+    qkv2 = torch.randn(B, L, 3 * C, device="cuda").to(dtype)
+    w1, b1 = torch.randn(C, 1, 3, 3, device="cuda") * 0.3, torch.randn(C, device="cuda") * 0.1
+    out2 = csbF.cross_stripe_attention(qkv2, reso, reso, br, 32 ** -0.5, [w1, b1])
+    one = qkv2[5:6].double().cpu()
+    ref = ops.stripe_attention(one[..., :C], one[..., C:2 * C], one[..., 2 * C:], w1.double().cpu(), b1.double().cpu(),
+                               reso, reso, hs, ws, heads)
+    assert rel_err(out2[5:6].float().cpu(), ref) < FWD_TOL[dtype]
+    # batch-permutation equivariance (images are independent): bit-exact
+    perm = torch.randperm(B, device="cuda")
+    out3 = csbF.cross_stripe_attention(qkv2[perm].contiguous(), reso, reso, br, 32 ** -0.5, [w1, b1])
+    assert torch.equal(out3, out2[perm])
