@@ -1,0 +1,123 @@
+#!/usr/bin/env python
+"""Per-kernel roofline microbenchmarks (one JSON line per case) — SimAM against the HBM roofline,
+stripe attention against the tensor and HBM rooflines.  Inputs rotate through enough distinct
+buffers to exceed the 126 MB L2 between repeats; CUDA events on the launching stream.
+
+    python benchmarks/kernel_bench.py simam        # BASELINE config 2 / 3 SimAM call sites
+    python benchmarks/kernel_bench.py attn [--engine simt|tcgen05|auto]   # config 3 attention calls
+"""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import cswin_simam_unet_b200 as pkg  # noqa: E402
+from cswin_simam_unet_b200 import functional as csbF  # noqa: E402
+
+PEAKS = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
+    os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0,
+                                                      "bf16_tflops_sustained": 1400.0}
+L2_BYTES = 126 << 20
+
+
+def time_ms(fn, nbuf, reps=20, warmup=3):
+    for i in range(warmup):
+        fn(i % nbuf)
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for i in range(reps):
+        fn(i % nbuf)
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / reps
+
+
+def bench_simam():
+    # config 2 (UNet 256^2, B=16): DoubleConv outputs, NCHW; config 3 (CSWin 512^2, B=32): skips, NLC
+    cases = [("NCHW", (16, 64, 256, 256)), ("NCHW", (16, 128, 128, 128)), ("NCHW", (16, 256, 64, 64)),
+             ("NCHW", (16, 512, 32, 32)), ("NCHW", (16, 1024, 16, 16)),
+             ("NLC", (32, 16384, 64)), ("NLC", (32, 4096, 128)), ("NLC", (32, 1024, 256))]
+    for dtype in (torch.bfloat16, torch.float32):
+        for layout, shape in cases:
+            numel = 1
+            for s in shape:
+                numel *= s
+            nbytes = numel * (2 if dtype == torch.bfloat16 else 4)
+            nbuf = max(2, -(-2 * L2_BYTES // nbytes))
+            xs = [torch.randn(shape, device="cuda").to(dtype) for _ in range(nbuf)]
+            gs = [torch.randn(shape, device="cuda").to(dtype) for _ in range(min(nbuf, 4))]
+            ys = [None] * nbuf
+
+            def fwd(i):
+                xs[i].requires_grad_(True)
+                ys[i] = pkg.simam(xs[i], 1e-4, layout)
+            ms_f = time_ms(fwd, nbuf)
+            for i in range(nbuf):
+                fwd(i)
+
+            def bwd(i):
+                torch.autograd.grad(ys[i], xs[i], gs[i % len(gs)], retain_graph=True)
+            ms_b = time_ms(bwd, nbuf)
+            for name, ms, mult in (("simam_fwd", ms_f, 2), ("simam_bwd", ms_b, 3)):
+                gbs = mult * nbytes / ms / 1e6
+                print(json.dumps({"kernel": name, "layout": layout, "shape": shape, "dtype": str(dtype)[6:],
+                                  "us": round(ms * 1e3, 2), "algorithmic_GBps": round(gbs, 1),
+                                  "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3), "buffers": nbuf}),
+                      flush=True)
+            del xs, gs, ys
+
+
+def bench_attn(engine):
+    # config 3 per-call shapes: (reso, split, heads_total, C)
+    stages = [("s1", 128, 1, 2, 64), ("s2", 64, 2, 4, 128), ("s3", 32, 8, 8, 256), ("s4", 16, 16, 16, 512)]
+    B = 32
+    for dtype in (torch.bfloat16,) if engine == "tcgen05" else (torch.bfloat16, torch.float32):
+        for name, reso, split, heads, C in stages:
+            blk = pkg.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, last_stage=(name == "s4")).cuda()
+            for a in blk.attns:
+                a.engine = engine
+            L = reso * reso
+            nbytes = B * L * 3 * C * (2 if dtype == torch.bfloat16 else 4)
+            nbuf = max(2, -(-2 * L2_BYTES // nbytes))
+            qs = [(torch.randn(B, L, 3 * C, device="cuda")).to(dtype).requires_grad_(True) for _ in range(nbuf)]
+            g = torch.randn(B, L, C, device="cuda").to(dtype)
+            outs = [None] * nbuf
+            t = csbF.KernelTimer()
+
+            def fwd(i):
+                outs[i] = blk.attend(qs[i])
+            ms_f = time_ms(fwd, nbuf)
+            for i in range(nbuf):
+                fwd(i)
+            params = [p for a in blk.attns for p in (a.get_v.weight, a.get_v.bias)]
+
+            def bwd(i):
+                torch.autograd.grad(outs[i], [qs[i]] + params, g, retain_graph=True)
+            ms_b = time_ms(bwd, nbuf)
+            csbF.set_kernel_timer(t)
+            fwd(0)
+            bwd(0)
+            csbF.set_kernel_timer(None)
+            work = t.summary()
+            for fam, ms in (("attn_fwd", ms_f), ("attn_bwd", ms_b)):
+                fl, by = work[fam]["flops"], work[fam]["bytes"]
+                N = reso * split if name != "s4" else reso * reso
+                print(json.dumps({"kernel": fam, "stage": name, "N": N, "dtype": str(dtype)[6:], "engine": engine,
+                                  "us": round(ms * 1e3, 1), "TFLOPs": round(fl / ms / 1e9, 2),
+                                  "frac_of_bf16_sustained": round(fl / ms / 1e9 / PEAKS["bf16_tflops_sustained"], 4),
+                                  "algorithmic_GBps": round(by / ms / 1e6, 1),
+                                  "frac_of_measured_hbm": round(by / ms / 1e6 / PEAKS["hbm_gbs"], 3),
+                                  "attainable_tensor_frac": round(min(1.0, (fl / by) / 210.0), 3)}), flush=True)
+            del qs, outs
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("what", choices=["simam", "attn"])
+    ap.add_argument("--engine", default="auto")
+    a = ap.parse_args()
+    bench_simam() if a.what == "simam" else bench_attn(a.engine)

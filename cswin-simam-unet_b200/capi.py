@@ -58,7 +58,7 @@ def lib() -> ctypes.CDLL:
         L.csb200_stripe_attn_fwd.argtypes = [dp, vp, vp, vp, f32p, f32p, vp, f32p, vp]
         L.csb200_stripe_attn_bwd_workspace_bytes.argtypes = [dp]
         L.csb200_stripe_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
-        L.csb200_stripe_attn_bwd.argtypes = [dp] + [vp] * 15 + [ctypes.c_size_t, vp]
+        L.csb200_stripe_attn_bwd.argtypes = [dp] + [vp] * 14 + [ctypes.c_size_t, vp]
         for fn in ("csb200_simam_fwd", "csb200_simam_bwd", "csb200_stripe_attn_engine",
                    "csb200_stripe_attn_fwd", "csb200_stripe_attn_bwd"):
             getattr(L, fn).restype = ctypes.c_int

@@ -42,12 +42,16 @@ struct Sig<__nv_bfloat16> {
   }
 };
 
+// The mean is carried as (pivot, dmean) with pivot = the plane's first element and
+// dmean = mean - pivot: x - pivot is exact in fp32 for nearby values (Sterbenz), so the centred value
+// t = (x - pivot) - dmean keeps full relative accuracy even when |mean| >> std.
 struct FwdCoef {
-  float mean, inv4v;
+  float pivot, dmean, inv4v;
 };
+__device__ __forceinline__ float centred(float x, float pivot, float dmean) { return (x - pivot) - dmean; }
 template <typename T>
 __device__ __forceinline__ float simam_fwd_elem(float x, const FwdCoef& c) {
-  float t = x - c.mean;
+  float t = centred(x, c.pivot, c.dmean);
   return x * Sig<T>::f(fmaf(t * t, c.inv4v, 0.5f));
 }
 
@@ -122,18 +126,21 @@ __global__ void __launch_bounds__(THREADS)
     int vi = v0 + i * vstride;
     d[i] = (vi < nvec) ? ld_stream(xp + vi) : make_uint4(0, 0, 0, 0);
   }
-  // pass A: sum (zero padding of invalid slots is harmless)
+  const float pivot = to_f32(__ldg(x + plane * nvec * VE));  // first element of the plane
+  // pass A: sum of (x - pivot)
   float red[1] = {0.f};
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
-    float f[VE];
-    unpack<T>(d[i], f);
+    if (v0 + i * vstride < nvec) {
+      float f[VE];
+      unpack<T>(d[i], f);
 #pragma unroll
-    for (int e = 0; e < VE; ++e) red[0] += f[e];
+      for (int e = 0; e < VE; ++e) red[0] += f[e] - pivot;
+    }
   }
   if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
   else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp, s_cta);
-  const float mean = red[0] / S;
+  const float dmean = red[0] / S;
 
   // pass B: centred second moment
   red[0] = 0.f;
@@ -144,7 +151,7 @@ __global__ void __launch_bounds__(THREADS)
       unpack<T>(d[i], f);
 #pragma unroll
       for (int e = 0; e < VE; ++e) {
-        float t = f[e] - mean;
+        float t = centred(f[e], pivot, dmean);
         red[0] = fmaf(t, t, red[0]);
       }
     }
@@ -152,7 +159,7 @@ __global__ void __launch_bounds__(THREADS)
   if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
   else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp + 32, s_cta + 1);
   const float v = red[0] / (S - 1.f) + e_lambda;
-  FwdCoef c{mean, 1.f / (4.f * v)};
+  FwdCoef c{pivot, dmean, 1.f / (4.f * v)};
 
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
@@ -166,7 +173,7 @@ __global__ void __launch_bounds__(THREADS)
     }
   }
   if (stats != nullptr && v0 == 0) {
-    stats[2 * plane] = mean;
+    stats[2 * plane] = dmean;
     stats[2 * plane + 1] = v;
   }
   if constexpr (CLUSTER > 1) cluster_sync_all();  // keep s_cta alive until every peer has read it
@@ -207,7 +214,8 @@ __global__ void __launch_bounds__(THREADS)
     dx[i] = ok ? ld_stream(xp + vi) : make_uint4(0, 0, 0, 0);
     dg[i] = ok ? ld_stream(gp + vi) : make_uint4(0, 0, 0, 0);
   }
-  const float mean = __ldg(stats + 2 * plane), v = __ldg(stats + 2 * plane + 1);
+  const float pivot = to_f32(__ldg(x + plane * nvec * VE));
+  const float dmean = __ldg(stats + 2 * plane), v = __ldg(stats + 2 * plane + 1);
   const float inv4v = 1.f / (4.f * v);
 
   float red[2] = {0.f, 0.f};  // R1 = sum a*d, R2' = sum a*t  (grad of zero-padded slots is 0 -> a = 0)
@@ -218,7 +226,7 @@ __global__ void __launch_bounds__(THREADS)
     unpack<T>(dg[i], fg);
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
-      float t = fx[e] - mean, dd = t * t;
+      float t = centred(fx[e], pivot, dmean), dd = t * t;
       float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
       float a = fg[e] * fx[e] * s * (1.f - s);
       red[0] = fmaf(a, dd, red[0]);
@@ -242,7 +250,7 @@ __global__ void __launch_bounds__(THREADS)
       unpack<T>(dg[i], fg);
 #pragma unroll
       for (int e = 0; e < VE; ++e) {
-        float t = fx[e] - mean, dd = t * t;
+        float t = centred(fx[e], pivot, dmean), dd = t * t;
         float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
         float a = fg[e] * fx[e] * s * (1.f - s);
         fx[e] = fmaf(fg[e], s, 2.f * t * fmaf(a, inv4v, -c1)) - c2;
@@ -328,18 +336,22 @@ __global__ void __launch_bounds__(THREADS)
     int r = r0 + i * RPI;
     d[i] = (r < L) ? ld_stream(xp + (int64_t)r * cvec) : make_uint4(0, 0, 0, 0);
   }
+  float pivot[VE];  // row 0 of this thread's channel vector (same address for the whole column)
+  unpack<T>(__ldg(xp), pivot);
   float acc[1][VE];
 #pragma unroll
   for (int e = 0; e < VE; ++e) acc[0][e] = 0.f;
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
-    float f[VE];
-    unpack<T>(d[i], f);
+    if (r0 + i * RPI < L) {
+      float f[VE];
+      unpack<T>(d[i], f);
 #pragma unroll
-    for (int e = 0; e < VE; ++e) acc[0][e] += f[e];
+      for (int e = 0; e < VE; ++e) acc[0][e] += f[e] - pivot[e];
+    }
   }
   slab_reduce<VE, CWV, THREADS, CLUSTER, 1>(acc, s_red, s_part[0], s_fin);
-  float mean[VE];
+  float mean[VE];  // mean - pivot
 #pragma unroll
   for (int e = 0; e < VE; ++e) {
     mean[e] = acc[0][e] / (float)L;
@@ -352,7 +364,7 @@ __global__ void __launch_bounds__(THREADS)
       unpack<T>(d[i], f);
 #pragma unroll
       for (int e = 0; e < VE; ++e) {
-        float t = f[e] - mean[e];
+        float t = centred(f[e], pivot[e], mean[e]);
         acc[0][e] = fmaf(t, t, acc[0][e]);
       }
     }
@@ -363,7 +375,8 @@ __global__ void __launch_bounds__(THREADS)
 #pragma unroll
   for (int e = 0; e < VE; ++e) {
     float v = acc[0][e] / ((float)L - 1.f) + e_lambda;
-    c[e].mean = mean[e];
+    c[e].pivot = pivot[e];
+    c[e].dmean = mean[e];
     c[e].inv4v = 1.f / (4.f * v);
     acc[0][e] = v;
   }
@@ -421,7 +434,9 @@ __global__ void __launch_bounds__(THREADS)
     dx[i] = ok ? ld_stream(xp + (int64_t)r * cvec) : make_uint4(0, 0, 0, 0);
     dg[i] = ok ? ld_stream(gp + (int64_t)r * cvec) : make_uint4(0, 0, 0, 0);
   }
-  float mean[VE], v[VE], inv4v[VE];
+  float pivot[VE];
+  unpack<T>(__ldg(xp), pivot);
+  float mean[VE], v[VE], inv4v[VE];  // mean[] holds mean - pivot
   {
     const int64_t p0 = (int64_t)b * C + slab * CW + cv * VE;
 #pragma unroll
@@ -441,7 +456,7 @@ __global__ void __launch_bounds__(THREADS)
     unpack<T>(dg[i], fg);
 #pragma unroll
     for (int e = 0; e < VE; ++e) {
-      float t = fx[e] - mean[e], dd = t * t;
+      float t = centred(fx[e], pivot[e], mean[e]), dd = t * t;
       float s = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
       float a = fg[e] * fx[e] * s * (1.f - s);
       acc[0][e] = fmaf(a, dd, acc[0][e]);
@@ -464,7 +479,7 @@ __global__ void __launch_bounds__(THREADS)
       unpack<T>(dg[i], fg);
 #pragma unroll
       for (int e = 0; e < VE; ++e) {
-        float t = fx[e] - mean[e], dd = t * t;
+        float t = centred(fx[e], pivot[e], mean[e]), dd = t * t;
         float s = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
         float a = fg[e] * fx[e] * s * (1.f - s);
         fx[e] = fmaf(fg[e], s, 2.f * t * fmaf(a, inv4v[e], -c1[e])) - c2[e];
@@ -535,22 +550,23 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
   };
   const float Sf = (float)S;
-  float mean, v;
+  const float pivot = to_f32(x[base]);
+  float mean, v;  // mean holds mean - pivot
   if constexpr (!BWD) {
     float sum = 0.f, dummy = 0.f;
     if (active)
-      for (int64_t i = grp; i < S; i += ngrp) sum += to_f32(x[base + i * istride]);
+      for (int64_t i = grp; i < S; i += ngrp) sum += to_f32(x[base + i * istride]) - pivot;
     reduce2(sum, dummy);
     mean = sum / Sf;
     float m2 = 0.f;
     if (active)
       for (int64_t i = grp; i < S; i += ngrp) {
-        float t = to_f32(x[base + i * istride]) - mean;
+        float t = centred(to_f32(x[base + i * istride]), pivot, mean);
         m2 = fmaf(t, t, m2);
       }
     reduce2(m2, dummy);
     v = m2 / (Sf - 1.f) + e_lambda;
-    FwdCoef c{mean, 1.f / (4.f * v)};
+    FwdCoef c{pivot, mean, 1.f / (4.f * v)};
     if (active) {
       for (int64_t i = grp; i < S; i += ngrp)
         out[base + i * istride] = from_f32<T>(simam_fwd_elem<T>(to_f32(x[base + i * istride]), c));
@@ -567,7 +583,7 @@ __global__ void __launch_bounds__(256)
     if (active)
       for (int64_t i = grp; i < S; i += ngrp) {
         float xv = to_f32(x[base + i * istride]), g = to_f32(gy[base + i * istride]);
-        float t = xv - mean, dd = t * t;
+        float t = centred(xv, pivot, mean), dd = t * t;
         float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
         float a = g * xv * s * (1.f - s);
         r1 = fmaf(a, dd, r1);
@@ -578,7 +594,7 @@ __global__ void __launch_bounds__(256)
     if (active)
       for (int64_t i = grp; i < S; i += ngrp) {
         float xv = to_f32(x[base + i * istride]), g = to_f32(gy[base + i * istride]);
-        float t = xv - mean, dd = t * t;
+        float t = centred(xv, pivot, mean), dd = t * t;
         float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
         float a = g * xv * s * (1.f - s);
         out[base + i * istride] = from_f32<T>(fmaf(g, s, 2.f * t * fmaf(a, inv4v, -c1)) - c2);

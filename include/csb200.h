@@ -65,7 +65,9 @@ CSB200_API uint64_t csb200_launch_count(void);
  * SimAM — NOT present in the reference checkout; restates the public SimAM module
  * (Yang et al., ICML 2021):  n = H*W - 1;  d = (x - mean)^2;  v = sum(d)/n + e_lambda;
  *                            y = x * sigmoid(d / (4 v) + 0.5)
- * stats (optional in fwd, required in bwd): float[2 * B * C] = {mean, v} per (b, c), index b*C + c.
+ * stats (optional in fwd, required in bwd): float[2 * B * C], index b*C + c — state saved for the
+ * backward pass: {mean - x_first, v}, x_first being the plane's first spatial element (the mean is
+ * kept relative to that pivot so that large-mean planes lose no precision).
  * `spatial` = H*W (NCHW) or L (NLC).
  * ---------------------------------------------------------------------------------------------- */
 CSB200_API int csb200_simam_fwd(const void* x, void* y, float* stats, int64_t batch, int64_t channels,

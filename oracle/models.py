@@ -151,12 +151,15 @@ def unet_forward(p, x, training=True, simam=False, e_lambda=1e-4):
 # ---------------------------------------------------------------------------------------------
 # deterministic synthetic parameters keyed by name (weights cannot travel as fixtures: 94 MB)
 # ---------------------------------------------------------------------------------------------
-def synth_params(shapes: Dict[str, tuple], seed: int = 0, dtype=torch.float32) -> Params:
+def synth_params(shapes: Dict[str, tuple], seed: int = 0, dtype=torch.float32, style: str = "unit") -> Params:
     """Reproducible parameters from (name, shape) alone — same values on any machine / torch CPU.
 
-    Linear / conv weights ~ N(0, std) with a fan-in scaled std so activations stay O(1) through 26
-    blocks; norm weights near 1; biases small.  Generated per key, so the reference model (golden
-    generation) and the product model (tests) can both be filled without sharing constructor order.
+    style "unit": Linear / conv weights ~ N(0, 1/fan_in) so activations stay O(1) through 26 blocks
+    (a stress regime: every op contributes); norm weights near 1; biases small.
+    style "init": the scale of the reference's own initialisation (C:607-614) — Linear ~ N(0, .02)
+    clipped at 2 sigma with zero bias, norms 1/0, convolutions U(+-1/sqrt(fan_in)) like torch's default.
+    Generated per key, so the reference model (golden generation) and the product model (tests) can
+    both be filled without sharing constructor order.
     """
     import zlib
     out = {}
@@ -167,6 +170,27 @@ def synth_params(shapes: Dict[str, tuple], seed: int = 0, dtype=torch.float32) -
             out[name] = torch.zeros(shape, dtype=torch.long)
             continue
         r = torch.randn(shape, generator=gen, dtype=torch.float64)
+        if style == "init" and not name.endswith(("running_mean", "running_var")):
+            if len(shape) == 1:
+                is_norm = "norm" in name or name.startswith("stage1_conv_embed.2")
+                if is_norm or len(shapes.get(name[:-4] + "weight", ())) == 2:  # norm or Linear bias
+                    val = torch.ones(shape, dtype=torch.float64) if (is_norm and name.endswith("weight")) \
+                        else torch.zeros(shape, dtype=torch.float64)
+                else:  # conv bias
+                    wshape = shapes[name[:-4] + "weight"]
+                    fan_in = 1
+                    for d in wshape[1:]:
+                        fan_in *= d
+                    val = (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) / math.sqrt(fan_in)
+            elif len(shape) == 2:
+                val = (0.02 * r).clamp(-0.04, 0.04)
+            else:
+                fan_in = 1
+                for d in shape[1:]:
+                    fan_in *= d
+                val = (torch.rand(shape, generator=gen, dtype=torch.float64) * 2 - 1) / math.sqrt(fan_in)
+            out[name] = val.to(dtype)
+            continue
         if name.endswith("running_mean"):
             val = 0.1 * r
         elif name.endswith("running_var"):

@@ -87,6 +87,29 @@ def block_case(ref):
     return dict(x=x.detach().numpy(), gout=gout.numpy(), y=y.detach().numpy(), dx=x.grad.numpy(), **grads)
 
 
+def bf16_drift_case(ref, img_size, split, batch, seed):
+    """fp32 logits of the reference at ITS OWN initialisation scale, plus how far the reference's own
+    bf16 (CPU autocast) forward drifts from them — the yardstick for the bf16 tolerance."""
+    cfg = om.CSWinConfig(img_size=img_size, split_size=split)
+    net = ref.CSWinTransformer(img_size=img_size, split_size=split)
+    params = om.synth_params(om.cswin_param_shapes(cfg), seed, style="init")
+    net.load_state_dict(params)
+    g = torch.Generator().manual_seed(200 + seed)
+    x = torch.rand((batch, 3, img_size, img_size), generator=g)
+    grabbed = {}
+    net.output.register_forward_hook(lambda m, i, o: grabbed.__setitem__("logits", o.detach().float()))
+    with torch.no_grad():
+        net(x)
+        fp32 = grabbed["logits"].clone()
+        with torch.autocast("cpu", dtype=torch.bfloat16):
+            net(x)
+        bf16 = grabbed["logits"].clone()
+    thr = fp32.median()
+    return dict(meta=np.array([img_size, batch, seed] + list(split), dtype=np.int64), x=x.numpy(),
+                logits=fp32.numpy(), ref_bf16_max_abs=np.array((fp32 - bf16).abs().max().item()),
+                ref_bf16_median_mask_agreement=np.array(((fp32 > thr) == (bf16 > thr)).float().mean().item()))
+
+
 def model_case(ref, img_size, split, batch, seed):
     cfg = om.CSWinConfig(img_size=img_size, split_size=split)
     net = ref.CSWinTransformer(img_size=img_size, split_size=split)
@@ -149,6 +172,7 @@ def main():
     np.savez(os.path.join(OUT, "cswin_64.npz"), **model_case(ref, 64, [1, 2, 2, 2], 2, 0))
     np.savez(os.path.join(OUT, "cswin_224_config1.npz"), **model_case(ref, 224, [1, 2, 7, 7], 2, 0))
     np.savez(os.path.join(OUT, "unet_64.npz"), **unet_case(refu))
+    np.savez(os.path.join(OUT, "cswin_224_init_bf16.npz"), **bf16_drift_case(ref, 224, [1, 2, 7, 7], 2, 0))
     # reference failure modes that the drop-in must mirror
     try:
         ref.CSWinTransformer(img_size=512)(torch.rand(1, 3, 512, 512))
