@@ -36,12 +36,15 @@ def time_ms(fn, nbuf, reps=20, warmup=3):
     return a.elapsed_time(b) / reps
 
 
-def bench_simam():
+def bench_simam(only_layout=None, only_dtype=None, first=None):
     # config 2 (UNet 256^2, B=16): DoubleConv outputs, NCHW; config 3 (CSWin 512^2, B=32): skips, NLC
     cases = [("NCHW", (16, 64, 256, 256)), ("NCHW", (16, 128, 128, 128)), ("NCHW", (16, 256, 64, 64)),
              ("NCHW", (16, 512, 32, 32)), ("NCHW", (16, 1024, 16, 16)),
              ("NLC", (32, 16384, 64)), ("NLC", (32, 4096, 128)), ("NLC", (32, 1024, 256))]
+    cases = [c for c in cases if only_layout in (None, c[0])][:first]
     for dtype in (torch.bfloat16, torch.float32):
+        if only_dtype not in (None, str(dtype)[6:]):
+            continue
         for layout, shape in cases:
             numel = 1
             for s in shape:
@@ -119,5 +122,8 @@ if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("what", choices=["simam", "attn"])
     ap.add_argument("--engine", default="auto")
+    ap.add_argument("--layout", default=None, choices=["NCHW", "NLC"])
+    ap.add_argument("--dtype", default=None, choices=["bfloat16", "float32"])
+    ap.add_argument("--first", type=int, default=None, help="only the first K SimAM shapes")
     a = ap.parse_args()
-    bench_simam() if a.what == "simam" else bench_attn(a.engine)
+    bench_simam(a.layout, a.dtype, a.first) if a.what == "simam" else bench_attn(a.engine)
