@@ -1,12 +1,391 @@
-// tcgen05 / TMEM / TMA engine of the stripe attention (bf16, fp32 accumulate) — placeholder that
-// reports "unsupported" until the kernels land; AUTO then resolves to the CUDA-core engine.
+// Stripe attention + LePE, tcgen05 / TMEM / TMA engine (bf16 in, fp32 accumulate) — forward.
+//
+// One persistent CTA per SM walks the (image, stripe, head) groups.  Per group the stripe's K and V
+// (N x 32 bf16 each) and, per 128-row query tile, Q are fetched by TMA straight out of the packed
+// token-major qkv buffer: the tensor map is (channel, x, y, image) and the box is
+// (32, min(w_sp,128), 128/min(w_sp,128), 1), so the reference's img2windows / im2cswin copies
+// (C:199-206, C:248-254) ARE the TMA address generation.  Tiles land 64-byte-swizzled, which is at
+// once the K-major layout of Q and K for S = Q K^T and the MN-major layout of V for O = P V.
+//
+//   warp 0      TMA producer (K, V, LePE taps per group; Q per tile)
+//   warp 1      single-thread tcgen05.mma issuer:  S = Q K^T (M128 x N{128,256} x K32) into TMEM,
+//               O = P V (M128 x N32 x K{128,256}) with P read from TMEM as the A operand
+//   warp 2      TMEM allocator
+//   warps 4-7 / 8-11   two softmax warpgroups ping-ponging on two TMEM buffers: one thread per query
+//               row reads its S row with tcgen05.ld, max / exp2 / sum in registers, writes bf16 P back
+//               over S with tcgen05.st; later reads O, scales by 1/sum, adds the LePE depthwise 3x3
+//               evaluated from the V tile that is already in shared memory (zero padding at the
+//               stripe border, C:244,263-265), and stores the row to out[b, token, head*32 ..] —
+//               windows2img (C:209-217) and the branch concat (C:363) are this store's address.
+//
+// TMEM map per buffer (256 columns): S fp32 [0,N) -> P bf16 [0,N/2) -> O fp32 [N/2, N/2+32).
+
+#include <mutex>
+
 #include "stripe_attn.cuh"
+#include "tc_common.cuh"
 
 namespace csb200 {
-bool tc_fwd_supported(const StripeGeom&, int) { return false; }
-bool tc_bwd_supported(const StripeGeom&, int) { return false; }
-int tc_fwd(const StripeGeom&, const void*, const void*, const void*, const float*, const float*,
-           void*, float*, cudaStream_t) {
-  return fail(CSB200_ERR_UNSUPPORTED, "tcgen05 engine not built");
+
+EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
 }
+
+namespace {
+using namespace tc;
+
+constexpr int HD = 32;
+constexpr int TILE = 128;                   // query rows per tile == TMEM lanes
+constexpr int ROW_BYTES = HD * 2;           // 64 B per token row of one head
+constexpr int TILE_BYTES = TILE * ROW_BYTES;  // 8 KB
+constexpr int QS = 4;                       // Q ring stages
+constexpr int THREADS = 384;
+constexpr int LEPE_FLOATS = 10 * HD;        // 9 taps + bias for the 32 channels of a head
+
+struct FwdParams {
+  int B, W, L, hs, ws, nwy, nwx, heads;
+  int bx, by;          // TMA box extent in x / y (bx * by == 128)
+  int groups;          // B * nwy * nwx * heads
+  float scale_log2;    // scale * log2(e)
+  float scale;
+  const float* lepe_w;  // [C'][9]
+  const float* lepe_b;  // [C']
+  __nv_bfloat16* out;
+  int64_t o_sb, o_sl;
+  float* lse;
+};
+
+template <int NK>
+struct Smem {
+  static constexpr int KV_BYTES = NK * ROW_BYTES;
+  alignas(1024) uint8_t q[QS][TILE_BYTES];
+  alignas(1024) uint8_t k[2][KV_BYTES];
+  alignas(1024) uint8_t v[2][KV_BYTES];
+  alignas(16) float lepe[2][LEPE_FLOATS];  // [tap][c] then bias[c]
+  alignas(8) uint64_t q_full[QS], q_empty[QS];
+  uint64_t kv_full[2], kv_empty[2];
+  uint64_t s_full[2], p_full[2], o_full[2], buf_empty[2];
+  uint32_t tmem_base;
+};
+
+// address of 16-byte chunk `chunk` (0..3) of row n inside a 64B-swizzled tile
+__device__ __forceinline__ const uint4* sw64_chunk(const uint8_t* tile, int n, int chunk) {
+  return reinterpret_cast<const uint4*>(tile + n * ROW_BYTES + ((chunk ^ ((n >> 1) & 3)) << 4));
+}
+
+struct GroupCoord {
+  int b, wy, wx, head;
+};
+__device__ __forceinline__ GroupCoord decode_group(const FwdParams& p, int g) {
+  GroupCoord c;
+  c.head = g % p.heads;
+  g /= p.heads;
+  c.wx = g % p.nwx;
+  g /= p.nwx;
+  c.wy = g % p.nwy;
+  c.b = g / p.nwy;
+  return c;
+}
+
+template <int NK>
+__global__ void __launch_bounds__(THREADS, 1)
+    stripe_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                  const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+  constexpr int T = NK / TILE;          // query tiles per group
+  constexpr int NBOX = NK / TILE;       // TMA boxes per K (or V) load
+  constexpr uint32_t P_COL = 0, O_COL = NK / 2, BUF_COLS = 256;
+  extern __shared__ uint8_t smem_raw[];
+  Smem<NK>& sm = *reinterpret_cast<Smem<NK>*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_groups = (p.groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int my_tiles = my_groups * T;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_q);
+    prefetch_tensormap(&tm_k);
+    prefetch_tensormap(&tm_v);
+    for (int i = 0; i < QS; ++i) {
+      mbar_init(&sm.q_full[i], 1);
+      mbar_init(&sm.q_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.kv_full[i], 1);
+      mbar_init(&sm.kv_empty[i], 4 * T);  // one arrival per softmax warp per tile of the group
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.p_full[i], 128);
+      mbar_init(&sm.o_full[i], 1);
+      mbar_init(&sm.buf_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&sm.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    int it = 0;
+    for (int gi = 0; gi < my_groups; ++gi) {
+      const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
+      const int kvs = gi & 1;
+      mbar_wait(&sm.kv_empty[kvs], ((gi >> 1) & 1) ^ 1);
+      // LePE taps of this head -> smem as [tap][c], bias last (plain stores, released by the arrive)
+      for (int i = lane; i < LEPE_FLOATS; i += 32) {
+        const int tap = i / HD, ch = i % HD;
+        sm.lepe[kvs][i] = tap < 9 ? __ldg(p.lepe_w + (c.head * HD + ch) * 9 + tap)
+                                  : __ldg(p.lepe_b + c.head * HD + ch);
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&sm.kv_full[kvs], 2 * Smem<NK>::KV_BYTES);
+        const int x0 = c.wx * p.ws, y0 = c.wy * p.hs;
+#pragma unroll
+        for (int bx = 0; bx < NBOX; ++bx) {
+          // box `bx` covers in-stripe rows [128 bx, 128 bx + 128)
+          const int dx = (p.ws > TILE) ? (bx * TILE) % p.ws : 0;
+          const int dy = (p.ws > TILE) ? (bx * TILE) / p.ws : bx * p.by;
+          tma_load_4d(sm.k[kvs] + bx * TILE_BYTES, &tm_k, &sm.kv_full[kvs], c.head * HD, x0 + dx,
+                      y0 + dy, c.b);
+          tma_load_4d(sm.v[kvs] + bx * TILE_BYTES, &tm_v, &sm.kv_full[kvs], c.head * HD, x0 + dx,
+                      y0 + dy, c.b);
+        }
+        for (int t = 0; t < T; ++t, ++it) {
+          const int qs = it % QS;
+          mbar_wait(&sm.q_empty[qs], ((it / QS) & 1) ^ 1);
+          mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
+          const int dx = (p.ws > TILE) ? (t * TILE) % p.ws : 0;
+          const int dy = (p.ws > TILE) ? (t * TILE) / p.ws : t * p.by;
+          tma_load_4d(sm.q[qs], &tm_q, &sm.q_full[qs], c.head * HD, x0 + dx, y0 + dy, c.b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = umma_idesc_bf16(NK, false, false);
+      constexpr uint32_t idesc_pv = umma_idesc_bf16(HD, false, true);
+      auto issue_pv = [&](int it) {
+        const int buf = it & 1, kvs = (it / T) & 1;
+        mbar_wait(&sm.p_full[buf], (it >> 1) & 1);
+        fence_after_sync();
+        const uint32_t d = tmem + buf * BUF_COLS + O_COL, a = tmem + buf * BUF_COLS + P_COL;
+        const uint32_t vb = smem_u32(sm.v[kvs]);
+#pragma unroll
+        for (int k = 0; k < NK / 16; ++k)  // 16 keys per step: 8 TMEM columns of P, 1024 B of V
+          umma_ts(d, a + 8 * k, umma_desc_sw64(vb + k * 1024), idesc_pv, k > 0);
+        umma_commit(&sm.o_full[buf]);
+      };
+      for (int it = 0; it < my_tiles; ++it) {
+        const int buf = it & 1, qs = it % QS, gi = it / T, kvs = gi & 1;
+        mbar_wait(&sm.q_full[qs], (it / QS) & 1);
+        if (it % T == 0) mbar_wait(&sm.kv_full[kvs], (gi >> 1) & 1);
+        mbar_wait(&sm.buf_empty[buf], ((it >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t qa = smem_u32(sm.q[qs]), kb = smem_u32(sm.k[kvs]);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)  // 16 channels per step: 32 B inside the swizzled row
+          umma_ss(tmem + buf * BUF_COLS, umma_desc_sw64(qa + k * 32), umma_desc_sw64(kb + k * 32),
+                  idesc_s, k > 0);
+        umma_commit(&sm.s_full[buf]);
+        umma_commit(&sm.q_empty[qs]);
+        if (it > 0) issue_pv(it - 1);
+      }
+      if (my_tiles > 0) issue_pv(my_tiles - 1);
+    }
+    __syncwarp();
+  } else if (warp >= 4) {
+    // ============================ softmax + epilogue warpgroups ============================
+    const int wg = (warp - 4) >> 2;                  // 0 / 1 == TMEM buffer
+    const int row = ((warp & 3) << 5) | lane;        // query row inside the tile == TMEM lane
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + wg * BUF_COLS;
+    for (int it = wg; it < my_tiles; it += 2) {
+      const int gi = it / T, t = it % T, kvs = gi & 1;
+      const uint32_t use = (it >> 1) & 1;
+      const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
+      mbar_wait(&sm.s_full[wg], use);
+      fence_after_sync();
+      uint32_t r[32];
+      float m = -INFINITY;
+#pragma unroll 1
+      for (int ch = 0; ch < NK / 32; ++ch) {
+        tmem_ld32(lane_base + ch * 32, r);
+        tmem_wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+      }
+      const float neg_m = -m * p.scale_log2;
+      float l = 0.f;
+#pragma unroll 1
+      for (int ch = 0; ch < NK / 32; ++ch) {
+        tmem_ld32(lane_base + ch * 32, r);
+        tmem_wait_ld();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
+          const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+          l += p0 + p1;
+          pk[i] = pack_bf16x2(p0, p1);
+        }
+        tmem_st16(lane_base + P_COL + ch * 16, pk);  // P over the S columns already consumed
+      }
+      tmem_wait_st();
+      fence_before_sync();
+      mbar_arrive(&sm.p_full[wg]);
+
+      // ---- epilogue: O / l + LePE -> out, lse ----
+      mbar_wait(&sm.o_full[wg], use);
+      fence_after_sync();
+      tmem_ld32(lane_base + O_COL, r);
+      tmem_wait_ld();
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.buf_empty[wg]);  // S(it+2) may now overwrite this buffer
+
+      // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
+      // barrier the MMA warp used (already complete; cannot advance before this warp's kv_empty)
+      mbar_wait(&sm.kv_full[kvs], (gi >> 1) & 1);
+      const float inv_l = 1.f / l;
+      const int n = t * TILE + row;  // in-stripe index
+      const int yy = n / p.ws, xx = n % p.ws;
+      float o[HD];
+      const float* lw = sm.lepe[kvs];
+#pragma unroll
+      for (int cc = 0; cc < HD; ++cc) o[cc] = fmaf(__uint_as_float(r[cc]), inv_l, lw[9 * HD + cc]);
+      const uint8_t* vt = sm.v[kvs];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ny = yy + ky - 1;
+        if (ny < 0 || ny >= p.hs) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int nx = xx + kx - 1;
+          if (nx < 0 || nx >= p.ws) continue;
+          const int nn = ny * p.ws + nx;
+          const float* wt = lw + (ky * 3 + kx) * HD;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float f[8];
+            unpack<__nv_bfloat16>(*sw64_chunk(vt, nn, q4), f);
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + q4 * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + q4 * 8 + 4);
+            o[q4 * 8 + 0] = fmaf(w0.x, f[0], o[q4 * 8 + 0]);
+            o[q4 * 8 + 1] = fmaf(w0.y, f[1], o[q4 * 8 + 1]);
+            o[q4 * 8 + 2] = fmaf(w0.z, f[2], o[q4 * 8 + 2]);
+            o[q4 * 8 + 3] = fmaf(w0.w, f[3], o[q4 * 8 + 3]);
+            o[q4 * 8 + 4] = fmaf(w1.x, f[4], o[q4 * 8 + 4]);
+            o[q4 * 8 + 5] = fmaf(w1.y, f[5], o[q4 * 8 + 5]);
+            o[q4 * 8 + 6] = fmaf(w1.z, f[6], o[q4 * 8 + 6]);
+            o[q4 * 8 + 7] = fmaf(w1.w, f[7], o[q4 * 8 + 7]);
+          }
+        }
+      }
+      const int tok = (c.wy * p.hs + yy) * p.W + c.wx * p.ws + xx;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)c.b * p.o_sb + (int64_t)tok * p.o_sl +
+                                            c.head * HD);
+#pragma unroll
+      for (int q4 = 0; q4 < 4; ++q4) {
+        float f[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) f[e] = o[q4 * 8 + e];
+        dst[q4] = pack<__nv_bfloat16>(f);
+      }
+      p.lse[((int64_t)c.b * p.heads + c.head) * p.L + tok] = m * p.scale + __logf(l);
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.kv_empty[kvs]);  // this warp is done with K/V/LePE of the group
+    }
+  }
+  // teardown
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+int make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t sb, int64_t sl, int bx,
+             int by) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t dims[4] = {(cuuint64_t)g.heads * HD, (cuuint64_t)g.W, (cuuint64_t)g.H,
+                              (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)sl * 2, (cuuint64_t)sl * 2 * g.W, (cuuint64_t)sb * 2};
+  const cuuint32_t box[4] = {HD, (cuuint32_t)bx, (cuuint32_t)by, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CSB200_OK;
+}
+
+template <int NK>
+int launch_fwd(const StripeGeom& g, const void* q, const void* k, const void* v,
+               const float* lepe_w, const float* lepe_b, void* out, float* lse, cudaStream_t st) {
+  const int bx = g.ws < TILE ? g.ws : TILE, by = TILE / bx;
+  CUtensorMap mq, mk, mv;
+  int rc;
+  if ((rc = make_map(&mq, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = make_map(&mk, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = make_map(&mv, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
+  FwdParams p;
+  p.B = g.B; p.W = g.W; p.L = g.L; p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx;
+  p.heads = g.heads; p.bx = bx; p.by = by;
+  p.groups = g.B * g.nwy * g.nwx * g.heads;
+  p.scale = g.scale;
+  p.scale_log2 = g.scale * 1.4426950408889634f;
+  p.lepe_w = lepe_w; p.lepe_b = lepe_b;
+  p.out = static_cast<__nv_bfloat16*>(out);
+  p.o_sb = g.o_sb; p.o_sl = g.o_sl;
+  p.lse = lse;
+
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    CSB200_CUDA(cudaGetDevice(&dev));
+    CSB200_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  // > half of the 227 KB so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
+  const int smem = (int)sizeof(Smem<NK>) + 1024 > 120 * 1024 ? (int)sizeof(Smem<NK>) + 1024 : 120 * 1024;
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[NK / 256]) {
+    CSB200_CUDA(cudaFuncSetAttribute(stripe_fwd_tc<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done[NK / 256] = true;
+  }
+  const int grid = p.groups < sm_count ? p.groups : sm_count;
+  stripe_fwd_tc<NK><<<grid, THREADS, smem, st>>>(mq, mk, mv, p);
+  return check_launch("stripe_fwd_tc");
+}
+
+}  // namespace
+
+// Shapes the tcgen05 engine tiles: bf16, stripes of exactly 128 or 256 tokens whose width divides
+// (or is a multiple of) 128, so that a 128-row tile is a rectangular TMA box.
+bool tc_fwd_supported(const StripeGeom& g, int dtype) {
+  if (dtype != CSB200_BF16) return false;
+  if (g.N != 128 && g.N != 256) return false;
+  if (!((g.ws <= TILE && TILE % g.ws == 0) || (g.ws % TILE == 0))) return false;
+  if (g.ws > 256 || g.hs > 256) return false;
+  return true;
+}
+bool tc_bwd_supported(const StripeGeom&, int) { return false; }
+
+int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
+           const float* lepe_b, void* out, float* lse, cudaStream_t st) {
+  return g.N == 128 ? launch_fwd<128>(g, q, k, v, lepe_w, lepe_b, out, lse, st)
+                    : launch_fwd<256>(g, q, k, v, lepe_w, lepe_b, out, lse, st);
+}
+
 }  // namespace csb200

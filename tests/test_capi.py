@@ -60,6 +60,24 @@ def test_shape_validation_mirrors_reference_failures():
         capi.check(-lib.csb200_stripe_attn_engine(ctypes.byref(_desc(w_sp=7)), 0), "engine")
 
 
+def test_engine_selection():
+    lib = capi.lib()
+    bf = dict(dtype=capi.BF16)
+    # config-3 stripes (N = 128 / 256, width dividing 128) go to the tcgen05 engine in forward
+    for kw in (dict(height=128, width=128, h_sp=128, w_sp=1), dict(height=64, width=64, h_sp=2, w_sp=64),
+               dict(height=32, width=32, h_sp=32, w_sp=8), dict(height=16, width=16, h_sp=16, w_sp=16)):
+        L = kw["height"] * kw["width"]
+        d = _desc(q_sb=L * 96, k_sb=L * 96, v_sb=L * 96, o_sb=L * 32, **bf, **kw)
+        assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_TCGEN05, kw
+        d.engine = capi.ENGINE_SIMT
+        assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_SIMT
+    # config-1 stripes (N = 49, 56, 98) and fp32 stay on the CUDA-core engine
+    d = _desc(height=14, width=14, h_sp=14, w_sp=7, q_sb=196 * 96, k_sb=196 * 96, v_sb=196 * 96, o_sb=196 * 32, **bf)
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_SIMT
+    d = _desc(height=16, width=16, h_sp=16, w_sp=16, q_sb=256 * 96, k_sb=256 * 96, v_sb=256 * 96, o_sb=256 * 32)
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_SIMT
+
+
 def test_simam_argument_validation():
     lib = capi.lib()
     one = ctypes.c_void_p(16)

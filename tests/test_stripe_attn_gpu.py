@@ -75,6 +75,22 @@ def test_random_shapes_match_oracle(case, dtype):
     assert rel_err(dw, w64.grad) < BWD_TOL[dtype] and rel_err(db, b64.grad) < BWD_TOL[dtype]
 
 
+@pytest.mark.parametrize("name", ["h_sw8_n128", "full_n256", "v_sw4_n128"])
+def test_tcgen05_and_simt_engines_agree_on_golden(name):
+    """The same bf16 inputs through both engines: each within tolerance of the reference golden,
+    and the saved log-sum-exp (consumed by backward) consistent between them."""
+    g = golden(f"attn_{name}.npz")
+    dim, reso, idx, split, heads, B, hs, ws = [int(v) for v in g["meta"]]
+    outs = {}
+    for engine in ("tcgen05", "simt"):
+        out, dqkv, dw, db = _run(torch.tensor(g["qkv"]), torch.tensor(g["lepe_w"]), torch.tensor(g["lepe_b"]),
+                                 torch.tensor(g["gout"]), (reso, reso), hs, ws, heads, torch.bfloat16, engine)
+        assert rel_err(out, g["out"]) < FWD_TOL[torch.bfloat16], engine
+        assert rel_err(dqkv, g["dqkv"]) < BWD_TOL[torch.bfloat16], engine
+        outs[engine] = out
+    assert rel_err(outs["tcgen05"], outs["simt"]) < 2 ** -7
+
+
 def test_two_branches_share_one_packed_buffer(no_tf32):
     # the CSWinBlock call: two orientations on the channel halves of one (B, L, 3C) buffer (C:360-363)
     torch.manual_seed(0)
