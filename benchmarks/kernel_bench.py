@@ -93,7 +93,11 @@ def bench_attn(engine):
 
             def fwd(i):
                 outs[i] = blk.attend(qs[i])
-            ms_f = time_ms(fwd, nbuf)
+
+            def fwd_nograd(i):
+                with torch.no_grad():
+                    blk.attend(qs[i])
+            ms_f = time_ms(fwd_nograd, nbuf)
             for i in range(nbuf):
                 fwd(i)
             params = [p for a in blk.attns for p in (a.get_v.weight, a.get_v.bias)]

@@ -11,14 +11,16 @@
 //   warp 1      single-thread tcgen05.mma issuer:  S = Q K^T (M128 x N{128,256} x K32) into TMEM,
 //               O = P V (M128 x N32 x K{128,256}) with P read from TMEM as the A operand
 //   warp 2      TMEM allocator
-//   warps 4-7 / 8-11   two softmax warpgroups ping-ponging on two TMEM buffers: one thread per query
+//   warps 4..   NWG softmax warpgroups (3 for N=128, 2 for N=256), each on its own TMEM buffer and
+//               taking every NWG-th tile, so loads, MMAs, exponentials and stores of different tiles
+//               overlap (the chain TMA -> S -> softmax -> PV -> epilogue is ~4 us long): one thread per query
 //               row reads its S row with tcgen05.ld, max / exp2 / sum in registers, writes bf16 P back
 //               over S with tcgen05.st; later reads O, scales by 1/sum, adds the LePE depthwise 3x3
 //               evaluated from the V tile that is already in shared memory (zero padding at the
 //               stripe border, C:244,263-265), and stores the row to out[b, token, head*32 ..] —
 //               windows2img (C:209-217) and the branch concat (C:363) are this store's address.
 //
-// TMEM map per buffer (256 columns): S fp32 [0,N) -> P bf16 [0,N/2) -> O fp32 [N/2, N/2+32).
+// TMEM map per buffer (N columns): S fp32 [0,N) -> P bf16 [0,N/2) -> O fp32 [N/2, N/2+32).
 
 #include <mutex>
 
@@ -47,8 +49,6 @@ constexpr int HD = 32;
 constexpr int TILE = 128;                   // query rows per tile == TMEM lanes
 constexpr int ROW_BYTES = HD * 2;           // 64 B per token row of one head
 constexpr int TILE_BYTES = TILE * ROW_BYTES;  // 8 KB
-constexpr int QS = 4;                       // Q ring stages
-constexpr int THREADS = 384;
 constexpr int LEPE_FLOATS = 10 * HD;        // 9 taps + bias for the 32 channels of a head
 
 struct FwdParams {
@@ -64,16 +64,29 @@ struct FwdParams {
   float* lse;
 };
 
+// Pipeline depths per stripe length: softmax warpgroups (== TMEM buffers), K/V ring, Q ring.
+template <int NK>
+struct Cfg;
+template <>
+struct Cfg<128> {
+  static constexpr int NWG = 3, KVS = 6, QS = 6;
+};
+template <>
+struct Cfg<256> {
+  static constexpr int NWG = 2, KVS = 4, QS = 8;
+};
+
 template <int NK>
 struct Smem {
   static constexpr int KV_BYTES = NK * ROW_BYTES;
+  static constexpr int NWG = Cfg<NK>::NWG, KVS = Cfg<NK>::KVS, QS = Cfg<NK>::QS;
   alignas(1024) uint8_t q[QS][TILE_BYTES];
-  alignas(1024) uint8_t k[2][KV_BYTES];
-  alignas(1024) uint8_t v[2][KV_BYTES];
-  alignas(16) float lepe[2][LEPE_FLOATS];  // [tap][c] then bias[c]
+  alignas(1024) uint8_t k[KVS][KV_BYTES];
+  alignas(1024) uint8_t v[KVS][KV_BYTES];
+  alignas(16) float lepe[KVS][LEPE_FLOATS];  // [tap][c] then bias[c]
   alignas(8) uint64_t q_full[QS], q_empty[QS];
-  uint64_t kv_full[2], kv_empty[2];
-  uint64_t s_full[2], p_full[2], o_full[2], buf_empty[2];
+  uint64_t kv_full[KVS], kv_empty[KVS];
+  uint64_t s_full[NWG], p_full[NWG], o_full[NWG], buf_empty[NWG];
   uint32_t tmem_base;
 };
 
@@ -97,12 +110,13 @@ __device__ __forceinline__ GroupCoord decode_group(const FwdParams& p, int g) {
 }
 
 template <int NK>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     stripe_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
                   const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
   constexpr int T = NK / TILE;          // query tiles per group
   constexpr int NBOX = NK / TILE;       // TMA boxes per K (or V) load
-  constexpr uint32_t P_COL = 0, O_COL = NK / 2, BUF_COLS = 256;
+  constexpr int NWG = Cfg<NK>::NWG, KVS = Cfg<NK>::KVS, QS = Cfg<NK>::QS;
+  constexpr uint32_t P_COL = 0, O_COL = NK / 2, BUF_COLS = NK;
   extern __shared__ uint8_t smem_raw[];
   Smem<NK>& sm = *reinterpret_cast<Smem<NK>*>(
       (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
@@ -119,9 +133,11 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(&sm.q_full[i], 1);
       mbar_init(&sm.q_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < KVS; ++i) {
       mbar_init(&sm.kv_full[i], 1);
       mbar_init(&sm.kv_empty[i], 4 * T);  // one arrival per softmax warp per tile of the group
+    }
+    for (int i = 0; i < NWG; ++i) {
       mbar_init(&sm.s_full[i], 1);
       mbar_init(&sm.p_full[i], 128);
       mbar_init(&sm.o_full[i], 1);
@@ -140,8 +156,8 @@ __global__ void __launch_bounds__(THREADS, 1)
     int it = 0;
     for (int gi = 0; gi < my_groups; ++gi) {
       const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
-      const int kvs = gi & 1;
-      mbar_wait(&sm.kv_empty[kvs], ((gi >> 1) & 1) ^ 1);
+      const int kvs = gi % KVS;
+      mbar_wait(&sm.kv_empty[kvs], ((gi / KVS) & 1) ^ 1);
       // LePE taps of this head -> smem as [tap][c], bias last (plain stores, released by the arrive)
       for (int i = lane; i < LEPE_FLOATS; i += 32) {
         const int tap = i / HD, ch = i % HD;
@@ -179,8 +195,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       constexpr uint32_t idesc_s = umma_idesc_bf16(NK, false, false);
       constexpr uint32_t idesc_pv = umma_idesc_bf16(HD, false, true);
       auto issue_pv = [&](int it) {
-        const int buf = it & 1, kvs = (it / T) & 1;
-        mbar_wait(&sm.p_full[buf], (it >> 1) & 1);
+        const int buf = it % NWG, kvs = (it / T) % KVS;
+        mbar_wait(&sm.p_full[buf], (it / NWG) & 1);
         fence_after_sync();
         const uint32_t d = tmem + buf * BUF_COLS + O_COL, a = tmem + buf * BUF_COLS + P_COL;
         const uint32_t vb = smem_u32(sm.v[kvs]);
@@ -189,60 +205,82 @@ __global__ void __launch_bounds__(THREADS, 1)
           umma_ts(d, a + 8 * k, umma_desc_sw64(vb + k * 1024), idesc_pv, k > 0);
         umma_commit(&sm.o_full[buf]);
       };
-      for (int it = 0; it < my_tiles; ++it) {
-        const int buf = it & 1, qs = it % QS, gi = it / T, kvs = gi & 1;
-        mbar_wait(&sm.q_full[qs], (it / QS) & 1);
-        if (it % T == 0) mbar_wait(&sm.kv_full[kvs], (gi >> 1) & 1);
-        mbar_wait(&sm.buf_empty[buf], ((it >> 1) & 1) ^ 1);
-        fence_after_sync();
-        const uint32_t qa = smem_u32(sm.q[qs]), kb = smem_u32(sm.k[kvs]);
+      // S of tile `it` is issued NWG-1 tiles ahead of the PV it feeds, so every warpgroup has work
+      constexpr int LAG = NWG - 1;
+      for (int it = 0; it < my_tiles + LAG; ++it) {
+        if (it < my_tiles) {
+          const int buf = it % NWG, qs = it % QS, gi = it / T, kvs = gi % KVS;
+          mbar_wait(&sm.q_full[qs], (it / QS) & 1);
+          if (it % T == 0) mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
+          mbar_wait(&sm.buf_empty[buf], ((it / NWG) & 1) ^ 1);
+          fence_after_sync();
+          const uint32_t qa = smem_u32(sm.q[qs]), kb = smem_u32(sm.k[kvs]);
 #pragma unroll
-        for (int k = 0; k < HD / 16; ++k)  // 16 channels per step: 32 B inside the swizzled row
-          umma_ss(tmem + buf * BUF_COLS, umma_desc_sw64(qa + k * 32), umma_desc_sw64(kb + k * 32),
-                  idesc_s, k > 0);
-        umma_commit(&sm.s_full[buf]);
-        umma_commit(&sm.q_empty[qs]);
-        if (it > 0) issue_pv(it - 1);
+          for (int k = 0; k < HD / 16; ++k)  // 16 channels per step: 32 B inside the swizzled row
+            umma_ss(tmem + buf * BUF_COLS, umma_desc_sw64(qa + k * 32), umma_desc_sw64(kb + k * 32),
+                    idesc_s, k > 0);
+          umma_commit(&sm.s_full[buf]);
+          umma_commit(&sm.q_empty[qs]);
+        }
+        if (it >= LAG) issue_pv(it - LAG);
       }
-      if (my_tiles > 0) issue_pv(my_tiles - 1);
     }
     __syncwarp();
   } else if (warp >= 4) {
     // ============================ softmax + epilogue warpgroups ============================
-    const int wg = (warp - 4) >> 2;                  // 0 / 1 == TMEM buffer
+    const int wg = (warp - 4) >> 2;                  // warpgroup == TMEM buffer
     const int row = ((warp & 3) << 5) | lane;        // query row inside the tile == TMEM lane
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + wg * BUF_COLS;
-    for (int it = wg; it < my_tiles; it += 2) {
-      const int gi = it / T, t = it % T, kvs = gi & 1;
-      const uint32_t use = (it >> 1) & 1;
+    constexpr int NCH = NK / 32;
+    for (int it = wg; it < my_tiles; it += NWG) {
+      const int gi = it / T, t = it % T, kvs = gi % KVS;
+      const uint32_t use = (it / NWG) & 1;
       const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
       mbar_wait(&sm.s_full[wg], use);
       fence_after_sync();
-      uint32_t r[32];
+      // Both sweeps double-buffer the TMEM reads: chunk ch+1 is in flight while chunk ch is consumed.
+      uint32_t ra[32], rb[32];
       float m = -INFINITY;
-#pragma unroll 1
-      for (int ch = 0; ch < NK / 32; ++ch) {
-        tmem_ld32(lane_base + ch * 32, r);
-        tmem_wait_ld();
+      tmem_ld32(lane_base, ra);
+      tmem_wait_ld();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(r[i]));
+      for (int ch = 0; ch < NCH; ch += 2) {
+        tmem_ld32(lane_base + (ch + 1) * 32, rb);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(ra[i]));
+        tmem_wait_ld();
+        if (ch + 2 < NCH) tmem_ld32(lane_base + (ch + 2) * 32, ra);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rb[i]));
+        tmem_wait_ld();
       }
       const float neg_m = -m * p.scale_log2;
-      float l = 0.f;
-#pragma unroll 1
-      for (int ch = 0; ch < NK / 32; ++ch) {
-        tmem_ld32(lane_base + ch * 32, r);
-        tmem_wait_ld();
+      float l0 = 0.f, l1 = 0.f;
+      auto exp_chunk = [&](const uint32_t (&r)[32], int ch) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
           const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
           const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
-          l += p0 + p1;
+          l0 += p0;
+          l1 += p1;
           pk[i] = pack_bf16x2(p0, p1);
         }
-        tmem_st16(lane_base + P_COL + ch * 16, pk);  // P over the S columns already consumed
+        tmem_st16(lane_base + P_COL + ch * 16, pk);  // P over S columns that were already consumed
+      };
+      tmem_ld32(lane_base, ra);
+      tmem_wait_ld();
+#pragma unroll
+      for (int ch = 0; ch < NCH; ch += 2) {
+        tmem_ld32(lane_base + (ch + 1) * 32, rb);
+        exp_chunk(ra, ch);
+        tmem_wait_ld();
+        if (ch + 2 < NCH) tmem_ld32(lane_base + (ch + 2) * 32, ra);
+        exp_chunk(rb, ch + 1);
+        tmem_wait_ld();
       }
+      const float l = l0 + l1;
+      uint32_t (&r)[32] = ra;
       tmem_wait_st();
       fence_before_sync();
       mbar_arrive(&sm.p_full[wg]);
@@ -258,7 +296,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 
       // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
       // barrier the MMA warp used (already complete; cannot advance before this warp's kv_empty)
-      mbar_wait(&sm.kv_full[kvs], (gi >> 1) & 1);
+      mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
       const float inv_l = 1.f / l;
       const int n = t * TILE + row;  // in-stripe index
       const int yy = n / p.ws, xx = n % p.ws;
@@ -315,6 +353,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
+// A token row of one head is 64 B.  With >= 2 heads the other half of the 128-B line is the
+// neighbouring head, which the neighbouring CTA wants at the same moment: promote to 128 B.  With a
+// single head it belongs to the other branch / operand: promoting would double the DRAM traffic.
 int make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t sb, int64_t sl, int bx,
              int by) {
   EncodeTiledFn enc = encode_tiled_fn();
@@ -326,7 +367,8 @@ int make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t sb, 
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   g.heads >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return CSB200_OK;
 }
@@ -365,7 +407,7 @@ int launch_fwd(const StripeGeom& g, const void* q, const void* k, const void* v,
     attr_done[NK / 256] = true;
   }
   const int grid = p.groups < sm_count ? p.groups : sm_count;
-  stripe_fwd_tc<NK><<<grid, THREADS, smem, st>>>(mq, mk, mv, p);
+  stripe_fwd_tc<NK><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(mq, mk, mv, p);
   return check_launch("stripe_fwd_tc");
 }
 

@@ -77,18 +77,23 @@ def test_random_shapes_match_oracle(case, dtype):
 
 @pytest.mark.parametrize("name", ["h_sw8_n128", "full_n256", "v_sw4_n128"])
 def test_tcgen05_and_simt_engines_agree_on_golden(name):
-    """The same bf16 inputs through both engines: each within tolerance of the reference golden,
-    and the saved log-sum-exp (consumed by backward) consistent between them."""
+    """The same bf16 inputs through both forward engines (forced, so neither can stand in for the
+    other): each within tolerance of the reference golden and of each other."""
     g = golden(f"attn_{name}.npz")
     dim, reso, idx, split, heads, B, hs, ws = [int(v) for v in g["meta"]]
+    qkv = torch.tensor(g["qkv"])
+    packed = torch.cat([qkv[0], qkv[1], qkv[2]], dim=-1).to(torch.bfloat16).cuda()
+    w, b = torch.tensor(g["lepe_w"]).cuda(), torch.tensor(g["lepe_b"]).cuda()
     outs = {}
-    for engine in ("tcgen05", "simt"):
-        out, dqkv, dw, db = _run(torch.tensor(g["qkv"]), torch.tensor(g["lepe_w"]), torch.tensor(g["lepe_b"]),
-                                 torch.tensor(g["gout"]), (reso, reso), hs, ws, heads, torch.bfloat16, engine)
-        assert rel_err(out, g["out"]) < FWD_TOL[torch.bfloat16], engine
-        assert rel_err(dqkv, g["dqkv"]) < BWD_TOL[torch.bfloat16], engine
-        outs[engine] = out
+    with torch.no_grad():
+        for engine in ("tcgen05", "simt"):
+            outs[engine] = csbF.cross_stripe_attention(packed, reso, reso, [csbF.Branch(hs, ws, heads, 0, dim)],
+                                                       (dim // heads) ** -0.5, [w, b], engine).float().cpu()
+            assert rel_err(outs[engine], g["out"]) < FWD_TOL[torch.bfloat16], engine
     assert rel_err(outs["tcgen05"], outs["simt"]) < 2 ** -7
+    with pytest.raises(RuntimeError, match="tcgen05 engine does not tile"):  # forced but untileable: refused
+        csbF.cross_stripe_attention(packed.float(), reso, reso, [csbF.Branch(hs, ws, heads, 0, dim)], 0.17, [w, b],
+                                    "tcgen05")
 
 
 def test_two_branches_share_one_packed_buffer(no_tf32):
