@@ -22,6 +22,10 @@ int simt_bwd(const StripeGeom& g, int dtype, const void* q, const void* k, const
              const float* lepe_w, const float* lepe_b, const void* out, const void* gout,
              const float* lse, void* dq, void* dk, void* dv, float* gw, float* gb, float* delta,
              float* partial, cudaStream_t st);
+// delta[b,h,l] = sum_c grad_out * (out - lepe): the row term of the softmax gradient
+int simt_delta(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
+               const float* lepe_b, const void* out, const void* gout, float* delta,
+               cudaStream_t st);
 // depthwise-3x3 weight / bias gradient (shared by both engines); partial: [wgrad_blocks][C'][10]
 int wgrad_blocks(const StripeGeom& g);
 template <typename T>
@@ -33,5 +37,9 @@ bool tc_fwd_supported(const StripeGeom& g, int dtype);
 bool tc_bwd_supported(const StripeGeom& g, int dtype);
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st);
+// dq, dk, dv from q, k, v, grad_out, lse and delta (stripe_attn_tc_bwd.cu)
+int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
+                const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
+                void* dv, cudaStream_t st);
 
 }  // namespace csb200

@@ -514,6 +514,23 @@ template int lepe_wgrad<float>(const StripeGeom&, const float*, const float*, fl
 template int lepe_wgrad<__nv_bfloat16>(const StripeGeom&, const __nv_bfloat16*,
                                        const __nv_bfloat16*, float*, float*, float*, cudaStream_t);
 
+int simt_delta(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
+               const float* lepe_b, const void* out, const void* gout, float* delta,
+               cudaStream_t st) {
+  const int tiles = (g.N + ROWS - 1) / ROWS;
+  const int64_t grid = (int64_t)g.B * g.nwy * g.nwx * g.heads * tiles;
+  if (grid > 0x7fffffffLL) return fail(CSB200_ERR_INVALID, "stripe_attn: grid too large");
+  if (dtype == CSB200_F32)
+    stripe_bwd_delta_simt<float><<<(unsigned)grid, ROWS, 0, st>>>(
+        g, static_cast<const float*>(v), lepe_w, lepe_b, static_cast<const float*>(out),
+        static_cast<const float*>(gout), delta, tiles);
+  else
+    stripe_bwd_delta_simt<__nv_bfloat16><<<(unsigned)grid, ROWS, 0, st>>>(
+        g, static_cast<const __nv_bfloat16*>(v), lepe_w, lepe_b,
+        static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(gout), delta, tiles);
+  return check_launch("stripe_bwd_delta_simt");
+}
+
 int simt_fwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,
              const float* lepe_w, const float* lepe_b, void* out, float* lse, cudaStream_t st) {
   return dtype == CSB200_F32 ? fwd_t<float>(g, q, k, v, lepe_w, lepe_b, out, lse, st)

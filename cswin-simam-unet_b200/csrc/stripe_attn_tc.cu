@@ -42,6 +42,28 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+constexpr int HD_ = 32;
+// A token row of one head is 64 B.  With >= 2 heads the other half of the 128-B line is the
+// neighbouring head, which the neighbouring CTA wants at the same moment: promote to 128 B.  With a
+// single head it belongs to the other branch / operand: promoting would double the DRAM traffic.
+int tc_make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t sb, int64_t sl, int bx,
+             int by) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  const cuuint64_t dims[4] = {(cuuint64_t)g.heads * HD_, (cuuint64_t)g.W, (cuuint64_t)g.H,
+                              (cuuint64_t)g.B};
+  const cuuint64_t strides[3] = {(cuuint64_t)sl * 2, (cuuint64_t)sl * 2 * g.W, (cuuint64_t)sb * 2};
+  const cuuint32_t box[4] = {HD_, (cuuint32_t)bx, (cuuint32_t)by, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
+                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                   g.heads >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CSB200_OK;
+}
+
+
 namespace {
 using namespace tc;
 
@@ -54,6 +76,7 @@ constexpr int LEPE_FLOATS = 10 * HD;        // 9 taps + bias for the 32 channels
 struct FwdParams {
   int B, W, L, hs, ws, nwy, nwx, heads;
   int bx, by;          // TMA box extent in x / y (bx * by == 128)
+  int ws_log2;         // N is a power of two, hence so are h_sp and w_sp
   int groups;          // B * nwy * nwx * heads
   float scale_log2;    // scale * log2(e)
   float scale;
@@ -84,6 +107,7 @@ struct Smem {
   alignas(1024) uint8_t k[KVS][KV_BYTES];
   alignas(1024) uint8_t v[KVS][KV_BYTES];
   alignas(16) float lepe[KVS][LEPE_FLOATS];  // [tap][c] then bias[c]
+  alignas(16) int4 coord[KVS];               // (image, first token of the stripe, head, -) per K/V stage
   alignas(8) uint64_t q_full[QS], q_empty[QS];
   uint64_t kv_full[KVS], kv_empty[KVS];
   uint64_t s_full[NWG], p_full[NWG], o_full[NWG], buf_empty[NWG];
@@ -164,6 +188,8 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         sm.lepe[kvs][i] = tap < 9 ? __ldg(p.lepe_w + (c.head * HD + ch) * 9 + tap)
                                   : __ldg(p.lepe_b + c.head * HD + ch);
       }
+      if (lane == 0)
+        sm.coord[kvs] = make_int4(c.b, (c.wy * p.hs) * p.W + c.wx * p.ws, c.head, 0);
       __syncwarp();
       if (lane == 0) {
         mbar_expect_tx(&sm.kv_full[kvs], 2 * Smem<NK>::KV_BYTES);
@@ -235,7 +261,6 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     for (int it = wg; it < my_tiles; it += NWG) {
       const int gi = it / T, t = it % T, kvs = gi % KVS;
       const uint32_t use = (it / NWG) & 1;
-      const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
       mbar_wait(&sm.s_full[wg], use);
       fence_after_sync();
       // Both sweeps double-buffer the TMEM reads: chunk ch+1 is in flight while chunk ch is consumed.
@@ -297,9 +322,10 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
       // barrier the MMA warp used (already complete; cannot advance before this warp's kv_empty)
       mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
+      const int4 gc = sm.coord[kvs];  // image, first token of the stripe, head
       const float inv_l = 1.f / l;
       const int n = t * TILE + row;  // in-stripe index
-      const int yy = n / p.ws, xx = n % p.ws;
+      const int yy = n >> p.ws_log2, xx = n & (p.ws - 1);
       float o[HD];
       const float* lw = sm.lepe[kvs];
 #pragma unroll
@@ -313,7 +339,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         for (int kx = 0; kx < 3; ++kx) {
           const int nx = xx + kx - 1;
           if (nx < 0 || nx >= p.ws) continue;
-          const int nn = ny * p.ws + nx;
+          const int nn = (ny << p.ws_log2) + nx;
           const float* wt = lw + (ky * 3 + kx) * HD;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -332,9 +358,9 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
           }
         }
       }
-      const int tok = (c.wy * p.hs + yy) * p.W + c.wx * p.ws + xx;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)c.b * p.o_sb + (int64_t)tok * p.o_sl +
-                                            c.head * HD);
+      const int tok = gc.y + yy * p.W + xx;
+      uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)gc.x * p.o_sb + (int64_t)tok * p.o_sl +
+                                            gc.z * HD);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
         float f[8];
@@ -342,7 +368,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         for (int e = 0; e < 8; ++e) f[e] = o[q4 * 8 + e];
         dst[q4] = pack<__nv_bfloat16>(f);
       }
-      p.lse[((int64_t)c.b * p.heads + c.head) * p.L + tok] = m * p.scale + __logf(l);
+      p.lse[((int64_t)gc.x * p.heads + gc.z) * p.L + tok] = m * p.scale + __logf(l);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.kv_empty[kvs]);  // this warp is done with K/V/LePE of the group
     }
@@ -353,38 +379,20 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-// A token row of one head is 64 B.  With >= 2 heads the other half of the 128-B line is the
-// neighbouring head, which the neighbouring CTA wants at the same moment: promote to 128 B.  With a
-// single head it belongs to the other branch / operand: promoting would double the DRAM traffic.
-int make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t sb, int64_t sl, int bx,
-             int by) {
-  EncodeTiledFn enc = encode_tiled_fn();
-  if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
-  const cuuint64_t dims[4] = {(cuuint64_t)g.heads * HD, (cuuint64_t)g.W, (cuuint64_t)g.H,
-                              (cuuint64_t)g.B};
-  const cuuint64_t strides[3] = {(cuuint64_t)sl * 2, (cuuint64_t)sl * 2 * g.W, (cuuint64_t)sb * 2};
-  const cuuint32_t box[4] = {HD, (cuuint32_t)bx, (cuuint32_t)by, 1};
-  const cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
-                   box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                   g.heads >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  return CSB200_OK;
-}
-
 template <int NK>
 int launch_fwd(const StripeGeom& g, const void* q, const void* k, const void* v,
                const float* lepe_w, const float* lepe_b, void* out, float* lse, cudaStream_t st) {
   const int bx = g.ws < TILE ? g.ws : TILE, by = TILE / bx;
   CUtensorMap mq, mk, mv;
   int rc;
-  if ((rc = make_map(&mq, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = make_map(&mk, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = make_map(&mv, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = tc_make_map(&mq, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = tc_make_map(&mk, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = tc_make_map(&mv, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
   FwdParams p;
   p.B = g.B; p.W = g.W; p.L = g.L; p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx;
   p.heads = g.heads; p.bx = bx; p.by = by;
+  p.ws_log2 = 0;
+  while ((1 << p.ws_log2) < g.ws) ++p.ws_log2;
   p.groups = g.B * g.nwy * g.nwx * g.heads;
   p.scale = g.scale;
   p.scale_log2 = g.scale * 1.4426950408889634f;
@@ -422,7 +430,7 @@ bool tc_fwd_supported(const StripeGeom& g, int dtype) {
   if (g.ws > 256 || g.hs > 256) return false;
   return true;
 }
-bool tc_bwd_supported(const StripeGeom&, int) { return false; }
+bool tc_bwd_supported(const StripeGeom& g, int dtype) { return tc_fwd_supported(g, dtype); }
 
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st) {

@@ -1,0 +1,455 @@
+// Stripe attention + LePE, tcgen05 / TMEM / TMA engine — backward (bf16 in, fp32 accumulate).
+//
+// Replaces what autograd records for LePEAttention.forward (C:271-298): the N x N probabilities
+// are recomputed from the saved log-sum-exp, never stored.  Per (image, stripe, head) group the
+// stripe's Q, K, V and grad_out tiles (N x 32 bf16) arrive by TMA, 64-byte swizzled, and serve
+// both as K-major operands (contraction over the 32 channels) and as MN-major operands
+// (contraction over tokens), so five GEMMs run on the tensor core with no transposes:
+//
+//   per key tile kt (128 keys = TMEM lanes), per 64-query half-block qh:
+//     S^T  = K_kt Q_qh^T          M128 x N64 x K32   (A, B K-major smem)      -> TMEM
+//     dP^T = V_kt dO_qh^T         M128 x N64 x K32                            -> TMEM
+//     convert warps, one thread per key row:
+//       P^T = exp2(S^T scale log2e - lse log2e);  dS^T = scale P^T (dP^T - delta)
+//       P^T, dS^T -> TMEM as bf16 (A operands);  dS^T -> smem, 128B-swizzled MN-major (A of dQ)
+//     dV_kt += P^T  dO_qh         M128 x N32 x K64   (A TMEM, B MN-major smem)
+//     dK_kt += dS^T Q_qh          M128 x N32 x K64
+//     every second qh:  dQ_qb += dS K_kt   M128 x N32 x K128 (A MN-major smem, B MN-major smem)
+//
+//   delta = rowsum(grad_out * (out - lepe)) comes from stripe_bwd_delta (CUDA cores, HBM-bound);
+//   the LePE transposed stencil on grad_out is added to dV in the epilogue from the grad_out tile
+//   in shared memory; the depthwise weight / bias gradients use the shared reduction kernels.
+//
+//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-7, 8-11 convert
+//   warpgroups (even / odd half-blocks, TMEM stage 0 / 1) | warps 12-15 epilogue warpgroup.
+//
+// TMEM (512 columns): stage s at 128 s: S^T [0,64) -> P^T bf16 [0,32); dP^T [64,128) -> dS^T bf16
+// [64,96).  Accumulators: (dV, dK) sets at 256 + 64 a (a = key-tile parity); dQ sets at 384 + 64 g
+// (g = group parity), 32 columns per 128-query block.
+
+#include "stripe_attn.cuh"
+#include "tc_common.cuh"
+
+namespace csb200 {
+namespace {
+using namespace tc;
+
+constexpr int HD = 32;
+constexpr int TILE = 128;
+constexpr int ROW_BYTES = HD * 2;
+constexpr int TILE_BYTES = TILE * ROW_BYTES;  // 8 KB
+constexpr int HALF = 64;                      // queries per convert iteration
+constexpr int DS_BLOCK_BYTES = TILE * 128;    // 128 key rows x 64 queries bf16 = 16 KB
+constexpr int THREADS = 512;
+
+struct BwdParams {
+  int B, W, L, hs, ws, nwy, nwx, heads;
+  int bx, by, ws_log2;
+  int groups;
+  float scale, scale_log2;
+  const float* lepe_w;  // [C'][9]
+  const float* lse;     // [B][heads][L]
+  const float* delta;   // [B][heads][L]
+  __nv_bfloat16 *dq, *dk, *dv;
+  int64_t dq_sb, dq_sl, dk_sb, dk_sl, dv_sb, dv_sl;
+};
+
+template <int NK>
+struct BCfg;
+template <>
+struct BCfg<128> {
+  static constexpr int GS = 4;  // group stages in shared memory
+};
+template <>
+struct BCfg<256> {
+  static constexpr int GS = 2;
+};
+
+template <int NK>
+struct BSmem {
+  static constexpr int GS = BCfg<NK>::GS;
+  static constexpr int OP_BYTES = NK * ROW_BYTES;
+  alignas(1024) uint8_t q[GS][OP_BYTES];
+  alignas(1024) uint8_t k[GS][OP_BYTES];
+  alignas(1024) uint8_t v[GS][OP_BYTES];
+  alignas(1024) uint8_t go[GS][OP_BYTES];
+  alignas(1024) uint8_t ds[2][2 * DS_BLOCK_BYTES];  // dS^T of one 128-query block, two 64-blocks
+  alignas(16) float lse2[GS][NK];                   // lse * log2(e)
+  alignas(16) float delta[GS][NK];
+  alignas(16) float lepe[GS][9 * HD];               // [tap][c]
+  alignas(16) int4 coord[GS];                       // image, first token of the stripe, head
+  alignas(8) uint64_t grp_full[GS], grp_empty[GS];
+  uint64_t sdp_full[2], conv_done[2], stage_free[2], ds_free[2];
+  uint64_t dvdk_full[2], dvdk_empty[2], dq_full[2], dq_empty[2];
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ const uint4* sw64_chunk(const uint8_t* tile, int n, int chunk) {
+  return reinterpret_cast<const uint4*>(tile + n * ROW_BYTES + ((chunk ^ ((n >> 1) & 3)) << 4));
+}
+
+template <int NK>
+__global__ void __launch_bounds__(THREADS, 1)
+    stripe_bwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
+                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_go,
+                  const BwdParams p) {
+  constexpr int T = NK / TILE;      // key tiles (and 128-query blocks) per group
+  constexpr int NH = NK / HALF;     // 64-query half-blocks per key tile
+  constexpr int NIT = T * NH;       // convert iterations per group (2 or 8: always even)
+  constexpr int GS = BCfg<NK>::GS;
+  constexpr uint32_t ACC_DVDK = 256, ACC_DQ = 384;
+  extern __shared__ uint8_t smem_raw[];
+  BSmem<NK>& sm = *reinterpret_cast<BSmem<NK>*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int my_groups = (p.groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_it = my_groups * NIT;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&tm_q);
+    prefetch_tensormap(&tm_k);
+    prefetch_tensormap(&tm_v);
+    prefetch_tensormap(&tm_go);
+    for (int i = 0; i < GS; ++i) {
+      mbar_init(&sm.grp_full[i], 1);
+      mbar_init(&sm.grp_empty[i], 4);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.sdp_full[i], 1);
+      mbar_init(&sm.conv_done[i], 128);
+      mbar_init(&sm.stage_free[i], 1);
+      mbar_init(&sm.ds_free[i], 1);
+      mbar_init(&sm.dvdk_full[i], 1);
+      mbar_init(&sm.dvdk_empty[i], 4);
+      mbar_init(&sm.dq_full[i], 1);
+      mbar_init(&sm.dq_empty[i], 4);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&sm.tmem_base, 512);
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ===================================== producer =========================================
+    for (int gi = 0; gi < my_groups; ++gi) {
+      int g = (int)blockIdx.x + gi * (int)gridDim.x;
+      const int head = g % p.heads;
+      g /= p.heads;
+      const int wx = g % p.nwx;
+      g /= p.nwx;
+      const int wy = g % p.nwy, b = g / p.nwy;
+      const int gs = gi % GS;
+      mbar_wait(&sm.grp_empty[gs], ((gi / GS) & 1) ^ 1);
+      const int tok0 = (wy * p.hs) * p.W + wx * p.ws;
+      const float* lse = p.lse + ((int64_t)b * p.heads + head) * p.L;
+      const float* dl = p.delta + ((int64_t)b * p.heads + head) * p.L;
+      for (int i = lane; i < NK; i += 32) {
+        const int tok = tok0 + (i >> p.ws_log2) * p.W + (i & (p.ws - 1));
+        sm.lse2[gs][i] = __ldg(lse + tok) * 1.4426950408889634f;
+        sm.delta[gs][i] = __ldg(dl + tok);
+      }
+      for (int i = lane; i < 9 * HD; i += 32)
+        sm.lepe[gs][i] = __ldg(p.lepe_w + (head * HD + i % HD) * 9 + i / HD);
+      if (lane == 0) sm.coord[gs] = make_int4(b, tok0, head, 0);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_expect_tx(&sm.grp_full[gs], 4 * BSmem<NK>::OP_BYTES);
+        const int x0 = wx * p.ws, y0 = wy * p.hs;
+#pragma unroll
+        for (int bxi = 0; bxi < T; ++bxi) {
+          const int dx = (p.ws > TILE) ? (bxi * TILE) % p.ws : 0;
+          const int dy = (p.ws > TILE) ? (bxi * TILE) / p.ws : bxi * p.by;
+          const int off = bxi * TILE_BYTES;
+          tma_load_4d(sm.k[gs] + off, &tm_k, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.q[gs] + off, &tm_q, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.v[gs] + off, &tm_v, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.go[gs] + off, &tm_go, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+        }
+      }
+      __syncwarp();
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      constexpr uint32_t idesc_sdp = umma_idesc_bf16(HALF, false, false);
+      constexpr uint32_t idesc_acc = umma_idesc_bf16(HD, false, true);   // A from TMEM, B MN-major
+      constexpr uint32_t idesc_dq = umma_idesc_bf16(HD, true, true);     // A MN-major smem
+      // MMAs that consume what the convert warps produced for iteration y
+      auto dependent = [&](int y) {
+        const int st = y & 1, gi = y / NIT, r = y % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
+        const int ktc = gi * T + kt, aset = ktc & 1;
+        mbar_wait(&sm.conv_done[st], (y >> 1) & 1);
+        if (qh == 0) mbar_wait(&sm.dvdk_empty[aset], ((ktc >> 1) & 1) ^ 1);
+        fence_after_sync();
+        const uint32_t sbase = tmem + st * 128;
+        const uint32_t gob = smem_u32(sm.go[gs]) + qh * (HALF * ROW_BYTES);
+        const uint32_t qb_ = smem_u32(sm.q[gs]) + qh * (HALF * ROW_BYTES);
+#pragma unroll
+        for (int k = 0; k < HALF / 16; ++k)  // dV += P^T dO : 16 queries per step
+          umma_ts(tmem + ACC_DVDK + aset * 64, sbase + 8 * k, umma_desc_sw64(gob + k * 1024),
+                  idesc_acc, (qh > 0 || k > 0));
+#pragma unroll
+        for (int k = 0; k < HALF / 16; ++k)  // dK += dS^T Q
+          umma_ts(tmem + ACC_DVDK + aset * 64 + 32, sbase + 64 + 8 * k,
+                  umma_desc_sw64(qb_ + k * 1024), idesc_acc, (qh > 0 || k > 0));
+        umma_commit(&sm.stage_free[st]);
+        if (qh & 1) {  // a 128-query block of dS^T is complete in shared memory
+          const int qb = qh >> 1, qbc = ktc * T + qb, dsb = qbc & 1;
+          if (kt == 0 && qb == 0) mbar_wait(&sm.dq_empty[gi & 1], ((gi >> 1) & 1) ^ 1);
+          fence_after_sync();
+          const uint32_t dsa = smem_u32(sm.ds[dsb]);
+          const uint32_t kb = smem_u32(sm.k[gs]) + kt * TILE_BYTES;
+#pragma unroll
+          for (int k = 0; k < TILE / 16; ++k)  // dQ += dS K : 16 keys per step
+            umma_ss(tmem + ACC_DQ + (gi & 1) * 64 + qb * 32,
+                    umma_desc_sw128_mn(dsa + k * 2048, DS_BLOCK_BYTES), umma_desc_sw64(kb + k * 1024),
+                    idesc_dq, (kt > 0 || k > 0));
+          umma_commit(&sm.ds_free[dsb]);
+        }
+        if (qh == NH - 1) {
+          umma_commit(&sm.dvdk_full[aset]);
+          if (kt == T - 1) umma_commit(&sm.dq_full[gi & 1]);
+        }
+      };
+      for (int x = 0; x < total_it + 1; ++x) {
+        if (x < total_it) {
+          const int st = x & 1, gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
+          if (r == 0) mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
+          mbar_wait(&sm.stage_free[st], ((x >> 1) & 1) ^ 1);
+          fence_after_sync();
+          const uint32_t ka = smem_u32(sm.k[gs]) + kt * TILE_BYTES;
+          const uint32_t va = smem_u32(sm.v[gs]) + kt * TILE_BYTES;
+          const uint32_t qb_ = smem_u32(sm.q[gs]) + qh * (HALF * ROW_BYTES);
+          const uint32_t gob = smem_u32(sm.go[gs]) + qh * (HALF * ROW_BYTES);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_ss(tmem + st * 128, umma_desc_sw64(ka + k * 32), umma_desc_sw64(qb_ + k * 32),
+                    idesc_sdp, k > 0);
+#pragma unroll
+          for (int k = 0; k < HD / 16; ++k)
+            umma_ss(tmem + st * 128 + 64, umma_desc_sw64(va + k * 32), umma_desc_sw64(gob + k * 32),
+                    idesc_sdp, k > 0);
+          umma_commit(&sm.sdp_full[st]);
+        }
+        if (x >= 1) dependent(x - 1);
+      }
+    }
+    __syncwarp();
+  } else if (warp >= 4 && warp < 12) {
+    // ================================ convert warpgroups ====================================
+    const int wg = (warp - 4) >> 2;             // == TMEM stage == parity of the half-block
+    const int j = ((warp & 3) << 5) | lane;     // key row inside the tile == TMEM lane
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + wg * 128;
+    for (int x = wg; x < total_it; x += 2) {
+      const int gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
+      const int qbc = (gi * T + kt) * T + (qh >> 1), dsb = qbc & 1;
+      mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);   // lse / delta visibility (already complete)
+      mbar_wait(&sm.ds_free[dsb], ((qbc >> 1) & 1) ^ 1);
+      mbar_wait(&sm.sdp_full[wg], (x >> 1) & 1);
+      fence_after_sync();
+      uint8_t* ds_row = sm.ds[dsb] + (qh & 1) * DS_BLOCK_BYTES + j * 128;
+      const float* lse2 = sm.lse2[gs] + qh * HALF;
+      const float* dlt = sm.delta[gs] + qh * HALF;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {  // 32 query columns at a time
+        uint32_t rs[32], rd[32];
+        tmem_ld32(lane_base + 32 * c, rs);
+        tmem_ld32(lane_base + 64 + 32 * c, rd);
+        tmem_wait_ld();
+        uint32_t pp[16], pd[16];
+#pragma unroll
+        for (int e4 = 0; e4 < 8; ++e4) {
+          const float4 l4 = *reinterpret_cast<const float4*>(lse2 + 32 * c + 4 * e4);  // broadcast
+          const float4 d4 = *reinterpret_cast<const float4*>(dlt + 32 * c + 4 * e4);
+          const float p0 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 0]), p.scale_log2, -l4.x));
+          const float p1 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 1]), p.scale_log2, -l4.y));
+          const float p2 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 2]), p.scale_log2, -l4.z));
+          const float p3 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 3]), p.scale_log2, -l4.w));
+          const float s0 = p0 * p.scale * (__uint_as_float(rd[4 * e4 + 0]) - d4.x);
+          const float s1 = p1 * p.scale * (__uint_as_float(rd[4 * e4 + 1]) - d4.y);
+          const float s2 = p2 * p.scale * (__uint_as_float(rd[4 * e4 + 2]) - d4.z);
+          const float s3 = p3 * p.scale * (__uint_as_float(rd[4 * e4 + 3]) - d4.w);
+          pp[2 * e4] = pack_bf16x2(p0, p1);
+          pp[2 * e4 + 1] = pack_bf16x2(p2, p3);
+          pd[2 * e4] = pack_bf16x2(s0, s1);
+          pd[2 * e4 + 1] = pack_bf16x2(s2, s3);
+        }
+        tmem_st16(lane_base + 16 * c, pp);       // P^T over S^T columns already consumed
+        tmem_st16(lane_base + 64 + 16 * c, pd);  // dS^T over dP^T columns already consumed
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {         // dS^T row -> smem, 128B swizzle: chunk ^ (row & 7)
+          const int chunk = 4 * c + q4;
+          *reinterpret_cast<uint4*>(ds_row + ((chunk ^ (j & 7)) << 4)) =
+              make_uint4(pd[4 * q4], pd[4 * q4 + 1], pd[4 * q4 + 2], pd[4 * q4 + 3]);
+        }
+      }
+      tmem_wait_st();
+      fence_before_sync();
+      fence_proxy_async_smem();
+      mbar_arrive(&sm.conv_done[wg]);
+    }
+  } else if (warp >= 12) {
+    // ================================== epilogue warpgroup ==================================
+    const int row = ((warp & 3) << 5) | lane;
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16);
+    for (int gi = 0; gi < my_groups; ++gi) {
+      const int gs = gi % GS;
+      mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
+      const int4 gc = sm.coord[gs];
+      const float* lw = sm.lepe[gs];
+      const uint8_t* got = sm.go[gs];
+#pragma unroll 1
+      for (int kt = 0; kt < T; ++kt) {
+        const int ktc = gi * T + kt, aset = ktc & 1;
+        mbar_wait(&sm.dvdk_full[aset], (ktc >> 1) & 1);
+        fence_after_sync();
+        uint32_t rv[32], rk[32];
+        tmem_ld32(lane_base + ACC_DVDK + aset * 64, rv);
+        tmem_ld32(lane_base + ACC_DVDK + aset * 64 + 32, rk);
+        tmem_wait_ld();
+        fence_before_sync();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.dvdk_empty[aset]);
+        const int n = kt * TILE + row;
+        const int yy = n >> p.ws_log2, xx = n & (p.ws - 1);
+        const int tok = gc.y + yy * p.W + xx;
+        float dv[HD];
+#pragma unroll
+        for (int cc = 0; cc < HD; ++cc) dv[cc] = __uint_as_float(rv[cc]);
+        // transposed LePE stencil: v_n receives w[tap] * grad_out[n - offset(tap)] (stripe-local)
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          const int ny = yy - ky + 1;
+          if (ny < 0 || ny >= p.hs) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            const int nx = xx - kx + 1;
+            if (nx < 0 || nx >= p.ws) continue;
+            const int nn = (ny << p.ws_log2) + nx;
+            const float* wt = lw + (ky * 3 + kx) * HD;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {
+              float f[8];
+              unpack<__nv_bfloat16>(*sw64_chunk(got, nn, q4), f);
+              const float4 w0 = *reinterpret_cast<const float4*>(wt + q4 * 8);
+              const float4 w1 = *reinterpret_cast<const float4*>(wt + q4 * 8 + 4);
+              dv[q4 * 8 + 0] = fmaf(w0.x, f[0], dv[q4 * 8 + 0]);
+              dv[q4 * 8 + 1] = fmaf(w0.y, f[1], dv[q4 * 8 + 1]);
+              dv[q4 * 8 + 2] = fmaf(w0.z, f[2], dv[q4 * 8 + 2]);
+              dv[q4 * 8 + 3] = fmaf(w0.w, f[3], dv[q4 * 8 + 3]);
+              dv[q4 * 8 + 4] = fmaf(w1.x, f[4], dv[q4 * 8 + 4]);
+              dv[q4 * 8 + 5] = fmaf(w1.y, f[5], dv[q4 * 8 + 5]);
+              dv[q4 * 8 + 6] = fmaf(w1.z, f[6], dv[q4 * 8 + 6]);
+              dv[q4 * 8 + 7] = fmaf(w1.w, f[7], dv[q4 * 8 + 7]);
+            }
+          }
+        }
+        uint4* dvp = reinterpret_cast<uint4*>(p.dv + (int64_t)gc.x * p.dv_sb + (int64_t)tok * p.dv_sl +
+                                              gc.z * HD);
+        uint4* dkp = reinterpret_cast<uint4*>(p.dk + (int64_t)gc.x * p.dk_sb + (int64_t)tok * p.dk_sl +
+                                              gc.z * HD);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float f[8], h[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = dv[q4 * 8 + e];
+            h[e] = __uint_as_float(rk[q4 * 8 + e]);  // scale already folded into dS^T
+          }
+          dvp[q4] = pack<__nv_bfloat16>(f);
+          dkp[q4] = pack<__nv_bfloat16>(h);
+        }
+      }
+      // dQ of the whole group
+      mbar_wait(&sm.dq_full[gi & 1], (gi >> 1) & 1);
+      fence_after_sync();
+#pragma unroll 1
+      for (int qb = 0; qb < T; ++qb) {
+        uint32_t rq[32];
+        tmem_ld32(lane_base + ACC_DQ + (gi & 1) * 64 + qb * 32, rq);
+        tmem_wait_ld();
+        const int n = qb * TILE + row;
+        const int tok = gc.y + (n >> p.ws_log2) * p.W + (n & (p.ws - 1));
+        uint4* dqp = reinterpret_cast<uint4*>(p.dq + (int64_t)gc.x * p.dq_sb + (int64_t)tok * p.dq_sl +
+                                              gc.z * HD);
+#pragma unroll
+        for (int q4 = 0; q4 < 4; ++q4) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(rq[q4 * 8 + e]);
+          dqp[q4] = pack<__nv_bfloat16>(f);
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm.dq_empty[gi & 1]);
+        mbar_arrive(&sm.grp_empty[gs]);  // every MMA of the group has completed (dq_full)
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+template <int NK>
+int launch_bwd(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
+               const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
+               void* dv, cudaStream_t st) {
+  const int bx = g.ws < TILE ? g.ws : TILE, by = TILE / bx;
+  CUtensorMap mq, mk, mv, mg;
+  int rc;
+  if ((rc = tc_make_map(&mq, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = tc_make_map(&mk, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = tc_make_map(&mv, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
+  if ((rc = tc_make_map(&mg, gout, g, g.o_sb, g.o_sl, bx, by)) != CSB200_OK) return rc;
+  BwdParams p;
+  p.B = g.B; p.W = g.W; p.L = g.L; p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx;
+  p.heads = g.heads; p.bx = bx; p.by = by;
+  p.ws_log2 = 0;
+  while ((1 << p.ws_log2) < g.ws) ++p.ws_log2;
+  p.groups = g.B * g.nwy * g.nwx * g.heads;
+  p.scale = g.scale;
+  p.scale_log2 = g.scale * 1.4426950408889634f;
+  p.lepe_w = lepe_w; p.lse = lse; p.delta = delta;
+  p.dq = static_cast<__nv_bfloat16*>(dq);
+  p.dk = static_cast<__nv_bfloat16*>(dk);
+  p.dv = static_cast<__nv_bfloat16*>(dv);
+  p.dq_sb = g.dq_sb; p.dq_sl = g.dq_sl; p.dk_sb = g.dk_sb; p.dk_sl = g.dk_sl;
+  p.dv_sb = g.dv_sb; p.dv_sl = g.dv_sl;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    CSB200_CUDA(cudaGetDevice(&dev));
+    CSB200_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int smem = (int)sizeof(BSmem<NK>) + 1024;  // > 113 KB: one CTA (all 512 TMEM columns) per SM
+  static bool attr_done[2] = {false, false};
+  if (!attr_done[NK / 256]) {
+    CSB200_CUDA(cudaFuncSetAttribute(stripe_bwd_tc<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    attr_done[NK / 256] = true;
+  }
+  const int grid = p.groups < sm_count ? p.groups : sm_count;
+  stripe_bwd_tc<NK><<<grid, THREADS, smem, st>>>(mq, mk, mv, mg, p);
+  return check_launch("stripe_bwd_tc");
+}
+
+}  // namespace
+
+int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
+                const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
+                void* dv, cudaStream_t st) {
+  static_assert(sizeof(BSmem<128>) + 1024 > 114 * 1024 && sizeof(BSmem<256>) + 1024 > 114 * 1024,
+                "two CTAs must not fit one SM");
+  static_assert(sizeof(BSmem<128>) + 1024 <= 227 * 1024 && sizeof(BSmem<256>) + 1024 <= 227 * 1024,
+                "shared memory budget");
+  return g.N == 128 ? launch_bwd<128>(g, q, k, v, gout, lepe_w, lse, delta, dq, dk, dv, st)
+                    : launch_bwd<256>(g, q, k, v, gout, lepe_w, lse, delta, dq, dk, dv, st);
+}
+
+}  // namespace csb200

@@ -122,6 +122,18 @@ __device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(4) << 61;                    // layout type SWIZZLE_64B
   return d;
 }
+// Shared-memory matrix descriptor for a 128-byte-swizzled MN-major tile: rows are the K index and
+// hold 64 MN elements (128 B); 8-row groups are 1024 B apart (SBO); successive 64-element MN blocks
+// are `lbo_bytes` apart.  Advance 2048 B per K=16 step.
+__device__ __forceinline__ uint64_t umma_desc_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;  // layout type SWIZZLE_128B
+  return d;
+}
 // Instruction descriptor, kind::f16, bf16 x bf16 -> fp32, dense, M = 128.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int n, bool a_mn_major, bool b_mn_major) {
   return (1u << 4)                                 // D format F32
@@ -169,5 +181,11 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();
+
+struct StripeGeom;
+// (channel, x, y, image) map over one token-major operand of a branch; box = (32, bx, by, 1),
+// 64-byte swizzle.  Defined in stripe_attn_tc.cu.
+int tc_make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t sb, int64_t sl, int bx,
+                int by);
 
 }  // namespace csb200

@@ -91,6 +91,13 @@ def test_tcgen05_and_simt_engines_agree_on_golden(name):
                                                        (dim // heads) ** -0.5, [w, b], engine).float().cpu()
             assert rel_err(outs[engine], g["out"]) < FWD_TOL[torch.bfloat16], engine
     assert rel_err(outs["tcgen05"], outs["simt"]) < 2 ** -7
+    # backward through each engine (forced): both within the stated gradient tolerance of the golden
+    for engine in ("tcgen05", "simt"):
+        out, dqkv, dw, db = _run(qkv, torch.tensor(g["lepe_w"]), torch.tensor(g["lepe_b"]), torch.tensor(g["gout"]),
+                                 (reso, reso), hs, ws, heads, torch.bfloat16, engine)
+        for i, nm in enumerate("qkv"):
+            assert rel_err(dqkv[i], g["dqkv"][i]) < BWD_TOL[torch.bfloat16], (engine, nm)
+        assert rel_err(dw, g["dw"]) < BWD_TOL[torch.bfloat16] and rel_err(db, g["db"]) < BWD_TOL[torch.bfloat16]
     with pytest.raises(RuntimeError, match="tcgen05 engine does not tile"):  # forced but untileable: refused
         csbF.cross_stripe_attention(packed.float(), reso, reso, [csbF.Branch(hs, ws, heads, 0, dim)], 0.17, [w, b],
                                     "tcgen05")
