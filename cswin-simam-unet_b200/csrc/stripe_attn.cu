@@ -152,13 +152,10 @@ extern "C" int csb200_stripe_attn_bwd(const csb200_stripe_desc* d, const void* q
       static_cast<char*>(workspace) + align_up((size_t)g.B * g.heads * g.L * sizeof(float), 256));
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (engine == CSB200_ENGINE_TCGEN05) {
-    using bf16 = __nv_bfloat16;
-    if ((rc = simt_delta(g, d->dtype, v, lepe_w, lepe_b, out, grad_out, delta, st)) != CSB200_OK)
+    if ((rc = lepe_bwd_prep(g, d->dtype, v, lepe_w, lepe_b, out, grad_out, delta, partial,
+                            grad_lepe_w, grad_lepe_b, st)) != CSB200_OK)
       return rc;
-    if ((rc = tc_bwd_core(g, q, k, v, grad_out, lepe_w, lse, delta, dq, dk, dv, st)) != CSB200_OK)
-      return rc;
-    return lepe_wgrad<bf16>(g, static_cast<const bf16*>(v), static_cast<const bf16*>(grad_out),
-                            grad_lepe_w, grad_lepe_b, partial, st);
+    return tc_bwd_core(g, q, k, v, grad_out, lepe_w, lse, delta, dq, dk, dv, st);
   }
   return simt_bwd(g, d->dtype, q, k, v, lepe_w, lepe_b, out, grad_out, lse, dq, dk, dv,
                   grad_lepe_w, grad_lepe_b, delta, partial, st);

@@ -22,15 +22,13 @@ int simt_bwd(const StripeGeom& g, int dtype, const void* q, const void* k, const
              const float* lepe_w, const float* lepe_b, const void* out, const void* gout,
              const float* lse, void* dq, void* dk, void* dv, float* gw, float* gb, float* delta,
              float* partial, cudaStream_t st);
-// delta[b,h,l] = sum_c grad_out * (out - lepe): the row term of the softmax gradient
-int simt_delta(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
-               const float* lepe_b, const void* out, const void* gout, float* delta,
-               cudaStream_t st);
-// depthwise-3x3 weight / bias gradient (shared by both engines); partial: [wgrad_blocks][C'][10]
+// One pass (both engines): delta[b,h,l] = sum_c grad_out * (out - lepe) — the row term of the
+// softmax gradient — plus the depthwise-3x3 weight / bias gradients (gw [C'][9], gb [C']) through
+// `partial` ([wgrad_blocks][C'][10] floats of scratch).
 int wgrad_blocks(const StripeGeom& g);
-template <typename T>
-int lepe_wgrad(const StripeGeom& g, const T* v, const T* gout, float* gw, float* gb,
-               float* partial, cudaStream_t st);
+int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
+                  const float* lepe_b, const void* out, const void* gout, float* delta,
+                  float* partial, float* gw, float* gb, cudaStream_t st);
 
 // ---- tcgen05 engine (stripe_attn_tc.cu) -------------------------------------------------------
 bool tc_fwd_supported(const StripeGeom& g, int dtype);

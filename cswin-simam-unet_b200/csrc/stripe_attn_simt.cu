@@ -16,6 +16,12 @@
 #include "stripe_attn.cuh"
 
 namespace csb200 {
+
+template <typename T>
+int lepe_bwd_prep_t(const StripeGeom& g, const T* v, const float* lepe_w, const float* lepe_b,
+                    const T* out, const T* gout, float* delta, float* partial, float* gw, float* gb,
+                    cudaStream_t st);
+
 namespace {
 
 constexpr int HD = 32;      // head_dim (dim // num_heads is 32 in every stage)
@@ -248,35 +254,6 @@ __global__ void __launch_bounds__(ROWS)
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, step 1: delta[b,h,l] = sum_c grad_out * (out - lepe)   (= sum_j P_ij dP_ij)
-// ------------------------------------------------------------------------------------------------
-template <typename T>
-__global__ void __launch_bounds__(ROWS)
-    stripe_bwd_delta_simt(StripeGeom g, const T* __restrict__ v, const float* __restrict__ lepe_w,
-                          const float* __restrict__ lepe_b, const T* __restrict__ out,
-                          const T* __restrict__ gout, float* __restrict__ delta, int tiles) {
-  __shared__ __align__(16) float s_w[9 * HD];
-  __shared__ float s_b[HD];
-  const Work w = decode_work(g, tiles);
-  const int n = w.tile * ROWS + threadIdx.x;
-  const int co = w.head * HD;
-  load_lepe_weights(s_w, s_b, lepe_w, lepe_b, w.head);
-  __syncthreads();
-  if (n >= g.N) return;
-  const int tok = token_of(g, w, n);
-  float lp[HD], o[HD], go[HD];
-#pragma unroll
-  for (int c = 0; c < HD; ++c) lp[c] = s_b[c];
-  lepe_stencil<T, false>(lp, v + (int64_t)w.b * g.v_sb + co, g.v_sl, g, w, n, s_w);
-  load_row<T>(out + (int64_t)w.b * g.o_sb + (int64_t)tok * g.o_sl + co, o);
-  load_row<T>(gout + (int64_t)w.b * g.o_sb + (int64_t)tok * g.o_sl + co, go);
-  float d = 0.f;
-#pragma unroll
-  for (int c = 0; c < HD; ++c) d = fmaf(go[c], o[c] - lp[c], d);
-  delta[((int64_t)w.b * g.heads + w.head) * g.L + tok] = d;
-}
-
-// ------------------------------------------------------------------------------------------------
 // backward, step 2: grad_q.  Thread = query row; K and V stream through smem.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
@@ -390,55 +367,117 @@ __global__ void __launch_bounds__(ROWS)
 }
 
 // ------------------------------------------------------------------------------------------------
-// backward, step 4: grad of the depthwise 3x3 weights and bias (get_v, C:244).
-//   gw[c][tap] = sum_tokens grad_out[l][c] * v[neighbour_tap(l)][c];  gb[c] = sum grad_out[l][c]
-// Deterministic two-stage reduction: per-CTA partials [blocks][C'][10] then a column sum.
-// blockDim = (32 channels, 8 token lanes); grid = (token tiles, C'/32).
+// backward, step 1 (both engines): ONE pass over grad_out, out and the 3x3 neighbourhood of v gives
+//   delta[b,h,l] = sum_c grad_out * (out - lepe)      (the row term of the softmax gradient), and
+//   per-CTA partials of the depthwise weight / bias gradients of get_v (C:244):
+//   gw[c][tap] = sum_tokens grad_out[l][c] * v[neighbour_tap(l)][c],  gb[c] = sum grad_out[l][c].
+// A CTA owns one head and a contiguous token range; 4 adjacent lanes cover the 32 channels of a
+// token (8 each, one 16/32-byte load), so a warp reads 8 whole token rows per step.  The 80
+// accumulators stay in registers across the whole range and are reduced once at the end
+// (shuffles -> shared memory -> partial[block][C'][10]); lepe_wgrad_final sums the partials in a
+// fixed order, so the result is deterministic.
 // ------------------------------------------------------------------------------------------------
-constexpr int WG_TOK = 512;  // tokens per CTA
+constexpr int PREP_THREADS = 256;
+constexpr int PREP_TOK_PER_ITER = PREP_THREADS / 4;  // 64 tokens per iteration
 
 template <typename T>
-__global__ void __launch_bounds__(256)
-    lepe_wgrad_partial(StripeGeom g, const T* __restrict__ v, const T* __restrict__ gout,
-                       float* __restrict__ partial) {
-  __shared__ float s_red[8][10][33];
-  const int cx = threadIdx.x & 31, ty = threadIdx.x >> 5;
-  const int c = blockIdx.y * 32 + cx;
-  const int cp = g.heads * HD;
+__device__ __forceinline__ void ld8(const T* p, float (&f)[8]);
+template <>
+__device__ __forceinline__ void ld8<float>(const float* p, float (&f)[8]) {
+  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
+  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+template <>
+__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
+  unpack<__nv_bfloat16>(__ldg(reinterpret_cast<const uint4*>(p)), f);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(PREP_THREADS)
+    lepe_bwd_prep(StripeGeom g, const T* __restrict__ v, const float* __restrict__ lepe_w,
+                  const float* __restrict__ lepe_b, const T* __restrict__ out,
+                  const T* __restrict__ gout, float* __restrict__ delta,
+                  float* __restrict__ partial, int tok_per_cta) {
+  __shared__ __align__(16) float s_w[10 * HD];       // [tap][c], bias last
+  __shared__ float s_part[PREP_THREADS / 32][10 * HD];
+  const int head = blockIdx.y, cp = g.heads * HD;
+  for (int i = threadIdx.x; i < 10 * HD; i += PREP_THREADS) {
+    const int tap = i / HD, c = i % HD;
+    s_w[i] = tap < 9 ? __ldg(lepe_w + (head * HD + c) * 9 + tap) : __ldg(lepe_b + head * HD + c);
+  }
+  __syncthreads();
+  const int cg = threadIdx.x & 3;              // which 8 of the head's 32 channels
+  const int co = head * HD + cg * 8;
   const int64_t total = (int64_t)g.B * g.L;
-  const int64_t t0 = (int64_t)blockIdx.x * WG_TOK;
-  float acc[10];
+  const int64_t t_begin = (int64_t)blockIdx.x * tok_per_cta;
+  float acc[10][8];
 #pragma unroll
-  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
-  for (int t = ty; t < WG_TOK; t += 8) {
-    const int64_t gt = t0 + t;
-    if (gt >= total) break;
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+
+  for (int it = threadIdx.x >> 2; it < tok_per_cta; it += PREP_TOK_PER_ITER) {
+    const int64_t gt = t_begin + it;
+    if (gt >= total) break;  // uniform over the 4 lanes of a token
     const int b = (int)(gt / g.L), l = (int)(gt % g.L);
-    const int y = l / g.W, x = l % g.W;
-    const int yy = y % g.hs, xx = x % g.ws;
-    const float go = to_f32(gout[(int64_t)b * g.o_sb + (int64_t)l * g.o_sl + c]);
-    acc[9] += go;
+    const int y = l / g.W, x = l % g.W, yy = y % g.hs, xx = x % g.ws;
+    float go[8], o[8], lp[8];
+    ld8<T>(gout + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, go);
+    ld8<T>(out + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, o);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      lp[e] = s_w[9 * HD + cg * 8 + e];
+      acc[9][e] += go[e];
+    }
+    const T* vb = v + (int64_t)b * g.v_sb + co;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      if (yy + ky - 1 < 0 || yy + ky - 1 >= g.hs) continue;
+      if (yy + ky - 1 < 0 || yy + ky - 1 >= g.hs) continue;  // zero padding at the STRIPE border
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         if (xx + kx - 1 < 0 || xx + kx - 1 >= g.ws) continue;
-        const int ln = (y + ky - 1) * g.W + (x + kx - 1);
-        acc[ky * 3 + kx] =
-            fmaf(go, to_f32(v[(int64_t)b * g.v_sb + (int64_t)ln * g.v_sl + c]), acc[ky * 3 + kx]);
+        float vn[8];
+        ld8<T>(vb + (int64_t)((y + ky - 1) * g.W + (x + kx - 1)) * g.v_sl, vn);
+        const float* wt = s_w + (ky * 3 + kx) * HD + cg * 8;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          lp[e] = fmaf(wt[e], vn[e], lp[e]);
+          acc[ky * 3 + kx][e] = fmaf(go[e], vn[e], acc[ky * 3 + kx][e]);
+        }
       }
     }
-  }
+    float d = 0.f;
 #pragma unroll
-  for (int i = 0; i < 10; ++i) s_red[ty][i][cx] = acc[i];
+    for (int e = 0; e < 8; ++e) d = fmaf(go[e], o[e] - lp[e], d);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    d += __shfl_xor_sync(0xffffffffu, d, 2);
+    if (cg == 0) delta[((int64_t)b * g.heads + head) * g.L + l] = d;
+  }
+  // reduce the 80 accumulators over the 8 token lanes of the warp, then over the 8 warps
+#pragma unroll
+  for (int t = 0; t < 10; ++t)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      float a = acc[t][e];
+      a += __shfl_xor_sync(0xffffffffu, a, 4);
+      a += __shfl_xor_sync(0xffffffffu, a, 8);
+      a += __shfl_xor_sync(0xffffffffu, a, 16);
+      acc[t][e] = a;
+    }
+  if ((threadIdx.x & 31) < 4) {
+#pragma unroll
+    for (int t = 0; t < 10; ++t)
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s_part[threadIdx.x >> 5][t * HD + cg * 8 + e] = acc[t][e];
+  }
   __syncthreads();
-  for (int i = threadIdx.x; i < 320; i += 256) {
-    const int tap = i / 32, cc = i % 32;
+  for (int i = threadIdx.x; i < 10 * HD; i += PREP_THREADS) {
     float a = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) a += s_red[r][tap][cc];
-    partial[((int64_t)blockIdx.x * cp + blockIdx.y * 32 + cc) * 10 + tap] = a;
+    for (int w = 0; w < PREP_THREADS / 32; ++w) a += s_part[w][i];
+    const int tap = i / HD, c = i % HD;
+    partial[((int64_t)blockIdx.x * cp + head * HD + c) * 10 + tap] = a;
   }
 }
 
@@ -480,55 +519,54 @@ int bwd_t(const StripeGeom& g, const void* q, const void* k, const void* v, cons
   const T* ot = static_cast<const T*>(out);
   const T* gt = static_cast<const T*>(gout);
   int rc;
-  stripe_bwd_delta_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(g, vt, lepe_w, lepe_b, ot, gt, delta,
-                                                            tiles);
-  if ((rc = check_launch("stripe_bwd_delta_simt")) != CSB200_OK) return rc;
+  if ((rc = lepe_bwd_prep_t<T>(g, vt, lepe_w, lepe_b, ot, gt, delta, partial, gw, gb, st)) != CSB200_OK)
+    return rc;
   stripe_bwd_dq_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(g, qt, kt, vt, gt, lse, delta,
                                                          static_cast<T*>(dq), tiles);
   if ((rc = check_launch("stripe_bwd_dq_simt")) != CSB200_OK) return rc;
   stripe_bwd_dkv_simt<T><<<(unsigned)grid, ROWS, 0, st>>>(
       g, qt, kt, vt, lepe_w, gt, lse, delta, static_cast<T*>(dk), static_cast<T*>(dv), tiles);
-  if ((rc = check_launch("stripe_bwd_dkv_simt")) != CSB200_OK) return rc;
-  return lepe_wgrad<T>(g, vt, gt, gw, gb, partial, st);
+  return check_launch("stripe_bwd_dkv_simt");
 }
 
 }  // namespace
 
+// tokens per CTA of lepe_bwd_prep: long ranges amortise the final reduction, but keep >= ~4 CTAs/SM
+static int prep_tok_per_cta(const StripeGeom& g) {
+  const int64_t total = (int64_t)g.B * g.L;
+  int tpc = 2048;
+  while (tpc > PREP_TOK_PER_ITER && (total + tpc - 1) / tpc * g.heads < 600) tpc >>= 1;
+  return tpc;
+}
 int wgrad_blocks(const StripeGeom& g) {
-  return (int)(((int64_t)g.B * g.L + WG_TOK - 1) / WG_TOK);
+  const int tpc = prep_tok_per_cta(g);
+  return (int)(((int64_t)g.B * g.L + tpc - 1) / tpc);
 }
 
 template <typename T>
-int lepe_wgrad(const StripeGeom& g, const T* v, const T* gout, float* gw, float* gb,
-               float* partial, cudaStream_t st) {
-  const int cp = g.heads * HD;
-  const int blocks = wgrad_blocks(g);
-  lepe_wgrad_partial<T><<<dim3(blocks, cp / 32), 256, 0, st>>>(g, v, gout, partial);
-  int rc = check_launch("lepe_wgrad_partial");
+int lepe_bwd_prep_t(const StripeGeom& g, const T* v, const float* lepe_w, const float* lepe_b,
+                    const T* out, const T* gout, float* delta, float* partial, float* gw, float* gb,
+                    cudaStream_t st) {
+  const int cp = g.heads * HD, blocks = wgrad_blocks(g);
+  lepe_bwd_prep<T><<<dim3(blocks, g.heads), PREP_THREADS, 0, st>>>(g, v, lepe_w, lepe_b, out, gout, delta,
+                                                                    partial, prep_tok_per_cta(g));
+  int rc = check_launch("lepe_bwd_prep");
   if (rc != CSB200_OK) return rc;
   lepe_wgrad_final<<<(cp * 10 + 255) / 256, 256, 0, st>>>(partial, blocks, cp, gw, gb);
   return check_launch("lepe_wgrad_final");
 }
-template int lepe_wgrad<float>(const StripeGeom&, const float*, const float*, float*, float*,
-                               float*, cudaStream_t);
-template int lepe_wgrad<__nv_bfloat16>(const StripeGeom&, const __nv_bfloat16*,
-                                       const __nv_bfloat16*, float*, float*, float*, cudaStream_t);
 
-int simt_delta(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
-               const float* lepe_b, const void* out, const void* gout, float* delta,
-               cudaStream_t st) {
-  const int tiles = (g.N + ROWS - 1) / ROWS;
-  const int64_t grid = (int64_t)g.B * g.nwy * g.nwx * g.heads * tiles;
-  if (grid > 0x7fffffffLL) return fail(CSB200_ERR_INVALID, "stripe_attn: grid too large");
-  if (dtype == CSB200_F32)
-    stripe_bwd_delta_simt<float><<<(unsigned)grid, ROWS, 0, st>>>(
-        g, static_cast<const float*>(v), lepe_w, lepe_b, static_cast<const float*>(out),
-        static_cast<const float*>(gout), delta, tiles);
-  else
-    stripe_bwd_delta_simt<__nv_bfloat16><<<(unsigned)grid, ROWS, 0, st>>>(
-        g, static_cast<const __nv_bfloat16*>(v), lepe_w, lepe_b,
-        static_cast<const __nv_bfloat16*>(out), static_cast<const __nv_bfloat16*>(gout), delta, tiles);
-  return check_launch("stripe_bwd_delta_simt");
+int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
+                  const float* lepe_b, const void* out, const void* gout, float* delta,
+                  float* partial, float* gw, float* gb, cudaStream_t st) {
+  using bf16 = __nv_bfloat16;
+  return dtype == CSB200_F32
+             ? lepe_bwd_prep_t<float>(g, static_cast<const float*>(v), lepe_w, lepe_b,
+                                      static_cast<const float*>(out), static_cast<const float*>(gout),
+                                      delta, partial, gw, gb, st)
+             : lepe_bwd_prep_t<bf16>(g, static_cast<const bf16*>(v), lepe_w, lepe_b,
+                                     static_cast<const bf16*>(out), static_cast<const bf16*>(gout),
+                                     delta, partial, gw, gb, st);
 }
 
 int simt_fwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,
