@@ -74,6 +74,40 @@ def bench_simam(only_layout=None, only_dtype=None, first=None):
             del xs, gs, ys
 
 
+def bench_layernorm():
+    # CSWin 512^2, B=32 norm sites: fp32 residual stream -> bf16 GEMM operand (autocast), and back
+    for rows, C in ((32 * 16384, 64), (32 * 4096, 128), (32 * 1024, 256), (32 * 256, 512)):
+        nbuf = max(2, -(-2 * L2_BYTES // (rows * C * 4)))
+        xs = [torch.randn(rows, C, device="cuda", requires_grad=True) for _ in range(nbuf)]
+        w = torch.randn(C, device="cuda", requires_grad=True)
+        b = torch.randn(C, device="cuda", requires_grad=True)
+        g = torch.randn(rows, C, device="cuda").bfloat16()
+        ys = [None] * nbuf
+
+        def fwd(i):
+            ys[i] = csbF.layer_norm(xs[i], w, b, 1e-5, torch.bfloat16)
+        ms_f = time_ms(fwd, nbuf)
+        for i in range(nbuf):
+            fwd(i)
+
+        def bwd(i):
+            torch.autograd.grad(ys[i], [xs[i], w, b], g, retain_graph=True)
+        ms_b = time_ms(bwd, nbuf)
+
+        def torch_fwd(i):
+            ys[i] = torch.nn.functional.layer_norm(xs[i], (C,), w, b).bfloat16()
+        ms_tf = time_ms(torch_fwd, nbuf)
+        for i in range(nbuf):
+            torch_fwd(i)
+        ms_tb = time_ms(bwd, nbuf)
+        for name, ms, bpe, ref in (("layernorm_fwd", ms_f, 6, ms_tf), ("layernorm_bwd", ms_b, 10, ms_tb)):
+            gbs = rows * C * bpe / ms / 1e6
+            print(json.dumps({"kernel": name, "rows": rows, "C": C, "io": "fp32 -> bf16", "us": round(ms * 1e3, 1),
+                              "algorithmic_GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3),
+                              "aten_us": round(ref * 1e3, 1)}), flush=True)
+        del xs, ys
+
+
 def bench_attn(engine):
     # config 3 per-call shapes: (reso, split, heads_total, C)
     stages = [("s1", 128, 1, 2, 64), ("s2", 64, 2, 4, 128), ("s3", 32, 8, 8, 256), ("s4", 16, 16, 16, 512)]
@@ -124,10 +158,15 @@ def bench_attn(engine):
 
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["simam", "attn"])
+    ap.add_argument("what", choices=["simam", "attn", "layernorm"])
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--layout", default=None, choices=["NCHW", "NLC"])
     ap.add_argument("--dtype", default=None, choices=["bfloat16", "float32"])
     ap.add_argument("--first", type=int, default=None, help="only the first K SimAM shapes")
     a = ap.parse_args()
-    bench_simam(a.layout, a.dtype, a.first) if a.what == "simam" else bench_attn(a.engine)
+    if a.what == "simam":
+        bench_simam(a.layout, a.dtype, a.first)
+    elif a.what == "layernorm":
+        bench_layernorm()
+    else:
+        bench_attn(a.engine)

@@ -1,0 +1,361 @@
+// Token-major LayerNorm forward / backward for sm_100a — the pre-norms of CSWinBlock (C:357, C:368),
+// Merge_Block (C:386), the stem (C:507) and the decoder norms (C:648, C:671).
+//
+// Why it is here: with C = 64..512 channels and up to 524 288 token rows per call (512^2, batch 32)
+// ATen's LayerNorm backward (GammaBetaBackward + grad_input) was the largest single item of the train
+// step (28 % of kernel time, profiles/r1_step_launches.md).  Both passes are HBM-bound streams:
+//   forward : read x, write y (+ 8 B/row of statistics)           bytes = rows*C*(sizeof x + sizeof y)
+//   backward: read x and grad_y, write grad_x                      bytes = rows*C*(sx + sgy + sgx)
+// Design: a persistent grid; each warp walks row groups with 16-byte loads — LPR = min(32, C*sizeof/16)
+// lanes per row, 32/LPR rows per warp step — statistics by xor-shuffles inside the row's lanes, exact
+// two-pass variance in registers.  The output type is independent of the input type, so under autocast
+// the fp32 residual stream is normalised straight into the bf16 operand of the next GEMM (no cast pass).
+// Backward keeps gamma/beta gradient accumulators in registers over all rows of the warp and reduces
+// them once (shuffles -> shared memory -> per-CTA partials -> fixed-order final sum: deterministic).
+
+#include "common.cuh"
+
+namespace csb200 {
+namespace {
+
+constexpr int LN_THREADS = 256;
+constexpr int LN_WARPS = LN_THREADS / 32;
+
+// convert NE fp32 values to TOut and store them contiguously (NE = 4 or 8)
+template <typename TOut, int NE>
+__device__ __forceinline__ void store_n(TOut* p, const float (&f)[NE]) {
+  if constexpr (sizeof(TOut) == 4) {
+#pragma unroll
+    for (int i = 0; i < NE; i += 4)
+      st_stream(p + i, make_uint4(__float_as_uint(f[i]), __float_as_uint(f[i + 1]),
+                                  __float_as_uint(f[i + 2]), __float_as_uint(f[i + 3])));
+  } else {
+    if constexpr (NE == 8) {
+      st_stream(p, make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]),
+                              pack_bf16x2(f[6], f[7])));
+    } else {
+      *reinterpret_cast<uint2*>(p) = make_uint2(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]));
+    }
+  }
+}
+template <typename TIn, int NE>
+__device__ __forceinline__ void load_n(const TIn* p, float (&f)[NE]) {
+  if constexpr (sizeof(TIn) == 4) {
+#pragma unroll
+    for (int i = 0; i < NE; i += 4) {
+      const uint4 u = ld_stream(p + i);
+      f[i] = __uint_as_float(u.x);
+      f[i + 1] = __uint_as_float(u.y);
+      f[i + 2] = __uint_as_float(u.z);
+      f[i + 3] = __uint_as_float(u.w);
+    }
+  } else {
+    if constexpr (NE == 8) {
+      float t[8];
+      unpack<__nv_bfloat16>(ld_stream(p), t);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = t[i];
+    } else {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+      f[0] = __uint_as_float(u.x << 16);
+      f[1] = __uint_as_float(u.x & 0xffff0000u);
+      f[2] = __uint_as_float(u.y << 16);
+      f[3] = __uint_as_float(u.y & 0xffff0000u);
+    }
+  }
+}
+
+template <int LPR>
+__device__ __forceinline__ float row_sum(float v) {
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// A lane holds CPL chunks of NE elements; chunk j of
+// a lane covers channels (j * LPR + lane_in_row) * NE .. + NE  (coalesced across the row's lanes).
+template <typename TIn, typename TOut, int LPR, int CPL, int NE>
+__global__ void __launch_bounds__(LN_THREADS)
+    layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
+                         const float* __restrict__ beta, TOut* __restrict__ y,
+                         float* __restrict__ stats, int64_t rows, float eps) {
+  constexpr int C = LPR * CPL * NE, RPW = 32 / LPR;
+  const int lane = threadIdx.x & 31, lr = lane % LPR, sub = lane / LPR;
+  float g[CPL][NE], b[CPL][NE];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      g[j][e] = __ldg(gamma + (j * LPR + lr) * NE + e);
+      b[j][e] = __ldg(beta + (j * LPR + lr) * NE + e);
+    }
+  const int64_t warp_global = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
+  const int64_t warp_count = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warp_count * RPW) {
+    const int64_t r = r0 + sub;
+    const bool ok = r < rows;
+    float v[CPL][NE];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      if (ok) load_n<TIn, NE>(x + r * C + (j * LPR + lr) * NE, v[j]);
+      else
+#pragma unroll
+        for (int e = 0; e < NE; ++e) v[j][e] = 0.f;
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) s += v[j][e];
+    const float mean = row_sum<LPR>(s) * (1.f / C);
+    float m2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const float t = v[j][e] - mean;
+        m2 = fmaf(t, t, m2);
+      }
+    const float rstd = rsqrtf(row_sum<LPR>(m2) * (1.f / C) + eps);
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float o[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) o[e] = fmaf((v[j][e] - mean) * rstd, g[j][e], b[j][e]);
+        store_n<TOut, NE>(y + r * C + (j * LPR + lr) * NE, o);
+      }
+      if (lr == 0) {
+        stats[2 * r] = mean;
+        stats[2 * r + 1] = rstd;
+      }
+    }
+  }
+}
+
+template <typename TIn, typename TGy, typename TGx, int LPR, int CPL, int NE>
+__global__ void __launch_bounds__(LN_THREADS)
+    layernorm_bwd_kernel(const TIn* __restrict__ x, const TGy* __restrict__ gy,
+                         const float* __restrict__ gamma, const float* __restrict__ stats,
+                         TGx* __restrict__ gx, float* __restrict__ partial, int64_t rows) {
+  constexpr int C = LPR * CPL * NE, RPW = 32 / LPR;
+  __shared__ float s_part[LN_WARPS][2 * C];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane % LPR, sub = lane / LPR;
+  float g[CPL][NE], dg[CPL][NE], db[CPL][NE];
+#pragma unroll
+  for (int j = 0; j < CPL; ++j)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+      g[j][e] = __ldg(gamma + (j * LPR + lr) * NE + e);
+      dg[j][e] = db[j][e] = 0.f;
+    }
+  const int64_t warp_global = (int64_t)blockIdx.x * LN_WARPS + warp;
+  const int64_t warp_count = (int64_t)gridDim.x * LN_WARPS;
+  for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warp_count * RPW) {
+    const int64_t r = r0 + sub;
+    const bool ok = r < rows;
+    float xv[CPL][NE], gv[CPL][NE];
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      if (ok) {
+        load_n<TIn, NE>(x + r * C + (j * LPR + lr) * NE, xv[j]);
+        load_n<TGy, NE>(gy + r * C + (j * LPR + lr) * NE, gv[j]);
+      } else {
+#pragma unroll
+        for (int e = 0; e < NE; ++e) xv[j][e] = gv[j][e] = 0.f;
+      }
+    }
+    const float mean = ok ? __ldg(stats + 2 * r) : 0.f, rstd = ok ? __ldg(stats + 2 * r + 1) : 0.f;
+    float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        const float xh = (xv[j][e] - mean) * rstd;
+        const float gg = gv[j][e] * g[j][e];
+        dg[j][e] = fmaf(gv[j][e], xh, dg[j][e]);  // zero rows contribute nothing
+        db[j][e] += gv[j][e];
+        s1 += gg;
+        s2 = fmaf(gg, xh, s2);
+        xv[j][e] = xh;
+        gv[j][e] = gg;
+      }
+    const float c1 = row_sum<LPR>(s1) * (1.f / C), c2 = row_sum<LPR>(s2) * (1.f / C);
+    if (ok) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float o[NE];
+#pragma unroll
+        for (int e = 0; e < NE; ++e) o[e] = rstd * (gv[j][e] - c1 - xv[j][e] * c2);
+        store_n<TGx, NE>(gx + r * C + (j * LPR + lr) * NE, o);
+      }
+    }
+  }
+  // gamma / beta gradients: over the RPW row slots of the warp, then over the warps of the CTA
+#pragma unroll
+  for (int j = 0; j < CPL; ++j)
+#pragma unroll
+    for (int e = 0; e < NE; ++e) {
+#pragma unroll
+      for (int o = 16; o >= LPR; o >>= 1) {
+        dg[j][e] += __shfl_xor_sync(0xffffffffu, dg[j][e], o);
+        db[j][e] += __shfl_xor_sync(0xffffffffu, db[j][e], o);
+      }
+    }
+  if (sub == 0) {
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+        s_part[warp][(j * LPR + lr) * NE + e] = dg[j][e];
+        s_part[warp][C + (j * LPR + lr) * NE + e] = db[j][e];
+      }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += LN_THREADS) {
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < LN_WARPS; ++w) a += s_part[w][i];
+    partial[(int64_t)blockIdx.x * 2 * C + i] = a;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+    layernorm_param_grad_final(const float* __restrict__ partial, int blocks, int C,
+                               float* __restrict__ ggamma, float* __restrict__ gbeta) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i >= 2 * C) return;
+  float a = 0.f;
+  for (int b = 0; b < blocks; ++b) a += partial[(int64_t)b * 2 * C + i];
+  if (i < C) ggamma[i] = a;
+  else gbeta[i - C] = a;
+}
+
+constexpr int LN_MAX_GRID = 148 * 8;  // persistent: 8 CTAs of 256 threads per B200 SM
+int ln_grid(int64_t rows, int rpw) {
+  const int64_t need = (rows + (int64_t)rpw * LN_WARPS - 1) / ((int64_t)rpw * LN_WARPS);
+  return (int)(need < LN_MAX_GRID ? (need > 0 ? need : 1) : LN_MAX_GRID);
+}
+
+// vectors of 16 B of the INPUT per row decide the tiling: LPR lanes per row, CPL chunks per lane
+template <typename TIn>
+bool ln_shape(int64_t C, int* lpr, int* cpl) {
+  constexpr int NE = 16 / sizeof(TIn);
+  if (C % NE != 0) return false;
+  const int64_t nv = C / NE;
+  if (nv == 8 || nv == 16 || nv == 32) { *lpr = (int)nv; *cpl = 1; return true; }
+  if (nv == 64) { *lpr = 32; *cpl = 2; return true; }
+  if (nv == 128 && NE == 4) { *lpr = 32; *cpl = 4; return true; }  // fp32 C = 512
+  return false;
+}
+
+#define LN_DISPATCH_SHAPE(CALL)                                  \
+  if (lpr == 8 && cpl == 1) { CALL(8, 1); }                      \
+  else if (lpr == 16 && cpl == 1) { CALL(16, 1); }               \
+  else if (lpr == 32 && cpl == 1) { CALL(32, 1); }               \
+  else if (lpr == 32 && cpl == 2) { CALL(32, 2); }               \
+  else { if constexpr (NE == 4) { CALL(32, 4); } }
+
+template <typename TIn, typename TOut>
+int ln_fwd_t(const void* x, const float* gamma, const float* beta, void* y, float* stats,
+             int64_t rows, int64_t C, float eps, cudaStream_t st) {
+  constexpr int NE = 16 / sizeof(TIn);
+  int lpr, cpl;
+  if (!ln_shape<TIn>(C, &lpr, &cpl))
+    return fail(CSB200_ERR_UNSUPPORTED, "layernorm: C=%lld is not tiled for this dtype", (long long)C);
+#define CALL(L, P)                                                                              \
+  layernorm_fwd_kernel<TIn, TOut, L, P, NE><<<ln_grid(rows, 32 / L), LN_THREADS, 0, st>>>(      \
+      static_cast<const TIn*>(x), gamma, beta, static_cast<TOut*>(y), stats, rows, eps)
+  LN_DISPATCH_SHAPE(CALL)
+#undef CALL
+  return check_launch("layernorm_fwd_kernel");
+}
+
+template <typename TIn, typename TGy, typename TGx>
+int ln_bwd_t(const void* x, const void* gy, const float* gamma, const float* stats, void* gx,
+             float* ggamma, float* gbeta, float* partial, int64_t rows, int64_t C,
+             cudaStream_t st) {
+  constexpr int NE = 16 / sizeof(TIn);
+  int lpr, cpl;
+  if (!ln_shape<TIn>(C, &lpr, &cpl))
+    return fail(CSB200_ERR_UNSUPPORTED, "layernorm: C=%lld is not tiled for this dtype", (long long)C);
+  const int grid = ln_grid(rows, 32 / lpr);
+#define CALL(L, P)                                                                       \
+  layernorm_bwd_kernel<TIn, TGy, TGx, L, P, NE><<<grid, LN_THREADS, 0, st>>>(            \
+      static_cast<const TIn*>(x), static_cast<const TGy*>(gy), gamma, stats,             \
+      static_cast<TGx*>(gx), partial, rows)
+  LN_DISPATCH_SHAPE(CALL)
+#undef CALL
+  int rc = check_launch("layernorm_bwd_kernel");
+  if (rc != CSB200_OK) return rc;
+  layernorm_param_grad_final<<<(int)((2 * C + 255) / 256), 256, 0, st>>>(partial, grid, (int)C,
+                                                                         ggamma, gbeta);
+  return check_launch("layernorm_param_grad_final");
+}
+
+bool ok_dtype(int d) { return d == CSB200_F32 || d == CSB200_BF16; }
+
+}  // namespace
+}  // namespace csb200
+
+using namespace csb200;
+using bf16 = __nv_bfloat16;
+
+extern "C" int csb200_layernorm_supported(int64_t channels, int x_dtype) {
+  int lpr, cpl;
+  if (x_dtype == CSB200_F32) return ln_shape<float>(channels, &lpr, &cpl) ? 1 : 0;
+  if (x_dtype == CSB200_BF16) return ln_shape<bf16>(channels, &lpr, &cpl) ? 1 : 0;
+  return 0;
+}
+
+extern "C" int csb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                                    float* stats, int64_t rows, int64_t channels, int x_dtype,
+                                    int y_dtype, float eps, void* stream) {
+  if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(y_dtype))
+    return fail(CSB200_ERR_INVALID, "layernorm_fwd: bad size or dtype");
+  if (rows == 0) return CSB200_OK;
+  if (!x || !gamma || !beta || !y || !stats) return fail(CSB200_ERR_INVALID, "layernorm_fwd: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == CSB200_F32)
+    return y_dtype == CSB200_F32 ? ln_fwd_t<float, float>(x, gamma, beta, y, stats, rows, channels, eps, st)
+                                 : ln_fwd_t<float, bf16>(x, gamma, beta, y, stats, rows, channels, eps, st);
+  return y_dtype == CSB200_F32 ? ln_fwd_t<bf16, float>(x, gamma, beta, y, stats, rows, channels, eps, st)
+                               : ln_fwd_t<bf16, bf16>(x, gamma, beta, y, stats, rows, channels, eps, st);
+}
+
+extern "C" size_t csb200_layernorm_bwd_workspace_bytes(int64_t rows, int64_t channels) {
+  (void)rows;
+  return (size_t)LN_MAX_GRID * 2 * (size_t)channels * sizeof(float) + 256;  // per-CTA partials
+}
+
+extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const float* gamma,
+                                    const float* stats, void* grad_x, float* grad_gamma,
+                                    float* grad_beta, void* workspace, size_t workspace_bytes,
+                                    int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
+                                    void* stream) {
+  if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(gy_dtype))
+    return fail(CSB200_ERR_INVALID, "layernorm_bwd: bad size or dtype");
+  if (!x || !grad_y || !gamma || !stats || !grad_x || !grad_gamma || !grad_beta || !workspace)
+    return fail(CSB200_ERR_INVALID, "layernorm_bwd: null pointer");
+  if (workspace_bytes < csb200_layernorm_bwd_workspace_bytes(rows, channels))
+    return fail(CSB200_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  if (rows == 0) {
+    CSB200_CUDA(cudaMemsetAsync(grad_gamma, 0, channels * sizeof(float), st));
+    CSB200_CUDA(cudaMemsetAsync(grad_beta, 0, channels * sizeof(float), st));
+    return CSB200_OK;
+  }
+  // grad_x has the type of x
+  if (x_dtype == CSB200_F32)
+    return gy_dtype == CSB200_F32
+               ? ln_bwd_t<float, float, float>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
+                                               partial, rows, channels, st)
+               : ln_bwd_t<float, bf16, float>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
+                                              partial, rows, channels, st);
+  return gy_dtype == CSB200_F32
+             ? ln_bwd_t<bf16, float, bf16>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
+                                           partial, rows, channels, st)
+             : ln_bwd_t<bf16, bf16, bf16>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
+                                          partial, rows, channels, st);
+}

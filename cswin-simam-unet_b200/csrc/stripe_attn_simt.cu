@@ -419,12 +419,17 @@ __global__ void __launch_bounds__(PREP_THREADS)
 
   for (int it = threadIdx.x >> 2; it < tok_per_cta; it += PREP_TOK_PER_ITER) {
     const int64_t gt = t_begin + it;
-    if (gt >= total) break;  // uniform over the 4 lanes of a token
-    const int b = (int)(gt / g.L), l = (int)(gt % g.L);
+    const bool valid = gt < total;  // no early exit: every lane takes part in the shuffles below
+    const int b = valid ? (int)(gt / g.L) : 0, l = valid ? (int)(gt % g.L) : 0;
     const int y = l / g.W, x = l % g.W, yy = y % g.hs, xx = x % g.ws;
     float go[8], o[8], lp[8];
-    ld8<T>(gout + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, go);
-    ld8<T>(out + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, o);
+    if (valid) {
+      ld8<T>(gout + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, go);
+      ld8<T>(out + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, o);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) go[e] = o[e] = 0.f;
+    }
 #pragma unroll
     for (int e = 0; e < 8; ++e) {
       lp[e] = s_w[9 * HD + cg * 8 + e];
@@ -433,7 +438,7 @@ __global__ void __launch_bounds__(PREP_THREADS)
     const T* vb = v + (int64_t)b * g.v_sb + co;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
-      if (yy + ky - 1 < 0 || yy + ky - 1 >= g.hs) continue;  // zero padding at the STRIPE border
+      if (!valid || yy + ky - 1 < 0 || yy + ky - 1 >= g.hs) continue;  // zero padding at the STRIPE border
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         if (xx + kx - 1 < 0 || xx + kx - 1 >= g.ws) continue;
@@ -452,7 +457,7 @@ __global__ void __launch_bounds__(PREP_THREADS)
     for (int e = 0; e < 8; ++e) d = fmaf(go[e], o[e] - lp[e], d);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
-    if (cg == 0) delta[((int64_t)b * g.heads + head) * g.L + l] = d;
+    if (cg == 0 && valid) delta[((int64_t)b * g.heads + head) * g.L + l] = d;
   }
   // reduce the 80 accumulators over the 8 token lanes of the warp, then over the 8 warps
 #pragma unroll

@@ -135,6 +135,60 @@ def simam(x: torch.Tensor, e_lambda: float = 1e-4, layout: str = "NCHW") -> torc
 
 
 # ------------------------------------------------------------------------------------------------
+# LayerNorm (token-major, last dimension)
+# ------------------------------------------------------------------------------------------------
+class _LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias, eps, out_dtype):
+        capi.require_cuda(x)
+        x = x.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+        nbytes = x.numel() * (x.element_size() + y.element_size())
+        with torch.cuda.device(x.device), _span("layernorm_fwd", nbytes):
+            capi.check(capi.lib().csb200_layernorm_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), _ptr(stats), rows, C,
+                                                       capi.dtype_code(x), capi.dtype_code(y), float(eps),
+                                                       _vp(capi.stream_of(x))), "csb200_layernorm_fwd")
+        ctx.save_for_backward(x, w, stats)
+        return y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        x, w, stats = ctx.saved_tensors
+        C = x.shape[-1]
+        rows = x.numel() // C
+        gy = gy.contiguous()
+        gx = torch.empty_like(x)
+        gw, gb = torch.empty_like(w), torch.empty_like(w)
+        lib = capi.lib()
+        nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
+        wsp = torch.empty(nws, dtype=torch.uint8, device=x.device)
+        nbytes = x.numel() * (2 * x.element_size() + gy.element_size())
+        with torch.cuda.device(x.device), _span("layernorm_bwd", nbytes):
+            capi.check(lib.csb200_layernorm_bwd(_ptr(x), _ptr(gy), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb),
+                                                _ptr(wsp), nws, rows, C, capi.dtype_code(x), capi.dtype_code(gy),
+                                                _vp(capi.stream_of(x))), "csb200_layernorm_bwd")
+        return gx, gw, gb, None, None
+
+
+def layer_norm_supported(x: torch.Tensor) -> bool:
+    return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and \
+        bool(capi.lib().csb200_layernorm_supported(x.shape[-1], capi.dtype_code(x)))
+
+
+def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5,
+               out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """LayerNorm over the last dimension in one HBM pass; ``out_dtype`` (default: x.dtype) lets the
+    fp32 residual stream be normalised straight into the bf16 operand of the following GEMM."""
+    return _LayerNormFn.apply(x, weight, bias, eps, out_dtype or x.dtype)
+
+
+# ------------------------------------------------------------------------------------------------
 # stripe attention
 # ------------------------------------------------------------------------------------------------
 class Branch:

@@ -13,8 +13,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, carafe_kernels,
-                      carafe_reassemble, tokens_as_image, _side)
+from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_norm,
+                      carafe_kernels, carafe_reassemble, image_as_tokens, tokens_as_image, _side)
 
 
 def _trunc_normal_linear_init(m: nn.Module):
@@ -111,7 +111,8 @@ class CSWinTransformer(nn.Module):
         """Encoder + bottleneck (C:625-650).  Skips are returned, not stashed on the module, so the
         model is re-entrant (CUDA graphs, overlapping micro-batches)."""
         # channels-last stem: the 7x7 conv then emits NHWC, which IS the token layout (no transpose copy)
-        x = self.pos_drop(self.stage1_conv_embed(x.contiguous(memory_format=torch.channels_last)))
+        stem = self.stage1_conv_embed
+        x = self.pos_drop(apply_norm(stem[2], stem[1](stem[0](x.contiguous(memory_format=torch.channels_last)))))
         skips: List[torch.Tensor] = []
         for blocks, merge in ((self.stage1, self.merge1), (self.stage2, self.merge2), (self.stage3, self.merge3)):
             for blk in blocks:
@@ -120,7 +121,7 @@ class CSWinTransformer(nn.Module):
             x = merge(x)
         for blk in self.stage4:
             x = blk(x)
-        return self.norm(x), skips
+        return apply_norm(self.norm, x), skips
 
     def forward_up_features(self, x, skips: Sequence[torch.Tensor]):
         """Decoder with skip connections (C:653-672)."""
@@ -133,7 +134,7 @@ class CSWinTransformer(nn.Module):
             x = fuse(torch.cat([skip, upsample(x)], dim=-1))
         for blk in self.stage_up1:
             x = blk(x)
-        return self.norm_up(x)
+        return apply_norm(self.norm_up, x, feeds_gemm=True)
 
     def up_x4(self, x):
         """CARAFE x4 -> 1x1 `out` conv (64->64) -> 1x1 `output` conv (64->classes)  (C:674-682).

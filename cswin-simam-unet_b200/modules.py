@@ -35,6 +35,20 @@ def image_as_tokens(img: torch.Tensor) -> torch.Tensor:
     return img.permute(0, 2, 3, 1).reshape(B, H * W, C)
 
 
+def apply_norm(norm: nn.Module, x: torch.Tensor, feeds_gemm: bool = False) -> torch.Tensor:
+    """Run a ``norm_layer`` instance.  A plain ``nn.LayerNorm`` over the channel dimension goes through
+    the fused csb200 kernel (parameters stay in the module: same ``state_dict``); under bf16 autocast a
+    norm whose only consumer is a Linear / conv (``feeds_gemm``) emits bf16 directly.  Anything else
+    (custom norm_layer, CPU tensors, untiled widths) runs the module as given."""
+    if type(norm) is nn.LayerNorm and x.is_cuda and len(norm.normalized_shape) == 1 \
+            and norm.elementwise_affine and norm.bias is not None and csbF.layer_norm_supported(x):
+        out_dtype = x.dtype
+        if feeds_gemm and torch.is_autocast_enabled("cuda"):
+            out_dtype = torch.get_autocast_dtype("cuda")
+        return csbF.layer_norm(x, norm.weight, norm.bias, norm.eps, out_dtype)
+    return norm(x)
+
+
 class SimAM(nn.Module):
     """Parameter-free SimAM attention (Yang et al., ICML 2021) as ONE fused kernel per direction.
 
@@ -176,9 +190,9 @@ class CSWinBlock(nn.Module):
         B, L, C = x.shape
         if L != self.patches_resolution ** 2:
             raise AssertionError("flatten img_tokens has wrong size")
-        attended = self.proj(self.attend(self.qkv(self.norm1(x))))
+        attended = self.proj(self.attend(self.qkv(apply_norm(self.norm1, x, feeds_gemm=True))))
         x = x + self.drop_path(attended)  # proj_drop exists but is never applied in the reference (C:366-367)
-        return x + self.drop_path(self.mlp(self.norm2(x)))
+        return x + self.drop_path(self.mlp(apply_norm(self.norm2, x, feeds_gemm=True)))
 
 
 class Merge_Block(nn.Module):
@@ -191,7 +205,7 @@ class Merge_Block(nn.Module):
 
     def forward(self, x):
         side = _side(x.shape[1])
-        return self.norm(image_as_tokens(self.conv(tokens_as_image(x, side, side))))
+        return apply_norm(self.norm, image_as_tokens(self.conv(tokens_as_image(x, side, side))))
 
 
 def carafe_kernels(img: torch.Tensor, down: nn.Conv2d, encoder: nn.Conv2d, up: int) -> torch.Tensor:

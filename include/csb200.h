@@ -77,6 +77,25 @@ CSB200_API int csb200_simam_bwd(const void* x, const void* grad_y, const float* 
                      float e_lambda, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Token-major LayerNorm over the last dimension — the pre-norms at the CSWinBlock call site (C:357,
+ * C:368) and C:386, C:507, C:648, C:671: y = (x - mean) * rstd * gamma + beta, biased variance.
+ * x: [rows][channels] contiguous, type x_dtype; y has its own type (fp32 residual stream -> bf16 GEMM
+ * operand in one pass); gamma / beta / their gradients fp32; stats: float[2*rows] = {mean, rstd}.
+ * grad_x has the type of x.  csb200_layernorm_supported tells whether `channels` is tiled (16-byte
+ * vectors per row in {8,16,32,64,128}); otherwise the functions return CSB200_ERR_UNSUPPORTED.
+ * ---------------------------------------------------------------------------------------------- */
+CSB200_API int csb200_layernorm_supported(int64_t channels, int x_dtype);
+CSB200_API int csb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
+                                    float* stats, int64_t rows, int64_t channels, int x_dtype,
+                                    int y_dtype, float eps, void* stream);
+CSB200_API size_t csb200_layernorm_bwd_workspace_bytes(int64_t rows, int64_t channels);
+CSB200_API int csb200_layernorm_bwd(const void* x, const void* grad_y, const float* gamma,
+                                    const float* stats, void* grad_x, float* grad_gamma,
+                                    float* grad_beta, void* workspace, size_t workspace_bytes,
+                                    int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
+                                    void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Cross-shaped stripe attention with LePE — replaces the body of LePEAttention.forward (C:271-298)
  * including im2cswin (C:248-254), get_lepe (C:256-269), img2windows / windows2img (C:199-217) and, on
  * the caller's side, the torch.cat of the two branches (C:363): q/k/v are read in place from the

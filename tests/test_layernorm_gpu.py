@@ -1,0 +1,74 @@
+"""GPU: fused token-major LayerNorm (csb200_layernorm_fwd / _bwd) vs torch.nn.functional.layer_norm
+evaluated in fp64 on the same inputs.  fp32 <= 1e-5 relative; bf16 output / bf16 incoming gradient
+<= 2^-7 (one bf16 rounding of the result)."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import rel_err
+import cswin_simam_unet_b200 as pkg
+from cswin_simam_unet_b200 import functional as csbF, modules
+
+pytestmark = pytest.mark.gpu
+
+# (rows..., C): every tiling (8/16/32/64/128 vectors per row), ragged row counts, CSWin widths
+SHAPES = [(2, 49, 64), (3, 100, 32), (2, 3136, 64), (1, 784, 128), (2, 196, 256), (2, 49, 512), (5, 7, 128), (1, 1, 64)]
+
+
+@pytest.mark.parametrize("x_dtype,out_dtype", [(torch.float32, torch.float32), (torch.float32, torch.bfloat16),
+                                               (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("shape", SHAPES)
+def test_layernorm_matches_fp64_reference(shape, x_dtype, out_dtype):
+    torch.manual_seed(sum(shape))
+    C = shape[-1]
+    x = (torch.randn(shape) * 2 + 0.3).to(x_dtype)
+    w, b = torch.randn(C) * 0.5 + 1, torch.randn(C) * 0.2
+    gy = torch.randn(shape).to(out_dtype)
+    xd = x.cuda().requires_grad_(True)
+    wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    if not csbF.layer_norm_supported(xd):
+        pytest.skip("width not tiled for this dtype")
+    y = csbF.layer_norm(xd, wd, bd, 1e-5, out_dtype)
+    y.backward(gy.cuda())
+    x64 = x.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    F.layer_norm(x64, (C,), w64, b64, 1e-5).backward(gy.double())
+    tol = 1e-5 if (x_dtype == torch.float32 and out_dtype == torch.float32) else 2 ** -7
+    assert y.dtype == out_dtype and xd.grad.dtype == x_dtype
+    assert rel_err(y.float().cpu(), F.layer_norm(x.double(), (C,), w.double(), b.double(), 1e-5)) < tol
+    assert rel_err(xd.grad.float().cpu(), x64.grad) < tol
+    assert rel_err(wd.grad.cpu(), w64.grad) < max(tol, 2e-5)
+    assert rel_err(bd.grad.cpu(), b64.grad) < max(tol, 2e-5)
+
+
+def test_apply_norm_routes_and_falls_back():
+    ln = torch.nn.LayerNorm(64).cuda()
+    x = torch.randn(2, 50, 64, device="cuda")
+    n0 = pkg.capi.launch_count()
+    y = modules.apply_norm(ln, x)
+    assert pkg.capi.launch_count() == n0 + 1 and rel_err(y.cpu(), ln(x).cpu()) < 1e-5
+    with torch.autocast("cuda", dtype=torch.bfloat16):
+        assert modules.apply_norm(ln, x, feeds_gemm=True).dtype == torch.bfloat16
+        assert modules.apply_norm(ln, x).dtype == torch.float32
+    odd = torch.nn.LayerNorm(40).cuda()  # 40 fp32 channels = 10 vectors: not tiled -> module itself
+    xo = torch.randn(3, 40, device="cuda")
+    n0 = pkg.capi.launch_count()
+    assert torch.equal(modules.apply_norm(odd, xo), odd(xo)) and pkg.capi.launch_count() == n0
+    ident = torch.nn.Identity()
+    assert modules.apply_norm(ident, x) is x
+
+
+def test_layernorm_large_rows_deterministic():
+    torch.manual_seed(0)
+    x = torch.randn(32 * 4096, 128, device="cuda", requires_grad=True)
+    w = torch.randn(128, device="cuda", requires_grad=True)
+    b = torch.randn(128, device="cuda", requires_grad=True)
+    g = torch.randn_like(x)
+    outs = []
+    for _ in range(2):
+        x.grad = w.grad = b.grad = None
+        csbF.layer_norm(x, w, b).backward(g)
+        outs.append((x.grad.clone(), w.grad.clone(), b.grad.clone()))
+    assert all(torch.equal(a, c) for a, c in zip(*outs))  # fixed-order reductions
+    ref = F.layer_norm(x.detach().double(), (128,), w.detach().double(), b.detach().double())
+    assert rel_err(csbF.layer_norm(x, w, b).detach().cpu(), ref.cpu()) < 1e-5
