@@ -10,7 +10,7 @@ BCELoss on probabilities).  No ``.item()`` is called here: the reference's five 
 (C:797-806) are the caller's choice, not the step's.
 """
 import contextlib
-from typing import Optional, Tuple
+from typing import Tuple
 
 import torch
 import torch.nn.functional as F
@@ -40,13 +40,24 @@ def bce_from_logits_as_probabilities(probs: torch.Tensor, target: torch.Tensor) 
 
 
 class TrainStep:
-    """One optimisation step; returns the loss as a device tensor (no host sync)."""
+    """One optimisation step; returns the loss as a device tensor (no host sync).
+
+    ``cuda_graph=True`` captures zero_grad -> forward -> loss -> backward -> [all-reduce] -> optimizer
+    into ONE CUDA graph on the first call and replays it afterwards: the step is
+    ~5000 kernel launches, which the Python host cannot issue as fast as a B200 executes them.  Requires
+    static shapes, a capturable optimizer (``AdamW(..., capturable=True)``) and no host syncs inside the
+    model (true for the models of this package).  The lazy-initialisation warm-up runs that capture
+    needs are undone (parameters, buffers and optimizer state are restored), so the first replay is
+    step 1 of training exactly as in eager mode.
+    """
 
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, precision: str = "bf16",
-                 reducer=None):
+                 reducer=None, cuda_graph: bool = False):
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.model, self.optimizer, self.precision, self.reducer = model, optimizer, precision, reducer
+        self.cuda_graph = cuda_graph
+        self._graph = None
 
     def _autocast(self, device_type: str):
         if self.precision == "bf16":
@@ -59,6 +70,46 @@ class TrainStep:
         return bce_from_logits_as_probabilities(probs, masks)
 
     def __call__(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
+        if self.cuda_graph:
+            return self._graph_step(images, masks)
+        return self._eager_step(images, masks)
+
+    # ---- CUDA-graph path -----------------------------------------------------------------------
+    def _graph_step(self, images, masks):
+        if self._graph is None:
+            self._capture(images, masks)
+        self._x.copy_(images, non_blocking=True)
+        self._y.copy_(masks, non_blocking=True)
+        self._graph.replay()
+        return self._loss
+
+    def _capture(self, images, masks):
+        dev = next(self.model.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("cuda_graph=True needs the model on a CUDA device")
+        self._x, self._y = images.to(dev, copy=True), masks.to(dev, copy=True)
+        images = self._x
+        saved_model = {k: v.clone() for k, v in self.model.state_dict().items()}
+        side = torch.cuda.Stream(device=images.device)
+        side.wait_stream(torch.cuda.current_stream(images.device))
+        with torch.cuda.stream(side):
+            for _ in range(3):  # lazy init: cuBLAS/cuDNN handles and autotune, optimizer state
+                self._eager_step(self._x, self._y)
+        torch.cuda.current_stream(images.device).wait_stream(side)
+        # undo the warm-up: weights / buffers back, optimizer moments and step counters to zero
+        with torch.no_grad():
+            self.model.load_state_dict(saved_model)
+            for st in self.optimizer.state.values():
+                for v in st.values():
+                    if torch.is_tensor(v):
+                        v.zero_()
+        if self.reducer is None:
+            self.optimizer.zero_grad(set_to_none=True)
+        self._graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self._graph):
+            self._loss = self._eager_step(self._x, self._y)
+
+    def _eager_step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         if self.reducer is not None:
             self.reducer.begin_step()  # zeroes the flat gradient buckets (== zero_grad)
         else:

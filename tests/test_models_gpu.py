@@ -139,3 +139,21 @@ def test_bf16_train_step_runs_and_decreases_loss():
     x, y = pkg.synthetic_batch(4, 128, "cuda", seed=1)
     losses = [step(x, y).item() for _ in range(6)]
     assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+def test_cuda_graph_step_matches_eager_step():
+    """TrainStep(cuda_graph=True): same loss trajectory as the eager step, from the same start (the
+    capture warm-up must leave weights and optimizer state untouched), host batches accepted."""
+    losses = {}
+    for mode in (False, True):
+        torch.manual_seed(0)
+        net = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], simam=True).cuda()
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=mode)
+        step = pkg.TrainStep(net, opt, precision="bf16", cuda_graph=mode)
+        run = []
+        for it in range(4):
+            x, y = pkg.synthetic_batch(2, 64, "cpu", seed=it, pin=True)
+            run.append(step(x if mode else x.cuda(), y if mode else y.cuda()).item())
+        losses[mode] = run
+    assert np.allclose(losses[True], losses[False], rtol=2e-3), losses
+    assert losses[True][-1] != losses[True][0]
