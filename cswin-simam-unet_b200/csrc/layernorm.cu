@@ -220,18 +220,23 @@ __global__ void __launch_bounds__(LN_THREADS)
   }
 }
 
+// one warp per output: lanes stride over the per-CTA partials (coalescing is across neighbouring
+// warps), fixed summation order -> deterministic
 __global__ void __launch_bounds__(256)
     layernorm_param_grad_final(const float* __restrict__ partial, int blocks, int C,
                                float* __restrict__ ggamma, float* __restrict__ gbeta) {
-  const int i = blockIdx.x * 256 + threadIdx.x;
+  const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= 2 * C) return;
   float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += partial[(int64_t)b * 2 * C + i];
-  if (i < C) ggamma[i] = a;
-  else gbeta[i - C] = a;
+  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * 2 * C + i];
+  a = warp_sum(a);
+  if (lane == 0) {
+    if (i < C) ggamma[i] = a;
+    else gbeta[i - C] = a;
+  }
 }
 
-constexpr int LN_MAX_GRID = 148 * 8;  // persistent: 8 CTAs of 256 threads per B200 SM
+constexpr int LN_MAX_GRID = 148 * 4;  // persistent: 4 CTAs of 256 threads per B200 SM
 int ln_grid(int64_t rows, int rpw) {
   const int64_t need = (rows + (int64_t)rpw * LN_WARPS - 1) / ((int64_t)rpw * LN_WARPS);
   return (int)(need < LN_MAX_GRID ? (need > 0 ? need : 1) : LN_MAX_GRID);
@@ -288,7 +293,7 @@ int ln_bwd_t(const void* x, const void* gy, const float* gamma, const float* sta
 #undef CALL
   int rc = check_launch("layernorm_bwd_kernel");
   if (rc != CSB200_OK) return rc;
-  layernorm_param_grad_final<<<(int)((2 * C + 255) / 256), 256, 0, st>>>(partial, grid, (int)C,
+  layernorm_param_grad_final<<<(int)((2 * C * 32 + 255) / 256), 256, 0, st>>>(partial, grid, (int)C,
                                                                          ggamma, gbeta);
   return check_launch("layernorm_param_grad_final");
 }

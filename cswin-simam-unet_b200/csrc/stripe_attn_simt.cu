@@ -378,23 +378,10 @@ __global__ void __launch_bounds__(ROWS)
 // fixed order, so the result is deterministic.
 // ------------------------------------------------------------------------------------------------
 constexpr int PREP_THREADS = 256;
-constexpr int PREP_TOK_PER_ITER = PREP_THREADS / 4;  // 64 tokens per iteration
+constexpr int PREP_TOK_PER_ITER = PREP_THREADS / 8;  // 8 lanes x 4 channels per token
 
 template <typename T>
-__device__ __forceinline__ void ld8(const T* p, float (&f)[8]);
-template <>
-__device__ __forceinline__ void ld8<float>(const float* p, float (&f)[8]) {
-  const float4 a = __ldg(reinterpret_cast<const float4*>(p));
-  const float4 b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
-}
-template <>
-__device__ __forceinline__ void ld8<__nv_bfloat16>(const __nv_bfloat16* p, float (&f)[8]) {
-  unpack<__nv_bfloat16>(__ldg(reinterpret_cast<const uint4*>(p)), f);
-}
-
-template <typename T>
-__global__ void __launch_bounds__(PREP_THREADS)
+__global__ void __launch_bounds__(PREP_THREADS, 3)
     lepe_bwd_prep(StripeGeom g, const T* __restrict__ v, const float* __restrict__ lepe_w,
                   const float* __restrict__ lepe_b, const T* __restrict__ out,
                   const T* __restrict__ gout, float* __restrict__ delta,
@@ -407,34 +394,26 @@ __global__ void __launch_bounds__(PREP_THREADS)
     s_w[i] = tap < 9 ? __ldg(lepe_w + (head * HD + c) * 9 + tap) : __ldg(lepe_b + head * HD + c);
   }
   __syncthreads();
-  const int cg = threadIdx.x & 3;              // which 8 of the head's 32 channels
-  const int co = head * HD + cg * 8;
+  const int cg = threadIdx.x & 7;              // which 4 of the head's 32 channels
+  const int co = head * HD + cg * 4;
   const int64_t total = (int64_t)g.B * g.L;
   const int64_t t_begin = (int64_t)blockIdx.x * tok_per_cta;
-  float acc[10][8];
+  float4 acc[10];
 #pragma unroll
-  for (int t = 0; t < 10; ++t)
-#pragma unroll
-    for (int e = 0; e < 8; ++e) acc[t][e] = 0.f;
+  for (int t = 0; t < 10; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  for (int it = threadIdx.x >> 2; it < tok_per_cta; it += PREP_TOK_PER_ITER) {
+  for (int it = threadIdx.x >> 3; it < tok_per_cta; it += PREP_TOK_PER_ITER) {
     const int64_t gt = t_begin + it;
     const bool valid = gt < total;  // no early exit: every lane takes part in the shuffles below
     const int b = valid ? (int)(gt / g.L) : 0, l = valid ? (int)(gt % g.L) : 0;
     const int y = l / g.W, x = l % g.W, yy = y % g.hs, xx = x % g.ws;
-    float go[8], o[8], lp[8];
+    float4 go = make_float4(0.f, 0.f, 0.f, 0.f), o = go;
     if (valid) {
-      ld8<T>(gout + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, go);
-      ld8<T>(out + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co, o);
-    } else {
-#pragma unroll
-      for (int e = 0; e < 8; ++e) go[e] = o[e] = 0.f;
+      go = ld4<T>(gout + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co);
+      o = ld4<T>(out + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co);
     }
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      lp[e] = s_w[9 * HD + cg * 8 + e];
-      acc[9][e] += go[e];
-    }
+    float4 lp = *reinterpret_cast<const float4*>(s_w + 9 * HD + cg * 4);
+    acc[9].x += go.x; acc[9].y += go.y; acc[9].z += go.z; acc[9].w += go.w;
     const T* vb = v + (int64_t)b * g.v_sb + co;
 #pragma unroll
     for (int ky = 0; ky < 3; ++ky) {
@@ -442,39 +421,37 @@ __global__ void __launch_bounds__(PREP_THREADS)
 #pragma unroll
       for (int kx = 0; kx < 3; ++kx) {
         if (xx + kx - 1 < 0 || xx + kx - 1 >= g.ws) continue;
-        float vn[8];
-        ld8<T>(vb + (int64_t)((y + ky - 1) * g.W + (x + kx - 1)) * g.v_sl, vn);
-        const float* wt = s_w + (ky * 3 + kx) * HD + cg * 8;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          lp[e] = fmaf(wt[e], vn[e], lp[e]);
-          acc[ky * 3 + kx][e] = fmaf(go[e], vn[e], acc[ky * 3 + kx][e]);
-        }
+        const float4 vn = ld4<T>(vb + (int64_t)((y + ky - 1) * g.W + (x + kx - 1)) * g.v_sl);
+        const float4 wt = *reinterpret_cast<const float4*>(s_w + (ky * 3 + kx) * HD + cg * 4);
+        lp.x = fmaf(wt.x, vn.x, lp.x); lp.y = fmaf(wt.y, vn.y, lp.y);
+        lp.z = fmaf(wt.z, vn.z, lp.z); lp.w = fmaf(wt.w, vn.w, lp.w);
+        float4& a = acc[ky * 3 + kx];
+        a.x = fmaf(go.x, vn.x, a.x); a.y = fmaf(go.y, vn.y, a.y);
+        a.z = fmaf(go.z, vn.z, a.z); a.w = fmaf(go.w, vn.w, a.w);
       }
     }
-    float d = 0.f;
-#pragma unroll
-    for (int e = 0; e < 8; ++e) d = fmaf(go[e], o[e] - lp[e], d);
+    float d = go.x * (o.x - lp.x) + go.y * (o.y - lp.y) + go.z * (o.z - lp.z) + go.w * (o.w - lp.w);
     d += __shfl_xor_sync(0xffffffffu, d, 1);
     d += __shfl_xor_sync(0xffffffffu, d, 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 4);
     if (cg == 0 && valid) delta[((int64_t)b * g.heads + head) * g.L + l] = d;
   }
-  // reduce the 80 accumulators over the 8 token lanes of the warp, then over the 8 warps
+  // reduce the 40 accumulators over the 4 token lanes of the warp, then over the 8 warps
 #pragma unroll
-  for (int t = 0; t < 10; ++t)
+  for (int t = 0; t < 10; ++t) {
+    float* f = reinterpret_cast<float*>(&acc[t]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      float a = acc[t][e];
-      a += __shfl_xor_sync(0xffffffffu, a, 4);
+    for (int e = 0; e < 4; ++e) {
+      float a = f[e];
       a += __shfl_xor_sync(0xffffffffu, a, 8);
       a += __shfl_xor_sync(0xffffffffu, a, 16);
-      acc[t][e] = a;
+      f[e] = a;
     }
-  if ((threadIdx.x & 31) < 4) {
+  }
+  if ((threadIdx.x & 31) < 8) {
 #pragma unroll
     for (int t = 0; t < 10; ++t)
-#pragma unroll
-      for (int e = 0; e < 8; ++e) s_part[threadIdx.x >> 5][t * HD + cg * 8 + e] = acc[t][e];
+      *reinterpret_cast<float4*>(&s_part[threadIdx.x >> 5][t * HD + cg * 4]) = acc[t];
   }
   __syncthreads();
   for (int i = threadIdx.x; i < 10 * HD; i += PREP_THREADS) {
@@ -486,13 +463,16 @@ __global__ void __launch_bounds__(PREP_THREADS)
   }
 }
 
+// one warp per (channel, tap): lanes stride over the per-CTA partials, fixed order -> deterministic
 __global__ void __launch_bounds__(256)
     lepe_wgrad_final(const float* __restrict__ partial, int blocks, int cp,
                      float* __restrict__ gw, float* __restrict__ gb) {
-  const int i = blockIdx.x * 256 + threadIdx.x;  // (c, tap)
+  const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // (c, tap)
   if (i >= cp * 10) return;
   float a = 0.f;
-  for (int b = 0; b < blocks; ++b) a += partial[(int64_t)b * cp * 10 + i];
+  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * cp * 10 + i];
+  a = warp_sum(a);
+  if (lane != 0) return;
   const int c = i / 10, tap = i % 10;
   if (tap == 9) gb[c] = a;
   else gw[c * 9 + tap] = a;
@@ -557,7 +537,7 @@ int lepe_bwd_prep_t(const StripeGeom& g, const T* v, const float* lepe_w, const 
                                                                     partial, prep_tok_per_cta(g));
   int rc = check_launch("lepe_bwd_prep");
   if (rc != CSB200_OK) return rc;
-  lepe_wgrad_final<<<(cp * 10 + 255) / 256, 256, 0, st>>>(partial, blocks, cp, gw, gb);
+  lepe_wgrad_final<<<(cp * 10 * 32 + 255) / 256, 256, 0, st>>>(partial, blocks, cp, gw, gb);
   return check_launch("lepe_wgrad_final");
 }
 

@@ -13,7 +13,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_norm,
+from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_linear, apply_norm,
                       carafe_kernels, carafe_reassemble, image_as_tokens, tokens_as_image, _side)
 
 
@@ -131,7 +131,7 @@ class CSWinTransformer(nn.Module):
         for blocks, upsample, fuse, skip in plan:
             for blk in blocks:
                 x = blk(x)
-            x = fuse(torch.cat([skip, upsample(x)], dim=-1))
+            x = apply_linear(fuse, torch.cat([skip, upsample(x)], dim=-1))
         for blk in self.stage_up1:
             x = blk(x)
         return apply_norm(self.norm_up, x, feeds_gemm=True)

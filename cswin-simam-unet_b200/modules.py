@@ -49,6 +49,13 @@ def apply_norm(norm: nn.Module, x: torch.Tensor, feeds_gemm: bool = False) -> to
     return norm(x)
 
 
+def apply_linear(lin: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """A plain ``nn.Linear`` runs through csbF.linear (cuBLAS GEMMs + one-pass bias gradient)."""
+    if type(lin) is nn.Linear and x.is_cuda:
+        return csbF.linear(x, lin.weight, lin.bias)
+    return lin(x)
+
+
 class SimAM(nn.Module):
     """Parameter-free SimAM attention (Yang et al., ICML 2021) as ONE fused kernel per direction.
 
@@ -94,7 +101,7 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(self.fc2(self.drop(self.act(self.fc1(x)))))
+        return self.drop(apply_linear(self.fc2, self.drop(self.act(apply_linear(self.fc1, x)))))
 
 
 class LePEAttention(nn.Module):
@@ -190,7 +197,7 @@ class CSWinBlock(nn.Module):
         B, L, C = x.shape
         if L != self.patches_resolution ** 2:
             raise AssertionError("flatten img_tokens has wrong size")
-        attended = self.proj(self.attend(self.qkv(apply_norm(self.norm1, x, feeds_gemm=True))))
+        attended = apply_linear(self.proj, self.attend(apply_linear(self.qkv, apply_norm(self.norm1, x, feeds_gemm=True))))
         x = x + self.drop_path(attended)  # proj_drop exists but is never applied in the reference (C:366-367)
         return x + self.drop_path(self.mlp(apply_norm(self.norm2, x, feeds_gemm=True)))
 

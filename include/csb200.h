@@ -96,6 +96,16 @@ CSB200_API int csb200_layernorm_bwd(const void* x, const void* grad_y, const flo
                                     void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Column sums of a row-major [rows][cols] matrix (fp32 out) — the bias gradient of the Linear layers
+ * on the token path (C:358, C:366, C:188-196, C:658): grad_bias = sum over tokens of grad_out.
+ * Supported when cols is a multiple of the 16-byte vector width and cols / width <= 256.
+ * ---------------------------------------------------------------------------------------------- */
+CSB200_API int csb200_colsum_supported(int64_t cols, int dtype);
+CSB200_API size_t csb200_colsum_workspace_bytes(int64_t cols);
+CSB200_API int csb200_colsum(const void* x, float* out, void* workspace, size_t workspace_bytes,
+                             int64_t rows, int64_t cols, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Cross-shaped stripe attention with LePE — replaces the body of LePEAttention.forward (C:271-298)
  * including im2cswin (C:248-254), get_lepe (C:256-269), img2windows / windows2img (C:199-217) and, on
  * the caller's side, the torch.cat of the two branches (C:363): q/k/v are read in place from the

@@ -72,3 +72,36 @@ def test_layernorm_large_rows_deterministic():
     assert all(torch.equal(a, c) for a, c in zip(*outs))  # fixed-order reductions
     ref = F.layer_norm(x.detach().double(), (128,), w.detach().double(), b.detach().double())
     assert rel_err(csbF.layer_norm(x, w, b).detach().cpu(), ref.cpu()) < 1e-5
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("rows,cols", [(1000, 64), (4097, 192), (333, 768), (50, 1536), (7, 2048), (1, 8), (20000, 256)])
+def test_column_sum_matches_fp64(rows, cols, dtype):
+    torch.manual_seed(rows + cols)
+    x = torch.randn(rows, cols).to(dtype)
+    got = csbF.column_sum(x.cuda())
+    assert rel_err(got.cpu(), x.double().sum(0)) < (1e-5 if dtype == torch.float32 else 1e-4)
+    assert torch.equal(got, csbF.column_sum(x.cuda()))  # deterministic
+
+
+@pytest.mark.parametrize("autocast", [False, True])
+def test_linear_function_matches_torch(autocast):
+    torch.manual_seed(0)
+    lin = torch.nn.Linear(64, 192).cuda()
+    ref = torch.nn.Linear(64, 192).cuda()
+    ref.load_state_dict(lin.state_dict())
+    x = torch.randn(2, 300, 64, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    g = torch.randn(2, 300, 192, device="cuda")
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        ya = modules.apply_linear(lin, xa)
+        yb = ref(xb)
+    assert ya.dtype == yb.dtype
+    ya.backward(g.to(ya.dtype))
+    yb.backward(g.to(yb.dtype))
+    tol = 2 ** -7 if autocast else 1e-5
+    assert rel_err(ya.float().cpu(), yb.float().cpu()) < tol
+    assert rel_err(xa.grad.cpu(), xb.grad.cpu()) < tol
+    assert rel_err(lin.weight.grad.cpu(), ref.weight.grad.cpu()) < tol
+    assert rel_err(lin.bias.grad.cpu(), ref.bias.grad.cpu()) < tol
+    assert lin.weight.grad.dtype == torch.float32 and xa.grad.dtype == torch.float32
