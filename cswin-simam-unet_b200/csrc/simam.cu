@@ -54,6 +54,15 @@ __device__ __forceinline__ float simam_fwd_elem(float x, const FwdCoef& c) {
   float t = centred(x, c.pivot, c.dmean);
   return x * Sig<T>::f(fmaf(t * t, c.inv4v, 0.5f));
 }
+// bf16 fast form: sigmoid(e) = 0.5 tanh(e/2) + 0.5 with the halves folded into the coefficients,
+//   y = hx * tanh(t^2 * inv8v + 0.25) + hx,  hx = x / 2,  t = x - mean  (7 issue slots + 1 MUFU)
+__device__ __forceinline__ float simam_fwd_fast(float x, float mean, float inv8v) {
+  const float t = x - mean;
+  float th;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(fmaf(t * t, inv8v, 0.25f)));
+  const float hx = 0.5f * x;
+  return fmaf(hx, th, hx);
+}
 
 // ------------------------------------------------------------------------------------------------
 // block / cluster reduction of NV scalars held by every thread (NCHW: one plane per CTA/cluster)
@@ -97,7 +106,7 @@ __device__ __forceinline__ void plane_reduce(float (&v)[NV], float* s_warp /*[NV
 // NCHW resident forward.  WARP_PLANE: one warp per plane (small planes), else one CTA / cluster.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int VPT, int THREADS, int CLUSTER, bool WARP_PLANE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2))
     simam_nchw_fwd_resident(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats,
                             int64_t planes, int nvec, float S, float e_lambda) {
   constexpr int VE = Vec16<T>::N;
@@ -127,39 +136,69 @@ __global__ void __launch_bounds__(THREADS)
     d[i] = (vi < nvec) ? ld_stream(xp + vi) : make_uint4(0, 0, 0, 0);
   }
   const float pivot = to_f32(__ldg(x + plane * nvec * VE));  // first element of the plane
-  // pass A: sum of (x - pivot)
-  float red[1] = {0.f};
+  constexpr bool ONEPASS = sizeof(T) == 2;
+  float dmean, v;
+  FwdCoef c;
+  if constexpr (ONEPASS) {
+    // bf16 inputs carry 8 significant bits: shifted single-pass moments in fp32 are exact enough
+    // (sum d, sum d^2 with d = x - pivot) and need ONE reduction round instead of two
+    float red[2] = {0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    if (v0 + i * vstride < nvec) {
-      float f[VE];
-      unpack<T>(d[i], f);
+    for (int i = 0; i < VPT; ++i) {
+      if (v0 + i * vstride < nvec) {
+        float f[VE];
+        unpack<T>(d[i], f);
 #pragma unroll
-      for (int e = 0; e < VE; ++e) red[0] += f[e] - pivot;
-    }
-  }
-  if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
-  else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp, s_cta);
-  const float dmean = red[0] / S;
-
-  // pass B: centred second moment
-  red[0] = 0.f;
-#pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    if (v0 + i * vstride < nvec) {
-      float f[VE];
-      unpack<T>(d[i], f);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        float t = centred(f[e], pivot, dmean);
-        red[0] = fmaf(t, t, red[0]);
+        for (int e = 0; e < VE; ++e) {
+          const float t = f[e] - pivot;
+          red[0] += t;
+          red[1] = fmaf(t, t, red[1]);
+        }
       }
     }
+    if constexpr (WARP_PLANE) {
+      red[0] = warp_sum(red[0]);
+      red[1] = warp_sum(red[1]);
+    } else {
+      plane_reduce<THREADS, CLUSTER, 2>(red, s_warp, s_cta);
+    }
+    dmean = red[0] / S;
+    v = fmaxf(red[1] - red[0] * dmean, 0.f) / (S - 1.f) + e_lambda;
+    c = FwdCoef{0.f, pivot + dmean, 1.f / (8.f * v)};  // (unused, mean, 1/(8v)) for simam_fwd_fast
+  } else {
+    // pass A: sum of (x - pivot)
+    float red[1] = {0.f};
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      if (v0 + i * vstride < nvec) {
+        float f[VE];
+        unpack<T>(d[i], f);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) red[0] += f[e] - pivot;
+      }
+    }
+    if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
+    else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp, s_cta);
+    dmean = red[0] / S;
+    // pass B: centred second moment
+    red[0] = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      if (v0 + i * vstride < nvec) {
+        float f[VE];
+        unpack<T>(d[i], f);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          float t = centred(f[e], pivot, dmean);
+          red[0] = fmaf(t, t, red[0]);
+        }
+      }
+    }
+    if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
+    else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp + 32, s_cta + 1);
+    v = red[0] / (S - 1.f) + e_lambda;
+    c = FwdCoef{pivot, dmean, 1.f / (4.f * v)};
   }
-  if constexpr (WARP_PLANE) red[0] = warp_sum(red[0]);
-  else plane_reduce<THREADS, CLUSTER, 1>(red, s_warp + 32, s_cta + 1);
-  const float v = red[0] / (S - 1.f) + e_lambda;
-  FwdCoef c{pivot, dmean, 1.f / (4.f * v)};
 
 #pragma unroll
   for (int i = 0; i < VPT; ++i) {
@@ -168,7 +207,10 @@ __global__ void __launch_bounds__(THREADS)
       float f[VE];
       unpack<T>(d[i], f);
 #pragma unroll
-      for (int e = 0; e < VE; ++e) f[e] = simam_fwd_elem<T>(f[e], c);
+      for (int e = 0; e < VE; ++e) {
+        if constexpr (ONEPASS) f[e] = simam_fwd_fast(f[e], c.dmean, c.inv4v);
+        else f[e] = simam_fwd_elem<T>(f[e], c);
+      }
       st_stream(yp + vi, pack<T>(f));
     }
   }
@@ -181,7 +223,7 @@ __global__ void __launch_bounds__(THREADS)
 
 // NCHW resident backward: holds x and grad_y; one reduction of (R1, R2').
 template <typename T, int VPT, int THREADS, int CLUSTER, bool WARP_PLANE>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (VPT <= 4 ? 3 : 2) : 1))
     simam_nchw_bwd_resident(const T* __restrict__ x, const T* __restrict__ gy,
                             const float* __restrict__ stats, T* __restrict__ gx, int64_t planes,
                             int nvec, float S) {
@@ -655,6 +697,8 @@ int nchw_resident(const T* x, const T* gy, float* stats_out, const float* stats_
                     CLUSTER, st, "simam_nchw_fwd_resident", x, out, stats_out, planes, nvec, Sf,  \
                     e_lambda);                                                                    \
   } while (0)
+  // CTAs of 256 threads keep 4 (forward) / 3 (backward) of them resident per SM, so the load, reduce
+  // and store phases of different planes overlap; a plane larger than one CTA spans a cluster.
   if constexpr (!BWD) {
     if (nvec <= 32) CSB_NCHW(1, 256, 1, true);
     if (nvec <= 64) CSB_NCHW(2, 256, 1, true);
@@ -663,9 +707,9 @@ int nchw_resident(const T* x, const T* gy, float* stats_out, const float* stats_
     if (nvec <= 512) CSB_NCHW(4, 128, 1, false);
     if (nvec <= 1024) CSB_NCHW(4, 256, 1, false);
     if (nvec <= 2048) CSB_NCHW(8, 256, 1, false);
-    if (nvec <= 4096) CSB_NCHW(8, 512, 1, false);
-    if (nvec <= 8192) CSB_NCHW(8, 512, 2, false);
-    if (nvec <= 16384) CSB_NCHW(8, 512, 4, false);
+    if (nvec <= 4096) CSB_NCHW(8, 256, 2, false);
+    if (nvec <= 8192) CSB_NCHW(8, 256, 4, false);
+    if (nvec <= 16384) CSB_NCHW(8, 256, 8, false);
     CSB_NCHW(8, 512, 8, false);
   } else {
     if (nvec <= 32) CSB_NCHW(1, 256, 1, true);
@@ -673,10 +717,10 @@ int nchw_resident(const T* x, const T* gy, float* stats_out, const float* stats_
     if (nvec <= 128) CSB_NCHW(4, 256, 1, true);
     if (nvec <= 512) CSB_NCHW(4, 128, 1, false);
     if (nvec <= 1024) CSB_NCHW(4, 256, 1, false);
-    if (nvec <= 2048) CSB_NCHW(4, 512, 1, false);
-    if (nvec <= 4096) CSB_NCHW(4, 512, 2, false);
-    if (nvec <= 8192) CSB_NCHW(4, 512, 4, false);
-    if (nvec <= 16384) CSB_NCHW(4, 512, 8, false);
+    if (nvec <= 2048) CSB_NCHW(4, 256, 2, false);
+    if (nvec <= 4096) CSB_NCHW(4, 256, 4, false);
+    if (nvec <= 8192) CSB_NCHW(4, 256, 8, false);
+    if (nvec <= 16384) CSB_NCHW(8, 256, 8, false);
     CSB_NCHW(8, 512, 8, false);
   }
 #undef CSB_NCHW
