@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2))
 
 // NCHW resident backward: holds x and grad_y; one reduction of (R1, R2').
 template <typename T, int VPT, int THREADS, int CLUSTER, bool WARP_PLANE>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (VPT <= 4 ? 3 : 2) : 1))
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1))
     simam_nchw_bwd_resident(const T* __restrict__ x, const T* __restrict__ gy,
                             const float* __restrict__ stats, T* __restrict__ gx, int64_t planes,
                             int nvec, float S) {
@@ -261,32 +261,59 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (VPT <= 4 ? 3 : 2) 
   const float inv4v = 1.f / (4.f * v);
 
   float red[2] = {0.f, 0.f};  // R1 = sum a*d, R2' = sum a*t  (grad of zero-padded slots is 0 -> a = 0)
+  if constexpr (sizeof(T) == 2) {
+    // bf16: the pass-1 products g*s and a = g x s (1-s) are kept, packed to bf16, in the registers
+    // that held grad_y (+ VPT more), so pass 2 is 8 issue slots per element instead of a recompute.
+    const float mean = pivot + dmean, inv8v = 0.5f * inv4v;
+    uint4 da[VPT];
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    float fx[VE], fg[VE];
-    unpack<T>(dx[i], fx);
-    unpack<T>(dg[i], fg);
+    for (int i = 0; i < VPT; ++i) {
+      float fx[VE], fg[VE], fa[VE];
+      unpack<T>(dx[i], fx);
+      unpack<T>(dg[i], fg);
 #pragma unroll
-    for (int e = 0; e < VE; ++e) {
-      float t = centred(fx[e], pivot, dmean), dd = t * t;
-      float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
-      float a = fg[e] * fx[e] * s * (1.f - s);
-      red[0] = fmaf(a, dd, red[0]);
-      red[1] = fmaf(a, t, red[1]);
+      for (int e = 0; e < VE; ++e) {
+        const float t = fx[e] - mean, dd = t * t;
+        float th;
+        asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(fmaf(dd, inv8v, 0.25f)));
+        const float s = fmaf(0.5f, th, 0.5f);
+        const float gs = fg[e] * s;
+        const float a = gs * fx[e] * (1.f - s);
+        red[0] = fmaf(a, dd, red[0]);
+        red[1] = fmaf(a, t, red[1]);
+        fg[e] = gs;
+        fa[e] = a;
+      }
+      dg[i] = pack<T>(fg);
+      da[i] = pack<T>(fa);
     }
-  }
-  if constexpr (WARP_PLANE) {
-    red[0] = warp_sum(red[0]);
-    red[1] = warp_sum(red[1]);
-  } else {
-    plane_reduce<THREADS, CLUSTER, 2>(red, s_warp, s_cta);
-  }
-  const float c1 = red[0] * inv4v / (v * (S - 1.f));  // R1 / (4 v^2 n)
-  const float c2 = 2.f / S * red[1] * inv4v;          // (2/HW) R2
+    if constexpr (WARP_PLANE) {
+      red[0] = warp_sum(red[0]);
+      red[1] = warp_sum(red[1]);
+    } else {
+      plane_reduce<THREADS, CLUSTER, 2>(red, s_warp, s_cta);
+    }
+    const float c1 = red[0] * inv4v / (v * (S - 1.f));  // R1 / (4 v^2 n)
+    const float c2 = 2.f / S * red[1] * inv4v;          // (2/HW) R2
 #pragma unroll
-  for (int i = 0; i < VPT; ++i) {
-    int vi = v0 + i * vstride;
-    if (vi < nvec) {
+    for (int i = 0; i < VPT; ++i) {
+      const int vi = v0 + i * vstride;
+      if (vi < nvec) {
+        float fx[VE], fg[VE], fa[VE];
+        unpack<T>(dx[i], fx);
+        unpack<T>(dg[i], fg);
+        unpack<T>(da[i], fa);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          const float t2 = 2.f * (fx[e] - mean);
+          fx[e] = fmaf(t2, fmaf(fa[e], inv4v, -c1), fg[e]) - c2;
+        }
+        st_stream(op + vi, pack<T>(fx));
+      }
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
       float fx[VE], fg[VE];
       unpack<T>(dx[i], fx);
       unpack<T>(dg[i], fg);
@@ -295,9 +322,34 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (VPT <= 4 ? 3 : 2) 
         float t = centred(fx[e], pivot, dmean), dd = t * t;
         float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
         float a = fg[e] * fx[e] * s * (1.f - s);
-        fx[e] = fmaf(fg[e], s, 2.f * t * fmaf(a, inv4v, -c1)) - c2;
+        red[0] = fmaf(a, dd, red[0]);
+        red[1] = fmaf(a, t, red[1]);
       }
-      st_stream(op + vi, pack<T>(fx));
+    }
+    if constexpr (WARP_PLANE) {
+      red[0] = warp_sum(red[0]);
+      red[1] = warp_sum(red[1]);
+    } else {
+      plane_reduce<THREADS, CLUSTER, 2>(red, s_warp, s_cta);
+    }
+    const float c1 = red[0] * inv4v / (v * (S - 1.f));  // R1 / (4 v^2 n)
+    const float c2 = 2.f / S * red[1] * inv4v;          // (2/HW) R2
+#pragma unroll
+    for (int i = 0; i < VPT; ++i) {
+      int vi = v0 + i * vstride;
+      if (vi < nvec) {
+        float fx[VE], fg[VE];
+        unpack<T>(dx[i], fx);
+        unpack<T>(dg[i], fg);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          float t = centred(fx[e], pivot, dmean), dd = t * t;
+          float s = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+          float a = fg[e] * fx[e] * s * (1.f - s);
+          fx[e] = fmaf(fg[e], s, 2.f * t * fmaf(a, inv4v, -c1)) - c2;
+        }
+        st_stream(op + vi, pack<T>(fx));
+      }
     }
   }
   if constexpr (CLUSTER > 1) cluster_sync_all();
@@ -351,7 +403,7 @@ __device__ __forceinline__ void slab_reduce(float (&acc)[NQ][VE], float* s_red /
 }
 
 template <typename T, int VPT, int CWV, int THREADS, int CLUSTER>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, 2)
     simam_nlc_fwd_resident(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats,
                            int L, int C, int slabs, float e_lambda) {
   constexpr int VE = Vec16<T>::N;
