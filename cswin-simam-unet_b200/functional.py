@@ -252,6 +252,58 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) 
 
 
 # ------------------------------------------------------------------------------------------------
+# CARAFE reassembly
+# ------------------------------------------------------------------------------------------------
+class _CarafeFn(torch.autograd.Function):
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, low, enc, up):
+        capi.require_cuda(low, enc)
+        CL = torch.channels_last
+        low = low.contiguous(memory_format=CL)
+        enc = enc.to(low.dtype).contiguous(memory_format=CL)
+        B, C, H, W = low.shape
+        out = torch.empty((B, C, H * up, W * up), dtype=low.dtype, device=low.device, memory_format=CL)
+        wt = torch.empty((B, H * up, W * up, 9), dtype=low.dtype, device=low.device)
+        nbytes = (low.numel() + enc.numel() + out.numel() + wt.numel()) * low.element_size()
+        with torch.cuda.device(low.device), _span("carafe_fwd", nbytes):
+            capi.check(capi.lib().csb200_carafe_fwd(_ptr(low), _ptr(enc), _ptr(out), _ptr(wt), B, H, W, C, up,
+                                                    capi.dtype_code(low), _vp(capi.stream_of(low))),
+                       "csb200_carafe_fwd")
+        ctx.save_for_backward(low, wt)
+        ctx.cfg = (up, enc.shape)
+        return out
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gout):
+        low, wt = ctx.saved_tensors
+        up, enc_shape = ctx.cfg
+        CL = torch.channels_last
+        B, C, H, W = low.shape
+        gout = gout.to(low.dtype).contiguous(memory_format=CL)
+        d_low = torch.empty_like(low, memory_format=CL)
+        d_enc = torch.empty(enc_shape, dtype=low.dtype, device=low.device, memory_format=CL)
+        nbytes = (2 * low.numel() + d_enc.numel() + 2 * gout.numel() + 2 * wt.numel()) * low.element_size()
+        with torch.cuda.device(low.device), _span("carafe_bwd", nbytes):
+            capi.check(capi.lib().csb200_carafe_bwd(_ptr(low), _ptr(wt), _ptr(gout), _ptr(d_low), _ptr(d_enc), B, H, W,
+                                                    C, up, capi.dtype_code(low), _vp(capi.stream_of(low))),
+                       "csb200_carafe_bwd")
+        return d_low, d_enc, None
+
+
+def carafe_supported(low: torch.Tensor) -> bool:
+    return low.is_cuda and low.dtype in (torch.float32, torch.bfloat16) and \
+        bool(capi.lib().csb200_carafe_supported(low.shape[1]))
+
+
+def carafe_reassemble(low: torch.Tensor, enc: torch.Tensor, up: int) -> torch.Tensor:
+    """Fused kernel-softmax + content-aware reassembly (C:408-431).  low: (B, C, H, W) features,
+    enc: (B, 9*up*up, H, W) raw encoder logits; returns (B, C, H*up, W*up), channels-last."""
+    return _CarafeFn.apply(low, enc, up)
+
+
+# ------------------------------------------------------------------------------------------------
 # stripe attention
 # ------------------------------------------------------------------------------------------------
 class Branch:

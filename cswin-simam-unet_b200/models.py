@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_linear, apply_norm,
-                      carafe_kernels, carafe_reassemble, image_as_tokens, tokens_as_image, _side)
+                      carafe_upsample, image_as_tokens, tokens_as_image, _side)
 
 
 def _trunc_normal_linear_init(m: nn.Module):
@@ -147,12 +147,11 @@ class CSWinTransformer(nn.Module):
         up = self.upsample1
         side = _side(x.shape[1])
         img = tokens_as_image(x, side, side)
-        kern = carafe_kernels(img, up.down, up.encoder, up.up_factor)
         w_out = self.output.weight.flatten(1)  # (classes, 64)
         w_eff = (w_out @ up.out.weight.flatten(1)).unsqueeze(-1).unsqueeze(-1)  # (classes, 64, 1, 1)
         b_eff = w_out @ up.out.bias
         low = F.conv2d(img, w_eff)
-        logits = carafe_reassemble(low, kern, up.up_factor, up.kernel_size)
+        logits = carafe_upsample(low, img, up.down, up.encoder, up.up_factor, up.kernel_size)
         return logits + b_eff.to(logits.dtype).view(1, -1, 1, 1)
 
     def forward_logits(self, x):

@@ -230,6 +230,17 @@ def carafe_reassemble(low: torch.Tensor, kern: torch.Tensor, up: int, k: int = 3
     return out.reshape(B, C, H * up, W * up)
 
 
+def carafe_upsample(low: torch.Tensor, img: torch.Tensor, down: nn.Conv2d, encoder: nn.Conv2d, up: int,
+                    k: int = 3) -> torch.Tensor:
+    """Kernel prediction (two convs on cuDNN) + fused softmax / reassembly kernel; on tensors the kernel
+    does not take (CPU, channel counts that are neither 1 nor a multiple of 8, k != 3) the same maths
+    runs as torch ops."""
+    enc = encoder(down(img))
+    if k == 3 and low.dtype == enc.dtype and csbF.carafe_supported(low):
+        return csbF.carafe_reassemble(low, enc, up)
+    return carafe_reassemble(low, torch.softmax(F.pixel_shuffle(enc, up), dim=1), up, k)
+
+
 class CARAFE(nn.Module):
     """Content-aware upsampling (C:391-437): predict a softmax 3x3 kernel per output pixel, then
     reassemble each output pixel from the 3x3 neighbourhood of its source pixel, then a 1x1 conv.
@@ -250,9 +261,8 @@ class CARAFE(nn.Module):
     def forward(self, x):
         side = _side(x.shape[1])
         img = tokens_as_image(x, side, side)
-        kern = carafe_kernels(img, self.down, self.encoder, self.up_factor)
         low = F.conv2d(img, self.out.weight)  # bias deferred past the reassembly
-        up = carafe_reassemble(low, kern, self.up_factor, self.kernel_size)
+        up = carafe_upsample(low, img, self.down, self.encoder, self.up_factor, self.kernel_size)
         return image_as_tokens(up + self.out.bias.to(up.dtype).view(1, -1, 1, 1))
 
 

@@ -106,6 +106,24 @@ CSB200_API int csb200_colsum(const void* x, float* out, void* workspace, size_t 
                              int64_t rows, int64_t cols, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Fused CARAFE reassembly — CARAFE.forward C:406-431 / CARAFE4 C:455-480 without the pixel-shuffled
+ * logits, the fp32 softmax tensor, the 9x unfold and the batched 9 x up^2 matmul:
+ *   out[b, h*up+dy, w*up+dx, c] = sum_tap softmax_tap(enc[b, h, w, tap*up^2 + dy*up + dx])
+ *                                         * low[b, h+ky-1, w+kx-1, c]        (zero padding)
+ * All tensors channels-last (token-major), one type T: low [B][H][W][C], enc [B][H][W][9 up^2]
+ * (the raw `encoder` conv output, C:407), out / grad_out [B][H up][W up][C], weights
+ * [B][H up][W up][9] (the softmax result, written by fwd when non-NULL, required by bwd).
+ * channels == 1 or a multiple of 8.
+ * ---------------------------------------------------------------------------------------------- */
+CSB200_API int csb200_carafe_supported(int64_t channels);
+CSB200_API int csb200_carafe_fwd(const void* low, const void* enc, void* out, void* weights,
+                                 int64_t batch, int64_t height, int64_t width, int64_t channels,
+                                 int up, int dtype, void* stream);
+CSB200_API int csb200_carafe_bwd(const void* low, const void* weights, const void* grad_out,
+                                 void* grad_low, void* grad_enc, int64_t batch, int64_t height,
+                                 int64_t width, int64_t channels, int up, int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Cross-shaped stripe attention with LePE — replaces the body of LePEAttention.forward (C:271-298)
  * including im2cswin (C:248-254), get_lepe (C:256-269), img2windows / windows2img (C:199-217) and, on
  * the caller's side, the torch.cat of the two branches (C:363): q/k/v are read in place from the
