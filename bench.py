@@ -146,7 +146,7 @@ def run_ours(args, rank, local_rank, world):
     B = args.batch_per_gpu
     torch.manual_seed(0)  # identical replicas on every rank
     net = pkg.CSWinTransformer(img_size=IMG, split_size=SPLIT, simam=True, attn_engine=args.attn_engine).to(dev)
-    use_graph = args.cuda_graph and world == 1
+    use_graph = args.cuda_graph
     opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
     reducer = pkg.GradientAllReducer(net.parameters()) if world > 1 else None
     step = pkg.TrainStep(net, opt, precision="bf16", reducer=reducer, cuda_graph=use_graph)
