@@ -223,7 +223,7 @@ __global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 4 : 2))
 
 // NCHW resident backward: holds x and grad_y; one reduction of (R1, R2').
 template <typename T, int VPT, int THREADS, int CLUSTER, bool WARP_PLANE>
-__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? 2 : 1))
+__global__ void __launch_bounds__(THREADS, (THREADS <= 256 ? (sizeof(T) == 2 && VPT <= 4 ? 3 : 2) : 1))
     simam_nchw_bwd_resident(const T* __restrict__ x, const T* __restrict__ gy,
                             const float* __restrict__ stats, T* __restrict__ gx, int64_t planes,
                             int nvec, float S) {
@@ -771,7 +771,7 @@ int nchw_resident(const T* x, const T* gy, float* stats_out, const float* stats_
     if (nvec <= 1024) CSB_NCHW(4, 256, 1, false);
     if (nvec <= 2048) CSB_NCHW(4, 256, 2, false);
     if (nvec <= 4096) CSB_NCHW(4, 256, 4, false);
-    if (nvec <= 8192) CSB_NCHW(4, 256, 8, false);
+    if (nvec <= 8192) CSB_NCHW(8, 256, 4, false);
     if (nvec <= 16384) CSB_NCHW(8, 256, 8, false);
     CSB_NCHW(8, 512, 8, false);
   }
