@@ -24,6 +24,8 @@
 namespace csb200 {
 namespace {
 
+inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
 // ------------------------------------------------------------------------------------------------
 // shared arithmetic
 // ------------------------------------------------------------------------------------------------
@@ -697,6 +699,349 @@ __global__ void __launch_bounds__(256)
 }
 
 // ------------------------------------------------------------------------------------------------
+// NCHW streaming forward for planes that are whole multiples of 16 KB (64 KB .. any size): one
+// persistent CTA per SM, a producer warp feeds a 12-stage shared-memory ring with 16-KB bulk copies
+// (cp.async.bulk + mbarrier: loads never wait for arithmetic), 8 consumer warps sweep each plane
+// twice — moments, then rescale + store.  The second sweep re-reads the plane through the ring; with
+// <= 148 planes of <= 256 KB in flight it is served by the 126-MB L2, so DRAM traffic stays
+// 1 read + 1 write.  No clusters, no per-plane launch phases, registers hold only the current vector.
+// ------------------------------------------------------------------------------------------------
+constexpr int ST_CHUNK = 16384, ST_STAGES = 12, ST_CONSUMERS = 256;
+
+__device__ __forceinline__ uint32_t st_smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void st_mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tSW_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra SD_%=;\n\tbra SW_%=;\n\tSD_%=:\n\t}" ::"r"(st_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+
+template <typename T>
+__global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
+    simam_nchw_fwd_stream(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats,
+                          int planes, int chunks, float S, float e_lambda) {
+  constexpr int VE = Vec16<T>::N;
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  uint8_t* ring = st_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + ST_STAGES * ST_CHUNK);
+  uint64_t* empty = full + ST_STAGES;
+  float* s_red = reinterpret_cast<float*>(empty + ST_STAGES);  // [8][2]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&full[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(8));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_planes = (planes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int64_t plane_bytes = (int64_t)chunks * ST_CHUNK;
+
+  if (warp == ST_CONSUMERS / 32) {
+    // ------------------------------- producer -------------------------------
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = 0; pi < my_planes; ++pi) {
+        const uint8_t* src = reinterpret_cast<const uint8_t*>(x) +
+                             ((int64_t)blockIdx.x + (int64_t)pi * gridDim.x) * plane_bytes;
+        for (int pass = 0; pass < 2; ++pass)
+          for (int c = 0; c < chunks; ++c, ++it) {
+            const int s = it % ST_STAGES;
+            st_mbar_wait(&empty[s], ((it / ST_STAGES) & 1) ^ 1);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                             st_smem_u32(&full[s])),
+                         "r"(ST_CHUNK)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(st_smem_u32(ring + s * ST_CHUNK)),
+                "l"(src + (int64_t)c * ST_CHUNK), "r"(ST_CHUNK), "r"(st_smem_u32(&full[s]))
+                : "memory");
+          }
+      }
+    }
+    return;
+  }
+  // --------------------------------- consumers ---------------------------------
+  int it = 0;
+  for (int pi = 0; pi < my_planes; ++pi) {
+    const int64_t plane = (int64_t)blockIdx.x + (int64_t)pi * gridDim.x;
+    float pivot = 0.f, sum = 0.f, sq = 0.f;
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int s = it % ST_STAGES;
+      st_mbar_wait(&full[s], (it / ST_STAGES) & 1);
+      const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+      if (c == 0) pivot = to_f32(*reinterpret_cast<const T*>(v));  // plane's first element (broadcast)
+#pragma unroll
+      for (int i = 0; i < ST_CHUNK / 16 / ST_CONSUMERS; ++i) {
+        float f[VE];
+        unpack<T>(v[threadIdx.x + i * ST_CONSUMERS], f);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          const float d = f[e] - pivot;
+          sum += d;
+          sq = fmaf(d, d, sq);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
+    }
+    sum = warp_sum(sum);
+    sq = warp_sum(sq);
+    if (lane == 0) {
+      s_red[warp * 2] = sum;
+      s_red[warp * 2 + 1] = sq;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory");
+    sum = sq = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST_CONSUMERS / 32; ++w) {
+      sum += s_red[w * 2];
+      sq += s_red[w * 2 + 1];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory");  // s_red is reused by the next plane
+    const float dmean = sum / S;
+    const float var = fmaxf(sq - sum * dmean, 0.f) / (S - 1.f) + e_lambda;
+    if (threadIdx.x == 0 && stats != nullptr) {
+      stats[2 * plane] = dmean;
+      stats[2 * plane + 1] = var;
+    }
+    const float mean = pivot + dmean;
+    FwdCoef cf{pivot, dmean, 1.f / (4.f * var)};
+    const float inv8v = 1.f / (8.f * var);
+    uint4* dst = reinterpret_cast<uint4*>(y) + plane * (plane_bytes / 16);
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int s = it % ST_STAGES;
+      st_mbar_wait(&full[s], (it / ST_STAGES) & 1);
+      const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+#pragma unroll
+      for (int i = 0; i < ST_CHUNK / 16 / ST_CONSUMERS; ++i) {
+        float f[VE];
+        unpack<T>(v[threadIdx.x + i * ST_CONSUMERS], f);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          if constexpr (sizeof(T) == 2) f[e] = simam_fwd_fast(f[e], mean, inv8v);
+          else f[e] = simam_fwd_elem<T>(f[e], cf);
+        }
+        st_stream(dst + (int64_t)c * (ST_CHUNK / 16) + threadIdx.x + i * ST_CONSUMERS, pack<T>(f));
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
+    }
+  }
+}
+
+// Streaming backward: a ring stage holds an 8-KB chunk of x and the matching 8-KB chunk of grad_y.
+// Sweep 1 accumulates R1 = sum a d and R2' = sum a t, sweep 2 (served by L2) writes grad_x.
+// bf16 uses sigmoid = 0.5 tanh + 0.5, hence s (1 - s) = (1 - tanh^2) / 4, and folds the constants.
+template <typename T>
+__global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
+    simam_nchw_bwd_stream(const T* __restrict__ x, const T* __restrict__ gy,
+                          const float* __restrict__ stats, T* __restrict__ gx, int planes, int chunks,
+                          float S) {
+  constexpr int VE = Vec16<T>::N, HALF = ST_CHUNK / 2;
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  uint8_t* ring = st_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + ST_STAGES * ST_CHUNK);
+  uint64_t* empty = full + ST_STAGES;
+  float* s_red = reinterpret_cast<float*>(empty + ST_STAGES);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < ST_STAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&full[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(8));
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int my_planes = (planes - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int64_t plane_bytes = (int64_t)chunks * HALF;
+
+  if (warp == ST_CONSUMERS / 32) {
+    if (lane == 0) {
+      int it = 0;
+      for (int pi = 0; pi < my_planes; ++pi) {
+        const int64_t off = ((int64_t)blockIdx.x + (int64_t)pi * gridDim.x) * plane_bytes;
+        const uint8_t* sx = reinterpret_cast<const uint8_t*>(x) + off;
+        const uint8_t* sg = reinterpret_cast<const uint8_t*>(gy) + off;
+        for (int pass = 0; pass < 2; ++pass)
+          for (int c = 0; c < chunks; ++c, ++it) {
+            const int s = it % ST_STAGES;
+            st_mbar_wait(&empty[s], ((it / ST_STAGES) & 1) ^ 1);
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(
+                             st_smem_u32(&full[s])),
+                         "r"(ST_CHUNK)
+                         : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(st_smem_u32(ring + s * ST_CHUNK)),
+                "l"(sx + (int64_t)c * HALF), "r"(HALF), "r"(st_smem_u32(&full[s]))
+                : "memory");
+            asm volatile(
+                "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+                    "r"(st_smem_u32(ring + s * ST_CHUNK + HALF)),
+                "l"(sg + (int64_t)c * HALF), "r"(HALF), "r"(st_smem_u32(&full[s]))
+                : "memory");
+          }
+      }
+    }
+    return;
+  }
+  int it = 0;
+  for (int pi = 0; pi < my_planes; ++pi) {
+    const int64_t plane = (int64_t)blockIdx.x + (int64_t)pi * gridDim.x;
+    const float dmean = __ldg(stats + 2 * plane), v = __ldg(stats + 2 * plane + 1);
+    const float inv4v = 1.f / (4.f * v), inv8v = 0.5f * inv4v;
+    float pivot = 0.f, mean = 0.f, r1 = 0.f, r2 = 0.f;
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int s = it % ST_STAGES;
+      st_mbar_wait(&full[s], (it / ST_STAGES) & 1);
+      const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+      const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+      if (c == 0) {
+        pivot = to_f32(*reinterpret_cast<const T*>(vx));
+        mean = pivot + dmean;
+      }
+#pragma unroll
+      for (int i = 0; i < HALF / 16 / ST_CONSUMERS; ++i) {
+        float fx[VE], fg[VE];
+        unpack<T>(vx[threadIdx.x + i * ST_CONSUMERS], fx);
+        unpack<T>(vg[threadIdx.x + i * ST_CONSUMERS], fg);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          if constexpr (sizeof(T) == 2) {
+            const float t = fx[e] - mean, dd = t * t;
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(fmaf(dd, inv8v, 0.25f)));
+            const float a4 = fg[e] * fx[e] * fmaf(-th, th, 1.f);  // 4 a
+            r1 = fmaf(a4, dd, r1);
+            r2 = fmaf(a4, t, r2);
+          } else {
+            const float t = centred(fx[e], pivot, dmean), dd = t * t;
+            const float sg_ = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+            const float a4 = 4.f * fg[e] * fx[e] * sg_ * (1.f - sg_);
+            r1 = fmaf(a4, dd, r1);
+            r2 = fmaf(a4, t, r2);
+          }
+        }
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
+    }
+    r1 = warp_sum(r1);
+    r2 = warp_sum(r2);
+    if (lane == 0) {
+      s_red[warp * 2] = r1;
+      s_red[warp * 2 + 1] = r2;
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory");
+    r1 = r2 = 0.f;
+#pragma unroll
+    for (int w = 0; w < ST_CONSUMERS / 32; ++w) {
+      r1 += s_red[w * 2];
+      r2 += s_red[w * 2 + 1];
+    }
+    asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory");
+    r1 *= 0.25f;  // the sweeps accumulate 4 a
+    r2 *= 0.25f;
+    const float c1 = r1 * inv4v / (v * (S - 1.f));  // R1 / (4 v^2 n)
+    const float c2 = 2.f / S * r2 * inv4v;          // (2/HW) R2
+    const float k1 = 0.5f * inv4v, k2 = 2.f * c1;   // 2 (a inv4v - c1) = a4 k1 - k2
+    uint4* dst = reinterpret_cast<uint4*>(gx) + plane * (plane_bytes / 16);
+    for (int c = 0; c < chunks; ++c, ++it) {
+      const int s = it % ST_STAGES;
+      st_mbar_wait(&full[s], (it / ST_STAGES) & 1);
+      const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+      const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+#pragma unroll
+      for (int i = 0; i < HALF / 16 / ST_CONSUMERS; ++i) {
+        float fx[VE], fg[VE];
+        unpack<T>(vx[threadIdx.x + i * ST_CONSUMERS], fx);
+        unpack<T>(vg[threadIdx.x + i * ST_CONSUMERS], fg);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          if constexpr (sizeof(T) == 2) {
+            const float t = fx[e] - mean, dd = t * t;
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(fmaf(dd, inv8v, 0.25f)));
+            const float a4 = fg[e] * fx[e] * fmaf(-th, th, 1.f);
+            const float hg = 0.5f * fg[e];
+            fx[e] = fmaf(t, fmaf(a4, k1, -k2), fmaf(hg, th, hg)) - c2;
+          } else {
+            const float t = centred(fx[e], pivot, dmean), dd = t * t;
+            const float sg_ = Sig<T>::f(fmaf(dd, inv4v, 0.5f));
+            const float a = fg[e] * fx[e] * sg_ * (1.f - sg_);
+            fx[e] = fmaf(fg[e], sg_, 2.f * t * fmaf(a, inv4v, -c1)) - c2;
+          }
+        }
+        st_stream(dst + (int64_t)c * (HALF / 16) + threadIdx.x + i * ST_CONSUMERS, pack<T>(fx));
+      }
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
+    }
+  }
+}
+
+template <typename T>
+int nchw_bwd_stream(const T* x, const T* gy, const float* stats, T* gx, int64_t planes, int64_t S,
+                    cudaStream_t st) {
+  const int64_t plane_bytes = S * (int64_t)sizeof(T);
+  if (plane_bytes % (ST_CHUNK / 2) != 0 || plane_bytes < 4 * (ST_CHUNK / 2) || planes > 0x7fffffff) return -1;
+  if (!aligned16(x) || !aligned16(gy) || !aligned16(gx)) return -1;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return -1;
+  }
+  const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 64;
+  static bool attr[2] = {false, false};
+  if (!attr[sizeof(T) == 2]) {
+    if (cudaFuncSetAttribute(simam_nchw_bwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return -1;
+    attr[sizeof(T) == 2] = true;
+  }
+  const int grid = planes < sms ? (int)planes : sms;
+  simam_nchw_bwd_stream<T><<<grid, ST_CONSUMERS + 32, smem, st>>>(
+      x, gy, stats, gx, (int)planes, (int)(plane_bytes / (ST_CHUNK / 2)), (float)S);
+  return check_launch("simam_nchw_bwd_stream");
+}
+
+template <typename T>
+int nchw_fwd_stream(const T* x, T* y, float* stats, int64_t planes, int64_t S, float e_lambda,
+                    cudaStream_t st) {
+  const int64_t plane_bytes = S * (int64_t)sizeof(T);
+  if (plane_bytes % ST_CHUNK != 0 || plane_bytes < 2 * ST_CHUNK || planes > 0x7fffffff) return -1;
+  if (!aligned16(x) || !aligned16(y)) return -1;
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return -1;
+  }
+  const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 64;
+  static bool attr[2] = {false, false};
+  if (!attr[sizeof(T) == 2]) {
+    if (cudaFuncSetAttribute(simam_nchw_fwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess)
+      return -1;
+    attr[sizeof(T) == 2] = true;
+  }
+  const int grid = planes < sms ? (int)planes : sms;
+  simam_nchw_fwd_stream<T><<<grid, ST_CONSUMERS + 32, smem, st>>>(x, y, stats, (int)planes,
+                                                                   (int)(plane_bytes / ST_CHUNK), (float)S, e_lambda);
+  return check_launch("simam_nchw_fwd_stream");
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 template <typename K, typename... Args>
@@ -724,7 +1069,6 @@ int launch(K kernel, int64_t grid, int threads, int cluster, cudaStream_t st, co
   return check_launch(name);
 }
 
-inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 // NCHW resident dispatch.  Returns -1 if no resident configuration fits.
 template <typename T, bool BWD>
@@ -830,6 +1174,12 @@ int simam_dispatch(const void* x_, const void* gy_, float* stats_out, const floa
   const T* x = static_cast<const T*>(x_);
   const T* gy = static_cast<const T*>(gy_);
   T* out = static_cast<T*>(out_);
+  if (layout == CSB200_NCHW) {
+    int rs;
+    if constexpr (BWD) rs = nchw_bwd_stream<T>(x, gy, stats_in, out, B * C, S, st);
+    else rs = nchw_fwd_stream<T>(x, out, stats_out, B * C, S, e_lambda, st);
+    if (rs >= 0) return rs;
+  }
   int rc = (layout == CSB200_NCHW)
                ? nchw_resident<T, BWD>(x, gy, stats_out, stats_in, out, B * C, S, e_lambda, st)
                : nlc_resident<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, st);
