@@ -7,6 +7,7 @@ buffers to exceed the 126 MB L2 between repeats; CUDA events on the launching st
     python benchmarks/kernel_bench.py attn [--engine simt|tcgen05|auto]   # config 3 attention calls
 """
 import argparse
+import ctypes
 import json
 import os
 import sys
@@ -65,22 +66,25 @@ def bench_simam(only_layout=None, only_dtype=None, first=None):
             nbytes = numel * (2 if dtype == torch.bfloat16 else 4)
             nbuf = max(2, -(-2 * L2_BYTES // nbytes))
             xs = [torch.randn(shape, device="cuda").to(dtype) for _ in range(nbuf)]
-            gs = [torch.randn(shape, device="cuda").to(dtype) for _ in range(min(nbuf, 4))]
-            ys = [None] * nbuf
+            gs = [torch.randn(shape, device="cuda").to(dtype) for _ in range(nbuf)]
+            ys = [torch.empty_like(t) for t in xs]
+            B, C, S = (shape[0], shape[1], shape[2] * shape[3]) if layout == "NCHW" else (shape[0], shape[2], shape[1])
+            stats = [torch.empty(B * C, 2, device="cuda") for _ in range(nbuf)]
+            lib, vp = pkg.capi.lib(), ctypes.c_void_p
+            lay = pkg.capi.NCHW if layout == "NCHW" else pkg.capi.NLC
+            code = pkg.capi.dtype_code(xs[0])
 
-            def fwd(i):
-                xs[i].requires_grad_(True)
-                ys[i] = pkg.simam(xs[i], 1e-4, layout)
-
-            def fwd_nograd(i):
-                with torch.no_grad():
-                    pkg.simam(xs[i], 1e-4, layout)
-            ms_f = time_ms(fwd_nograd, nbuf)
-            for i in range(nbuf):
-                fwd(i)
+            def fwd(i):  # straight through the C ABI, on torch's current stream
+                st = vp(torch.cuda.current_stream().cuda_stream)
+                pkg.capi.check(lib.csb200_simam_fwd(vp(xs[i].data_ptr()), vp(ys[i].data_ptr()),
+                                                    vp(stats[i].data_ptr()), B, C, S, lay, code, 1e-4, st), "fwd")
 
             def bwd(i):
-                torch.autograd.grad(ys[i], xs[i], gs[i % len(gs)], retain_graph=True)
+                st = vp(torch.cuda.current_stream().cuda_stream)
+                pkg.capi.check(lib.csb200_simam_bwd(vp(xs[i].data_ptr()), vp(gs[i].data_ptr()),
+                                                    vp(stats[i].data_ptr()), vp(ys[i].data_ptr()), B, C, S, lay,
+                                                    code, 1e-4, st), "bwd")
+            ms_f = time_ms(fwd, nbuf)
             ms_b = time_ms(bwd, nbuf)
             for name, ms, mult in (("simam_fwd", ms_f, 2), ("simam_bwd", ms_b, 3)):
                 gbs = mult * nbytes / ms / 1e6
@@ -88,7 +92,7 @@ def bench_simam(only_layout=None, only_dtype=None, first=None):
                                   "us": round(ms * 1e3, 2), "algorithmic_GBps": round(gbs, 1),
                                   "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3), "buffers": nbuf}),
                       flush=True)
-            del xs, gs, ys
+            del xs, gs, ys, stats
 
 
 def bench_layernorm():

@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(256)
 // <= 148 planes of <= 256 KB in flight it is served by the 126-MB L2, so DRAM traffic stays
 // 1 read + 1 write.  No clusters, no per-plane launch phases, registers hold only the current vector.
 // ------------------------------------------------------------------------------------------------
-constexpr int ST_CHUNK = 16384, ST_STAGES = 12, ST_CONSUMERS = 256;
+constexpr int ST_CHUNK = 16384, ST_STAGES = 12, ST_CONSUMERS = 512;  // 16 consumer warps + 1 producer
 
 __device__ __forceinline__ uint32_t st_smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -729,12 +729,12 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
   uint8_t* ring = st_smem;
   uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + ST_STAGES * ST_CHUNK);
   uint64_t* empty = full + ST_STAGES;
-  float* s_red = reinterpret_cast<float*>(empty + ST_STAGES);  // [8][2]
+  float* s_red = reinterpret_cast<float*>(empty + ST_STAGES);  // [warps][2]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST_STAGES; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&full[i])), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(8));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(ST_CONSUMERS / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -854,7 +854,7 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
   if (threadIdx.x == 0) {
     for (int i = 0; i < ST_STAGES; ++i) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&full[i])), "r"(1));
-      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(8));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(ST_CONSUMERS / 32));
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -1000,7 +1000,7 @@ int nchw_bwd_stream(const T* x, const T* gy, const float* stats, T* gx, int64_t 
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return -1;
   }
-  const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 64;
+  const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 2 * (ST_CONSUMERS / 32) * 4 + 64;
   static bool attr[2] = {false, false};
   if (!attr[sizeof(T) == 2]) {
     if (cudaFuncSetAttribute(simam_nchw_bwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
@@ -1027,7 +1027,7 @@ int nchw_fwd_stream(const T* x, T* y, float* stats, int64_t planes, int64_t S, f
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
       return -1;
   }
-  const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 64;
+  const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 2 * (ST_CONSUMERS / 32) * 4 + 64;
   static bool attr[2] = {false, false};
   if (!attr[sizeof(T) == 2]) {
     if (cudaFuncSetAttribute(simam_nchw_fwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
