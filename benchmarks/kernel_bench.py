@@ -103,30 +103,29 @@ def bench_layernorm():
         w = torch.randn(C, device="cuda", requires_grad=True)
         b = torch.randn(C, device="cuda", requires_grad=True)
         g = torch.randn(rows, C, device="cuda").bfloat16()
-        ys = [None] * nbuf
-
         def fwd(i):
-            ys[i] = csbF.layer_norm(xs[i], w, b, 1e-5, torch.bfloat16)
-        ms_f = time_ms(fwd, nbuf)
-        for i in range(nbuf):
-            fwd(i)
+            with torch.no_grad():
+                csbF.layer_norm(xs[i], w, b, 1e-5, torch.bfloat16)
 
-        def bwd(i):
-            torch.autograd.grad(ys[i], [xs[i], w, b], g, retain_graph=True)
-        ms_b = time_ms(bwd, nbuf)
+        def fwd_bwd(i):
+            torch.autograd.grad(csbF.layer_norm(xs[i], w, b, 1e-5, torch.bfloat16), [xs[i], w, b], g)
+        ms_f = time_ms(fwd, nbuf)
+        ms_b = time_ms(fwd_bwd, nbuf) - ms_f
 
         def torch_fwd(i):
-            ys[i] = torch.nn.functional.layer_norm(xs[i], (C,), w, b).bfloat16()
+            with torch.no_grad():
+                torch.nn.functional.layer_norm(xs[i], (C,), w, b).bfloat16()
+
+        def torch_fwd_bwd(i):
+            torch.autograd.grad(torch.nn.functional.layer_norm(xs[i], (C,), w, b).bfloat16(), [xs[i], w, b], g)
         ms_tf = time_ms(torch_fwd, nbuf)
-        for i in range(nbuf):
-            torch_fwd(i)
-        ms_tb = time_ms(bwd, nbuf)
+        ms_tb = time_ms(torch_fwd_bwd, nbuf) - ms_tf
         for name, ms, bpe, ref in (("layernorm_fwd", ms_f, 6, ms_tf), ("layernorm_bwd", ms_b, 10, ms_tb)):
             gbs = rows * C * bpe / ms / 1e6
             print(json.dumps({"kernel": name, "rows": rows, "C": C, "io": "fp32 -> bf16", "us": round(ms * 1e3, 1),
                               "algorithmic_GBps": round(gbs, 1), "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3),
                               "aten_us": round(ref * 1e3, 1)}), flush=True)
-        del xs, ys
+        del xs
 
 
 def bench_attn(engine):
@@ -153,16 +152,13 @@ def bench_attn(engine):
                 with torch.no_grad():
                     blk.attend(qs[i])
             ms_f = time_ms(fwd_nograd, nbuf)
-            for i in range(nbuf):
-                fwd(i)
             params = [p for a in blk.attns for p in (a.get_v.weight, a.get_v.bias)]
 
-            def bwd(i):
-                torch.autograd.grad(outs[i], [qs[i]] + params, g, retain_graph=True)
-            ms_b = time_ms(bwd, nbuf)
+            def fwd_bwd(i):  # forward + backward inside one captured region (same stream)
+                torch.autograd.grad(blk.attend(qs[i]), [qs[i]] + params, g)
+            ms_b = time_ms(fwd_bwd, nbuf) - ms_f
             csbF.set_kernel_timer(t)
-            fwd(0)
-            bwd(0)
+            fwd_bwd(0)
             csbF.set_kernel_timer(None)
             work = t.summary()
             for fam, ms in (("attn_fwd", ms_f), ("attn_bwd", ms_b)):

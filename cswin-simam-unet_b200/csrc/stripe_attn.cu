@@ -29,7 +29,8 @@ int make_geom(const csb200_stripe_desc* d, bool backward, StripeGeom* g) {
   if (d->head_dim != 32)
     return fail(CSB200_ERR_UNSUPPORTED, "stripe_attn: head_dim %d (only 32 is built)",
                 d->head_dim);
-  if ((int64_t)d->height * d->width > 0x7fffffff / 4)
+  if ((int64_t)d->height * d->width > 0x7fffffff / 4 ||
+      (int64_t)d->batch * d->height * d->width > 0x7fffffff)
     return fail(CSB200_ERR_INVALID, "stripe_attn: token grid too large");
   const int64_t strides[] = {d->q_sb, d->q_sl, d->k_sb, d->k_sl, d->v_sb, d->v_sl, d->o_sb, d->o_sl};
   for (int64_t s : strides)

@@ -396,17 +396,17 @@ __global__ void __launch_bounds__(PREP_THREADS, 3)
   __syncthreads();
   const int cg = threadIdx.x & 7;              // which 4 of the head's 32 channels
   const int co = head * HD + cg * 4;
-  const int64_t total = (int64_t)g.B * g.L;
-  const int64_t t_begin = (int64_t)blockIdx.x * tok_per_cta;
+  const int total = g.B * g.L;                       // < 2^31 (checked on the host)
+  const int t_begin = blockIdx.x * tok_per_cta;
   float4 acc[10];
 #pragma unroll
   for (int t = 0; t < 10; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
 
   for (int it = threadIdx.x >> 3; it < tok_per_cta; it += PREP_TOK_PER_ITER) {
-    const int64_t gt = t_begin + it;
+    const int gt = t_begin + it;
     const bool valid = gt < total;  // no early exit: every lane takes part in the shuffles below
-    const int b = valid ? (int)(gt / g.L) : 0, l = valid ? (int)(gt % g.L) : 0;
-    const int y = l / g.W, x = l % g.W, yy = y % g.hs, xx = x % g.ws;
+    const int b = valid ? gt / g.L : 0, l = valid ? gt - b * g.L : 0;
+    const int y = l / g.W, x = l - y * g.W, yy = y % g.hs, xx = x % g.ws;
     float4 go = make_float4(0.f, 0.f, 0.f, 0.f), o = go;
     if (valid) {
       go = ld4<T>(gout + (int64_t)b * g.o_sb + (int64_t)l * g.o_sl + co);
@@ -516,12 +516,15 @@ int bwd_t(const StripeGeom& g, const void* q, const void* k, const void* v, cons
 
 }  // namespace
 
-// tokens per CTA of lepe_bwd_prep: long ranges amortise the final reduction, but keep >= ~4 CTAs/SM
+// tokens per CTA of lepe_bwd_prep: ONE wave of CTAs (3 x 148, split over the heads), each walking a
+// contiguous token range — the 40 accumulators are reduced once per CTA, and the final sum reads
+// at most ~444 partials per output.
 static int prep_tok_per_cta(const StripeGeom& g) {
   const int64_t total = (int64_t)g.B * g.L;
-  int tpc = 2048;
-  while (tpc > PREP_TOK_PER_ITER && (total + tpc - 1) / tpc * g.heads < 600) tpc >>= 1;
-  return tpc;
+  const int ctas_per_head = (444 + g.heads - 1) / g.heads;
+  int64_t tpc = (total + ctas_per_head - 1) / ctas_per_head;
+  tpc = (tpc + PREP_TOK_PER_ITER - 1) / PREP_TOK_PER_ITER * PREP_TOK_PER_ITER;
+  return (int)(tpc < PREP_TOK_PER_ITER ? PREP_TOK_PER_ITER : tpc);
 }
 int wgrad_blocks(const StripeGeom& g) {
   const int tpc = prep_tok_per_cta(g);

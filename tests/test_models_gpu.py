@@ -157,3 +157,62 @@ def test_cuda_graph_step_matches_eager_step():
         losses[mode] = run
     assert np.allclose(losses[True], losses[False], rtol=2e-3), losses
     assert losses[True][-1] != losses[True][0]
+
+
+def test_cuda_graph_step_with_reducer_single_rank():
+    """The data-parallel graph path (two graphs around the bucket all-reduce) on one rank: same
+    trajectory as the plain eager step; gradients live in the reducer's flat buckets."""
+    losses = {}
+    for mode in ("eager", "graph+reducer"):
+        torch.manual_seed(0)
+        net = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], simam=True).cuda()
+        graph = mode != "eager"
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=1e-4, fused=True, capturable=graph)
+        red = pkg.GradientAllReducer(net.parameters()) if graph else None
+        step = pkg.TrainStep(net, opt, precision="bf16", reducer=red, cuda_graph=graph)
+        run = []
+        for it in range(4):
+            x, y = pkg.synthetic_batch(2, 64, "cuda", seed=it)
+            run.append(step(x, y).item())
+        losses[mode] = run
+    assert np.allclose(losses["graph+reducer"], losses["eager"], rtol=2e-3), losses
+
+
+def test_config2_unet_simam_bf16_train_step():
+    """BASELINE config 2: plain UNet + SimAM after every DoubleConv, 256^2, batch 16, bf16."""
+    torch.manual_seed(0)
+    net = pkg.UNet(simam=True).cuda()
+    step = pkg.TrainStep(net, torch.optim.Adam(net.parameters(), lr=1e-3, weight_decay=1e-4), precision="bf16")  # U:486
+    x, y = pkg.synthetic_batch(16, 256, "cuda", seed=0)
+    n0 = pkg.capi.launch_count()
+    losses = [step(x, y).item() for _ in range(4)]
+    assert pkg.capi.launch_count() - n0 >= 4 * 18  # 9 SimAM sites, forward + backward, every step
+    assert all(np.isfinite(losses)) and losses[-1] < losses[0]
+
+
+@pytest.mark.parametrize("size,sw", [(1024, 1), (1024, 2), (1024, 8), (896, 7)])
+def test_config5_high_res_inference_stripe_width_sweep(size, sw):
+    """BASELINE config 5: 1024^2 inference with uniform stripe widths.  sw = 7 does not divide the
+    1024 grid (the reference raises from view()), so that point runs at 896^2.
+    Checked: bf16 logits against this package's own fp32 path (<= 2e-2, the stated bf16 tolerance)
+    and one image against the CPU oracle for the cheapest case."""
+    torch.manual_seed(0)
+    net = pkg.CSWinTransformer(img_size=size, split_size=[sw] * 4, simam=True).cuda().eval()
+    x = torch.rand(2, 3, size, size, device="cuda")
+    with torch.no_grad():
+        ref = net.forward_logits(x).float()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            out = net.forward_logits(x).float()
+            prob = net(x)
+    assert out.shape == (2, 1, size, size) and torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= 2e-2
+    assert prob.min() >= 0 and prob.max() <= 1
+    if (size, sw) == (1024, 1):
+        cfg = om.CSWinConfig(img_size=size, split_size=[sw] * 4, simam=True)
+        p = {k: v.detach().cpu() for k, v in net.state_dict().items()}
+        with torch.no_grad():
+            want = om.cswin_unet_logits(p, x[:1].cpu(), cfg)
+        assert rel_err(ref[:1].cpu(), want) < 5e-5
+    if sw == 7:
+        with pytest.raises(RuntimeError):  # 1024/16 = 64 is not divisible by 7, exactly like the reference
+            pkg.CSWinTransformer(img_size=1024, split_size=[7] * 4).cuda()(torch.rand(1, 3, 1024, 1024, device="cuda"))
