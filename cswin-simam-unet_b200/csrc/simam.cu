@@ -587,6 +587,214 @@ __global__ void __launch_bounds__(THREADS)
 }
 
 // ------------------------------------------------------------------------------------------------
+// NLC two-sweep kernels: a cluster owns (image b, slab of CWV 16-byte vectors per row) and splits the
+// L rows among its CTAs; sweep 1 accumulates the per-channel moments (forward) or R1 / R2'
+// (backward) in registers, one slab_reduce (shuffles -> smem -> DSMEM) combines them, sweep 2
+// re-reads the rows — served by L2: an image is 2-4 MB and was just read — and writes the result.
+// Nothing is held between the sweeps, so any L fits, registers stay low (3 CTAs / SM) and DRAM
+// traffic remains 1 read + 1 write.
+// ------------------------------------------------------------------------------------------------
+template <typename T, int CWV, int CLUSTER>
+__global__ void __launch_bounds__(256, 3)
+    simam_nlc_fwd_2pass(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats, int L,
+                        int C, int slabs, int ngroups, float e_lambda) {
+  constexpr int VE = Vec16<T>::N, CW = CWV * VE, THREADS = 256, RPI = THREADS / CWV, WARPS = THREADS / 32;
+  __shared__ float s_red[WARPS * 2 * CW];
+  __shared__ float s_part[2 * CW];
+  __shared__ float s_fin[2 * CW];
+  const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  // persistent clusters: the host sizes the grid so that the groups in flight fit in L2
+  for (int group = blockIdx.x / CLUSTER; group < ngroups; group += gridDim.x / CLUSTER) {
+  const int b = group / slabs, slab = group % slabs, cv = threadIdx.x % CWV;
+  const int cvec = C / VE;
+  const int rpc = (L + CLUSTER - 1) / CLUSTER;
+  const int r_begin = rank * rpc + threadIdx.x / CWV, r_end = min(L, (rank + 1) * rpc);
+  const int64_t base = (int64_t)b * L * cvec + slab * CWV + cv;
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + base;
+  uint4* yp = reinterpret_cast<uint4*>(y) + base;
+  float pivot[VE];
+  unpack<T>(__ldg(xp), pivot);  // row 0 of the image, this thread's channels
+  float acc[2][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+  for (int r = r_begin; r < r_end; r += 4 * RPI) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      u[i] = (r + i * RPI < r_end) ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r + i * RPI < r_end) {
+        float f[VE];
+        unpack<T>(u[i], f);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          const float d = f[e] - pivot[e];
+          acc[0][e] += d;
+          acc[1][e] = fmaf(d, d, acc[1][e]);
+        }
+      }
+    }
+  }
+  slab_reduce<VE, CWV, THREADS, CLUSTER, 2>(acc, s_red, s_part, s_fin);
+  float mean[VE], k[VE];  // full mean; 1/(8v) (bf16) or 1/(4v) (fp32)
+  FwdCoef cf[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) {
+    const float dmean = acc[0][e] / (float)L;
+    const float var = fmaxf(acc[1][e] - acc[0][e] * dmean, 0.f) / ((float)L - 1.f) + e_lambda;
+    mean[e] = pivot[e] + dmean;
+    k[e] = 1.f / (8.f * var);
+    cf[e] = FwdCoef{pivot[e], dmean, 2.f * k[e]};
+    acc[0][e] = dmean;
+    acc[1][e] = var;
+  }
+  if (stats != nullptr && rank == 0 && threadIdx.x < CWV) {
+    const int64_t p0 = (int64_t)b * C + slab * CW + cv * VE;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      stats[2 * (p0 + e)] = acc[0][e];
+      stats[2 * (p0 + e) + 1] = acc[1][e];
+    }
+  }
+  for (int r = r_begin; r < r_end; r += 4 * RPI) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+      u[i] = (r + i * RPI < r_end) ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      if (r + i * RPI < r_end) {
+        float f[VE];
+        unpack<T>(u[i], f);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          if constexpr (sizeof(T) == 2) f[e] = simam_fwd_fast(f[e], mean[e], k[e]);
+          else f[e] = simam_fwd_elem<T>(f[e], cf[e]);
+        }
+        st_stream(yp + (int64_t)(r + i * RPI) * cvec, pack<T>(f));
+      }
+    }
+  }
+  if constexpr (CLUSTER > 1) cluster_sync_all();  // peers have finished reading s_part
+  }
+}
+
+template <typename T, int CWV, int CLUSTER>
+__global__ void __launch_bounds__(256, 2)
+    simam_nlc_bwd_2pass(const T* __restrict__ x, const T* __restrict__ gy,
+                        const float* __restrict__ stats, T* __restrict__ gx, int L, int C, int slabs,
+                        int ngroups) {
+  constexpr int VE = Vec16<T>::N, CW = CWV * VE, THREADS = 256, RPI = THREADS / CWV, WARPS = THREADS / 32;
+  __shared__ float s_red[WARPS * 2 * CW];
+  __shared__ float s_part[2 * CW];
+  __shared__ float s_fin[2 * CW];
+  const int rank = CLUSTER > 1 ? (int)cluster_ctarank() : 0;
+  for (int group = blockIdx.x / CLUSTER; group < ngroups; group += gridDim.x / CLUSTER) {
+  const int b = group / slabs, slab = group % slabs, cv = threadIdx.x % CWV;
+  const int cvec = C / VE;
+  const int rpc = (L + CLUSTER - 1) / CLUSTER;
+  const int r_begin = rank * rpc + threadIdx.x / CWV, r_end = min(L, (rank + 1) * rpc);
+  const int64_t base = (int64_t)b * L * cvec + slab * CWV + cv;
+  const uint4* xp = reinterpret_cast<const uint4*>(x) + base;
+  const uint4* gp = reinterpret_cast<const uint4*>(gy) + base;
+  uint4* op = reinterpret_cast<uint4*>(gx) + base;
+  float pivot[VE], mean[VE], inv4v[VE], vv[VE];  // mean[]: full mean (bf16) or mean - pivot (fp32)
+  unpack<T>(__ldg(xp), pivot);
+  {
+    const int64_t p0 = (int64_t)b * C + slab * CW + cv * VE;
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      const float dm = __ldg(stats + 2 * (p0 + e));
+      mean[e] = sizeof(T) == 2 ? pivot[e] + dm : dm;
+      vv[e] = __ldg(stats + 2 * (p0 + e) + 1);
+      inv4v[e] = 1.f / (4.f * vv[e]);
+    }
+  }
+  // a4 = 4 a = g x (1 - tanh^2) (bf16) or 4 g x s (1 - s) (fp32); t is formed against (pivot, dmean)
+  auto elem = [&](float xe, float ge, int e, float& t, float& dd, float& a4, float& gs) {
+    if constexpr (sizeof(T) == 2) {
+      t = xe - mean[e];
+      dd = t * t;
+      float th;
+      asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(fmaf(dd, 0.5f * inv4v[e], 0.25f)));
+      a4 = ge * xe * fmaf(-th, th, 1.f);
+      const float hg = 0.5f * ge;
+      gs = fmaf(hg, th, hg);
+    } else {
+      t = (xe - pivot[e]) - mean[e];
+      dd = t * t;
+      const float sg = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
+      a4 = 4.f * ge * xe * sg * (1.f - sg);
+      gs = ge * sg;
+    }
+  };
+  float acc[2][VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+  for (int r = r_begin; r < r_end; r += 2 * RPI) {
+    uint4 ux[2], ug[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = r + i * RPI < r_end;
+      ux[i] = ok ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+      ug[i] = ok ? ld_stream(gp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (r + i * RPI < r_end) {
+        float fx[VE], fg[VE];
+        unpack<T>(ux[i], fx);
+        unpack<T>(ug[i], fg);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          float t, dd, a4, gs;
+          elem(fx[e], fg[e], e, t, dd, a4, gs);
+          acc[0][e] = fmaf(a4, dd, acc[0][e]);
+          acc[1][e] = fmaf(a4, t, acc[1][e]);
+        }
+      }
+    }
+  }
+  slab_reduce<VE, CWV, THREADS, CLUSTER, 2>(acc, s_red, s_part, s_fin);
+  float k1[VE], k2[VE], c2[VE];
+#pragma unroll
+  for (int e = 0; e < VE; ++e) {
+    const float r1 = 0.25f * acc[0][e], r2 = 0.25f * acc[1][e];
+    const float c1 = r1 * inv4v[e] / (vv[e] * ((float)L - 1.f));
+    c2[e] = 2.f / (float)L * r2 * inv4v[e];
+    k1[e] = 0.5f * inv4v[e];  // 2 (a inv4v - c1) = a4 k1 - k2
+    k2[e] = 2.f * c1;
+  }
+  for (int r = r_begin; r < r_end; r += 2 * RPI) {
+    uint4 ux[2], ug[2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const bool ok = r + i * RPI < r_end;
+      ux[i] = ok ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+      ug[i] = ok ? ld_stream(gp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      if (r + i * RPI < r_end) {
+        float fx[VE], fg[VE];
+        unpack<T>(ux[i], fx);
+        unpack<T>(ug[i], fg);
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          float t, dd, a4, gs;
+          elem(fx[e], fg[e], e, t, dd, a4, gs);
+          fx[e] = fmaf(t, fmaf(a4, k1[e], -k2[e]), gs) - c2[e];
+        }
+        st_stream(op + (int64_t)(r + i * RPI) * cvec, pack<T>(fx));
+      }
+    }
+  }
+  if constexpr (CLUSTER > 1) cluster_sync_all();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // generic (any shape, any alignment): element (plane p, position i) at  base(p) + i * istride.
 //   NCHW: base = p*S, istride = 1, 256 threads per plane, one plane per CTA.
 //   NLC : blockDim = (32 channels, 8 row groups); a CTA covers 32 adjacent channels of one image.
@@ -1122,6 +1330,47 @@ int nchw_resident(const T* x, const T* gy, float* stats_out, const float* stats_
 #undef CSB_NCHW
 }
 
+// NLC two-sweep dispatch: widest slab (128/64/32 B per row) that divides the row, and the smallest
+// cluster that puts >= 2 CTAs on every SM (or 8).
+template <typename T, bool BWD>
+int nlc_2pass(const T* x, const T* gy, float* stats_out, const float* stats_in, T* out, int64_t B,
+              int64_t C, int64_t L, float e_lambda, cudaStream_t st) {
+  constexpr int VE = Vec16<T>::N;
+  if (C % VE != 0 || !aligned16(x) || !aligned16(out) || (BWD && !aligned16(gy))) return -1;
+  if (L > 0x7fffffff / 64 || B * C > 0x7fffffff || L < 2) return -1;
+  const int cvec = (int)(C / VE);
+  const int cwv = cvec % 8 == 0 ? 8 : (cvec % 4 == 0 ? 4 : (cvec % 2 == 0 ? 2 : 0));
+  if (cwv == 0) return -1;
+  const int slabs = cvec / cwv;
+  const int64_t groups = B * slabs;
+  int cluster = 1;
+  while (cluster < 8 && groups * cluster < 296 && L / (cluster * 2) >= 256 / cwv) cluster *= 2;
+  // One cluster per group, all resident at once: measured faster than throttling the groups in
+  // flight to an L2 budget (more bytes in flight beats a higher second-sweep hit rate).
+  const int64_t resident = groups;
+  const int ngroups = (int)groups;
+#define CSB_2P(CWV, CL)                                                                           \
+  do {                                                                                            \
+    if constexpr (BWD)                                                                            \
+      return launch(simam_nlc_bwd_2pass<T, CWV, CL>, resident * (CL), 256, CL, st,                \
+                    "simam_nlc_bwd_2pass", x, gy, stats_in, out, (int)L, (int)C, slabs, ngroups); \
+    else                                                                                          \
+      return launch(simam_nlc_fwd_2pass<T, CWV, CL>, resident * (CL), 256, CL, st,                \
+                    "simam_nlc_fwd_2pass", x, out, stats_out, (int)L, (int)C, slabs, ngroups,     \
+                    e_lambda);                                                                    \
+  } while (0)
+#define CSB_2P_CL(CWV)                     \
+  if (cluster == 1) CSB_2P(CWV, 1);        \
+  if (cluster == 2) CSB_2P(CWV, 2);        \
+  if (cluster == 4) CSB_2P(CWV, 4);        \
+  CSB_2P(CWV, 8);
+  if (cwv == 8) { CSB_2P_CL(8) }
+  if (cwv == 4) { CSB_2P_CL(4) }
+  CSB_2P_CL(2)
+#undef CSB_2P_CL
+#undef CSB_2P
+}
+
 // NLC resident dispatch: widest slab (128/64/32 B per row) whose L rows fit a cluster of <= 8 CTAs.
 template <typename T, bool BWD>
 int nlc_resident(const T* x, const T* gy, float* stats_out, const float* stats_in, T* out,
@@ -1182,7 +1431,9 @@ int simam_dispatch(const void* x_, const void* gy_, float* stats_out, const floa
   }
   int rc = (layout == CSB200_NCHW)
                ? nchw_resident<T, BWD>(x, gy, stats_out, stats_in, out, B * C, S, e_lambda, st)
-               : nlc_resident<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, st);
+               : nlc_2pass<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, st);
+  if (rc < 0 && layout == CSB200_NLC)
+    rc = nlc_resident<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, st);
   if (rc >= 0) return rc;
   const int64_t grid = (layout == CSB200_NCHW) ? B * C : B * ((C + 31) / 32);
   return launch(simam_generic<T, BWD>, grid, 256, 1, st, "simam_generic", x, gy, stats_out,
