@@ -27,6 +27,13 @@ class StripeDesc(ctypes.Structure):
                                       "dq_sb", "dq_sl", "dk_sb", "dk_sl", "dv_sb", "dv_sl")]
 
 
+class BranchIO(ctypes.Structure):
+    """Mirror of csb200_branch_io."""
+    _fields_ = [(n, ctypes.c_void_p) for n in ("q", "k", "v", "lepe_w", "lepe_b", "out", "lse", "grad_out", "dq",
+                                               "dk", "dv", "grad_lepe_w", "grad_lepe_b", "workspace")] + \
+               [("workspace_bytes", ctypes.c_size_t)]
+
+
 _lib = None
 _lock = threading.Lock()
 
@@ -35,7 +42,8 @@ EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_coun
            "csb200_layernorm_bwd_workspace_bytes", "csb200_layernorm_bwd", "csb200_colsum_supported",
            "csb200_colsum_workspace_bytes", "csb200_colsum", "csb200_carafe_supported", "csb200_carafe_fwd",
            "csb200_carafe_bwd", "csb200_stripe_attn_engine", "csb200_stripe_attn_fwd",
-           "csb200_stripe_attn_bwd_workspace_bytes", "csb200_stripe_attn_bwd")
+           "csb200_stripe_attn_bwd_workspace_bytes", "csb200_stripe_attn_bwd", "csb200_cross_stripe_attn_fwd",
+           "csb200_cross_stripe_attn_bwd")
 
 
 def lib() -> ctypes.CDLL:
@@ -82,6 +90,10 @@ def lib() -> ctypes.CDLL:
         L.csb200_stripe_attn_bwd_workspace_bytes.argtypes = [dp]
         L.csb200_stripe_attn_bwd_workspace_bytes.restype = ctypes.c_size_t
         L.csb200_stripe_attn_bwd.argtypes = [dp] + [vp] * 14 + [ctypes.c_size_t, vp]
+        bp = ctypes.POINTER(BranchIO)
+        L.csb200_cross_stripe_attn_fwd.argtypes = [ctypes.c_int, dp, bp, vp]
+        L.csb200_cross_stripe_attn_bwd.argtypes = [ctypes.c_int, dp, bp, vp]
+        L.csb200_cross_stripe_attn_fwd.restype = L.csb200_cross_stripe_attn_bwd.restype = ctypes.c_int
         for fn in ("csb200_simam_fwd", "csb200_simam_bwd", "csb200_stripe_attn_engine",
                    "csb200_stripe_attn_fwd", "csb200_stripe_attn_bwd"):
             getattr(L, fn).restype = ctypes.c_int

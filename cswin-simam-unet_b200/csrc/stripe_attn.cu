@@ -161,3 +161,86 @@ extern "C" int csb200_stripe_attn_bwd(const csb200_stripe_desc* d, const void* q
   return simt_bwd(g, d->dtype, q, k, v, lepe_w, lepe_b, out, grad_out, lse, dq, dk, dv,
                   grad_lepe_w, grad_lepe_b, delta, partial, st);
 }
+
+// ---- all branches of a block -------------------------------------------------------------------
+namespace {
+bool mergeable(const csb200_stripe_desc* d, const StripeGeom* g, int n, bool backward) {
+  if (n != 2) return false;
+  for (int i = 0; i < 2; ++i)
+    if (pick_engine(&d[i], g[i], backward) != CSB200_ENGINE_TCGEN05) return false;
+  return g[0].N == g[1].N && g[0].B == g[1].B && g[0].H == g[1].H && g[0].W == g[1].W &&
+         g[0].scale == g[1].scale && d[0].dtype == d[1].dtype;
+}
+}  // namespace
+
+extern "C" int csb200_cross_stripe_attn_fwd(int n, const csb200_stripe_desc* d,
+                                            const csb200_branch_io* io, void* stream) {
+  if (n < 1 || n > 2 || !d || !io) return fail(CSB200_ERR_INVALID, "cross_stripe_attn: 1 or 2 branches");
+  StripeGeom g[2];
+  for (int i = 0; i < n; ++i) {
+    int rc = make_geom(&d[i], false, &g[i]);
+    if (rc != CSB200_OK) return rc;
+  }
+  if (g[0].B > 0 && mergeable(d, g, n, false)) {
+    TcFwdIO t[2];
+    for (int i = 0; i < 2; ++i) {
+      if (!io[i].q || !io[i].k || !io[i].v || !io[i].lepe_w || !io[i].lepe_b || !io[i].out || !io[i].lse)
+        return fail(CSB200_ERR_INVALID, "cross_stripe_attn_fwd: null pointer");
+      if (!aligned(io[i].q, 16) || !aligned(io[i].k, 16) || !aligned(io[i].v, 16) || !aligned(io[i].out, 16))
+        return fail(CSB200_ERR_INVALID, "cross_stripe_attn_fwd: q/k/v/out must be 16-byte aligned");
+      t[i] = TcFwdIO{io[i].q, io[i].k, io[i].v, io[i].lepe_w, io[i].lepe_b, io[i].out, io[i].lse};
+    }
+    return tc_fwd_multi(2, g, t, static_cast<cudaStream_t>(stream));
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc = csb200_stripe_attn_fwd(&d[i], io[i].q, io[i].k, io[i].v, io[i].lepe_w, io[i].lepe_b,
+                                    io[i].out, io[i].lse, stream);
+    if (rc != CSB200_OK) return rc;
+  }
+  return CSB200_OK;
+}
+
+extern "C" int csb200_cross_stripe_attn_bwd(int n, const csb200_stripe_desc* d,
+                                            const csb200_branch_io* io, void* stream) {
+  if (n < 1 || n > 2 || !d || !io) return fail(CSB200_ERR_INVALID, "cross_stripe_attn: 1 or 2 branches");
+  StripeGeom g[2];
+  for (int i = 0; i < n; ++i) {
+    int rc = make_geom(&d[i], true, &g[i]);
+    if (rc != CSB200_OK) return rc;
+  }
+  if (g[0].B > 0 && mergeable(d, g, n, true)) {
+    PrepIO pio[2];
+    TcBwdIO tio[2];
+    for (int i = 0; i < 2; ++i) {
+      const csb200_branch_io& b = io[i];
+      if (!b.q || !b.k || !b.v || !b.lepe_w || !b.lepe_b || !b.out || !b.grad_out || !b.lse || !b.dq ||
+          !b.dk || !b.dv || !b.grad_lepe_w || !b.grad_lepe_b || !b.workspace)
+        return fail(CSB200_ERR_INVALID, "cross_stripe_attn_bwd: null pointer");
+      const void* ptrs[] = {b.q, b.k, b.v, b.out, b.grad_out, b.dq, b.dk, b.dv, b.workspace};
+      for (const void* ptr : ptrs)
+        if (!aligned(ptr, 16))
+          return fail(CSB200_ERR_INVALID, "cross_stripe_attn_bwd: tensors must be 16-byte aligned");
+      if (b.workspace_bytes < csb200_stripe_attn_bwd_workspace_bytes(&d[i]))
+        return fail(CSB200_ERR_WORKSPACE, "cross_stripe_attn_bwd: workspace too small");
+      float* delta = static_cast<float*>(b.workspace);
+      float* partial = reinterpret_cast<float*>(
+          static_cast<char*>(b.workspace) +
+          align_up((size_t)g[i].B * g[i].heads * g[i].L * sizeof(float), 256));
+      pio[i] = PrepIO{b.v, b.out, b.grad_out, b.lepe_w, b.lepe_b, delta, partial, b.grad_lepe_w,
+                      b.grad_lepe_b};
+      tio[i] = TcBwdIO{b.q, b.k, b.v, b.grad_out, b.lepe_w, b.lse, delta, b.dq, b.dk, b.dv};
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int rc = lepe_bwd_prep_multi(2, g, d[0].dtype, pio, st);
+    if (rc != CSB200_OK) return rc;
+    return tc_bwd_multi(2, g, tio, st);
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc = csb200_stripe_attn_bwd(&d[i], io[i].q, io[i].k, io[i].v, io[i].lepe_w, io[i].lepe_b,
+                                    io[i].out, io[i].grad_out, io[i].lse, io[i].dq, io[i].dk, io[i].dv,
+                                    io[i].grad_lepe_w, io[i].grad_lepe_b, io[i].workspace,
+                                    io[i].workspace_bytes, stream);
+    if (rc != CSB200_OK) return rc;
+  }
+  return CSB200_OK;
+}

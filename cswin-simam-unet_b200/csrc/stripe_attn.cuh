@@ -26,6 +26,13 @@ int simt_bwd(const StripeGeom& g, int dtype, const void* q, const void* k, const
 // softmax gradient — plus the depthwise-3x3 weight / bias gradients (gw [C'][9], gb [C']) through
 // `partial` ([wgrad_blocks][C'][10] floats of scratch).
 int wgrad_blocks(const StripeGeom& g);
+struct PrepIO {
+  const void *v, *out, *gout;
+  const float *lepe_w, *lepe_b;
+  float *delta, *partial, *gw, *gb;
+};
+// up to two branches of equal (B, L) in one launch
+int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st);
 int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
                   const float* lepe_b, const void* out, const void* gout, float* delta,
                   float* partial, float* gw, float* gb, cudaStream_t st);
@@ -35,6 +42,20 @@ bool tc_fwd_supported(const StripeGeom& g, int dtype);
 bool tc_bwd_supported(const StripeGeom& g, int dtype);
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st);
+// up to two branches (the two stripe orientations of one CSWinBlock) in ONE launch; same N, batch
+struct TcFwdIO {
+  const void *q, *k, *v;
+  const float *lepe_w, *lepe_b;
+  void* out;
+  float* lse;
+};
+int tc_fwd_multi(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st);
+struct TcBwdIO {
+  const void *q, *k, *v, *gout;
+  const float *lepe_w, *lse, *delta;
+  void *dq, *dk, *dv;
+};
+int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st);
 // dq, dk, dv from q, k, v, grad_out, lse and delta (stripe_attn_tc_bwd.cu)
 int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
                 const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,

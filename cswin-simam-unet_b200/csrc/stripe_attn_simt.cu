@@ -13,6 +13,8 @@
 // in 64-row chunks read as warp-wide broadcasts; softmax is the online (running max / sum) form.
 // Backward recomputes the probabilities from the saved log-sum-exp (no N x N tensor ever exists).
 
+#include <cstring>
+
 #include "stripe_attn.cuh"
 
 namespace csb200 {
@@ -380,15 +382,36 @@ __global__ void __launch_bounds__(ROWS)
 constexpr int PREP_THREADS = 256;
 constexpr int PREP_TOK_PER_ITER = PREP_THREADS / 8;  // 8 lanes x 4 channels per token
 
+// arguments of one branch; a launch covers up to two (blockIdx.y runs over the heads of both)
+template <typename T>
+struct PrepBranch {
+  StripeGeom g;
+  const T *v, *out, *gout;
+  const float *lepe_w, *lepe_b;
+  float *delta, *partial;
+};
+template <typename T>
+struct PrepArgs {
+  PrepBranch<T> br[2];
+  int heads0;  // heads of branch 0
+};
+
 template <typename T>
 __global__ void __launch_bounds__(PREP_THREADS, 3)
-    lepe_bwd_prep(StripeGeom g, const T* __restrict__ v, const float* __restrict__ lepe_w,
-                  const float* __restrict__ lepe_b, const T* __restrict__ out,
-                  const T* __restrict__ gout, float* __restrict__ delta,
-                  float* __restrict__ partial, int tok_per_cta) {
+    lepe_bwd_prep(const __grid_constant__ PrepArgs<T> args, int tok_per_cta) {
   __shared__ __align__(16) float s_w[10 * HD];       // [tap][c], bias last
   __shared__ float s_part[PREP_THREADS / 32][10 * HD];
-  const int head = blockIdx.y, cp = g.heads * HD;
+  const int which = (int)blockIdx.y >= args.heads0 ? 1 : 0;
+  const PrepBranch<T>& A = args.br[which];
+  const StripeGeom& g = A.g;
+  const T* __restrict__ v = A.v;
+  const T* __restrict__ out = A.out;
+  const T* __restrict__ gout = A.gout;
+  const float* __restrict__ lepe_w = A.lepe_w;
+  const float* __restrict__ lepe_b = A.lepe_b;
+  float* __restrict__ delta = A.delta;
+  float* __restrict__ partial = A.partial;
+  const int head = (int)blockIdx.y - (which ? args.heads0 : 0), cp = g.heads * HD;
   for (int i = threadIdx.x; i < 10 * HD; i += PREP_THREADS) {
     const int tap = i / HD, c = i % HD;
     s_w[i] = tap < 9 ? __ldg(lepe_w + (head * HD + c) * 9 + tap) : __ldg(lepe_b + head * HD + c);
@@ -464,18 +487,23 @@ __global__ void __launch_bounds__(PREP_THREADS, 3)
 }
 
 // one warp per (channel, tap): lanes stride over the per-CTA partials, fixed order -> deterministic
+struct WgradFinal {
+  const float* partial;
+  int cp;
+  float *gw, *gb;
+};
 __global__ void __launch_bounds__(256)
-    lepe_wgrad_final(const float* __restrict__ partial, int blocks, int cp,
-                     float* __restrict__ gw, float* __restrict__ gb) {
+    lepe_wgrad_final(WgradFinal f0, WgradFinal f1, int blocks) {
+  const WgradFinal f = blockIdx.y ? f1 : f0;
   const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // (c, tap)
-  if (i >= cp * 10) return;
+  if (i >= f.cp * 10) return;
   float a = 0.f;
-  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * cp * 10 + i];
+  for (int b = lane; b < blocks; b += 32) a += f.partial[(int64_t)b * f.cp * 10 + i];
   a = warp_sum(a);
   if (lane != 0) return;
   const int c = i / 10, tap = i % 10;
-  if (tap == 9) gb[c] = a;
-  else gw[c * 9 + tap] = a;
+  if (tap == 9) f.gb[c] = a;
+  else f.gw[c * 9 + tap] = a;
 }
 
 template <typename T>
@@ -519,42 +547,69 @@ int bwd_t(const StripeGeom& g, const void* q, const void* k, const void* v, cons
 // tokens per CTA of lepe_bwd_prep: ONE wave of CTAs (3 x 148, split over the heads), each walking a
 // contiguous token range — the 40 accumulators are reduced once per CTA, and the final sum reads
 // at most ~444 partials per output.
-static int prep_tok_per_cta(const StripeGeom& g) {
+static int prep_tok_per_cta(const StripeGeom& g, int total_heads) {
   const int64_t total = (int64_t)g.B * g.L;
-  const int ctas_per_head = (444 + g.heads - 1) / g.heads;
+  const int ctas_per_head = (444 + total_heads - 1) / total_heads;
   int64_t tpc = (total + ctas_per_head - 1) / ctas_per_head;
   tpc = (tpc + PREP_TOK_PER_ITER - 1) / PREP_TOK_PER_ITER * PREP_TOK_PER_ITER;
   return (int)(tpc < PREP_TOK_PER_ITER ? PREP_TOK_PER_ITER : tpc);
 }
+// upper bound on the CTAs per head (sizes the partial buffer): a single-branch launch is the worst case
 int wgrad_blocks(const StripeGeom& g) {
-  const int tpc = prep_tok_per_cta(g);
+  const int tpc = prep_tok_per_cta(g, g.heads);
   return (int)(((int64_t)g.B * g.L + tpc - 1) / tpc);
+}
+
+template <typename T>
+int lepe_bwd_prep_multi_t(int nbr, const StripeGeom* g, const PrepIO* io, cudaStream_t st) {
+  PrepArgs<T> a;
+  memset(&a, 0, sizeof(a));
+  int heads = 0, cp_max = 0;
+  for (int i = 0; i < nbr; ++i) {
+    a.br[i].g = g[i];
+    a.br[i].v = static_cast<const T*>(io[i].v);
+    a.br[i].out = static_cast<const T*>(io[i].out);
+    a.br[i].gout = static_cast<const T*>(io[i].gout);
+    a.br[i].lepe_w = io[i].lepe_w;
+    a.br[i].lepe_b = io[i].lepe_b;
+    a.br[i].delta = io[i].delta;
+    a.br[i].partial = io[i].partial;
+    heads += g[i].heads;
+    cp_max = g[i].heads * HD > cp_max ? g[i].heads * HD : cp_max;
+  }
+  a.heads0 = g[0].heads;
+  const int tpc = prep_tok_per_cta(g[0], heads);
+  const int blocks = (int)(((int64_t)g[0].B * g[0].L + tpc - 1) / tpc);
+  lepe_bwd_prep<T><<<dim3(blocks, heads), PREP_THREADS, 0, st>>>(a, tpc);
+  int rc = check_launch("lepe_bwd_prep");
+  if (rc != CSB200_OK) return rc;
+  WgradFinal f[2];
+  for (int i = 0; i < 2; ++i) {
+    const int j = i < nbr ? i : 0;
+    f[i] = WgradFinal{io[j].partial, g[j].heads * HD, io[j].gw, io[j].gb};
+  }
+  lepe_wgrad_final<<<dim3((cp_max * 10 * 32 + 255) / 256, nbr), 256, 0, st>>>(f[0], f[1], blocks);
+  return check_launch("lepe_wgrad_final");
+}
+
+int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st) {
+  return dtype == CSB200_F32 ? lepe_bwd_prep_multi_t<float>(nbr, g, io, st)
+                             : lepe_bwd_prep_multi_t<__nv_bfloat16>(nbr, g, io, st);
 }
 
 template <typename T>
 int lepe_bwd_prep_t(const StripeGeom& g, const T* v, const float* lepe_w, const float* lepe_b,
                     const T* out, const T* gout, float* delta, float* partial, float* gw, float* gb,
                     cudaStream_t st) {
-  const int cp = g.heads * HD, blocks = wgrad_blocks(g);
-  lepe_bwd_prep<T><<<dim3(blocks, g.heads), PREP_THREADS, 0, st>>>(g, v, lepe_w, lepe_b, out, gout, delta,
-                                                                    partial, prep_tok_per_cta(g));
-  int rc = check_launch("lepe_bwd_prep");
-  if (rc != CSB200_OK) return rc;
-  lepe_wgrad_final<<<(cp * 10 * 32 + 255) / 256, 256, 0, st>>>(partial, blocks, cp, gw, gb);
-  return check_launch("lepe_wgrad_final");
+  const PrepIO io{v, out, gout, lepe_w, lepe_b, delta, partial, gw, gb};
+  return lepe_bwd_prep_multi_t<T>(1, &g, &io, st);
 }
 
 int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
                   const float* lepe_b, const void* out, const void* gout, float* delta,
                   float* partial, float* gw, float* gb, cudaStream_t st) {
-  using bf16 = __nv_bfloat16;
-  return dtype == CSB200_F32
-             ? lepe_bwd_prep_t<float>(g, static_cast<const float*>(v), lepe_w, lepe_b,
-                                      static_cast<const float*>(out), static_cast<const float*>(gout),
-                                      delta, partial, gw, gb, st)
-             : lepe_bwd_prep_t<bf16>(g, static_cast<const bf16*>(v), lepe_w, lepe_b,
-                                     static_cast<const bf16*>(out), static_cast<const bf16*>(gout),
-                                     delta, partial, gw, gb, st);
+  const PrepIO io{v, out, gout, lepe_w, lepe_b, delta, partial, gw, gb};
+  return lepe_bwd_prep_multi(1, &g, dtype, &io, st);
 }
 
 int simt_fwd(const StripeGeom& g, int dtype, const void* q, const void* k, const void* v,

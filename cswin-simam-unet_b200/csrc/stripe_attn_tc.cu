@@ -22,6 +22,7 @@
 //
 // TMEM map per buffer (N columns): S fp32 [0,N) -> P bf16 [0,N/2) -> O fp32 [N/2, N/2+32).
 
+#include <cstring>
 #include <mutex>
 
 #include "stripe_attn.cuh"
@@ -73,18 +74,28 @@ constexpr int ROW_BYTES = HD * 2;           // 64 B per token row of one head
 constexpr int TILE_BYTES = TILE * ROW_BYTES;  // 8 KB
 constexpr int LEPE_FLOATS = 10 * HD;        // 9 taps + bias for the 32 channels of a head
 
-struct FwdParams {
-  int B, W, L, hs, ws, nwy, nwx, heads;
-  int bx, by;          // TMA box extent in x / y (bx * by == 128)
-  int ws_log2;         // N is a power of two, hence so are h_sp and w_sp
-  int groups;          // B * nwy * nwx * heads
-  float scale_log2;    // scale * log2(e)
-  float scale;
+// Geometry and outputs of one branch (orientation).  A launch covers up to two branches — the
+// horizontal and the vertical stripes of one CSWinBlock (C:360-363) — whose groups are interleaved
+// image by image, so the two halves of every 128-byte line of the packed qkv buffer are consumed
+// close together in time and one launch fills the machine where two half-size ones left a tail.
+struct FwdBranch {
+  int hs, ws, ws_log2, nwy, nwx, heads, by;  // by: TMA box extent in y (bx * by == 128)
   const float* lepe_w;  // [C'][9]
   const float* lepe_b;  // [C']
   __nv_bfloat16* out;
   int64_t o_sb, o_sl;
   float* lse;
+};
+struct FwdParams {
+  int B, W, L;
+  int g0, gpi;         // groups per image of branch 0 / of both branches
+  int groups;          // B * gpi
+  float scale_log2;    // scale * log2(e)
+  float scale;
+  FwdBranch br[2];
+};
+struct FwdMaps {
+  CUtensorMap q[2], k[2], v[2];
 };
 
 // Pipeline depths per stripe length: softmax warpgroups (== TMEM buffers), K/V ring, Q ring.
@@ -120,23 +131,25 @@ __device__ __forceinline__ const uint4* sw64_chunk(const uint8_t* tile, int n, i
 }
 
 struct GroupCoord {
-  int b, wy, wx, head;
+  int b, wy, wx, head, br;
 };
 __device__ __forceinline__ GroupCoord decode_group(const FwdParams& p, int g) {
   GroupCoord c;
-  c.head = g % p.heads;
-  g /= p.heads;
-  c.wx = g % p.nwx;
-  g /= p.nwx;
-  c.wy = g % p.nwy;
-  c.b = g / p.nwy;
+  c.b = g / p.gpi;
+  int r = g - c.b * p.gpi;
+  c.br = r >= p.g0 ? 1 : 0;
+  r -= c.br ? p.g0 : 0;
+  const FwdBranch& bg = p.br[c.br];
+  c.head = r % bg.heads;
+  r /= bg.heads;
+  c.wx = r % bg.nwx;
+  c.wy = r / bg.nwx;
   return c;
 }
 
 template <int NK>
 __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
-    stripe_fwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                  const __grid_constant__ CUtensorMap tm_v, const FwdParams p) {
+    stripe_fwd_tc(const __grid_constant__ FwdMaps maps, const __grid_constant__ FwdParams p) {
   constexpr int T = NK / TILE;          // query tiles per group
   constexpr int NBOX = NK / TILE;       // TMA boxes per K (or V) load
   constexpr int NWG = Cfg<NK>::NWG, KVS = Cfg<NK>::KVS, QS = Cfg<NK>::QS;
@@ -150,9 +163,11 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
   const int my_tiles = my_groups * T;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm_q);
-    prefetch_tensormap(&tm_k);
-    prefetch_tensormap(&tm_v);
+    for (int i = 0; i < (p.gpi > p.g0 ? 2 : 1); ++i) {
+      prefetch_tensormap(&maps.q[i]);
+      prefetch_tensormap(&maps.k[i]);
+      prefetch_tensormap(&maps.v[i]);
+    }
     for (int i = 0; i < QS; ++i) {
       mbar_init(&sm.q_full[i], 1);
       mbar_init(&sm.q_empty[i], 1);
@@ -180,37 +195,38 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     int it = 0;
     for (int gi = 0; gi < my_groups; ++gi) {
       const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
+      const FwdBranch& bg = p.br[c.br];
       const int kvs = gi % KVS;
       mbar_wait(&sm.kv_empty[kvs], ((gi / KVS) & 1) ^ 1);
       // LePE taps of this head -> smem as [tap][c], bias last (plain stores, released by the arrive)
       for (int i = lane; i < LEPE_FLOATS; i += 32) {
         const int tap = i / HD, ch = i % HD;
-        sm.lepe[kvs][i] = tap < 9 ? __ldg(p.lepe_w + (c.head * HD + ch) * 9 + tap)
-                                  : __ldg(p.lepe_b + c.head * HD + ch);
+        sm.lepe[kvs][i] = tap < 9 ? __ldg(bg.lepe_w + (c.head * HD + ch) * 9 + tap)
+                                  : __ldg(bg.lepe_b + c.head * HD + ch);
       }
       if (lane == 0)
-        sm.coord[kvs] = make_int4(c.b, (c.wy * p.hs) * p.W + c.wx * p.ws, c.head, 0);
+        sm.coord[kvs] = make_int4(c.b, (c.wy * bg.hs) * p.W + c.wx * bg.ws, c.head, c.br);
       __syncwarp();
       if (lane == 0) {
         mbar_expect_tx(&sm.kv_full[kvs], 2 * Smem<NK>::KV_BYTES);
-        const int x0 = c.wx * p.ws, y0 = c.wy * p.hs;
+        const int x0 = c.wx * bg.ws, y0 = c.wy * bg.hs;
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) {
           // box `bx` covers in-stripe rows [128 bx, 128 bx + 128)
-          const int dx = (p.ws > TILE) ? (bx * TILE) % p.ws : 0;
-          const int dy = (p.ws > TILE) ? (bx * TILE) / p.ws : bx * p.by;
-          tma_load_4d(sm.k[kvs] + bx * TILE_BYTES, &tm_k, &sm.kv_full[kvs], c.head * HD, x0 + dx,
-                      y0 + dy, c.b);
-          tma_load_4d(sm.v[kvs] + bx * TILE_BYTES, &tm_v, &sm.kv_full[kvs], c.head * HD, x0 + dx,
-                      y0 + dy, c.b);
+          const int dx = (bg.ws > TILE) ? (bx * TILE) % bg.ws : 0;
+          const int dy = (bg.ws > TILE) ? (bx * TILE) / bg.ws : bx * bg.by;
+          tma_load_4d(sm.k[kvs] + bx * TILE_BYTES, &maps.k[c.br], &sm.kv_full[kvs], c.head * HD,
+                      x0 + dx, y0 + dy, c.b);
+          tma_load_4d(sm.v[kvs] + bx * TILE_BYTES, &maps.v[c.br], &sm.kv_full[kvs], c.head * HD,
+                      x0 + dx, y0 + dy, c.b);
         }
         for (int t = 0; t < T; ++t, ++it) {
           const int qs = it % QS;
           mbar_wait(&sm.q_empty[qs], ((it / QS) & 1) ^ 1);
           mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
-          const int dx = (p.ws > TILE) ? (t * TILE) % p.ws : 0;
-          const int dy = (p.ws > TILE) ? (t * TILE) / p.ws : t * p.by;
-          tma_load_4d(sm.q[qs], &tm_q, &sm.q_full[qs], c.head * HD, x0 + dx, y0 + dy, c.b);
+          const int dx = (bg.ws > TILE) ? (t * TILE) % bg.ws : 0;
+          const int dy = (bg.ws > TILE) ? (t * TILE) / bg.ws : t * bg.by;
+          tma_load_4d(sm.q[qs], &maps.q[c.br], &sm.q_full[qs], c.head * HD, x0 + dx, y0 + dy, c.b);
         }
       }
       __syncwarp();
@@ -322,10 +338,11 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
       // barrier the MMA warp used (already complete; cannot advance before this warp's kv_empty)
       mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
-      const int4 gc = sm.coord[kvs];  // image, first token of the stripe, head
+      const int4 gc = sm.coord[kvs];  // image, first token of the stripe, head, branch
+      const FwdBranch& bg = p.br[gc.w];
       const float inv_l = 1.f / l;
       const int n = t * TILE + row;  // in-stripe index
-      const int yy = n >> p.ws_log2, xx = n & (p.ws - 1);
+      const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
       float o[HD];
       const float* lw = sm.lepe[kvs];
 #pragma unroll
@@ -334,12 +351,12 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int ny = yy + ky - 1;
-        if (ny < 0 || ny >= p.hs) continue;
+        if (ny < 0 || ny >= bg.hs) continue;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int nx = xx + kx - 1;
-          if (nx < 0 || nx >= p.ws) continue;
-          const int nn = (ny << p.ws_log2) + nx;
+          if (nx < 0 || nx >= bg.ws) continue;
+          const int nn = (ny << bg.ws_log2) + nx;
           const float* wt = lw + (ky * 3 + kx) * HD;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -359,7 +376,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         }
       }
       const int tok = gc.y + yy * p.W + xx;
-      uint4* dst = reinterpret_cast<uint4*>(p.out + (int64_t)gc.x * p.o_sb + (int64_t)tok * p.o_sl +
+      uint4* dst = reinterpret_cast<uint4*>(bg.out + (int64_t)gc.x * bg.o_sb + (int64_t)tok * bg.o_sl +
                                             gc.z * HD);
 #pragma unroll
       for (int q4 = 0; q4 < 4; ++q4) {
@@ -368,7 +385,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         for (int e = 0; e < 8; ++e) f[e] = o[q4 * 8 + e];
         dst[q4] = pack<__nv_bfloat16>(f);
       }
-      p.lse[((int64_t)gc.x * p.heads + gc.z) * p.L + tok] = m * p.scale + __logf(l);
+      bg.lse[((int64_t)gc.x * bg.heads + gc.z) * p.L + tok] = m * p.scale + __logf(l);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.kv_empty[kvs]);  // this warp is done with K/V/LePE of the group
     }
@@ -380,26 +397,34 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
 }
 
 template <int NK>
-int launch_fwd(const StripeGeom& g, const void* q, const void* k, const void* v,
-               const float* lepe_w, const float* lepe_b, void* out, float* lse, cudaStream_t st) {
-  const int bx = g.ws < TILE ? g.ws : TILE, by = TILE / bx;
-  CUtensorMap mq, mk, mv;
-  int rc;
-  if ((rc = tc_make_map(&mq, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = tc_make_map(&mk, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = tc_make_map(&mv, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
+int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st) {
+  FwdMaps maps;
   FwdParams p;
-  p.B = g.B; p.W = g.W; p.L = g.L; p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx;
-  p.heads = g.heads; p.bx = bx; p.by = by;
-  p.ws_log2 = 0;
-  while ((1 << p.ws_log2) < g.ws) ++p.ws_log2;
-  p.groups = g.B * g.nwy * g.nwx * g.heads;
-  p.scale = g.scale;
-  p.scale_log2 = g.scale * 1.4426950408889634f;
-  p.lepe_w = lepe_w; p.lepe_b = lepe_b;
-  p.out = static_cast<__nv_bfloat16*>(out);
-  p.o_sb = g.o_sb; p.o_sl = g.o_sl;
-  p.lse = lse;
+  memset(&maps, 0, sizeof(maps));
+  memset(&p, 0, sizeof(p));
+  p.B = g[0].B; p.W = g[0].W; p.L = g[0].L;
+  p.scale = g[0].scale;
+  p.scale_log2 = g[0].scale * 1.4426950408889634f;
+  int gpi = 0;
+  for (int i = 0; i < nbr; ++i) {
+    const int bx = g[i].ws < TILE ? g[i].ws : TILE, by = TILE / bx;
+    int rc;
+    if ((rc = tc_make_map(&maps.q[i], io[i].q, g[i], g[i].q_sb, g[i].q_sl, bx, by)) != CSB200_OK) return rc;
+    if ((rc = tc_make_map(&maps.k[i], io[i].k, g[i], g[i].k_sb, g[i].k_sl, bx, by)) != CSB200_OK) return rc;
+    if ((rc = tc_make_map(&maps.v[i], io[i].v, g[i], g[i].v_sb, g[i].v_sl, bx, by)) != CSB200_OK) return rc;
+    FwdBranch& b = p.br[i];
+    b.hs = g[i].hs; b.ws = g[i].ws; b.nwy = g[i].nwy; b.nwx = g[i].nwx; b.heads = g[i].heads; b.by = by;
+    b.ws_log2 = 0;
+    while ((1 << b.ws_log2) < g[i].ws) ++b.ws_log2;
+    b.lepe_w = io[i].lepe_w; b.lepe_b = io[i].lepe_b;
+    b.out = static_cast<__nv_bfloat16*>(io[i].out);
+    b.o_sb = g[i].o_sb; b.o_sl = g[i].o_sl;
+    b.lse = io[i].lse;
+    if (i == 0) p.g0 = g[i].nwy * g[i].nwx * g[i].heads;
+    gpi += g[i].nwy * g[i].nwx * g[i].heads;
+  }
+  p.gpi = gpi;
+  p.groups = p.B * gpi;
 
   static int sm_count = 0;
   if (sm_count == 0) {
@@ -415,7 +440,7 @@ int launch_fwd(const StripeGeom& g, const void* q, const void* k, const void* v,
     attr_done[NK / 256] = true;
   }
   const int grid = p.groups < sm_count ? p.groups : sm_count;
-  stripe_fwd_tc<NK><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(mq, mk, mv, p);
+  stripe_fwd_tc<NK><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
   return check_launch("stripe_fwd_tc");
 }
 
@@ -432,10 +457,14 @@ bool tc_fwd_supported(const StripeGeom& g, int dtype) {
 }
 bool tc_bwd_supported(const StripeGeom& g, int dtype) { return tc_fwd_supported(g, dtype); }
 
+int tc_fwd_multi(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st) {
+  return g[0].N == 128 ? launch_fwd<128>(nbr, g, io, st) : launch_fwd<256>(nbr, g, io, st);
+}
+
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st) {
-  return g.N == 128 ? launch_fwd<128>(g, q, k, v, lepe_w, lepe_b, out, lse, st)
-                    : launch_fwd<256>(g, q, k, v, lepe_w, lepe_b, out, lse, st);
+  const TcFwdIO io{q, k, v, lepe_w, lepe_b, out, lse};
+  return tc_fwd_multi(1, &g, &io, st);
 }
 
 }  // namespace csb200

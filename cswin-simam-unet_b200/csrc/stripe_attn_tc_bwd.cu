@@ -27,6 +27,8 @@
 // [64,96).  Accumulators: (dV, dK) sets at 256 + 64 a (a = key-tile parity); dQ sets at 384 + 64 g
 // (g = group parity), 32 columns per 128-query block.
 
+#include <cstring>
+
 #include "stripe_attn.cuh"
 #include "tc_common.cuh"
 
@@ -42,16 +44,23 @@ constexpr int HALF = 64;                      // queries per convert iteration
 constexpr int DS_BLOCK_BYTES = TILE * 128;    // 128 key rows x 64 queries bf16 = 16 KB
 constexpr int THREADS = 512;
 
-struct BwdParams {
-  int B, W, L, hs, ws, nwy, nwx, heads;
-  int bx, by, ws_log2;
-  int groups;
-  float scale, scale_log2;
+// one branch (stripe orientation); a launch covers up to two, interleaved image by image
+struct BwdBranch {
+  int hs, ws, ws_log2, nwy, nwx, heads, by;
   const float* lepe_w;  // [C'][9]
   const float* lse;     // [B][heads][L]
   const float* delta;   // [B][heads][L]
   __nv_bfloat16 *dq, *dk, *dv;
   int64_t dq_sb, dq_sl, dk_sb, dk_sl, dv_sb, dv_sl;
+};
+struct BwdParams {
+  int B, W, L;
+  int g0, gpi, groups;  // groups per image of branch 0 / of both; B * gpi
+  float scale, scale_log2;
+  BwdBranch br[2];
+};
+struct BwdMaps {
+  CUtensorMap q[2], k[2], v[2], go[2];
 };
 
 template <int NK>
@@ -90,9 +99,7 @@ __device__ __forceinline__ const uint4* sw64_chunk(const uint8_t* tile, int n, i
 
 template <int NK>
 __global__ void __launch_bounds__(THREADS, 1)
-    stripe_bwd_tc(const __grid_constant__ CUtensorMap tm_q, const __grid_constant__ CUtensorMap tm_k,
-                  const __grid_constant__ CUtensorMap tm_v, const __grid_constant__ CUtensorMap tm_go,
-                  const BwdParams p) {
+    stripe_bwd_tc(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdParams p) {
   constexpr int T = NK / TILE;      // key tiles (and 128-query blocks) per group
   constexpr int NH = NK / HALF;     // 64-query half-blocks per key tile
   constexpr int NIT = T * NH;       // convert iterations per group (2 or 8: always even)
@@ -107,10 +114,12 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int total_it = my_groups * NIT;
 
   if (warp == 0 && lane == 0) {
-    prefetch_tensormap(&tm_q);
-    prefetch_tensormap(&tm_k);
-    prefetch_tensormap(&tm_v);
-    prefetch_tensormap(&tm_go);
+    for (int i = 0; i < (p.gpi > p.g0 ? 2 : 1); ++i) {
+      prefetch_tensormap(&maps.q[i]);
+      prefetch_tensormap(&maps.k[i]);
+      prefetch_tensormap(&maps.v[i]);
+      prefetch_tensormap(&maps.go[i]);
+    }
     for (int i = 0; i < GS; ++i) {
       mbar_init(&sm.grp_full[i], 1);
       mbar_init(&sm.grp_empty[i], 4);
@@ -136,38 +145,41 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == 0) {
     // ===================================== producer =========================================
     for (int gi = 0; gi < my_groups; ++gi) {
-      int g = (int)blockIdx.x + gi * (int)gridDim.x;
-      const int head = g % p.heads;
-      g /= p.heads;
-      const int wx = g % p.nwx;
-      g /= p.nwx;
-      const int wy = g % p.nwy, b = g / p.nwy;
+      const int g = (int)blockIdx.x + gi * (int)gridDim.x;
+      const int b = g / p.gpi;
+      int r = g - b * p.gpi;
+      const int br = r >= p.g0 ? 1 : 0;
+      r -= br ? p.g0 : 0;
+      const BwdBranch& bg = p.br[br];
+      const int head = r % bg.heads;
+      r /= bg.heads;
+      const int wx = r % bg.nwx, wy = r / bg.nwx;
       const int gs = gi % GS;
       mbar_wait(&sm.grp_empty[gs], ((gi / GS) & 1) ^ 1);
-      const int tok0 = (wy * p.hs) * p.W + wx * p.ws;
-      const float* lse = p.lse + ((int64_t)b * p.heads + head) * p.L;
-      const float* dl = p.delta + ((int64_t)b * p.heads + head) * p.L;
+      const int tok0 = (wy * bg.hs) * p.W + wx * bg.ws;
+      const float* lse = bg.lse + ((int64_t)b * bg.heads + head) * p.L;
+      const float* dl = bg.delta + ((int64_t)b * bg.heads + head) * p.L;
       for (int i = lane; i < NK; i += 32) {
-        const int tok = tok0 + (i >> p.ws_log2) * p.W + (i & (p.ws - 1));
+        const int tok = tok0 + (i >> bg.ws_log2) * p.W + (i & (bg.ws - 1));
         sm.lse2[gs][i] = __ldg(lse + tok) * 1.4426950408889634f;
         sm.delta[gs][i] = __ldg(dl + tok);
       }
       for (int i = lane; i < 9 * HD; i += 32)
-        sm.lepe[gs][i] = __ldg(p.lepe_w + (head * HD + i % HD) * 9 + i / HD);
-      if (lane == 0) sm.coord[gs] = make_int4(b, tok0, head, 0);
+        sm.lepe[gs][i] = __ldg(bg.lepe_w + (head * HD + i % HD) * 9 + i / HD);
+      if (lane == 0) sm.coord[gs] = make_int4(b, tok0, head, br);
       __syncwarp();
       if (lane == 0) {
         mbar_expect_tx(&sm.grp_full[gs], 4 * BSmem<NK>::OP_BYTES);
-        const int x0 = wx * p.ws, y0 = wy * p.hs;
+        const int x0 = wx * bg.ws, y0 = wy * bg.hs;
 #pragma unroll
         for (int bxi = 0; bxi < T; ++bxi) {
-          const int dx = (p.ws > TILE) ? (bxi * TILE) % p.ws : 0;
-          const int dy = (p.ws > TILE) ? (bxi * TILE) / p.ws : bxi * p.by;
+          const int dx = (bg.ws > TILE) ? (bxi * TILE) % bg.ws : 0;
+          const int dy = (bg.ws > TILE) ? (bxi * TILE) / bg.ws : bxi * bg.by;
           const int off = bxi * TILE_BYTES;
-          tma_load_4d(sm.k[gs] + off, &tm_k, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
-          tma_load_4d(sm.q[gs] + off, &tm_q, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
-          tma_load_4d(sm.v[gs] + off, &tm_v, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
-          tma_load_4d(sm.go[gs] + off, &tm_go, &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.k[gs] + off, &maps.k[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.q[gs] + off, &maps.q[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.v[gs] + off, &maps.v[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.go[gs] + off, &maps.go[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
         }
       }
       __syncwarp();
@@ -300,6 +312,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int gs = gi % GS;
       mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
       const int4 gc = sm.coord[gs];
+      const BwdBranch& bg = p.br[gc.w];
       const float* lw = sm.lepe[gs];
       const uint8_t* got = sm.go[gs];
 #pragma unroll 1
@@ -315,7 +328,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.dvdk_empty[aset]);
         const int n = kt * TILE + row;
-        const int yy = n >> p.ws_log2, xx = n & (p.ws - 1);
+        const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
         const int tok = gc.y + yy * p.W + xx;
         float dv[HD];
 #pragma unroll
@@ -324,12 +337,12 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
         for (int ky = 0; ky < 3; ++ky) {
           const int ny = yy - ky + 1;
-          if (ny < 0 || ny >= p.hs) continue;
+          if (ny < 0 || ny >= bg.hs) continue;
 #pragma unroll
           for (int kx = 0; kx < 3; ++kx) {
             const int nx = xx - kx + 1;
-            if (nx < 0 || nx >= p.ws) continue;
-            const int nn = (ny << p.ws_log2) + nx;
+            if (nx < 0 || nx >= bg.ws) continue;
+            const int nn = (ny << bg.ws_log2) + nx;
             const float* wt = lw + (ky * 3 + kx) * HD;
 #pragma unroll
             for (int q4 = 0; q4 < 4; ++q4) {
@@ -348,9 +361,9 @@ __global__ void __launch_bounds__(THREADS, 1)
             }
           }
         }
-        uint4* dvp = reinterpret_cast<uint4*>(p.dv + (int64_t)gc.x * p.dv_sb + (int64_t)tok * p.dv_sl +
+        uint4* dvp = reinterpret_cast<uint4*>(bg.dv + (int64_t)gc.x * bg.dv_sb + (int64_t)tok * bg.dv_sl +
                                               gc.z * HD);
-        uint4* dkp = reinterpret_cast<uint4*>(p.dk + (int64_t)gc.x * p.dk_sb + (int64_t)tok * p.dk_sl +
+        uint4* dkp = reinterpret_cast<uint4*>(bg.dk + (int64_t)gc.x * bg.dk_sb + (int64_t)tok * bg.dk_sl +
                                               gc.z * HD);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -373,8 +386,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         tmem_ld32(lane_base + ACC_DQ + (gi & 1) * 64 + qb * 32, rq);
         tmem_wait_ld();
         const int n = qb * TILE + row;
-        const int tok = gc.y + (n >> p.ws_log2) * p.W + (n & (p.ws - 1));
-        uint4* dqp = reinterpret_cast<uint4*>(p.dq + (int64_t)gc.x * p.dq_sb + (int64_t)tok * p.dq_sl +
+        const int tok = gc.y + (n >> bg.ws_log2) * p.W + (n & (bg.ws - 1));
+        uint4* dqp = reinterpret_cast<uint4*>(bg.dq + (int64_t)gc.x * bg.dq_sb + (int64_t)tok * bg.dq_sl +
                                               gc.z * HD);
 #pragma unroll
         for (int q4 = 0; q4 < 4; ++q4) {
@@ -398,30 +411,37 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 template <int NK>
-int launch_bwd(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
-               const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
-               void* dv, cudaStream_t st) {
-  const int bx = g.ws < TILE ? g.ws : TILE, by = TILE / bx;
-  CUtensorMap mq, mk, mv, mg;
-  int rc;
-  if ((rc = tc_make_map(&mq, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = tc_make_map(&mk, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = tc_make_map(&mv, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
-  if ((rc = tc_make_map(&mg, gout, g, g.o_sb, g.o_sl, bx, by)) != CSB200_OK) return rc;
+int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st) {
+  BwdMaps maps;
   BwdParams p;
-  p.B = g.B; p.W = g.W; p.L = g.L; p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx;
-  p.heads = g.heads; p.bx = bx; p.by = by;
-  p.ws_log2 = 0;
-  while ((1 << p.ws_log2) < g.ws) ++p.ws_log2;
-  p.groups = g.B * g.nwy * g.nwx * g.heads;
-  p.scale = g.scale;
-  p.scale_log2 = g.scale * 1.4426950408889634f;
-  p.lepe_w = lepe_w; p.lse = lse; p.delta = delta;
-  p.dq = static_cast<__nv_bfloat16*>(dq);
-  p.dk = static_cast<__nv_bfloat16*>(dk);
-  p.dv = static_cast<__nv_bfloat16*>(dv);
-  p.dq_sb = g.dq_sb; p.dq_sl = g.dq_sl; p.dk_sb = g.dk_sb; p.dk_sl = g.dk_sl;
-  p.dv_sb = g.dv_sb; p.dv_sl = g.dv_sl;
+  memset(&maps, 0, sizeof(maps));
+  memset(&p, 0, sizeof(p));
+  p.B = g[0].B; p.W = g[0].W; p.L = g[0].L;
+  p.scale = g[0].scale;
+  p.scale_log2 = g[0].scale * 1.4426950408889634f;
+  int gpi = 0;
+  for (int i = 0; i < nbr; ++i) {
+    const int bx = g[i].ws < TILE ? g[i].ws : TILE, by = TILE / bx;
+    int rc;
+    if ((rc = tc_make_map(&maps.q[i], io[i].q, g[i], g[i].q_sb, g[i].q_sl, bx, by)) != CSB200_OK) return rc;
+    if ((rc = tc_make_map(&maps.k[i], io[i].k, g[i], g[i].k_sb, g[i].k_sl, bx, by)) != CSB200_OK) return rc;
+    if ((rc = tc_make_map(&maps.v[i], io[i].v, g[i], g[i].v_sb, g[i].v_sl, bx, by)) != CSB200_OK) return rc;
+    if ((rc = tc_make_map(&maps.go[i], io[i].gout, g[i], g[i].o_sb, g[i].o_sl, bx, by)) != CSB200_OK) return rc;
+    BwdBranch& b = p.br[i];
+    b.hs = g[i].hs; b.ws = g[i].ws; b.nwy = g[i].nwy; b.nwx = g[i].nwx; b.heads = g[i].heads; b.by = by;
+    b.ws_log2 = 0;
+    while ((1 << b.ws_log2) < g[i].ws) ++b.ws_log2;
+    b.lepe_w = io[i].lepe_w; b.lse = io[i].lse; b.delta = io[i].delta;
+    b.dq = static_cast<__nv_bfloat16*>(io[i].dq);
+    b.dk = static_cast<__nv_bfloat16*>(io[i].dk);
+    b.dv = static_cast<__nv_bfloat16*>(io[i].dv);
+    b.dq_sb = g[i].dq_sb; b.dq_sl = g[i].dq_sl; b.dk_sb = g[i].dk_sb; b.dk_sl = g[i].dk_sl;
+    b.dv_sb = g[i].dv_sb; b.dv_sl = g[i].dv_sl;
+    if (i == 0) p.g0 = g[i].nwy * g[i].nwx * g[i].heads;
+    gpi += g[i].nwy * g[i].nwx * g[i].heads;
+  }
+  p.gpi = gpi;
+  p.groups = p.B * gpi;
   static int sm_count = 0;
   if (sm_count == 0) {
     int dev = 0;
@@ -435,21 +455,25 @@ int launch_bwd(const StripeGeom& g, const void* q, const void* k, const void* v,
     attr_done[NK / 256] = true;
   }
   const int grid = p.groups < sm_count ? p.groups : sm_count;
-  stripe_bwd_tc<NK><<<grid, THREADS, smem, st>>>(mq, mk, mv, mg, p);
+  stripe_bwd_tc<NK><<<grid, THREADS, smem, st>>>(maps, p);
   return check_launch("stripe_bwd_tc");
 }
 
 }  // namespace
 
-int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
-                const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
-                void* dv, cudaStream_t st) {
+int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st) {
   static_assert(sizeof(BSmem<128>) + 1024 > 114 * 1024 && sizeof(BSmem<256>) + 1024 > 114 * 1024,
                 "two CTAs must not fit one SM");
   static_assert(sizeof(BSmem<128>) + 1024 <= 227 * 1024 && sizeof(BSmem<256>) + 1024 <= 227 * 1024,
                 "shared memory budget");
-  return g.N == 128 ? launch_bwd<128>(g, q, k, v, gout, lepe_w, lse, delta, dq, dk, dv, st)
-                    : launch_bwd<256>(g, q, k, v, gout, lepe_w, lse, delta, dq, dk, dv, st);
+  return g[0].N == 128 ? launch_bwd<128>(nbr, g, io, st) : launch_bwd<256>(nbr, g, io, st);
+}
+
+int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
+                const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
+                void* dv, cudaStream_t st) {
+  const TcBwdIO io{q, k, v, gout, lepe_w, lse, delta, dq, dk, dv};
+  return tc_bwd_multi(1, &g, &io, st);
 }
 
 }  // namespace csb200

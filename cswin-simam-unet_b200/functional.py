@@ -360,14 +360,21 @@ class _CrossStripeFn(torch.autograd.Function):
         ws = [w.detach().float().contiguous() for w in wb]
         lib = capi.lib()
         st = _vp(capi.stream_of(qkv))
-        with torch.cuda.device(qkv.device):
-            for i, br in enumerate(branches):
-                d = _desc(code, B, H, W, br, scale, engine, [(L * C3, C3)] * 3, (L * C, C))
-                with _span("attn_fwd", *_attn_work(B, L, br, qkv.element_size(), False)):
-                    capi.check(lib.csb200_stripe_attn_fwd(
-                        ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
-                        _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(lses[i]), st),
-                        "csb200_stripe_attn_fwd")
+        n = len(branches)
+        descs = (capi.StripeDesc * n)()
+        ios = (capi.BranchIO * n)()
+        nbytes = flops = 0
+        for i, br in enumerate(branches):
+            descs[i] = _desc(code, B, H, W, br, scale, engine, [(L * C3, C3)] * 3, (L * C, C))
+            io = ios[i]
+            io.q, io.k, io.v = (_ptr(qkv, br.chan0).value, _ptr(qkv, C + br.chan0).value,
+                                _ptr(qkv, 2 * C + br.chan0).value)
+            io.lepe_w, io.lepe_b = ws[2 * i].data_ptr(), ws[2 * i + 1].data_ptr()
+            io.out, io.lse = _ptr(out, br.chan0).value, lses[i].data_ptr()
+            w_ = _attn_work(B, L, br, qkv.element_size(), False)
+            nbytes, flops = nbytes + w_[0], flops + w_[1]
+        with torch.cuda.device(qkv.device), _span("attn_fwd", nbytes, flops):
+            capi.check(lib.csb200_cross_stripe_attn_fwd(n, descs, ios, st), "csb200_cross_stripe_attn_fwd")
         ctx.save_for_backward(qkv, out, *lses, *ws)
         ctx.cfg = (H, W, branches, scale, engine)
         return out
@@ -387,22 +394,33 @@ class _CrossStripeFn(torch.autograd.Function):
         gqkv = torch.empty_like(qkv)
         lib = capi.lib()
         st = _vp(capi.stream_of(qkv))
-        grads = []
-        with torch.cuda.device(qkv.device):
-            for i, br in enumerate(branches):
-                s3 = [(L * C3, C3)] * 3
-                d = _desc(code, B, H, W, br, scale, engine, s3, (L * C, C), s3)
-                nbytes = lib.csb200_stripe_attn_bwd_workspace_bytes(ctypes.byref(d))
-                wsp = torch.empty(max(nbytes, 16), dtype=torch.uint8, device=qkv.device)
-                gw = torch.empty_like(ws[2 * i])
-                gb = torch.empty_like(ws[2 * i + 1])
-                with _span("attn_bwd", *_attn_work(B, L, br, qkv.element_size(), True)):
-                    capi.check(lib.csb200_stripe_attn_bwd(
-                        ctypes.byref(d), _ptr(qkv, br.chan0), _ptr(qkv, C + br.chan0), _ptr(qkv, 2 * C + br.chan0),
-                        _ptr(ws[2 * i]), _ptr(ws[2 * i + 1]), _ptr(out, br.chan0), _ptr(gout, br.chan0),
-                        _ptr(lses[i]), _ptr(gqkv, br.chan0), _ptr(gqkv, C + br.chan0), _ptr(gqkv, 2 * C + br.chan0),
-                        _ptr(gw), _ptr(gb), _ptr(wsp), nbytes, st), "csb200_stripe_attn_bwd")
-                grads += [gw, gb]
+        grads, keep = [], []
+        n = len(branches)
+        descs = (capi.StripeDesc * n)()
+        ios = (capi.BranchIO * n)()
+        nbytes = flops = 0
+        for i, br in enumerate(branches):
+            s3 = [(L * C3, C3)] * 3
+            descs[i] = _desc(code, B, H, W, br, scale, engine, s3, (L * C, C), s3)
+            nws = lib.csb200_stripe_attn_bwd_workspace_bytes(ctypes.byref(descs[i]))
+            wsp = torch.empty(max(nws, 16), dtype=torch.uint8, device=qkv.device)
+            gw, gb = torch.empty_like(ws[2 * i]), torch.empty_like(ws[2 * i + 1])
+            keep.append(wsp)
+            io = ios[i]
+            io.q, io.k, io.v = (_ptr(qkv, br.chan0).value, _ptr(qkv, C + br.chan0).value,
+                                _ptr(qkv, 2 * C + br.chan0).value)
+            io.lepe_w, io.lepe_b = ws[2 * i].data_ptr(), ws[2 * i + 1].data_ptr()
+            io.out, io.lse = _ptr(out, br.chan0).value, lses[i].data_ptr()
+            io.grad_out = _ptr(gout, br.chan0).value
+            io.dq, io.dk, io.dv = (_ptr(gqkv, br.chan0).value, _ptr(gqkv, C + br.chan0).value,
+                                   _ptr(gqkv, 2 * C + br.chan0).value)
+            io.grad_lepe_w, io.grad_lepe_b = gw.data_ptr(), gb.data_ptr()
+            io.workspace, io.workspace_bytes = wsp.data_ptr(), nws
+            grads += [gw, gb]
+            w_ = _attn_work(B, L, br, qkv.element_size(), True)
+            nbytes, flops = nbytes + w_[0], flops + w_[1]
+        with torch.cuda.device(qkv.device), _span("attn_bwd", nbytes, flops):
+            capi.check(lib.csb200_cross_stripe_attn_bwd(n, descs, ios, st), "csb200_cross_stripe_attn_bwd")
         return (gqkv, None, None, None, None, None, *grads)
 
 

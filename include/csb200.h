@@ -173,6 +173,31 @@ CSB200_API int csb200_stripe_attn_bwd(const csb200_stripe_desc* d, const void* q
                            float* grad_lepe_w, float* grad_lepe_b, void* workspace,
                            size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * All branches of one CSWinBlock (C:360-363: the two stripe orientations on the two channel halves,
+ * or the single full-window branch of the last stage) in one call.  Two tcgen05-eligible branches of
+ * equal stripe length run as ONE launch whose work items are interleaved image by image (both halves
+ * of every 128-byte line of the packed qkv buffer are consumed together; no half-empty tail wave);
+ * anything else runs branch by branch exactly like the single-branch entry points.
+ * io[i] carries the pointers of branch i; fields not used by a direction may be NULL.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct csb200_branch_io {
+  const void *q, *k, *v;            /* already offset to the branch's first channel */
+  const float *lepe_w, *lepe_b;
+  void* out;                        /* forward: written; backward: read */
+  float* lse;                       /* forward: written; backward: read */
+  const void* grad_out;             /* backward only from here on */
+  void *dq, *dk, *dv;
+  float *grad_lepe_w, *grad_lepe_b;
+  void* workspace;
+  size_t workspace_bytes;           /* >= csb200_stripe_attn_bwd_workspace_bytes(&descs[i]) */
+} csb200_branch_io;
+
+CSB200_API int csb200_cross_stripe_attn_fwd(int n_branches, const csb200_stripe_desc* descs,
+                                            const csb200_branch_io* io, void* stream);
+CSB200_API int csb200_cross_stripe_attn_bwd(int n_branches, const csb200_stripe_desc* descs,
+                                            const csb200_branch_io* io, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
