@@ -31,7 +31,7 @@ with profile(activities=[ProfilerActivity.CUDA]) as prof:
 rows = sorted(prof.key_averages(), key=lambda e: -e.device_time_total)
 total = sum(e.device_time_total for e in rows)
 print(f"total device time {total / steps / 1e3:.2f} ms/step over {steps} steps")
-for e in rows[:45]:
+for e in rows[:70]:
     print(f"{e.device_time_total / steps / 1e3:8.3f} ms {100 * e.device_time_total / total:5.1f}%  n={e.count // steps:4d}  {e.key[:110]}")
 
 if len(sys.argv) > 2 and sys.argv[2] == "ops":

@@ -1,0 +1,348 @@
+// Backward step 1 of stripe attention, TMA-streamed (both engines, any stripe shape, bf16 / fp32).
+//
+// ONE pass over grad_out, out and the 3x3 neighbourhood of v (get_v, C:244,256-269) yields
+//   delta[b,h,l]  = sum_c grad_out * (out - lepe)          (row term of the softmax gradient)
+//   gw[c][tap]    = sum_l grad_out[l][c] * v[nbr_tap(l)][c]   (depthwise weight gradient)
+//   gb[c]         = sum_l grad_out[l][c]
+// It is HBM-bound: 3 reads of (tokens x C') + 4 B per (token, head).  A persistent CTA owns one
+// (branch, channel block) and walks (image, row block) tiles.  A producer warp fetches the three
+// tiles of an item with TMA — v with a one-row halo above and below, out-of-image rows zero-filled
+// by the copy engine — into a 2..3-stage shared-memory ring; 12 consumer warps read them back
+// 4 channels per thread.  A thread keeps its channels for the whole kernel, so the 36 taps + bias
+// and the 40 gradient accumulators live in registers and are reduced once at the end into
+// partial[cta][C'][10]; lepe_wgrad_final adds the per-CTA partials in a fixed order (deterministic).
+// The zero padding at the STRIPE border (get_lepe convolves each window separately, C:263-265) is a
+// per-row / per-column bit mask built once per CTA.
+
+#include <cstring>
+
+#include "stripe_attn.cuh"
+#include "tc_common.cuh"
+
+namespace csb200 {
+namespace {
+using namespace tc;
+
+constexpr int HD = 32;
+constexpr int CONSUMERS = 384;  // 12 warps: with the producer warp 416 threads -> 128 registers each
+constexpr int THREADS = CONSUMERS + 32;
+constexpr int MAX_STAGES = 3;
+constexpr int STAGE_BUDGET = 64 * 1024;
+constexpr int SMEM_BUDGET = 200 * 1024;
+constexpr int PART_BYTES = (CONSUMERS / 32) * 32 * 40 * (int)sizeof(float);  // final reduction scratch
+
+struct PrepTBranch {
+  int hs, ws, heads;
+  int cb, ncb;              // channels per CTA, channel blocks (cb * ncb == C')
+  int R, nrb;               // rows per tile, row blocks per image
+  int v_bytes, t_bytes;     // v tile (R + 2 rows) / grad_out, out tile (R rows), 128-byte multiples
+  int stages;
+  const float *lepe_w, *lepe_b;
+  float *delta, *partial;
+};
+struct PrepTParams {
+  int B, H, W, L;
+  int ncb0;                 // channel blocks of branch 0 (blockIdx.y below this -> branch 0)
+  PrepTBranch br[2];
+};
+struct PrepTMaps {
+  CUtensorMap v[2], g[2], o[2];
+};
+
+template <typename T>
+__device__ __forceinline__ float4 lds4(const uint8_t* p);
+template <>
+__device__ __forceinline__ float4 lds4<float>(const uint8_t* p) {
+  return *reinterpret_cast<const float4*>(p);
+}
+template <>
+__device__ __forceinline__ float4 lds4<__nv_bfloat16>(const uint8_t* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
+                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
+template <typename T>
+__global__ void __launch_bounds__(THREADS, 1)
+    lepe_prep_tma(const __grid_constant__ PrepTMaps maps, const __grid_constant__ PrepTParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
+                                             ~static_cast<uintptr_t>(127));
+  __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
+  __shared__ uint8_t s_my[256], s_mx[256];
+
+  const int which = (int)blockIdx.y >= p.ncb0 ? 1 : 0;
+  const PrepTBranch& bg = p.br[which];
+  const int c0 = ((int)blockIdx.y - (which ? p.ncb0 : 0)) * bg.cb;  // first channel of this CTA
+  const int items = p.B * bg.nrb;
+  const int my_items = (items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int stage_bytes = bg.v_bytes + 2 * bg.t_bytes;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  // bit 0: the neighbour above / to the left is inside the stripe; bit 1: below / to the right
+  for (int i = threadIdx.x; i < p.H; i += THREADS) {
+    const int yy = i % bg.hs;
+    s_my[i] = (uint8_t)((yy > 0 ? 1 : 0) | (yy < bg.hs - 1 ? 2 : 0));
+  }
+  for (int i = threadIdx.x; i < p.W; i += THREADS) {
+    const int xx = i % bg.ws;
+    s_mx[i] = (uint8_t)((xx > 0 ? 1 : 0) | (xx < bg.ws - 1 ? 2 : 0));
+  }
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < MAX_STAGES; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], CONSUMERS / 32);
+    }
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  if (warp == CONSUMERS / 32) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      prefetch_tensormap(&maps.v[which]);
+      prefetch_tensormap(&maps.g[which]);
+      prefetch_tensormap(&maps.o[which]);
+      for (int i = 0; i < my_items; ++i) {
+        const int item = (int)blockIdx.x + i * (int)gridDim.x;
+        const int b = item / bg.nrb, y0 = (item - b * bg.nrb) * bg.R;
+        const int s = i % bg.stages;
+        mbar_wait(&empty[s], ((i / bg.stages) & 1) ^ 1);
+        uint8_t* st = ring + (size_t)s * stage_bytes;
+        mbar_expect_tx(&full[s], (uint32_t)stage_bytes);
+        tma_load_4d(st, &maps.v[which], &full[s], c0, 0, y0 - 1, b);
+        tma_load_4d(st + bg.v_bytes, &maps.g[which], &full[s], c0, 0, y0, b);
+        tma_load_4d(st + bg.v_bytes + bg.t_bytes, &maps.o[which], &full[s], c0, 0, y0, b);
+      }
+    }
+    return;
+  }
+
+  // ======================================= consumers ========================================
+  constexpr int ES = (int)sizeof(T);
+  const int cgn = bg.cb >> 2;                    // channel groups (of 4) per token: 8, 16, 32 or 64
+  const int cg = (int)threadIdx.x % cgn;
+  const int walker = (int)threadIdx.x / cgn, walkers = CONSUMERS / cgn;
+  const int ch = c0 + cg * 4, head = ch / HD;    // channel inside the branch
+  const int tok_bytes = bg.cb * ES, cg_off = cg * 4 * ES;
+
+  float4 w[10];  // [tap] for this thread's 4 channels, bias last
+  {
+    float t[4][10];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) t[e][k] = __ldg(bg.lepe_w + (ch + e) * 9 + k);
+      t[e][9] = __ldg(bg.lepe_b + ch + e);
+    }
+#pragma unroll
+    for (int k = 0; k < 10; ++k) w[k] = make_float4(t[0][k], t[1][k], t[2][k], t[3][k]);
+  }
+  float4 acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+
+  const int tokens = bg.R * p.W;
+  const int steps = (tokens + walkers - 1) / walkers;
+  const int ry0 = walker / p.W, x0 = walker - ry0 * p.W;
+  const int dry = walkers / p.W, dx = walkers - dry * p.W;
+
+  for (int i = 0; i < my_items; ++i) {
+    const int item = (int)blockIdx.x + i * (int)gridDim.x;
+    const int b = item / bg.nrb, y0 = (item - b * bg.nrb) * bg.R;
+    const int s = i % bg.stages;
+    mbar_wait(&full[s], (i / bg.stages) & 1);
+    const uint8_t* vt = ring + (size_t)s * stage_bytes + cg_off;  // row 0 of the v tile is y0 - 1
+    const uint8_t* gt = vt + bg.v_bytes;
+    const uint8_t* ot = gt + bg.t_bytes;
+    float* drow = bg.delta + ((int64_t)b * bg.heads + head) * p.L;
+    int ry = ry0, x = x0;
+    for (int it = 0; it < steps; ++it) {
+      const int y = y0 + ry;
+      const bool valid = ry < bg.R && y < p.H;
+      float d = 0.f;
+      if (valid) {
+        const int t = ry * p.W + x;
+        const float4 go = lds4<T>(gt + t * tok_bytes);
+        const float4 o = lds4<T>(ot + t * tok_bytes);
+        float4 lp = w[9];
+        acc[9].x += go.x; acc[9].y += go.y; acc[9].z += go.z; acc[9].w += go.w;
+        const int my = s_my[y], mx = s_mx[x];
+#pragma unroll
+        for (int ky = 0; ky < 3; ++ky) {
+          if ((ky == 0 && !(my & 1)) || (ky == 2 && !(my & 2))) continue;
+#pragma unroll
+          for (int kx = 0; kx < 3; ++kx) {
+            if ((kx == 0 && !(mx & 1)) || (kx == 2 && !(mx & 2))) continue;
+            const float4 vn = lds4<T>(vt + ((ry + ky) * p.W + x + kx - 1) * tok_bytes);
+            const float4 wt = w[ky * 3 + kx];
+            lp.x = fmaf(wt.x, vn.x, lp.x); lp.y = fmaf(wt.y, vn.y, lp.y);
+            lp.z = fmaf(wt.z, vn.z, lp.z); lp.w = fmaf(wt.w, vn.w, lp.w);
+            float4& a = acc[ky * 3 + kx];
+            a.x = fmaf(go.x, vn.x, a.x); a.y = fmaf(go.y, vn.y, a.y);
+            a.z = fmaf(go.z, vn.z, a.z); a.w = fmaf(go.w, vn.w, a.w);
+          }
+        }
+        d = go.x * (o.x - lp.x) + go.y * (o.y - lp.y) + go.z * (o.z - lp.z) + go.w * (o.w - lp.w);
+      }
+      // 8 adjacent lanes hold the 32 channels of one (token, head)
+      d += __shfl_xor_sync(0xffffffffu, d, 1);
+      d += __shfl_xor_sync(0xffffffffu, d, 2);
+      d += __shfl_xor_sync(0xffffffffu, d, 4);
+      if (valid && (cg & 7) == 0) drow[y * p.W + x] = d;
+      x += dx;
+      ry += dry;
+      if (x >= p.W) {
+        x -= p.W;
+        ++ry;
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+
+  // ---- reduce the 40 accumulators over the walkers of this CTA (fixed order) ----
+  for (int off = cgn; off < 32; off <<= 1) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k) {
+      acc[k].x += __shfl_xor_sync(0xffffffffu, acc[k].x, off);
+      acc[k].y += __shfl_xor_sync(0xffffffffu, acc[k].y, off);
+      acc[k].z += __shfl_xor_sync(0xffffffffu, acc[k].z, off);
+      acc[k].w += __shfl_xor_sync(0xffffffffu, acc[k].w, off);
+    }
+  }
+  // every stage has been consumed (all TMA writes landed): reuse the ring as scratch
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+  float* part = reinterpret_cast<float*>(ring);  // [warp][lane][10][4]
+  const int held = cgn < 32 ? cgn : 32;          // channel groups a warp holds (lanes 0..held-1)
+  if (lane < held) {
+#pragma unroll
+    for (int k = 0; k < 10; ++k)
+      *reinterpret_cast<float4*>(part + ((warp * 32 + lane) * 10 + k) * 4) = acc[k];
+  }
+  asm volatile("bar.sync 1, %0;" ::"n"(CONSUMERS) : "memory");
+  const int cp = bg.heads * HD;
+  const int wstep = cgn <= 32 ? 1 : cgn / 32;    // warps wstep apart hold the same channel groups
+  for (int idx = threadIdx.x; idx < cgn * 40; idx += CONSUMERS) {
+    const int cgi = idx / 40, r = idx - cgi * 40, k = r >> 2, e = r & 3;
+    const int w0 = cgn <= 32 ? 0 : cgi / 32, l = cgn <= 32 ? cgi : cgi & 31;
+    float a = 0.f;
+    for (int wv = w0; wv < CONSUMERS / 32; wv += wstep) a += part[((wv * 32 + l) * 10 + k) * 4 + e];
+    bg.partial[((int64_t)blockIdx.x * cp + c0 + cgi * 4 + e) * 10 + k] = a;
+  }
+}
+
+int make_tok_map(CUtensorMap* m, const void* base, int dtype, int cp, int W, int H, int B, int64_t sb,
+                 int64_t sl, int box_c, int box_y) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  ensure_context();
+  const cuuint64_t es = dtype == CSB200_F32 ? 4 : 2;
+  const cuuint64_t dims[4] = {(cuuint64_t)cp, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t strides[3] = {(cuuint64_t)sl * es, (cuuint64_t)sl * es * W, (cuuint64_t)sb * es};
+  const cuuint32_t box[4] = {(cuuint32_t)box_c, (cuuint32_t)W, (cuuint32_t)box_y, 1};
+  const cuuint32_t estr[4] = {1, 1, 1, 1};
+  CUresult r = enc(m, dtype == CSB200_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                   4, const_cast<void*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CSB200_OK;
+}
+
+// tile plan of one branch; false if the shape does not fit the TMA path
+bool plan_branch(const StripeGeom& g, int dtype, const PrepIO& io, PrepTBranch* b) {
+  const int es = dtype == CSB200_F32 ? 4 : 2;
+  const int cp = g.heads * HD;
+  if (g.W > 256 || g.H > 256 || g.B < 1) return false;
+  const uintptr_t al = reinterpret_cast<uintptr_t>(io.v) | reinterpret_cast<uintptr_t>(io.out) |
+                       reinterpret_cast<uintptr_t>(io.gout);
+  if (al & 15) return false;
+  const int64_t strides[4] = {g.v_sb, g.v_sl, g.o_sb, g.o_sl};
+  for (int64_t s : strides)
+    if (s <= 0 || (s * es) % 16 != 0) return false;
+  // the token grid of a map is (W, H) with row stride sl * W: fine for any sb
+  int cb = 256;
+  while (cb > 32 && (cp % cb != 0 || 5LL * g.W * cb * es > SMEM_BUDGET / 2)) cb >>= 1;
+  const int64_t row = (int64_t)g.W * cb * es;
+  if (cp % cb != 0 || 5 * row > SMEM_BUDGET / 2) return false;
+  int R = (int)((STAGE_BUDGET / row - 2) / 3);
+  if (R < 1) R = 1;
+  if (R > g.H) R = g.H;
+  if (R > 254) R = 254;
+  b->hs = g.hs; b->ws = g.ws; b->heads = g.heads;
+  b->cb = cb; b->ncb = cp / cb;
+  b->R = R; b->nrb = (g.H + R - 1) / R;
+  b->v_bytes = (int)(((R + 2) * row + 127) / 128 * 128);
+  b->t_bytes = (int)((R * row + 127) / 128 * 128);
+  const int stage = b->v_bytes + 2 * b->t_bytes;
+  b->stages = SMEM_BUDGET / stage < MAX_STAGES ? SMEM_BUDGET / stage : MAX_STAGES;
+  if (b->stages < 2) return false;
+  b->lepe_w = io.lepe_w; b->lepe_b = io.lepe_b;
+  b->delta = io.delta; b->partial = io.partial;
+  return true;
+}
+
+}  // namespace
+
+// Upper bound on blockIdx.x of the TMA path (sizes the partial buffer together with the generic one).
+int lepe_prep_tma_max_blocks() { return 160; }
+
+// Returns CSB200_OK and sets *blocks (CTAs per channel block == partials per output) when the TMA
+// path ran; CSB200_ERR_UNSUPPORTED (without touching the error text) when the caller should use the
+// generic kernel.
+int lepe_prep_tma_launch(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, int* blocks,
+                         cudaStream_t st) {
+  PrepTMaps maps;
+  PrepTParams p;
+  memset(&maps, 0, sizeof(maps));
+  memset(&p, 0, sizeof(p));
+  p.B = g[0].B; p.H = g[0].H; p.W = g[0].W; p.L = g[0].L;
+  int ncb = 0, smem = PART_BYTES, items = 0;
+  for (int i = 0; i < nbr; ++i) {
+    if (g[i].B != p.B || g[i].H != p.H || g[i].W != p.W) return CSB200_ERR_UNSUPPORTED;
+    if (!plan_branch(g[i], dtype, io[i], &p.br[i])) return CSB200_ERR_UNSUPPORTED;
+    const PrepTBranch& b = p.br[i];
+    const int need = b.stages * (b.v_bytes + 2 * b.t_bytes);
+    smem = need > smem ? need : smem;
+    items = i == 0 || p.B * b.nrb < items ? p.B * b.nrb : items;
+    ncb += b.ncb;
+  }
+  p.ncb0 = p.br[0].ncb;
+  static int sm_count = 0;
+  if (sm_count == 0) {
+    int dev = 0;
+    CSB200_CUDA(cudaGetDevice(&dev));
+    CSB200_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
+  }
+  int gx = sm_count / ncb;
+  if (gx < 1) gx = 1;
+  if (gx > items) gx = items;
+  if (gx > lepe_prep_tma_max_blocks()) gx = lepe_prep_tma_max_blocks();
+  for (int i = 0; i < nbr; ++i) {
+    const int cp = g[i].heads * HD;
+    const PrepTBranch& b = p.br[i];
+    int rc;
+    if ((rc = make_tok_map(&maps.v[i], io[i].v, dtype, cp, p.W, p.H, p.B, g[i].v_sb, g[i].v_sl, b.cb, b.R + 2)) != CSB200_OK) return rc;
+    if ((rc = make_tok_map(&maps.g[i], io[i].gout, dtype, cp, p.W, p.H, p.B, g[i].o_sb, g[i].o_sl, b.cb, b.R)) != CSB200_OK) return rc;
+    if ((rc = make_tok_map(&maps.o[i], io[i].out, dtype, cp, p.W, p.H, p.B, g[i].o_sb, g[i].o_sl, b.cb, b.R)) != CSB200_OK) return rc;
+  }
+  smem += 128;
+  static int attr[2] = {0, 0};
+  const int ti = dtype == CSB200_F32 ? 0 : 1;
+  if (attr[ti] < smem) {
+    if (ti == 0)
+      CSB200_CUDA(cudaFuncSetAttribute(lepe_prep_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 128));
+    else
+      CSB200_CUDA(cudaFuncSetAttribute(lepe_prep_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 128));
+    attr[ti] = SMEM_BUDGET + 128;
+  }
+  if (ti == 0)
+    lepe_prep_tma<float><<<dim3(gx, ncb), THREADS, smem, st>>>(maps, p);
+  else
+    lepe_prep_tma<__nv_bfloat16><<<dim3(gx, ncb), THREADS, smem, st>>>(maps, p);
+  *blocks = gx;
+  return check_launch("lepe_prep_tma");
+}
+
+}  // namespace csb200

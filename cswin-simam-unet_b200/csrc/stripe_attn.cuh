@@ -31,6 +31,10 @@ struct PrepIO {
   const float *lepe_w, *lepe_b;
   float *delta, *partial, *gw, *gb;
 };
+// TMA-streamed variant (lepe_prep.cu): CSB200_ERR_UNSUPPORTED means "use the generic kernel"
+int lepe_prep_tma_max_blocks();
+int lepe_prep_tma_launch(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, int* blocks,
+                         cudaStream_t st);
 // up to two branches of equal (B, L) in one launch
 int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st);
 int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,

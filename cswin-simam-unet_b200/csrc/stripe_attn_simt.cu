@@ -14,6 +14,7 @@
 // Backward recomputes the probabilities from the saved log-sum-exp (no N x N tensor ever exists).
 
 #include <cstring>
+#include <type_traits>
 
 #include "stripe_attn.cuh"
 
@@ -557,7 +558,8 @@ static int prep_tok_per_cta(const StripeGeom& g, int total_heads) {
 // upper bound on the CTAs per head (sizes the partial buffer): a single-branch launch is the worst case
 int wgrad_blocks(const StripeGeom& g) {
   const int tpc = prep_tok_per_cta(g, g.heads);
-  return (int)(((int64_t)g.B * g.L + tpc - 1) / tpc);
+  const int generic = (int)(((int64_t)g.B * g.L + tpc - 1) / tpc);
+  return generic > lepe_prep_tma_max_blocks() ? generic : lepe_prep_tma_max_blocks();
 }
 
 template <typename T>
@@ -578,10 +580,16 @@ int lepe_bwd_prep_multi_t(int nbr, const StripeGeom* g, const PrepIO* io, cudaSt
     cp_max = g[i].heads * HD > cp_max ? g[i].heads * HD : cp_max;
   }
   a.heads0 = g[0].heads;
-  const int tpc = prep_tok_per_cta(g[0], heads);
-  const int blocks = (int)(((int64_t)g[0].B * g[0].L + tpc - 1) / tpc);
-  lepe_bwd_prep<T><<<dim3(blocks, heads), PREP_THREADS, 0, st>>>(a, tpc);
-  int rc = check_launch("lepe_bwd_prep");
+  // TMA-streamed kernel (lepe_prep.cu) when the shape and alignment allow, else the generic one
+  int blocks = 0;
+  int rc = lepe_prep_tma_launch(nbr, g, std::is_same<T, float>::value ? CSB200_F32 : CSB200_BF16, io,
+                                &blocks, st);
+  if (rc == CSB200_ERR_UNSUPPORTED) {
+    const int tpc = prep_tok_per_cta(g[0], heads);
+    blocks = (int)(((int64_t)g[0].B * g[0].L + tpc - 1) / tpc);
+    lepe_bwd_prep<T><<<dim3(blocks, heads), PREP_THREADS, 0, st>>>(a, tpc);
+    rc = check_launch("lepe_bwd_prep");
+  }
   if (rc != CSB200_OK) return rc;
   WgradFinal f[2];
   for (int i = 0; i < 2; ++i) {

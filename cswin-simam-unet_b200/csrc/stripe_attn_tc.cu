@@ -43,6 +43,16 @@ EncodeTiledFn encode_tiled_fn() {
   return fn;
 }
 
+// cuTensorMapEncodeTiled needs a current context; a host thread that has issued no runtime work yet
+// (autograd's backward thread on its first call) has none bound.
+void ensure_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(nullptr);
+    bound = true;
+  }
+}
+
 constexpr int HD_ = 32;
 // A token row of one head is 64 B.  With >= 2 heads the other half of the 128-B line is the
 // neighbouring head, which the neighbouring CTA wants at the same moment: promote to 128 B.  With a
@@ -51,6 +61,7 @@ int tc_make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t s
              int by) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  ensure_context();
   const cuuint64_t dims[4] = {(cuuint64_t)g.heads * HD_, (cuuint64_t)g.W, (cuuint64_t)g.H,
                               (cuuint64_t)g.B};
   const cuuint64_t strides[3] = {(cuuint64_t)sl * 2, (cuuint64_t)sl * 2 * g.W, (cuuint64_t)sb * 2};
