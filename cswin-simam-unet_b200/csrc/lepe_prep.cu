@@ -27,7 +27,7 @@ constexpr int HD = 32;
 constexpr int CONSUMERS = 384;  // 12 warps: with the producer warp 416 threads -> 128 registers each
 constexpr int THREADS = CONSUMERS + 32;
 constexpr int MAX_STAGES = 3;
-constexpr int STAGE_BUDGET = 64 * 1024;
+constexpr int STAGE_BUDGET = 88 * 1024;  // 3 rows of 8 KB per tile: tokens divisible by the 3 * 2^k walkers
 constexpr int SMEM_BUDGET = 200 * 1024;
 constexpr int PART_BYTES = (CONSUMERS / 32) * 32 * 40 * (int)sizeof(float);  // final reduction scratch
 
@@ -49,17 +49,120 @@ struct PrepTMaps {
   CUtensorMap v[2], g[2], o[2];
 };
 
+// 4 consecutive channels of one token from shared memory (explicit 32-bit shared address: a generic
+// pointer into the dynamic ring makes the compiler emit generic loads with 64-bit address math)
 template <typename T>
-__device__ __forceinline__ float4 lds4(const uint8_t* p);
+__device__ __forceinline__ float4 lds4(uint32_t addr);
 template <>
-__device__ __forceinline__ float4 lds4<float>(const uint8_t* p) {
-  return *reinterpret_cast<const float4*>(p);
+__device__ __forceinline__ float4 lds4<float>(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
 }
 template <>
-__device__ __forceinline__ float4 lds4<__nv_bfloat16>(const uint8_t* p) {
-  const uint2 u = *reinterpret_cast<const uint2*>(p);
+__device__ __forceinline__ float4 lds4<__nv_bfloat16>(uint32_t addr) {
+  uint2 u;
+  asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(addr));
   return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
                      __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+}
+
+struct Walk {        // per-thread constants of the token walk inside a tile
+  int t0, dt;        // first token of this thread, tokens per step (== walkers)
+  int x0, ry0, dx, dry;
+  uint32_t tok_bytes, row_bytes;
+};
+
+// One token: lepe recomputation, weight-gradient accumulation, and the thread's share of delta.
+// HAS_X / HAS_Y: the stripe is wider / taller than one token (else those taps never exist).
+template <typename T, bool HAS_X, bool HAS_Y>
+__device__ __forceinline__ float prep_token(uint32_t va, uint32_t ga, uint32_t oa, const Walk& wk, int mx,
+                                            int my, const float4 (&w)[10], float4 (&acc)[10]) {
+  const float4 go = lds4<T>(ga);
+  const float4 o = lds4<T>(oa);
+  float4 lp = w[9];
+  acc[9].x += go.x; acc[9].y += go.y; acc[9].z += go.z; acc[9].w += go.w;
+#pragma unroll
+  for (int ky = 0; ky < 3; ++ky) {
+    if (!HAS_Y && ky != 1) continue;
+    if (HAS_Y && ((ky == 0 && !(my & 1)) || (ky == 2 && !(my & 2)))) continue;
+#pragma unroll
+    for (int kx = 0; kx < 3; ++kx) {
+      if (!HAS_X && kx != 1) continue;
+      if (HAS_X && ((kx == 0 && !(mx & 1)) || (kx == 2 && !(mx & 2)))) continue;
+      const float4 vn = lds4<T>(va + ky * wk.row_bytes + kx * wk.tok_bytes);  // va: tap (0,0)
+      const float4 wt = w[ky * 3 + kx];
+      lp.x = fmaf(wt.x, vn.x, lp.x); lp.y = fmaf(wt.y, vn.y, lp.y);
+      lp.z = fmaf(wt.z, vn.z, lp.z); lp.w = fmaf(wt.w, vn.w, lp.w);
+      float4& a = acc[ky * 3 + kx];
+      a.x = fmaf(go.x, vn.x, a.x); a.y = fmaf(go.y, vn.y, a.y);
+      a.z = fmaf(go.z, vn.z, a.z); a.w = fmaf(go.w, vn.w, a.w);
+    }
+  }
+  return go.x * (o.x - lp.x) + go.y * (o.y - lp.y) + go.z * (o.z - lp.z) + go.w * (o.w - lp.w);
+}
+
+__device__ __forceinline__ float head_sum(float d) {  // 8 adjacent lanes = the 32 channels of a head
+  d += __shfl_xor_sync(0xffffffffu, d, 1);
+  d += __shfl_xor_sync(0xffffffffu, d, 2);
+  d += __shfl_xor_sync(0xffffffffu, d, 4);
+  return d;
+}
+
+// All items of this CTA.  Token t of a tile sits at byte t * tok_bytes of the grad_out / out tiles and
+// one row lower in the v tile (whose row 0 is the halo row y0 - 1); delta[y0 * W + t] is its output.
+template <typename T, bool HAS_X, bool HAS_Y>
+__device__ __forceinline__ void prep_items(const PrepTParams& p, const PrepTBranch& bg, uint32_t ring,
+                                           uint64_t* full, uint64_t* empty, const uint8_t* s_my,
+                                           const uint8_t* s_mx, const Walk& wk, int my_items, int head,
+                                           bool writer, const float4 (&w)[10], float4 (&acc)[10]) {
+  const int stage_bytes = bg.v_bytes + 2 * bg.t_bytes;
+  const int tokens = bg.R * p.W;
+  const int lane = threadIdx.x & 31;
+  for (int i = 0; i < my_items; ++i) {
+    const int item = (int)blockIdx.x + i * (int)gridDim.x;
+    const int b = item / bg.nrb, y0 = (item - b * bg.nrb) * bg.R;
+    const int s = i % bg.stages;
+    const int rows = p.H - y0 < bg.R ? p.H - y0 : bg.R;
+    const int tmax = rows * p.W;  // tokens of this tile that exist
+    mbar_wait(&full[s], (i / bg.stages) & 1);
+    // v address of tap (ky = 0, kx = 0) of token 0: tile row 0 is y0 - 1, one token to the left
+    const uint32_t vbase = ring + (uint32_t)(s * stage_bytes) - wk.tok_bytes;
+    const uint32_t gbase = ring + (uint32_t)(s * stage_bytes + bg.v_bytes);
+    const uint32_t obase = gbase + (uint32_t)bg.t_bytes;
+    float* drow = bg.delta + ((int64_t)b * bg.heads + head) * p.L + (int64_t)y0 * p.W;
+    int x = wk.x0, ry = wk.ry0;
+    const int iters = (tokens + 2 * wk.dt - 1) / (2 * wk.dt);  // same trip count for every lane
+    for (int k = 0, t = wk.t0; k < iters; ++k, t += 2 * wk.dt) {
+      // two tokens per iteration: two independent shuffle / FMA chains in flight
+      const int ta = t, tb = t + wk.dt;
+      int mxa = 0, mya = 0, mxb = 0, myb = 0;
+      if (HAS_X) mxa = s_mx[x];
+      if (HAS_Y) mya = s_my[min(y0 + ry, 511)];
+      x += wk.dx; ry += wk.dry;
+      if (x >= p.W) { x -= p.W; ++ry; }
+      const bool vb_ = tb < tmax;
+      if (HAS_X) mxb = s_mx[x];
+      if (HAS_Y) myb = s_my[min(y0 + ry, 511)];
+      x += wk.dx; ry += wk.dry;
+      if (x >= p.W) { x -= p.W; ++ry; }
+      float da = 0.f, db = 0.f;
+      if (ta < tmax) {
+        const uint32_t off = (uint32_t)ta * wk.tok_bytes;
+        da = prep_token<T, HAS_X, HAS_Y>(vbase + off, gbase + off, obase + off, wk, mxa, mya, w, acc);
+      }
+      if (vb_) {
+        const uint32_t off = (uint32_t)tb * wk.tok_bytes;
+        db = prep_token<T, HAS_X, HAS_Y>(vbase + off, gbase + off, obase + off, wk, mxb, myb, w, acc);
+      }
+      da = head_sum(da);
+      db = head_sum(db);
+      if (writer && ta < tmax) drow[ta] = da;
+      if (writer && vb_) drow[tb] = db;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
 }
 
 template <typename T>
@@ -69,7 +172,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
                                              ~static_cast<uintptr_t>(127));
   __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
-  __shared__ uint8_t s_my[256], s_mx[256];
+  __shared__ uint8_t s_my[256 + 256], s_mx[256];  // s_my: slack for the rows a partial tile lacks
 
   const int which = (int)blockIdx.y >= p.ncb0 ? 1 : 0;
   const PrepTBranch& bg = p.br[which];
@@ -80,9 +183,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   // bit 0: the neighbour above / to the left is inside the stripe; bit 1: below / to the right
-  for (int i = threadIdx.x; i < p.H; i += THREADS) {
+  for (int i = threadIdx.x; i < 512; i += THREADS) {
     const int yy = i % bg.hs;
-    s_my[i] = (uint8_t)((yy > 0 ? 1 : 0) | (yy < bg.hs - 1 ? 2 : 0));
+    s_my[i] = i < p.H ? (uint8_t)((yy > 0 ? 1 : 0) | (yy < bg.hs - 1 ? 2 : 0)) : (uint8_t)0;
   }
   for (int i = threadIdx.x; i < p.W; i += THREADS) {
     const int xx = i % bg.ws;
@@ -124,7 +227,6 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int cg = (int)threadIdx.x % cgn;
   const int walker = (int)threadIdx.x / cgn, walkers = CONSUMERS / cgn;
   const int ch = c0 + cg * 4, head = ch / HD;    // channel inside the branch
-  const int tok_bytes = bg.cb * ES, cg_off = cg * 4 * ES;
 
   float4 w[10];  // [tap] for this thread's 4 channels, bias last
   {
@@ -142,64 +244,23 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
   for (int k = 0; k < 10; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
-  const int tokens = bg.R * p.W;
-  const int steps = (tokens + walkers - 1) / walkers;
-  const int ry0 = walker / p.W, x0 = walker - ry0 * p.W;
-  const int dry = walkers / p.W, dx = walkers - dry * p.W;
-
-  for (int i = 0; i < my_items; ++i) {
-    const int item = (int)blockIdx.x + i * (int)gridDim.x;
-    const int b = item / bg.nrb, y0 = (item - b * bg.nrb) * bg.R;
-    const int s = i % bg.stages;
-    mbar_wait(&full[s], (i / bg.stages) & 1);
-    const uint8_t* vt = ring + (size_t)s * stage_bytes + cg_off;  // row 0 of the v tile is y0 - 1
-    const uint8_t* gt = vt + bg.v_bytes;
-    const uint8_t* ot = gt + bg.t_bytes;
-    float* drow = bg.delta + ((int64_t)b * bg.heads + head) * p.L;
-    int ry = ry0, x = x0;
-    for (int it = 0; it < steps; ++it) {
-      const int y = y0 + ry;
-      const bool valid = ry < bg.R && y < p.H;
-      float d = 0.f;
-      if (valid) {
-        const int t = ry * p.W + x;
-        const float4 go = lds4<T>(gt + t * tok_bytes);
-        const float4 o = lds4<T>(ot + t * tok_bytes);
-        float4 lp = w[9];
-        acc[9].x += go.x; acc[9].y += go.y; acc[9].z += go.z; acc[9].w += go.w;
-        const int my = s_my[y], mx = s_mx[x];
-#pragma unroll
-        for (int ky = 0; ky < 3; ++ky) {
-          if ((ky == 0 && !(my & 1)) || (ky == 2 && !(my & 2))) continue;
-#pragma unroll
-          for (int kx = 0; kx < 3; ++kx) {
-            if ((kx == 0 && !(mx & 1)) || (kx == 2 && !(mx & 2))) continue;
-            const float4 vn = lds4<T>(vt + ((ry + ky) * p.W + x + kx - 1) * tok_bytes);
-            const float4 wt = w[ky * 3 + kx];
-            lp.x = fmaf(wt.x, vn.x, lp.x); lp.y = fmaf(wt.y, vn.y, lp.y);
-            lp.z = fmaf(wt.z, vn.z, lp.z); lp.w = fmaf(wt.w, vn.w, lp.w);
-            float4& a = acc[ky * 3 + kx];
-            a.x = fmaf(go.x, vn.x, a.x); a.y = fmaf(go.y, vn.y, a.y);
-            a.z = fmaf(go.z, vn.z, a.z); a.w = fmaf(go.w, vn.w, a.w);
-          }
-        }
-        d = go.x * (o.x - lp.x) + go.y * (o.y - lp.y) + go.z * (o.z - lp.z) + go.w * (o.w - lp.w);
-      }
-      // 8 adjacent lanes hold the 32 channels of one (token, head)
-      d += __shfl_xor_sync(0xffffffffu, d, 1);
-      d += __shfl_xor_sync(0xffffffffu, d, 2);
-      d += __shfl_xor_sync(0xffffffffu, d, 4);
-      if (valid && (cg & 7) == 0) drow[y * p.W + x] = d;
-      x += dx;
-      ry += dry;
-      if (x >= p.W) {
-        x -= p.W;
-        ++ry;
-      }
-    }
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&empty[s]);
-  }
+  Walk wk;
+  wk.t0 = walker; wk.dt = walkers;
+  wk.ry0 = walker / p.W; wk.x0 = walker - wk.ry0 * p.W;
+  wk.dry = walkers / p.W; wk.dx = walkers - wk.dry * p.W;
+  wk.tok_bytes = (uint32_t)(bg.cb * ES);
+  wk.row_bytes = wk.tok_bytes * (uint32_t)p.W;
+  const uint32_t ring_a = smem_u32(ring) + (uint32_t)(cg * 4 * ES);
+  const bool writer = (cg & 7) == 0;
+  const bool has_x = bg.ws > 1, has_y = bg.hs > 1;
+  if (has_x && has_y)
+    prep_items<T, true, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+  else if (has_y)
+    prep_items<T, false, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+  else if (has_x)
+    prep_items<T, true, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+  else
+    prep_items<T, false, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
 
   // ---- reduce the 40 accumulators over the walkers of this CTA (fixed order) ----
   for (int off = cgn; off < 32; off <<= 1) {

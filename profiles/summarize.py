@@ -46,7 +46,8 @@ for rep in sys.argv[1:]:
         h = src[1]
         ix = {k: i for i, k in enumerate(h)}
         if "# Samples" in ix:
-            body = sorted(src[2:], key=lambda r: -int(r[ix["# Samples"]] or 0))[:30]
+            n = len(h)
+            body = sorted([r for r in src[2:] if len(r) == n and (r[ix["# Samples"]] or "0").isdigit()], key=lambda r: -int(r[ix["# Samples"]] or 0))[:30]
             with open(os.path.join(OUT, name + ".hot.csv"), "w", newline="") as f:
                 w = csv.writer(f)
                 w.writerow(["samples", "instructions_executed", "sass"])
