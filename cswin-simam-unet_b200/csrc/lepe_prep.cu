@@ -169,8 +169,7 @@ template <typename T>
 __global__ void __launch_bounds__(THREADS, 1)
     lepe_prep_tma(const __grid_constant__ PrepTMaps maps, const __grid_constant__ PrepTParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* ring = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 127) &
-                                             ~static_cast<uintptr_t>(127));
+  uint8_t* ring = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
   __shared__ uint8_t s_my[256 + 256], s_mx[256];  // s_my: slack for the rows a partial tile lacks
 

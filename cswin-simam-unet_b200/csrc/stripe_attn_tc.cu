@@ -76,6 +76,17 @@ int tc_make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t s
 }
 
 
+#ifdef CSB_PROF
+__device__ unsigned long long g_prof[32];
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADD(i, a, b) if (blockIdx.x == 0 && (threadIdx.x & 127) == 0) atomicAdd(&g_prof[i], (unsigned long long)((b) - (a)))
+#define PROF_ADD1(i, a, b) if (blockIdx.x == 0 && threadIdx.x == 32) atomicAdd(&g_prof[i], (unsigned long long)((b) - (a)))
+#else
+#define PROF_T(v)
+#define PROF_ADD(i, a, b)
+#define PROF_ADD1(i, a, b)
+#endif
+
 namespace {
 using namespace tc;
 
@@ -166,8 +177,9 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
   constexpr int NWG = Cfg<NK>::NWG, KVS = Cfg<NK>::KVS, QS = Cfg<NK>::QS;
   constexpr uint32_t P_COL = 0, O_COL = NK / 2, BUF_COLS = NK;
   extern __shared__ uint8_t smem_raw[];
-  Smem<NK>& sm = *reinterpret_cast<Smem<NK>*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // align inside the shared window: pointer + integer offset keeps the shared address space (an
+  // integer -> pointer cast makes every access a generic LD/ST with 64-bit address math)
+  Smem<NK>& sm = *reinterpret_cast<Smem<NK>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_groups = (p.groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -200,6 +212,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  PROF_T(k0);
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -244,41 +257,54 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_s = umma_idesc_bf16(NK, false, false);
-      constexpr uint32_t idesc_pv = umma_idesc_bf16(HD, false, true);
-      auto issue_pv = [&](int it) {
-        const int buf = it % NWG, kvs = (it / T) % KVS;
-        mbar_wait(&sm.p_full[buf], (it / NWG) & 1);
-        fence_after_sync();
+    // the whole warp walks the loop; one elected lane issues (see tc_common.cuh, "cheap issue path")
+    constexpr uint32_t idesc_s = umma_idesc_bf16(NK, false, false);
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(HD, false, true);
+    const uint32_t q_lo0 = desc_lo_sw64(smem_u32(sm.q[0])), k_lo0 = desc_lo_sw64(smem_u32(sm.k[0]));
+    const uint32_t v_lo0 = desc_lo_sw64(smem_u32(sm.v[0]));
+    auto issue_pv = [&](int it) {
+      const int buf = it % NWG, kvs = (it / T) % KVS;
+      PROF_T(m0);
+      mbar_wait(&sm.p_full[buf], (it / NWG) & 1);
+      fence_after_sync();
+      PROF_T(m1);
+      PROF_ADD1(8, m0, m1);
+      if (elect_one_sync()) {
         const uint32_t d = tmem + buf * BUF_COLS + O_COL, a = tmem + buf * BUF_COLS + P_COL;
-        const uint32_t vb = smem_u32(sm.v[kvs]);
+        const uint32_t v_lo = v_lo0 + kvs * (Smem<NK>::KV_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < NK / 16; ++k)  // 16 keys per step: 8 TMEM columns of P, 1024 B of V
-          umma_ts(d, a + 8 * k, umma_desc_sw64(vb + k * 1024), idesc_pv, k > 0);
+          umma_ts2(d, a + 8 * k, v_lo + k * (1024 >> 4), DESC_HI_SW64, idesc_pv, k > 0);
         umma_commit(&sm.o_full[buf]);
-      };
-      // S of tile `it` is issued NWG-1 tiles ahead of the PV it feeds, so every warpgroup has work
-      constexpr int LAG = NWG - 1;
-      for (int it = 0; it < my_tiles + LAG; ++it) {
-        if (it < my_tiles) {
-          const int buf = it % NWG, qs = it % QS, gi = it / T, kvs = gi % KVS;
-          mbar_wait(&sm.q_full[qs], (it / QS) & 1);
-          if (it % T == 0) mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
-          mbar_wait(&sm.buf_empty[buf], ((it / NWG) & 1) ^ 1);
-          fence_after_sync();
-          const uint32_t qa = smem_u32(sm.q[qs]), kb = smem_u32(sm.k[kvs]);
+      }
+      __syncwarp();
+    };
+    // S of tile `it` is issued NWG-1 tiles ahead of the PV it feeds, so every warpgroup has work
+    constexpr int LAG = NWG - 1;
+    for (int it = 0; it < my_tiles + LAG; ++it) {
+      if (it < my_tiles) {
+        const int buf = it % NWG, qs = it % QS, gi = it / T, kvs = gi % KVS;
+        PROF_T(m0);
+        mbar_wait(&sm.q_full[qs], (it / QS) & 1);
+        if (it % T == 0) mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
+        PROF_T(m1);
+        mbar_wait(&sm.buf_empty[buf], ((it / NWG) & 1) ^ 1);
+        fence_after_sync();
+        PROF_T(m2);
+        PROF_ADD1(9, m0, m1); PROF_ADD1(10, m1, m2);
+        if (elect_one_sync()) {
+          const uint32_t q_lo = q_lo0 + qs * (TILE_BYTES >> 4), k_lo = k_lo0 + kvs * (Smem<NK>::KV_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)  // 16 channels per step: 32 B inside the swizzled row
-            umma_ss(tmem + buf * BUF_COLS, umma_desc_sw64(qa + k * 32), umma_desc_sw64(kb + k * 32),
-                    idesc_s, k > 0);
+            umma_ss2(tmem + buf * BUF_COLS, q_lo + k * (32 >> 4), DESC_HI_SW64, k_lo + k * (32 >> 4),
+                     DESC_HI_SW64, idesc_s, k > 0);
           umma_commit(&sm.s_full[buf]);
           umma_commit(&sm.q_empty[qs]);
         }
-        if (it >= LAG) issue_pv(it - LAG);
+        __syncwarp();
       }
+      if (it >= LAG) issue_pv(it - LAG);
     }
-    __syncwarp();
   } else if (warp >= 4) {
     // ============================ softmax + epilogue warpgroups ============================
     const int wg = (warp - 4) >> 2;                  // warpgroup == TMEM buffer
@@ -288,8 +314,10 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     for (int it = wg; it < my_tiles; it += NWG) {
       const int gi = it / T, t = it % T, kvs = gi % KVS;
       const uint32_t use = (it / NWG) & 1;
+      PROF_T(t0);
       mbar_wait(&sm.s_full[wg], use);
       fence_after_sync();
+      PROF_T(t1);
       // Both sweeps double-buffer the TMEM reads: chunk ch+1 is in flight while chunk ch is consumed.
       uint32_t ra[32], rb[32];
       float m = -INFINITY;
@@ -307,6 +335,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         tmem_wait_ld();
       }
       const float neg_m = -m * p.scale_log2;
+      PROF_T(t2);
       float l0 = 0.f, l1 = 0.f;
       auto exp_chunk = [&](const uint32_t (&r)[32], int ch) {
         uint32_t pk[16];
@@ -336,10 +365,12 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       tmem_wait_st();
       fence_before_sync();
       mbar_arrive(&sm.p_full[wg]);
+      PROF_T(t3);
 
       // ---- epilogue: O / l + LePE -> out, lse ----
       mbar_wait(&sm.o_full[wg], use);
       fence_after_sync();
+      PROF_T(t4);
       tmem_ld32(lane_base + O_COL, r);
       tmem_wait_ld();
       fence_before_sync();
@@ -352,6 +383,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       const int4 gc = sm.coord[kvs];  // image, first token of the stripe, head, branch
       const FwdBranch& bg = p.br[gc.w];
       const float inv_l = 1.f / l;
+      PROF_T(t4a);
       const int n = t * TILE + row;  // in-stripe index
       const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
       float o[HD];
@@ -386,6 +418,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
           }
         }
       }
+      PROF_T(t4b);
       const int tok = gc.y + yy * p.W + xx;
       uint4* dst = reinterpret_cast<uint4*>(bg.out + (int64_t)gc.x * bg.o_sb + (int64_t)tok * bg.o_sl +
                                             gc.z * HD);
@@ -399,11 +432,17 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       bg.lse[((int64_t)gc.x * bg.heads + gc.z) * p.L + tok] = m * p.scale + __logf(l);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.kv_empty[kvs]);  // this warp is done with K/V/LePE of the group
+      PROF_T(t5);
+      PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, t4, t5);
+      PROF_ADD(5, t0, t0 + 1);
+      PROF_ADD(12, t4, t4a); PROF_ADD(13, t4a, t4b); PROF_ADD(14, t4b, t5);
     }
   }
   // teardown
   fence_before_sync();
   __syncthreads();
+  PROF_T(k1);
+  PROF_ADD1(11, k0, k1);
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
@@ -467,6 +506,18 @@ bool tc_fwd_supported(const StripeGeom& g, int dtype) {
   return true;
 }
 bool tc_bwd_supported(const StripeGeom& g, int dtype) { return tc_fwd_supported(g, dtype); }
+
+#ifdef CSB_PROF
+extern "C" __attribute__((visibility("default"))) int csb200_debug_prof_fwd(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_prof, sizeof(g_prof));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int tc_fwd_multi(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st) {
   return g[0].N == 128 ? launch_fwd<128>(nbr, g, io, st) : launch_fwd<256>(nbr, g, io, st);

@@ -33,6 +33,14 @@
 #include "tc_common.cuh"
 
 namespace csb200 {
+#ifdef CSB_PROF
+__device__ unsigned long long g_prof_bwd[32];
+#define PROF_T(v) const long long v = clock64()
+#define PROF_ADDT(tid, i, a, b) if (blockIdx.x == 0 && threadIdx.x == (tid)) atomicAdd(&g_prof_bwd[i], (unsigned long long)((b) - (a)))
+#else
+#define PROF_T(v)
+#define PROF_ADDT(tid, i, a, b)
+#endif
 namespace {
 using namespace tc;
 
@@ -106,8 +114,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   constexpr int GS = BCfg<NK>::GS;
   constexpr uint32_t ACC_DVDK = 256, ACC_DQ = 384;
   extern __shared__ uint8_t smem_raw[];
-  BSmem<NK>& sm = *reinterpret_cast<BSmem<NK>*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // align inside the shared window: pointer + integer offset keeps the shared address space (an
+  // integer -> pointer cast makes every access a generic LD/ST with 64-bit address math)
+  BSmem<NK>& sm = *reinterpret_cast<BSmem<NK>*>(smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int my_groups = (p.groups - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -141,6 +150,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
+  PROF_T(kbeg);
 
   if (warp == 0) {
     // ===================================== producer =========================================
@@ -186,71 +196,85 @@ __global__ void __launch_bounds__(THREADS, 1)
     }
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
-      constexpr uint32_t idesc_sdp = umma_idesc_bf16(HALF, false, false);
-      constexpr uint32_t idesc_acc = umma_idesc_bf16(HD, false, true);   // A from TMEM, B MN-major
-      constexpr uint32_t idesc_dq = umma_idesc_bf16(HD, true, true);     // A MN-major smem
-      // MMAs that consume what the convert warps produced for iteration y
-      auto dependent = [&](int y) {
-        const int st = y & 1, gi = y / NIT, r = y % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
-        const int ktc = gi * T + kt, aset = ktc & 1;
-        mbar_wait(&sm.conv_done[st], (y >> 1) & 1);
-        if (qh == 0) mbar_wait(&sm.dvdk_empty[aset], ((ktc >> 1) & 1) ^ 1);
-        fence_after_sync();
+    // the whole warp walks the loop; one elected lane issues (see tc_common.cuh, "cheap issue path")
+    constexpr uint32_t idesc_sdp = umma_idesc_bf16(HALF, false, false);
+    constexpr uint32_t idesc_acc = umma_idesc_bf16(HD, false, true);   // A from TMEM, B MN-major
+    constexpr uint32_t idesc_dq = umma_idesc_bf16(HD, true, true);     // A MN-major smem
+    constexpr uint32_t OP16 = BSmem<NK>::OP_BYTES >> 4, HALF16 = (HALF * ROW_BYTES) >> 4;
+    const uint32_t q_lo0 = desc_lo_sw64(smem_u32(sm.q[0])), k_lo0 = desc_lo_sw64(smem_u32(sm.k[0]));
+    const uint32_t v_lo0 = desc_lo_sw64(smem_u32(sm.v[0])), go_lo0 = desc_lo_sw64(smem_u32(sm.go[0]));
+    const uint32_t ds_lo0 = desc_lo_sw128_mn(smem_u32(sm.ds[0]), DS_BLOCK_BYTES);
+    // MMAs that consume what the convert warps produced for iteration y
+    auto dependent = [&](int y) {
+      const int st = y & 1, gi = y / NIT, r = y % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
+      const int ktc = gi * T + kt, aset = ktc & 1;
+      const int qb = qh >> 1, qbc = ktc * T + qb, dsb = qbc & 1;
+      PROF_T(d0);
+      mbar_wait(&sm.conv_done[st], (y >> 1) & 1);
+      PROF_T(d1);
+      if (qh == 0) mbar_wait(&sm.dvdk_empty[aset], ((ktc >> 1) & 1) ^ 1);
+      if ((qh & 1) && kt == 0 && qb == 0) mbar_wait(&sm.dq_empty[gi & 1], ((gi >> 1) & 1) ^ 1);
+      fence_after_sync();
+      PROF_T(d2);
+      PROF_ADDT(32, 8, d0, d1); PROF_ADDT(32, 9, d1, d2);
+      if (elect_one_sync()) {
         const uint32_t sbase = tmem + st * 128;
-        const uint32_t gob = smem_u32(sm.go[gs]) + qh * (HALF * ROW_BYTES);
-        const uint32_t qb_ = smem_u32(sm.q[gs]) + qh * (HALF * ROW_BYTES);
+        const uint32_t go_lo = go_lo0 + gs * OP16 + qh * HALF16;
+        const uint32_t q_lo = q_lo0 + gs * OP16 + qh * HALF16;
 #pragma unroll
         for (int k = 0; k < HALF / 16; ++k)  // dV += P^T dO : 16 queries per step
-          umma_ts(tmem + ACC_DVDK + aset * 64, sbase + 8 * k, umma_desc_sw64(gob + k * 1024),
-                  idesc_acc, (qh > 0 || k > 0));
+          umma_ts2(tmem + ACC_DVDK + aset * 64, sbase + 8 * k, go_lo + k * (1024 >> 4), DESC_HI_SW64,
+                   idesc_acc, (qh > 0 || k > 0));
 #pragma unroll
         for (int k = 0; k < HALF / 16; ++k)  // dK += dS^T Q
-          umma_ts(tmem + ACC_DVDK + aset * 64 + 32, sbase + 64 + 8 * k,
-                  umma_desc_sw64(qb_ + k * 1024), idesc_acc, (qh > 0 || k > 0));
+          umma_ts2(tmem + ACC_DVDK + aset * 64 + 32, sbase + 64 + 8 * k, q_lo + k * (1024 >> 4),
+                   DESC_HI_SW64, idesc_acc, (qh > 0 || k > 0));
         umma_commit(&sm.stage_free[st]);
         if (qh & 1) {  // a 128-query block of dS^T is complete in shared memory
-          const int qb = qh >> 1, qbc = ktc * T + qb, dsb = qbc & 1;
-          if (kt == 0 && qb == 0) mbar_wait(&sm.dq_empty[gi & 1], ((gi >> 1) & 1) ^ 1);
-          fence_after_sync();
-          const uint32_t dsa = smem_u32(sm.ds[dsb]);
-          const uint32_t kb = smem_u32(sm.k[gs]) + kt * TILE_BYTES;
+          const uint32_t ds_lo = ds_lo0 + dsb * ((2 * DS_BLOCK_BYTES) >> 4);
+          const uint32_t k_lo = k_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
 #pragma unroll
           for (int k = 0; k < TILE / 16; ++k)  // dQ += dS K : 16 keys per step
-            umma_ss(tmem + ACC_DQ + (gi & 1) * 64 + qb * 32,
-                    umma_desc_sw128_mn(dsa + k * 2048, DS_BLOCK_BYTES), umma_desc_sw64(kb + k * 1024),
-                    idesc_dq, (kt > 0 || k > 0));
+            umma_ss2(tmem + ACC_DQ + (gi & 1) * 64 + qb * 32, ds_lo + k * (2048 >> 4), DESC_HI_SW128,
+                     k_lo + k * (1024 >> 4), DESC_HI_SW64, idesc_dq, (kt > 0 || k > 0));
           umma_commit(&sm.ds_free[dsb]);
         }
         if (qh == NH - 1) {
           umma_commit(&sm.dvdk_full[aset]);
           if (kt == T - 1) umma_commit(&sm.dq_full[gi & 1]);
         }
-      };
-      for (int x = 0; x < total_it + 1; ++x) {
-        if (x < total_it) {
-          const int st = x & 1, gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
-          if (r == 0) mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
-          mbar_wait(&sm.stage_free[st], ((x >> 1) & 1) ^ 1);
-          fence_after_sync();
-          const uint32_t ka = smem_u32(sm.k[gs]) + kt * TILE_BYTES;
-          const uint32_t va = smem_u32(sm.v[gs]) + kt * TILE_BYTES;
-          const uint32_t qb_ = smem_u32(sm.q[gs]) + qh * (HALF * ROW_BYTES);
-          const uint32_t gob = smem_u32(sm.go[gs]) + qh * (HALF * ROW_BYTES);
+      }
+      __syncwarp();
+    };
+    for (int x = 0; x < total_it + 1; ++x) {
+      if (x < total_it) {
+        const int st = x & 1, gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
+        PROF_T(e0);
+        if (r == 0) mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
+        PROF_T(e1);
+        mbar_wait(&sm.stage_free[st], ((x >> 1) & 1) ^ 1);
+        fence_after_sync();
+        PROF_T(e2);
+        PROF_ADDT(32, 10, e0, e1); PROF_ADDT(32, 11, e1, e2);
+        if (elect_one_sync()) {
+          const uint32_t k_lo = k_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
+          const uint32_t v_lo = v_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
+          const uint32_t q_lo = q_lo0 + gs * OP16 + qh * HALF16;
+          const uint32_t go_lo = go_lo0 + gs * OP16 + qh * HALF16;
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
-            umma_ss(tmem + st * 128, umma_desc_sw64(ka + k * 32), umma_desc_sw64(qb_ + k * 32),
-                    idesc_sdp, k > 0);
+            umma_ss2(tmem + st * 128, k_lo + k * (32 >> 4), DESC_HI_SW64, q_lo + k * (32 >> 4),
+                     DESC_HI_SW64, idesc_sdp, k > 0);
 #pragma unroll
           for (int k = 0; k < HD / 16; ++k)
-            umma_ss(tmem + st * 128 + 64, umma_desc_sw64(va + k * 32), umma_desc_sw64(gob + k * 32),
-                    idesc_sdp, k > 0);
+            umma_ss2(tmem + st * 128 + 64, v_lo + k * (32 >> 4), DESC_HI_SW64, go_lo + k * (32 >> 4),
+                     DESC_HI_SW64, idesc_sdp, k > 0);
           umma_commit(&sm.sdp_full[st]);
         }
-        if (x >= 1) dependent(x - 1);
+        __syncwarp();
       }
+      if (x >= 1) dependent(x - 1);
     }
-    __syncwarp();
   } else if (warp >= 4 && warp < 12) {
     // ================================ convert warpgroups ====================================
     const int wg = (warp - 4) >> 2;             // == TMEM stage == parity of the half-block
@@ -259,10 +283,13 @@ __global__ void __launch_bounds__(THREADS, 1)
     for (int x = wg; x < total_it; x += 2) {
       const int gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
       const int qbc = (gi * T + kt) * T + (qh >> 1), dsb = qbc & 1;
+      PROF_T(c0);
       mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);   // lse / delta visibility (already complete)
       mbar_wait(&sm.ds_free[dsb], ((qbc >> 1) & 1) ^ 1);
+      PROF_T(c1);
       mbar_wait(&sm.sdp_full[wg], (x >> 1) & 1);
       fence_after_sync();
+      PROF_T(c2);
       uint8_t* ds_row = sm.ds[dsb] + (qh & 1) * DS_BLOCK_BYTES + j * 128;
       const float* lse2 = sm.lse2[gs] + qh * HALF;
       const float* dlt = sm.delta[gs] + qh * HALF;
@@ -303,6 +330,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       fence_before_sync();
       fence_proxy_async_smem();
       mbar_arrive(&sm.conv_done[wg]);
+      PROF_T(c3);
+      PROF_ADDT(128, 0, c0, c1); PROF_ADDT(128, 1, c1, c2); PROF_ADDT(128, 2, c2, c3); PROF_ADDT(128, 3, c0, c0 + 1);
     }
   } else if (warp >= 12) {
     // ================================== epilogue warpgroup ==================================
@@ -318,8 +347,11 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll 1
       for (int kt = 0; kt < T; ++kt) {
         const int ktc = gi * T + kt, aset = ktc & 1;
+        PROF_T(f0);
         mbar_wait(&sm.dvdk_full[aset], (ktc >> 1) & 1);
         fence_after_sync();
+        PROF_T(f1);
+        PROF_ADDT(384, 16, f0, f1);
         uint32_t rv[32], rk[32];
         tmem_ld32(lane_base + ACC_DVDK + aset * 64, rv);
         tmem_ld32(lane_base + ACC_DVDK + aset * 64 + 32, rk);
@@ -376,10 +408,15 @@ __global__ void __launch_bounds__(THREADS, 1)
           dvp[q4] = pack<__nv_bfloat16>(f);
           dkp[q4] = pack<__nv_bfloat16>(h);
         }
+        PROF_T(f2);
+        PROF_ADDT(384, 17, f1, f2);
       }
+      PROF_T(h0);
       // dQ of the whole group
       mbar_wait(&sm.dq_full[gi & 1], (gi >> 1) & 1);
       fence_after_sync();
+      PROF_T(h1);
+      PROF_ADDT(384, 18, h0, h1);
 #pragma unroll 1
       for (int qb = 0; qb < T; ++qb) {
         uint32_t rq[32];
@@ -403,10 +440,14 @@ __global__ void __launch_bounds__(THREADS, 1)
         mbar_arrive(&sm.dq_empty[gi & 1]);
         mbar_arrive(&sm.grp_empty[gs]);  // every MMA of the group has completed (dq_full)
       }
+      PROF_T(h2);
+      PROF_ADDT(384, 19, h1, h2); PROF_ADDT(384, 20, h0, h0 + 1);
     }
   }
   fence_before_sync();
   __syncthreads();
+  PROF_T(kend);
+  PROF_ADDT(32, 24, kbeg, kend);
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
@@ -460,6 +501,18 @@ int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st)
 }
 
 }  // namespace
+
+#ifdef CSB_PROF
+extern "C" __attribute__((visibility("default"))) int csb200_debug_prof_bwd(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_prof_bwd, sizeof(g_prof_bwd));
+  if (reset) {
+    unsigned long long z[32] = {0};
+    cudaMemcpyToSymbol(g_prof_bwd, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
 
 int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st) {
   static_assert(sizeof(BSmem<128>) + 1024 > 114 * 1024 && sizeof(BSmem<256>) + 1024 > 114 * 1024,

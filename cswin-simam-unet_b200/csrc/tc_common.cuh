@@ -160,6 +160,53 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- cheap issue path --------------------------------------------------------------------------
+// One MMA-issuing thread executes every descriptor instruction serially, so the issue stream itself
+// bounds the pipeline when tiles are small (measured: ~490 SASS instructions per backward iteration,
+// ~8 cycles each, r1_attn_bwd_tc_s3).  Two things keep it short: (1) the whole warp runs the loop and
+// one lane is chosen with elect.sync, which ptxas recognises as single-thread code — a plain
+// `if (lane == 0)` makes it wrap every UTCHMMA in an ELECT / R2UR.BROADCAST / BRA.U.ANY loop;
+// (2) descriptors are (lo, hi) register pairs whose hi word is a constant and whose lo word advances
+// by an immediate (shared memory is < 256 KB, so address >> 4 never leaves its 14-bit field).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  __syncwarp();  // lanes leave the mbarrier spin loops at different times
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "@p mov.s32 %0, 1;\n\t}"
+      : "+r"(pred));
+  return pred != 0;
+}
+constexpr uint32_t DESC_HI_SW64 = (512u >> 4) | (1u << 14) | (4u << 29);      // SBO 512, version, SWIZZLE_64B
+constexpr uint32_t DESC_HI_SW128 = (1024u >> 4) | (1u << 14) | (2u << 29);    // SBO 1024, version, SWIZZLE_128B
+__device__ __forceinline__ uint32_t desc_lo_sw64(uint32_t smem_addr) { return (smem_addr >> 4) | (1u << 16); }
+__device__ __forceinline__ uint32_t desc_lo_sw128_mn(uint32_t smem_addr, uint32_t lbo_bytes) {
+  return (smem_addr >> 4) | ((lbo_bytes >> 4) << 16);
+}
+// D[tmem] (+)= A[smem] * B[smem], descriptors as (lo, hi) words
+__device__ __forceinline__ void umma_ss2(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo,
+                                         uint32_t b_hi, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void umma_ts2(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_lo, uint32_t b_hi,
+                                         uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 db;\n\t"
+      "setp.ne.b32 p, %5, 0;\n\t"
+      "mov.b64 db, {%2, %3};\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], db, %4, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when they complete
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(
