@@ -204,6 +204,39 @@ def column_sum(x2d: torch.Tensor) -> torch.Tensor:
     return out
 
 
+# Low-precision shadows of the fp32 master parameters.  Under autocast every Linear used to cast its
+# weight and bias on every call (250 cast launches per 512^2 step); TrainStep refreshes all shadows
+# with ONE multi-tensor copy after the optimizer step instead.  A shadow is only trusted while the
+# parameter's version counter still has the value it had when the shadow was written.
+def shadow_params(params, dtype=torch.bfloat16):
+    """(Re)build the shadows of `params`; returns (masters, shadows) for later ``refresh_shadows``."""
+    masters = [p for p in params if p.is_cuda and p.dtype == torch.float32]
+    shadows = []
+    with torch.no_grad():
+        for p in masters:
+            sh = p.detach().to(dtype)
+            p._csb_shadow = (sh, p._version)
+            shadows.append(sh)
+    return masters, shadows
+
+
+def refresh_shadows(masters, shadows):
+    """shadow <- master for every pair, as one multi-tensor launch; call after optimizer.step()."""
+    with torch.no_grad():
+        torch._foreach_copy_(shadows, masters)
+    for p, sh in zip(masters, shadows):
+        p._csb_shadow = (sh, p._version)
+
+
+def cast_param(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:
+    if p is None or p.dtype == dtype:
+        return p
+    sh = getattr(p, "_csb_shadow", None)
+    if sh is not None and sh[1] == p._version and sh[0].dtype == dtype:
+        return sh[0]
+    return p.to(dtype)
+
+
 class _LinearFn(torch.autograd.Function):
     """y = x W^T + b.  GEMMs stay on cuBLAS (torch.mm); the bias gradient, which ATen computes with a
     generic strided reduction at ~1/9 of the HBM roofline, is one csb200_colsum pass."""
@@ -212,8 +245,7 @@ class _LinearFn(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, weight, bias, compute_dtype):
         xc = x if x.dtype == compute_dtype else x.to(compute_dtype)
-        wc = weight if weight.dtype == compute_dtype else weight.to(compute_dtype)
-        bc = None if bias is None else (bias if bias.dtype == compute_dtype else bias.to(compute_dtype))
+        wc, bc = cast_param(weight, compute_dtype), cast_param(bias, compute_dtype)
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
         return torch.nn.functional.linear(xc, wc, bc)
@@ -234,10 +266,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = torch.mm(g2.t(), x2).to(w_dtype)
         if b_dtype is not None and ctx.needs_input_grad[2]:
-            if capi.lib().csb200_colsum_supported(n, capi.dtype_code(g2)) and g2.data_ptr() % 16 == 0:
-                gb = column_sum(g2).to(b_dtype)
-            else:
-                gb = g2.sum(0).to(b_dtype)
+            gb = _bias_grad(g2, n).to(b_dtype)
         return gx, gw, gb, None
 
 
@@ -249,6 +278,140 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) 
     if dt not in (torch.float32, torch.bfloat16):
         return torch.nn.functional.linear(x, weight, bias)
     return _LinearFn.apply(x, weight, bias, dt)
+
+
+def _bias_grad(g2: torch.Tensor, n: int) -> torch.Tensor:
+    """fp32 column sums of a (rows, n) gradient: csb200_colsum when the width tiles, else ATen."""
+    if g2.is_contiguous() and capi.lib().csb200_colsum_supported(n, capi.dtype_code(g2)) and g2.data_ptr() % 16 == 0:
+        return column_sum(g2)
+    return g2.sum(0, dtype=torch.float32)
+
+
+class _LinearGeluFn(torch.autograd.Function):
+    """a = GELU(x W^T + b) — fc1 + act of the Mlp (C:188-196).  The GEMMs stay on cuBLAS; the exact-erf
+    GELU is one csb200 pass, and its backward pass also emits the bias gradient (csb200_gelu_bwd), so
+    neither ATen's GeluBackward nor a separate column-sum pass over the 4C-wide tensor runs."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias, compute_dtype):
+        xc = x if x.dtype == compute_dtype else x.to(compute_dtype)
+        wc, bc = cast_param(weight, compute_dtype), cast_param(bias, compute_dtype)
+        h = torch.nn.functional.linear(xc, wc, bc)
+        n = wc.shape[0]
+        h2 = h.reshape(-1, n)
+        a = torch.empty_like(h)
+        lib = capi.lib()
+        with torch.cuda.device(h.device), _span("gelu_fwd", 2 * h.numel() * h.element_size()):
+            capi.check(lib.csb200_gelu_fwd(_ptr(h2), _ptr(a), h2.shape[0], n, capi.dtype_code(h),
+                                           _vp(capi.stream_of(h))), "csb200_gelu_fwd")
+        ctx.save_for_backward(xc, wc, h)
+        ctx.meta = (x.dtype, weight.dtype, bias.dtype)
+        return a
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, ga):
+        xc, wc, h = ctx.saved_tensors
+        x_dtype, w_dtype, b_dtype = ctx.meta
+        n = wc.shape[0]
+        g2 = ga.reshape(-1, n)
+        if not g2.is_contiguous() or g2.dtype != h.dtype:
+            g2 = g2.to(h.dtype).contiguous()
+        rows = g2.shape[0]
+        dh = torch.empty_like(g2)
+        gb = torch.empty(n, dtype=torch.float32, device=h.device)
+        lib = capi.lib()
+        nws = lib.csb200_gelu_bwd_workspace_bytes(n)
+        wsp = torch.empty(nws, dtype=torch.uint8, device=h.device)
+        with torch.cuda.device(h.device), _span("gelu_bwd", 3 * h.numel() * h.element_size()):
+            capi.check(lib.csb200_gelu_bwd(_ptr(g2), _ptr(h), _ptr(dh), _ptr(gb), _ptr(wsp), nws, rows, n,
+                                           capi.dtype_code(h), _vp(capi.stream_of(h))), "csb200_gelu_bwd")
+        x2 = xc.reshape(-1, wc.shape[1])
+        gx = gw = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(dh, wc).reshape(xc.shape).to(x_dtype)
+        if ctx.needs_input_grad[1]:
+            gw = torch.mm(dh.t(), x2).to(w_dtype)
+        return gx, gw, (gb.to(b_dtype) if ctx.needs_input_grad[2] else None), None
+
+
+def linear_gelu_supported(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    if bias is None or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return dt in (torch.float32, torch.bfloat16) and \
+        bool(capi.lib().csb200_gelu_supported(weight.shape[0], capi._DTYPES[dt]))
+
+
+def linear_gelu(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    """GELU(F.linear(x, weight, bias)) with the fused csb200 GELU passes (exact erf form)."""
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    return _LinearGeluFn.apply(x, weight, bias, dt)
+
+
+class _Conv2dFn(torch.autograd.Function):
+    """F.conv2d on cuDNN with the bias gradient taken out of ATen's strided reduce_kernel: on a
+    channels-last gradient it is a column sum of the (B*H*W, C) matrix (csb200_colsum)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, weight, bias, stride, padding, compute_dtype):
+        xc = x if x.dtype == compute_dtype else x.to(compute_dtype)
+        wc, bc = cast_param(weight, compute_dtype), cast_param(bias, compute_dtype)
+        ctx.save_for_backward(xc, wc)
+        ctx.cfg = (stride, padding, x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        return torch.nn.functional.conv2d(xc, wc, bc, stride, padding)
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        xc, wc = ctx.saved_tensors
+        stride, padding, x_dtype, w_dtype, b_dtype = ctx.cfg
+        gy = gy.to(xc.dtype)
+        gx, gw, _ = torch.ops.aten.convolution_backward(
+            gy, xc, wc, None, list(stride), list(padding), [1, 1], False, [0, 0], 1,
+            [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
+        gb = None
+        if b_dtype is not None and ctx.needs_input_grad[2]:
+            gb = channel_sum(gy).to(b_dtype)
+        return (None if gx is None else gx.to(x_dtype)), (None if gw is None else gw.to(w_dtype)), gb, None, None, None
+
+
+def channel_sum(g: torch.Tensor) -> torch.Tensor:
+    """fp32 sum over (B, H, W) of a (B, C, H, W) tensor; one flat csb200 pass when it is channels-last."""
+    B, C, H, W = g.shape
+    if g.is_contiguous(memory_format=torch.channels_last) and g.dtype in (torch.float32, torch.bfloat16):
+        return _bias_grad(g.permute(0, 2, 3, 1).reshape(B * H * W, C), C)
+    return g.sum((0, 2, 3), dtype=torch.float32)
+
+
+def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride=1, padding=0) -> torch.Tensor:
+    """Drop-in for ``F.conv2d`` (groups = 1, dilation = 1) on CUDA float32 / bfloat16 tensors."""
+    pair = lambda v: (v, v) if isinstance(v, int) else tuple(v)
+    if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+        return torch.nn.functional.conv2d(x, weight, bias, stride, padding)
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    if dt not in (torch.float32, torch.bfloat16):
+        return torch.nn.functional.conv2d(x, weight, bias, stride, padding)
+    return _Conv2dFn.apply(x, weight, bias, pair(stride), pair(padding), dt)
+
+
+class _ChannelBiasFn(torch.autograd.Function):
+    """x + bias[None, :, None, None] whose bias gradient is a csb200 column sum."""
+
+    @staticmethod
+    def forward(ctx, x, bias):
+        ctx.b_dtype = bias.dtype
+        return x + bias.to(x.dtype).view(1, -1, 1, 1)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g, (channel_sum(g).to(ctx.b_dtype) if ctx.needs_input_grad[1] else None)
+
+
+def add_channel_bias(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:
+    return _ChannelBiasFn.apply(x, bias) if x.is_cuda else x + bias.to(x.dtype).view(1, -1, 1, 1)
 
 
 # ------------------------------------------------------------------------------------------------

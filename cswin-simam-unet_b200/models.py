@@ -13,7 +13,8 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_linear, apply_norm,
+from . import functional as csbF
+from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_conv, apply_linear, apply_norm,
                       carafe_upsample, image_as_tokens, tokens_as_image, _side)
 
 
@@ -112,7 +113,7 @@ class CSWinTransformer(nn.Module):
         model is re-entrant (CUDA graphs, overlapping micro-batches)."""
         # channels-last stem: the 7x7 conv then emits NHWC, which IS the token layout (no transpose copy)
         stem = self.stage1_conv_embed
-        x = self.pos_drop(apply_norm(stem[2], stem[1](stem[0](x.contiguous(memory_format=torch.channels_last)))))
+        x = self.pos_drop(apply_norm(stem[2], stem[1](apply_conv(stem[0], x.contiguous(memory_format=torch.channels_last)))))
         skips: List[torch.Tensor] = []
         for blocks, merge in ((self.stage1, self.merge1), (self.stage2, self.merge2), (self.stage3, self.merge3)):
             for blk in blocks:
@@ -152,7 +153,7 @@ class CSWinTransformer(nn.Module):
         b_eff = w_out @ up.out.bias
         low = F.conv2d(img, w_eff)
         logits = carafe_upsample(low, img, up.down, up.encoder, up.up_factor, up.kernel_size)
-        return logits + b_eff.to(logits.dtype).view(1, -1, 1, 1)
+        return csbF.add_channel_bias(logits, b_eff)
 
     def forward_logits(self, x):
         feats, skips = self.forward_features(x)

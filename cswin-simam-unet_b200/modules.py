@@ -49,6 +49,15 @@ def apply_norm(norm: nn.Module, x: torch.Tensor, feeds_gemm: bool = False) -> to
     return norm(x)
 
 
+def apply_conv(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
+    """A plain ``nn.Conv2d`` (groups 1, dilation 1, zero padding) runs cuDNN through csbF.conv2d, which
+    takes the bias gradient as one flat column-sum pass; anything else runs the module as given."""
+    if type(conv) is nn.Conv2d and x.is_cuda and conv.groups == 1 and conv.dilation == (1, 1) \
+            and conv.padding_mode == "zeros" and not isinstance(conv.padding, str):
+        return csbF.conv2d(x, conv.weight, conv.bias, conv.stride, conv.padding)
+    return conv(x)
+
+
 def apply_linear(lin: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """A plain ``nn.Linear`` runs through csbF.linear (cuBLAS GEMMs + one-pass bias gradient)."""
     if type(lin) is nn.Linear and x.is_cuda:
@@ -101,7 +110,12 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x):
-        return self.drop(apply_linear(self.fc2, self.drop(self.act(apply_linear(self.fc1, x)))))
+        if type(self.fc1) is nn.Linear and type(self.act) is nn.GELU and self.act.approximate == "none" \
+                and csbF.linear_gelu_supported(x, self.fc1.weight, self.fc1.bias):
+            hidden = csbF.linear_gelu(x, self.fc1.weight, self.fc1.bias)  # fc1 + GELU, fused passes
+        else:
+            hidden = self.act(apply_linear(self.fc1, x))
+        return self.drop(apply_linear(self.fc2, self.drop(hidden)))
 
 
 class LePEAttention(nn.Module):
@@ -212,7 +226,7 @@ class Merge_Block(nn.Module):
 
     def forward(self, x):
         side = _side(x.shape[1])
-        return apply_norm(self.norm, image_as_tokens(self.conv(tokens_as_image(x, side, side))))
+        return apply_norm(self.norm, image_as_tokens(apply_conv(self.conv, tokens_as_image(x, side, side))))
 
 
 def carafe_kernels(img: torch.Tensor, down: nn.Conv2d, encoder: nn.Conv2d, up: int) -> torch.Tensor:
@@ -235,7 +249,7 @@ def carafe_upsample(low: torch.Tensor, img: torch.Tensor, down: nn.Conv2d, encod
     """Kernel prediction (two convs on cuDNN) + fused softmax / reassembly kernel; on tensors the kernel
     does not take (CPU, channel counts that are neither 1 nor a multiple of 8, k != 3) the same maths
     runs as torch ops."""
-    enc = encoder(down(img))
+    enc = apply_conv(encoder, apply_conv(down, img))
     if k == 3 and low.dtype == enc.dtype and csbF.carafe_supported(low):
         return csbF.carafe_reassemble(low, enc, up)
     return carafe_reassemble(low, torch.softmax(F.pixel_shuffle(enc, up), dim=1), up, k)
@@ -263,7 +277,7 @@ class CARAFE(nn.Module):
         img = tokens_as_image(x, side, side)
         low = F.conv2d(img, self.out.weight)  # bias deferred past the reassembly
         up = carafe_upsample(low, img, self.down, self.encoder, self.up_factor, self.kernel_size)
-        return image_as_tokens(up + self.out.bias.to(up.dtype).view(1, -1, 1, 1))
+        return image_as_tokens(csbF.add_channel_bias(up, self.out.bias))
 
 
 class CARAFE4(CARAFE):

@@ -15,6 +15,8 @@ from typing import Tuple
 import torch
 import torch.nn.functional as F
 
+from . import functional as csbF
+
 
 def synthetic_batch(batch: int, size: int, device, seed: int = 0, first_index: int = 0,
                     pin: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
@@ -58,6 +60,18 @@ class TrainStep:
         self.model, self.optimizer, self.precision, self.reducer = model, optimizer, precision, reducer
         self.cuda_graph = cuda_graph
         self._graph = self._graph_opt = None
+        self._shadow = None  # (fp32 masters, bf16 shadows): see functional.shadow_params
+
+    def _optimizer_step(self):
+        """optimizer.step() + ONE multi-tensor refresh of the bf16 shadows the Linear / conv layers read
+        (instead of one cast kernel per layer per step)."""
+        self.optimizer.step()
+        if self.precision == "bf16":
+            if self._shadow is None:
+                params = [p for g in self.optimizer.param_groups for p in g["params"]]
+                self._shadow = csbF.shadow_params(params)
+            else:
+                csbF.refresh_shadows(*self._shadow)
 
     def _autocast(self, device_type: str):
         if self.precision == "bf16":
@@ -106,6 +120,8 @@ class TrainStep:
                 for v in st.values():
                     if torch.is_tensor(v):
                         v.zero_()
+            if self._shadow is not None:
+                csbF.refresh_shadows(*self._shadow)
         self._graph = torch.cuda.CUDAGraph()
         self._graph_opt = None
         if self.reducer is None:
@@ -124,7 +140,7 @@ class TrainStep:
             self._loss = loss.detach()
         self._graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
-            self.optimizer.step()
+            self._optimizer_step()
 
     def _eager_step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         if self.reducer is not None:
@@ -135,5 +151,5 @@ class TrainStep:
         loss.backward()
         if self.reducer is not None:
             self.reducer.finish_step()  # wait for the bucketed all-reduces
-        self.optimizer.step()
+        self._optimizer_step()
         return loss.detach()

@@ -106,6 +106,20 @@ CSB200_API int csb200_colsum(const void* x, float* out, void* workspace, size_t 
                              int64_t rows, int64_t cols, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * GELU of the Mlp hidden layer (Mlp.forward C:188-196, act_layer() = nn.GELU in its exact erf form)
+ * on a row-major [rows][cols] matrix: forward in one pass; backward writes grad_h = grad_out * gelu'(h)
+ * AND the column sums of grad_h (the bias gradient of fc1) in the same pass.  Same tiling rule as
+ * csb200_colsum (cols a multiple of the 16-byte vector width, cols / width <= 256).
+ * ---------------------------------------------------------------------------------------------- */
+CSB200_API int csb200_gelu_supported(int64_t cols, int dtype);
+CSB200_API int csb200_gelu_fwd(const void* h, void* out, int64_t rows, int64_t cols, int dtype,
+                               void* stream);
+CSB200_API size_t csb200_gelu_bwd_workspace_bytes(int64_t cols);
+CSB200_API int csb200_gelu_bwd(const void* grad_out, const void* h, void* grad_h, float* grad_bias,
+                               void* workspace, size_t workspace_bytes, int64_t rows, int64_t cols,
+                               int dtype, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused CARAFE reassembly — CARAFE.forward C:406-431 / CARAFE4 C:455-480 without the pixel-shuffled
  * logits, the fp32 softmax tensor, the 9x unfold and the batched 9 x up^2 matmul:
  *   out[b, h*up+dy, w*up+dx, c] = sum_tap softmax_tap(enc[b, h, w, tap*up^2 + dy*up + dx])
