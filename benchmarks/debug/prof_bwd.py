@@ -20,4 +20,5 @@ for name, reso, split, heads, C in [("s1",128,1,2,64),("s2",64,2,4,128),("s3",32
     print(name, "kernel cycles", v[24], "convert iters (WG0)", v[3], "groups", v[20])
     print("  convert WG0 per iter: wait_ds %.0f  wait_sdp %.0f  compute %.0f" % (v[0]/nc, v[1]/nc, v[2]/nc))
     print("  MMA per iter(all): wait_conv %.0f wait_acc %.0f wait_grp %.0f wait_stage %.0f" % tuple(x/(2*nc) for x in v[8:12]))
+    print("  MMA issue per iter: sdp %.0f  dependent %.0f" % (v[12]/(2*nc), v[13]/(2*nc)))
     print("  epilogue per group: wait_dvdk %.0f  dvdk_out %.0f  wait_dq %.0f  dq_out %.0f" % tuple(x/ng for x in v[16:20]))

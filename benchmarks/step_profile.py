@@ -40,5 +40,6 @@ if len(sys.argv) > 2 and sys.argv[2] == "ops":
         torch.cuda.synchronize()
     ops = sorted(prof.key_averages(group_by_input_shape=True), key=lambda e: -e.self_device_time_total)
     print("\n--- aten ops by self device time (one step), with input shapes ---")
-    for e in ops[:40]:
+    ops = [e for e in ops if not e.key.startswith("void ") and "::" in e.key or e.key.startswith("_")]
+    for e in ops[:70]:
         print(f"{e.self_device_time_total / 1e3:8.3f} ms  n={e.count:4d}  {e.key[:40]:40s} {str(e.input_shapes)[:110]}")

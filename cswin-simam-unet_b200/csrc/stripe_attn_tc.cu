@@ -7,10 +7,11 @@
 // (C:199-206, C:248-254) ARE the TMA address generation.  Tiles land 64-byte-swizzled, which is at
 // once the K-major layout of Q and K for S = Q K^T and the MN-major layout of V for O = P V.
 //
-//   warp 0      TMA producer (K, V, LePE taps per group; Q per tile)
-//   warp 1      single-thread tcgen05.mma issuer:  S = Q K^T (M128 x N{128,256} x K32) into TMEM,
-//               O = P V (M128 x N32 x K{128,256}) with P read from TMEM as the A operand
+//   warp 0      TMA producer (K, V, LePE taps per group; Q per tile); K and V in separate rings: K is
+//               released as soon as S = Q K^T has completed, V after the epilogue
+//   warp 1      tcgen05.mma issuer:  S = Q K^T (M128 x N{128,256} x K32) into TMEM
 //   warp 2      TMEM allocator
+//   warp 3      tcgen05.mma issuer:  O = P V (M128 x N32 x K{128,256}), P read from TMEM as the A operand
 //   warps 4..   NWG softmax warpgroups (3 for N=128, 2 for N=256), each on its own TMEM buffer and
 //               taking every NWG-th tile, so loads, MMAs, exponentials and stores of different tiles
 //               overlap (the chain TMA -> S -> softmax -> PV -> epilogue is ~4 us long): one thread per query
@@ -125,24 +126,24 @@ template <int NK>
 struct Cfg;
 template <>
 struct Cfg<128> {
-  static constexpr int NWG = 3, KVS = 6, QS = 6;
+  static constexpr int NWG = 3, KS = 5, VS = 10, QS = 5;
 };
 template <>
 struct Cfg<256> {
-  static constexpr int NWG = 2, KVS = 4, QS = 8;
+  static constexpr int NWG = 2, KS = 3, VS = 5, QS = 6;
 };
 
 template <int NK>
 struct Smem {
   static constexpr int KV_BYTES = NK * ROW_BYTES;
-  static constexpr int NWG = Cfg<NK>::NWG, KVS = Cfg<NK>::KVS, QS = Cfg<NK>::QS;
+  static constexpr int NWG = Cfg<NK>::NWG, KS = Cfg<NK>::KS, VS = Cfg<NK>::VS, QS = Cfg<NK>::QS;
   alignas(1024) uint8_t q[QS][TILE_BYTES];
-  alignas(1024) uint8_t k[KVS][KV_BYTES];
-  alignas(1024) uint8_t v[KVS][KV_BYTES];
-  alignas(16) float lepe[KVS][LEPE_FLOATS];  // [tap][c] then bias[c]
-  alignas(16) int4 coord[KVS];               // (image, first token of the stripe, head, -) per K/V stage
+  alignas(1024) uint8_t k[KS][KV_BYTES];
+  alignas(1024) uint8_t v[VS][KV_BYTES];
+  alignas(16) float lepe[VS][LEPE_FLOATS];   // [tap][c] then bias[c]
+  alignas(16) int4 coord[VS];                // (image, first token of the stripe, head, branch) per V stage
   alignas(8) uint64_t q_full[QS], q_empty[QS];
-  uint64_t kv_full[KVS], kv_empty[KVS];
+  uint64_t k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];
   uint64_t s_full[NWG], p_full[NWG], o_full[NWG], buf_empty[NWG];
   uint32_t tmem_base;
 };
@@ -174,7 +175,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     stripe_fwd_tc(const __grid_constant__ FwdMaps maps, const __grid_constant__ FwdParams p) {
   constexpr int T = NK / TILE;          // query tiles per group
   constexpr int NBOX = NK / TILE;       // TMA boxes per K (or V) load
-  constexpr int NWG = Cfg<NK>::NWG, KVS = Cfg<NK>::KVS, QS = Cfg<NK>::QS;
+  constexpr int NWG = Cfg<NK>::NWG, KS = Cfg<NK>::KS, VS = Cfg<NK>::VS, QS = Cfg<NK>::QS;
   constexpr uint32_t P_COL = 0, O_COL = NK / 2, BUF_COLS = NK;
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window: pointer + integer offset keeps the shared address space (an
@@ -195,9 +196,13 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       mbar_init(&sm.q_full[i], 1);
       mbar_init(&sm.q_empty[i], 1);
     }
-    for (int i = 0; i < KVS; ++i) {
-      mbar_init(&sm.kv_full[i], 1);
-      mbar_init(&sm.kv_empty[i], 4 * T);  // one arrival per softmax warp per tile of the group
+    for (int i = 0; i < KS; ++i) {
+      mbar_init(&sm.k_full[i], 1);
+      mbar_init(&sm.k_empty[i], 1);       // tcgen05.commit after the last S = Q K^T of the group
+    }
+    for (int i = 0; i < VS; ++i) {
+      mbar_init(&sm.v_full[i], 2);        // expect_tx arrival (before the TMA) + one after the LePE taps
+      mbar_init(&sm.v_empty[i], 4 * T);   // one arrival per softmax warp per tile of the group
     }
     for (int i = 0; i < NWG; ++i) {
       mbar_init(&sm.s_full[i], 1);
@@ -220,28 +225,24 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     for (int gi = 0; gi < my_groups; ++gi) {
       const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
       const FwdBranch& bg = p.br[c.br];
-      const int kvs = gi % KVS;
-      mbar_wait(&sm.kv_empty[kvs], ((gi / KVS) & 1) ^ 1);
-      // LePE taps of this head -> smem as [tap][c], bias last (plain stores, released by the arrive)
-      for (int i = lane; i < LEPE_FLOATS; i += 32) {
-        const int tap = i / HD, ch = i % HD;
-        sm.lepe[kvs][i] = tap < 9 ? __ldg(bg.lepe_w + (c.head * HD + ch) * 9 + tap)
-                                  : __ldg(bg.lepe_b + c.head * HD + ch);
-      }
-      if (lane == 0)
-        sm.coord[kvs] = make_int4(c.b, (c.wy * bg.hs) * p.W + c.wx * bg.ws, c.head, c.br);
-      __syncwarp();
+      // K lives only until its S = Q K^T has been issued and completed; V (with the LePE taps) until
+      // the epilogue: separate rings, so K and Q run far ahead of the tiles still in the softmax
+      // warpgroups (one shared ring left ~1.5 groups = 36 KB in flight per SM: latency-bound loads).
+      const int ks = gi % KS, vs = gi % VS;
+      mbar_wait(&sm.k_empty[ks], ((gi / KS) & 1) ^ 1);
+      mbar_wait(&sm.v_empty[vs], ((gi / VS) & 1) ^ 1);
       if (lane == 0) {
-        mbar_expect_tx(&sm.kv_full[kvs], 2 * Smem<NK>::KV_BYTES);
+        mbar_expect_tx(&sm.k_full[ks], Smem<NK>::KV_BYTES);
+        mbar_expect_tx(&sm.v_full[vs], Smem<NK>::KV_BYTES);
         const int x0 = c.wx * bg.ws, y0 = c.wy * bg.hs;
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) {
           // box `bx` covers in-stripe rows [128 bx, 128 bx + 128)
           const int dx = (bg.ws > TILE) ? (bx * TILE) % bg.ws : 0;
           const int dy = (bg.ws > TILE) ? (bx * TILE) / bg.ws : bx * bg.by;
-          tma_load_4d(sm.k[kvs] + bx * TILE_BYTES, &maps.k[c.br], &sm.kv_full[kvs], c.head * HD,
+          tma_load_4d(sm.k[ks] + bx * TILE_BYTES, &maps.k[c.br], &sm.k_full[ks], c.head * HD,
                       x0 + dx, y0 + dy, c.b);
-          tma_load_4d(sm.v[kvs] + bx * TILE_BYTES, &maps.v[c.br], &sm.kv_full[kvs], c.head * HD,
+          tma_load_4d(sm.v[vs] + bx * TILE_BYTES, &maps.v[c.br], &sm.v_full[vs], c.head * HD,
                       x0 + dx, y0 + dy, c.b);
         }
         for (int t = 0; t < T; ++t, ++it) {
@@ -253,57 +254,65 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
           tma_load_4d(sm.q[qs], &maps.q[c.br], &sm.q_full[qs], c.head * HD, x0 + dx, y0 + dy, c.b);
         }
       }
+      // LePE taps of this head -> smem as [tap][c], bias last, AFTER the copies are in flight (the
+      // loads are an L2 round trip); plain stores, released by the second arrival on v_full
+      for (int i = lane; i < LEPE_FLOATS; i += 32) {
+        const int tap = i / HD, ch = i % HD;
+        sm.lepe[vs][i] = tap < 9 ? __ldg(bg.lepe_w + (c.head * HD + ch) * 9 + tap)
+                                 : __ldg(bg.lepe_b + c.head * HD + ch);
+      }
+      if (lane == 0)
+        sm.coord[vs] = make_int4(c.b, (c.wy * bg.hs) * p.W + c.wx * bg.ws, c.head, c.br);
       __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.v_full[vs]);
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    // the whole warp walks the loop; one elected lane issues (see tc_common.cuh, "cheap issue path")
+    // ================================ MMA issuer 1: S = Q K^T ================================
+    // Two issuing warps (S here, PV in warp 3): a single in-order issuer held PV(it-2) back while it
+    // waited for the Q/K/V tiles of tile `it` (measured: the softmax warps then waited ~2400 cycles
+    // for O).  The whole warp walks the loop; one elected lane issues (tc_common.cuh).
     constexpr uint32_t idesc_s = umma_idesc_bf16(NK, false, false);
-    constexpr uint32_t idesc_pv = umma_idesc_bf16(HD, false, true);
     const uint32_t q_lo0 = desc_lo_sw64(smem_u32(sm.q[0])), k_lo0 = desc_lo_sw64(smem_u32(sm.k[0]));
-    const uint32_t v_lo0 = desc_lo_sw64(smem_u32(sm.v[0]));
-    auto issue_pv = [&](int it) {
-      const int buf = it % NWG, kvs = (it / T) % KVS;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int buf = it % NWG, qs = it % QS, gi = it / T, ks = gi % KS;
       PROF_T(m0);
+      mbar_wait(&sm.q_full[qs], (it / QS) & 1);
+      if (it % T == 0) mbar_wait(&sm.k_full[ks], (gi / KS) & 1);
+      PROF_T(m1);
+      mbar_wait(&sm.buf_empty[buf], ((it / NWG) & 1) ^ 1);
+      fence_after_sync();
+      PROF_T(m2);
+      PROF_ADD1(9, m0, m1); PROF_ADD1(10, m1, m2);
+      if (elect_one_sync()) {
+        const uint32_t q_lo = q_lo0 + qs * (TILE_BYTES >> 4), k_lo = k_lo0 + ks * (Smem<NK>::KV_BYTES >> 4);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)  // 16 channels per step: 32 B inside the swizzled row
+          umma_ss2(tmem + buf * BUF_COLS, q_lo + k * (32 >> 4), DESC_HI_SW64, k_lo + k * (32 >> 4),
+                   DESC_HI_SW64, idesc_s, k > 0);
+        umma_commit(&sm.s_full[buf]);
+        umma_commit(&sm.q_empty[qs]);
+        if (it % T == T - 1) umma_commit(&sm.k_empty[ks]);  // every S of the group has read K
+      }
+      __syncwarp();
+    }
+  } else if (warp == 3) {
+    // ================================ MMA issuer 2: O = P V =================================
+    constexpr uint32_t idesc_pv = umma_idesc_bf16(HD, false, true);
+    const uint32_t v_lo0 = desc_lo_sw64(smem_u32(sm.v[0]));
+    for (int it = 0; it < my_tiles; ++it) {
+      const int buf = it % NWG, gi = it / T, vs = gi % VS;
+      if (it % T == 0) mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
       mbar_wait(&sm.p_full[buf], (it / NWG) & 1);
       fence_after_sync();
-      PROF_T(m1);
-      PROF_ADD1(8, m0, m1);
       if (elect_one_sync()) {
         const uint32_t d = tmem + buf * BUF_COLS + O_COL, a = tmem + buf * BUF_COLS + P_COL;
-        const uint32_t v_lo = v_lo0 + kvs * (Smem<NK>::KV_BYTES >> 4);
+        const uint32_t v_lo = v_lo0 + vs * (Smem<NK>::KV_BYTES >> 4);
 #pragma unroll
         for (int k = 0; k < NK / 16; ++k)  // 16 keys per step: 8 TMEM columns of P, 1024 B of V
           umma_ts2(d, a + 8 * k, v_lo + k * (1024 >> 4), DESC_HI_SW64, idesc_pv, k > 0);
         umma_commit(&sm.o_full[buf]);
       }
       __syncwarp();
-    };
-    // S of tile `it` is issued NWG-1 tiles ahead of the PV it feeds, so every warpgroup has work
-    constexpr int LAG = NWG - 1;
-    for (int it = 0; it < my_tiles + LAG; ++it) {
-      if (it < my_tiles) {
-        const int buf = it % NWG, qs = it % QS, gi = it / T, kvs = gi % KVS;
-        PROF_T(m0);
-        mbar_wait(&sm.q_full[qs], (it / QS) & 1);
-        if (it % T == 0) mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
-        PROF_T(m1);
-        mbar_wait(&sm.buf_empty[buf], ((it / NWG) & 1) ^ 1);
-        fence_after_sync();
-        PROF_T(m2);
-        PROF_ADD1(9, m0, m1); PROF_ADD1(10, m1, m2);
-        if (elect_one_sync()) {
-          const uint32_t q_lo = q_lo0 + qs * (TILE_BYTES >> 4), k_lo = k_lo0 + kvs * (Smem<NK>::KV_BYTES >> 4);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)  // 16 channels per step: 32 B inside the swizzled row
-            umma_ss2(tmem + buf * BUF_COLS, q_lo + k * (32 >> 4), DESC_HI_SW64, k_lo + k * (32 >> 4),
-                     DESC_HI_SW64, idesc_s, k > 0);
-          umma_commit(&sm.s_full[buf]);
-          umma_commit(&sm.q_empty[qs]);
-        }
-        __syncwarp();
-      }
-      if (it >= LAG) issue_pv(it - LAG);
     }
   } else if (warp >= 4) {
     // ============================ softmax + epilogue warpgroups ============================
@@ -312,7 +321,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + wg * BUF_COLS;
     constexpr int NCH = NK / 32;
     for (int it = wg; it < my_tiles; it += NWG) {
-      const int gi = it / T, t = it % T, kvs = gi % KVS;
+      const int gi = it / T, t = it % T, vs = gi % VS;
       const uint32_t use = (it / NWG) & 1;
       PROF_T(t0);
       mbar_wait(&sm.s_full[wg], use);
@@ -378,19 +387,19 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       if (lane == 0) mbar_arrive(&sm.buf_empty[wg]);  // S(it+2) may now overwrite this buffer
 
       // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
-      // barrier the MMA warp used (already complete; cannot advance before this warp's kv_empty)
-      mbar_wait(&sm.kv_full[kvs], (gi / KVS) & 1);
-      const int4 gc = sm.coord[kvs];  // image, first token of the stripe, head, branch
+      // barrier the PV issuer used (already complete; cannot advance before this warp's v_empty)
+      mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
+      const int4 gc = sm.coord[vs];  // image, first token of the stripe, head, branch
       const FwdBranch& bg = p.br[gc.w];
       const float inv_l = 1.f / l;
       PROF_T(t4a);
       const int n = t * TILE + row;  // in-stripe index
       const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
       float o[HD];
-      const float* lw = sm.lepe[kvs];
+      const float* lw = sm.lepe[vs];
 #pragma unroll
       for (int cc = 0; cc < HD; ++cc) o[cc] = fmaf(__uint_as_float(r[cc]), inv_l, lw[9 * HD + cc]);
-      const uint8_t* vt = sm.v[kvs];
+      const uint8_t* vt = sm.v[vs];
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int ny = yy + ky - 1;
@@ -431,7 +440,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       }
       bg.lse[((int64_t)gc.x * bg.heads + gc.z) * p.L + tok] = m * p.scale + __logf(l);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.kv_empty[kvs]);  // this warp is done with K/V/LePE of the group
+      if (lane == 0) mbar_arrive(&sm.v_empty[vs]);  // this warp is done with V / LePE of the group
       PROF_T(t5);
       PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, t4, t5);
       PROF_ADD(5, t0, t0 + 1);

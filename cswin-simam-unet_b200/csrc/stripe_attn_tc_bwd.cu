@@ -20,7 +20,8 @@
 //   the LePE transposed stencil on grad_out is added to dV in the epilogue from the grad_out tile
 //   in shared memory; the depthwise weight / bias gradients use the shared reduction kernels.
 //
-//   warp 0 TMA producer | warp 1 MMA issuer | warp 2 TMEM allocator | warps 4-7, 8-11 convert
+//   warp 0 TMA producer | warp 1 MMA issuer (S^T, dP^T) | warp 2 TMEM allocator | warp 3 MMA issuer
+//   (dV, dK, dQ) | warps 4-7, 8-11 convert
 //   warpgroups (even / odd half-blocks, TMEM stage 0 / 1) | warps 12-15 epilogue warpgroup.
 //
 // TMEM (512 columns): stage s at 128 s: S^T [0,64) -> P^T bf16 [0,32); dP^T [64,128) -> dS^T bf16
@@ -130,7 +131,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       prefetch_tensormap(&maps.go[i]);
     }
     for (int i = 0; i < GS; ++i) {
-      mbar_init(&sm.grp_full[i], 1);
+      mbar_init(&sm.grp_full[i], 2);  // expect_tx arrival + one after the lse / delta / tap stores
       mbar_init(&sm.grp_empty[i], 4);
     }
     for (int i = 0; i < 2; ++i) {
@@ -167,17 +168,8 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int gs = gi % GS;
       mbar_wait(&sm.grp_empty[gs], ((gi / GS) & 1) ^ 1);
       const int tok0 = (wy * bg.hs) * p.W + wx * bg.ws;
-      const float* lse = bg.lse + ((int64_t)b * bg.heads + head) * p.L;
-      const float* dl = bg.delta + ((int64_t)b * bg.heads + head) * p.L;
-      for (int i = lane; i < NK; i += 32) {
-        const int tok = tok0 + (i >> bg.ws_log2) * p.W + (i & (bg.ws - 1));
-        sm.lse2[gs][i] = __ldg(lse + tok) * 1.4426950408889634f;
-        sm.delta[gs][i] = __ldg(dl + tok);
-      }
-      for (int i = lane; i < 9 * HD; i += 32)
-        sm.lepe[gs][i] = __ldg(bg.lepe_w + (head * HD + i % HD) * 9 + i / HD);
-      if (lane == 0) sm.coord[gs] = make_int4(b, tok0, head, br);
-      __syncwarp();
+      // the four tile copies first: the lse / delta gathers below are an L2 / DRAM round trip that
+      // used to sit in front of every group's TMA issue
       if (lane == 0) {
         mbar_expect_tx(&sm.grp_full[gs], 4 * BSmem<NK>::OP_BYTES);
         const int x0 = wx * bg.ws, y0 = wy * bg.hs;
@@ -192,31 +184,79 @@ __global__ void __launch_bounds__(THREADS, 1)
           tma_load_4d(sm.go[gs] + off, &maps.go[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
         }
       }
+      const float* lse = bg.lse + ((int64_t)b * bg.heads + head) * p.L;
+      const float* dl = bg.delta + ((int64_t)b * bg.heads + head) * p.L;
+      for (int i = lane; i < NK; i += 32) {
+        const int tok = tok0 + (i >> bg.ws_log2) * p.W + (i & (bg.ws - 1));
+        sm.lse2[gs][i] = __ldg(lse + tok) * 1.4426950408889634f;
+        sm.delta[gs][i] = __ldg(dl + tok);
+      }
+      for (int i = lane; i < 9 * HD; i += 32)
+        sm.lepe[gs][i] = __ldg(bg.lepe_w + (head * HD + i % HD) * 9 + i / HD);
+      if (lane == 0) sm.coord[gs] = make_int4(b, tok0, head, br);
       __syncwarp();
+      if (lane == 0) mbar_arrive(&sm.grp_full[gs]);  // second arrival: the plain stores above are done
     }
   } else if (warp == 1) {
-    // ===================================== MMA issuer =======================================
-    // the whole warp walks the loop; one elected lane issues (see tc_common.cuh, "cheap issue path")
+    // ============================ MMA issuer 1: S^T and dP^T ================================
+    // Two issuing warps: measured, one warp needs ~400 cycles to issue the S^T / dP^T MMAs of an
+    // iteration and ~600 for the dependent ones, and — being in order — it also held S^T(x+1) back
+    // until convert(x-1) had finished.  Ordering between the two warps' MMAs is carried by the same
+    // mbarriers as before (stage_free / conv_done), so nothing else changes.
+    // The whole warp walks the loop; one elected lane issues (tc_common.cuh, "cheap issue path").
     constexpr uint32_t idesc_sdp = umma_idesc_bf16(HALF, false, false);
+    constexpr uint32_t OP16 = BSmem<NK>::OP_BYTES >> 4, HALF16 = (HALF * ROW_BYTES) >> 4;
+    const uint32_t q_lo0 = desc_lo_sw64(smem_u32(sm.q[0])), k_lo0 = desc_lo_sw64(smem_u32(sm.k[0]));
+    const uint32_t v_lo0 = desc_lo_sw64(smem_u32(sm.v[0])), go_lo0 = desc_lo_sw64(smem_u32(sm.go[0]));
+    for (int x = 0; x < total_it; ++x) {
+      const int st = x & 1, gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
+      PROF_T(e0);
+      if (r == 0) mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
+      PROF_T(e1);
+      mbar_wait(&sm.stage_free[st], ((x >> 1) & 1) ^ 1);
+      fence_after_sync();
+      PROF_T(e2);
+      PROF_ADDT(32, 10, e0, e1); PROF_ADDT(32, 11, e1, e2);
+      if (elect_one_sync()) {
+        const uint32_t k_lo = k_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
+        const uint32_t v_lo = v_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
+        const uint32_t q_lo = q_lo0 + gs * OP16 + qh * HALF16;
+        const uint32_t go_lo = go_lo0 + gs * OP16 + qh * HALF16;
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_ss2(tmem + st * 128, k_lo + k * (32 >> 4), DESC_HI_SW64, q_lo + k * (32 >> 4),
+                   DESC_HI_SW64, idesc_sdp, k > 0);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k)
+          umma_ss2(tmem + st * 128 + 64, v_lo + k * (32 >> 4), DESC_HI_SW64, go_lo + k * (32 >> 4),
+                   DESC_HI_SW64, idesc_sdp, k > 0);
+        umma_commit(&sm.sdp_full[st]);
+      }
+      __syncwarp();
+      PROF_T(e3);
+      PROF_ADDT(32, 12, e2, e3);
+    }
+  } else if (warp == 3) {
+    // ==================== MMA issuer 2: dV, dK, dQ (consume the converted tiles) ==================
     constexpr uint32_t idesc_acc = umma_idesc_bf16(HD, false, true);   // A from TMEM, B MN-major
     constexpr uint32_t idesc_dq = umma_idesc_bf16(HD, true, true);     // A MN-major smem
     constexpr uint32_t OP16 = BSmem<NK>::OP_BYTES >> 4, HALF16 = (HALF * ROW_BYTES) >> 4;
     const uint32_t q_lo0 = desc_lo_sw64(smem_u32(sm.q[0])), k_lo0 = desc_lo_sw64(smem_u32(sm.k[0]));
-    const uint32_t v_lo0 = desc_lo_sw64(smem_u32(sm.v[0])), go_lo0 = desc_lo_sw64(smem_u32(sm.go[0]));
+    const uint32_t go_lo0 = desc_lo_sw64(smem_u32(sm.go[0]));
     const uint32_t ds_lo0 = desc_lo_sw128_mn(smem_u32(sm.ds[0]), DS_BLOCK_BYTES);
-    // MMAs that consume what the convert warps produced for iteration y
-    auto dependent = [&](int y) {
+    for (int y = 0; y < total_it; ++y) {
       const int st = y & 1, gi = y / NIT, r = y % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
       const int ktc = gi * T + kt, aset = ktc & 1;
       const int qb = qh >> 1, qbc = ktc * T + qb, dsb = qbc & 1;
       PROF_T(d0);
+      if (r == 0) mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);  // this thread's own view of the TMA data
       mbar_wait(&sm.conv_done[st], (y >> 1) & 1);
       PROF_T(d1);
       if (qh == 0) mbar_wait(&sm.dvdk_empty[aset], ((ktc >> 1) & 1) ^ 1);
       if ((qh & 1) && kt == 0 && qb == 0) mbar_wait(&sm.dq_empty[gi & 1], ((gi >> 1) & 1) ^ 1);
       fence_after_sync();
       PROF_T(d2);
-      PROF_ADDT(32, 8, d0, d1); PROF_ADDT(32, 9, d1, d2);
+      PROF_ADDT(96, 8, d0, d1); PROF_ADDT(96, 9, d1, d2);
       if (elect_one_sync()) {
         const uint32_t sbase = tmem + st * 128;
         const uint32_t go_lo = go_lo0 + gs * OP16 + qh * HALF16;
@@ -245,35 +285,8 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
       }
       __syncwarp();
-    };
-    for (int x = 0; x < total_it + 1; ++x) {
-      if (x < total_it) {
-        const int st = x & 1, gi = x / NIT, r = x % NIT, kt = r / NH, qh = r % NH, gs = gi % GS;
-        PROF_T(e0);
-        if (r == 0) mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
-        PROF_T(e1);
-        mbar_wait(&sm.stage_free[st], ((x >> 1) & 1) ^ 1);
-        fence_after_sync();
-        PROF_T(e2);
-        PROF_ADDT(32, 10, e0, e1); PROF_ADDT(32, 11, e1, e2);
-        if (elect_one_sync()) {
-          const uint32_t k_lo = k_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
-          const uint32_t v_lo = v_lo0 + gs * OP16 + kt * (TILE_BYTES >> 4);
-          const uint32_t q_lo = q_lo0 + gs * OP16 + qh * HALF16;
-          const uint32_t go_lo = go_lo0 + gs * OP16 + qh * HALF16;
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_ss2(tmem + st * 128, k_lo + k * (32 >> 4), DESC_HI_SW64, q_lo + k * (32 >> 4),
-                     DESC_HI_SW64, idesc_sdp, k > 0);
-#pragma unroll
-          for (int k = 0; k < HD / 16; ++k)
-            umma_ss2(tmem + st * 128 + 64, v_lo + k * (32 >> 4), DESC_HI_SW64, go_lo + k * (32 >> 4),
-                     DESC_HI_SW64, idesc_sdp, k > 0);
-          umma_commit(&sm.sdp_full[st]);
-        }
-        __syncwarp();
-      }
-      if (x >= 1) dependent(x - 1);
+      PROF_T(d3);
+      PROF_ADDT(96, 13, d2, d3);
     }
   } else if (warp >= 4 && warp < 12) {
     // ================================ convert warpgroups ====================================
