@@ -39,7 +39,8 @@ _lock = threading.Lock()
 
 EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_count", "csb200_simam_fwd",
            "csb200_simam_bwd", "csb200_layernorm_supported", "csb200_layernorm_fwd",
-           "csb200_layernorm_bwd_workspace_bytes", "csb200_layernorm_bwd", "csb200_colsum_supported",
+           "csb200_layernorm_bwd_workspace_bytes", "csb200_layernorm_bwd", "csb200_add_layernorm_fwd",
+           "csb200_add_layernorm_bwd", "csb200_colsum_supported",
            "csb200_colsum_workspace_bytes", "csb200_colsum", "csb200_gelu_supported", "csb200_gelu_fwd",
            "csb200_gelu_bwd_workspace_bytes", "csb200_gelu_bwd", "csb200_carafe_supported", "csb200_carafe_fwd",
            "csb200_carafe_bwd", "csb200_stripe_attn_engine", "csb200_stripe_attn_fwd",
@@ -73,6 +74,10 @@ def lib() -> ctypes.CDLL:
         L.csb200_layernorm_bwd_workspace_bytes.restype = ctypes.c_size_t
         L.csb200_layernorm_bwd.argtypes = [vp] * 8 + [ctypes.c_size_t, i64, i64, ctypes.c_int, ctypes.c_int, vp]
         L.csb200_layernorm_bwd.restype = ctypes.c_int
+        L.csb200_add_layernorm_fwd.argtypes = [vp] * 7 + [i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp]
+        L.csb200_add_layernorm_fwd.restype = ctypes.c_int
+        L.csb200_add_layernorm_bwd.argtypes = [vp] * 9 + [ctypes.c_size_t, i64, i64, ctypes.c_int, ctypes.c_int, vp]
+        L.csb200_add_layernorm_bwd.restype = ctypes.c_int
         L.csb200_colsum_supported.argtypes = [i64, ctypes.c_int]
         L.csb200_colsum_supported.restype = ctypes.c_int
         L.csb200_colsum_workspace_bytes.argtypes = [i64]

@@ -76,9 +76,9 @@ __device__ __forceinline__ float row_sum(float v) {
 // a lane covers channels (j * LPR + lane_in_row) * NE .. + NE  (coalesced across the row's lanes).
 template <typename TIn, typename TOut, int LPR, int CPL, int NE>
 __global__ void __launch_bounds__(LN_THREADS)
-    layernorm_fwd_kernel(const TIn* __restrict__ x, const float* __restrict__ gamma,
-                         const float* __restrict__ beta, TOut* __restrict__ y,
-                         float* __restrict__ stats, int64_t rows, float eps) {
+    layernorm_fwd_kernel(const TIn* __restrict__ x, const TIn* __restrict__ res, TIn* __restrict__ sum_out,
+                         const float* __restrict__ gamma, const float* __restrict__ beta,
+                         TOut* __restrict__ y, float* __restrict__ stats, int64_t rows, float eps) {
   constexpr int C = LPR * CPL * NE, RPW = 32 / LPR;
   const int lane = threadIdx.x & 31, lr = lane % LPR, sub = lane / LPR;
   float g[CPL][NE], b[CPL][NE];
@@ -101,6 +101,22 @@ __global__ void __launch_bounds__(LN_THREADS)
       else
 #pragma unroll
         for (int e = 0; e < NE; ++e) v[j][e] = 0.f;
+    }
+    if (res != nullptr && ok) {
+      // fused residual add (C:367 / C:369 feeding the next pre-norm): s = x + res is written once, in
+      // the stream's dtype, and the statistics are taken from the ROUNDED s — exactly what a separate
+      // add kernel followed by this LayerNorm would produce
+#pragma unroll
+      for (int j = 0; j < CPL; ++j) {
+        float rv[NE];
+        load_n<TIn, NE>(res + r * C + (j * LPR + lr) * NE, rv);
+#pragma unroll
+        for (int e = 0; e < NE; ++e) {
+          v[j][e] += rv[e];
+          if constexpr (sizeof(TIn) == 2) v[j][e] = __bfloat162float(__float2bfloat16_rn(v[j][e]));
+        }
+        store_n<TIn, NE>(sum_out + r * C + (j * LPR + lr) * NE, v[j]);
+      }
     }
     float s = 0.f;
 #pragma unroll
@@ -137,7 +153,8 @@ template <typename TIn, typename TGy, typename TGx, int LPR, int CPL, int NE>
 __global__ void __launch_bounds__(LN_THREADS)
     layernorm_bwd_kernel(const TIn* __restrict__ x, const TGy* __restrict__ gy,
                          const float* __restrict__ gamma, const float* __restrict__ stats,
-                         TGx* __restrict__ gx, float* __restrict__ partial, int64_t rows) {
+                         const TGx* __restrict__ gres, TGx* __restrict__ gx, float* __restrict__ partial,
+                         int64_t rows) {
   constexpr int C = LPR * CPL * NE, RPW = 32 / LPR;
   __shared__ float s_part[LN_WARPS][2 * C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane % LPR, sub = lane / LPR;
@@ -187,6 +204,12 @@ __global__ void __launch_bounds__(LN_THREADS)
         float o[NE];
 #pragma unroll
         for (int e = 0; e < NE; ++e) o[e] = rstd * (gv[j][e] - c1 - xv[j][e] * c2);
+        if (gres != nullptr) {  // gradient arriving on the residual stream itself: summed here, not by autograd
+          float rv[NE];
+          load_n<TGx, NE>(gres + r * C + (j * LPR + lr) * NE, rv);
+#pragma unroll
+          for (int e = 0; e < NE; ++e) o[e] += rv[e];
+        }
         store_n<TGx, NE>(gx + r * C + (j * LPR + lr) * NE, o);
       }
     }
@@ -262,23 +285,24 @@ bool ln_shape(int64_t C, int* lpr, int* cpl) {
   else { if constexpr (NE == 4) { CALL(32, 4); } }
 
 template <typename TIn, typename TOut>
-int ln_fwd_t(const void* x, const float* gamma, const float* beta, void* y, float* stats,
-             int64_t rows, int64_t C, float eps, cudaStream_t st) {
+int ln_fwd_t(const void* x, const void* res, void* sum_out, const float* gamma, const float* beta, void* y,
+             float* stats, int64_t rows, int64_t C, float eps, cudaStream_t st) {
   constexpr int NE = 16 / sizeof(TIn);
   int lpr, cpl;
   if (!ln_shape<TIn>(C, &lpr, &cpl))
     return fail(CSB200_ERR_UNSUPPORTED, "layernorm: C=%lld is not tiled for this dtype", (long long)C);
 #define CALL(L, P)                                                                              \
   layernorm_fwd_kernel<TIn, TOut, L, P, NE><<<ln_grid(rows, 32 / L), LN_THREADS, 0, st>>>(      \
-      static_cast<const TIn*>(x), gamma, beta, static_cast<TOut*>(y), stats, rows, eps)
+      static_cast<const TIn*>(x), static_cast<const TIn*>(res), static_cast<TIn*>(sum_out), gamma, beta, \
+      static_cast<TOut*>(y), stats, rows, eps)
   LN_DISPATCH_SHAPE(CALL)
 #undef CALL
   return check_launch("layernorm_fwd_kernel");
 }
 
 template <typename TIn, typename TGy, typename TGx>
-int ln_bwd_t(const void* x, const void* gy, const float* gamma, const float* stats, void* gx,
-             float* ggamma, float* gbeta, float* partial, int64_t rows, int64_t C,
+int ln_bwd_t(const void* x, const void* gy, const void* gres, const float* gamma, const float* stats,
+             void* gx, float* ggamma, float* gbeta, float* partial, int64_t rows, int64_t C,
              cudaStream_t st) {
   constexpr int NE = 16 / sizeof(TIn);
   int lpr, cpl;
@@ -288,7 +312,7 @@ int ln_bwd_t(const void* x, const void* gy, const float* gamma, const float* sta
 #define CALL(L, P)                                                                       \
   layernorm_bwd_kernel<TIn, TGy, TGx, L, P, NE><<<grid, LN_THREADS, 0, st>>>(            \
       static_cast<const TIn*>(x), static_cast<const TGy*>(gy), gamma, stats,             \
-      static_cast<TGx*>(gx), partial, rows)
+      static_cast<const TGx*>(gres), static_cast<TGx*>(gx), partial, rows)
   LN_DISPATCH_SHAPE(CALL)
 #undef CALL
   int rc = check_launch("layernorm_bwd_kernel");
@@ -313,19 +337,38 @@ extern "C" int csb200_layernorm_supported(int64_t channels, int x_dtype) {
   return 0;
 }
 
+static int ln_fwd_dispatch(const void* x, const void* res, void* sum_out, const float* gamma,
+                           const float* beta, void* y, float* stats, int64_t rows, int64_t channels,
+                           int x_dtype, int y_dtype, float eps, void* stream, const char* who) {
+  if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(y_dtype))
+    return fail(CSB200_ERR_INVALID, "%s: bad size or dtype", who);
+  if (rows == 0) return CSB200_OK;
+  if (!x || !gamma || !beta || !y || !stats || ((res == nullptr) != (sum_out == nullptr)))
+    return fail(CSB200_ERR_INVALID, "%s: null pointer", who);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (x_dtype == CSB200_F32)
+    return y_dtype == CSB200_F32
+               ? ln_fwd_t<float, float>(x, res, sum_out, gamma, beta, y, stats, rows, channels, eps, st)
+               : ln_fwd_t<float, bf16>(x, res, sum_out, gamma, beta, y, stats, rows, channels, eps, st);
+  return y_dtype == CSB200_F32
+             ? ln_fwd_t<bf16, float>(x, res, sum_out, gamma, beta, y, stats, rows, channels, eps, st)
+             : ln_fwd_t<bf16, bf16>(x, res, sum_out, gamma, beta, y, stats, rows, channels, eps, st);
+}
+
 extern "C" int csb200_layernorm_fwd(const void* x, const float* gamma, const float* beta, void* y,
                                     float* stats, int64_t rows, int64_t channels, int x_dtype,
                                     int y_dtype, float eps, void* stream) {
-  if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(y_dtype))
-    return fail(CSB200_ERR_INVALID, "layernorm_fwd: bad size or dtype");
-  if (rows == 0) return CSB200_OK;
-  if (!x || !gamma || !beta || !y || !stats) return fail(CSB200_ERR_INVALID, "layernorm_fwd: null pointer");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (x_dtype == CSB200_F32)
-    return y_dtype == CSB200_F32 ? ln_fwd_t<float, float>(x, gamma, beta, y, stats, rows, channels, eps, st)
-                                 : ln_fwd_t<float, bf16>(x, gamma, beta, y, stats, rows, channels, eps, st);
-  return y_dtype == CSB200_F32 ? ln_fwd_t<bf16, float>(x, gamma, beta, y, stats, rows, channels, eps, st)
-                               : ln_fwd_t<bf16, bf16>(x, gamma, beta, y, stats, rows, channels, eps, st);
+  return ln_fwd_dispatch(x, nullptr, nullptr, gamma, beta, y, stats, rows, channels, x_dtype, y_dtype, eps,
+                         stream, "layernorm_fwd");
+}
+
+extern "C" int csb200_add_layernorm_fwd(const void* x, const void* residual, void* sum_out,
+                                        const float* gamma, const float* beta, void* y, float* stats,
+                                        int64_t rows, int64_t channels, int x_dtype, int y_dtype, float eps,
+                                        void* stream) {
+  if (rows > 0 && (!residual || !sum_out)) return fail(CSB200_ERR_INVALID, "add_layernorm_fwd: null pointer");
+  return ln_fwd_dispatch(x, residual, sum_out, gamma, beta, y, stats, rows, channels, x_dtype, y_dtype, eps,
+                         stream, "add_layernorm_fwd");
 }
 
 extern "C" size_t csb200_layernorm_bwd_workspace_bytes(int64_t rows, int64_t channels) {
@@ -333,11 +376,10 @@ extern "C" size_t csb200_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cha
   return (size_t)LN_MAX_GRID * 2 * (size_t)channels * sizeof(float) + 256;  // per-CTA partials
 }
 
-extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const float* gamma,
-                                    const float* stats, void* grad_x, float* grad_gamma,
-                                    float* grad_beta, void* workspace, size_t workspace_bytes,
-                                    int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
-                                    void* stream) {
+static int ln_bwd_dispatch(const void* x, const void* grad_y, const void* grad_res, const float* gamma,
+                           const float* stats, void* grad_x, float* grad_gamma, float* grad_beta,
+                           void* workspace, size_t workspace_bytes, int64_t rows, int64_t channels,
+                           int x_dtype, int gy_dtype, void* stream) {
   if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(gy_dtype))
     return fail(CSB200_ERR_INVALID, "layernorm_bwd: bad size or dtype");
   if (!x || !grad_y || !gamma || !stats || !grad_x || !grad_gamma || !grad_beta || !workspace)
@@ -351,16 +393,34 @@ extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const flo
     CSB200_CUDA(cudaMemsetAsync(grad_beta, 0, channels * sizeof(float), st));
     return CSB200_OK;
   }
-  // grad_x has the type of x
+  // grad_x (and grad_res) have the type of x
   if (x_dtype == CSB200_F32)
     return gy_dtype == CSB200_F32
-               ? ln_bwd_t<float, float, float>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
-                                               partial, rows, channels, st)
-               : ln_bwd_t<float, bf16, float>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
-                                              partial, rows, channels, st);
+               ? ln_bwd_t<float, float, float>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma,
+                                               grad_beta, partial, rows, channels, st)
+               : ln_bwd_t<float, bf16, float>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma,
+                                              grad_beta, partial, rows, channels, st);
   return gy_dtype == CSB200_F32
-             ? ln_bwd_t<bf16, float, bf16>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
+             ? ln_bwd_t<bf16, float, bf16>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma, grad_beta,
                                            partial, rows, channels, st)
-             : ln_bwd_t<bf16, bf16, bf16>(x, grad_y, gamma, stats, grad_x, grad_gamma, grad_beta,
+             : ln_bwd_t<bf16, bf16, bf16>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma, grad_beta,
                                           partial, rows, channels, st);
+}
+
+extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const float* gamma,
+                                    const float* stats, void* grad_x, float* grad_gamma,
+                                    float* grad_beta, void* workspace, size_t workspace_bytes,
+                                    int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
+                                    void* stream) {
+  return ln_bwd_dispatch(x, grad_y, nullptr, gamma, stats, grad_x, grad_gamma, grad_beta, workspace,
+                         workspace_bytes, rows, channels, x_dtype, gy_dtype, stream);
+}
+
+extern "C" int csb200_add_layernorm_bwd(const void* sum, const void* grad_y, const void* grad_sum,
+                                        const float* gamma, const float* stats, void* grad_x,
+                                        float* grad_gamma, float* grad_beta, void* workspace,
+                                        size_t workspace_bytes, int64_t rows, int64_t channels, int x_dtype,
+                                        int gy_dtype, void* stream) {
+  return ln_bwd_dispatch(sum, grad_y, grad_sum, gamma, stats, grad_x, grad_gamma, grad_beta, workspace,
+                         workspace_bytes, rows, channels, x_dtype, gy_dtype, stream);
 }

@@ -176,6 +176,58 @@ class _LayerNormFn(torch.autograd.Function):
         return gx, gw, gb, None, None
 
 
+class _AddLayerNormFn(torch.autograd.Function):
+    """(s, y) = (x + r, LayerNorm(x + r)) in one pass; backward folds the gradient arriving on s into
+    the LayerNorm backward pass (csb200_add_layernorm_fwd / _bwd)."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, r, weight, bias, eps, out_dtype):
+        capi.require_cuda(x, r)
+        x, r = x.contiguous(), r.contiguous()
+        C = x.shape[-1]
+        rows = x.numel() // C
+        w, b = weight.detach().float().contiguous(), bias.detach().float().contiguous()
+        s = torch.empty_like(x)
+        y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
+        stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
+        nbytes = x.numel() * (3 * x.element_size() + y.element_size())
+        with torch.cuda.device(x.device), _span("layernorm_fwd", nbytes):
+            capi.check(capi.lib().csb200_add_layernorm_fwd(
+                _ptr(x), _ptr(r), _ptr(s), _ptr(w), _ptr(b), _ptr(y), _ptr(stats), rows, C, capi.dtype_code(x),
+                capi.dtype_code(y), float(eps), _vp(capi.stream_of(x))), "csb200_add_layernorm_fwd")
+        ctx.save_for_backward(s, w, stats)
+        return s, y
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gs, gy):
+        s, w, stats = ctx.saved_tensors
+        C = s.shape[-1]
+        rows = s.numel() // C
+        if gy is None:  # the normalised branch was unused: only the residual stream carries gradient
+            return gs, gs, None, None, None, None
+        gy = gy.contiguous()
+        gres = None if gs is None else gs.to(s.dtype).contiguous()
+        gx = torch.empty_like(s)
+        gw, gb = torch.empty_like(w), torch.empty_like(w)
+        lib = capi.lib()
+        nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
+        wsp = torch.empty(nws, dtype=torch.uint8, device=s.device)
+        nbytes = s.numel() * ((2 + (gres is not None)) * s.element_size() + gy.element_size())
+        with torch.cuda.device(s.device), _span("layernorm_bwd", nbytes):
+            capi.check(lib.csb200_add_layernorm_bwd(
+                _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(wsp), nws,
+                rows, C, capi.dtype_code(s), capi.dtype_code(gy), _vp(capi.stream_of(s))), "csb200_add_layernorm_bwd")
+        return gx, gx, gw, gb, None, None
+
+
+def add_layer_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
+                   eps: float = 1e-5, out_dtype: Optional[torch.dtype] = None):
+    """Returns (x + residual, LayerNorm(x + residual)); both tensors have the shape of x."""
+    return _AddLayerNormFn.apply(x, residual, weight, bias, eps, out_dtype or x.dtype)
+
+
 def layer_norm_supported(x: torch.Tensor) -> bool:
     return x.is_cuda and x.dtype in (torch.float32, torch.bfloat16) and \
         bool(capi.lib().csb200_layernorm_supported(x.shape[-1], capi.dtype_code(x)))

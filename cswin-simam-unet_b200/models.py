@@ -14,7 +14,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import functional as csbF
-from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_conv, apply_linear, apply_norm,
+from .modules import (CARAFE, CARAFE4, ConvEmbedTokens, CSWinBlock, Merge_Block, SimAM, apply_conv, apply_linear, apply_norm, run_blocks,
                       carafe_upsample, image_as_tokens, tokens_as_image, _side)
 
 
@@ -116,12 +116,10 @@ class CSWinTransformer(nn.Module):
         x = self.pos_drop(apply_norm(stem[2], stem[1](apply_conv(stem[0], x.contiguous(memory_format=torch.channels_last)))))
         skips: List[torch.Tensor] = []
         for blocks, merge in ((self.stage1, self.merge1), (self.stage2, self.merge2), (self.stage3, self.merge3)):
-            for blk in blocks:
-                x = blk(x)
+            x = run_blocks(blocks, x)
             skips.append(self._gate(x))
             x = merge(x)
-        for blk in self.stage4:
-            x = blk(x)
+        x = run_blocks(self.stage4, x)
         return apply_norm(self.norm, x), skips
 
     def forward_up_features(self, x, skips: Sequence[torch.Tensor]):
@@ -130,11 +128,9 @@ class CSWinTransformer(nn.Module):
                 (self.stage_up3, self.upsample3, self.concat_linear3, skips[1]),
                 (self.stage_up2, self.upsample2, self.concat_linear2, skips[0]))
         for blocks, upsample, fuse, skip in plan:
-            for blk in blocks:
-                x = blk(x)
+            x = run_blocks(blocks, x)
             x = apply_linear(fuse, torch.cat([skip, upsample(x)], dim=-1))
-        for blk in self.stage_up1:
-            x = blk(x)
+        x = run_blocks(self.stage_up1, x)
         return apply_norm(self.norm_up, x, feeds_gemm=True)
 
     def up_x4(self, x):

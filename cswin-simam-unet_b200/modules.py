@@ -49,6 +49,34 @@ def apply_norm(norm: nn.Module, x: torch.Tensor, feeds_gemm: bool = False) -> to
     return norm(x)
 
 
+def apply_add_norm(norm: nn.Module, x: torch.Tensor, delta: torch.Tensor, feeds_gemm: bool = False):
+    """(x + delta, norm(x + delta)).  With a plain LayerNorm on a tiled width the residual add rides in
+    the LayerNorm kernel (one pass instead of an add kernel plus a norm kernel, and in backward the
+    residual-stream gradient is summed inside the LayerNorm backward pass)."""
+    if type(norm) is nn.LayerNorm and x.is_cuda and delta.dtype == x.dtype and delta.shape == x.shape \
+            and len(norm.normalized_shape) == 1 and norm.elementwise_affine and norm.bias is not None \
+            and csbF.layer_norm_supported(x):
+        out_dtype = x.dtype
+        if feeds_gemm and torch.is_autocast_enabled("cuda"):
+            out_dtype = torch.get_autocast_dtype("cuda")
+        return csbF.add_layer_norm(x, delta, norm.weight, norm.bias, norm.eps, out_dtype)
+    s = x + delta
+    return s, apply_norm(norm, s, feeds_gemm)
+
+
+def run_blocks(blocks, x: torch.Tensor) -> torch.Tensor:
+    """A stage of CSWinBlocks with every residual add fused into the LayerNorm that follows it: the
+    Mlp branch of block i is added inside norm1 of block i + 1 (only the last add stays a plain add)."""
+    pending = None
+    for blk in blocks:
+        if isinstance(blk, CSWinBlock):
+            x, pending = blk.forward_fused(x, pending)
+        else:
+            x = blk(x if pending is None else x + pending)
+            pending = None
+    return x if pending is None else x + pending
+
+
 def apply_conv(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
     """A plain ``nn.Conv2d`` (groups 1, dilation 1, zero padding) runs cuDNN through csbF.conv2d, which
     takes the bias gradient as one flat column-sum pass; anything else runs the module as given."""
@@ -207,13 +235,24 @@ class CSWinBlock(nn.Module):
             params += [att.get_v.weight, att.get_v.bias]
         return csbF.cross_stripe_attention(qkv, reso, reso, branches, self._scale, params, self.attns[0].engine)
 
-    def forward(self, x):
+    def forward_fused(self, x, pending=None):
+        """The block with its LAST residual add left pending: returns (x', delta) with
+        block(x + pending) == x' + delta, so the caller can fuse `+ delta` into the next pre-norm."""
         B, L, C = x.shape
         if L != self.patches_resolution ** 2:
             raise AssertionError("flatten img_tokens has wrong size")
-        attended = apply_linear(self.proj, self.attend(apply_linear(self.qkv, apply_norm(self.norm1, x, feeds_gemm=True))))
-        x = x + self.drop_path(attended)  # proj_drop exists but is never applied in the reference (C:366-367)
-        return x + self.drop_path(self.mlp(apply_norm(self.norm2, x, feeds_gemm=True)))
+        if pending is None:
+            n1 = apply_norm(self.norm1, x, feeds_gemm=True)
+        else:
+            x, n1 = apply_add_norm(self.norm1, x, pending, feeds_gemm=True)
+        attended = apply_linear(self.proj, self.attend(apply_linear(self.qkv, n1)))
+        # proj_drop exists but is never applied in the reference (C:366-367)
+        x, n2 = apply_add_norm(self.norm2, x, self.drop_path(attended), feeds_gemm=True)
+        return x, self.drop_path(self.mlp(n2))
+
+    def forward(self, x):
+        x, delta = self.forward_fused(x)
+        return x + delta
 
 
 class Merge_Block(nn.Module):

@@ -94,6 +94,19 @@ CSB200_API int csb200_layernorm_bwd(const void* x, const void* grad_y, const flo
                                     float* grad_beta, void* workspace, size_t workspace_bytes,
                                     int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
                                     void* stream);
+/* Residual add fused into the pre-norm that follows it (C:367 -> C:368, C:369 -> the next block's
+ * C:357):  sum_out = x + residual (type of x, written once),  y = LayerNorm(sum_out).
+ * Backward takes the gradient arriving on `sum` from later layers (grad_sum, type of x) and returns
+ *   grad_x = LayerNorm'(sum; grad_y) + grad_sum,  which is the gradient of BOTH x and residual. */
+CSB200_API int csb200_add_layernorm_fwd(const void* x, const void* residual, void* sum_out,
+                                        const float* gamma, const float* beta, void* y, float* stats,
+                                        int64_t rows, int64_t channels, int x_dtype, int y_dtype,
+                                        float eps, void* stream);
+CSB200_API int csb200_add_layernorm_bwd(const void* sum, const void* grad_y, const void* grad_sum,
+                                        const float* gamma, const float* stats, void* grad_x,
+                                        float* grad_gamma, float* grad_beta, void* workspace,
+                                        size_t workspace_bytes, int64_t rows, int64_t channels,
+                                        int x_dtype, int gy_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Column sums of a row-major [rows][cols] matrix (fp32 out) — the bias gradient of the Linear layers

@@ -109,3 +109,53 @@ def test_linear_function_matches_torch(autocast):
     assert rel_err(lin.weight.grad.cpu(), ref.weight.grad.cpu()) < tol
     assert rel_err(lin.bias.grad.cpu(), ref.bias.grad.cpu()) < tol
     assert lin.weight.grad.dtype == torch.float32 and xa.grad.dtype == torch.float32
+
+
+@pytest.mark.parametrize("x_dtype,out_dtype", [(torch.float32, torch.float32), (torch.bfloat16, torch.bfloat16)])
+@pytest.mark.parametrize("shape", [(2, 49, 64), (3, 100, 32), (1, 784, 128), (2, 196, 256), (2, 49, 512)])
+def test_residual_add_fused_into_layernorm(shape, x_dtype, out_dtype):
+    """(s, y) = (x + r, LN(x + r)) and its backward (gradient on s folded into the LN backward pass)
+    against the unfused torch ops in fp64."""
+    torch.manual_seed(sum(shape) + 1)
+    C = shape[-1]
+    x, r = (torch.randn(shape) * 2).to(x_dtype), torch.randn(shape).to(x_dtype)
+    w, b = torch.randn(C) * 0.5 + 1, torch.randn(C) * 0.2
+    gs, gy = torch.randn(shape).to(x_dtype), torch.randn(shape).to(out_dtype)
+    xd, rd = x.cuda().requires_grad_(True), r.cuda().requires_grad_(True)
+    wd, bd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True)
+    if not csbF.layer_norm_supported(xd):
+        pytest.skip("width not tiled for this dtype")
+    s, y = csbF.add_layer_norm(xd, rd, wd, bd, 1e-5, out_dtype)
+    torch.autograd.backward([s, y], [gs.cuda(), gy.cuda()])
+    x64, r64 = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    s64 = (x64 + r64)
+    s_in = s64 if x_dtype == torch.float32 else s64 + (s.detach().double().cpu() - s64.detach())  # LN sees the ROUNDED sum
+    y64 = F.layer_norm(s_in, (C,), w64, b64, 1e-5)
+    torch.autograd.backward([s64, y64], [gs.double(), gy.double()])
+    tol = 1e-5 if x_dtype == torch.float32 else 2 ** -7
+    assert s.dtype == x_dtype and y.dtype == out_dtype
+    assert rel_err(s.float().cpu(), s64.detach()) < tol
+    assert rel_err(y.float().cpu(), y64.detach()) < tol
+    assert rel_err(xd.grad.float().cpu(), x64.grad) < tol and torch.equal(xd.grad, rd.grad)
+    assert rel_err(wd.grad.cpu(), w64.grad) < max(tol, 2e-5)
+    assert rel_err(bd.grad.cpu(), b64.grad) < max(tol, 2e-5)
+
+
+def test_stage_runner_equals_block_by_block(no_tf32):
+    """run_blocks (adds fused into the next pre-norm) == calling the blocks one after another."""
+    torch.manual_seed(5)
+    blocks = torch.nn.ModuleList([modules.CSWinBlock(dim=64, reso=14, num_heads=2, split_size=2) for _ in range(3)]).cuda()
+    x = torch.randn(2, 196, 64, device="cuda")
+    xa, xb = x.clone().requires_grad_(True), x.clone().requires_grad_(True)
+    ya = modules.run_blocks(blocks, xa)
+    ya.square().mean().backward()
+    ga = [p.grad.clone() for p in blocks.parameters()]
+    blocks.zero_grad()
+    yb = xb
+    for blk in blocks:
+        yb = blk(yb)
+    yb.square().mean().backward()
+    assert rel_err(ya, yb) < 1e-5 and rel_err(xa.grad, xb.grad) < 2e-5
+    for g1, p in zip(ga, blocks.parameters()):
+        assert rel_err(g1, p.grad) < 5e-5
