@@ -1,0 +1,63 @@
+#!/usr/bin/env python
+"""One profiled call of each hot kernel, bracketed by cudaProfilerStart/Stop, for
+    ncu --set full --import-source on --clock-control none --profile-from-start off -o <rep> \\
+        python benchmarks/ncu_targets.py attn s3        # or: simam nchw | simam nlc | gelu | layernorm
+Shapes are BASELINE config 3 (512^2, batch 32, bf16) call sites; config 2 for SimAM NCHW."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import cswin_simam_unet_b200 as pkg  # noqa: E402
+from cswin_simam_unet_b200 import functional as csbF  # noqa: E402
+
+STAGES = {"s1": (128, 1, 2, 64), "s2": (64, 2, 4, 128), "s3": (32, 8, 8, 256), "s4": (16, 16, 16, 512)}
+what = sys.argv[1] if len(sys.argv) > 1 else "attn"
+arg = sys.argv[2] if len(sys.argv) > 2 else "s3"
+B = 32
+
+
+def profiled(fn, warm=2):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.start()
+    fn()
+    torch.cuda.synchronize()
+    torch.cuda.profiler.stop()
+
+
+if what == "attn":
+    reso, split, heads, C = STAGES[arg]
+    blk = pkg.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, last_stage=(arg == "s4")).cuda()
+    L = reso * reso
+    # two buffer sets larger than L2 together would be ideal; one call per profile range keeps it simple
+    q = torch.randn(B, L, 3 * C, device="cuda").bfloat16().requires_grad_(True)
+    g = torch.randn(B, L, C, device="cuda").bfloat16()
+    params = [p for a in blk.attns for p in (a.get_v.weight, a.get_v.bias)]
+    profiled(lambda: torch.autograd.grad(blk.attend(q), [q] + params, g))
+elif what == "simam":
+    if arg == "nchw":
+        x = torch.randn(16, 64, 256, 256, device="cuda").bfloat16().requires_grad_(True)
+        profiled(lambda: torch.autograd.grad(pkg.simam(x), [x], torch.ones_like(x)))
+    else:
+        x = torch.randn(32, 16384, 64, device="cuda").bfloat16().requires_grad_(True)
+        profiled(lambda: torch.autograd.grad(pkg.simam(x, layout="NLC"), [x], torch.ones_like(x)))
+elif what == "gelu":
+    x = torch.randn(B, 1024, 256, device="cuda").bfloat16().requires_grad_(True)
+    w = torch.randn(1024, 256, device="cuda").bfloat16().requires_grad_(True)
+    b = torch.randn(1024, device="cuda").bfloat16().requires_grad_(True)
+    profiled(lambda: torch.autograd.grad(csbF._LinearGeluFn.apply(x, w, b, torch.bfloat16), [x, w, b],
+                                         torch.ones(B, 1024, 1024, device="cuda").bfloat16()))
+elif what == "layernorm":
+    x = torch.randn(B, 1024, 256, device="cuda").bfloat16().requires_grad_(True)
+    r = torch.randn(B, 1024, 256, device="cuda").bfloat16().requires_grad_(True)
+    w = torch.ones(256, device="cuda", requires_grad=True)
+    b = torch.zeros(256, device="cuda", requires_grad=True)
+
+    def f():
+        s, y = csbF.add_layer_norm(x, r, w, b, 1e-5, torch.bfloat16)
+        torch.autograd.grad([s, y], [x, r, w, b], [torch.ones_like(s), torch.ones_like(y)])
+    profiled(f)
+print("done", what, arg)

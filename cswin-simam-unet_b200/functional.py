@@ -19,13 +19,16 @@ class KernelTimer:
     Events are recorded on the stream the kernels are launched on."""
 
     def __init__(self):
-        self.spans = []  # (family, start, end, bytes, flops)
+        self.spans = []  # (family, shape tag, start, end, bytes, flops)
 
-    def summary(self):
+    def summary(self, by_shape: bool = False):
+        """Totals per kernel family, or per (family, shape) when ``by_shape`` — the latter is one
+        physical launch configuration, which is what a roofline fraction should be quoted for."""
         torch.cuda.synchronize()
         out = {}
-        for fam, a, b, nbytes, flops in self.spans:
-            r = out.setdefault(fam, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
+        for fam, tag, a, b, nbytes, flops in self.spans:
+            key = f"{fam}|{tag}" if by_shape and tag else fam
+            r = out.setdefault(key, {"calls": 0, "ms": 0.0, "bytes": 0, "flops": 0})
             r["calls"] += 1
             r["ms"] += a.elapsed_time(b)
             r["bytes"] += nbytes
@@ -42,10 +45,10 @@ def set_kernel_timer(t: Optional[KernelTimer]):
 
 
 class _span:
-    __slots__ = ("fam", "nbytes", "flops", "start")
+    __slots__ = ("fam", "nbytes", "flops", "start", "tag")
 
-    def __init__(self, fam, nbytes, flops=0):
-        self.fam, self.nbytes, self.flops = fam, nbytes, flops
+    def __init__(self, fam, nbytes, flops=0, tag=""):
+        self.fam, self.nbytes, self.flops, self.tag = fam, nbytes, flops, tag
 
     def __enter__(self):
         if _timer is not None:
@@ -56,7 +59,7 @@ class _span:
         if _timer is not None:
             end = torch.cuda.Event(enable_timing=True)
             end.record()
-            _timer.spans.append((self.fam, self.start, end, self.nbytes, self.flops))
+            _timer.spans.append((self.fam, self.tag, self.start, end, self.nbytes, self.flops))
         return False
 
 
@@ -549,6 +552,10 @@ def _attn_work(B, L, br: Branch, itemsize, backward):
     return tensors * B * L * br.chans * itemsize, (10 if backward else 4) * N * hd * B * L * br.heads
 
 
+def _attn_tag(B, L, C, branches) -> str:
+    return f"B{B}xL{L}xC{C}xN{branches[0].h_sp * branches[0].w_sp}x{len(branches)}br"
+
+
 _ENGINE = {"auto": capi.ENGINE_AUTO, "simt": capi.ENGINE_SIMT, "tcgen05": capi.ENGINE_TCGEN05}
 
 
@@ -588,7 +595,7 @@ class _CrossStripeFn(torch.autograd.Function):
             io.out, io.lse = _ptr(out, br.chan0).value, lses[i].data_ptr()
             w_ = _attn_work(B, L, br, qkv.element_size(), False)
             nbytes, flops = nbytes + w_[0], flops + w_[1]
-        with torch.cuda.device(qkv.device), _span("attn_fwd", nbytes, flops):
+        with torch.cuda.device(qkv.device), _span("attn_fwd", nbytes, flops, _attn_tag(B, L, C, branches)):
             capi.check(lib.csb200_cross_stripe_attn_fwd(n, descs, ios, st), "csb200_cross_stripe_attn_fwd")
         ctx.save_for_backward(qkv, out, *lses, *ws)
         ctx.cfg = (H, W, branches, scale, engine)
@@ -634,7 +641,7 @@ class _CrossStripeFn(torch.autograd.Function):
             grads += [gw, gb]
             w_ = _attn_work(B, L, br, qkv.element_size(), True)
             nbytes, flops = nbytes + w_[0], flops + w_[1]
-        with torch.cuda.device(qkv.device), _span("attn_bwd", nbytes, flops):
+        with torch.cuda.device(qkv.device), _span("attn_bwd", nbytes, flops, _attn_tag(B, L, C, branches)):
             capi.check(lib.csb200_cross_stripe_attn_bwd(n, descs, ios, st), "csb200_cross_stripe_attn_bwd")
         return (gqkv, None, None, None, None, None, *grads)
 

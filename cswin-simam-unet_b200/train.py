@@ -83,17 +83,66 @@ class TrainStep:
             probs = self.model(images)
         return bce_from_logits_as_probabilities(probs, masks)
 
-    def __call__(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
-        if self.cuda_graph:
-            return self._graph_step(images, masks)
-        return self._eager_step(images, masks)
+    def __call__(self, images: torch.Tensor = None, masks: torch.Tensor = None) -> torch.Tensor:
+        """One step on (images, masks); with no arguments, on the batch staged by ``prefetch``."""
+        slot = None
+        if images is None:
+            images, masks, slot = self._take_staged()
+        loss = self._graph_step(images, masks, slot) if self.cuda_graph else self._eager_step(images, masks)
+        if slot is not None and not self.cuda_graph:
+            self._mark_consumed(slot)  # eager: the staged tensors are read until the end of the step
+        return loss
+
+    # ---- input pipeline: host -> device copy of the NEXT batch under the current step ------------
+    def prefetch(self, images: torch.Tensor, masks: torch.Tensor) -> None:
+        """Start the host->device copy of the next batch (pinned host tensors) on a side stream; the
+        following ``step()`` call (no arguments) consumes it.  The copy engine works while the SMs run
+        the current step, which is how a training loop with a data loader behaves."""
+        dev = next(self.model.parameters()).device
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(device=dev)
+            self._staged = None
+            self._stage_bufs = [None, None]
+            self._stage_idx = 0
+            self._consumed = [None, None]
+        i = self._stage_idx = self._stage_idx ^ 1
+        cs = self._copy_stream
+        # two staging pairs alternate; overwriting pair i only has to wait for the step that last READ it
+        # (not for the step running now, which reads the other pair): that is the whole overlap
+        if self._consumed[i] is not None:
+            cs.wait_event(self._consumed[i])
+        with torch.cuda.stream(cs):
+            if self._stage_bufs[i] is None:
+                self._stage_bufs[i] = (torch.empty(images.shape, dtype=images.dtype, device=dev),
+                                       torch.empty(masks.shape, dtype=masks.dtype, device=dev))
+            x, y = self._stage_bufs[i]
+            x.copy_(images, non_blocking=True)
+            y.copy_(masks, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(cs)
+        self._staged = (x, y, ev, i)
+
+    def _take_staged(self):
+        if getattr(self, "_staged", None) is None:
+            raise RuntimeError("step() without arguments needs a batch staged by prefetch()")
+        x, y, ev, slot = self._staged
+        self._staged = None
+        torch.cuda.current_stream(x.device).wait_event(ev)
+        return x, y, slot
+
+    def _mark_consumed(self, slot):
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream())
+        self._consumed[slot] = ev
 
     # ---- CUDA-graph path -----------------------------------------------------------------------
-    def _graph_step(self, images, masks):
+    def _graph_step(self, images, masks, slot=None):
         if self._graph is None:
             self._capture(images, masks)
         self._x.copy_(images, non_blocking=True)
         self._y.copy_(masks, non_blocking=True)
+        if slot is not None:
+            self._mark_consumed(slot)  # the graph reads its own static copies from here on
         self._graph.replay()
         if self._graph_opt is not None:  # data parallel: gradients are averaged between the two graphs
             self.reducer.finish_step()
