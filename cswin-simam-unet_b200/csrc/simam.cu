@@ -595,10 +595,13 @@ __global__ void __launch_bounds__(THREADS)
 // traffic remains 1 read + 1 write.
 // ------------------------------------------------------------------------------------------------
 template <typename T, int CWV, int CLUSTER>
-__global__ void __launch_bounds__(256, 3)
+__global__ void __launch_bounds__(256, 2)
     simam_nlc_fwd_2pass(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats, int L,
                         int C, int slabs, int ngroups, float e_lambda) {
   constexpr int VE = Vec16<T>::N, CW = CWV * VE, THREADS = 256, RPI = THREADS / CWV, WARPS = THREADS / 32;
+  // 16-byte loads in flight per thread: the sweeps are latency-bound (a CTA streams only ~256 KB),
+  // 4 in flight left the kernel at 42 % of HBM bandwidth
+  constexpr int UF = 4;  // x 2: double-buffered
   __shared__ float s_red[WARPS * 2 * CW];
   __shared__ float s_part[2 * CW];
   __shared__ float s_fin[2 * CW];
@@ -617,13 +620,19 @@ __global__ void __launch_bounds__(256, 3)
   float acc[2][VE];
 #pragma unroll
   for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
-  for (int r = r_begin; r < r_end; r += 4 * RPI) {
-    uint4 u[4];
+  // software-pipelined: the loads of step i+1 are in flight while step i is reduced (all CTAs start
+  // together, so without this every warp waits for DRAM and then computes, in lock-step)
+  auto load_rows = [&](int r, uint4 (&u)[UF]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
+    for (int i = 0; i < UF; ++i)
       u[i] = (r + i * RPI < r_end) ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
+  };
+  uint4 u[UF], un[UF];
+  load_rows(r_begin, u);
+  for (int r = r_begin; r < r_end; r += UF * RPI) {
+    load_rows(r + UF * RPI, un);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < UF; ++i) {
       if (r + i * RPI < r_end) {
         float f[VE];
         unpack<T>(u[i], f);
@@ -635,6 +644,8 @@ __global__ void __launch_bounds__(256, 3)
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < UF; ++i) u[i] = un[i];
   }
   slab_reduce<VE, CWV, THREADS, CLUSTER, 2>(acc, s_red, s_part, s_fin);
   float mean[VE], k[VE];  // full mean; 1/(8v) (bf16) or 1/(4v) (fp32)
@@ -657,13 +668,11 @@ __global__ void __launch_bounds__(256, 3)
       stats[2 * (p0 + e) + 1] = acc[1][e];
     }
   }
-  for (int r = r_begin; r < r_end; r += 4 * RPI) {
-    uint4 u[4];
+  load_rows(r_begin, u);
+  for (int r = r_begin; r < r_end; r += UF * RPI) {
+    load_rows(r + UF * RPI, un);
 #pragma unroll
-    for (int i = 0; i < 4; ++i)
-      u[i] = (r + i * RPI < r_end) ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < UF; ++i) {
       if (r + i * RPI < r_end) {
         float f[VE];
         unpack<T>(u[i], f);
@@ -675,6 +684,8 @@ __global__ void __launch_bounds__(256, 3)
         st_stream(yp + (int64_t)(r + i * RPI) * cvec, pack<T>(f));
       }
     }
+#pragma unroll
+    for (int i = 0; i < UF; ++i) u[i] = un[i];
   }
   if constexpr (CLUSTER > 1) cluster_sync_all();  // peers have finished reading s_part
   }
@@ -686,6 +697,7 @@ __global__ void __launch_bounds__(256, 2)
                         const float* __restrict__ stats, T* __restrict__ gx, int L, int C, int slabs,
                         int ngroups) {
   constexpr int VE = Vec16<T>::N, CW = CWV * VE, THREADS = 256, RPI = THREADS / CWV, WARPS = THREADS / 32;
+  constexpr int UB = 2;  // rows per thread per step; double-buffered: 4 x UB 16-byte loads in flight
   __shared__ float s_red[WARPS * 2 * CW];
   __shared__ float s_part[2 * CW];
   __shared__ float s_fin[2 * CW];
@@ -732,16 +744,20 @@ __global__ void __launch_bounds__(256, 2)
   float acc[2][VE];
 #pragma unroll
   for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
-  for (int r = r_begin; r < r_end; r += 2 * RPI) {
-    uint4 ux[2], ug[2];
+  auto load_rows = [&](int r, uint4 (&ux)[UB], uint4 (&ug)[UB]) {
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < UB; ++i) {
       const bool ok = r + i * RPI < r_end;
       ux[i] = ok ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
       ug[i] = ok ? ld_stream(gp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
     }
+  };
+  uint4 ux[UB], ug[UB], nx[UB], ng[UB];
+  load_rows(r_begin, ux, ug);
+  for (int r = r_begin; r < r_end; r += UB * RPI) {
+    load_rows(r + UB * RPI, nx, ng);  // next step's rows in flight while this one is reduced
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < UB; ++i) {
       if (r + i * RPI < r_end) {
         float fx[VE], fg[VE];
         unpack<T>(ux[i], fx);
@@ -755,6 +771,11 @@ __global__ void __launch_bounds__(256, 2)
         }
       }
     }
+#pragma unroll
+    for (int i = 0; i < UB; ++i) {
+      ux[i] = nx[i];
+      ug[i] = ng[i];
+    }
   }
   slab_reduce<VE, CWV, THREADS, CLUSTER, 2>(acc, s_red, s_part, s_fin);
   float k1[VE], k2[VE], c2[VE];
@@ -766,16 +787,11 @@ __global__ void __launch_bounds__(256, 2)
     k1[e] = 0.5f * inv4v[e];  // 2 (a inv4v - c1) = a4 k1 - k2
     k2[e] = 2.f * c1;
   }
-  for (int r = r_begin; r < r_end; r += 2 * RPI) {
-    uint4 ux[2], ug[2];
+  load_rows(r_begin, ux, ug);
+  for (int r = r_begin; r < r_end; r += UB * RPI) {
+    load_rows(r + UB * RPI, nx, ng);
 #pragma unroll
-    for (int i = 0; i < 2; ++i) {
-      const bool ok = r + i * RPI < r_end;
-      ux[i] = ok ? ld_stream(xp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
-      ug[i] = ok ? ld_stream(gp + (int64_t)(r + i * RPI) * cvec) : make_uint4(0, 0, 0, 0);
-    }
-#pragma unroll
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < UB; ++i) {
       if (r + i * RPI < r_end) {
         float fx[VE], fg[VE];
         unpack<T>(ux[i], fx);
@@ -788,6 +804,11 @@ __global__ void __launch_bounds__(256, 2)
         }
         st_stream(op + (int64_t)(r + i * RPI) * cvec, pack<T>(fx));
       }
+    }
+#pragma unroll
+    for (int i = 0; i < UB; ++i) {
+      ux[i] = nx[i];
+      ug[i] = ng[i];
     }
   }
   if constexpr (CLUSTER > 1) cluster_sync_all();

@@ -319,7 +319,7 @@ class _LinearFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.mm(g2, wc).reshape(xc.shape).to(x_dtype)
         if ctx.needs_input_grad[1]:
-            gw = torch.mm(g2.t(), x2).to(w_dtype)
+            gw = _wgrad(g2, x2, w_dtype)
         if b_dtype is not None and ctx.needs_input_grad[2]:
             gb = _bias_grad(g2, n).to(b_dtype)
         return gx, gw, gb, None
@@ -333,6 +333,14 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) 
     if dt not in (torch.float32, torch.bfloat16):
         return torch.nn.functional.linear(x, weight, bias)
     return _LinearFn.apply(x, weight, bias, dt)
+
+
+def _wgrad(g2: torch.Tensor, x2: torch.Tensor, w_dtype: torch.dtype) -> torch.Tensor:
+    """grad_W = g^T x with the output written in the master-weight dtype by the GEMM itself (fp32
+    accumulators stored unrounded; no bf16 -> fp32 cast kernel per layer)."""
+    if g2.is_cuda and g2.dtype == torch.bfloat16 and w_dtype == torch.float32:
+        return torch.mm(g2.t(), x2, out_dtype=torch.float32)
+    return torch.mm(g2.t(), x2).to(w_dtype)
 
 
 def _bias_grad(g2: torch.Tensor, n: int) -> torch.Tensor:
@@ -387,7 +395,7 @@ class _LinearGeluFn(torch.autograd.Function):
         if ctx.needs_input_grad[0]:
             gx = torch.mm(dh, wc).reshape(xc.shape).to(x_dtype)
         if ctx.needs_input_grad[1]:
-            gw = torch.mm(dh.t(), x2).to(w_dtype)
+            gw = _wgrad(dh, x2, w_dtype)
         return gx, gw, (gb.to(b_dtype) if ctx.needs_input_grad[2] else None), None
 
 
