@@ -41,7 +41,7 @@ EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_coun
            "csb200_simam_bwd", "csb200_layernorm_supported", "csb200_layernorm_fwd",
            "csb200_layernorm_bwd_workspace_bytes", "csb200_layernorm_bwd", "csb200_add_layernorm_fwd",
            "csb200_add_layernorm_bwd", "csb200_colsum_supported",
-           "csb200_colsum_workspace_bytes", "csb200_colsum", "csb200_gelu_supported", "csb200_gelu_fwd",
+           "csb200_colsum_workspace_bytes", "csb200_colsum", "csb200_add_row_bias", "csb200_gelu_supported", "csb200_gelu_fwd",
            "csb200_gelu_bwd_workspace_bytes", "csb200_gelu_bwd", "csb200_carafe_supported", "csb200_carafe_fwd",
            "csb200_carafe_bwd", "csb200_stripe_attn_engine", "csb200_stripe_attn_fwd",
            "csb200_stripe_attn_bwd_workspace_bytes", "csb200_stripe_attn_bwd", "csb200_cross_stripe_attn_fwd",
@@ -84,6 +84,8 @@ def lib() -> ctypes.CDLL:
         L.csb200_colsum_workspace_bytes.restype = ctypes.c_size_t
         L.csb200_colsum.argtypes = [vp, vp, vp, ctypes.c_size_t, i64, i64, ctypes.c_int, vp]
         L.csb200_colsum.restype = ctypes.c_int
+        L.csb200_add_row_bias.argtypes = [vp, vp, vp, i64, i64, ctypes.c_int, vp]
+        L.csb200_add_row_bias.restype = ctypes.c_int
         L.csb200_gelu_supported.argtypes = [i64, ctypes.c_int]
         L.csb200_gelu_supported.restype = ctypes.c_int
         L.csb200_gelu_fwd.argtypes = [vp, vp, i64, i64, ctypes.c_int, vp]

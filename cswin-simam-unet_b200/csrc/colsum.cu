@@ -66,6 +66,59 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) out[i] = a;
 }
 
+// y[r][c] = x[r][c] + bias[c] over a flat stream of 16-byte vectors: the same "one fixed column vector
+// per thread" layout as colsum_partial, so the bias vector is loaded once and stays in registers.
+// Replaces the broadcasting add_ that follows every cuDNN convolution on a channels-last tensor
+// (ATen runs it through the non-vectorised elementwise_kernel: 0.17 ms for the 144-channel CARAFE
+// encoder output at 512^2, against 0.05 ms of HBM time).
+template <typename T>
+__global__ void __launch_bounds__(256)
+    add_row_bias_kernel(const T* __restrict__ x, const float* __restrict__ bias, T* __restrict__ y,
+                        int64_t nvec_total, int cvn) {
+  constexpr int VE = Vec16<T>::N;
+  const int tpb = blockDim.x;  // multiple of cvn
+  float b[VE];
+  const int cv = threadIdx.x % cvn;
+#pragma unroll
+  for (int e = 0; e < VE; ++e) b[e] = __ldg(bias + cv * VE + e);
+  const uint4* xv = reinterpret_cast<const uint4*>(x);
+  uint4* yv = reinterpret_cast<uint4*>(y);
+  const int64_t stride = (int64_t)gridDim.x * tpb;
+  int64_t f = (int64_t)blockIdx.x * tpb + threadIdx.x;
+  for (; f + 3 * stride < nvec_total; f += 4 * stride) {
+    uint4 u[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) u[i] = ld_stream(xv + f + i * stride);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t[VE];
+      unpack<T>(u[i], t);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) t[e] += b[e];
+      yv[f + i * stride] = pack<T>(t);
+    }
+  }
+  for (; f < nvec_total; f += stride) {
+    float t[VE];
+    unpack<T>(ld_stream(xv + f), t);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) t[e] += b[e];
+    yv[f] = pack<T>(t);
+  }
+}
+
+template <typename T>
+int add_row_bias_t(const void* x, const float* bias, void* y, int64_t rows, int64_t cols, cudaStream_t st) {
+  constexpr int VE = Vec16<T>::N;
+  const int cvn = (int)(cols / VE);
+  const int tpb = 256 / cvn * cvn;
+  const int64_t nvec = rows * cvn;
+  int64_t grid = (nvec + (int64_t)tpb * 8 - 1) / ((int64_t)tpb * 8);
+  grid = grid < 1 ? 1 : (grid > CS_MAX_GRID * 4 ? CS_MAX_GRID * 4 : grid);
+  add_row_bias_kernel<T><<<(int)grid, tpb, 0, st>>>(static_cast<const T*>(x), bias, static_cast<T*>(y), nvec, cvn);
+  return check_launch("add_row_bias");
+}
+
 template <typename T>
 int colsum_t(const void* x, float* out, float* partial, int64_t rows, int64_t cols, cudaStream_t st) {
   constexpr int VE = Vec16<T>::N;
@@ -111,4 +164,17 @@ extern "C" int csb200_colsum(const void* x, float* out, void* workspace, size_t 
   float* partial = static_cast<float*>(workspace);
   return dtype == CSB200_F32 ? colsum_t<float>(x, out, partial, rows, cols, st)
                              : colsum_t<__nv_bfloat16>(x, out, partial, rows, cols, st);
+}
+
+extern "C" int csb200_add_row_bias(const void* x, const float* bias, void* y, int64_t rows, int64_t cols,
+                                   int dtype, void* stream) {
+  if (rows < 0 || !csb200_colsum_supported(cols, dtype))
+    return fail(CSB200_ERR_UNSUPPORTED, "add_row_bias: cols=%lld dtype=%d is not tiled", (long long)cols, dtype);
+  if (rows == 0) return CSB200_OK;
+  if (!x || !bias || !y) return fail(CSB200_ERR_INVALID, "add_row_bias: null pointer");
+  if (((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) != 0)
+    return fail(CSB200_ERR_INVALID, "add_row_bias: tensors must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  return dtype == CSB200_F32 ? add_row_bias_t<float>(x, bias, y, rows, cols, st)
+                             : add_row_bias_t<__nv_bfloat16>(x, bias, y, rows, cols, st);
 }

@@ -345,8 +345,15 @@ def _wgrad(g2: torch.Tensor, x2: torch.Tensor, w_dtype: torch.dtype) -> torch.Te
 
 def _bias_grad(g2: torch.Tensor, n: int) -> torch.Tensor:
     """fp32 column sums of a (rows, n) gradient: csb200_colsum when the width tiles, else ATen."""
-    if g2.is_contiguous() and capi.lib().csb200_colsum_supported(n, capi.dtype_code(g2)) and g2.data_ptr() % 16 == 0:
-        return column_sum(g2)
+    if g2.is_contiguous() and g2.data_ptr() % 16 == 0:
+        code, rows = capi.dtype_code(g2), g2.shape[0]
+        if capi.lib().csb200_colsum_supported(n, code):
+            return column_sum(g2)
+        # widths that are not a multiple of the 16-byte vector (1 logit channel, 36 CARAFE taps): k rows
+        # side by side form one row of k*n columns; fold the k column groups afterwards
+        for k in (2, 4, 8):
+            if rows % k == 0 and capi.lib().csb200_colsum_supported(n * k, code):
+                return column_sum(g2.view(rows // k, n * k)).view(k, n).sum(0)
     return g2.sum(0, dtype=torch.float32)
 
 
@@ -424,7 +431,10 @@ class _Conv2dFn(torch.autograd.Function):
         wc, bc = cast_param(weight, compute_dtype), cast_param(bias, compute_dtype)
         ctx.save_for_backward(xc, wc)
         ctx.cfg = (stride, padding, x.dtype, weight.dtype, None if bias is None else bias.dtype)
-        return torch.nn.functional.conv2d(xc, wc, bc, stride, padding)
+        if bias is None:
+            return torch.nn.functional.conv2d(xc, wc, None, stride, padding)
+        y = torch.nn.functional.conv2d(xc, wc, None, stride, padding)
+        return add_row_bias(y, bias, inplace=True)
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
@@ -460,13 +470,31 @@ def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], 
     return _Conv2dFn.apply(x, weight, bias, pair(stride), pair(padding), dt)
 
 
+def add_row_bias(x: torch.Tensor, bias: torch.Tensor, inplace: bool = False) -> torch.Tensor:
+    """x + bias[None, :, None, None] for a (B, C, H, W) tensor.  Channels-last tensors of a tiled width
+    take one flat csb200 pass (cuDNN leaves the bias of a convolution to a broadcasting add_ that ATen
+    runs through its non-vectorised elementwise kernel); everything else takes the ATen add."""
+    B, C, H, W = x.shape
+    if x.is_cuda and x.is_contiguous(memory_format=torch.channels_last) and not x.is_contiguous() \
+            and x.dtype in (torch.float32, torch.bfloat16) and x.data_ptr() % 16 == 0 \
+            and capi.lib().csb200_colsum_supported(C, capi.dtype_code(x)):
+        y = x if inplace else torch.empty_like(x)  # preserves the channels-last strides
+        b32 = bias.detach().float().contiguous()
+        with torch.cuda.device(x.device), _span("row_bias", 2 * x.numel() * x.element_size()):
+            capi.check(capi.lib().csb200_add_row_bias(_ptr(x), _ptr(b32), _ptr(y), B * H * W, C, capi.dtype_code(x),
+                                                      _vp(capi.stream_of(x))), "csb200_add_row_bias")
+        return y
+    b = bias.to(x.dtype).view(1, -1, 1, 1)
+    return x.add_(b) if inplace else x + b
+
+
 class _ChannelBiasFn(torch.autograd.Function):
     """x + bias[None, :, None, None] whose bias gradient is a csb200 column sum."""
 
     @staticmethod
     def forward(ctx, x, bias):
         ctx.b_dtype = bias.dtype
-        return x + bias.to(x.dtype).view(1, -1, 1, 1)
+        return add_row_bias(x, bias)
 
     @staticmethod
     def backward(ctx, g):

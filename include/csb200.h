@@ -117,6 +117,10 @@ CSB200_API int csb200_colsum_supported(int64_t cols, int dtype);
 CSB200_API size_t csb200_colsum_workspace_bytes(int64_t cols);
 CSB200_API int csb200_colsum(const void* x, float* out, void* workspace, size_t workspace_bytes,
                              int64_t rows, int64_t cols, int dtype, void* stream);
+/* y[r][c] = x[r][c] + bias[c] (y may alias x): the bias add of a convolution on a channels-last tensor
+ * (rows = B*H*W, cols = channels), which cuDNN leaves to a broadcasting add_.  Same tiling rule. */
+CSB200_API int csb200_add_row_bias(const void* x, const float* bias, void* y, int64_t rows, int64_t cols,
+                                   int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * GELU of the Mlp hidden layer (Mlp.forward C:188-196, act_layer() = nn.GELU in its exact erf form)
