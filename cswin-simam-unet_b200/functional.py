@@ -454,8 +454,13 @@ class _Conv2dFn(torch.autograd.Function):
 def channel_sum(g: torch.Tensor) -> torch.Tensor:
     """fp32 sum over (B, H, W) of a (B, C, H, W) tensor; one flat csb200 pass when it is channels-last."""
     B, C, H, W = g.shape
-    if g.is_contiguous(memory_format=torch.channels_last) and g.dtype in (torch.float32, torch.bfloat16):
-        return _bias_grad(g.permute(0, 2, 3, 1).reshape(B * H * W, C), C)
+    if g.dtype in (torch.float32, torch.bfloat16) and g.is_cuda:
+        if not g.is_contiguous(memory_format=torch.channels_last) and g.stride(1) == 1:
+            # a channel slice of a wider channels-last tensor (the backward of the decoder's torch.cat,
+            # C:657): one compacting copy + a flat column sum beats ATen's strided reduction 5x
+            g = g.contiguous(memory_format=torch.channels_last)
+        if g.is_contiguous(memory_format=torch.channels_last):
+            return _bias_grad(g.permute(0, 2, 3, 1).reshape(B * H * W, C), C)
     return g.sum((0, 2, 3), dtype=torch.float32)
 
 
