@@ -126,7 +126,12 @@ template <int NK>
 struct Cfg;
 template <>
 struct Cfg<128> {
-  static constexpr int NWG = 3, KS = 5, VS = 10, QS = 5;
+#ifndef CSB_KS128
+#define CSB_KS128 5
+#define CSB_VS128 10
+#define CSB_QS128 5
+#endif
+  static constexpr int NWG = 3, KS = CSB_KS128, VS = CSB_VS128, QS = CSB_QS128;
 };
 template <>
 struct Cfg<256> {

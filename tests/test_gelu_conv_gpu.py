@@ -114,3 +114,52 @@ def test_parameter_shadows_follow_the_optimizer_and_are_never_stale():
     with torch.no_grad():
         lin.weight.mul_(2.0)
     assert csbF.cast_param(lin.weight, torch.bfloat16) is not shadows[0]
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("C", [16, 64, 144, 36, 1])
+def test_row_bias_and_bias_gradient_on_channels_last(C, dtype):
+    """x + bias[None, :, None, None] through csb200_add_row_bias (tiled widths) or ATen, and the bias
+    gradient through csb200_colsum — directly, by row folding (36, 1) or after compaction (a slice)."""
+    torch.manual_seed(C)
+    x = torch.randn(3, C, 20, 24, device="cuda").to(dtype).contiguous(memory_format=torch.channels_last)
+    b = torch.randn(C, device="cuda", requires_grad=True)
+    xa = x.clone().requires_grad_(True)
+    y = csbF.add_channel_bias(xa, b)
+    want = x.double() + b.detach().double().view(1, -1, 1, 1)
+    assert rel_err(y.double(), want) < (1e-6 if dtype == torch.float32 else 2 ** -8)
+    g = torch.randn_like(y)
+    y.backward(g)
+    assert torch.equal(xa.grad, g)
+    assert rel_err(b.grad, g.double().sum((0, 2, 3))) < 2e-5
+    # a channel slice of a wider channels-last gradient (what torch.cat's backward hands over)
+    wide = torch.randn(3, 20, 24, 2 * C + 8, device="cuda").to(dtype).permute(0, 3, 1, 2)
+    sl = wide[:, 8:8 + C]
+    assert rel_err(csbF.channel_sum(sl), sl.double().sum((0, 2, 3))) < 2e-5
+
+
+def test_prefetched_steps_equal_direct_steps():
+    """TrainStep.prefetch + step() (H2D on a side stream under the previous step) == step(x, y)."""
+    import copy
+    torch.manual_seed(0)
+    net_a = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], simam=True).cuda()
+    net_b = copy.deepcopy(net_a)
+    batches = [pkg.synthetic_batch(2, 64, "cpu", seed=s, pin=True) for s in range(4)]
+    losses = {}
+    for name, net in (("direct", net_a), ("prefetch", net_b)):
+        step = pkg.TrainStep(net, torch.optim.AdamW(net.parameters(), lr=1e-3), precision="fp32")
+        out = []
+        if name == "prefetch":
+            step.prefetch(*batches[0])
+        for i in range(4):
+            if name == "direct":
+                out.append(step(batches[i][0].cuda(), batches[i][1].cuda()).item())
+            else:
+                loss = step()
+                if i + 1 < 4:
+                    step.prefetch(*batches[i + 1])
+                out.append(loss.item())
+        losses[name] = out
+    assert losses["direct"] == losses["prefetch"], losses
+    with pytest.raises(RuntimeError):
+        pkg.TrainStep(net_a, torch.optim.AdamW(net_a.parameters()), precision="fp32")()
