@@ -66,6 +66,46 @@ __device__ __forceinline__ float simam_fwd_fast(float x, float mean, float inv8v
   return fmaf(hx, th, hx);
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2: two fp32 lanes per issue slot) ------------------------------
+// The bf16 backward is bound by instruction issue, not by HBM (~36 slots per element over two sweeps).
+// A 32-bit word of the input holds two bf16 values: (w << 16, w & 0xffff0000) IS the pair of fp32
+// values, so the whole per-element chain runs on pairs and only the two tanh stay scalar.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_make(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_splat(float v) { return f2_make(v, v); }
+__device__ __forceinline__ void f2_split(f2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_from_bf16x2(uint32_t w) {
+  return f2_make(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_tanh(f2_t a) {
+  float lo, hi;
+  f2_split(a, lo, hi);
+  asm("tanh.approx.f32 %0, %0;" : "+f"(lo));
+  asm("tanh.approx.f32 %0, %0;" : "+f"(hi));
+  return f2_make(lo, hi);
+}
+
 // ------------------------------------------------------------------------------------------------
 // block / cluster reduction of NV scalars held by every thread (NCHW: one plane per CTA/cluster)
 // ------------------------------------------------------------------------------------------------
@@ -1127,6 +1167,8 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
     const float dmean = __ldg(stats + 2 * plane), v = __ldg(stats + 2 * plane + 1);
     const float inv4v = 1.f / (4.f * v), inv8v = 0.5f * inv4v;
     float pivot = 0.f, mean = 0.f, r1 = 0.f, r2 = 0.f;
+    f2_t r1p = f2_splat(0.f), r2p = f2_splat(0.f), nmean2 = f2_splat(0.f);
+    const f2_t inv8v2 = f2_splat(inv8v), quarter2 = f2_splat(0.25f), mone2 = f2_splat(-1.f);
     for (int c = 0; c < chunks; ++c, ++it) {
       const int s = it % ST_STAGES;
       st_mbar_wait(&full[s], (it / ST_STAGES) & 1);
@@ -1135,9 +1177,25 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
       if (c == 0) {
         pivot = to_f32(*reinterpret_cast<const T*>(vx));
         mean = pivot + dmean;
+        nmean2 = f2_splat(-mean);
       }
 #pragma unroll
       for (int i = 0; i < HALF / 16 / ST_CONSUMERS; ++i) {
+        if constexpr (sizeof(T) == 2) {
+          // pairs: -4a = g x (tanh^2 - 1); the sign is undone when the sums are finalised
+          const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
+          const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
+            const f2_t t = f2_add(x2, nmean2), dd = f2_mul(t, t);
+            const f2_t th = f2_tanh(f2_fma(dd, inv8v2, quarter2));
+            const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));
+            r1p = f2_fma(na4, dd, r1p);
+            r2p = f2_fma(na4, t, r2p);
+          }
+          continue;
+        }
         float fx[VE], fg[VE];
         unpack<T>(vx[threadIdx.x + i * ST_CONSUMERS], fx);
         unpack<T>(vg[threadIdx.x + i * ST_CONSUMERS], fg);
@@ -1162,6 +1220,13 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
       __syncwarp();
       if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
     }
+    if constexpr (sizeof(T) == 2) {
+      float a, b;
+      f2_split(r1p, a, b);
+      r1 = -(a + b);  // the pairs accumulate -4a
+      f2_split(r2p, a, b);
+      r2 = -(a + b);
+    }
     r1 = warp_sum(r1);
     r2 = warp_sum(r2);
     if (lane == 0) {
@@ -1181,6 +1246,7 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
     const float c1 = r1 * inv4v / (v * (S - 1.f));  // R1 / (4 v^2 n)
     const float c2 = 2.f / S * r2 * inv4v;          // (2/HW) R2
     const float k1 = 0.5f * inv4v, k2 = 2.f * c1;   // 2 (a inv4v - c1) = a4 k1 - k2
+    const f2_t half2 = f2_splat(0.5f), nc2_2 = f2_splat(-c2), nk1_2 = f2_splat(-k1), nk2_2 = f2_splat(-k2);
     uint4* dst = reinterpret_cast<uint4*>(gx) + plane * (plane_bytes / 16);
     for (int c = 0; c < chunks; ++c, ++it) {
       const int s = it % ST_STAGES;
@@ -1189,6 +1255,27 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
       const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
 #pragma unroll
       for (int i = 0; i < HALF / 16 / ST_CONSUMERS; ++i) {
+        if constexpr (sizeof(T) == 2) {
+          // grad_x = 0.5 g (1 + tanh) + t (4a k1 - k2) - c2, on pairs; -4a as in sweep 1, so k1 enters negated
+          const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
+          const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
+            const f2_t t = f2_add(x2, nmean2), dd = f2_mul(t, t);
+            const f2_t th = f2_tanh(f2_fma(dd, inv8v2, quarter2));
+            const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));
+            const f2_t hg = f2_mul(g2, half2);
+            const f2_t gs = f2_fma(hg, th, f2_add(hg, nc2_2));              // 0.5 g (1 + tanh) - c2
+            const f2_t r = f2_fma(t, f2_fma(na4, nk1_2, nk2_2), gs);
+            float lo, hi;
+            f2_split(r, lo, hi);
+            o[q] = pack_bf16x2(lo, hi);
+          }
+          st_stream(dst + (int64_t)c * (HALF / 16) + threadIdx.x + i * ST_CONSUMERS, make_uint4(o[0], o[1], o[2], o[3]));
+          continue;
+        }
         float fx[VE], fg[VE];
         unpack<T>(vx[threadIdx.x + i * ST_CONSUMERS], fx);
         unpack<T>(vg[threadIdx.x + i * ST_CONSUMERS], fg);
