@@ -121,6 +121,38 @@ __device__ __forceinline__ uint4 pack<__nv_bfloat16>(const float (&f)[8]) {
                     pack_bf16x2(f[6], f[7]));
 }
 
+// ---- packed fp32x2 arithmetic (FFMA2: two fp32 lanes per issue slot, sm_100) ----------------------
+// For kernels bound by instruction issue rather than by HBM: a 32-bit word holding two bf16 values IS
+// a pair of fp32 values after (w << 16, w & 0xffff0000), so whole per-element chains run on pairs.
+typedef unsigned long long f2_t;
+__device__ __forceinline__ f2_t f2_make(float lo, float hi) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ f2_t f2_splat(float v) { return f2_make(v, v); }
+__device__ __forceinline__ void f2_split(f2_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f2_t f2_from_bf16x2(uint32_t w) {
+  return f2_make(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
+}
+__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
+  f2_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
+  f2_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
+  f2_t d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+  return d;
+}
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -30,38 +30,78 @@ struct Gelu<float> {
     return g * fmaf(x, pdf, cdf);
   }
 };
-// erf(z) = sign(z) (1 - poly(t) e^{-z^2}), t = 1 / (1 + p |z|), with e^{-z^2} = e^{-x^2 / 2}
-__device__ __forceinline__ void erf_and_gauss(float x, float& erf_z, float& gauss) {
-  const float z = fabsf(x) * kSqrtHalf;
-  float e;
-  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170368f));  // e^{-x^2/2}
-  float t;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.f)));
-  float p = fmaf(1.061405429f, t, -1.453152027f);
-  p = fmaf(p, t, 1.421413741f);
-  p = fmaf(p, t, -0.284496736f);
-  p = fmaf(p, t, 0.254829592f);
-  p *= t;
-  erf_z = copysignf(fmaf(-p, e, 1.f), x);
-  gauss = e;
-}
-template <>
-struct Gelu<__nv_bfloat16> {
-  static __device__ __forceinline__ float fwd(float x) {
-    float er, e;
-    erf_and_gauss(x, er, e);
-    return 0.5f * x * (1.f + er);
-  }
-  static __device__ __forceinline__ float bwd(float g, float x) {
-    float er, e;
-    erf_and_gauss(x, er, e);
-    return g * fmaf(x, e * kInvSqrt2Pi, fmaf(0.5f, er, 0.5f));
-  }
+// bf16: erf(z) = sign(z) (1 - poly(t) e^{-z^2}), t = 1 / (1 + p |z|), with e^{-z^2} = e^{-x^2 / 2}, evaluated
+// on packed fp32 pairs below.
+// ---- bf16 on packed fp32 pairs (FFMA2): both kernels are bound by instruction issue + MUFU --------
+struct GeluPair {
+  f2_t erf, gauss;  // erf(x / sqrt 2), e^{-x^2 / 2}
 };
+__device__ __forceinline__ GeluPair erf_and_gauss2(f2_t x) {
+  const f2_t ax = x & 0x7fffffff7fffffffull;                       // |x| on both halves
+  const f2_t z = f2_mul(ax, f2_splat(kSqrtHalf));
+  float e0, e1, d0, d1;
+  f2_split(f2_mul(f2_mul(x, x), f2_splat(-0.72134752044448170368f)), e0, e1);
+  asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e0));
+  asm("ex2.approx.ftz.f32 %0, %0;" : "+f"(e1));
+  f2_split(f2_fma(z, f2_splat(0.3275911f), f2_splat(1.f)), d0, d1);
+  asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(d0));
+  asm("rcp.approx.ftz.f32 %0, %0;" : "+f"(d1));
+  const f2_t t = f2_make(d0, d1), e = f2_make(e0, e1);
+  // -poly(t): the negated Abramowitz-Stegun coefficients, so that erf|x| = 1 + (-poly) e
+  f2_t p = f2_fma(f2_splat(-1.061405429f), t, f2_splat(1.453152027f));
+  p = f2_fma(p, t, f2_splat(-1.421413741f));
+  p = f2_fma(p, t, f2_splat(0.284496736f));
+  p = f2_fma(p, t, f2_splat(-0.254829592f));
+  p = f2_mul(p, t);
+  const f2_t erf_abs = f2_fma(p, e, f2_splat(1.f));                 // in [0, 1]: sign bit clear
+  return GeluPair{erf_abs | (x & 0x8000000080000000ull), e};       // copysign on both halves
+}
+__device__ __forceinline__ uint32_t gelu_fwd2(uint32_t w) {
+  const f2_t x = f2_from_bf16x2(w);
+  const GeluPair g = erf_and_gauss2(x);
+  const f2_t hx = f2_mul(x, f2_splat(0.5f));
+  float lo, hi;
+  f2_split(f2_fma(hx, g.erf, hx), lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+__device__ __forceinline__ uint32_t gelu_bwd2(uint32_t wg, uint32_t wh) {
+  const f2_t g = f2_from_bf16x2(wg), x = f2_from_bf16x2(wh);
+  const GeluPair r = erf_and_gauss2(x);
+  const f2_t cdf = f2_fma(r.erf, f2_splat(0.5f), f2_splat(0.5f));
+  const f2_t xpdf = f2_mul(x, f2_mul(r.gauss, f2_splat(kInvSqrt2Pi)));
+  float lo, hi;
+  f2_split(f2_mul(g, f2_add(cdf, xpdf)), lo, hi);
+  return pack_bf16x2(lo, hi);
+}
+// element-wise forward / backward of one 16-byte vector
+template <typename T>
+__device__ __forceinline__ uint4 gelu_fwd_vec(const uint4& u) {
+  if constexpr (sizeof(T) == 2) {
+    return make_uint4(gelu_fwd2(u.x), gelu_fwd2(u.y), gelu_fwd2(u.z), gelu_fwd2(u.w));
+  } else {
+    float t[Vec16<T>::N];
+    unpack<T>(u, t);
+#pragma unroll
+    for (int e = 0; e < Vec16<T>::N; ++e) t[e] = Gelu<T>::fwd(t[e]);
+    return pack<T>(t);
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint4 gelu_bwd_vec(const uint4& ug, const uint4& uh) {
+  if constexpr (sizeof(T) == 2) {
+    return make_uint4(gelu_bwd2(ug.x, uh.x), gelu_bwd2(ug.y, uh.y), gelu_bwd2(ug.z, uh.z), gelu_bwd2(ug.w, uh.w));
+  } else {
+    float tg[Vec16<T>::N], th[Vec16<T>::N];
+    unpack<T>(ug, tg);
+    unpack<T>(uh, th);
+#pragma unroll
+    for (int e = 0; e < Vec16<T>::N; ++e) tg[e] = Gelu<T>::bwd(tg[e], th[e]);
+    return pack<T>(tg);
+  }
+}
 
 template <typename T>
 __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ h, T* __restrict__ out, int64_t nvec) {
-  constexpr int VE = Vec16<T>::N;
   const uint4* hv = reinterpret_cast<const uint4*>(h);
   uint4* ov = reinterpret_cast<uint4*>(out);
   const int64_t stride = (int64_t)gridDim.x * blockDim.x;
@@ -71,21 +111,9 @@ __global__ void __launch_bounds__(256) gelu_fwd_kernel(const T* __restrict__ h, 
 #pragma unroll
     for (int i = 0; i < 4; ++i) u[i] = ld_stream(hv + f + i * stride);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float t[VE];
-      unpack<T>(u[i], t);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) t[e] = Gelu<T>::fwd(t[e]);
-      ov[f + i * stride] = pack<T>(t);  // re-read by the fc2 GEMM: leave it in L2
-    }
+    for (int i = 0; i < 4; ++i) ov[f + i * stride] = gelu_fwd_vec<T>(u[i]);  // re-read by the fc2 GEMM: leave it in L2
   }
-  for (; f < nvec; f += stride) {
-    float t[VE];
-    unpack<T>(ld_stream(hv + f), t);
-#pragma unroll
-    for (int e = 0; e < VE; ++e) t[e] = Gelu<T>::fwd(t[e]);
-    ov[f] = pack<T>(t);
-  }
+  for (; f < nvec; f += stride) ov[f] = gelu_fwd_vec<T>(ld_stream(hv + f));
 }
 
 template <typename T>
@@ -112,27 +140,19 @@ __global__ void __launch_bounds__(256)
     }
 #pragma unroll
     for (int i = 0; i < 2; ++i) {
-      float tg[VE], th[VE];
-      unpack<T>(ug[i], tg);
-      unpack<T>(uh[i], th);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) tg[e] = Gelu<T>::bwd(tg[e], th[e]);
-      const uint4 o = pack<T>(tg);
+      const uint4 o = gelu_bwd_vec<T>(ug[i], uh[i]);
       dv[f + i * stride] = o;
       // the bias gradient sums what the GEMMs will read: the ROUNDED dh (as ATen's sum over it would)
+      float tg[VE];
       unpack<T>(o, tg);
 #pragma unroll
       for (int e = 0; e < VE; ++e) acc[e] += tg[e];
     }
   }
   for (; f < nvec; f += stride) {
-    float tg[VE], th[VE];
-    unpack<T>(ld_stream(gv + f), tg);
-    unpack<T>(ld_stream(hv + f), th);
-#pragma unroll
-    for (int e = 0; e < VE; ++e) tg[e] = Gelu<T>::bwd(tg[e], th[e]);
-    const uint4 o = pack<T>(tg);
+    const uint4 o = gelu_bwd_vec<T>(ld_stream(gv + f), ld_stream(hv + f));
     dv[f] = o;
+    float tg[VE];
     unpack<T>(o, tg);
 #pragma unroll
     for (int e = 0; e < VE; ++e) acc[e] += tg[e];

@@ -66,38 +66,8 @@ __device__ __forceinline__ float simam_fwd_fast(float x, float mean, float inv8v
   return fmaf(hx, th, hx);
 }
 
-// ---- packed fp32x2 arithmetic (FFMA2: two fp32 lanes per issue slot) ------------------------------
-// The bf16 backward is bound by instruction issue, not by HBM (~36 slots per element over two sweeps).
-// A 32-bit word of the input holds two bf16 values: (w << 16, w & 0xffff0000) IS the pair of fp32
-// values, so the whole per-element chain runs on pairs and only the two tanh stay scalar.
-typedef unsigned long long f2_t;
-__device__ __forceinline__ f2_t f2_make(float lo, float hi) {
-  f2_t r;
-  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
-  return r;
-}
-__device__ __forceinline__ f2_t f2_splat(float v) { return f2_make(v, v); }
-__device__ __forceinline__ void f2_split(f2_t v, float& lo, float& hi) {
-  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
-}
-__device__ __forceinline__ f2_t f2_from_bf16x2(uint32_t w) {
-  return f2_make(__uint_as_float(w << 16), __uint_as_float(w & 0xffff0000u));
-}
-__device__ __forceinline__ f2_t f2_fma(f2_t a, f2_t b, f2_t c) {
-  f2_t d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
-  return d;
-}
-__device__ __forceinline__ f2_t f2_mul(f2_t a, f2_t b) {
-  f2_t d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
-__device__ __forceinline__ f2_t f2_add(f2_t a, f2_t b) {
-  f2_t d;
-  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
-  return d;
-}
+// The bf16 backward is bound by instruction issue, not by HBM (~36 slots per element over two sweeps):
+// the whole per-element chain runs on packed fp32 pairs (common.cuh) and only the two tanh stay scalar.
 __device__ __forceinline__ f2_t f2_tanh(f2_t a) {
   float lo, hi;
   f2_split(a, lo, hi);
