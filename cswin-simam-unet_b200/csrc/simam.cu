@@ -1328,6 +1328,705 @@ int nchw_fwd_stream(const T* x, T* y, float* stats, int64_t planes, int64_t S, f
 }
 
 // ------------------------------------------------------------------------------------------------
+// NLC streaming kernels (token layout, the CSWin skips of config 3): a cluster of 1/2/4/8 CTAs owns
+// one image — L*C contiguous elements — and each CTA streams its contiguous share of the rows
+// through the same bulk-copy ring as the NCHW kernels (whole 128..1024-byte rows, 16 KB per copy,
+// instead of 32..128-byte row segments fetched by the threads themselves).  512 % (16-byte vectors
+// per row) == 0, so a consumer thread meets the same 8 (bf16) / 4 (fp32) channels in every vector it
+// reads and keeps their moments in registers.  The per-channel partials of the CTAs meet once per
+// image: every CTA PUSHES its partials into the shared memory of all peers (st.shared::cluster) and
+// then arrives on their mbarriers, so a CTA only ever reads its own shared memory and needs no
+// hand-shake before it exits.  Only consumer threads take part; the producer thread keeps
+// prefetching.  A cluster that owns several images software-pipelines them: the second sweep of
+// image i (reads served by L2, writes to DRAM) is interleaved chunk by chunk with the first sweep of
+// image i+1 (reads from DRAM).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t cluster_nctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t nl_mapa(const void* local_smem_ptr, uint32_t rank) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(st_smem_u32(local_smem_ptr)), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void nl_remote_arrive(uint64_t* bar, uint32_t rank) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(nl_mapa(bar, rank)) : "memory");
+}
+__device__ __forceinline__ void nl_wait_cluster(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tXW_%=:\n\t"
+      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra XD_%=;\n\tbra XW_%=;\n\tXD_%=:\n\t}" ::"r"(st_smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void nl_consumer_sync() {
+  asm volatile("bar.sync 1, %0;" ::"n"(ST_CONSUMERS) : "memory");
+}
+// streaming store whose line is the first candidate for eviction from L2 (outputs are never re-read)
+__device__ __forceinline__ void st_stream_first(void* p, const uint4& v, uint64_t policy) {
+  asm volatile("st.global.L1::no_allocate.L2::cache_hint.v4.u32 [%0], {%1,%2,%3,%4}, %5;" ::"l"(p), "r"(v.x),
+               "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t l2_evict_first_policy() {
+  uint64_t p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+
+template <int VE, int CVEC>
+struct NlSmem {
+  static constexpr int GW = CVEC < 32 ? CVEC : 32;        // column vectors a warp covers
+  static constexpr int NCLS = CVEC < 32 ? 1 : CVEC / 32;  // warp w covers vectors (w % NCLS) * 32 + lane
+  static constexpr int CW = CVEC * VE;                    // channels
+  static constexpr int WARPS = ST_CONSUMERS / 32;
+  static constexpr int RED_BYTES = WARPS * 2 * VE * GW * 4;  // [WARPS][2][VE][GW] floats
+  static constexpr int PART_BYTES = 2 * 8 * 2 * CW * 4;      // [image parity][source rank][2 * CW] floats
+  static constexpr int FIN_BYTES = 2 * CW * 4;
+  static constexpr int BAR_BYTES = 256;                      // full[STAGES], empty[STAGES], xbar
+  static constexpr int MAX_SMEM = 227 * 1024;
+  static constexpr int FIT = (MAX_SMEM - BAR_BYTES - RED_BYTES - PART_BYTES - FIN_BYTES) / ST_CHUNK;
+  static constexpr int STAGES = FIT < 10 ? FIT : 10;
+  static constexpr int BARS = STAGES * ST_CHUNK;
+  static constexpr int RED = BARS + BAR_BYTES;
+  static constexpr int PART = RED + RED_BYTES;
+  static constexpr int FIN = PART + PART_BYTES;
+  static constexpr int BYTES = FIN + FIN_BYTES;
+  static_assert(STAGES >= 4 && 2 * STAGES + 1 <= BAR_BYTES / 8, "ring too shallow");
+};
+
+// Sum acc[q][e] over all consumer threads of the cluster that hold the same channel; fixed order,
+// identical in every CTA of the cluster.
+template <int VE, int CVEC>
+__device__ __forceinline__ void nl_reduce(float (&acc)[2][VE], uint8_t* smem, int image_parity, int CL, int rank) {
+  using S = NlSmem<VE, CVEC>;
+  float* s_red = reinterpret_cast<float*>(smem + S::RED);
+  float* s_part = reinterpret_cast<float*>(smem + S::PART) + image_parity * (8 * 2 * S::CW);
+  float* s_fin = reinterpret_cast<float*>(smem + S::FIN);
+  uint64_t* xbar = reinterpret_cast<uint64_t*>(smem + S::BARS) + 2 * S::STAGES;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+#pragma unroll
+      for (int o = 16; o >= CVEC; o >>= 1) acc[q][e] += __shfl_xor_sync(0xffffffffu, acc[q][e], o);
+    }
+  if (lane < S::GW) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q)
+#pragma unroll
+      for (int e = 0; e < VE; ++e) s_red[((warp * 2 + q) * VE + e) * S::GW + lane] = acc[q][e];
+  }
+  nl_consumer_sync();
+  for (int j = threadIdx.x; j < 2 * S::CW; j += ST_CONSUMERS) {
+    const int q = j / S::CW, ch = j % S::CW, g = ch / VE, e = ch % VE;
+    const int cls = g / S::GW, gl = g % S::GW;
+    float a = 0.f;
+#pragma unroll
+    for (int w = 0; w < S::WARPS / S::NCLS; ++w)
+      a += s_red[(((cls + w * S::NCLS) * 2 + q) * VE + e) * S::GW + gl];
+    if (CL > 1) {
+      for (int r = 0; r < CL; ++r)
+        asm volatile("st.shared::cluster.f32 [%0], %1;" ::"r"(nl_mapa(&s_part[rank * 2 * S::CW + j], (uint32_t)r)), "f"(a)
+                     : "memory");
+    } else {
+      s_fin[j] = a;
+    }
+  }
+  if (CL > 1) {
+    asm volatile("fence.acq_rel.cluster;" ::: "memory");
+    nl_consumer_sync();  // every partial of this CTA has been pushed
+    if (threadIdx.x == 0)
+      for (int r = 0; r < CL; ++r) nl_remote_arrive(xbar, (uint32_t)r);
+    nl_wait_cluster(xbar, (uint32_t)image_parity);  // ... and every peer's has landed here
+    for (int j = threadIdx.x; j < 2 * S::CW; j += ST_CONSUMERS) {
+      float a = 0.f;
+      for (int r = 0; r < CL; ++r) a += s_part[r * 2 * S::CW + j];  // same order in every CTA
+      s_fin[j] = a;
+    }
+  }
+  nl_consumer_sync();
+  const int cv = threadIdx.x % CVEC;
+#pragma unroll
+  for (int q = 0; q < 2; ++q)
+#pragma unroll
+    for (int e = 0; e < VE; ++e) acc[q][e] = s_fin[q * S::CW + cv * VE + e];
+}
+
+// barriers + the cluster-wide start line; returns after every CTA of the cluster has initialised
+template <int VE, int CVEC>
+__device__ __forceinline__ void nl_init(uint8_t* smem, int CL) {
+  using S = NlSmem<VE, CVEC>;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + S::BARS);
+  uint64_t* empty = full + S::STAGES;
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < S::STAGES; ++i) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&full[i])), "r"(1));
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[i])), "r"(ST_CONSUMERS / 32));
+    }
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(st_smem_u32(&empty[S::STAGES])), "r"(CL));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (CL > 1) cluster_sync_all();  // every thread is still here: nobody touches a peer that has not initialised
+}
+
+// Producer: one thread streams this CTA's share of the cluster's images.  Phase p interleaves, chunk by
+// chunk, the second sweep of image p-1 (an L2 hit, marked evict-first: it is dead afterwards) with
+// the first sweep of image p; the consumers walk the ring in the same order.  The second sweep walks
+// its chunks BACKWARDS: when the batch does not fit in L2 (backward at 512^2: x and grad_y are
+// 128 MB) a forward re-walk of an LRU cache misses every time, the reverse walk hits whatever the
+// cache still holds.
+template <int STAGES>
+__device__ __forceinline__ void nl_produce(uint8_t* smem, int bars_off, const uint8_t* x, const uint8_t* g,
+                                           int my_images, int first_image, int image_step, int64_t image_bytes,
+                                           int64_t cta_off, int chunks, int part_bytes) {
+  uint8_t* ring = smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + bars_off);
+  uint64_t* empty = full + STAGES;
+  const uint64_t pol_first = l2_evict_first_policy();
+  int ring_s = 0;
+  uint32_t ring_par = 0;
+  auto issue = [&](int64_t off, bool again) {
+    const int s = ring_s;
+    st_mbar_wait(&empty[s], ring_par ^ 1u);
+    if (++ring_s == STAGES) {
+      ring_s = 0;
+      ring_par ^= 1u;
+    }
+    const uint32_t bar = st_smem_u32(&full[s]), dst = st_smem_u32(ring + s * ST_CHUNK);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(ST_CHUNK) : "memory");
+    if (again) {
+      asm volatile(
+          "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+              "r"(dst), "l"(x + off), "r"(part_bytes), "r"(bar), "l"(pol_first) : "memory");
+      if (g != nullptr)
+        asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint [%0], [%1], %2, [%3], %4;" ::
+                "r"(dst + part_bytes), "l"(g + off), "r"(part_bytes), "r"(bar), "l"(pol_first) : "memory");
+    } else {
+      asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                   "l"(x + off), "r"(part_bytes), "r"(bar)
+                   : "memory");
+      if (g != nullptr)
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         dst + part_bytes),
+                     "l"(g + off), "r"(part_bytes), "r"(bar)
+                     : "memory");
+    }
+  };
+  for (int ph = 0; ph <= my_images; ++ph) {
+    const int64_t off2 = ((int64_t)first_image + (int64_t)(ph - 1) * image_step) * image_bytes + cta_off;
+    const int64_t off1 = off2 + (int64_t)image_step * image_bytes;
+    for (int c = 0; c < chunks; ++c) {
+      if (ph > 0) issue(off2 + (int64_t)(chunks - 1 - c) * part_bytes, true);
+      if (ph < my_images) issue(off1 + (int64_t)c * part_bytes, false);
+    }
+  }
+}
+
+template <typename T, int CVEC, bool PIPE>
+__global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
+    simam_nlc_fwd_stream(const T* __restrict__ x, T* __restrict__ y, float* __restrict__ stats, int B, int L,
+                         int chunks /* 16-KB chunks per CTA per image */, float e_lambda) {
+  constexpr int VE = Vec16<T>::N, NP = VE / 2, VPC = ST_CHUNK / 16 / ST_CONSUMERS;
+  constexpr bool BF = sizeof(T) == 2;
+  using S = NlSmem<VE, CVEC>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  uint8_t* ring = st_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + S::BARS);
+  uint64_t* empty = full + STAGES;
+  const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  nl_init<VE, CVEC>(st_smem, CL);
+  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+  const int my_images = (B - cid + ncl - 1) / ncl;
+  const int64_t cta_bytes = (int64_t)chunks * ST_CHUNK, image_bytes = cta_bytes * CL;
+
+  if (warp == ST_CONSUMERS / 32) {
+    if (lane == 0)
+      nl_produce<STAGES>(st_smem, S::BARS, reinterpret_cast<const uint8_t*>(x), nullptr, my_images, cid, ncl,
+                         image_bytes, rank * cta_bytes, chunks, ST_CHUNK);
+    return;
+  }
+  const int cv = threadIdx.x % CVEC;
+  const uint64_t pol_first = l2_evict_first_policy();
+  const f2_t quarter2 = f2_splat(0.25f), half2 = f2_splat(0.5f);
+  // first-sweep state (image ph): pivot and running moments; second-sweep state (image ph-1): coefficients
+  float pivot[VE], acc[2][VE];
+  f2_t npivot2[NP], sum2[NP], sq2[NP];          // bf16: packed pairs
+  f2_t nmean2[NP], inv8v2[NP];                  // bf16 second sweep
+  float piv2[VE], dmean2[VE], inv4v2[VE];       // fp32 second sweep
+  int ring_s = 0;
+  uint32_t ring_par = 0;
+  auto release = [&](int s) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
+  };
+  int64_t b1 = 0;
+  uint4* dst = nullptr;
+  auto start_first = [&](int ph) {
+    b1 = (int64_t)cid + (int64_t)ph * ncl;
+      const uint4* ximg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + b1 * image_bytes);
+      unpack<T>(__ldg(ximg + cv), pivot);  // row 0 of the image, this thread's channels
+#pragma unroll
+      for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        npivot2[q] = f2_make(-pivot[2 * q], -pivot[2 * q + 1]);
+        sum2[q] = sq2[q] = f2_splat(0.f);
+      }
+  };
+  auto start_second = [&](int ph) {
+    const int64_t b2 = (int64_t)cid + (int64_t)(ph - 1) * ncl;
+    dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + b2 * image_bytes + rank * cta_bytes);
+  };
+  auto second_chunk = [&](int c) {
+        const int s = ring_s;
+        st_mbar_wait(&full[s], ring_par);
+        if (++ring_s == STAGES) {
+          ring_s = 0;
+          ring_par ^= 1u;
+        }
+        const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+#pragma unroll
+        for (int i = 0; i < VPC; ++i) {
+          const uint4 u = v[threadIdx.x + i * ST_CONSUMERS];
+          uint4 r;
+          if constexpr (BF) {
+            // y = hx tanh(t^2 / (8v) + 1/4) + hx, hx = x / 2, on packed pairs
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const f2_t x2 = f2_from_bf16x2(w[q]);
+              const f2_t t = f2_add(x2, nmean2[q]);
+              const f2_t th = f2_tanh(f2_fma(f2_mul(t, t), inv8v2[q], quarter2));
+              const f2_t hx = f2_mul(x2, half2);
+              float lo, hi;
+              f2_split(f2_fma(hx, th, hx), lo, hi);
+              o[q] = pack_bf16x2(lo, hi);
+            }
+            r = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            float f[VE];
+            unpack<T>(u, f);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) f[e] = simam_fwd_elem<T>(f[e], FwdCoef{piv2[e], dmean2[e], inv4v2[e]});
+            r = pack<T>(f);
+          }
+          st_stream_first(dst + (int64_t)(chunks - 1 - c) * (ST_CHUNK / 16) + threadIdx.x + i * ST_CONSUMERS, r, pol_first);
+        }
+        release(s);
+  };
+  auto first_chunk = [&](int c) {
+        const int s = ring_s;
+        st_mbar_wait(&full[s], ring_par);
+        if (++ring_s == STAGES) {
+          ring_s = 0;
+          ring_par ^= 1u;
+        }
+        const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+#pragma unroll
+        for (int i = 0; i < VPC; ++i) {
+          const uint4 u = v[threadIdx.x + i * ST_CONSUMERS];
+          if constexpr (BF) {
+            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const f2_t d = f2_add(f2_from_bf16x2(w[q]), npivot2[q]);
+              sum2[q] = f2_add(sum2[q], d);
+              sq2[q] = f2_fma(d, d, sq2[q]);
+            }
+          } else {
+            float f[VE];
+            unpack<T>(u, f);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) {
+              const float d = f[e] - pivot[e];
+              acc[0][e] += d;
+              acc[1][e] = fmaf(d, d, acc[1][e]);
+            }
+          }
+        }
+        release(s);
+  };
+  auto finish_first = [&](int ph) {
+      if constexpr (BF) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          f2_split(sum2[q], acc[0][2 * q], acc[0][2 * q + 1]);
+          f2_split(sq2[q], acc[1][2 * q], acc[1][2 * q + 1]);
+        }
+      }
+      nl_reduce<VE, CVEC>(acc, st_smem, ph & 1, CL, rank);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        const float dmean = acc[0][e] / (float)L;
+        const float var = fmaxf(acc[1][e] - acc[0][e] * dmean, 0.f) / ((float)L - 1.f) + e_lambda;
+        acc[0][e] = dmean;
+        acc[1][e] = var;
+        piv2[e] = pivot[e];
+        dmean2[e] = dmean;
+        inv4v2[e] = 1.f / (4.f * var);
+      }
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        nmean2[q] = f2_make(-(pivot[2 * q] + acc[0][2 * q]), -(pivot[2 * q + 1] + acc[0][2 * q + 1]));
+        inv8v2[q] = f2_make(1.f / (8.f * acc[1][2 * q]), 1.f / (8.f * acc[1][2 * q + 1]));
+      }
+      if (stats != nullptr && rank == 0 && threadIdx.x < CVEC) {
+        const int64_t p0 = b1 * S::CW + cv * VE;
+#pragma unroll
+        for (int e = 0; e < VE; ++e) {
+          stats[2 * (p0 + e)] = acc[0][e];
+          stats[2 * (p0 + e) + 1] = acc[1][e];
+        }
+      }
+  };
+  if constexpr (!PIPE) {
+    // one image per cluster: the two sweeps never overlap and their state shares registers
+    start_first(0);
+    for (int c = 0; c < chunks; ++c) first_chunk(c);
+    finish_first(0);
+    start_second(1);
+    for (int c = 0; c < chunks; ++c) second_chunk(c);
+  } else {
+    for (int ph = 0; ph <= my_images; ++ph) {
+      const bool first = ph < my_images, second = ph > 0;
+      if (first) start_first(ph);
+      if (second) start_second(ph);
+      for (int c = 0; c < chunks; ++c) {
+        if (second) second_chunk(c);
+        if (first) first_chunk(c);
+      }
+      if (first) finish_first(ph);
+    }
+  }
+}
+
+template <typename T, int CVEC, bool PIPE>
+__global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
+    simam_nlc_bwd_stream(const T* __restrict__ x, const T* __restrict__ gy, const float* __restrict__ stats,
+                         T* __restrict__ gx, int B, int L, int chunks /* 8-KB chunks per CTA per image */) {
+  constexpr int VE = Vec16<T>::N, NP = VE / 2, HALF = ST_CHUNK / 2, VPC = HALF / 16 / ST_CONSUMERS;
+  constexpr bool BF = sizeof(T) == 2;
+  using S = NlSmem<VE, CVEC>;
+  constexpr int STAGES = S::STAGES;
+  extern __shared__ __align__(128) uint8_t st_smem[];
+  uint8_t* ring = st_smem;
+  uint64_t* full = reinterpret_cast<uint64_t*>(st_smem + S::BARS);
+  uint64_t* empty = full + STAGES;
+  const int CL = (int)cluster_nctarank(), rank = (int)cluster_ctarank();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  nl_init<VE, CVEC>(st_smem, CL);
+  const int cid = (int)blockIdx.x / CL, ncl = (int)gridDim.x / CL;
+  const int my_images = (B - cid + ncl - 1) / ncl;
+  const int64_t cta_bytes = (int64_t)chunks * HALF, image_bytes = cta_bytes * CL;
+
+  if (warp == ST_CONSUMERS / 32) {
+    if (lane == 0)
+      nl_produce<STAGES>(st_smem, S::BARS, reinterpret_cast<const uint8_t*>(x), reinterpret_cast<const uint8_t*>(gy),
+                         my_images, cid, ncl, image_bytes, rank * cta_bytes, chunks, HALF);
+    return;
+  }
+  const int cv = threadIdx.x % CVEC;
+  const float Lf = (float)L;
+  const uint64_t pol_first = l2_evict_first_policy();
+  const f2_t quarter2 = f2_splat(0.25f), mone2 = f2_splat(-1.f), half2 = f2_splat(0.5f);
+  // first-sweep state (image ph)
+  float pivot[VE], dmean[VE], inv4v[VE], vv[VE], acc[2][VE];
+  f2_t r1p[NP], r2p[NP], nmean2[NP], inv8v2[NP];
+  // second-sweep state (image ph-1)
+  float piv_b[VE], dmean_b[VE], inv4v_b[VE], c1_b[VE], c2_b[VE];
+  f2_t nmean2_b[NP], inv8v2_b[NP], nk2_b[NP], nc2_b[NP];
+  int ring_s = 0;
+  uint32_t ring_par = 0;
+  auto release = [&](int s) {
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(st_smem_u32(&empty[s])) : "memory");
+  };
+  int64_t b1 = 0;
+  uint4* dst = nullptr;
+  auto start_first = [&](int ph) {
+    b1 = (int64_t)cid + (int64_t)ph * ncl;
+      const uint4* ximg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + b1 * image_bytes);
+      unpack<T>(__ldg(ximg + cv), pivot);
+      const int64_t p0 = b1 * S::CW + cv * VE;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        dmean[e] = __ldg(stats + 2 * (p0 + e));
+        vv[e] = __ldg(stats + 2 * (p0 + e) + 1);
+        inv4v[e] = 1.f / (4.f * vv[e]);
+        acc[0][e] = acc[1][e] = 0.f;
+      }
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        r1p[q] = r2p[q] = f2_splat(0.f);
+        nmean2[q] = f2_make(-(pivot[2 * q] + dmean[2 * q]), -(pivot[2 * q + 1] + dmean[2 * q + 1]));
+        inv8v2[q] = f2_make(0.5f * inv4v[2 * q], 0.5f * inv4v[2 * q + 1]);
+      }
+  };
+  auto start_second = [&](int ph) {
+    const int64_t b2 = (int64_t)cid + (int64_t)(ph - 1) * ncl;
+    dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gx) + b2 * image_bytes + rank * cta_bytes);
+  };
+  auto second_chunk = [&](int c) {
+        const int s = ring_s;
+        st_mbar_wait(&full[s], ring_par);
+        if (++ring_s == STAGES) {
+          ring_s = 0;
+          ring_par ^= 1u;
+        }
+        const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+        const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+#pragma unroll
+        for (int i = 0; i < VPC; ++i) {
+          const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
+          uint4 res;
+          if constexpr (BF) {
+            // grad_x = 0.5 g (1 + tanh) + t (4a k1 - k2) - c2 with k1 = 1/(8v); the pairs hold -4a
+            const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+            uint32_t o[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
+              const f2_t t = f2_add(x2, nmean2_b[q]), dd = f2_mul(t, t);
+              const f2_t th = f2_tanh(f2_fma(dd, inv8v2_b[q], quarter2));
+              const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));
+              const f2_t hg = f2_mul(g2, half2);
+              const f2_t gs = f2_fma(hg, th, f2_add(hg, nc2_b[q]));
+              // t (-4a)(-k1) = t (na4 * inv8v) with the sign carried by nk2: t (na4 (-k1) - k2)
+              const f2_t r = f2_fma(t, f2_fma(f2_mul(na4, mone2), inv8v2_b[q], nk2_b[q]), gs);
+              float lo, hi;
+              f2_split(r, lo, hi);
+              o[q] = pack_bf16x2(lo, hi);
+            }
+            res = make_uint4(o[0], o[1], o[2], o[3]);
+          } else {
+            float fx[VE], fg[VE];
+            unpack<T>(ux, fx);
+            unpack<T>(ug, fg);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) {
+              const float t = centred(fx[e], piv_b[e], dmean_b[e]), dd = t * t;
+              const float sg_ = Sig<T>::f(fmaf(dd, inv4v_b[e], 0.5f));
+              const float a = fg[e] * fx[e] * sg_ * (1.f - sg_);
+              fx[e] = fmaf(fg[e], sg_, 2.f * t * fmaf(a, inv4v_b[e], -c1_b[e])) - c2_b[e];
+            }
+            res = pack<T>(fx);
+          }
+          st_stream_first(dst + (int64_t)(chunks - 1 - c) * (HALF / 16) + threadIdx.x + i * ST_CONSUMERS, res, pol_first);
+        }
+        release(s);
+  };
+  auto first_chunk = [&](int c) {
+        const int s = ring_s;
+        st_mbar_wait(&full[s], ring_par);
+        if (++ring_s == STAGES) {
+          ring_s = 0;
+          ring_par ^= 1u;
+        }
+        const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+        const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+#pragma unroll
+        for (int i = 0; i < VPC; ++i) {
+          const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
+          if constexpr (BF) {
+            const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
+              const f2_t t = f2_add(x2, nmean2[q]), dd = f2_mul(t, t);
+              const f2_t th = f2_tanh(f2_fma(dd, inv8v2[q], quarter2));
+              const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));  // -4a = g x (tanh^2 - 1)
+              r1p[q] = f2_fma(na4, dd, r1p[q]);
+              r2p[q] = f2_fma(na4, t, r2p[q]);
+            }
+          } else {
+            float fx[VE], fg[VE];
+            unpack<T>(ux, fx);
+            unpack<T>(ug, fg);
+#pragma unroll
+            for (int e = 0; e < VE; ++e) {
+              const float t = centred(fx[e], pivot[e], dmean[e]), dd = t * t;
+              const float sg_ = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
+              const float a4 = 4.f * fg[e] * fx[e] * sg_ * (1.f - sg_);
+              acc[0][e] = fmaf(a4, dd, acc[0][e]);
+              acc[1][e] = fmaf(a4, t, acc[1][e]);
+            }
+          }
+        }
+        release(s);
+  };
+  auto finish_first = [&](int ph) {
+      if constexpr (BF) {
+#pragma unroll
+        for (int q = 0; q < NP; ++q) {
+          float lo, hi;
+          f2_split(r1p[q], lo, hi);
+          acc[0][2 * q] = -lo;
+          acc[0][2 * q + 1] = -hi;
+          f2_split(r2p[q], lo, hi);
+          acc[1][2 * q] = -lo;
+          acc[1][2 * q + 1] = -hi;
+        }
+      }
+      nl_reduce<VE, CVEC>(acc, st_smem, ph & 1, CL, rank);
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        const float r1 = 0.25f * acc[0][e], r2 = 0.25f * acc[1][e];  // the sweeps accumulate 4 a
+        c1_b[e] = r1 * inv4v[e] / (vv[e] * (Lf - 1.f));              // R1 / (4 v^2 n)
+        c2_b[e] = 2.f / Lf * r2 * inv4v[e];                          // (2/L) R2
+        piv_b[e] = pivot[e];
+        dmean_b[e] = dmean[e];
+        inv4v_b[e] = inv4v[e];
+      }
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        nmean2_b[q] = nmean2[q];
+        inv8v2_b[q] = inv8v2[q];
+        nk2_b[q] = f2_make(-2.f * c1_b[2 * q], -2.f * c1_b[2 * q + 1]);
+        nc2_b[q] = f2_make(-c2_b[2 * q], -c2_b[2 * q + 1]);
+      }
+  };
+  if constexpr (!PIPE) {
+    // one image per cluster: the two sweeps never overlap and their state shares registers
+    start_first(0);
+    for (int c = 0; c < chunks; ++c) first_chunk(c);
+    finish_first(0);
+    start_second(1);
+    for (int c = 0; c < chunks; ++c) second_chunk(c);
+  } else {
+    for (int ph = 0; ph <= my_images; ++ph) {
+      const bool first = ph < my_images, second = ph > 0;
+      if (first) start_first(ph);
+      if (second) start_second(ph);
+      for (int c = 0; c < chunks; ++c) {
+        if (second) second_chunk(c);
+        if (first) first_chunk(c);
+      }
+      if (first) finish_first(ph);
+    }
+  }
+}
+
+// Launch: the largest cluster (<= 8 CTAs) that still gives every image of the batch its own cluster in
+// ONE wave and divides the image into whole chunks; persistent, pipelined clusters when the batch is larger.
+template <typename T, bool BWD, int CVEC, bool PIPE>
+int nlc_stream_launch2(const cudaLaunchConfig_t& cfg, const T* x, const T* gy, float* stats_out, const float* stats_in,
+                       T* out, int B, int L, int chunks, float e_lambda) {
+  constexpr int SMEM = NlSmem<Vec16<T>::N, CVEC>::BYTES;
+  static bool ready = false;
+  cudaError_t e;
+  if (!ready) {
+    if constexpr (BWD)
+      e = cudaFuncSetAttribute(simam_nlc_bwd_stream<T, CVEC, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else
+      e = cudaFuncSetAttribute(simam_nlc_fwd_stream<T, CVEC, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) return fail(CSB200_ERR_CUDA, "simam_nlc_stream: %s", cudaGetErrorString(e));
+    ready = true;
+  }
+  if constexpr (BWD)
+    e = cudaLaunchKernelEx(&cfg, simam_nlc_bwd_stream<T, CVEC, PIPE>, x, gy, stats_in, out, B, L, chunks);
+  else
+    e = cudaLaunchKernelEx(&cfg, simam_nlc_fwd_stream<T, CVEC, PIPE>, x, out, stats_out, B, L, chunks, e_lambda);
+  if (e != cudaSuccess) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    return fail(CSB200_ERR_CUDA, "simam_nlc_stream: %s", cudaGetErrorString(e));
+  }
+  return check_launch(BWD ? "simam_nlc_bwd_stream" : "simam_nlc_fwd_stream");
+}
+
+// Launch: the largest cluster (<= 8 CTAs) that still gives every image of the batch its own cluster in
+// ONE wave and divides the image into whole chunks; persistent, pipelined clusters when the batch is larger.
+template <typename T, bool BWD, int CVEC>
+int nlc_stream_launch(const T* x, const T* gy, float* stats_out, const float* stats_in, T* out, int64_t B,
+                      int64_t L, int64_t image_bytes, float e_lambda, cudaStream_t st) {
+  constexpr int VE = Vec16<T>::N;
+  constexpr int PART = BWD ? ST_CHUNK / 2 : ST_CHUNK;
+  constexpr int SMEM = NlSmem<VE, CVEC>::BYTES;
+  static int sms = 0;
+  static int max_clusters[4] = {0, 0, 0, 0};  // by log2(cluster size)
+  if (sms == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+      return -1;
+    cudaError_t e;
+    if constexpr (BWD) e = cudaFuncSetAttribute(simam_nlc_bwd_stream<T, CVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    else e = cudaFuncSetAttribute(simam_nlc_fwd_stream<T, CVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
+    if (e != cudaSuccess) {
+      cudaGetLastError();
+      return -1;
+    }
+    sms = n;
+  }
+  int cl = 8, lg = 3;
+  while (cl > 1 && (B * cl > sms || image_bytes % ((int64_t)cl * PART) != 0 ||
+                    image_bytes / ((int64_t)cl * PART) < 2)) {
+    cl >>= 1;
+    --lg;
+  }
+  if (image_bytes % ((int64_t)cl * PART) != 0 || image_bytes / ((int64_t)cl * PART) > 0x7fffffff) return -1;
+  cudaLaunchConfig_t cfg{};
+  cfg.blockDim = dim3(ST_CONSUMERS + 32);
+  cfg.dynamicSmemBytes = SMEM;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  if (max_clusters[lg] == 0) {
+    int n = 0;
+    cfg.gridDim = dim3((unsigned)(sms / cl * cl));
+    cudaError_t e;
+    if constexpr (BWD) e = cudaOccupancyMaxActiveClusters(&n, simam_nlc_bwd_stream<T, CVEC, true>, &cfg);
+    else e = cudaOccupancyMaxActiveClusters(&n, simam_nlc_fwd_stream<T, CVEC, true>, &cfg);
+    if (e != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      n = sms / cl > 1 ? sms / cl / 2 : 1;  // conservative: correctness never depends on co-residency of clusters
+    }
+    max_clusters[lg] = n;
+  }
+  // even rounds: with r = ceil(B / resident) rounds, ceil(B / r) clusters finish together
+  const int64_t rounds = (B + max_clusters[lg] - 1) / max_clusters[lg];
+  const int64_t nclusters = (B + rounds - 1) / rounds;
+  cfg.gridDim = dim3((unsigned)(nclusters * cl));
+  const int chunks = (int)(image_bytes / ((int64_t)cl * PART));
+  if (rounds > 1)
+    return nlc_stream_launch2<T, BWD, CVEC, true>(cfg, x, gy, stats_out, stats_in, out, (int)B, (int)L, chunks, e_lambda);
+  return nlc_stream_launch2<T, BWD, CVEC, false>(cfg, x, gy, stats_out, stats_in, out, (int)B, (int)L, chunks, e_lambda);
+}
+
+// Rows of 8..64 16-byte vectors (bf16: 64..512 channels, fp32: 32..256), images of >= 128 KB.
+template <typename T, bool BWD>
+int nlc_stream(const T* x, const T* gy, float* stats_out, const float* stats_in, T* out, int64_t B, int64_t C,
+               int64_t L, float e_lambda, cudaStream_t st) {
+  constexpr int VE = Vec16<T>::N;
+  if (C % VE != 0 || !aligned16(x) || !aligned16(out) || (BWD && !aligned16(gy))) return -1;
+  if (B > 0x7fffffff || L > 0x7fffffff || L < 2) return -1;
+  const int64_t cvec = C / VE, image_bytes = L * C * (int64_t)sizeof(T);
+  if (image_bytes < (128 << 10)) return -1;
+#define CSB_NLS(CV) \
+  if (cvec == CV) return nlc_stream_launch<T, BWD, CV>(x, gy, stats_out, stats_in, out, B, L, image_bytes, e_lambda, st);
+  CSB_NLS(8)
+  CSB_NLS(16)
+  CSB_NLS(32)
+  CSB_NLS(64)
+#undef CSB_NLS
+  return -1;
+}
+
+// ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
 template <typename K, typename... Args>
@@ -1505,6 +2204,10 @@ int simam_dispatch(const void* x_, const void* gy_, float* stats_out, const floa
     int rs;
     if constexpr (BWD) rs = nchw_bwd_stream<T>(x, gy, stats_in, out, B * C, S, st);
     else rs = nchw_fwd_stream<T>(x, out, stats_out, B * C, S, e_lambda, st);
+    if (rs >= 0) return rs;
+  }
+  if (layout == CSB200_NLC) {
+    const int rs = nlc_stream<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, st);
     if (rs >= 0) return rs;
   }
   int rc = (layout == CSB200_NCHW)

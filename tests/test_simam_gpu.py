@@ -18,7 +18,10 @@ TOL = {torch.float32: 1e-5, torch.bfloat16: 2 ** -7}
 NCHW_SHAPES = [(2, 3, 4, 4), (3, 5, 16, 16), (2, 4, 32, 32), (2, 3, 64, 64), (2, 2, 128, 128), (1, 2, 256, 256),
                (1, 1, 512, 512), (2, 3, 7, 7), (1, 2, 224, 224), (1, 3, 14, 14), (2, 2, 56, 56), (1, 1, 600, 600)]
 NLC_SHAPES = [(2, 16, 64), (2, 1024, 256), (2, 4096, 128), (1, 16384, 64), (1, 256, 512), (2, 49, 24), (1, 3136, 64),
-              (1, 100, 13), (1, 65536, 32)]
+              (1, 100, 13), (1, 65536, 32),
+              # streaming kernels: clusters of 8 / 4 / 1 with more images than co-resident clusters (persistent
+              # loop, alternating partial buffers), a ragged last chunk count, 512 channels
+              (18, 2048, 64), (37, 1024, 64), (150, 1024, 64), (3, 1536, 128), (2, 512, 512)]
 
 
 def _check(x, layout, dtype, offset=0.0):
@@ -54,6 +57,20 @@ def test_simam_large_mean_keeps_fp32_parity():
     torch.manual_seed(0)
     _check(torch.randn(2, 3, 64, 64), "NCHW", torch.float32, offset=300.0)
     _check(torch.randn(2, 1024, 64), "NLC", torch.float32, offset=300.0)
+    _check(torch.randn(2, 4096, 64), "NLC", torch.float32, offset=300.0)  # streaming kernel
+
+
+def test_simam_nlc_streaming_is_deterministic_and_image_independent():
+    # config 3 skip shape x2; every image is reduced by its own cluster in a fixed order
+    torch.manual_seed(3)
+    x = (torch.randn(32, 4096, 128, device="cuda") * 3 - 1).bfloat16()
+    y = pkg.simam(x, 1e-4, "NLC")
+    assert torch.equal(y, pkg.simam(x, 1e-4, "NLC"))
+    perm = torch.randperm(32, device="cuda")
+    assert torch.equal(pkg.simam(x[perm].contiguous(), 1e-4, "NLC"), y[perm])
+    for b in (0, 13, 31):
+        ref = ops.simam(x[b:b + 1].double().cpu(), 1e-4, "NLC")
+        assert rel_err(y[b:b + 1].float().cpu(), ref) < TOL[torch.bfloat16]
 
 
 def test_simam_channels_last_takes_the_token_kernel_in_place():
