@@ -40,7 +40,7 @@ _lock = threading.Lock()
 EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_count", "csb200_simam_fwd",
            "csb200_simam_bwd", "csb200_layernorm_supported", "csb200_layernorm_fwd",
            "csb200_layernorm_bwd_workspace_bytes", "csb200_layernorm_bwd", "csb200_add_layernorm_fwd",
-           "csb200_add_layernorm_bwd", "csb200_colsum_supported",
+           "csb200_add_layernorm_bwd", "csb200_add_layernorm_bwd_rb", "csb200_colsum_supported",
            "csb200_colsum_workspace_bytes", "csb200_colsum", "csb200_add_row_bias", "csb200_gelu_supported", "csb200_gelu_fwd",
            "csb200_gelu_bwd_workspace_bytes", "csb200_gelu_bwd", "csb200_carafe_supported", "csb200_carafe_fwd",
            "csb200_carafe_bwd", "csb200_stripe_attn_engine", "csb200_stripe_attn_fwd",
@@ -78,6 +78,8 @@ def lib() -> ctypes.CDLL:
         L.csb200_add_layernorm_fwd.restype = ctypes.c_int
         L.csb200_add_layernorm_bwd.argtypes = [vp] * 9 + [ctypes.c_size_t, i64, i64, ctypes.c_int, ctypes.c_int, vp]
         L.csb200_add_layernorm_bwd.restype = ctypes.c_int
+        L.csb200_add_layernorm_bwd_rb.argtypes = [vp] * 10 + [ctypes.c_size_t, i64, i64, ctypes.c_int, ctypes.c_int, vp]
+        L.csb200_add_layernorm_bwd_rb.restype = ctypes.c_int
         L.csb200_colsum_supported.argtypes = [i64, ctypes.c_int]
         L.csb200_colsum_supported.restype = ctypes.c_int
         L.csb200_colsum_workspace_bytes.argtypes = [i64]

@@ -149,22 +149,27 @@ __global__ void __launch_bounds__(LN_THREADS)
   }
 }
 
-template <typename TIn, typename TGy, typename TGx, int LPR, int CPL, int NE>
+// RB: also accumulate the column sums of the gradient written to grad_x — the bias gradient of the
+// Linear whose output was the `residual` operand of the fused add (proj C:366, Mlp.fc2 C:195): that
+// Linear then needs no column-sum pass of its own.  The sums are taken over the ROUNDED values, i.e.
+// exactly what a separate pass over the stored tensor would see.
+template <typename TIn, typename TGy, typename TGx, int LPR, int CPL, int NE, bool RB>
 __global__ void __launch_bounds__(LN_THREADS)
     layernorm_bwd_kernel(const TIn* __restrict__ x, const TGy* __restrict__ gy,
                          const float* __restrict__ gamma, const float* __restrict__ stats,
                          const TGx* __restrict__ gres, TGx* __restrict__ gx, float* __restrict__ partial,
                          int64_t rows) {
-  constexpr int C = LPR * CPL * NE, RPW = 32 / LPR;
+  constexpr int C = LPR * CPL * NE, RPW = 32 / LPR, K = RB ? 3 : 2;
   __shared__ float s_part[LN_WARPS][2 * C];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, lr = lane % LPR, sub = lane / LPR;
-  float g[CPL][NE], dg[CPL][NE], db[CPL][NE];
+  float g[CPL][NE], dg[CPL][NE], db[CPL][NE], dr[RB ? CPL : 1][NE];
 #pragma unroll
   for (int j = 0; j < CPL; ++j)
 #pragma unroll
     for (int e = 0; e < NE; ++e) {
       g[j][e] = __ldg(gamma + (j * LPR + lr) * NE + e);
       dg[j][e] = db[j][e] = 0.f;
+      if constexpr (RB) dr[j][e] = 0.f;
     }
   const int64_t warp_global = (int64_t)blockIdx.x * LN_WARPS + warp;
   const int64_t warp_count = (int64_t)gridDim.x * LN_WARPS;
@@ -211,6 +216,11 @@ __global__ void __launch_bounds__(LN_THREADS)
           for (int e = 0; e < NE; ++e) o[e] += rv[e];
         }
         store_n<TGx, NE>(gx + r * C + (j * LPR + lr) * NE, o);
+        if constexpr (RB) {
+#pragma unroll
+          for (int e = 0; e < NE; ++e)
+            dr[j][e] += sizeof(TGx) == 2 ? __bfloat162float(__float2bfloat16_rn(o[e])) : o[e];
+        }
       }
     }
   }
@@ -239,30 +249,58 @@ __global__ void __launch_bounds__(LN_THREADS)
     float a = 0.f;
 #pragma unroll
     for (int w = 0; w < LN_WARPS; ++w) a += s_part[w][i];
-    partial[(int64_t)blockIdx.x * 2 * C + i] = a;
+    partial[(int64_t)blockIdx.x * K * C + i] = a;
+  }
+  if constexpr (RB) {
+    __syncthreads();  // s_part is reused for the third vector
+#pragma unroll
+    for (int j = 0; j < CPL; ++j)
+#pragma unroll
+      for (int e = 0; e < NE; ++e) {
+#pragma unroll
+        for (int o = 16; o >= LPR; o >>= 1) dr[j][e] += __shfl_xor_sync(0xffffffffu, dr[j][e], o);
+      }
+    if (sub == 0) {
+#pragma unroll
+      for (int j = 0; j < CPL; ++j)
+#pragma unroll
+        for (int e = 0; e < NE; ++e) s_part[warp][(j * LPR + lr) * NE + e] = dr[j][e];
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < C; i += LN_THREADS) {
+      float a = 0.f;
+#pragma unroll
+      for (int w = 0; w < LN_WARPS; ++w) a += s_part[w][i];
+      partial[(int64_t)blockIdx.x * K * C + 2 * C + i] = a;
+    }
   }
 }
 
 // one warp per output: lanes stride over the per-CTA partials (coalescing is across neighbouring
 // warps), fixed summation order -> deterministic
 __global__ void __launch_bounds__(256)
-    layernorm_param_grad_final(const float* __restrict__ partial, int blocks, int C,
-                               float* __restrict__ ggamma, float* __restrict__ gbeta) {
+    layernorm_param_grad_final(const float* __restrict__ partial, int blocks, int C, int K,
+                               float* __restrict__ ggamma, float* __restrict__ gbeta,
+                               float* __restrict__ grbias) {
   const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
-  if (i >= 2 * C) return;
+  if (i >= K * C) return;
   float a = 0.f;
-  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * 2 * C + i];
+  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * K * C + i];
   a = warp_sum(a);
   if (lane == 0) {
     if (i < C) ggamma[i] = a;
-    else gbeta[i - C] = a;
+    else if (i < 2 * C) gbeta[i - C] = a;
+    else grbias[i - 2 * C] = a;
   }
 }
 
 constexpr int LN_MAX_GRID = 148 * 4;  // persistent: 4 CTAs of 256 threads per B200 SM
-int ln_grid(int64_t rows, int rpw) {
+// the backward kernel that also sums the residual-bias gradient holds 16 more accumulators: 80 registers,
+// 3 CTAs per SM — a grid of 4 per SM would run as 1.33 waves
+constexpr int LN_MAX_GRID_RB = 148 * 3;
+int ln_grid(int64_t rows, int rpw, int max_grid = LN_MAX_GRID) {
   const int64_t need = (rows + (int64_t)rpw * LN_WARPS - 1) / ((int64_t)rpw * LN_WARPS);
-  return (int)(need < LN_MAX_GRID ? (need > 0 ? need : 1) : LN_MAX_GRID);
+  return (int)(need < max_grid ? (need > 0 ? need : 1) : max_grid);
 }
 
 // vectors of 16 B of the INPUT per row decide the tiling: LPR lanes per row, CPL chunks per lane
@@ -302,23 +340,31 @@ int ln_fwd_t(const void* x, const void* res, void* sum_out, const float* gamma, 
 
 template <typename TIn, typename TGy, typename TGx>
 int ln_bwd_t(const void* x, const void* gy, const void* gres, const float* gamma, const float* stats,
-             void* gx, float* ggamma, float* gbeta, float* partial, int64_t rows, int64_t C,
+             void* gx, float* ggamma, float* gbeta, float* grbias, float* partial, int64_t rows, int64_t C,
              cudaStream_t st) {
   constexpr int NE = 16 / sizeof(TIn);
   int lpr, cpl;
   if (!ln_shape<TIn>(C, &lpr, &cpl))
     return fail(CSB200_ERR_UNSUPPORTED, "layernorm: C=%lld is not tiled for this dtype", (long long)C);
-  const int grid = ln_grid(rows, 32 / lpr);
+  const int grid = ln_grid(rows, 32 / lpr, grbias != nullptr ? LN_MAX_GRID_RB : LN_MAX_GRID);
 #define CALL(L, P)                                                                       \
-  layernorm_bwd_kernel<TIn, TGy, TGx, L, P, NE><<<grid, LN_THREADS, 0, st>>>(            \
-      static_cast<const TIn*>(x), static_cast<const TGy*>(gy), gamma, stats,             \
-      static_cast<const TGx*>(gres), static_cast<TGx*>(gx), partial, rows)
+  do {                                                                                   \
+    if (grbias != nullptr)                                                               \
+      layernorm_bwd_kernel<TIn, TGy, TGx, L, P, NE, true><<<grid, LN_THREADS, 0, st>>>(  \
+          static_cast<const TIn*>(x), static_cast<const TGy*>(gy), gamma, stats,         \
+          static_cast<const TGx*>(gres), static_cast<TGx*>(gx), partial, rows);          \
+    else                                                                                 \
+      layernorm_bwd_kernel<TIn, TGy, TGx, L, P, NE, false><<<grid, LN_THREADS, 0, st>>>( \
+          static_cast<const TIn*>(x), static_cast<const TGy*>(gy), gamma, stats,         \
+          static_cast<const TGx*>(gres), static_cast<TGx*>(gx), partial, rows);          \
+  } while (0)
   LN_DISPATCH_SHAPE(CALL)
 #undef CALL
   int rc = check_launch("layernorm_bwd_kernel");
   if (rc != CSB200_OK) return rc;
-  layernorm_param_grad_final<<<(int)((2 * C * 32 + 255) / 256), 256, 0, st>>>(partial, grid, (int)C,
-                                                                         ggamma, gbeta);
+  const int K = grbias != nullptr ? 3 : 2;
+  layernorm_param_grad_final<<<(int)((K * C * 32 + 255) / 256), 256, 0, st>>>(partial, grid, (int)C, K,
+                                                                         ggamma, gbeta, grbias);
   return check_launch("layernorm_param_grad_final");
 }
 
@@ -373,13 +419,13 @@ extern "C" int csb200_add_layernorm_fwd(const void* x, const void* residual, voi
 
 extern "C" size_t csb200_layernorm_bwd_workspace_bytes(int64_t rows, int64_t channels) {
   (void)rows;
-  return (size_t)LN_MAX_GRID * 2 * (size_t)channels * sizeof(float) + 256;  // per-CTA partials
+  return (size_t)LN_MAX_GRID * 3 * (size_t)channels * sizeof(float) + 256;  // per-CTA partials
 }
 
 static int ln_bwd_dispatch(const void* x, const void* grad_y, const void* grad_res, const float* gamma,
                            const float* stats, void* grad_x, float* grad_gamma, float* grad_beta,
-                           void* workspace, size_t workspace_bytes, int64_t rows, int64_t channels,
-                           int x_dtype, int gy_dtype, void* stream) {
+                           float* grad_res_bias, void* workspace, size_t workspace_bytes, int64_t rows,
+                           int64_t channels, int x_dtype, int gy_dtype, void* stream) {
   if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(gy_dtype))
     return fail(CSB200_ERR_INVALID, "layernorm_bwd: bad size or dtype");
   if (!x || !grad_y || !gamma || !stats || !grad_x || !grad_gamma || !grad_beta || !workspace)
@@ -391,20 +437,21 @@ static int ln_bwd_dispatch(const void* x, const void* grad_y, const void* grad_r
   if (rows == 0) {
     CSB200_CUDA(cudaMemsetAsync(grad_gamma, 0, channels * sizeof(float), st));
     CSB200_CUDA(cudaMemsetAsync(grad_beta, 0, channels * sizeof(float), st));
+    if (grad_res_bias) CSB200_CUDA(cudaMemsetAsync(grad_res_bias, 0, channels * sizeof(float), st));
     return CSB200_OK;
   }
   // grad_x (and grad_res) have the type of x
   if (x_dtype == CSB200_F32)
     return gy_dtype == CSB200_F32
                ? ln_bwd_t<float, float, float>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma,
-                                               grad_beta, partial, rows, channels, st)
+                                               grad_beta, grad_res_bias, partial, rows, channels, st)
                : ln_bwd_t<float, bf16, float>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma,
-                                              grad_beta, partial, rows, channels, st);
+                                              grad_beta, grad_res_bias, partial, rows, channels, st);
   return gy_dtype == CSB200_F32
              ? ln_bwd_t<bf16, float, bf16>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma, grad_beta,
-                                           partial, rows, channels, st)
+                                           grad_res_bias, partial, rows, channels, st)
              : ln_bwd_t<bf16, bf16, bf16>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma, grad_beta,
-                                          partial, rows, channels, st);
+                                          grad_res_bias, partial, rows, channels, st);
 }
 
 extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const float* gamma,
@@ -412,7 +459,7 @@ extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const flo
                                     float* grad_beta, void* workspace, size_t workspace_bytes,
                                     int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
                                     void* stream) {
-  return ln_bwd_dispatch(x, grad_y, nullptr, gamma, stats, grad_x, grad_gamma, grad_beta, workspace,
+  return ln_bwd_dispatch(x, grad_y, nullptr, gamma, stats, grad_x, grad_gamma, grad_beta, nullptr, workspace,
                          workspace_bytes, rows, channels, x_dtype, gy_dtype, stream);
 }
 
@@ -421,6 +468,16 @@ extern "C" int csb200_add_layernorm_bwd(const void* sum, const void* grad_y, con
                                         float* grad_gamma, float* grad_beta, void* workspace,
                                         size_t workspace_bytes, int64_t rows, int64_t channels, int x_dtype,
                                         int gy_dtype, void* stream) {
-  return ln_bwd_dispatch(sum, grad_y, grad_sum, gamma, stats, grad_x, grad_gamma, grad_beta, workspace,
+  return ln_bwd_dispatch(sum, grad_y, grad_sum, gamma, stats, grad_x, grad_gamma, grad_beta, nullptr, workspace,
                          workspace_bytes, rows, channels, x_dtype, gy_dtype, stream);
+}
+
+extern "C" int csb200_add_layernorm_bwd_rb(const void* sum, const void* grad_y, const void* grad_sum,
+                                           const float* gamma, const float* stats, void* grad_x,
+                                           float* grad_gamma, float* grad_beta, float* grad_res_bias,
+                                           void* workspace, size_t workspace_bytes, int64_t rows,
+                                           int64_t channels, int x_dtype, int gy_dtype, void* stream) {
+  if (!grad_res_bias) return fail(CSB200_ERR_INVALID, "add_layernorm_bwd_rb: null pointer");
+  return ln_bwd_dispatch(sum, grad_y, grad_sum, gamma, stats, grad_x, grad_gamma, grad_beta, grad_res_bias,
+                         workspace, workspace_bytes, rows, channels, x_dtype, gy_dtype, stream);
 }

@@ -181,11 +181,16 @@ class _LayerNormFn(torch.autograd.Function):
 
 class _AddLayerNormFn(torch.autograd.Function):
     """(s, y) = (x + r, LayerNorm(x + r)) in one pass; backward folds the gradient arriving on s into
-    the LayerNorm backward pass (csb200_add_layernorm_fwd / _bwd)."""
+    the LayerNorm backward pass (csb200_add_layernorm_fwd / _bwd).
+
+    ``r_bias``: when r is the output of a Linear whose bias gradient was deferred (``linear(...,
+    defer_bias_grad=True)``), its bias parameter.  The forward value is not touched (the GEMM already
+    added the bias); backward returns its gradient — the column sums of grad_r, accumulated by the same
+    LayerNorm backward pass — so no column-sum pass over that tensor runs."""
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, x, r, weight, bias, eps, out_dtype):
+    def forward(ctx, x, r, weight, bias, eps, out_dtype, r_bias=None):
         capi.require_cuda(x, r)
         x, r = x.contiguous(), r.contiguous()
         C = x.shape[-1]
@@ -200,6 +205,7 @@ class _AddLayerNormFn(torch.autograd.Function):
                 _ptr(x), _ptr(r), _ptr(s), _ptr(w), _ptr(b), _ptr(y), _ptr(stats), rows, C, capi.dtype_code(x),
                 capi.dtype_code(y), float(eps), _vp(capi.stream_of(x))), "csb200_add_layernorm_fwd")
         ctx.save_for_backward(s, w, stats)
+        ctx.rb_dtype = None if r_bias is None else r_bias.dtype
         return s, y
 
     @staticmethod
@@ -208,27 +214,63 @@ class _AddLayerNormFn(torch.autograd.Function):
         s, w, stats = ctx.saved_tensors
         C = s.shape[-1]
         rows = s.numel() // C
+        want_rb = ctx.rb_dtype is not None and ctx.needs_input_grad[6]
         if gy is None:  # the normalised branch was unused: only the residual stream carries gradient
-            return gs, gs, None, None, None, None
+            grb = None
+            if want_rb and gs is not None:
+                grb = _bias_grad(gs.reshape(rows, C).contiguous(), C).to(ctx.rb_dtype)
+            return gs, gs, None, None, None, None, grb
         gy = gy.contiguous()
         gres = None if gs is None else gs.to(s.dtype).contiguous()
         gx = torch.empty_like(s)
         gw, gb = torch.empty_like(w), torch.empty_like(w)
+        grb = torch.empty_like(w) if want_rb else None
         lib = capi.lib()
         nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
         wsp = torch.empty(nws, dtype=torch.uint8, device=s.device)
         nbytes = s.numel() * ((2 + (gres is not None)) * s.element_size() + gy.element_size())
         with torch.cuda.device(s.device), _span("layernorm_bwd", nbytes):
-            capi.check(lib.csb200_add_layernorm_bwd(
-                _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(wsp), nws,
-                rows, C, capi.dtype_code(s), capi.dtype_code(gy), _vp(capi.stream_of(s))), "csb200_add_layernorm_bwd")
-        return gx, gx, gw, gb, None, None
+            if want_rb:
+                capi.check(lib.csb200_add_layernorm_bwd_rb(
+                    _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(grb),
+                    _ptr(wsp), nws, rows, C, capi.dtype_code(s), capi.dtype_code(gy), _vp(capi.stream_of(s))),
+                    "csb200_add_layernorm_bwd_rb")
+            else:
+                capi.check(lib.csb200_add_layernorm_bwd(
+                    _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(wsp),
+                    nws, rows, C, capi.dtype_code(s), capi.dtype_code(gy), _vp(capi.stream_of(s))),
+                    "csb200_add_layernorm_bwd")
+        return gx, gx, gw, gb, None, None, None if grb is None else grb.to(ctx.rb_dtype)
 
 
 def add_layer_norm(x: torch.Tensor, residual: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor,
-                   eps: float = 1e-5, out_dtype: Optional[torch.dtype] = None):
-    """Returns (x + residual, LayerNorm(x + residual)); both tensors have the shape of x."""
-    return _AddLayerNormFn.apply(x, residual, weight, bias, eps, out_dtype or x.dtype)
+                   eps: float = 1e-5, out_dtype: Optional[torch.dtype] = None,
+                   residual_bias: Optional[torch.Tensor] = None):
+    """Returns (x + residual, LayerNorm(x + residual)); both tensors have the shape of x.
+    ``residual_bias``: see ``_AddLayerNormFn`` (gradient routing of a deferred Linear bias)."""
+    return _AddLayerNormFn.apply(x, residual, weight, bias, eps, out_dtype or x.dtype, residual_bias)
+
+
+class _RouteBiasGradFn(torch.autograd.Function):
+    """Identity on `delta` that returns the column sums of its gradient to `bias`: the landing pad of a
+    deferred Linear bias gradient whose delta did not end in a fused add + LayerNorm."""
+
+    @staticmethod
+    def forward(ctx, delta, bias):
+        ctx.b_dtype = bias.dtype
+        return delta.view_as(delta)
+
+    @staticmethod
+    def backward(ctx, g):
+        n = g.shape[-1]
+        g2 = g.reshape(-1, n)
+        if not g2.is_contiguous():
+            g2 = g2.contiguous()
+        return g, _bias_grad(g2, n).to(ctx.b_dtype)
+
+
+def route_bias_grad(delta: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    return delta if bias is None else _RouteBiasGradFn.apply(delta, bias)
 
 
 def layer_norm_supported(x: torch.Tensor) -> bool:
@@ -325,8 +367,13 @@ class _LinearFn(torch.autograd.Function):
         return gx, gw, gb, None
 
 
-def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
-    """Drop-in for ``F.linear`` on CUDA float32 / bfloat16 tensors (autocast aware)."""
+def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
+           defer_bias_grad: bool = False) -> torch.Tensor:
+    """Drop-in for ``F.linear`` on CUDA float32 / bfloat16 tensors (autocast aware).
+    ``defer_bias_grad``: the bias enters detached (no column-sum pass in backward); the CALLER must hand
+    the output and the bias to ``add_layer_norm(..., residual_bias=bias)`` or ``route_bias_grad``."""
+    if defer_bias_grad and bias is not None:
+        bias = bias.detach()
     if not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
         return torch.nn.functional.linear(x, weight, bias)
     dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype

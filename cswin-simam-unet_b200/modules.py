@@ -49,32 +49,48 @@ def apply_norm(norm: nn.Module, x: torch.Tensor, feeds_gemm: bool = False) -> to
     return norm(x)
 
 
-def apply_add_norm(norm: nn.Module, x: torch.Tensor, delta: torch.Tensor, feeds_gemm: bool = False):
+def apply_add_norm(norm: nn.Module, x: torch.Tensor, delta: torch.Tensor, feeds_gemm: bool = False,
+                   delta_bias: Optional[torch.Tensor] = None):
     """(x + delta, norm(x + delta)).  With a plain LayerNorm on a tiled width the residual add rides in
     the LayerNorm kernel (one pass instead of an add kernel plus a norm kernel, and in backward the
-    residual-stream gradient is summed inside the LayerNorm backward pass)."""
+    residual-stream gradient is summed inside the LayerNorm backward pass).  ``delta_bias``: the bias of
+    the Linear that produced `delta` with ``defer_bias_grad`` — its gradient is returned by the same
+    backward pass (or by a column-sum pass on the fallback path)."""
     if type(norm) is nn.LayerNorm and x.is_cuda and delta.dtype == x.dtype and delta.shape == x.shape \
             and len(norm.normalized_shape) == 1 and norm.elementwise_affine and norm.bias is not None \
             and csbF.layer_norm_supported(x):
         out_dtype = x.dtype
         if feeds_gemm and torch.is_autocast_enabled("cuda"):
             out_dtype = torch.get_autocast_dtype("cuda")
-        return csbF.add_layer_norm(x, delta, norm.weight, norm.bias, norm.eps, out_dtype)
-    s = x + delta
+        return csbF.add_layer_norm(x, delta, norm.weight, norm.bias, norm.eps, out_dtype, delta_bias)
+    s = x + csbF.route_bias_grad(delta, delta_bias)
     return s, apply_norm(norm, s, feeds_gemm)
+
+
+def _can_defer_bias(lin: nn.Module, x: torch.Tensor, *between: nn.Module) -> bool:
+    """The bias gradient of `lin` can ride in the LayerNorm backward pass that consumes its output iff the
+    output reaches the residual add unchanged (every module in between is an identity in this mode)."""
+    if type(lin) is not nn.Linear or lin.bias is None or not x.is_cuda or not lin.bias.requires_grad \
+            or not torch.is_grad_enabled():
+        return False
+    for m in between:
+        if isinstance(m, nn.Identity) or (isinstance(m, nn.Dropout) and (m.p == 0.0 or not m.training)):
+            continue
+        return False
+    return True
 
 
 def run_blocks(blocks, x: torch.Tensor) -> torch.Tensor:
     """A stage of CSWinBlocks with every residual add fused into the LayerNorm that follows it: the
     Mlp branch of block i is added inside norm1 of block i + 1 (only the last add stays a plain add)."""
-    pending = None
+    pending, pending_bias = None, None
     for blk in blocks:
         if isinstance(blk, CSWinBlock):
-            x, pending = blk.forward_fused(x, pending)
+            x, pending, pending_bias = blk.forward_fused(x, pending, pending_bias)
         else:
-            x = blk(x if pending is None else x + pending)
-            pending = None
-    return x if pending is None else x + pending
+            x = blk(x if pending is None else x + csbF.route_bias_grad(pending, pending_bias))
+            pending, pending_bias = None, None
+    return x if pending is None else x + csbF.route_bias_grad(pending, pending_bias)
 
 
 def apply_conv(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
@@ -86,10 +102,11 @@ def apply_conv(conv: nn.Module, x: torch.Tensor) -> torch.Tensor:
     return conv(x)
 
 
-def apply_linear(lin: nn.Module, x: torch.Tensor) -> torch.Tensor:
+def apply_linear(lin: nn.Module, x: torch.Tensor, defer_bias_grad: bool = False) -> torch.Tensor:
     """A plain ``nn.Linear`` runs through csbF.linear (cuBLAS GEMMs + one-pass bias gradient)."""
     if type(lin) is nn.Linear and x.is_cuda:
-        return csbF.linear(x, lin.weight, lin.bias)
+        return csbF.linear(x, lin.weight, lin.bias, defer_bias_grad)
+    assert not defer_bias_grad
     return lin(x)
 
 
@@ -137,13 +154,13 @@ class Mlp(nn.Module):
         self.fc2 = nn.Linear(hidden_features or in_features, out_features or in_features)
         self.drop = nn.Dropout(drop)
 
-    def forward(self, x):
+    def forward(self, x, defer_fc2_bias_grad: bool = False):
         if type(self.fc1) is nn.Linear and type(self.act) is nn.GELU and self.act.approximate == "none" \
                 and csbF.linear_gelu_supported(x, self.fc1.weight, self.fc1.bias):
             hidden = csbF.linear_gelu(x, self.fc1.weight, self.fc1.bias)  # fc1 + GELU, fused passes
         else:
             hidden = self.act(apply_linear(self.fc1, x))
-        return self.drop(apply_linear(self.fc2, self.drop(hidden)))
+        return self.drop(apply_linear(self.fc2, self.drop(hidden), defer_fc2_bias_grad))
 
 
 class LePEAttention(nn.Module):
@@ -235,24 +252,31 @@ class CSWinBlock(nn.Module):
             params += [att.get_v.weight, att.get_v.bias]
         return csbF.cross_stripe_attention(qkv, reso, reso, branches, self._scale, params, self.attns[0].engine)
 
-    def forward_fused(self, x, pending=None):
-        """The block with its LAST residual add left pending: returns (x', delta) with
-        block(x + pending) == x' + delta, so the caller can fuse `+ delta` into the next pre-norm."""
+    def forward_fused(self, x, pending=None, pending_bias=None):
+        """The block with its LAST residual add left pending: returns (x', delta, delta_bias) with
+        block(x + pending) == x' + delta, so the caller can fuse `+ delta` into the next pre-norm.
+        ``delta_bias`` (and ``pending_bias`` on the way in) is the bias of the Linear that produced the
+        delta when its gradient has been deferred to the consumer of the delta (else None): the caller
+        MUST pass both on to ``apply_add_norm`` / ``csbF.route_bias_grad``."""
         B, L, C = x.shape
         if L != self.patches_resolution ** 2:
             raise AssertionError("flatten img_tokens has wrong size")
         if pending is None:
             n1 = apply_norm(self.norm1, x, feeds_gemm=True)
         else:
-            x, n1 = apply_add_norm(self.norm1, x, pending, feeds_gemm=True)
-        attended = apply_linear(self.proj, self.attend(apply_linear(self.qkv, n1)))
+            x, n1 = apply_add_norm(self.norm1, x, pending, feeds_gemm=True, delta_bias=pending_bias)
         # proj_drop exists but is never applied in the reference (C:366-367)
-        x, n2 = apply_add_norm(self.norm2, x, self.drop_path(attended), feeds_gemm=True)
-        return x, self.drop_path(self.mlp(n2))
+        defer = _can_defer_bias(self.proj, x, self.drop_path)
+        attended = apply_linear(self.proj, self.attend(apply_linear(self.qkv, n1)), defer)
+        x, n2 = apply_add_norm(self.norm2, x, self.drop_path(attended), feeds_gemm=True,
+                               delta_bias=self.proj.bias if defer else None)
+        if type(self.mlp) is Mlp and _can_defer_bias(self.mlp.fc2, x, self.mlp.drop, self.drop_path):
+            return x, self.drop_path(self.mlp(n2, defer_fc2_bias_grad=True)), self.mlp.fc2.bias
+        return x, self.drop_path(self.mlp(n2)), None
 
     def forward(self, x):
-        x, delta = self.forward_fused(x)
-        return x + delta
+        x, delta, delta_bias = self.forward_fused(x)
+        return x + csbF.route_bias_grad(delta, delta_bias)
 
 
 class Merge_Block(nn.Module):

@@ -107,6 +107,14 @@ CSB200_API int csb200_add_layernorm_bwd(const void* sum, const void* grad_y, con
                                         float* grad_gamma, float* grad_beta, void* workspace,
                                         size_t workspace_bytes, int64_t rows, int64_t channels,
                                         int x_dtype, int gy_dtype, void* stream);
+/* Same pass, which also returns grad_res_bias[c] = sum over rows of grad_x[r][c] (fp32): when `residual`
+ * was the output of a Linear (proj C:366 -> C:367, Mlp.fc2 C:195 -> C:369) that is the bias gradient of
+ * that Linear, which then needs no column-sum pass over the same tensor. */
+CSB200_API int csb200_add_layernorm_bwd_rb(const void* sum, const void* grad_y, const void* grad_sum,
+                                           const float* gamma, const float* stats, void* grad_x,
+                                           float* grad_gamma, float* grad_beta, float* grad_res_bias,
+                                           void* workspace, size_t workspace_bytes, int64_t rows,
+                                           int64_t channels, int x_dtype, int gy_dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Column sums of a row-major [rows][cols] matrix (fp32 out) — the bias gradient of the Linear layers

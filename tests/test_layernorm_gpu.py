@@ -41,6 +41,42 @@ def test_layernorm_matches_fp64_reference(shape, x_dtype, out_dtype):
     assert rel_err(bd.grad.cpu(), b64.grad) < max(tol, 2e-5)
 
 
+@pytest.mark.parametrize("autocast", [False, True])
+@pytest.mark.parametrize("shape", [(2, 49, 64), (1, 784, 128), (4, 196, 256), (2, 49, 512)])
+def test_deferred_linear_bias_gradient_rides_in_the_layernorm_backward(shape, autocast, no_tf32):
+    """r = Linear(h) with defer_bias_grad, (s, y) = add_layer_norm(x, r, residual_bias=bias): every gradient,
+    the Linear's bias included, equals the unfused torch graph; no csb200_colsum launch is needed."""
+    torch.manual_seed(sum(shape) + 7)
+    C = shape[-1]
+    lin, ref = torch.nn.Linear(2 * C, C).cuda(), torch.nn.Linear(2 * C, C).cuda()
+    ref.load_state_dict(lin.state_dict())
+    norm, nref = torch.nn.LayerNorm(C).cuda(), torch.nn.LayerNorm(C).cuda()
+    dt = torch.bfloat16 if autocast else torch.float32
+    x = torch.randn(shape, device="cuda").to(dt)
+    h = torch.randn(*shape[:-1], 2 * C, device="cuda").to(dt)
+    gs, gy = torch.randn(shape, device="cuda").to(dt), torch.randn(shape, device="cuda").to(dt)
+    xa, ha, xb, hb = (t.clone().requires_grad_(True) for t in (x, h, x, h))
+    with torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+        r = modules.apply_linear(lin, ha, defer_bias_grad=True)
+        s, y = modules.apply_add_norm(norm, xa, r, feeds_gemm=True, delta_bias=lin.bias)
+        sb = xb + ref(hb)
+        yb = nref(sb)
+    torch.autograd.backward([s, y], [gs, gy.to(y.dtype)])
+    torch.autograd.backward([sb, yb], [gs, gy.to(yb.dtype)])
+    tol = 2e-2 if autocast else 2e-5
+    assert rel_err(lin.bias.grad.cpu(), ref.bias.grad.cpu()) < tol
+    assert rel_err(lin.weight.grad.cpu(), ref.weight.grad.cpu()) < tol
+    assert rel_err(norm.weight.grad.cpu(), nref.weight.grad.cpu()) < tol
+    assert rel_err(norm.bias.grad.cpu(), nref.bias.grad.cpu()) < tol
+    assert rel_err(xa.grad.float().cpu(), xb.grad.float().cpu()) < tol
+    assert rel_err(ha.grad.float().cpu(), hb.grad.float().cpu()) < tol
+    # the landing pad for deltas that do not end in a fused add + LayerNorm
+    lin.zero_grad()
+    r2 = csbF.route_bias_grad(modules.apply_linear(lin, h, defer_bias_grad=True), lin.bias)
+    (r2.float() * gs.float()).sum().backward()
+    assert rel_err(lin.bias.grad.cpu(), gs.float().reshape(-1, C).sum(0).cpu()) < tol
+
+
 def test_apply_norm_routes_and_falls_back():
     ln = torch.nn.LayerNorm(64).cuda()
     x = torch.randn(2, 50, 64, device="cuda")
