@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One profiled call of each hot kernel, bracketed by cudaProfilerStart/Stop, for
     ncu --set full --import-source on --clock-control none --profile-from-start off -o <rep> \\
-        python benchmarks/ncu_targets.py attn s3        # or: simam nchw | simam nlc | gelu | layernorm
+        python benchmarks/ncu_targets.py attn s3        # or: simam nchw | simam nlc | gelu | layernorm | carafe up3 | carafe x4
 Shapes are BASELINE config 3 (512^2, batch 32, bf16) call sites; config 2 for SimAM NCHW."""
 import os
 import sys
@@ -60,4 +60,11 @@ elif what == "layernorm":
         s, y = csbF.add_layer_norm(x, r, w, b, 1e-5, torch.bfloat16)
         torch.autograd.grad([s, y], [x, r, w, b], [torch.ones_like(s), torch.ones_like(y)])
     profiled(f)
+elif what == "carafe":
+    # decoder call sites of config 3: up3 = upsample3 (64 ch, 64^2 -> 128^2), x4 = the final 1-channel 128^2 -> 512^2
+    C, H, up = (64, 64, 2) if arg == "up3" else (1, 128, 4)
+    low = torch.randn(B, C, H, H, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    enc = torch.randn(B, 9 * up * up, H, H, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
+    g = torch.randn(B, C, H * up, H * up, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
+    profiled(lambda: torch.autograd.grad(csbF.carafe_reassemble(low, enc, up), [low, enc], g))
 print("done", what, arg)

@@ -13,7 +13,10 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
 @pytest.mark.parametrize("B,C,H,up", [(2, 64, 8, 2), (1, 128, 6, 2), (2, 256, 4, 2), (2, 1, 16, 4), (1, 8, 5, 4),
-                                      (1, 64, 16, 4), (3, 16, 7, 2)])
+                                      (1, 64, 16, 4), (3, 16, 7, 2),
+                                      # tiled kernels (W % 16 == 0): tile widths 16 / 32 / 64, 1..32 lanes per pixel
+                                      (1, 64, 32, 2), (1, 8, 64, 2), (1, 128, 16, 2), (1, 256, 16, 2), (1, 1, 128, 4),
+                                      (2, 1, 32, 2), (1, 16, 48, 4), (2, 64, 64, 2)])
 def test_reassembly_kernel_matches_torch_ops(B, C, H, up, dtype):
     torch.manual_seed(B + C + H + up)
     low = torch.randn(B, C, H, H).to(dtype)
