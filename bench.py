@@ -148,7 +148,10 @@ def run_ours(args, rank, local_rank, world):
     torch.manual_seed(0)  # identical replicas on every rank
     net = pkg.CSWinTransformer(img_size=IMG, split_size=SPLIT, simam=True, attn_engine=args.attn_engine).to(dev)
     use_graph = args.cuda_graph
-    opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
+    if args.optimizer == "csb200":  # C:937-941 AdamW(lr 1e-4, wd 1e-4) as one csb200_adam_step launch
+        opt = pkg.FusedAdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+    else:
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
     reducer = pkg.GradientAllReducer(net.parameters()) if world > 1 else None
     step = pkg.TrainStep(net, opt, precision="bf16", reducer=reducer, cuda_graph=use_graph)
     # the roofline needs CUDA events around individual kernels, which a graph replay cannot give:
@@ -286,7 +289,7 @@ def run_ours(args, rank, local_rank, world):
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"CSWin-SimAM-UNet train step {IMG}x{IMG} (BASELINE configs[2]; configs[3] at N=8)",
                    "global_batch": B * world, "batch_per_gpu": B, "split_size": SPLIT, "simam": "3 skip tensors (NLC)",
-                   "precision": "autocast bf16, fp32 master weights, fp32 sigmoid+BCE", "optimizer": "AdamW fused",
+                   "precision": "autocast bf16, fp32 master weights, fp32 sigmoid+BCE", "optimizer": "AdamW, one csb200_adam_step launch" if args.optimizer == "csb200" else "AdamW (torch fused)",
                    "dropout": 0.0, "parallelism": f"dp{world}", "attn_engine": args.attn_engine,
                    "cuda_graph": bool(use_graph),
                    "l2": "no explicit flush: one step streams several GB of activations (>> 126 MB L2)",
@@ -314,6 +317,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--attn-engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--optimizer", default="csb200", choices=["csb200", "torch"])
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=True)
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
     args = ap.parse_args()

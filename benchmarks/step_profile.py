@@ -18,7 +18,7 @@ torch.backends.cudnn.allow_tf32 = True
 torch.backends.cudnn.benchmark = True
 torch.manual_seed(0)
 net = pkg.CSWinTransformer(img_size=512, split_size=[1, 2, 8, 8], simam=True).to(dev)
-opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True)
+opt = pkg.FusedAdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
 step = pkg.TrainStep(net, opt, precision="bf16")
 x, y = pkg.synthetic_batch(32, 512, dev, seed=0)
 for _ in range(3):

@@ -15,5 +15,6 @@ from .modules import (CARAFE, CARAFE4, CSWinBlock, DropPath, LePEAttention, Merg
                       SimAM)
 from .train import TrainStep, bce_from_logits_as_probabilities, synthetic_batch  # noqa: F401
 from .data_parallel import GradientAllReducer, shard_of_global_batch  # noqa: F401
+from .optim import FusedAdamW, fused_adam  # noqa: F401
 
 __version__ = "0.1.0"

@@ -45,7 +45,7 @@ EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_coun
            "csb200_gelu_bwd_workspace_bytes", "csb200_gelu_bwd", "csb200_carafe_supported", "csb200_carafe_fwd",
            "csb200_carafe_bwd", "csb200_stripe_attn_engine", "csb200_stripe_attn_fwd",
            "csb200_stripe_attn_bwd_workspace_bytes", "csb200_stripe_attn_bwd", "csb200_cross_stripe_attn_fwd",
-           "csb200_cross_stripe_attn_bwd")
+           "csb200_cross_stripe_attn_bwd", "csb200_adam_chunk_elems", "csb200_adam_step")
 
 
 def lib() -> ctypes.CDLL:
@@ -80,6 +80,9 @@ def lib() -> ctypes.CDLL:
         L.csb200_add_layernorm_bwd.restype = ctypes.c_int
         L.csb200_add_layernorm_bwd_rb.argtypes = [vp] * 10 + [ctypes.c_size_t, i64, i64, ctypes.c_int, ctypes.c_int, vp]
         L.csb200_add_layernorm_bwd_rb.restype = ctypes.c_int
+        L.csb200_adam_chunk_elems.restype = ctypes.c_int64
+        L.csb200_adam_step.argtypes = [vp, vp, i64, vp, vp, vp]
+        L.csb200_adam_step.restype = ctypes.c_int
         L.csb200_colsum_supported.argtypes = [i64, ctypes.c_int]
         L.csb200_colsum_supported.restype = ctypes.c_int
         L.csb200_colsum_workspace_bytes.argtypes = [i64]

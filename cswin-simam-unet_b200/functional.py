@@ -311,7 +311,12 @@ def shadow_params(params, dtype=torch.bfloat16):
     shadows = []
     with torch.no_grad():
         for p in masters:
-            sh = p.detach().to(dtype)
+            old = getattr(p, "_csb_shadow", None)
+            if old is not None and old[0].dtype == dtype and old[0].shape == p.shape and old[0].device == p.device:
+                sh = old[0]  # keep the tensor: an optimizer kernel or a captured graph may write to it
+                sh.copy_(p)
+            else:
+                sh = p.detach().to(dtype)
             p._csb_shadow = (sh, p._version)
             shadows.append(sh)
     return masters, shadows

@@ -70,7 +70,9 @@ class TrainStep:
             if self._shadow is None:
                 params = [p for g in self.optimizer.param_groups for p in g["params"]]
                 self._shadow = csbF.shadow_params(params)
-            else:
+                if getattr(self.optimizer, "writes_shadows", False):
+                    self.optimizer.attach_shadows(*self._shadow)  # csb200_adam_step refreshes them from now on
+            elif not getattr(self.optimizer, "writes_shadows", False):
                 csbF.refresh_shadows(*self._shadow)
 
     def _autocast(self, device_type: str):
@@ -144,8 +146,11 @@ class TrainStep:
         if slot is not None:
             self._mark_consumed(slot)  # the graph reads its own static copies from here on
         self._graph.replay()
-        if self._graph_opt is not None:  # data parallel: gradients are averaged between the two graphs
-            self.reducer.finish_step()
+        if self._graph_opt is not None:
+            if self.reducer is not None:  # data parallel: gradients are averaged between the two graphs
+                self.reducer.finish_step()
+            if hasattr(self.optimizer, "sync_hyperparameters"):
+                self.optimizer.sync_hyperparameters()  # a scheduler may have changed lr since the capture
             self._graph_opt.replay()
         return self._loss
 
@@ -173,10 +178,25 @@ class TrainStep:
                 csbF.refresh_shadows(*self._shadow)
         self._graph = torch.cuda.CUDAGraph()
         self._graph_opt = None
-        if self.reducer is None:
+        own_tables = hasattr(self.optimizer, "prepare")  # csb200 FusedAdamW: pointer tables built on the host
+        if self.reducer is None and not own_tables:
             self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(self._graph):
                 self._loss = self._eager_step(self._x, self._y)
+            return
+        if self.reducer is None:
+            # graph 1 = forward + backward (its gradient buffers keep their addresses over replays),
+            # host: pointer tables for exactly those buffers, graph 2 = the one-launch optimizer step
+            self.optimizer.zero_grad(set_to_none=True)
+            with torch.cuda.graph(self._graph):
+                loss = self.forward_loss(self._x, self._y)
+                loss.backward()
+                self._loss = loss.detach()
+            self.optimizer.prepare(freeze=True)
+            torch.cuda.synchronize(dev)
+            self._graph_opt = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
+                self._optimizer_step()
             return
         # Data parallel: graph 1 = zero the flat gradient buckets + forward + backward, then the
         # bucket all-reduces are issued eagerly (a handful of NCCL calls on static buffers; 94 MB is
@@ -187,6 +207,9 @@ class TrainStep:
             loss = self.forward_loss(self._x, self._y)
             loss.backward()
             self._loss = loss.detach()
+        if own_tables:
+            self.optimizer.prepare(freeze=True)
+            torch.cuda.synchronize(dev)
         self._graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
             self._optimizer_step()

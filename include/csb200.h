@@ -145,6 +145,31 @@ CSB200_API int csb200_gelu_bwd(const void* grad_out, const void* h, void* grad_h
                                int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Optimizer step for every parameter tensor of the model in one launch — `optimizer.step()` of the
+ * reference train loop (C:786) with torch.optim.AdamW (C:937-941, decoupled decay) or torch.optim.Adam
+ * (U:486-490, L2 decay); fp32 parameters, gradients and moments.  `shadow` (nullable) receives the bf16
+ * rounding of the updated parameter in the same pass.
+ *   tensors_dev : device array of csb200_adam_tensor
+ *   chunks_dev  : device array of n_chunks (tensor index, chunk index) int32 pairs; a chunk is
+ *                 csb200_adam_chunk_elems() consecutive elements of one tensor
+ *   hyper_dev   : device array [groups][8] = {lr, beta1, beta2, eps, weight_decay, decoupled (0/1), -, -}
+ *   step_dev    : device scalar, the step count INCLUDING this step (1 on the first call)
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct csb200_adam_tensor {
+  void* param;
+  const void* grad;
+  void* exp_avg;
+  void* exp_avg_sq;
+  void* shadow;
+  int64_t numel;
+  int32_t group;
+  int32_t reserved;
+} csb200_adam_tensor;
+CSB200_API int64_t csb200_adam_chunk_elems(void);
+CSB200_API int csb200_adam_step(const csb200_adam_tensor* tensors_dev, const int32_t* chunks_dev,
+                                int64_t n_chunks, const float* hyper_dev, const float* step_dev, void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Fused CARAFE reassembly — CARAFE.forward C:406-431 / CARAFE4 C:455-480 without the pixel-shuffled
  * logits, the fp32 softmax tensor, the 9x unfold and the batched 9 x up^2 matmul:
  *   out[b, h*up+dy, w*up+dx, c] = sum_tap softmax_tap(enc[b, h, w, tap*up^2 + dy*up + dx])
