@@ -60,9 +60,7 @@ __global__ void __launch_bounds__(256)
     colsum_final(const float* __restrict__ partial, int blocks, int cols, float* __restrict__ out) {
   const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= cols) return;
-  float a = 0.f;
-  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * cols + i];
-  a = warp_sum(a);
+  const float a = strided_partial_sum(partial + i, blocks, cols, lane);
   if (lane == 0) out[i] = a;
 }
 

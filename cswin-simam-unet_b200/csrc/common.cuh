@@ -159,6 +159,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   return v;
 }
 
+// Sum of p[b * stride] over b = lane, lane + 32, ... < n followed by a warp reduction: the last stage of the
+// deterministic two-stage reductions (per-CTA partials -> one warp per output).  Four independent
+// accumulators: the loads are L2 hits ~600 ns apart when they depend on one another (n = 592 partials was
+// 19 serial round trips, 4.6-8 us for a kernel that moves 2 MB), fixed order -> deterministic.
+__device__ __forceinline__ float strided_partial_sum(const float* __restrict__ p, int n, int64_t stride, int lane) {
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int b = lane;
+  for (; b + 96 < n; b += 128) {
+    a0 += p[(int64_t)b * stride];
+    a1 += p[(int64_t)(b + 32) * stride];
+    a2 += p[(int64_t)(b + 64) * stride];
+    a3 += p[(int64_t)(b + 96) * stride];
+  }
+  for (; b < n; b += 32) a0 += p[(int64_t)b * stride];
+  return warp_sum((a0 + a1) + (a2 + a3));
+}
+
 // sigmoid with the precise expf (fp32 parity target is 1e-5 relative)
 __device__ __forceinline__ float sigmoidf_precise(float y) { return 1.f / (1.f + expf(-y)); }
 

@@ -284,9 +284,7 @@ __global__ void __launch_bounds__(256)
                                float* __restrict__ grbias) {
   const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= K * C) return;
-  float a = 0.f;
-  for (int b = lane; b < blocks; b += 32) a += partial[(int64_t)b * K * C + i];
-  a = warp_sum(a);
+  const float a = strided_partial_sum(partial + i, blocks, (int64_t)K * C, lane);
   if (lane == 0) {
     if (i < C) ggamma[i] = a;
     else if (i < 2 * C) gbeta[i - C] = a;

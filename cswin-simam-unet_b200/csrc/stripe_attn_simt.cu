@@ -498,9 +498,7 @@ __global__ void __launch_bounds__(256)
   const WgradFinal f = blockIdx.y ? f1 : f0;
   const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;  // (c, tap)
   if (i >= f.cp * 10) return;
-  float a = 0.f;
-  for (int b = lane; b < blocks; b += 32) a += f.partial[(int64_t)b * f.cp * 10 + i];
-  a = warp_sum(a);
+  const float a = strided_partial_sum(f.partial + i, blocks, (int64_t)f.cp * 10, lane);
   if (lane != 0) return;
   const int c = i / 10, tap = i % 10;
   if (tap == 9) f.gb[c] = a;

@@ -32,6 +32,19 @@ def test_descriptor_layout_matches_header():
     assert capi.StripeDesc.q_sb.offset == 40
 
 
+def test_adam_tensor_layout_and_cpu_refusal():
+    from cswin_simam_unet_b200 import optim
+    # csb200_adam_tensor: 5 pointers, int64 numel, 2 x int32
+    assert ctypes.sizeof(optim._AdamTensor) == 5 * 8 + 8 + 8 and optim._AdamTensor.numel.offset == 40
+    assert capi.lib().csb200_adam_chunk_elems() > 0
+    p = torch.nn.Parameter(torch.zeros(3))
+    p.grad = torch.ones(3)
+    with pytest.raises(RuntimeError, match="no CPU"):
+        optim.FusedAdamW([p]).step()
+    o = optim.fused_adam([p], lr=1e-3, weight_decay=1e-4)
+    assert o.param_groups[0]["decoupled"] is False and o.param_groups[0]["betas"] == (0.9, 0.999)
+
+
 def _desc(**kw):
     d = capi.StripeDesc()
     base = dict(dtype=capi.F32, batch=1, height=8, width=8, h_sp=8, w_sp=2, heads=1, head_dim=32, scale=0.1,
