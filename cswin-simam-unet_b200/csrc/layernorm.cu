@@ -65,6 +65,39 @@ __device__ __forceinline__ void load_n(const TIn* p, float (&f)[NE]) {
   }
 }
 
+// NE elements of T kept PACKED (16 or 8 bytes): what the software pipeline holds for the next row group —
+// a quarter of the registers of the unpacked fp32 form
+template <typename T, int NE>
+struct RawN {
+  static constexpr int WORDS = NE * (int)sizeof(T) / 4;
+  uint32_t w[WORDS];
+  __device__ __forceinline__ void load(const T* p) {
+    if constexpr (WORDS == 4) {
+      const uint4 u = ld_stream(p);
+      w[0] = u.x; w[1] = u.y; w[2] = u.z; w[3] = u.w;
+    } else {
+      const uint2 u = __ldg(reinterpret_cast<const uint2*>(p));
+      w[0] = u.x; w[1] = u.y;
+    }
+  }
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < WORDS; ++i) w[i] = 0u;
+  }
+  __device__ __forceinline__ void unpack_to(float (&f)[NE]) const {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int i = 0; i < NE; ++i) f[i] = __uint_as_float(w[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < NE / 2; ++i) {
+        f[2 * i] = __uint_as_float(w[i] << 16);
+        f[2 * i + 1] = __uint_as_float(w[i] & 0xffff0000u);
+      }
+    }
+  }
+};
+
 template <int LPR>
 __device__ __forceinline__ float row_sum(float v) {
 #pragma unroll
@@ -91,28 +124,41 @@ __global__ void __launch_bounds__(LN_THREADS)
     }
   const int64_t warp_global = (int64_t)blockIdx.x * LN_WARPS + (threadIdx.x >> 5);
   const int64_t warp_count = (int64_t)gridDim.x * LN_WARPS;
+  // Software pipeline: the loads of the NEXT row group are issued before this one is reduced, so every
+  // warp keeps two row groups in flight (one was ~70 % of the bytes in flight the HBM latency asks for).
+  RawN<TIn, NE> nx[CPL], nr[CPL];
+  auto fetch = [&](int64_t rr) {
+    const bool okn = rr < rows;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      nx[j].zero();
+      nr[j].zero();
+      if (okn) {
+        nx[j].load(x + rr * C + (j * LPR + lr) * NE);
+        if (res != nullptr) nr[j].load(res + rr * C + (j * LPR + lr) * NE);
+      }
+    }
+  };
+  fetch(warp_global * RPW + sub);
   for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warp_count * RPW) {
     const int64_t r = r0 + sub;
     const bool ok = r < rows;
-    float v[CPL][NE];
+    float v[CPL][NE], rv_[CPL][NE];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      if (ok) load_n<TIn, NE>(x + r * C + (j * LPR + lr) * NE, v[j]);
-      else
-#pragma unroll
-        for (int e = 0; e < NE; ++e) v[j][e] = 0.f;
+      nx[j].unpack_to(v[j]);
+      nr[j].unpack_to(rv_[j]);
     }
+    fetch(r + warp_count * RPW);
     if (res != nullptr && ok) {
       // fused residual add (C:367 / C:369 feeding the next pre-norm): s = x + res is written once, in
       // the stream's dtype, and the statistics are taken from the ROUNDED s — exactly what a separate
       // add kernel followed by this LayerNorm would produce
 #pragma unroll
       for (int j = 0; j < CPL; ++j) {
-        float rv[NE];
-        load_n<TIn, NE>(res + r * C + (j * LPR + lr) * NE, rv);
 #pragma unroll
         for (int e = 0; e < NE; ++e) {
-          v[j][e] += rv[e];
+          v[j][e] += rv_[j][e];
           if constexpr (sizeof(TIn) == 2) v[j][e] = __bfloat162float(__float2bfloat16_rn(v[j][e]));
         }
         store_n<TIn, NE>(sum_out + r * C + (j * LPR + lr) * NE, v[j]);
@@ -154,7 +200,7 @@ __global__ void __launch_bounds__(LN_THREADS)
 // Linear then needs no column-sum pass of its own.  The sums are taken over the ROUNDED values, i.e.
 // exactly what a separate pass over the stored tensor would see.
 template <typename TIn, typename TGy, typename TGx, int LPR, int CPL, int NE, bool RB>
-__global__ void __launch_bounds__(LN_THREADS)
+__global__ void __launch_bounds__(LN_THREADS, CPL == 1 ? 3 : 1)
     layernorm_bwd_kernel(const TIn* __restrict__ x, const TGy* __restrict__ gy,
                          const float* __restrict__ gamma, const float* __restrict__ stats,
                          const TGx* __restrict__ gres, TGx* __restrict__ gx, float* __restrict__ partial,
@@ -173,21 +219,35 @@ __global__ void __launch_bounds__(LN_THREADS)
     }
   const int64_t warp_global = (int64_t)blockIdx.x * LN_WARPS + warp;
   const int64_t warp_count = (int64_t)gridDim.x * LN_WARPS;
+  RawN<TIn, NE> nxv[CPL];
+  RawN<TGy, NE> ngv[CPL];
+  float nmean = 0.f, nrstd = 0.f;
+  auto fetch = [&](int64_t rr) {
+    const bool okn = rr < rows;
+#pragma unroll
+    for (int j = 0; j < CPL; ++j) {
+      nxv[j].zero();
+      ngv[j].zero();
+      if (okn) {
+        nxv[j].load(x + rr * C + (j * LPR + lr) * NE);
+        ngv[j].load(gy + rr * C + (j * LPR + lr) * NE);
+      }
+    }
+    nmean = okn ? __ldg(stats + 2 * rr) : 0.f;
+    nrstd = okn ? __ldg(stats + 2 * rr + 1) : 0.f;
+  };
+  fetch(warp_global * RPW + sub);
   for (int64_t r0 = warp_global * RPW; r0 < rows; r0 += warp_count * RPW) {
     const int64_t r = r0 + sub;
     const bool ok = r < rows;
     float xv[CPL][NE], gv[CPL][NE];
 #pragma unroll
     for (int j = 0; j < CPL; ++j) {
-      if (ok) {
-        load_n<TIn, NE>(x + r * C + (j * LPR + lr) * NE, xv[j]);
-        load_n<TGy, NE>(gy + r * C + (j * LPR + lr) * NE, gv[j]);
-      } else {
-#pragma unroll
-        for (int e = 0; e < NE; ++e) xv[j][e] = gv[j][e] = 0.f;
-      }
+      nxv[j].unpack_to(xv[j]);
+      ngv[j].unpack_to(gv[j]);
     }
-    const float mean = ok ? __ldg(stats + 2 * r) : 0.f, rstd = ok ? __ldg(stats + 2 * r + 1) : 0.f;
+    const float mean = nmean, rstd = nrstd;
+    fetch(r + warp_count * RPW);  // next row group in flight while this one is reduced
     float s1 = 0.f, s2 = 0.f;
 #pragma unroll
     for (int j = 0; j < CPL; ++j)
@@ -292,10 +352,10 @@ __global__ void __launch_bounds__(256)
   }
 }
 
-constexpr int LN_MAX_GRID = 148 * 4;  // persistent: 4 CTAs of 256 threads per B200 SM
-// the backward kernel that also sums the residual-bias gradient holds 16 more accumulators: 80 registers,
-// 3 CTAs per SM — a grid of 4 per SM would run as 1.33 waves
-constexpr int LN_MAX_GRID_RB = 148 * 3;
+constexpr int LN_MAX_GRID = 148 * 4;  // persistent: 4 CTAs of 256 threads per B200 SM (forward)
+// the backward kernels hold the gamma / beta (/ residual-bias) accumulators and the prefetched next row
+// group: 80 registers, 3 CTAs per SM (__launch_bounds__) — a grid of 4 per SM would run as 1.33 waves
+constexpr int LN_MAX_GRID_BWD = 148 * 3;
 int ln_grid(int64_t rows, int rpw, int max_grid = LN_MAX_GRID) {
   const int64_t need = (rows + (int64_t)rpw * LN_WARPS - 1) / ((int64_t)rpw * LN_WARPS);
   return (int)(need < max_grid ? (need > 0 ? need : 1) : max_grid);
@@ -344,7 +404,7 @@ int ln_bwd_t(const void* x, const void* gy, const void* gres, const float* gamma
   int lpr, cpl;
   if (!ln_shape<TIn>(C, &lpr, &cpl))
     return fail(CSB200_ERR_UNSUPPORTED, "layernorm: C=%lld is not tiled for this dtype", (long long)C);
-  const int grid = ln_grid(rows, 32 / lpr, grbias != nullptr ? LN_MAX_GRID_RB : LN_MAX_GRID);
+  const int grid = ln_grid(rows, 32 / lpr, cpl == 1 ? LN_MAX_GRID_BWD : 148);  // wide rows: 150+ registers, 1 CTA / SM
 #define CALL(L, P)                                                                       \
   do {                                                                                   \
     if (grbias != nullptr)                                                               \
