@@ -119,10 +119,15 @@ class FusedAdamW(torch.optim.Optimizer):
             for p in g["params"]:
                 if p.grad is None:
                     continue
-                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse \
-                        or not p.is_contiguous() or not p.grad.is_contiguous():
-                    raise RuntimeError("FusedAdamW needs contiguous fp32 CUDA parameters and gradients "
+                if not p.is_cuda or p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse:
+                    raise RuntimeError("FusedAdamW needs fp32 CUDA parameters and gradients "
                                        "(there is no CPU or mixed-dtype fallback)")
+                # the update is elementwise in STORAGE order: any dense layout works (contiguous, or
+                # channels-last conv weights) as long as parameter, gradient and moments share it
+                dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
+                if not dense or p.grad.stride() != p.stride():
+                    raise RuntimeError("FusedAdamW needs dense parameters whose gradients have the same strides "
+                                       f"(parameter {tuple(p.shape)}: strides {p.stride()} vs {p.grad.stride()})")
                 dev = dev or p.device
                 items.append((p, gi))
         return items, dev
