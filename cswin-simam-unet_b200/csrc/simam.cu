@@ -1572,122 +1572,122 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
   uint4* dst = nullptr;
   auto start_first = [&](int ph) {
     b1 = (int64_t)cid + (int64_t)ph * ncl;
-      const uint4* ximg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + b1 * image_bytes);
-      unpack<T>(__ldg(ximg + cv), pivot);  // row 0 of the image, this thread's channels
+    const uint4* ximg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + b1 * image_bytes);
+    unpack<T>(__ldg(ximg + cv), pivot);  // row 0 of the image, this thread's channels
 #pragma unroll
-      for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
+    for (int e = 0; e < VE; ++e) acc[0][e] = acc[1][e] = 0.f;
 #pragma unroll
-      for (int q = 0; q < NP; ++q) {
-        npivot2[q] = f2_make(-pivot[2 * q], -pivot[2 * q + 1]);
-        sum2[q] = sq2[q] = f2_splat(0.f);
-      }
+    for (int q = 0; q < NP; ++q) {
+      npivot2[q] = f2_make(-pivot[2 * q], -pivot[2 * q + 1]);
+      sum2[q] = sq2[q] = f2_splat(0.f);
+    }
   };
   auto start_second = [&](int ph) {
     const int64_t b2 = (int64_t)cid + (int64_t)(ph - 1) * ncl;
     dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(y) + b2 * image_bytes + rank * cta_bytes);
   };
   auto second_chunk = [&](int c) {
-        const int s = ring_s;
-        st_mbar_wait(&full[s], ring_par);
-        if (++ring_s == STAGES) {
-          ring_s = 0;
-          ring_par ^= 1u;
+    const int s = ring_s;
+    st_mbar_wait(&full[s], ring_par);
+    if (++ring_s == STAGES) {
+      ring_s = 0;
+      ring_par ^= 1u;
+    }
+    const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+#pragma unroll
+    for (int i = 0; i < VPC; ++i) {
+      const uint4 u = v[threadIdx.x + i * ST_CONSUMERS];
+      uint4 r;
+      if constexpr (BF) {
+        // y = hx tanh(t^2 / (8v) + 1/4) + hx, hx = x / 2, on packed pairs
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const f2_t x2 = f2_from_bf16x2(w[q]);
+          const f2_t t = f2_add(x2, nmean2[q]);
+          const f2_t th = f2_tanh(f2_fma(f2_mul(t, t), inv8v2[q], quarter2));
+          const f2_t hx = f2_mul(x2, half2);
+          float lo, hi;
+          f2_split(f2_fma(hx, th, hx), lo, hi);
+          o[q] = pack_bf16x2(lo, hi);
         }
-        const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+        r = make_uint4(o[0], o[1], o[2], o[3]);
+      } else {
+        float f[VE];
+        unpack<T>(u, f);
 #pragma unroll
-        for (int i = 0; i < VPC; ++i) {
-          const uint4 u = v[threadIdx.x + i * ST_CONSUMERS];
-          uint4 r;
-          if constexpr (BF) {
-            // y = hx tanh(t^2 / (8v) + 1/4) + hx, hx = x / 2, on packed pairs
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const f2_t x2 = f2_from_bf16x2(w[q]);
-              const f2_t t = f2_add(x2, nmean2[q]);
-              const f2_t th = f2_tanh(f2_fma(f2_mul(t, t), inv8v2[q], quarter2));
-              const f2_t hx = f2_mul(x2, half2);
-              float lo, hi;
-              f2_split(f2_fma(hx, th, hx), lo, hi);
-              o[q] = pack_bf16x2(lo, hi);
-            }
-            r = make_uint4(o[0], o[1], o[2], o[3]);
-          } else {
-            float f[VE];
-            unpack<T>(u, f);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) f[e] = simam_fwd_elem<T>(f[e], FwdCoef{piv2[e], dmean2[e], inv4v2[e]});
-            r = pack<T>(f);
-          }
-          st_stream_first(dst + (int64_t)(chunks - 1 - c) * (ST_CHUNK / 16) + threadIdx.x + i * ST_CONSUMERS, r, pol_first);
-        }
-        release(s);
+        for (int e = 0; e < VE; ++e) f[e] = simam_fwd_elem<T>(f[e], FwdCoef{piv2[e], dmean2[e], inv4v2[e]});
+        r = pack<T>(f);
+      }
+      st_stream_first(dst + (int64_t)(chunks - 1 - c) * (ST_CHUNK / 16) + threadIdx.x + i * ST_CONSUMERS, r, pol_first);
+    }
+    release(s);
   };
   auto first_chunk = [&](int c) {
-        const int s = ring_s;
-        st_mbar_wait(&full[s], ring_par);
-        if (++ring_s == STAGES) {
-          ring_s = 0;
-          ring_par ^= 1u;
-        }
-        const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+    const int s = ring_s;
+    st_mbar_wait(&full[s], ring_par);
+    if (++ring_s == STAGES) {
+      ring_s = 0;
+      ring_par ^= 1u;
+    }
+    const uint4* v = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
 #pragma unroll
-        for (int i = 0; i < VPC; ++i) {
-          const uint4 u = v[threadIdx.x + i * ST_CONSUMERS];
-          if constexpr (BF) {
-            const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const f2_t d = f2_add(f2_from_bf16x2(w[q]), npivot2[q]);
-              sum2[q] = f2_add(sum2[q], d);
-              sq2[q] = f2_fma(d, d, sq2[q]);
-            }
-          } else {
-            float f[VE];
-            unpack<T>(u, f);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) {
-              const float d = f[e] - pivot[e];
-              acc[0][e] += d;
-              acc[1][e] = fmaf(d, d, acc[1][e]);
-            }
-          }
-        }
-        release(s);
-  };
-  auto finish_first = [&](int ph) {
+    for (int i = 0; i < VPC; ++i) {
+      const uint4 u = v[threadIdx.x + i * ST_CONSUMERS];
       if constexpr (BF) {
+        const uint32_t w[4] = {u.x, u.y, u.z, u.w};
 #pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          f2_split(sum2[q], acc[0][2 * q], acc[0][2 * q + 1]);
-          f2_split(sq2[q], acc[1][2 * q], acc[1][2 * q + 1]);
+        for (int q = 0; q < 4; ++q) {
+          const f2_t d = f2_add(f2_from_bf16x2(w[q]), npivot2[q]);
+          sum2[q] = f2_add(sum2[q], d);
+          sq2[q] = f2_fma(d, d, sq2[q]);
         }
-      }
-      nl_reduce<VE, CVEC>(acc, st_smem, ph & 1, CL, rank);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        const float dmean = acc[0][e] / (float)L;
-        const float var = fmaxf(acc[1][e] - acc[0][e] * dmean, 0.f) / ((float)L - 1.f) + e_lambda;
-        acc[0][e] = dmean;
-        acc[1][e] = var;
-        piv2[e] = pivot[e];
-        dmean2[e] = dmean;
-        inv4v2[e] = 1.f / (4.f * var);
-      }
-#pragma unroll
-      for (int q = 0; q < NP; ++q) {
-        nmean2[q] = f2_make(-(pivot[2 * q] + acc[0][2 * q]), -(pivot[2 * q + 1] + acc[0][2 * q + 1]));
-        inv8v2[q] = f2_make(1.f / (8.f * acc[1][2 * q]), 1.f / (8.f * acc[1][2 * q + 1]));
-      }
-      if (stats != nullptr && rank == 0 && threadIdx.x < CVEC) {
-        const int64_t p0 = b1 * S::CW + cv * VE;
+      } else {
+        float f[VE];
+        unpack<T>(u, f);
 #pragma unroll
         for (int e = 0; e < VE; ++e) {
-          stats[2 * (p0 + e)] = acc[0][e];
-          stats[2 * (p0 + e) + 1] = acc[1][e];
+          const float d = f[e] - pivot[e];
+          acc[0][e] += d;
+          acc[1][e] = fmaf(d, d, acc[1][e]);
         }
       }
+    }
+    release(s);
+  };
+  auto finish_first = [&](int ph) {
+    if constexpr (BF) {
+#pragma unroll
+      for (int q = 0; q < NP; ++q) {
+        f2_split(sum2[q], acc[0][2 * q], acc[0][2 * q + 1]);
+        f2_split(sq2[q], acc[1][2 * q], acc[1][2 * q + 1]);
+      }
+    }
+    nl_reduce<VE, CVEC>(acc, st_smem, ph & 1, CL, rank);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      const float dmean = acc[0][e] / (float)L;
+      const float var = fmaxf(acc[1][e] - acc[0][e] * dmean, 0.f) / ((float)L - 1.f) + e_lambda;
+      acc[0][e] = dmean;
+      acc[1][e] = var;
+      piv2[e] = pivot[e];
+      dmean2[e] = dmean;
+      inv4v2[e] = 1.f / (4.f * var);
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      nmean2[q] = f2_make(-(pivot[2 * q] + acc[0][2 * q]), -(pivot[2 * q + 1] + acc[0][2 * q + 1]));
+      inv8v2[q] = f2_make(1.f / (8.f * acc[1][2 * q]), 1.f / (8.f * acc[1][2 * q + 1]));
+    }
+    if (stats != nullptr && rank == 0 && threadIdx.x < CVEC) {
+      const int64_t p0 = b1 * S::CW + cv * VE;
+#pragma unroll
+      for (int e = 0; e < VE; ++e) {
+        stats[2 * (p0 + e)] = acc[0][e];
+        stats[2 * (p0 + e) + 1] = acc[1][e];
+      }
+    }
   };
   if constexpr (!PIPE) {
     // one image per cluster: the two sweeps never overlap and their state shares registers
@@ -1755,145 +1755,145 @@ __global__ void __launch_bounds__(ST_CONSUMERS + 32, 1)
   uint4* dst = nullptr;
   auto start_first = [&](int ph) {
     b1 = (int64_t)cid + (int64_t)ph * ncl;
-      const uint4* ximg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + b1 * image_bytes);
-      unpack<T>(__ldg(ximg + cv), pivot);
-      const int64_t p0 = b1 * S::CW + cv * VE;
+    const uint4* ximg = reinterpret_cast<const uint4*>(reinterpret_cast<const uint8_t*>(x) + b1 * image_bytes);
+    unpack<T>(__ldg(ximg + cv), pivot);
+    const int64_t p0 = b1 * S::CW + cv * VE;
 #pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        dmean[e] = __ldg(stats + 2 * (p0 + e));
-        vv[e] = __ldg(stats + 2 * (p0 + e) + 1);
-        inv4v[e] = 1.f / (4.f * vv[e]);
-        acc[0][e] = acc[1][e] = 0.f;
-      }
+    for (int e = 0; e < VE; ++e) {
+      dmean[e] = __ldg(stats + 2 * (p0 + e));
+      vv[e] = __ldg(stats + 2 * (p0 + e) + 1);
+      inv4v[e] = 1.f / (4.f * vv[e]);
+      acc[0][e] = acc[1][e] = 0.f;
+    }
 #pragma unroll
-      for (int q = 0; q < NP; ++q) {
-        r1p[q] = r2p[q] = f2_splat(0.f);
-        nmean2[q] = f2_make(-(pivot[2 * q] + dmean[2 * q]), -(pivot[2 * q + 1] + dmean[2 * q + 1]));
-        inv8v2[q] = f2_make(0.5f * inv4v[2 * q], 0.5f * inv4v[2 * q + 1]);
-      }
+    for (int q = 0; q < NP; ++q) {
+      r1p[q] = r2p[q] = f2_splat(0.f);
+      nmean2[q] = f2_make(-(pivot[2 * q] + dmean[2 * q]), -(pivot[2 * q + 1] + dmean[2 * q + 1]));
+      inv8v2[q] = f2_make(0.5f * inv4v[2 * q], 0.5f * inv4v[2 * q + 1]);
+    }
   };
   auto start_second = [&](int ph) {
     const int64_t b2 = (int64_t)cid + (int64_t)(ph - 1) * ncl;
     dst = reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(gx) + b2 * image_bytes + rank * cta_bytes);
   };
   auto second_chunk = [&](int c) {
-        const int s = ring_s;
-        st_mbar_wait(&full[s], ring_par);
-        if (++ring_s == STAGES) {
-          ring_s = 0;
-          ring_par ^= 1u;
+    const int s = ring_s;
+    st_mbar_wait(&full[s], ring_par);
+    if (++ring_s == STAGES) {
+      ring_s = 0;
+      ring_par ^= 1u;
+    }
+    const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+    const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+#pragma unroll
+    for (int i = 0; i < VPC; ++i) {
+      const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
+      uint4 res;
+      if constexpr (BF) {
+        // grad_x = 0.5 g (1 + tanh) + t (4a k1 - k2) - c2 with k1 = 1/(8v); the pairs hold -4a
+        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
+          const f2_t t = f2_add(x2, nmean2_b[q]), dd = f2_mul(t, t);
+          const f2_t th = f2_tanh(f2_fma(dd, inv8v2_b[q], quarter2));
+          const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));
+          const f2_t hg = f2_mul(g2, half2);
+          const f2_t gs = f2_fma(hg, th, f2_add(hg, nc2_b[q]));
+          // t (-4a)(-k1) = t (na4 * inv8v) with the sign carried by nk2: t (na4 (-k1) - k2)
+          const f2_t r = f2_fma(t, f2_fma(f2_mul(na4, mone2), inv8v2_b[q], nk2_b[q]), gs);
+          float lo, hi;
+          f2_split(r, lo, hi);
+          o[q] = pack_bf16x2(lo, hi);
         }
-        const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
-        const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+        res = make_uint4(o[0], o[1], o[2], o[3]);
+      } else {
+        float fx[VE], fg[VE];
+        unpack<T>(ux, fx);
+        unpack<T>(ug, fg);
 #pragma unroll
-        for (int i = 0; i < VPC; ++i) {
-          const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
-          uint4 res;
-          if constexpr (BF) {
-            // grad_x = 0.5 g (1 + tanh) + t (4a k1 - k2) - c2 with k1 = 1/(8v); the pairs hold -4a
-            const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
-            uint32_t o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
-              const f2_t t = f2_add(x2, nmean2_b[q]), dd = f2_mul(t, t);
-              const f2_t th = f2_tanh(f2_fma(dd, inv8v2_b[q], quarter2));
-              const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));
-              const f2_t hg = f2_mul(g2, half2);
-              const f2_t gs = f2_fma(hg, th, f2_add(hg, nc2_b[q]));
-              // t (-4a)(-k1) = t (na4 * inv8v) with the sign carried by nk2: t (na4 (-k1) - k2)
-              const f2_t r = f2_fma(t, f2_fma(f2_mul(na4, mone2), inv8v2_b[q], nk2_b[q]), gs);
-              float lo, hi;
-              f2_split(r, lo, hi);
-              o[q] = pack_bf16x2(lo, hi);
-            }
-            res = make_uint4(o[0], o[1], o[2], o[3]);
-          } else {
-            float fx[VE], fg[VE];
-            unpack<T>(ux, fx);
-            unpack<T>(ug, fg);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) {
-              const float t = centred(fx[e], piv_b[e], dmean_b[e]), dd = t * t;
-              const float sg_ = Sig<T>::f(fmaf(dd, inv4v_b[e], 0.5f));
-              const float a = fg[e] * fx[e] * sg_ * (1.f - sg_);
-              fx[e] = fmaf(fg[e], sg_, 2.f * t * fmaf(a, inv4v_b[e], -c1_b[e])) - c2_b[e];
-            }
-            res = pack<T>(fx);
-          }
-          st_stream_first(dst + (int64_t)(chunks - 1 - c) * (HALF / 16) + threadIdx.x + i * ST_CONSUMERS, res, pol_first);
+        for (int e = 0; e < VE; ++e) {
+          const float t = centred(fx[e], piv_b[e], dmean_b[e]), dd = t * t;
+          const float sg_ = Sig<T>::f(fmaf(dd, inv4v_b[e], 0.5f));
+          const float a = fg[e] * fx[e] * sg_ * (1.f - sg_);
+          fx[e] = fmaf(fg[e], sg_, 2.f * t * fmaf(a, inv4v_b[e], -c1_b[e])) - c2_b[e];
         }
-        release(s);
+        res = pack<T>(fx);
+      }
+      st_stream_first(dst + (int64_t)(chunks - 1 - c) * (HALF / 16) + threadIdx.x + i * ST_CONSUMERS, res, pol_first);
+    }
+    release(s);
   };
   auto first_chunk = [&](int c) {
-        const int s = ring_s;
-        st_mbar_wait(&full[s], ring_par);
-        if (++ring_s == STAGES) {
-          ring_s = 0;
-          ring_par ^= 1u;
+    const int s = ring_s;
+    st_mbar_wait(&full[s], ring_par);
+    if (++ring_s == STAGES) {
+      ring_s = 0;
+      ring_par ^= 1u;
+    }
+    const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
+    const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+#pragma unroll
+    for (int i = 0; i < VPC; ++i) {
+      const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
+      if constexpr (BF) {
+        const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
+          const f2_t t = f2_add(x2, nmean2[q]), dd = f2_mul(t, t);
+          const f2_t th = f2_tanh(f2_fma(dd, inv8v2[q], quarter2));
+          const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));  // -4a = g x (tanh^2 - 1)
+          r1p[q] = f2_fma(na4, dd, r1p[q]);
+          r2p[q] = f2_fma(na4, t, r2p[q]);
         }
-        const uint4* vx = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK);
-        const uint4* vg = reinterpret_cast<const uint4*>(ring + s * ST_CHUNK + HALF);
+      } else {
+        float fx[VE], fg[VE];
+        unpack<T>(ux, fx);
+        unpack<T>(ug, fg);
 #pragma unroll
-        for (int i = 0; i < VPC; ++i) {
-          const uint4 ux = vx[threadIdx.x + i * ST_CONSUMERS], ug = vg[threadIdx.x + i * ST_CONSUMERS];
-          if constexpr (BF) {
-            const uint32_t wx[4] = {ux.x, ux.y, ux.z, ux.w}, wg[4] = {ug.x, ug.y, ug.z, ug.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const f2_t x2 = f2_from_bf16x2(wx[q]), g2 = f2_from_bf16x2(wg[q]);
-              const f2_t t = f2_add(x2, nmean2[q]), dd = f2_mul(t, t);
-              const f2_t th = f2_tanh(f2_fma(dd, inv8v2[q], quarter2));
-              const f2_t na4 = f2_mul(f2_mul(g2, x2), f2_fma(th, th, mone2));  // -4a = g x (tanh^2 - 1)
-              r1p[q] = f2_fma(na4, dd, r1p[q]);
-              r2p[q] = f2_fma(na4, t, r2p[q]);
-            }
-          } else {
-            float fx[VE], fg[VE];
-            unpack<T>(ux, fx);
-            unpack<T>(ug, fg);
-#pragma unroll
-            for (int e = 0; e < VE; ++e) {
-              const float t = centred(fx[e], pivot[e], dmean[e]), dd = t * t;
-              const float sg_ = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
-              const float a4 = 4.f * fg[e] * fx[e] * sg_ * (1.f - sg_);
-              acc[0][e] = fmaf(a4, dd, acc[0][e]);
-              acc[1][e] = fmaf(a4, t, acc[1][e]);
-            }
-          }
+        for (int e = 0; e < VE; ++e) {
+          const float t = centred(fx[e], pivot[e], dmean[e]), dd = t * t;
+          const float sg_ = Sig<T>::f(fmaf(dd, inv4v[e], 0.5f));
+          const float a4 = 4.f * fg[e] * fx[e] * sg_ * (1.f - sg_);
+          acc[0][e] = fmaf(a4, dd, acc[0][e]);
+          acc[1][e] = fmaf(a4, t, acc[1][e]);
         }
-        release(s);
+      }
+    }
+    release(s);
   };
   auto finish_first = [&](int ph) {
-      if constexpr (BF) {
-#pragma unroll
-        for (int q = 0; q < NP; ++q) {
-          float lo, hi;
-          f2_split(r1p[q], lo, hi);
-          acc[0][2 * q] = -lo;
-          acc[0][2 * q + 1] = -hi;
-          f2_split(r2p[q], lo, hi);
-          acc[1][2 * q] = -lo;
-          acc[1][2 * q + 1] = -hi;
-        }
-      }
-      nl_reduce<VE, CVEC>(acc, st_smem, ph & 1, CL, rank);
-#pragma unroll
-      for (int e = 0; e < VE; ++e) {
-        const float r1 = 0.25f * acc[0][e], r2 = 0.25f * acc[1][e];  // the sweeps accumulate 4 a
-        c1_b[e] = r1 * inv4v[e] / (vv[e] * (Lf - 1.f));              // R1 / (4 v^2 n)
-        c2_b[e] = 2.f / Lf * r2 * inv4v[e];                          // (2/L) R2
-        piv_b[e] = pivot[e];
-        dmean_b[e] = dmean[e];
-        inv4v_b[e] = inv4v[e];
-      }
+    if constexpr (BF) {
 #pragma unroll
       for (int q = 0; q < NP; ++q) {
-        nmean2_b[q] = nmean2[q];
-        inv8v2_b[q] = inv8v2[q];
-        nk2_b[q] = f2_make(-2.f * c1_b[2 * q], -2.f * c1_b[2 * q + 1]);
-        nc2_b[q] = f2_make(-c2_b[2 * q], -c2_b[2 * q + 1]);
+        float lo, hi;
+        f2_split(r1p[q], lo, hi);
+        acc[0][2 * q] = -lo;
+        acc[0][2 * q + 1] = -hi;
+        f2_split(r2p[q], lo, hi);
+        acc[1][2 * q] = -lo;
+        acc[1][2 * q + 1] = -hi;
       }
+    }
+    nl_reduce<VE, CVEC>(acc, st_smem, ph & 1, CL, rank);
+#pragma unroll
+    for (int e = 0; e < VE; ++e) {
+      const float r1 = 0.25f * acc[0][e], r2 = 0.25f * acc[1][e];  // the sweeps accumulate 4 a
+      c1_b[e] = r1 * inv4v[e] / (vv[e] * (Lf - 1.f));              // R1 / (4 v^2 n)
+      c2_b[e] = 2.f / Lf * r2 * inv4v[e];                          // (2/L) R2
+      piv_b[e] = pivot[e];
+      dmean_b[e] = dmean[e];
+      inv4v_b[e] = inv4v[e];
+    }
+#pragma unroll
+    for (int q = 0; q < NP; ++q) {
+      nmean2_b[q] = nmean2[q];
+      inv8v2_b[q] = inv8v2[q];
+      nk2_b[q] = f2_make(-2.f * c1_b[2 * q], -2.f * c1_b[2 * q + 1]);
+      nc2_b[q] = f2_make(-c2_b[2 * q], -c2_b[2 * q + 1]);
+    }
   };
   if constexpr (!PIPE) {
     // one image per cluster: the two sweeps never overlap and their state shares registers
