@@ -125,7 +125,8 @@ class FusedAdamW(torch.optim.Optimizer):
                 # the update is elementwise in STORAGE order: any dense layout works (contiguous, or
                 # channels-last conv weights) as long as parameter, gradient and moments share it
                 dense = p.is_contiguous() or (p.dim() == 4 and p.is_contiguous(memory_format=torch.channels_last))
-                if not dense or p.grad.stride() != p.stride():
+                same = all(a == b for a, b, n in zip(p.stride(), p.grad.stride(), p.shape) if n > 1)  # size-1 dims: any stride
+                if not dense or not same:
                     raise RuntimeError("FusedAdamW needs dense parameters whose gradients have the same strides "
                                        f"(parameter {tuple(p.shape)}: strides {p.stride()} vs {p.grad.stride()})")
                 dev = dev or p.device
