@@ -235,6 +235,18 @@ def run_ours(args, rank, local_rank, world):
     ms_e2e = timed(step_e2e, args.steps)
     mem_gb = torch.cuda.max_memory_allocated(dev) / 2 ** 30
 
+    # data parallel: every rank must hold bit-identical weights after all those steps (same averaged
+    # gradients, same update) — a step that skipped its all-reduce would show up here, not in img/s
+    in_sync = None
+    if world > 1:
+        with torch.no_grad():
+            chk = torch.stack([p.detach().double().sum() for p in net.parameters()]).sum().reshape(1)
+        allchk = [torch.empty_like(chk) for _ in range(world)]
+        dist.all_gather(allchk, chk)
+        in_sync = all(torch.equal(c, allchk[0]) for c in allchk)
+        if not in_sync:
+            raise RuntimeError(f"replicas diverged: parameter checksums {[float(c) for c in allchk]}")
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -297,6 +309,7 @@ def run_ours(args, rank, local_rank, world):
         "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": int(launches), "host_issue_ms_per_step": round(host_issue_ms, 2),
+        "replicas_in_sync": in_sync,
         "clocks": clk.summary(),
         "roofline": roofline,
         "roofline_all": roof_all,

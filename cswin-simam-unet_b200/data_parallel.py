@@ -107,6 +107,9 @@ class GradientAllReducer:
             b.work.wait()
             if self._avg is None:
                 b.flat.div_(self.world)
+            # a captured train step replays backward WITHOUT calling begin_step() again: the next
+            # finish_step() must launch a fresh all-reduce, not wait on this finished one
+            b.work = None
 
     def gradient_bytes(self) -> int:
         return sum(b.flat.numel() * b.flat.element_size() for b in self.buckets)

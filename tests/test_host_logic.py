@@ -163,7 +163,16 @@ def _dp_worker(rank, world, port, overlap, q):
     for it in range(2):
         x, y = pkg.synthetic_batch(len(shard), 8, "cpu", seed=it, first_index=shard.start)
         step(x, y)
-    q.put((rank, [p.detach().numpy().copy() for p in model.parameters()], [p.grad.numpy().copy() for p in model.parameters()]))
+    params, grads = [p.detach().numpy().copy() for p in model.parameters()], [p.grad.numpy().copy() for p in model.parameters()]
+    # what a captured CUDA-graph step does: backward is REPLAYED into the buckets, begin_step() is not called
+    # again, finish_step() must still average (it used to wait on the finished all-reduce of the step before)
+    replay_ok = True
+    for it in range(2):
+        for b in red.buckets:
+            b.flat.fill_(float(rank + 1 + it))
+        red.finish_step()
+        replay_ok &= all(torch.allclose(b.flat, torch.full_like(b.flat, (1 + world) / 2 + it)) for b in red.buckets)
+    q.put((rank, params, grads, replay_ok))
     dist.barrier()
     dist.destroy_process_group()
 
@@ -189,7 +198,8 @@ def test_gradient_allreduce_matches_global_batch(overlap):
     for it in range(2):
         x, y = pkg.synthetic_batch(8, 8, "cpu", seed=it)
         step(x, y)
-    for (_, params, grads) in results:
+    for (_, params, grads, replay_ok) in results:
+        assert replay_ok
         for p, g, ref in zip(params, grads, model.parameters()):
             assert rel_err(p, ref.detach()) < 1e-5
             assert rel_err(g, ref.grad) < 1e-5
