@@ -198,7 +198,7 @@ class TrainStep:
             with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
                 self._optimizer_step()
             return
-        # Data parallel: graph 1 = zero the flat gradient buckets + forward + backward, then the
+        # Data parallel: graph 1 = forward + backward + packing the gradients into the flat buckets, then the
         # bucket all-reduces are issued eagerly (a handful of NCCL calls on static buffers; 94 MB is
         # < 1 ms on NVLink, so nothing is lost by not overlapping), graph 2 = optimizer step.
         self.reducer.overlap = False
@@ -206,6 +206,7 @@ class TrainStep:
             self.reducer.begin_step()
             loss = self.forward_loss(self._x, self._y)
             loss.backward()
+            self.reducer.pack()  # gradients -> flat buckets, inside the graph
             self._loss = loss.detach()
         if own_tables:
             self.optimizer.prepare(freeze=True)
@@ -216,7 +217,7 @@ class TrainStep:
 
     def _eager_step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         if self.reducer is not None:
-            self.reducer.begin_step()  # zeroes the flat gradient buckets (== zero_grad)
+            self.reducer.begin_step()  # == zero_grad(set_to_none=True)
         else:
             self.optimizer.zero_grad(set_to_none=True)
         loss = self.forward_loss(images, masks)
