@@ -37,6 +37,33 @@ class FusedAdamW(torch.optim.Optimizer):
         self._shadows = {}          # id(param) -> bf16 shadow written by the kernel
         self._frozen = {}           # pointer-set key -> tables owned by a captured CUDA graph
 
+    # ---- checkpoints --------------------------------------------------------------------------------
+    def load_state_dict(self, state_dict):
+        """torch's layout (one ``step`` per parameter): the kernel reads ONE device counter, restored here from
+        the loaded steps (they are equal for every parameter that has taken part in every step)."""
+        super().load_state_dict(state_dict)
+        for g in self.param_groups:  # a torch.optim.Adam(W) checkpoint: no "decoupled" key
+            if "decoupled" not in g:
+                g["decoupled"] = bool(g.get("decoupled_weight_decay", self.defaults["decoupled"]))
+        steps = [st["step"] for st in self.state.values() if "step" in st]
+        if steps:
+            first = steps[0]
+            dev = next(st["exp_avg"].device for st in self.state.values() if "exp_avg" in st)
+            value = float(first.item() if torch.is_tensor(first) else first)
+            if any(float(t.item() if torch.is_tensor(t) else t) != value for t in steps):
+                raise RuntimeError("FusedAdamW: parameters with different step counts are not supported")
+            self._steps = torch.full((), value, dtype=torch.float32, device=dev)
+            for st in self.state.values():
+                if "step" in st:
+                    st["step"] = self._steps
+            if self._hyper is None:
+                self._hyper_host = self._hyper_rows()
+                self._hyper = torch.tensor(self._hyper_host, dtype=torch.float32, device=dev)
+        self._table_key = None
+        if self._frozen:
+            raise RuntimeError("FusedAdamW: load_state_dict after a step has been captured in a CUDA graph "
+                               "(the graph holds the old moment buffers); load before the first captured step")
+
     # ---- bf16 shadows (functional.shadow_params) ------------------------------------------------
     def attach_shadows(self, masters, shadows):
         """From now on the kernel writes ``shadow <- bf16(master)`` for these pairs after every update."""

@@ -43,6 +43,19 @@ def test_adam_tensor_layout_and_cpu_refusal():
         optim.FusedAdamW([p]).step()
     o = optim.fused_adam([p], lr=1e-3, weight_decay=1e-4)
     assert o.param_groups[0]["decoupled"] is False and o.param_groups[0]["betas"] == (0.9, 0.999)
+    # checkpoints interchange with torch.optim.AdamW: per-parameter "step" entries collapse to ONE counter
+    q = [torch.nn.Parameter(torch.zeros(3)), torch.nn.Parameter(torch.zeros(2, 2))]
+    t = torch.optim.AdamW(q, lr=1e-3)
+    for v in q:
+        v.grad = torch.ones_like(v)
+    t.step(); t.step()
+    f = optim.FusedAdamW(q, lr=1e-3)
+    f.load_state_dict(t.state_dict())
+    assert float(f._steps) == 2.0 and all(f.state[v]["step"] is f._steps for v in q)
+    assert torch.equal(f.state[q[1]]["exp_avg"], t.state[q[1]]["exp_avg"])
+    back = torch.optim.AdamW(q, lr=1e-3)
+    back.load_state_dict(f.state_dict())
+    assert float(back.state[q[0]]["step"]) == 2.0
 
 
 def _desc(**kw):
