@@ -244,8 +244,10 @@ def run_ours(args, rank, local_rank, world):
         allchk = [torch.empty_like(chk) for _ in range(world)]
         dist.all_gather(allchk, chk)
         in_sync = all(torch.equal(c, allchk[0]) for c in allchk)
-        if not in_sync:
-            raise RuntimeError(f"replicas diverged: parameter checksums {[float(c) for c in allchk]}")
+        vals = [float(c) for c in allchk]
+        spread = (max(vals) - min(vals)) / max(abs(vals[0]), 1e-30)
+        if spread > 1e-7:  # a skipped all-reduce drifts by 1e-4 and more; identical updates give exactly 0
+            raise RuntimeError(f"replicas diverged: parameter checksums {vals}")
 
     if rank != 0:
         if world > 1:
