@@ -161,8 +161,9 @@ __device__ __forceinline__ float warp_sum(float v) {
 
 // Sum of p[b * stride] over b = lane, lane + 32, ... < n followed by a warp reduction: the last stage of the
 // deterministic two-stage reductions (per-CTA partials -> one warp per output).  Four independent
-// accumulators: the loads are L2 hits ~600 ns apart when they depend on one another (n = 592 partials was
-// 19 serial round trips, 4.6-8 us for a kernel that moves 2 MB), fixed order -> deterministic.
+// accumulators so the L2 round trips overlap; fixed order -> deterministic.  (Measured: these last-stage
+// kernels stay at 4-5 us each either way — they are launch-latency bound, ~210 of them per train step;
+// folding them into their producers is listed in DESIGN.md section 9.)
 __device__ __forceinline__ float strided_partial_sum(const float* __restrict__ p, int n, int64_t stride, int lane) {
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   int b = lane;
