@@ -43,6 +43,14 @@ inline int check_launch(const char* what) {
       return ::csb200::fail(CSB200_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));     \
   } while (0)
 
+// ---- host side: per-device launch-setup caches (defined in stripe_attn.cu) ----------------------------
+// All keyed by the CURRENT device and mutex-guarded: cudaFuncSetAttribute applies to the current device
+// only, a process may drive several GPUs, and the main thread and autograd's backward thread both launch.
+int device_sm_count();                                  // SM count of the current device (<= 0 on error)
+cudaError_t opt_in_smem(const void* func, int bytes);   // MaxDynamicSharedMemorySize >= bytes, once per (device, func)
+bool memo_get(const void* key, int tag, int* val);      // small integer memo, e.g. occupancy query results
+void memo_put(const void* key, int tag, int val);
+
 // ---- device side ------------------------------------------------------------------------------
 template <typename T>
 struct Vec16;  // 16-byte vector of T

@@ -369,12 +369,8 @@ int lepe_prep_tma_launch(int nbr, const StripeGeom* g, int dtype, const PrepIO* 
     ncb += b.ncb;
   }
   p.ncb0 = p.br[0].ncb;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    CSB200_CUDA(cudaGetDevice(&dev));
-    CSB200_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return fail(CSB200_ERR_CUDA, "lepe_prep_tma: cannot query the SM count");
   int gx = sm_count / ncb;
   if (gx < 1) gx = 1;
   if (gx > items) gx = items;
@@ -388,15 +384,11 @@ int lepe_prep_tma_launch(int nbr, const StripeGeom* g, int dtype, const PrepIO* 
     if ((rc = make_tok_map(&maps.o[i], io[i].out, dtype, cp, p.W, p.H, p.B, g[i].o_sb, g[i].o_sl, b.cb, b.R)) != CSB200_OK) return rc;
   }
   smem += 128;
-  static int attr[2] = {0, 0};
   const int ti = dtype == CSB200_F32 ? 0 : 1;
-  if (attr[ti] < smem) {
-    if (ti == 0)
-      CSB200_CUDA(cudaFuncSetAttribute(lepe_prep_tma<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 128));
-    else
-      CSB200_CUDA(cudaFuncSetAttribute(lepe_prep_tma<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BUDGET + 128));
-    attr[ti] = SMEM_BUDGET + 128;
-  }
+  if (ti == 0)
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&lepe_prep_tma<float>), SMEM_BUDGET + 128));
+  else
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&lepe_prep_tma<__nv_bfloat16>), SMEM_BUDGET + 128));
   if (ti == 0)
     lepe_prep_tma<float><<<dim3(gx, ncb), THREADS, smem, st>>>(maps, p);
   else

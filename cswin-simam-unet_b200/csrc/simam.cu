@@ -1279,21 +1279,10 @@ int nchw_bwd_stream(const T* x, const T* gy, const float* stats, T* gx, int64_t 
   const int64_t plane_bytes = S * (int64_t)sizeof(T);
   if (plane_bytes % (ST_CHUNK / 2) != 0 || plane_bytes < 4 * (ST_CHUNK / 2) || planes > 0x7fffffff) return -1;
   if (!aligned16(x) || !aligned16(gy) || !aligned16(gx)) return -1;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      return -1;
-  }
+  const int sms = device_sm_count();
+  if (sms <= 0) return -1;
   const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 2 * (ST_CONSUMERS / 32) * 4 + 64;
-  static bool attr[2] = {false, false};
-  if (!attr[sizeof(T) == 2]) {
-    if (cudaFuncSetAttribute(simam_nchw_bwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess)
-      return -1;
-    attr[sizeof(T) == 2] = true;
-  }
+  if (opt_in_smem(reinterpret_cast<const void*>(&simam_nchw_bwd_stream<T>), smem) != cudaSuccess) return -1;
   const int grid = planes < sms ? (int)planes : sms;
   simam_nchw_bwd_stream<T><<<grid, ST_CONSUMERS + 32, smem, st>>>(
       x, gy, stats, gx, (int)planes, (int)(plane_bytes / (ST_CHUNK / 2)), (float)S);
@@ -1306,21 +1295,10 @@ int nchw_fwd_stream(const T* x, T* y, float* stats, int64_t planes, int64_t S, f
   const int64_t plane_bytes = S * (int64_t)sizeof(T);
   if (plane_bytes % ST_CHUNK != 0 || plane_bytes < 2 * ST_CHUNK || planes > 0x7fffffff) return -1;
   if (!aligned16(x) || !aligned16(y)) return -1;
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      return -1;
-  }
+  const int sms = device_sm_count();
+  if (sms <= 0) return -1;
   const int smem = ST_STAGES * ST_CHUNK + 2 * ST_STAGES * 8 + 2 * (ST_CONSUMERS / 32) * 4 + 64;
-  static bool attr[2] = {false, false};
-  if (!attr[sizeof(T) == 2]) {
-    if (cudaFuncSetAttribute(simam_nchw_fwd_stream<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess)
-      return -1;
-    attr[sizeof(T) == 2] = true;
-  }
+  if (opt_in_smem(reinterpret_cast<const void*>(&simam_nchw_fwd_stream<T>), smem) != cudaSuccess) return -1;
   const int grid = planes < sms ? (int)planes : sms;
   simam_nchw_fwd_stream<T><<<grid, ST_CONSUMERS + 32, smem, st>>>(x, y, stats, (int)planes,
                                                                    (int)(plane_bytes / ST_CHUNK), (float)S, e_lambda);
@@ -1922,16 +1900,10 @@ template <typename T, bool BWD, int CVEC, bool PIPE>
 int nlc_stream_launch2(const cudaLaunchConfig_t& cfg, const T* x, const T* gy, float* stats_out, const float* stats_in,
                        T* out, int B, int L, int chunks, float e_lambda) {
   constexpr int SMEM = NlSmem<Vec16<T>::N, CVEC>::BYTES;
-  static bool ready = false;
   cudaError_t e;
-  if (!ready) {
-    if constexpr (BWD)
-      e = cudaFuncSetAttribute(simam_nlc_bwd_stream<T, CVEC, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    else
-      e = cudaFuncSetAttribute(simam_nlc_fwd_stream<T, CVEC, PIPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) return fail(CSB200_ERR_CUDA, "simam_nlc_stream: %s", cudaGetErrorString(e));
-    ready = true;
-  }
+  if constexpr (BWD) e = opt_in_smem(reinterpret_cast<const void*>(&simam_nlc_bwd_stream<T, CVEC, PIPE>), SMEM);
+  else e = opt_in_smem(reinterpret_cast<const void*>(&simam_nlc_fwd_stream<T, CVEC, PIPE>), SMEM);
+  if (e != cudaSuccess) return fail(CSB200_ERR_CUDA, "simam_nlc_stream: %s", cudaGetErrorString(e));
   if constexpr (BWD)
     e = cudaLaunchKernelEx(&cfg, simam_nlc_bwd_stream<T, CVEC, PIPE>, x, gy, stats_in, out, B, L, chunks);
   else
@@ -1951,21 +1923,13 @@ int nlc_stream_launch(const T* x, const T* gy, float* stats_out, const float* st
   constexpr int VE = Vec16<T>::N;
   constexpr int PART = BWD ? ST_CHUNK / 2 : ST_CHUNK;
   constexpr int SMEM = NlSmem<VE, CVEC>::BYTES;
-  static int sms = 0;
-  static int max_clusters[4] = {0, 0, 0, 0};  // by log2(cluster size)
-  if (sms == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess ||
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
-      return -1;
-    cudaError_t e;
-    if constexpr (BWD) e = cudaFuncSetAttribute(simam_nlc_bwd_stream<T, CVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    else e = cudaFuncSetAttribute(simam_nlc_fwd_stream<T, CVEC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM);
-    if (e != cudaSuccess) {
-      cudaGetLastError();
-      return -1;
-    }
-    sms = n;
+  const int sms = device_sm_count();
+  if (sms <= 0) return -1;
+  const void* kfun = BWD ? reinterpret_cast<const void*>(&simam_nlc_bwd_stream<T, CVEC, true>)
+                         : reinterpret_cast<const void*>(&simam_nlc_fwd_stream<T, CVEC, true>);
+  if (opt_in_smem(kfun, SMEM) != cudaSuccess) {
+    cudaGetLastError();
+    return -1;
   }
   int cl = 8, lg = 3;
   while (cl > 1 && (B * cl > sms || image_bytes % ((int64_t)cl * PART) != 0 ||
@@ -1985,7 +1949,8 @@ int nlc_stream_launch(const T* x, const T* gy, float* stats_out, const float* st
   at[0].val.clusterDim.z = 1;
   cfg.attrs = at;
   cfg.numAttrs = 1;
-  if (max_clusters[lg] == 0) {
+  int resident = 0;  // clusters of this size that are co-resident on the current device (memo per device)
+  if (!memo_get(kfun, 16 + lg, &resident)) {
     int n = 0;
     cfg.gridDim = dim3((unsigned)(sms / cl * cl));
     cudaError_t e;
@@ -1995,10 +1960,11 @@ int nlc_stream_launch(const T* x, const T* gy, float* stats_out, const float* st
       cudaGetLastError();
       n = sms / cl > 1 ? sms / cl / 2 : 1;  // conservative: correctness never depends on co-residency of clusters
     }
-    max_clusters[lg] = n;
+    resident = n;
+    memo_put(kfun, 16 + lg, n);
   }
   // even rounds: with r = ceil(B / resident) rounds, ceil(B / r) clusters finish together
-  const int64_t rounds = (B + max_clusters[lg] - 1) / max_clusters[lg];
+  const int64_t rounds = (B + resident - 1) / resident;
   const int64_t nclusters = (B + rounds - 1) / rounds;
   cfg.gridDim = dim3((unsigned)(nclusters * cl));
   const int chunks = (int)(image_bytes / ((int64_t)cl * PART));

@@ -1,11 +1,59 @@
 // C-ABI entry points of the stripe attention (include/csb200.h): validation, engine choice,
 // workspace carving.  The arithmetic lives in stripe_attn_simt.cu / stripe_attn_tc.cu.
 
+#include <mutex>
+#include <unordered_map>
+
 #include "stripe_attn.cuh"
 
 namespace csb200 {
 
 thread_local char g_err[512] = "";
+
+namespace {
+std::mutex g_memo_mu;
+std::unordered_map<uint64_t, int> g_memo;
+inline uint64_t memo_key(int dev, const void* key, int tag) {
+  uint64_t h = reinterpret_cast<uint64_t>(key) * 0x9E3779B97F4A7C15ull;
+  h ^= (static_cast<uint64_t>(static_cast<uint32_t>(dev)) << 48) ^ (static_cast<uint64_t>(static_cast<uint32_t>(tag)) << 32);
+  return h ^ (h >> 29);
+}
+const char kSmCountKey = 0, kSmemKey = 0;
+}  // namespace
+
+bool memo_get(const void* key, int tag, int* val) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return false;
+  std::lock_guard<std::mutex> lock(g_memo_mu);
+  auto it = g_memo.find(memo_key(dev, key, tag));
+  if (it == g_memo.end()) return false;
+  *val = it->second;
+  return true;
+}
+void memo_put(const void* key, int tag, int val) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return;
+  std::lock_guard<std::mutex> lock(g_memo_mu);
+  g_memo[memo_key(dev, key, tag)] = val;
+}
+int device_sm_count() {
+  int n = 0;
+  if (memo_get(&kSmCountKey, 0, &n)) return n;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess)
+    return -1;
+  memo_put(&kSmCountKey, 0, n);
+  return n;
+}
+cudaError_t opt_in_smem(const void* func, int bytes) {
+  int have = 0;
+  if (memo_get(func, 1, &have) && have >= bytes) return cudaSuccess;
+  cudaError_t e = cudaFuncSetAttribute(func, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+  if (e == cudaSuccess) memo_put(func, 1, bytes);
+  (void)kSmemKey;
+  return e;
+}
 std::atomic<uint64_t> g_launches{0};
 
 namespace {

@@ -490,19 +490,11 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
   p.gpi = gpi;
   p.groups = p.B * gpi;
 
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    CSB200_CUDA(cudaGetDevice(&dev));
-    CSB200_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
   // > half of the 227 KB so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
   const int smem = (int)sizeof(Smem<NK>) + 1024 > 120 * 1024 ? (int)sizeof(Smem<NK>) + 1024 : 120 * 1024;
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[NK / 256]) {
-    CSB200_CUDA(cudaFuncSetAttribute(stripe_fwd_tc<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done[NK / 256] = true;
-  }
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return fail(CSB200_ERR_CUDA, "stripe_fwd_tc: cannot query the SM count");
+  CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK>), smem));
   const int grid = p.groups < sm_count ? p.groups : sm_count;
   stripe_fwd_tc<NK><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
   return check_launch("stripe_fwd_tc");

@@ -496,18 +496,10 @@ int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st)
   }
   p.gpi = gpi;
   p.groups = p.B * gpi;
-  static int sm_count = 0;
-  if (sm_count == 0) {
-    int dev = 0;
-    CSB200_CUDA(cudaGetDevice(&dev));
-    CSB200_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, dev));
-  }
   const int smem = (int)sizeof(BSmem<NK>) + 1024;  // > 113 KB: one CTA (all 512 TMEM columns) per SM
-  static bool attr_done[2] = {false, false};
-  if (!attr_done[NK / 256]) {
-    CSB200_CUDA(cudaFuncSetAttribute(stripe_bwd_tc<NK>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    attr_done[NK / 256] = true;
-  }
+  const int sm_count = device_sm_count();
+  if (sm_count <= 0) return fail(CSB200_ERR_CUDA, "stripe_bwd_tc: cannot query the SM count");
+  CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_bwd_tc<NK>), smem));
   const int grid = p.groups < sm_count ? p.groups : sm_count;
   stripe_bwd_tc<NK><<<grid, THREADS, smem, st>>>(maps, p);
   return check_launch("stripe_bwd_tc");

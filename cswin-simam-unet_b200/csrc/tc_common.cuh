@@ -229,7 +229,6 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 EncodeTiledFn encode_tiled_fn();
 void ensure_context();  // binds the primary context to the calling host thread (once per thread)
-
 struct StripeGeom;
 // (channel, x, y, image) map over one token-major operand of a branch; box = (32, bx, by, 1),
 // 64-byte swizzle.  Defined in stripe_attn_tc.cu.

@@ -1,7 +1,10 @@
 """torch.autograd bindings of the csb200 kernels.
 
 Tensors stay ``torch.Tensor``; device pointers come from ``data_ptr()`` and kernels are enqueued on
-torch's current stream.  Nothing here computes on the host or falls back to ATen.
+torch's current stream.  Nothing here computes on the host and no csb200 kernel has a
+CPU or ATen stand-in.  What deliberately stays on library code is said where it happens: convolutions
+(cuDNN, ``conv2d``), GEMMs the tcgen05 token-path kernels do not tile (cuBLAS, ``linear``), and the column
+sums / bias adds of widths that are not a multiple of the 16-byte vector (``_bias_grad``, ``add_row_bias``).
 """
 import ctypes
 from typing import Optional, Sequence, Tuple
@@ -328,6 +331,13 @@ def refresh_shadows(masters, shadows):
         torch._foreach_copy_(shadows, masters)
     for p, sh in zip(masters, shadows):
         p._csb_shadow = (sh, p._version)
+
+
+def restamp_shadows(masters, shadows):
+    """Mark every shadow as current WITHOUT copying (the optimizer kernel has just written them)."""
+    for p, sh in zip(masters, shadows):
+        if p._csb_shadow[1] != p._version:
+            p._csb_shadow = (sh, p._version)
 
 
 def cast_param(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.Tensor]:

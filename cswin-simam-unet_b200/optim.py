@@ -124,19 +124,28 @@ class FusedAdamW(torch.optim.Optimizer):
             chunks = [v for i, n in enumerate(numels) for c in range(-(-n // chunk)) for v in (i, c)]
             dev_c = torch.tensor(chunks, dtype=torch.int32).to(dev)
             k = self._keep = {"numels": numels, "dev_c": dev_c, "n_chunks": len(chunks) // 2, "flip": 0,
+                              "uploaded": [None, None],
                               "host": [torch.empty(nbytes, dtype=torch.uint8).pin_memory() for _ in range(2)],
                               "dev_t": torch.empty(nbytes, dtype=torch.uint8, device=dev)}
         k["flip"] ^= 1  # two pinned staging buffers: the previous upload may still be queued on the stream
         host = k["host"][k["flip"]]
+        if k["uploaded"][k["flip"]] is not None:
+            k["uploaded"][k["flip"]].synchronize()  # the upload that last read THIS buffer (two rebuilds ago)
         ctypes.memmove(host.data_ptr(), ctypes.addressof(arr), nbytes)
         if freeze:
             # a table a captured CUDA graph will read on every replay: its own device copy, never rewritten
             # (an eager step() of the same optimizer with other gradient tensors builds another table)
             dev_t = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             dev_t.copy_(host, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream(dev))
+            k["uploaded"][k["flip"]] = ev
             self._frozen[key] = (dev_t, k["dev_c"], k["n_chunks"])
             return self._frozen[key]
         k["dev_t"].copy_(host, non_blocking=True)
+        ev = torch.cuda.Event()
+        ev.record(torch.cuda.current_stream(dev))
+        k["uploaded"][k["flip"]] = ev
         self._table_key = key
         return k["dev_t"], k["dev_c"], k["n_chunks"]
 

@@ -74,6 +74,10 @@ class TrainStep:
                     self.optimizer.attach_shadows(*self._shadow)  # csb200_adam_step refreshes them from now on
             elif not getattr(self.optimizer, "writes_shadows", False):
                 csbF.refresh_shadows(*self._shadow)
+            elif not torch.cuda.is_current_stream_capturing():
+                # the kernel wrote the shadows; re-stamp them in case something bumped a parameter's version
+                # counter since (load_state_dict), else every layer would cast per call from then on
+                csbF.restamp_shadows(*self._shadow)
 
     def _autocast(self, device_type: str):
         if self.precision == "bf16":
@@ -161,19 +165,18 @@ class TrainStep:
         self._x, self._y = images.to(dev, copy=True), masks.to(dev, copy=True)
         images = self._x
         saved_model = {k: v.clone() for k, v in self.model.state_dict().items()}
+        saved_opt = self._snapshot_optimizer()  # restored state / eager steps before the capture survive it
         side = torch.cuda.Stream(device=images.device)
         side.wait_stream(torch.cuda.current_stream(images.device))
         with torch.cuda.stream(side):
             for _ in range(3):  # lazy init: cuBLAS/cuDNN handles and autotune, optimizer state
                 self._eager_step(self._x, self._y)
         torch.cuda.current_stream(images.device).wait_stream(side)
-        # undo the warm-up: weights / buffers back, optimizer moments and step counters to zero
+        # undo the warm-up: weights / buffers and the optimizer state (moments, step counters) back to what
+        # they were before it; state the warm-up created is zeroed (== "not yet stepped")
         with torch.no_grad():
             self.model.load_state_dict(saved_model)
-            for st in self.optimizer.state.values():
-                for v in st.values():
-                    if torch.is_tensor(v):
-                        v.zero_()
+            self._restore_optimizer(saved_opt)
             if self._shadow is not None:
                 csbF.refresh_shadows(*self._shadow)
         self._graph = torch.cuda.CUDAGraph()
@@ -214,6 +217,32 @@ class TrainStep:
         self._graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
             self._optimizer_step()
+
+    def _snapshot_optimizer(self):
+        return {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
+                for p, st in self.optimizer.state.items()}
+
+    def _restore_optimizer(self, snap):
+        """In place (a later capture records these very tensors): copy the snapshot back, zero what is new."""
+        done = set()  # FusedAdamW shares one device step counter between all parameters
+        for p, st in self.optimizer.state.items():
+            old = snap.get(p, {})
+            for k, v in st.items():
+                if not torch.is_tensor(v) or id(v) in done:
+                    continue
+                done.add(id(v))
+                if torch.is_tensor(old.get(k)):
+                    v.copy_(old[k])
+                else:
+                    v.zero_()
+
+    def refresh_shadows(self):
+        """Re-synchronise the bf16 parameter shadows with the fp32 masters (and re-stamp them as current).
+        Call after writing parameters behind the optimizer's back — ``model.load_state_dict``, EMA swaps,
+        ``p.data.copy_`` — while a bf16 TrainStep is live; parameters must not be modified through ``.data``
+        without it (a stale shadow would be read by the next forward)."""
+        if self._shadow is not None:
+            csbF.refresh_shadows(*self._shadow)
 
     def _eager_step(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         if self.reducer is not None:

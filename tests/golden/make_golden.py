@@ -105,9 +105,57 @@ def bf16_drift_case(ref, img_size, split, batch, seed):
             net(x)
         bf16 = grabbed["logits"].clone()
     thr = fp32.median()
+    # random-init logits are all negative, so "mask agreement at p > 0.5" (C:731) is vacuous.
+    # The harness adds an output bias b_q = -quantile_q(logits) (the reference's `output` conv has none, C:603),
+    # i.e. a foreground fraction of 1 - q, and records the reference's OWN bf16 agreement at each setting.
+    qs = np.array(MASK_QUANTILES)
+    biases = np.array([-torch.quantile(fp32.flatten().double(), float(q)).item() for q in qs])
+    agree = np.array([((fp32 + b > 0) == (bf16 + b > 0)).float().mean().item() for b in biases])
     return dict(meta=np.array([img_size, batch, seed] + list(split), dtype=np.int64), x=x.numpy(),
                 logits=fp32.numpy(), ref_bf16_max_abs=np.array((fp32 - bf16).abs().max().item()),
-                ref_bf16_median_mask_agreement=np.array(((fp32 > thr) == (bf16 > thr)).float().mean().item()))
+                ref_bf16_median_mask_agreement=np.array(((fp32 > thr) == (bf16 > thr)).float().mean().item()),
+                mask_quantiles=qs, mask_biases=biases, ref_bf16_mask_agreement=agree)
+
+
+MASK_QUANTILES = (0.5, 0.9, 0.98)
+
+
+def model_case_512(ref, seed=0, batch=2):
+    """SURVEY.md §8(c) 'full-model logits at 512^2 B=2': the reference CSWinTransformer at BASELINE config 3's
+    geometry (split [1,2,8,8], stripes of 128 / 128 / 256 / 256 tokens — the shapes the tcgen05 engines tile),
+    fp32 on CPU, weights at the reference's init scale.  Inputs are NOT stored (8 MB): the test regenerates them
+    from the same seeded CPU generator (`inputs_512`)."""
+    img_size, split = 512, [1, 2, 8, 8]
+    cfg = om.CSWinConfig(img_size=img_size, split_size=split)
+    net = ref.CSWinTransformer(img_size=img_size, split_size=split)
+    shapes = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert shapes == om.cswin_param_shapes(cfg)
+    params = om.synth_params(shapes, seed, style="init")
+    net.load_state_dict(params)
+    x, y = inputs_512(seed, batch)
+    grabbed = {}
+    net.output.register_forward_hook(lambda m, i, o: grabbed.__setitem__("logits", o.detach()))
+    loss = torch.nn.BCELoss()(net(x), y)  # C:936
+    loss.backward()
+    logits = grabbed["logits"]
+    with torch.no_grad():
+        assert (om.cswin_unet_logits(params, x, cfg) - logits).abs().max() < 2e-5
+    named = dict(net.named_parameters())
+    names = list(named)
+    gnorm = np.array([named[k].grad.double().norm().item() for k in names])
+    keep = ["output.weight", "stage1.0.attns.0.get_v.weight", "stage1.0.attns.1.get_v.bias", "stage2.1.qkv.weight",
+            "stage3.0.qkv.bias", "stage3.5.attns.1.get_v.weight", "stage4.0.attns.0.get_v.weight",
+            "stage_up3.7.mlp.fc1.weight", "stage_up2.1.proj.weight", "upsample1.out.bias", "concat_linear3.weight"]
+    full = {("grad." + k): named[k].grad.numpy() for k in keep}
+    return dict(meta=np.array([img_size, batch, seed] + split, dtype=np.int64), logits=logits.numpy(),
+                loss=np.array(loss.item()), grad_norms=gnorm, grad_names=np.array(names), **full)
+
+
+def inputs_512(seed, batch):
+    g = torch.Generator().manual_seed(300 + seed)
+    x = torch.rand((batch, 3, 512, 512), generator=g)
+    y = (torch.rand((batch, 1, 512, 512), generator=g) > 0.5).float()
+    return x, y
 
 
 def model_case(ref, img_size, split, batch, seed):
@@ -173,6 +221,7 @@ def main():
     np.savez(os.path.join(OUT, "cswin_224_config1.npz"), **model_case(ref, 224, [1, 2, 7, 7], 2, 0))
     np.savez(os.path.join(OUT, "unet_64.npz"), **unet_case(refu))
     np.savez(os.path.join(OUT, "cswin_224_init_bf16.npz"), **bf16_drift_case(ref, 224, [1, 2, 7, 7], 2, 0))
+    np.savez_compressed(os.path.join(OUT, "cswin_512_b2.npz"), **model_case_512(ref))
     # reference failure modes that the drop-in must mirror
     try:
         ref.CSWinTransformer(img_size=512)(torch.rand(1, 3, 512, 512))

@@ -59,10 +59,14 @@ def test_cswin_model_bf16_within_stated_tolerance():
 
     Weights at the reference's initialisation scale (style="init"); the golden file also records the
     reference's OWN bf16 drift on the same input (CPU autocast) as the yardstick.  Random-init logits
-    are all negative (SURVEY.md H6), so the stated mask criterion (p > 0.5, C:731) is met trivially;
-    the median-threshold check below is the non-vacuous one: half the pixels sit on each side, so
-    pixels inside the error band may flip — we require to do no worse than the reference's own bf16
-    path does (minus a 1 % allowance) and that every flipped pixel lies inside the 2e-2 band."""
+    are all negative, so the stated mask criterion (p > 0.5, C:731) would be met vacuously.
+    As H6(i) prescribes, the harness adds an output bias b_q = -quantile_q(reference logits) (the `output`
+    conv has none, C:603), so that a fraction 1 - q of the pixels is foreground and the logits straddle 0:
+      * q = 0.98 (2 % foreground, a small-object segmentation): mask agreement at threshold 0 >= 99.9 %;
+      * q = 0.9 and q = 0.5 (the threshold sits in the densest part of the logit histogram, where ANY
+        bf16 path flips the pixels inside its error band — the reference's own CPU-bf16 forward agrees
+        99.83 % / 99.19 % there): at least the reference's own agreement, and every flipped pixel lies
+        inside the 2e-2 band."""
     g = golden("cswin_224_init_bf16.npz")
     img, batch, seed = [int(v) for v in g["meta"][:3]]
     split = [int(v) for v in g["meta"][3:]]
@@ -79,11 +83,53 @@ def test_cswin_model_bf16_within_stated_tolerance():
     assert rel_err(fp32, ref) < 5e-5
     err = (logits - ref).abs().max().item()
     assert err <= 2e-2, err
-    assert ((logits > 0) == (ref > 0)).float().mean().item() >= 0.999  # the stated criterion
-    thr = ref.median()
-    flipped = (logits > thr) != (ref > thr)
-    assert 1.0 - flipped.float().mean().item() >= float(g["ref_bf16_median_mask_agreement"]) - 0.01
-    assert ((ref - thr).abs()[flipped] <= 2e-2).all()
+    for q, bias, ref_agree in zip(g["mask_quantiles"], g["mask_biases"], g["ref_bf16_mask_agreement"]):
+        bias = float(bias)
+        want, got = (ref + bias) > 0, (logits + bias) > 0
+        assert abs(want.float().mean().item() - (1 - float(q))) < 1e-3  # the masks are not degenerate
+        agree = (want == got).float().mean().item()
+        if float(q) >= 0.98:
+            assert agree >= 0.999, (q, agree)  # the stated criterion, threshold 0 (p > 0.5, C:731)
+        assert agree >= float(ref_agree), (q, agree, float(ref_agree))
+        assert ((ref + bias).abs()[want != got] <= 2e-2).all()
+
+
+def test_cswin_512_golden_through_the_tcgen05_engines():
+    """SURVEY.md 8(c) golden 'CSWin 512^2, B=2' (reference CSWinTransformer(img_size=512, split_size=[1,2,8,8]),
+    fp32 CPU, init-scale weights): stripes of 128 / 256 tokens, so under bf16 autocast every LePEAttention call
+    runs on the tcgen05 forward AND backward engines inside the model.  Tolerances: logits max-abs <= 2e-2
+    (north_star), loss <= 2e-3 absolute, kept gradients <= 3e-2 of their max (the stated bf16 gradient
+    tolerance; the reference's own CPU-bf16 backward is within 1.5e-2 on the same tensors), gradient norms:
+    median deviation <= 1 %, at most 3 % of the 463 tensors off by more than 10 %."""
+    g = golden("cswin_512_b2.npz")
+    img, batch, seed = [int(v) for v in g["meta"][:3]]
+    split = [int(v) for v in g["meta"][3:]]
+    cfg = om.CSWinConfig(img_size=img, split_size=split)
+    net = pkg.CSWinTransformer(img_size=img, split_size=split, attn_engine="tcgen05")
+    net.load_state_dict(om.synth_params(om.cswin_param_shapes(cfg), seed, style="init"))
+    net.cuda()
+    gen = torch.Generator().manual_seed(300 + seed)  # == make_golden.inputs_512
+    x = torch.rand((batch, 3, img, img), generator=gen)
+    y = (torch.rand((batch, 1, img, img), generator=gen) > 0.5).float()
+    x, y = x.cuda(), y.cuda()
+    n0 = pkg.capi.launch_count()
+    step = pkg.TrainStep(net, torch.optim.SGD(net.parameters(), lr=0.0), precision="bf16")
+    loss = step.forward_loss(x, y)
+    loss.backward()
+    with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
+        logits = net.forward_logits(x).float().cpu()
+    assert pkg.capi.launch_count() - n0 > 100
+    ref = torch.tensor(g["logits"])
+    assert (logits - ref).abs().max().item() <= 2e-2
+    assert abs(loss.item() - float(g["loss"])) <= 2e-3
+    grads = dict(net.named_parameters())
+    for k in [k for k in g if k.startswith("grad.")]:
+        assert rel_err(grads[k[5:]].grad.cpu(), g[k]) < 3e-2, k
+    norms = np.array([grads[str(n)].grad.double().norm().item() for n in g["grad_names"]])
+    ratio = norms / g["grad_norms"]
+    assert np.median(np.abs(ratio - 1)) <= 1e-2, np.median(np.abs(ratio - 1))
+    off = np.abs(ratio - 1) > 0.1
+    assert off.mean() <= 0.03, [(str(n), float(r)) for n, r in zip(g["grad_names"][off], ratio[off])]
 
 
 def test_unet_golden_fp32_and_simam_variant(no_tf32):

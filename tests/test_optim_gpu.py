@@ -90,3 +90,40 @@ def test_bf16_graph_step_keeps_the_shadows_in_sync():
     for p in net.parameters():
         sh = getattr(p, "_csb_shadow", None)
         assert sh is not None and torch.equal(sh[0], p.detach().bfloat16())
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_graph_capture_keeps_restored_optimizer_state(fused, no_tf32):
+    """A checkpoint restored with optimizer.load_state_dict (or eager steps taken) BEFORE the first captured
+    step must survive the capture's warm-up: the captured run continues from moments / step count of the
+    checkpoint exactly like the eager run does (_capture used to zero every state tensor)."""
+    def make(net):
+        if fused:
+            return pkg.FusedAdamW(net.parameters(), lr=1e-3, weight_decay=1e-4)
+        return torch.optim.AdamW(net.parameters(), lr=1e-3, weight_decay=1e-4, capturable=True)
+
+    torch.manual_seed(0)
+    net0 = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], simam=True).cuda()
+    step0 = pkg.TrainStep(net0, make(net0), precision="fp32")
+    for s in range(3):
+        step0(*pkg.synthetic_batch(2, 64, "cuda", seed=s))
+    ckpt_model = {k: v.clone() for k, v in net0.state_dict().items()}
+    ckpt_opt = step0.optimizer.state_dict()
+
+    def resume(graph):
+        net = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], simam=True).cuda()
+        net.load_state_dict(ckpt_model)
+        opt = make(net)
+        opt.load_state_dict(ckpt_opt)
+        step = pkg.TrainStep(net, opt, precision="fp32", cuda_graph=graph)
+        losses = [step(*pkg.synthetic_batch(2, 64, "cuda", seed=10 + s)).item() for s in range(2)]
+        p0 = next(iter(opt.state))
+        return losses, [p.detach().clone() for p in net.parameters()], float(opt.state[p0]["step"])
+
+    le, we, se = resume(False)
+    lg, wg, sg = resume(True)
+    assert se == sg == 5.0  # 3 checkpointed steps + 2, not 2 (bias correction did not restart)
+    assert max(abs(a - b) for a, b in zip(le, lg)) < 1e-5
+    num = sum(float((a - b).double().pow(2).sum()) for a, b in zip(we, wg)) ** 0.5
+    den = sum(float(b.double().pow(2).sum()) for b in we) ** 0.5
+    assert num / den < 1e-5
