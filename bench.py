@@ -15,8 +15,11 @@ e2e     = same step through the public API with pinned HOST batches: H2D copy of
           timed region, every step
 roofline= the csb200 kernel family that takes the most time inside the timed steps, algorithmic
           FLOPs (attention) or bytes (SimAM) over its CUDA-event time, against MEASURED_PEAKS.json
-cpu_baseline / --impl reference = the oracle's CPU port of the reference model (the Python reference
-          itself cannot travel to the GPU box), fp32, all host threads, bounded sample (B=2 steps)
+cpu_baseline / --impl reference = the UNMODIFIED reference (baseline/_ref, installed by __graft_entry__.build();
+          kind "reference") on the host cores, fp32, all host threads, bounded sample (B=2 steps); the
+          oracle's CPU port (kind "port") only when that install is absent
+gpu_eager_baseline = the unmodified reference in stock PyTorch eager on the SAME B200 (fp32 TF32-off / TF32-on /
+          bf16 autocast), same batch and geometry: the bar BASELINE.md section 5 names (N = 1 only)
 """
 import argparse
 import json
@@ -90,29 +93,116 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # the reference algorithm on host cores (oracle port) — cpu_baseline and --impl reference
 # ------------------------------------------------------------------------------------------------
+def _reference_module():
+    """The UNMODIFIED reference script (train_cswinunet_segmentation.py) as installed under baseline/_ref by
+    __graft_entry__.build(), or None when that install is absent (then the oracle port stands in)."""
+    try:
+        from oracle import reference_shim
+        if reference_shim.available():
+            return reference_shim.load("cswin")
+    except Exception as e:  # a missing third-party import on the box: report the port instead
+        sys.stderr.write(f"reference scripts not loadable ({e}); using the oracle port\n")
+    return None
+
+
 def cpu_reference_steps(steps: int, warmup: int, batch: int = 2):
-    """fwd + BCE + bwd + AdamW of the reference CSWin-UNet arithmetic at 512^2 on the CPU, fp32.
-    SimAM on the skips is included so the work matches the GPU arm's model."""
-    from oracle import models as om
+    """One train step of the reference at 512^2 on the host cores, fp32, bounded sample (batch 2):
+    zero_grad -> forward -> BCELoss -> backward -> AdamW (C:780-786, C:936-941).  kind "reference": the
+    reference's own CSWinTransformer (no SimAM: the checkout has none); kind "port": oracle/models.py with
+    SimAM on the skips, when the reference scripts are not installed."""
     from cswin_simam_unet_b200.train import synthetic_batch
     torch.set_num_threads(os.cpu_count())
-    cfg = om.CSWinConfig(img_size=IMG, split_size=SPLIT, simam=True)
-    params = {k: v.requires_grad_(True) for k, v in om.synth_params(om.cswin_param_shapes(cfg), 0).items()}
-    opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=1e-4)
     x, y = synthetic_batch(batch, IMG, "cpu", seed=0)
+    ref = _reference_module()
+    if ref is not None:
+        torch.manual_seed(0)
+        net = ref.CSWinTransformer(img_size=IMG, split_size=SPLIT)  # ctor defaults: dropout 0 (C:495-496)
+        net.train()
+        opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)  # C:937-941
+        crit = torch.nn.BCELoss()  # C:936
+        kind, what = "reference", "unmodified reference CSWinTransformer (baseline/_ref, C:489-688, no SimAM)"
+
+        def one_step():
+            opt.zero_grad()
+            loss = crit(net(x), y)
+            loss.backward()
+            opt.step()
+    else:
+        from oracle import models as om
+        cfg = om.CSWinConfig(img_size=IMG, split_size=SPLIT, simam=True)
+        params = {k: v.requires_grad_(True) for k, v in om.synth_params(om.cswin_param_shapes(cfg), 0).items()}
+        opt = torch.optim.AdamW(list(params.values()), lr=1e-4, weight_decay=1e-4)
+        kind, what = "port", "oracle/models.py (CPU port of C:489-688 + SimAM on skips)"
+
+        def one_step():
+            opt.zero_grad()
+            loss = torch.nn.functional.binary_cross_entropy(om.cswin_unet_forward(params, x, cfg), y)
+            loss.backward()
+            opt.step()
     times = []
     for it in range(warmup + steps):
         t0 = time.perf_counter()
-        opt.zero_grad()
-        loss = torch.nn.functional.binary_cross_entropy(om.cswin_unet_forward(params, x, cfg), y)
-        loss.backward()
-        opt.step()
+        one_step()
         if it >= warmup:
             times.append(time.perf_counter() - t0)
     total = sum(times)
-    return {"value": batch * steps / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{steps} steps of batch {batch} at {IMG}^2 fp32 after {warmup} warm-up, oracle/models.py "
-                      f"(CPU port of C:489-688 + SimAM on skips), AdamW", "ms_per_step": 1e3 * total / steps}
+    return {"value": batch * steps / total, "unit": UNIT, "cores": torch.get_num_threads(), "kind": kind,
+            "sample": f"{steps} steps of batch {batch} at {IMG}^2 fp32 after {warmup} warm-up, {what}, AdamW",
+            "ms_per_step": 1e3 * total / steps}
+
+
+def gpu_eager_reference(dev, batch: int, steps: int = 3, warmup: int = 2):
+    """BASELINE.md section 5 / SURVEY.md 8(d) "end-to-end": the UNMODIFIED reference in stock PyTorch eager on the
+    same B200, same step (C:780-786), same batch and geometry: fp32 with TF32 off (the parity anchor), fp32
+    with TF32 on, and bf16 autocast with the BCE evaluated in fp32 (CUDA autocast refuses BCELoss).  Returns
+    None when baseline/_ref is not installed.  Halves the batch on out-of-memory and says so."""
+    ref = _reference_module()
+    if ref is None:
+        return None
+    from cswin_simam_unet_b200.train import synthetic_batch
+    out = {"model": "reference CSWinTransformer(img_size=512, split_size=[1,2,8,8]), stock PyTorch eager, no SimAM",
+           "steps": steps, "warmup": warmup, "unit": UNIT}
+    saved = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    for mode in ("fp32_tf32_off", "fp32_tf32_on", "bf16_autocast"):
+        b = batch
+        while b >= 1:
+            try:
+                torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = mode == "fp32_tf32_on"
+                torch.manual_seed(0)
+                net = ref.CSWinTransformer(img_size=IMG, split_size=SPLIT).to(dev).train()
+                opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+                crit = torch.nn.BCELoss()
+                x, y = synthetic_batch(b, IMG, dev, seed=0)
+                t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                for it in range(warmup + steps):
+                    if it == warmup:
+                        torch.cuda.synchronize(dev)
+                        t0.record()
+                    opt.zero_grad()
+                    if mode == "bf16_autocast":
+                        with torch.autocast("cuda", dtype=torch.bfloat16):
+                            probs = net(x)
+                        loss = crit(probs.float(), y)
+                    else:
+                        loss = crit(net(x), y)
+                    loss.backward()
+                    opt.step()
+                t1.record()
+                torch.cuda.synchronize(dev)
+                ms = t0.elapsed_time(t1) / steps
+                out[mode] = {"value": b * 1e3 / ms, "ms_per_step": ms, "batch": b,
+                             "peak_mem_gib": round(torch.cuda.max_memory_allocated(dev) / 2 ** 30, 1)}
+                break
+            except torch.OutOfMemoryError:
+                b //= 2
+            finally:
+                net = opt = x = y = loss = probs = None
+                torch.cuda.empty_cache()
+                torch.cuda.reset_peak_memory_stats(dev)
+        else:
+            out[mode] = {"value": None, "error": "out of memory at batch 1"}
+    torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = saved
+    return out
 
 
 def run_reference(args, rank):
@@ -123,7 +213,8 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": steps, "warmup": warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"CSWin-SimAM-UNet train step {IMG}x{IMG}, split {SPLIT}, CPU sample batch 2"},
+            "config": {"workload": f"CSWin-SimAM-UNet train step {IMG}x{IMG}, split {SPLIT}, CPU sample batch 2",
+                       "reference": r["kind"]},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
@@ -297,6 +388,12 @@ def run_ours(args, rank, local_rank, world):
                                   "of every kernel the C-ABI call launches)" if traffic is not None else None}
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     cpu = cpu_reference_steps(steps=3, warmup=1) if (world == 1 and not args.no_cpu_baseline) else None
+    gpu_ref = None
+    if world == 1 and not args.no_gpu_baseline:
+        step = eager = net = opt = resident = None  # release the graph pools before the reference allocates
+        torch.cuda.empty_cache()
+        torch.cuda.reset_peak_memory_stats(dev)
+        gpu_ref = gpu_eager_reference(dev, B)
     line = {
         "metric": METRIC, "value": B * world * args.steps / (ms / 1e3), "unit": UNIT, "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
@@ -318,6 +415,8 @@ def run_ours(args, rank, local_rank, world):
     }
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    if gpu_ref is not None:
+        line["gpu_eager_baseline"] = gpu_ref
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -332,6 +431,8 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--attn-engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-gpu-baseline", action="store_true",
+                    help="skip the reference-in-stock-PyTorch-eager leg on the same GPU (gpu_eager_baseline)")
     ap.add_argument("--optimizer", default="csb200", choices=["csb200", "torch"])
     ap.add_argument("--cuda-graph", dest="cuda_graph", action="store_true", default=True)
     ap.add_argument("--no-cuda-graph", dest="cuda_graph", action="store_false")
