@@ -1,5 +1,7 @@
 """GPU: csb200_adam_step (FusedAdamW) vs torch.optim.AdamW / Adam — `optimizer.step()` of the reference
 train loops (C:786 with C:937-941, U:348 with U:486-490) — eager and captured in the CUDA-graph train step."""
+import copy
+
 import pytest
 import torch
 
@@ -108,13 +110,13 @@ def test_graph_capture_keeps_restored_optimizer_state(fused, no_tf32):
     for s in range(3):
         step0(*pkg.synthetic_batch(2, 64, "cuda", seed=s))
     ckpt_model = {k: v.clone() for k, v in net0.state_dict().items()}
-    ckpt_opt = step0.optimizer.state_dict()
+    ckpt_opt = copy.deepcopy(step0.optimizer.state_dict())
 
     def resume(graph):
         net = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], simam=True).cuda()
         net.load_state_dict(ckpt_model)
         opt = make(net)
-        opt.load_state_dict(ckpt_opt)
+        opt.load_state_dict(copy.deepcopy(ckpt_opt))  # load_state_dict aliases tensors of matching dtype / device
         step = pkg.TrainStep(net, opt, precision="fp32", cuda_graph=graph)
         losses = [step(*pkg.synthetic_batch(2, 64, "cuda", seed=10 + s)).item() for s in range(2)]
         p0 = next(iter(opt.state))
