@@ -1,0 +1,77 @@
+#!/usr/bin/env python
+"""csb200_linear_fwd (tcgen05) vs cuBLAS (+ the flat GELU pass) on the K = C GEMM shapes of BASELINE config 3
+(512^2, batch 32).  Prints one JSON line per (shape, epilogue): microseconds (CUDA events over a CUDA-graph
+replay of `reps` back-to-back launches on rotating buffers > L2), algorithmic GB/s and TFLOP/s."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+from cswin_simam_unet_b200 import capi, functional as csbF  # noqa: E402
+
+SHAPES = {  # name: (M, K, N)
+    "s1.qkv": (524288, 64, 192), "s1.proj": (524288, 64, 64), "s1.fc1": (524288, 64, 256),
+    "s2.qkv": (131072, 128, 384), "s2.proj": (131072, 128, 128), "s2.fc1": (131072, 128, 512),
+    "s3.qkv": (32768, 256, 768), "s3.proj": (32768, 256, 256), "s3.fc1": (32768, 256, 1024),
+}
+
+
+def timed(fn, nbuf, reps=8):
+    for i in range(3):
+        fn(i % nbuf)
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for i in range(reps):
+            fn(i % nbuf)
+    g.replay()
+    torch.cuda.synchronize()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(5):
+        g.replay()
+    t1.record()
+    torch.cuda.synchronize()
+    return t0.elapsed_time(t1) * 1e3 / (5 * reps)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="")
+    args = ap.parse_args()
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0, "bf16_tflops_sustained": 1400.0}
+    for name, (M, K, N) in SHAPES.items():
+        if args.only and args.only not in name:
+            continue
+        nbuf = max(2, int(300e6 // (2 * M * (K + 2 * N))) + 1)  # rotate over > 2x L2
+        xs = [torch.randn(M, K, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+        w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
+        b = torch.randn(N, device="cuda")
+        bb = b.to(torch.bfloat16)
+        modes = [("bias", capi.EPI_BIAS)] + ([("gelu+h", capi.EPI_GELU_SAVE), ("gelu", capi.EPI_GELU)] if "fc1" in name else [])
+        for label, epi in modes:
+            us = timed(lambda i: csbF._tc_linear(xs[i], w, b, epi), nbuf)
+            outs = 2 if epi == capi.EPI_GELU_SAVE else 1
+            if epi == capi.EPI_BIAS:
+                base = timed(lambda i: torch.nn.functional.linear(xs[i], w, bb), nbuf)
+            else:
+                def two_pass(i):
+                    h = torch.nn.functional.linear(xs[i], w, bb)
+                    a = torch.empty_like(h)
+                    capi.check(capi.lib().csb200_gelu_fwd(csbF._ptr(h), csbF._ptr(a), M, N, capi.BF16,
+                                                          csbF._vp(capi.stream_of(h))), "gelu")
+                    return a
+                base = timed(two_pass, nbuf)
+            nbytes = 2 * (M * K + N * K + outs * M * N)
+            print(json.dumps({"shape": name, "M": M, "K": K, "N": N, "epilogue": label, "csb200_us": round(us, 2),
+                              "cublas_path_us": round(base, 2), "speedup": round(base / us, 3),
+                              "alg_gbs": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3),
+                              "tflops": round(2 * M * N * K / us / 1e6, 1)}), flush=True)
+        del xs
+
+
+if __name__ == "__main__":
+    main()

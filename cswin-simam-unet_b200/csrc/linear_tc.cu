@@ -1,0 +1,304 @@
+// Token-path Linear on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), bf16 in, fp32 accumulate:
+//
+//     Y = act(X W^T + b)        X (M, K) tokens, W (N, K) = nn.Linear.weight, b (N) fp32, Y (M, N)
+//
+// for the GEMMs of the CSWinBlock whose contraction is the block width (K = C in {64, 128, 256}):
+// `qkv` (C:357-358, N = 3C), `proj` (C:366, N = C) and `Mlp.fc1` + `act` (C:188-196, N = 4C, exact-erf GELU
+// in the epilogue, optionally also storing the pre-activation h that GELU' needs in backward).  M is the
+// token count of the batch (524 288 ... 32 768 at 512^2, batch 32), so these GEMMs are HBM- / epilogue-bound,
+// not tensor-bound, and the design follows from that:
+//
+//   * one persistent CTA per SM owns ONE n-tile of the weight (BN <= 256 output columns x K) and keeps it
+//     RESIDENT in shared memory for its whole life (<= 128 KB, 128-byte-swizzled K-major), so the only
+//     operand that streams is X: 16-KB TMA boxes (128 tokens x 64 channels) through a ring;
+//   * warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M128 x N{BN} x K16, smem x smem, accumulators in
+//     TMEM, two buffers of 256 columns so the MMAs of tile i+1 run under the epilogue of tile i), warp 2 =
+//     TMEM allocator, then FOUR epilogue warpgroups: warpgroup j drains column half (j >> 1) of TMEM buffer
+//     (j & 1) — 16 warps keep tcgen05.ld / MUFU latency covered; one thread owns one token row, adds the
+//     bias, applies GELU on packed fp32 pairs (gelu_math.cuh, the same arithmetic as the flat GELU pass),
+//     and stores 64 contiguous bytes per 32 columns.
+//
+// The separate GELU pass (1 read + 1 write of the 4C-wide hidden tensor) disappears: fc1 + GELU moves
+// M (K + N [+ N]) elements instead of M (K + 3N).
+
+#include <cstring>
+
+#include "gelu_math.cuh"
+#include "tc_common.cuh"
+
+namespace csb200 {
+namespace {
+using namespace tc;
+
+constexpr int BM = 128;                       // token rows per tile == TMEM lanes
+constexpr int BK = 64;                        // channels per k-chunk: one 128-byte swizzled row
+constexpr int A_STAGE_BYTES = BM * BK * 2;    // 16 KB
+constexpr int MAX_STAGES = 8;
+constexpr int NUM_EPI_WG = 4;
+constexpr int THREADS = 128 + 128 * NUM_EPI_WG;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct LinParams {
+  int M, N, K;
+  int BN, n_tiles, m_tiles, kchunks, stages;
+  int m_stride;            // CTAs that share an n-tile (stride of the m-tile walk)
+  uint32_t idesc;
+  uint32_t w_bytes;        // resident weight tile
+  const float* bias;       // [N] or nullptr
+  __nv_bfloat16* y;        // [M][N]
+  __nv_bfloat16* h;        // [M][N] pre-activation (EPI_GELU_SAVE) or nullptr
+};
+struct LinMaps {
+  CUtensorMap a, w;
+};
+
+enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_GELU_SAVE = 2 };
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+          "r"(dst), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+// shared-memory carve-up (dynamic; offsets from a 1024-byte aligned base):
+//   [0, w_bytes)                       weight tile: kchunks x (BN rows x 128 B), 128B-swizzled K-major
+//   [w_bytes, + stages * 16 KB)        X ring
+//   then bias (BN floats) and the mbarriers
+struct Bars {
+  uint64_t w_full;
+  uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES];
+  uint64_t acc_full[2], acc_empty[2];
+  uint32_t tmem_base;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(THREADS, 1)
+    linear_tc_kernel(const __grid_constant__ LinMaps maps, const __grid_constant__ LinParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = smem_u32(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
+  const uint32_t w_sm = base, a_sm = base + p.w_bytes;
+  float* bias_sm = reinterpret_cast<float*>(base_ptr + p.w_bytes + p.stages * A_STAGE_BYTES);
+  Bars& bar = *reinterpret_cast<Bars*>(base_ptr + p.w_bytes + p.stages * A_STAGE_BYTES + 256 * sizeof(float));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tile = (int)blockIdx.x % p.n_tiles, m0 = (int)blockIdx.x / p.n_tiles;
+  const int my_tiles = m0 < p.m_tiles ? (p.m_tiles - m0 + p.m_stride - 1) / p.m_stride : 0;
+  const int n0 = n_tile * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tensormap(&maps.a);
+    prefetch_tensormap(&maps.w);
+    mbar_init(&bar.w_full, 1);
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&bar.a_full[i], 1);
+      mbar_init(&bar.a_empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bar.acc_full[i], 1);
+      mbar_init(&bar.acc_empty[i], 8);  // one arrival per warp of the two warpgroups that drain the buffer
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) tmem_alloc(&bar.tmem_base, 512);
+  if (warp == 3)
+    for (int i = lane; i < p.BN; i += 32) bias_sm[i] = p.bias != nullptr ? __ldg(p.bias + n0 + i) : 0.f;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = bar.tmem_base;
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      mbar_expect_tx(&bar.w_full, p.w_bytes);
+      for (int kc = 0; kc < p.kchunks; ++kc)
+        tma_load_2d(w_sm + kc * (p.BN * 128), &maps.w, &bar.w_full, kc * BK, n0);
+      int it = 0;
+      for (int i = 0; i < my_tiles; ++i) {
+        const int row0 = (m0 + i * p.m_stride) * BM;
+        for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+          const int s = it % p.stages;
+          mbar_wait(&bar.a_empty[s], ((it / p.stages) & 1) ^ 1);
+          mbar_expect_tx(&bar.a_full[s], A_STAGE_BYTES);
+          tma_load_2d(a_sm + s * A_STAGE_BYTES, &maps.a, &bar.a_full[s], kc * BK, row0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================== MMA issuer ========================================
+    mbar_wait(&bar.w_full, 0);
+    const uint32_t a_lo0 = desc_lo_sw64(a_sm), w_lo0 = desc_lo_sw64(w_sm);  // (addr >> 4) | LBO = 1
+    int it = 0;
+    for (int i = 0; i < my_tiles; ++i) {
+      const int buf = i & 1;
+      mbar_wait(&bar.acc_empty[buf], ((i >> 1) & 1) ^ 1);
+      for (int kc = 0; kc < p.kchunks; ++kc, ++it) {
+        const int s = it % p.stages;
+        mbar_wait(&bar.a_full[s], (it / p.stages) & 1);
+        fence_after_sync();
+        if (elect_one_sync()) {
+          const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4), w_lo = w_lo0 + kc * ((p.BN * 128) >> 4);
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k)  // 16 channels per MMA: 32 B inside the 128-byte swizzled row
+            umma_ss2(tmem + buf * 256, a_lo + k * 2, DESC_HI_SW128, w_lo + k * 2, DESC_HI_SW128, p.idesc,
+                     (kc | k) != 0);
+          umma_commit(&bar.a_empty[s]);
+          if (kc == p.kchunks - 1) umma_commit(&bar.acc_full[buf]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp >= 4) {
+    // ================================= epilogue warpgroups ====================================
+    const int wg = (warp - 4) >> 2;           // 0..3
+    const int buf = wg & 1, half = wg >> 1;   // TMEM buffer, column half of the n-tile
+    const int row_in_tile = ((warp & 3) << 5) | lane;
+    const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + buf * 256;
+    const int chunks = p.BN / 32;             // 32-column chunks of the n-tile
+    const int c_lo = half == 0 ? 0 : (chunks + 1) / 2, c_hi = half == 0 ? (chunks + 1) / 2 : chunks;
+    for (int i = buf; i < my_tiles; i += 2) {
+      const int64_t row = (int64_t)(m0 + i * p.m_stride) * BM + row_in_tile;
+      mbar_wait(&bar.acc_full[buf], (i >> 1) & 1);
+      fence_after_sync();
+      __nv_bfloat16* yrow = p.y + row * p.N + n0;
+      __nv_bfloat16* hrow = EPI == EPI_GELU_SAVE ? p.h + row * p.N + n0 : nullptr;
+      for (int c = c_lo; c < c_hi; ++c) {
+        uint32_t r[32];
+        tmem_ld32(lane_base + c * 32, r);
+        tmem_wait_ld();
+        const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
+        uint32_t outw[16], hw[16];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float4 bb = b4[q];  // broadcast
+          const float v0 = __uint_as_float(r[4 * q + 0]) + bb.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y;
+          const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z, v3 = __uint_as_float(r[4 * q + 3]) + bb.w;
+          const uint32_t w0 = pack_bf16x2(v0, v1), w1 = pack_bf16x2(v2, v3);
+          if (EPI == EPI_BIAS) {
+            outw[2 * q] = w0;
+            outw[2 * q + 1] = w1;
+          } else {
+            // GELU of the bf16-ROUNDED pre-activation: what nn.GELU sees after a bf16 Linear under autocast,
+            // and exactly what the flat csb200_gelu_fwd pass computes from the stored h
+            hw[2 * q] = w0;
+            hw[2 * q + 1] = w1;
+            outw[2 * q] = gelu_fwd2(w0);
+            outw[2 * q + 1] = gelu_fwd2(w1);
+          }
+        }
+        if (row < p.M) {
+          uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
+          if (EPI == EPI_GELU_SAVE) {
+            uint4* hd = reinterpret_cast<uint4*>(hrow + c * 32);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) hd[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+          }
+        }
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&bar.acc_empty[buf]);
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = encode_tiled_fn();
+  if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  ensure_context();
+  const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
+  const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+  const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return CSB200_OK;
+}
+
+// n-tile width: the largest multiple of 32 that divides N, is <= 256 and whose resident weight tile leaves
+// room for at least 3 ring stages
+int pick_bn(int64_t N, int64_t K) {
+  for (int bn = 256; bn >= 32; bn -= 32) {
+    if (N % bn != 0) continue;
+    const int64_t w_bytes = (int64_t)bn * K * 2;
+    if (w_bytes + 3 * A_STAGE_BYTES + 4096 <= SMEM_LIMIT) return bn;
+  }
+  return 0;
+}
+
+}  // namespace
+}  // namespace csb200
+
+using namespace csb200;
+
+extern "C" {
+
+CSB200_API int csb200_linear_supported(int64_t M, int64_t N, int64_t K, int dtype) {
+  if (dtype != CSB200_BF16) return 0;
+  if (M < 1 || M > 0x7fffffff / 2 || N < 32 || N > 65536) return 0;
+  if (K != 64 && K != 128 && K != 256) return 0;
+  return pick_bn(N, K) != 0;
+}
+
+CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float* bias, void* y, void* pre_act, int64_t M,
+                      int64_t N, int64_t K, int64_t ldx, int dtype, int epilogue, void* stream) {
+  if (M == 0) return CSB200_OK;
+  if (x == nullptr || weight == nullptr || y == nullptr)
+    return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: null pointer");
+  if (epilogue < 0 || epilogue > 2 || (epilogue == EPI_GELU_SAVE && pre_act == nullptr))
+    return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: bad epilogue %d", epilogue);
+  if (!csb200_linear_supported(M, N, K, dtype))
+    return fail(CSB200_ERR_UNSUPPORTED, "csb200_linear_fwd: bf16 with K in {64,128,256} and N a multiple of 32 only "
+                "(M %lld, N %lld, K %lld)", (long long)M, (long long)N, (long long)K);
+  if (ldx < K || (ldx * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15) ||
+      (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(pre_act) & 15))
+    return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: operands must be 16-byte aligned (ldx %lld)", (long long)ldx);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  LinMaps maps;
+  LinParams p;
+  memset(&maps, 0, sizeof(maps));
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.BN = pick_bn(N, K);
+  p.n_tiles = (int)(N / p.BN);
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.kchunks = (int)(K / BK);
+  p.w_bytes = (uint32_t)(p.BN * K * 2);
+  const int fixed = (int)p.w_bytes + 256 * (int)sizeof(float) + (int)sizeof(Bars) + 1024;
+  p.stages = (SMEM_LIMIT - fixed) / A_STAGE_BYTES;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.idesc = umma_idesc_bf16(p.BN, false, false);
+  p.bias = bias;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.h = static_cast<__nv_bfloat16*>(pre_act);
+  int rc;
+  if ((rc = make_map_2d(&maps.a, x, K, M, ldx, BM)) != CSB200_OK) return rc;
+  if ((rc = make_map_2d(&maps.w, weight, K, N, K, p.BN)) != CSB200_OK) return rc;
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail(CSB200_ERR_CUDA, "csb200_linear_fwd: cannot query the SM count");
+  int per_n = sms / p.n_tiles;              // CTAs per n-tile
+  if (per_n < 1) per_n = 1;
+  if (per_n > p.m_tiles) per_n = p.m_tiles;
+  p.m_stride = per_n;
+  const int grid = per_n * p.n_tiles;
+  const int smem = fixed + p.stages * A_STAGE_BYTES;
+  const void* fn = epilogue == EPI_BIAS ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_BIAS>)
+                   : epilogue == EPI_GELU ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU>)
+                                          : reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU_SAVE>);
+  CSB200_CUDA(opt_in_smem(fn, SMEM_LIMIT));
+  if (epilogue == EPI_BIAS) linear_tc_kernel<EPI_BIAS><<<grid, THREADS, smem, st>>>(maps, p);
+  else if (epilogue == EPI_GELU) linear_tc_kernel<EPI_GELU><<<grid, THREADS, smem, st>>>(maps, p);
+  else linear_tc_kernel<EPI_GELU_SAVE><<<grid, THREADS, smem, st>>>(maps, p);
+  return check_launch("linear_tc_kernel");
+}
+
+}  // extern "C"

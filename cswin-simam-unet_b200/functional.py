@@ -349,8 +349,42 @@ def cast_param(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.
     return p.to(dtype)
 
 
+# Which Linear layers run on the csb200 tcgen05 GEMM (csb200_linear_fwd, K = C in {64, 128, 256}, bf16):
+# "gelu": Mlp.fc1 + GELU with the activation in the epilogue; "plain": qkv / proj (bias-only epilogue).
+TC_LINEAR = {"gelu": True, "plain": False}
+
+
+def set_tc_linear(gelu: Optional[bool] = None, plain: Optional[bool] = None):
+    if gelu is not None:
+        TC_LINEAR["gelu"] = bool(gelu)
+    if plain is not None:
+        TC_LINEAR["plain"] = bool(plain)
+
+
+def _tc_linear_ok(x2: torch.Tensor, wc: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
+    if x2.dtype != torch.bfloat16 or wc.dtype != torch.bfloat16 or not wc.is_contiguous() or x2.stride(1) != 1:
+        return False
+    if x2.data_ptr() % 16 or wc.data_ptr() % 16 or (x2.stride(0) * 2) % 16:
+        return False
+    return bool(capi.lib().csb200_linear_supported(x2.shape[0], wc.shape[0], wc.shape[1], capi.BF16))
+
+
+def _tc_linear(x2: torch.Tensor, wc: torch.Tensor, bias: Optional[torch.Tensor], epilogue: int):
+    """(y, pre_act) = csb200_linear_fwd on a (M, K) token matrix; bias is read in fp32."""
+    M, K = x2.shape
+    N = wc.shape[0]
+    y = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device)
+    h = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device) if epilogue == capi.EPI_GELU_SAVE else None
+    b32 = None if bias is None else bias.detach().float().contiguous()
+    nbytes = 2 * (M * K + N * K + M * N * (2 if h is not None else 1))
+    with torch.cuda.device(x2.device), _span("linear_tc", nbytes, 2 * M * N * K, f"M{M}xN{N}xK{K}e{epilogue}"):
+        capi.check(capi.lib().csb200_linear_fwd(_ptr(x2), _ptr(wc), _ptr(b32), _ptr(y), _ptr(h), M, N, K, x2.stride(0),
+                                                capi.BF16, epilogue, _vp(capi.stream_of(x2))), "csb200_linear_fwd")
+    return y, h
+
+
 class _LinearFn(torch.autograd.Function):
-    """y = x W^T + b.  GEMMs stay on cuBLAS (torch.mm); the bias gradient, which ATen computes with a
+    """y = x W^T + b.  GEMMs stay on cuBLAS (torch.mm) unless TC_LINEAR["plain"]; the bias gradient, which ATen computes with a
     generic strided reduction at ~1/9 of the HBM roofline, is one csb200_colsum pass."""
 
     @staticmethod
@@ -360,6 +394,11 @@ class _LinearFn(torch.autograd.Function):
         wc, bc = cast_param(weight, compute_dtype), cast_param(bias, compute_dtype)
         ctx.save_for_backward(xc, wc)
         ctx.meta = (x.dtype, weight.dtype, None if bias is None else bias.dtype)
+        if TC_LINEAR["plain"] and compute_dtype == torch.bfloat16:
+            x2 = xc.reshape(-1, xc.shape[-1])
+            if _tc_linear_ok(x2, wc, bias):
+                y, _ = _tc_linear(x2, wc, bias, capi.EPI_BIAS)
+                return y.view(*xc.shape[:-1], wc.shape[0])
         return torch.nn.functional.linear(xc, wc, bc)
 
     @staticmethod
@@ -428,9 +467,16 @@ class _LinearGeluFn(torch.autograd.Function):
     @torch.amp.custom_fwd(device_type="cuda")
     def forward(ctx, x, weight, bias, compute_dtype):
         xc = x if x.dtype == compute_dtype else x.to(compute_dtype)
-        wc, bc = cast_param(weight, compute_dtype), cast_param(bias, compute_dtype)
-        h = torch.nn.functional.linear(xc, wc, bc)
+        wc = cast_param(weight, compute_dtype)
         n = wc.shape[0]
+        ctx.meta = (x.dtype, weight.dtype, bias.dtype)
+        x2 = xc.reshape(-1, xc.shape[-1])
+        if TC_LINEAR["gelu"] and compute_dtype == torch.bfloat16 and _tc_linear_ok(x2, wc, bias):
+            # one tcgen05 GEMM whose epilogue adds the bias, applies GELU and stores both a and h (C:188-190)
+            a, h = _tc_linear(x2, wc, bias, capi.EPI_GELU_SAVE)
+            ctx.save_for_backward(xc, wc, h.view(*xc.shape[:-1], n))
+            return a.view(*xc.shape[:-1], n)
+        h = torch.nn.functional.linear(xc, wc, cast_param(bias, compute_dtype))
         h2 = h.reshape(-1, n)
         a = torch.empty_like(h)
         lib = capi.lib()
@@ -438,7 +484,6 @@ class _LinearGeluFn(torch.autograd.Function):
             capi.check(lib.csb200_gelu_fwd(_ptr(h2), _ptr(a), h2.shape[0], n, capi.dtype_code(h),
                                            _vp(capi.stream_of(h))), "csb200_gelu_fwd")
         ctx.save_for_backward(xc, wc, h)
-        ctx.meta = (x.dtype, weight.dtype, bias.dtype)
         return a
 
     @staticmethod

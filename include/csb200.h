@@ -145,6 +145,24 @@ CSB200_API int csb200_gelu_bwd(const void* grad_out, const void* h, void* grad_h
                                int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
+ * Token-path Linear on the tcgen05 tensor cores: y = epilogue(x W^T + b) for the nn.Linear layers of the
+ * CSWinBlock whose contraction is the block width — `qkv` (C:357-358), `proj` (C:366), `Mlp.fc1` + `act`
+ * (C:188-196) — SURVEY.md section 8(f)-2.  x: [M][K] tokens (row stride ldx elements), weight: [N][K]
+ * (nn.Linear.weight), bias: fp32 [N] or NULL, y: [M][N].  bf16 activations / weight, fp32 accumulation.
+ * epilogue: CSB200_EPI_BIAS       y = x W^T + b
+ *           CSB200_EPI_GELU       y = GELU(bf16(x W^T + b))   exact erf form, nn.GELU()
+ *           CSB200_EPI_GELU_SAVE  as above and pre_act = bf16(x W^T + b)  (what GELU' needs in backward)
+ * Supported (csb200_linear_supported): bf16, K in {64, 128, 256}, N a multiple of 32.
+ * ---------------------------------------------------------------------------------------------- */
+#define CSB200_EPI_BIAS 0
+#define CSB200_EPI_GELU 1
+#define CSB200_EPI_GELU_SAVE 2
+CSB200_API int csb200_linear_supported(int64_t M, int64_t N, int64_t K, int dtype);
+CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float* bias, void* y, void* pre_act,
+                                 int64_t M, int64_t N, int64_t K, int64_t ldx, int dtype, int epilogue,
+                                 void* stream);
+
+/* ------------------------------------------------------------------------------------------------
  * Optimizer step for every parameter tensor of the model in one launch — `optimizer.step()` of the
  * reference train loop (C:786) with torch.optim.AdamW (C:937-941, decoupled decay) or torch.optim.Adam
  * (U:486-490, L2 decay); fp32 parameters, gradients and moments.  `shadow` (nullable) receives the bf16

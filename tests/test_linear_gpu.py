@@ -1,0 +1,93 @@
+"""GPU: csb200_linear_fwd (tcgen05 Linear with bias / GELU epilogues) — the K = C GEMMs of the CSWinBlock
+(qkv C:357-358, proj C:366, Mlp.fc1 + act C:188-196) — against a plain PyTorch fp32 reference of the same op
+on the same bf16-rounded operands, through the C ABI.
+
+Tolerance: the kernel accumulates in fp32 and rounds ONCE to bf16, so y must be within one bf16 rounding
+(2^-8 relative to the row's scale) of the fp32 result; GELU is evaluated on the rounded pre-activation, so
+against GELU(bf16(h_ref)) the same bound holds except where h_ref sits on a rounding boundary (<= 2 ulp)."""
+import pytest
+import torch
+
+from conftest import rel_err
+import cswin_simam_unet_b200 as pkg
+from cswin_simam_unet_b200 import capi, functional as csbF
+
+pytestmark = pytest.mark.gpu
+
+# (M, K, N): config-3 widths of the four K = C GEMM families + ragged M, several n-tiles, one partial tile
+SHAPES = [(4096, 64, 192), (4096, 64, 64), (4096, 64, 256), (2048, 128, 384), (2048, 128, 512), (1024, 256, 768),
+          (1024, 256, 1024), (1000, 64, 256), (77, 128, 128), (300 * 128 + 5, 64, 256), (19000, 256, 256)]
+
+
+def _operands(M, K, N, seed):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.randn((M, K), generator=g).to(torch.bfloat16).cuda()
+    w = (torch.randn((N, K), generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    b = (torch.randn((N,), generator=g) * 0.5).cuda()
+    return x, w, b
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_bias_epilogue_matches_fp32_reference(shape):
+    M, K, N = shape
+    x, w, b = _operands(M, K, N, M + N)
+    assert capi.lib().csb200_linear_supported(M, N, K, capi.BF16)
+    y, _ = csbF._tc_linear(x, w, b, capi.EPI_BIAS)
+    ref = x.float() @ w.float().t() + b
+    assert rel_err(y.float(), ref) < 2 ** -8
+    # and no worse than cuBLAS on the same operands
+    cublas = torch.nn.functional.linear(x, w, b.to(torch.bfloat16))
+    assert rel_err(y.float(), ref) <= rel_err(cublas.float(), ref) + 2 ** -9
+
+
+@pytest.mark.parametrize("shape", SHAPES)
+def test_gelu_epilogue_and_saved_preactivation(shape):
+    M, K, N = shape
+    x, w, b = _operands(M, K, N, M + 2 * N)
+    a, h = csbF._tc_linear(x, w, b, capi.EPI_GELU_SAVE)
+    ref_h = x.float() @ w.float().t() + b
+    assert rel_err(h.float(), ref_h) < 2 ** -8
+    # GELU acts on the value that was stored (bit-exact contract with the flat csb200_gelu_fwd pass)
+    flat = torch.empty_like(h)
+    capi.check(capi.lib().csb200_gelu_fwd(csbF._ptr(h), csbF._ptr(flat), M, N, capi.BF16,
+                                          csbF._vp(capi.stream_of(h))), "csb200_gelu_fwd")
+    assert torch.equal(a, flat)
+    ref_a = torch.nn.functional.gelu(h.float())  # exact erf form, nn.GELU() of C:190
+    assert rel_err(a.float(), ref_a) < 2 ** -8
+    a_only, none = csbF._tc_linear(x, w, b, capi.EPI_GELU)
+    assert none is None and torch.equal(a_only, a)
+
+
+def test_strided_rows_no_bias_and_rejections():
+    M, K, N = 640, 64, 128
+    x, w, b = _operands(M, 2 * K, N, 3)
+    view = x[:, :K]  # row stride 2K: a channel slice of a wider token matrix
+    y, _ = csbF._tc_linear(view, w[:, :K].contiguous(), None, capi.EPI_BIAS)
+    assert rel_err(y.float(), view.float() @ w[:, :K].float().t()) < 2 ** -8
+    lib = capi.lib()
+    assert not lib.csb200_linear_supported(128, 128, 96, capi.BF16)   # K not tiled
+    assert not lib.csb200_linear_supported(128, 100, 64, capi.BF16)   # N not a multiple of 32
+    assert not lib.csb200_linear_supported(128, 128, 64, capi.F32)
+    with pytest.raises(RuntimeError, match="K in"):
+        csbF._tc_linear(torch.zeros(128, 96, dtype=torch.bfloat16, device="cuda"),
+                        torch.zeros(128, 96, dtype=torch.bfloat16, device="cuda"), None, capi.EPI_BIAS)
+
+
+def test_mlp_through_the_fused_path_matches_the_two_pass_path():
+    """Mlp.forward (C:188-196) under bf16 autocast: tcgen05 fc1 + GELU vs cuBLAS fc1 + flat GELU pass —
+    same h is saved, so the gradients are computed by the same backward kernels."""
+    torch.manual_seed(0)
+    mlp = pkg.modules.Mlp(128, 512).cuda()
+    x = torch.randn(4, 1024, 128, device="cuda").to(torch.bfloat16)
+    outs = {}
+    for fused in (True, False):
+        csbF.set_tc_linear(gelu=fused)
+        xi = x.clone().requires_grad_(True)
+        mlp.zero_grad()
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            y = mlp(xi)
+        y.float().square().mean().backward()
+        outs[fused] = (y.detach().float(), xi.grad.float(), mlp.fc1.weight.grad.clone(), mlp.fc1.bias.grad.clone())
+    csbF.set_tc_linear(gelu=True)
+    for a, b in zip(outs[True], outs[False]):
+        assert rel_err(a, b) < 2 ** -6
