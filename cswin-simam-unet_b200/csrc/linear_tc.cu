@@ -15,8 +15,10 @@
 //     TMEM, two buffers of 256 columns so the MMAs of tile i+1 run under the epilogue of tile i), warp 2 =
 //     TMEM allocator, then FOUR epilogue warpgroups: warpgroup j drains column half (j >> 1) of TMEM buffer
 //     (j & 1) — 16 warps keep tcgen05.ld / MUFU latency covered; one thread owns one token row, adds the
-//     bias, applies GELU on packed fp32 pairs (gelu_math.cuh, the same arithmetic as the flat GELU pass),
-//     and stores 64 contiguous bytes per 32 columns.
+//     bias, applies GELU on packed fp32 pairs (gelu_math.cuh, the same arithmetic as the flat GELU pass);
+//     a warp stages its 32 rows x 32 columns in shared memory and one lane hands the box to the TMA
+//     store engine (thread-per-row 16-byte global stores — half a sector each, 32 lines per instruction —
+//     ran the bias-only GEMM at 0.5x cuBLAS: profiles/r2_linear_bench_v1_direct_stores.jsonl).
 //
 // The separate GELU pass (1 read + 1 write of the 4C-wide hidden tensor) disappears: fc1 + GELU moves
 // M (K + N [+ N]) elements instead of M (K + 3N).
@@ -37,11 +39,13 @@ constexpr int MAX_STAGES = 8;
 constexpr int NUM_EPI_WG = 4;
 constexpr int THREADS = 128 + 128 * NUM_EPI_WG;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int STG_BYTES = 32 * 64;            // one staged store box: 32 rows x 32 bf16 columns
 
 struct LinParams {
   int M, N, K;
   int BN, n_tiles, m_tiles, kchunks, stages;
   int m_stride;            // CTAs that share an n-tile (stride of the m-tile walk)
+  int stage_bufs;          // staging buffers per epilogue warp (1 or 2), 2 KB each
   uint32_t idesc;
   uint32_t w_bytes;        // resident weight tile
   const float* bias;       // [N] or nullptr
@@ -50,9 +54,26 @@ struct LinParams {
 };
 struct LinMaps {
   CUtensorMap a, w;
+  CUtensorMap y, h;        // stores: box 32 columns x 32 rows, 64-byte swizzle (rows past M are clipped)
 };
 
 enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_GELU_SAVE = 2 };
+
+// shared -> global tile store (bulk async group of the issuing thread)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::
+                   "l"(reinterpret_cast<uint64_t>(m)), "r"(src), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {  // <= N groups of this thread still reading shared memory
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.u32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
 
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, uint64_t* bar, int c0, int c1) {
   asm volatile(
@@ -64,7 +85,8 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* m, 
 // shared-memory carve-up (dynamic; offsets from a 1024-byte aligned base):
 //   [0, w_bytes)                       weight tile: kchunks x (BN rows x 128 B), 128B-swizzled K-major
 //   [w_bytes, + stages * 16 KB)        X ring
-//   then bias (BN floats) and the mbarriers
+//   then 16 warps x stage_bufs x 2 KB  store staging (32 rows x 64 B, 64-byte swizzled: what the output
+//                                      tensor maps read), bias (BN floats) and the mbarriers
 struct Bars {
   uint64_t w_full;
   uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES];
@@ -79,8 +101,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t base = smem_u32(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t w_sm = base, a_sm = base + p.w_bytes;
-  float* bias_sm = reinterpret_cast<float*>(base_ptr + p.w_bytes + p.stages * A_STAGE_BYTES);
-  Bars& bar = *reinterpret_cast<Bars*>(base_ptr + p.w_bytes + p.stages * A_STAGE_BYTES + 256 * sizeof(float));
+  const uint32_t stg_off = p.w_bytes + p.stages * A_STAGE_BYTES;
+  const uint32_t misc_off = stg_off + (uint32_t)(4 * NUM_EPI_WG * p.stage_bufs * STG_BYTES);  // 16 epilogue warps
+  float* bias_sm = reinterpret_cast<float*>(base_ptr + misc_off);
+  Bars& bar = *reinterpret_cast<Bars*>(base_ptr + misc_off + 256 * sizeof(float));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tile = (int)blockIdx.x % p.n_tiles, m0 = (int)blockIdx.x / p.n_tiles;
@@ -90,6 +114,8 @@ __global__ void __launch_bounds__(THREADS, 1)
   if (warp == 0 && lane == 0) {
     prefetch_tensormap(&maps.a);
     prefetch_tensormap(&maps.w);
+    prefetch_tensormap(&maps.y);
+    if (EPI == EPI_GELU_SAVE) prefetch_tensormap(&maps.h);
     mbar_init(&bar.w_full, 1);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&bar.a_full[i], 1);
@@ -154,16 +180,19 @@ __global__ void __launch_bounds__(THREADS, 1)
     // ================================= epilogue warpgroups ====================================
     const int wg = (warp - 4) >> 2;           // 0..3
     const int buf = wg & 1, half = wg >> 1;   // TMEM buffer, column half of the n-tile
-    const int row_in_tile = ((warp & 3) << 5) | lane;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16) + buf * 256;
     const int chunks = p.BN / 32;             // 32-column chunks of the n-tile
     const int c_lo = half == 0 ? 0 : (chunks + 1) / 2, c_hi = half == 0 ? (chunks + 1) / 2 : chunks;
+    // this warp's staging buffers; a row of a staged box is 64 B, chunk q of row `lane` sits at the 64-byte
+    // swizzled position the store tensor map expects
+    const uint32_t stg0 = base + stg_off + (uint32_t)(warp - 4) * p.stage_bufs * STG_BYTES;
+    const uint32_t my_row = stg0 + lane * 64;
+    const int sw = (lane >> 1) & 3;
+    int sbuf = 0;                             // staging buffer of the next store
     for (int i = buf; i < my_tiles; i += 2) {
-      const int64_t row = (int64_t)(m0 + i * p.m_stride) * BM + row_in_tile;
+      const int row0 = (m0 + i * p.m_stride) * BM + ((warp & 3) << 5);  // first token row of this warp
       mbar_wait(&bar.acc_full[buf], (i >> 1) & 1);
       fence_after_sync();
-      __nv_bfloat16* yrow = p.y + row * p.N + n0;
-      __nv_bfloat16* hrow = EPI == EPI_GELU_SAVE ? p.h + row * p.N + n0 : nullptr;
       for (int c = c_lo; c < c_hi; ++c) {
         uint32_t r[32];
         tmem_ld32(lane_base + c * 32, r);
@@ -188,37 +217,49 @@ __global__ void __launch_bounds__(THREADS, 1)
             outw[2 * q + 1] = gelu_fwd2(w1);
           }
         }
-        if (row < p.M) {
-          uint4* dst = reinterpret_cast<uint4*>(yrow + c * 32);
+        // registers -> staging (conflict-free: 8 rows cover the 32 banks) -> one TMA store per 32 x 32 box
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dst[q] = make_uint4(outw[4 * q], outw[4 * q + 1], outw[4 * q + 2], outw[4 * q + 3]);
-          if (EPI == EPI_GELU_SAVE) {
-            uint4* hd = reinterpret_cast<uint4*>(hrow + c * 32);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) hd[q] = make_uint4(hw[4 * q], hw[4 * q + 1], hw[4 * q + 2], hw[4 * q + 3]);
+        for (int v = 0; v < (EPI == EPI_GELU_SAVE ? 2 : 1); ++v) {
+          const uint32_t (&src)[16] = v == 0 ? outw : hw;
+          if (lane == 0) {
+            if (p.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
           }
+          __syncwarp();
+          const uint32_t dst = my_row + sbuf * STG_BYTES;
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            sts128(dst + ((q ^ sw) << 4), src[4 * q], src[4 * q + 1], src[4 * q + 2], src[4 * q + 3]);
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(v == 0 ? &maps.y : &maps.h, stg0 + sbuf * STG_BYTES, n0 + c * 32, row0);
+            bulk_commit();
+          }
+          sbuf = p.stage_bufs == 2 ? sbuf ^ 1 : 0;
         }
       }
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(&bar.acc_empty[buf]);
     }
+    if (lane == 0) bulk_wait_all();  // the staged boxes have been read AND written before the CTA retires
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t ld, int box_rows) {
+int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t ld, int box_rows,
+                int box_inner = BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn enc = encode_tiled_fn();
   if (enc == nullptr) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
   ensure_context();
   const cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)rows};
   const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
-  const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
+  const cuuint32_t box[2] = {(cuuint32_t)box_inner, (cuuint32_t)box_rows};
   const cuuint32_t estr[2] = {1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return CSB200_OK;
@@ -230,7 +271,7 @@ int pick_bn(int64_t N, int64_t K) {
   for (int bn = 256; bn >= 32; bn -= 32) {
     if (N % bn != 0) continue;
     const int64_t w_bytes = (int64_t)bn * K * 2;
-    if (w_bytes + 3 * A_STAGE_BYTES + 4096 <= SMEM_LIMIT) return bn;
+    if (w_bytes + 3 * A_STAGE_BYTES + 16 * STG_BYTES + 4096 <= SMEM_LIMIT) return bn;
   }
   return 0;
 }
@@ -273,7 +314,10 @@ CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float*
   p.m_tiles = (int)((M + BM - 1) / BM);
   p.kchunks = (int)(K / BK);
   p.w_bytes = (uint32_t)(p.BN * K * 2);
-  const int fixed = (int)p.w_bytes + 256 * (int)sizeof(float) + (int)sizeof(Bars) + 1024;
+  // two staging buffers per epilogue warp when that still leaves >= 4 ring stages
+  const int misc = 256 * (int)sizeof(float) + (int)sizeof(Bars) + 1024;
+  p.stage_bufs = (SMEM_LIMIT - (int)p.w_bytes - misc - 2 * 4 * NUM_EPI_WG * STG_BYTES) / A_STAGE_BYTES >= 4 ? 2 : 1;
+  const int fixed = (int)p.w_bytes + misc + p.stage_bufs * 4 * NUM_EPI_WG * STG_BYTES;
   p.stages = (SMEM_LIMIT - fixed) / A_STAGE_BYTES;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
   p.idesc = umma_idesc_bf16(p.BN, false, false);
@@ -283,6 +327,10 @@ CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float*
   int rc;
   if ((rc = make_map_2d(&maps.a, x, K, M, ldx, BM)) != CSB200_OK) return rc;
   if ((rc = make_map_2d(&maps.w, weight, K, N, K, p.BN)) != CSB200_OK) return rc;
+  if ((rc = make_map_2d(&maps.y, y, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK) return rc;
+  if (pre_act != nullptr &&
+      (rc = make_map_2d(&maps.h, pre_act, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK)
+    return rc;
   const int sms = device_sm_count();
   if (sms <= 0) return fail(CSB200_ERR_CUDA, "csb200_linear_fwd: cannot query the SM count");
   int per_n = sms / p.n_tiles;              // CTAs per n-tile

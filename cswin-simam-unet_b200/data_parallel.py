@@ -79,7 +79,9 @@ class GradientAllReducer:
                 for p in b.params:
                     self._handles.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
         # the backend may lack a native average (gloo): sum, then scale once in finish_step
-        self._avg = dist.ReduceOp.AVG if self.world > 1 and dist.get_backend(process_group) == "nccl" else None
+        nccl = self.world > 1 and dist.get_backend(process_group) == "nccl"
+        self._avg = dist.ReduceOp.AVG if nccl else None
+        self.capturable = nccl  # NCCL collectives can be recorded into a CUDA graph; gloo's cannot
 
     def _launch(self, b: _Bucket):
         op = self._avg if self._avg is not None else dist.ReduceOp.SUM

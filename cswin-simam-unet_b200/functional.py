@@ -351,7 +351,7 @@ def cast_param(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.
 
 # Which Linear layers run on the csb200 tcgen05 GEMM (csb200_linear_fwd, K = C in {64, 128, 256}, bf16):
 # "gelu": Mlp.fc1 + GELU with the activation in the epilogue; "plain": qkv / proj (bias-only epilogue).
-TC_LINEAR = {"gelu": True, "plain": False}
+TC_LINEAR = {"gelu": True, "plain": True}
 
 
 def set_tc_linear(gelu: Optional[bool] = None, plain: Optional[bool] = None):

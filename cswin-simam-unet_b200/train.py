@@ -54,11 +54,13 @@ class TrainStep:
     """
 
     def __init__(self, model: torch.nn.Module, optimizer: torch.optim.Optimizer, precision: str = "bf16",
-                 reducer=None, cuda_graph: bool = False):
+                 reducer=None, cuda_graph: bool = False, capture_collectives: bool = True):
         if precision not in ("bf16", "fp32"):
             raise ValueError("precision must be 'bf16' or 'fp32'")
         self.model, self.optimizer, self.precision, self.reducer = model, optimizer, precision, reducer
         self.cuda_graph = cuda_graph
+        self.capture_collectives = capture_collectives  # data parallel: NCCL all-reduces inside the captured backward
+        self._reduce_in_graph = False
         self._graph = self._graph_opt = None
         self._shadow = None  # (fp32 masters, bf16 shadows): see functional.shadow_params
 
@@ -151,8 +153,8 @@ class TrainStep:
             self._mark_consumed(slot)  # the graph reads its own static copies from here on
         self._graph.replay()
         if self._graph_opt is not None:
-            if self.reducer is not None:  # data parallel: gradients are averaged between the two graphs
-                self.reducer.finish_step()
+            if self.reducer is not None and not self._reduce_in_graph:
+                self.reducer.finish_step()  # fallback: gradients averaged eagerly between the two graphs
             if hasattr(self.optimizer, "sync_hyperparameters"):
                 self.optimizer.sync_hyperparameters()  # a scheduler may have changed lr since the capture
             self._graph_opt.replay()
@@ -201,22 +203,39 @@ class TrainStep:
             with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
                 self._optimizer_step()
             return
-        # Data parallel: graph 1 = forward + backward + packing the gradients into the flat buckets, then the
-        # bucket all-reduces are issued eagerly (a handful of NCCL calls on static buffers; 94 MB is
-        # < 1 ms on NVLink, so nothing is lost by not overlapping), graph 2 = optimizer step.
-        self.reducer.overlap = False
-        with torch.cuda.graph(self._graph):
-            self.reducer.begin_step()
-            loss = self.forward_loss(self._x, self._y)
-            loss.backward()
-            self.reducer.pack()  # gradients -> flat buckets, inside the graph
-            self._loss = loss.detach()
+        # Data parallel: graph 1 = forward + backward with the bucket all-reduces CAPTURED as backward produces
+        # them (NCCL's stream is forked from / joined to the capture by events), so on replay the gradient
+        # exchange overlaps the rest of backward exactly as in the eager step and nothing is issued from the
+        # host between the graphs; graph 2 = optimizer step.  If the process group cannot be captured (gloo, an
+        # old NCCL) the all-reduces stay eager between the two graphs.
+        self._reduce_in_graph = self.reducer.world > 1 and self.reducer.capturable and self.capture_collectives
+        try:
+            self._capture_dp_graph(in_graph=self._reduce_in_graph)
+        except RuntimeError:
+            if not self._reduce_in_graph:
+                raise
+            torch.cuda.synchronize(dev)
+            self._reduce_in_graph = False
+            self._graph = torch.cuda.CUDAGraph()
+            self._capture_dp_graph(in_graph=False)
         if own_tables:
             self.optimizer.prepare(freeze=True)
             torch.cuda.synchronize(dev)
         self._graph_opt = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
             self._optimizer_step()
+
+    def _capture_dp_graph(self, in_graph: bool):
+        self.reducer.overlap = in_graph
+        with torch.cuda.graph(self._graph):
+            self.reducer.begin_step()
+            loss = self.forward_loss(self._x, self._y)
+            loss.backward()
+            if in_graph:
+                self.reducer.finish_step()  # launches what the hooks have not, joins NCCL's stream to the capture
+            else:
+                self.reducer.pack()  # gradients -> flat buckets, inside the graph
+            self._loss = loss.detach()
 
     def _snapshot_optimizer(self):
         return {p: {k: (v.clone() if torch.is_tensor(v) else v) for k, v in st.items()}
