@@ -386,6 +386,16 @@ def run_ours(args, rank, local_rank, world):
                 "share_of_step": round(r["ms"] / ms, 4),
                 "traffic_source": "profiles/traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum "
                                   "of every kernel the C-ABI call launches)" if traffic is not None else None}
+    # every (kernel family, shape) of the step, largest first: average launch duration and the fraction of the
+    # roofline that bounds it (tensor for attention, HBM for everything else)
+    shape_rows = []
+    for key, v in sorted(shapes.items(), key=lambda kv: -kv[1]["ms"])[:24]:
+        us = v["ms"] * 1e3 / v["calls"]
+        row = {"kernel": key, "calls_per_step": v["calls"] // args.steps, "us_per_launch": round(us, 2),
+               "hbm_frac": round(v["bytes"] / v["calls"] / us / 1e3 / pk["hbm_gbs"], 3)}
+        if v["flops"]:
+            row["tensor_frac"] = round(v["flops"] / v["calls"] / us / 1e6 / pk["bf16_tflops_sustained"], 3)
+        shape_rows.append(row)
     h2d = sum(t.numel() * t.element_size() for t in host[0])
     cpu = cpu_reference_steps(steps=3, warmup=1) if (world == 1 and not args.no_cpu_baseline) else None
     gpu_ref = None
@@ -412,6 +422,7 @@ def run_ours(args, rank, local_rank, world):
         "clocks": clk.summary(),
         "roofline": roofline,
         "roofline_all": roof_all,
+        "roofline_shapes": shape_rows,
     }
     if cpu is not None:
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}

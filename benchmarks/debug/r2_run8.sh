@@ -1,0 +1,16 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" || exit 1
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_linear_gpu.py tests/test_gelu_conv_gpu.py tests/test_models_gpu.py -q -m gpu > gpurun_out/r2_pytest_linear.log 2>&1
+echo "pytest rc=$?" >> gpurun_out/r2_pytest_linear.log
+tail -25 gpurun_out/r2_pytest_linear.log | cut -c1-220
+timeout 600 python benchmarks/linear_bench.py --only fc1 > gpurun_out/r2_linear_bench.jsonl 2> gpurun_out/r2_linear_bench.err
+echo "linear_bench rc=$?"; grep -v '"bias"' gpurun_out/r2_linear_bench.jsonl; tail -5 gpurun_out/r2_linear_bench.err
+timeout 900 python bench.py --steps 20 --warmup 5 --no-gpu-baseline --no-cpu-baseline > gpurun_out/r2_bench3.json 2> gpurun_out/r2_bench3.err
+echo "bench rc=$?"; python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r2_bench3.json').read().strip().splitlines()[-1])
+print(d['value'], d['ms_per_step'], d['e2e']['value'], d['gpu_launches'], d['roofline']['kernel'], d['roofline']['frac'])
+print({k:(v['frac'],v['ms_total']) for k,v in d['roofline_all'].items()})
+PY
+tail -3 gpurun_out/r2_bench3.err

@@ -70,6 +70,28 @@ def main():
                               "cublas_path_us": round(base, 2), "speedup": round(base / us, 3),
                               "alg_gbs": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3),
                               "tflops": round(2 * M * N * K / us / 1e6, 1)}), flush=True)
+        if "fc1" in name:  # backward: grad_h = (grad_y W2) * GELU'(h) — one tcgen05 GEMM vs cuBLAS + flat GELU' pass
+            hs = [torch.randn(M, N, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+            w2 = (torch.randn(K, N, device="cuda") / K ** 0.5).to(torch.bfloat16)
+            lib = capi.lib()
+            nws = lib.csb200_gelu_bwd_workspace_bytes(N)
+            wsp = torch.empty(nws, dtype=torch.uint8, device="cuda")
+            gb = torch.empty(N, dtype=torch.float32, device="cuda")
+
+            def two_pass_bwd(i):
+                da = torch.mm(xs[i], w2)
+                dh = torch.empty_like(da)
+                capi.check(lib.csb200_gelu_bwd(csbF._ptr(da), csbF._ptr(hs[i]), csbF._ptr(dh), csbF._ptr(gb), csbF._ptr(wsp),
+                                               nws, M, N, capi.BF16, csbF._vp(capi.stream_of(da))), "gelu_bwd")
+                return dh
+            us = timed(lambda i: csbF._tc_dgelu(xs[i], w2, hs[i]), nbuf)
+            base = timed(two_pass_bwd, nbuf)
+            nbytes = 2 * (M * K + N * K + 2 * M * N)
+            print(json.dumps({"shape": name, "M": M, "K": K, "N": N, "epilogue": "dgelu (backward)", "csb200_us": round(us, 2),
+                              "cublas_path_us": round(base, 2), "speedup": round(base / us, 3),
+                              "alg_gbs": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3),
+                              "tflops": round(2 * M * N * K / us / 1e6, 1)}), flush=True)
+            del hs
         del xs
 
 

@@ -52,4 +52,16 @@ __device__ __forceinline__ uint32_t gelu_bwd2(uint32_t wg, uint32_t wh) {
   f2_split(f2_mul(g, f2_add(cdf, xpdf)), lo, hi);
   return pack_bf16x2(lo, hi);
 }
+// grad_h = g * GELU'(h) for an fp32 pair g (e.g. tensor-core accumulators) and a packed bf16 pair h; fp32 pair
+__device__ __forceinline__ f2_t gelu_bwd2_f32(f2_t g, uint32_t wh) {
+  const f2_t x = f2_from_bf16x2(wh);
+  const GeluPair r = erf_and_gauss2(x);
+  const f2_t cdf = f2_fma(r.erf, f2_splat(0.5f), f2_splat(0.5f));
+  const f2_t xpdf = f2_mul(x, f2_mul(r.gauss, f2_splat(kInvSqrt2Pi)));
+  return f2_mul(g, f2_add(cdf, xpdf));
+}
+// (Measured, round 2: trading the reciprocal for a degree-9 erfcx polynomial — one MUFU op per element instead
+// of two, three more packed FMAs — made the GEMM epilogues 5-15 % SLOWER: they are bound by instruction issue,
+// not by the MUFU pipe.  profiles/r2_linear_bench_erfcx_experiment.jsonl)
+
 }  // namespace csb200

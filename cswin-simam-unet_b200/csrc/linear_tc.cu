@@ -46,6 +46,8 @@ struct LinParams {
   int BN, n_tiles, m_tiles, kchunks, stages;
   int m_stride;            // CTAs that share an n-tile (stride of the m-tile walk)
   int stage_bufs;          // staging buffers per epilogue warp (1 or 2), 2 KB each
+  int w_mn;                // weight operand is MN-major: memory [K][N] (the input-gradient form y = x W)
+  float* partial;          // EPI_DGELU: per-CTA column sums of the output, [m_stride][N]
   uint32_t idesc;
   uint32_t w_bytes;        // resident weight tile
   const float* bias;       // [N] or nullptr
@@ -57,7 +59,7 @@ struct LinMaps {
   CUtensorMap y, h;        // stores: box 32 columns x 32 rows, 64-byte swizzle (rows past M are clipped)
 };
 
-enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_GELU_SAVE = 2 };
+enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_GELU_SAVE = 2, EPI_DGELU = 3 };
 
 // shared -> global tile store (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
@@ -91,6 +93,7 @@ struct Bars {
   uint64_t w_full;
   uint64_t a_full[MAX_STAGES], a_empty[MAX_STAGES];
   uint64_t acc_full[2], acc_empty[2];
+  uint64_t h_full[4 * NUM_EPI_WG];   // EPI_DGELU: one per epilogue warp (its staged pre-activation box)
   uint32_t tmem_base;
 };
 
@@ -102,7 +105,9 @@ __global__ void __launch_bounds__(THREADS, 1)
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
   const uint32_t w_sm = base, a_sm = base + p.w_bytes;
   const uint32_t stg_off = p.w_bytes + p.stages * A_STAGE_BYTES;
-  const uint32_t misc_off = stg_off + (uint32_t)(4 * NUM_EPI_WG * p.stage_bufs * STG_BYTES);  // 16 epilogue warps
+  // 16 epilogue warps x stage_bufs output boxes, then (EPI_DGELU) 16 pre-activation boxes
+  const uint32_t hstg_off = stg_off + (uint32_t)(4 * NUM_EPI_WG * p.stage_bufs * STG_BYTES);
+  const uint32_t misc_off = hstg_off + (EPI == EPI_DGELU ? 4 * NUM_EPI_WG * STG_BYTES : 0);
   float* bias_sm = reinterpret_cast<float*>(base_ptr + misc_off);
   Bars& bar = *reinterpret_cast<Bars*>(base_ptr + misc_off + 256 * sizeof(float));
 
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     prefetch_tensormap(&maps.a);
     prefetch_tensormap(&maps.w);
     prefetch_tensormap(&maps.y);
-    if (EPI == EPI_GELU_SAVE) prefetch_tensormap(&maps.h);
+    if (EPI == EPI_GELU_SAVE || EPI == EPI_DGELU) prefetch_tensormap(&maps.h);
     mbar_init(&bar.w_full, 1);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&bar.a_full[i], 1);
@@ -125,6 +130,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       mbar_init(&bar.acc_full[i], 1);
       mbar_init(&bar.acc_empty[i], 8);  // one arrival per warp of the two warpgroups that drain the buffer
     }
+    for (int i = 0; i < 4 * NUM_EPI_WG; ++i) mbar_init(&bar.h_full[i], 1);
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&bar.tmem_base, 512);
@@ -139,8 +145,13 @@ __global__ void __launch_bounds__(THREADS, 1)
     // ===================================== TMA producer =====================================
     if (lane == 0) {
       mbar_expect_tx(&bar.w_full, p.w_bytes);
-      for (int kc = 0; kc < p.kchunks; ++kc)
-        tma_load_2d(w_sm + kc * (p.BN * 128), &maps.w, &bar.w_full, kc * BK, n0);
+      if (!p.w_mn) {
+        for (int kc = 0; kc < p.kchunks; ++kc)  // K-major: per k-chunk BN rows of 64 channels
+          tma_load_2d(w_sm + kc * (p.BN * 128), &maps.w, &bar.w_full, kc * BK, n0);
+      } else {
+        for (int j = 0; j < p.BN / 64; ++j)     // MN-major: per 64 output columns K rows of 128 B
+          tma_load_2d(w_sm + j * (p.K * 128), &maps.w, &bar.w_full, n0 + j * 64, 0);
+      }
       int it = 0;
       for (int i = 0; i < my_tiles; ++i) {
         const int row0 = (m0 + i * p.m_stride) * BM;
@@ -155,7 +166,12 @@ __global__ void __launch_bounds__(THREADS, 1)
   } else if (warp == 1) {
     // ===================================== MMA issuer ========================================
     mbar_wait(&bar.w_full, 0);
-    const uint32_t a_lo0 = desc_lo_sw64(a_sm), w_lo0 = desc_lo_sw64(w_sm);  // (addr >> 4) | LBO = 1
+    // K-major operands: (addr >> 4) | LBO = 1 (unused); an MN-major weight tile: LBO = bytes between its
+    // 64-column blocks, and a K = 16 step is 16 rows of 128 B
+    const uint32_t a_lo0 = desc_lo_sw64(a_sm);
+    const uint32_t w_lo0 = p.w_mn ? desc_lo_sw128_mn(w_sm, (uint32_t)p.K * 128u) : desc_lo_sw64(w_sm);
+    const uint32_t w_kc = p.w_mn ? (uint32_t)(BK * 128) >> 4 : (uint32_t)(p.BN * 128) >> 4;  // per k-chunk
+    const uint32_t w_k = p.w_mn ? (16u * 128u) >> 4 : 2u;                                     // per K = 16 step
     int it = 0;
     for (int i = 0; i < my_tiles; ++i) {
       const int buf = i & 1;
@@ -165,10 +181,10 @@ __global__ void __launch_bounds__(THREADS, 1)
         mbar_wait(&bar.a_full[s], (it / p.stages) & 1);
         fence_after_sync();
         if (elect_one_sync()) {
-          const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4), w_lo = w_lo0 + kc * ((p.BN * 128) >> 4);
+          const uint32_t a_lo = a_lo0 + s * (A_STAGE_BYTES >> 4), w_lo = w_lo0 + kc * w_kc;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k)  // 16 channels per MMA: 32 B inside the 128-byte swizzled row
-            umma_ss2(tmem + buf * 256, a_lo + k * 2, DESC_HI_SW128, w_lo + k * 2, DESC_HI_SW128, p.idesc,
+            umma_ss2(tmem + buf * 256, a_lo + k * 2, DESC_HI_SW128, w_lo + k * w_k, DESC_HI_SW128, p.idesc,
                      (kc | k) != 0);
           umma_commit(&bar.a_empty[s]);
           if (kc == p.kchunks - 1) umma_commit(&bar.acc_full[buf]);
@@ -189,38 +205,95 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t my_row = stg0 + lane * 64;
     const int sw = (lane >> 1) & 3;
     int sbuf = 0;                             // staging buffer of the next store
+    float colacc[4] = {0.f, 0.f, 0.f, 0.f};   // EPI_DGELU: column (32 cc + lane) of this warp's rows, all tiles
+    // EPI_DGELU: the warp's 32 x 32 box of pre-activations arrives by TMA (64-byte swizzled, rows past M
+    // zero-filled) one chunk AHEAD of its use: thread-per-row global loads touch 32 lines per instruction
+    // and sat un-prefetched in front of every chunk (0.58x of the two-pass path)
+    const uint32_t hstg = base + hstg_off + (uint32_t)(warp - 4) * STG_BYTES;
+    uint64_t* hbar = &bar.h_full[warp - 4];
+    uint32_t hphase = 0;
+    if (EPI == EPI_DGELU && lane == 0 && buf < my_tiles && c_lo < c_hi) {
+      mbar_expect_tx(hbar, STG_BYTES);
+      tma_load_2d(hstg, &maps.h, hbar, n0 + c_lo * 32, (m0 + buf * p.m_stride) * BM + ((warp & 3) << 5));
+    }
     for (int i = buf; i < my_tiles; i += 2) {
       const int row0 = (m0 + i * p.m_stride) * BM + ((warp & 3) << 5);  // first token row of this warp
       mbar_wait(&bar.acc_full[buf], (i >> 1) & 1);
       fence_after_sync();
-      for (int c = c_lo; c < c_hi; ++c) {
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {  // <= 4 chunks per column half (BN <= 256)
+        const int c = c_lo + cc;
+        if (c >= c_hi) break;
+        uint4 hv[4];
         uint32_t r[32];
         tmem_ld32(lane_base + c * 32, r);
-        tmem_wait_ld();
-        const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
-        uint32_t outw[16], hw[16];
+        if (EPI == EPI_DGELU) {  // this row's 32 pre-activations out of the staged box, then prefetch the next box
+          mbar_wait(hbar, hphase);
+          hphase ^= 1;
 #pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float4 bb = b4[q];  // broadcast
-          const float v0 = __uint_as_float(r[4 * q + 0]) + bb.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y;
-          const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z, v3 = __uint_as_float(r[4 * q + 3]) + bb.w;
-          const uint32_t w0 = pack_bf16x2(v0, v1), w1 = pack_bf16x2(v2, v3);
-          if (EPI == EPI_BIAS) {
-            outw[2 * q] = w0;
-            outw[2 * q + 1] = w1;
-          } else {
-            // GELU of the bf16-ROUNDED pre-activation: what nn.GELU sees after a bf16 Linear under autocast,
-            // and exactly what the flat csb200_gelu_fwd pass computes from the stored h
-            hw[2 * q] = w0;
-            hw[2 * q + 1] = w1;
-            outw[2 * q] = gelu_fwd2(w0);
-            outw[2 * q + 1] = gelu_fwd2(w1);
+          for (int q = 0; q < 4; ++q)
+            asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];"
+                         : "=r"(hv[q].x), "=r"(hv[q].y), "=r"(hv[q].z), "=r"(hv[q].w)
+                         : "r"(hstg + lane * 64 + ((q ^ sw) << 4)));
+          __syncwarp();
+          if (lane == 0) {
+            int nc = c + 1, ni = i;
+            if (nc >= c_hi) { nc = c_lo; ni = i + 2; }
+            if (ni < my_tiles) {
+              mbar_expect_tx(hbar, STG_BYTES);
+              tma_load_2d(hstg, &maps.h, hbar, n0 + nc * 32, (m0 + ni * p.m_stride) * BM + ((warp & 3) << 5));
+            }
+          }
+        }
+        tmem_wait_ld();
+        uint32_t outw[16], hw[16];
+        if (EPI == EPI_DGELU) {
+          const uint32_t* hwv = reinterpret_cast<const uint32_t*>(hv);
+          float d[32];
+#pragma unroll
+          for (int j2 = 0; j2 < 16; ++j2) {
+            const f2_t v = gelu_bwd2_f32(f2_make(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1])), hwv[j2]);
+            f2_split(v, d[2 * j2], d[2 * j2 + 1]);
+            outw[j2] = pack_bf16x2(d[2 * j2], d[2 * j2 + 1]);
+          }
+          // column sums over the 32 rows of this warp, from the fp32 values BEFORE the bf16 rounding (one
+          // rounding error less per term than a sum over the stored tensor): transpose-reduce, 31 shuffles;
+          // lane l ends up with column l of the chunk
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int e = 0; e < off; ++e) {
+              const float keep = upper ? d[e + off] : d[e], send = upper ? d[e] : d[e + off];
+              d[e] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+            }
+          }
+          colacc[cc] += d[0];
+        } else {
+          const float4* b4 = reinterpret_cast<const float4*>(bias_sm + c * 32);
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 bb = b4[q];  // broadcast
+            const float v0 = __uint_as_float(r[4 * q + 0]) + bb.x, v1 = __uint_as_float(r[4 * q + 1]) + bb.y;
+            const float v2 = __uint_as_float(r[4 * q + 2]) + bb.z, v3 = __uint_as_float(r[4 * q + 3]) + bb.w;
+            const uint32_t w0 = pack_bf16x2(v0, v1), w1 = pack_bf16x2(v2, v3);
+            if (EPI == EPI_BIAS) {
+              outw[2 * q] = w0;
+              outw[2 * q + 1] = w1;
+            } else {
+              // GELU of the bf16-ROUNDED pre-activation: what nn.GELU sees after a bf16 Linear under autocast,
+              // and exactly what the flat csb200_gelu_fwd pass computes from the stored h
+              hw[2 * q] = w0;
+              hw[2 * q + 1] = w1;
+              outw[2 * q] = gelu_fwd2(w0);
+              outw[2 * q + 1] = gelu_fwd2(w1);
+            }
           }
         }
         // registers -> staging (conflict-free: 8 rows cover the 32 banks) -> one TMA store per 32 x 32 box
 #pragma unroll
         for (int v = 0; v < (EPI == EPI_GELU_SAVE ? 2 : 1); ++v) {
-          const uint32_t (&src)[16] = v == 0 ? outw : hw;
+          const uint32_t (&src)[16] = (v == 0 || EPI != EPI_GELU_SAVE) ? outw : hw;
           if (lane == 0) {
             if (p.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
           }
@@ -243,10 +316,38 @@ __global__ void __launch_bounds__(THREADS, 1)
       if (lane == 0) mbar_arrive(&bar.acc_empty[buf]);
     }
     if (lane == 0) bulk_wait_all();  // the staged boxes have been read AND written before the CTA retires
+    if (EPI == EPI_DGELU) {
+      // per-CTA column sums: 16 warps x 4 chunks x 32 lanes through the (now idle) staging area, added in a
+      // fixed order; the per-CTA rows are summed by linear_colsum_final (deterministic)
+      __syncwarp();
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NUM_EPI_WG) : "memory");
+      float* cs = reinterpret_cast<float*>(base_ptr + stg_off);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) cs[((warp - 4) * 4 + cc) * 32 + lane] = colacc[cc];
+      asm volatile("bar.sync 1, %0;" ::"n"(128 * NUM_EPI_WG) : "memory");
+      for (int col = (int)threadIdx.x - 128; col < p.BN; col += 128 * NUM_EPI_WG) {
+        const int c = col >> 5, hf = c >= (chunks + 1) / 2 ? 1 : 0, cc = c - (hf ? (chunks + 1) / 2 : 0);
+        float a = 0.f;
+#pragma unroll
+        for (int b = 0; b < 2; ++b)
+#pragma unroll
+          for (int rw = 0; rw < 4; ++rw) a += cs[(((b + 2 * hf) * 4 + rw) * 4 + cc) * 32 + (col & 31)];
+        p.partial[(int64_t)m0 * p.N + n0 + col] = a;
+      }
+    }
   }
   fence_before_sync();
   __syncthreads();
   if (warp == 2) tmem_dealloc(tmem, 512);
+}
+
+// out[c] = sum over the per-CTA rows of partial[blocks][cols] (one warp per column, fixed order)
+__global__ void __launch_bounds__(256)
+    linear_colsum_final(const float* __restrict__ partial, int blocks, int cols, float* __restrict__ out) {
+  const int i = (blockIdx.x * 256 + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  if (i >= cols) return;
+  const float a = strided_partial_sum(partial + i, blocks, cols, lane);
+  if (lane == 0) out[i] = a;
 }
 
 int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int64_t ld, int box_rows,
@@ -265,16 +366,84 @@ int make_map_2d(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, i
   return CSB200_OK;
 }
 
-// n-tile width: the largest multiple of 32 that divides N, is <= 256 and whose resident weight tile leaves
-// room for at least 3 ring stages
-int pick_bn(int64_t N, int64_t K) {
-  for (int bn = 256; bn >= 32; bn -= 32) {
+// n-tile width: the largest multiple of `step` that divides N, is <= 256 and whose resident weight tile
+// leaves room for at least 3 ring stages and the store staging
+int pick_bn(int64_t N, int64_t K, int step = 32) {
+  // step 64 == the input-gradient form (EPI_DGELU): it also stages the pre-activation boxes
+  const int staging = (step == 64 ? 2 : 1) * 4 * NUM_EPI_WG * STG_BYTES;
+  for (int bn = 256; bn >= step; bn -= step) {
     if (N % bn != 0) continue;
     const int64_t w_bytes = (int64_t)bn * K * 2;
-    if (w_bytes + 3 * A_STAGE_BYTES + 16 * STG_BYTES + 4096 <= SMEM_LIMIT) return bn;
+    if (w_bytes + 4 * A_STAGE_BYTES + staging + 4096 <= SMEM_LIMIT) return bn;
   }
   return 0;
 }
+
+bool shape_ok(int64_t M, int64_t N, int64_t K, int dtype, int step) {
+  if (dtype != CSB200_BF16) return false;
+  if (M < 1 || M > 0x7fffffff / 2 || N < step || N > 65536) return false;
+  if (K != 64 && K != 128 && K != 256) return false;
+  return pick_bn(N, K, step) != 0;
+}
+
+// x [M][K] (row stride ldx) times the weight (w_mn ? [K][N] : [N][K]) -> y [M][N], epilogue EPI
+int launch_linear(int epilogue, bool w_mn, const void* x, const void* weight, const float* bias, void* y,
+                  void* pre_act, float* partial, int* partial_rows, int64_t M, int64_t N, int64_t K, int64_t ldx,
+                  cudaStream_t st) {
+  LinMaps maps;
+  LinParams p;
+  memset(&maps, 0, sizeof(maps));
+  memset(&p, 0, sizeof(p));
+  p.M = (int)M; p.N = (int)N; p.K = (int)K;
+  p.BN = pick_bn(N, K, w_mn ? 64 : 32);
+  p.n_tiles = (int)(N / p.BN);
+  p.m_tiles = (int)((M + BM - 1) / BM);
+  p.kchunks = (int)(K / BK);
+  p.w_bytes = (uint32_t)(p.BN * K * 2);
+  p.w_mn = w_mn ? 1 : 0;
+  // two staging buffers per epilogue warp when that still leaves >= 4 ring stages
+  const int misc = 256 * (int)sizeof(float) + (int)sizeof(Bars) + 1024 +
+                   (epilogue == EPI_DGELU ? 4 * NUM_EPI_WG * STG_BYTES : 0);
+  p.stage_bufs = (SMEM_LIMIT - (int)p.w_bytes - misc - 2 * 4 * NUM_EPI_WG * STG_BYTES) / A_STAGE_BYTES >= 5 ? 2 : 1;
+  const int fixed = (int)p.w_bytes + misc + p.stage_bufs * 4 * NUM_EPI_WG * STG_BYTES;
+  p.stages = (SMEM_LIMIT - fixed) / A_STAGE_BYTES;
+  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.idesc = umma_idesc_bf16(p.BN, false, w_mn);
+  p.bias = bias;
+  p.y = static_cast<__nv_bfloat16*>(y);
+  p.h = static_cast<__nv_bfloat16*>(pre_act);
+  p.partial = partial;
+  int rc;
+  if ((rc = make_map_2d(&maps.a, x, K, M, ldx, BM)) != CSB200_OK) return rc;
+  if (!w_mn) rc = make_map_2d(&maps.w, weight, K, N, K, p.BN);
+  else rc = make_map_2d(&maps.w, weight, N, K, N, (int)K);  // box: 64 output columns x all K rows
+  if (rc != CSB200_OK) return rc;
+  if ((rc = make_map_2d(&maps.y, y, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK) return rc;
+  if ((epilogue == EPI_GELU_SAVE || epilogue == EPI_DGELU) &&
+      (rc = make_map_2d(&maps.h, pre_act, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK)
+    return rc;
+  const int sms = device_sm_count();
+  if (sms <= 0) return fail(CSB200_ERR_CUDA, "csb200_linear: cannot query the SM count");
+  int per_n = sms / p.n_tiles;              // CTAs per n-tile
+  if (per_n < 1) per_n = 1;
+  if (per_n > p.m_tiles) per_n = p.m_tiles;
+  p.m_stride = per_n;
+  if (partial_rows != nullptr) *partial_rows = per_n;
+  const int grid = per_n * p.n_tiles;
+  const int smem = fixed + p.stages * A_STAGE_BYTES;
+  const void* fn = epilogue == EPI_BIAS ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_BIAS>)
+                   : epilogue == EPI_GELU ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU>)
+                   : epilogue == EPI_GELU_SAVE ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU_SAVE>)
+                                               : reinterpret_cast<const void*>(&linear_tc_kernel<EPI_DGELU>);
+  CSB200_CUDA(opt_in_smem(fn, SMEM_LIMIT));
+  if (epilogue == EPI_BIAS) linear_tc_kernel<EPI_BIAS><<<grid, THREADS, smem, st>>>(maps, p);
+  else if (epilogue == EPI_GELU) linear_tc_kernel<EPI_GELU><<<grid, THREADS, smem, st>>>(maps, p);
+  else if (epilogue == EPI_GELU_SAVE) linear_tc_kernel<EPI_GELU_SAVE><<<grid, THREADS, smem, st>>>(maps, p);
+  else linear_tc_kernel<EPI_DGELU><<<grid, THREADS, smem, st>>>(maps, p);
+  return check_launch("linear_tc_kernel");
+}
+
+constexpr int MAX_PARTIAL_ROWS = 160;
 
 }  // namespace
 }  // namespace csb200
@@ -284,10 +453,7 @@ using namespace csb200;
 extern "C" {
 
 CSB200_API int csb200_linear_supported(int64_t M, int64_t N, int64_t K, int dtype) {
-  if (dtype != CSB200_BF16) return 0;
-  if (M < 1 || M > 0x7fffffff / 2 || N < 32 || N > 65536) return 0;
-  if (K != 64 && K != 128 && K != 256) return 0;
-  return pick_bn(N, K) != 0;
+  return shape_ok(M, N, K, dtype, 32) ? 1 : 0;
 }
 
 CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float* bias, void* y, void* pre_act, int64_t M,
@@ -297,56 +463,49 @@ CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float*
     return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: null pointer");
   if (epilogue < 0 || epilogue > 2 || (epilogue == EPI_GELU_SAVE && pre_act == nullptr))
     return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: bad epilogue %d", epilogue);
-  if (!csb200_linear_supported(M, N, K, dtype))
+  if (!shape_ok(M, N, K, dtype, 32))
     return fail(CSB200_ERR_UNSUPPORTED, "csb200_linear_fwd: bf16 with K in {64,128,256} and N a multiple of 32 only "
                 "(M %lld, N %lld, K %lld)", (long long)M, (long long)N, (long long)K);
   if (ldx < K || (ldx * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(weight) & 15) ||
       (reinterpret_cast<uintptr_t>(y) & 15) || (reinterpret_cast<uintptr_t>(pre_act) & 15))
     return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: operands must be 16-byte aligned (ldx %lld)", (long long)ldx);
+  return launch_linear(epilogue, false, x, weight, bias, y, pre_act, nullptr, nullptr, M, N, K, ldx,
+                       static_cast<cudaStream_t>(stream));
+}
+
+CSB200_API int csb200_linear_dgelu_supported(int64_t M, int64_t N, int64_t K, int dtype) {
+  return shape_ok(M, N, K, dtype, 64) ? 1 : 0;
+}
+
+CSB200_API size_t csb200_linear_dgelu_workspace_bytes(int64_t N) {
+  return (size_t)MAX_PARTIAL_ROWS * (size_t)N * sizeof(float) + 256;
+}
+
+CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
+                                       float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
+                                       int64_t N, int64_t K, int64_t ldg, int dtype, void* stream) {
+  if (M == 0) return CSB200_OK;
+  if (grad_y == nullptr || weight == nullptr || pre_act == nullptr || grad_h == nullptr || grad_bias == nullptr ||
+      workspace == nullptr)
+    return fail(CSB200_ERR_INVALID, "csb200_linear_dgelu_bwd: null pointer");
+  if (!shape_ok(M, N, K, dtype, 64))
+    return fail(CSB200_ERR_UNSUPPORTED, "csb200_linear_dgelu_bwd: bf16 with K in {64,128,256} and N a multiple of 64 "
+                "only (M %lld, N %lld, K %lld)", (long long)M, (long long)N, (long long)K);
+  if (workspace_bytes < csb200_linear_dgelu_workspace_bytes(N))
+    return fail(CSB200_ERR_WORKSPACE, "csb200_linear_dgelu_bwd: workspace too small");
+  if (ldg < K || (ldg * 2) % 16 != 0 || (reinterpret_cast<uintptr_t>(grad_y) & 15) ||
+      (reinterpret_cast<uintptr_t>(weight) & 15) || (reinterpret_cast<uintptr_t>(pre_act) & 15) ||
+      (reinterpret_cast<uintptr_t>(grad_h) & 15))
+    return fail(CSB200_ERR_INVALID, "csb200_linear_dgelu_bwd: operands must be 16-byte aligned (ldg %lld)", (long long)ldg);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  LinMaps maps;
-  LinParams p;
-  memset(&maps, 0, sizeof(maps));
-  memset(&p, 0, sizeof(p));
-  p.M = (int)M; p.N = (int)N; p.K = (int)K;
-  p.BN = pick_bn(N, K);
-  p.n_tiles = (int)(N / p.BN);
-  p.m_tiles = (int)((M + BM - 1) / BM);
-  p.kchunks = (int)(K / BK);
-  p.w_bytes = (uint32_t)(p.BN * K * 2);
-  // two staging buffers per epilogue warp when that still leaves >= 4 ring stages
-  const int misc = 256 * (int)sizeof(float) + (int)sizeof(Bars) + 1024;
-  p.stage_bufs = (SMEM_LIMIT - (int)p.w_bytes - misc - 2 * 4 * NUM_EPI_WG * STG_BYTES) / A_STAGE_BYTES >= 4 ? 2 : 1;
-  const int fixed = (int)p.w_bytes + misc + p.stage_bufs * 4 * NUM_EPI_WG * STG_BYTES;
-  p.stages = (SMEM_LIMIT - fixed) / A_STAGE_BYTES;
-  if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
-  p.idesc = umma_idesc_bf16(p.BN, false, false);
-  p.bias = bias;
-  p.y = static_cast<__nv_bfloat16*>(y);
-  p.h = static_cast<__nv_bfloat16*>(pre_act);
-  int rc;
-  if ((rc = make_map_2d(&maps.a, x, K, M, ldx, BM)) != CSB200_OK) return rc;
-  if ((rc = make_map_2d(&maps.w, weight, K, N, K, p.BN)) != CSB200_OK) return rc;
-  if ((rc = make_map_2d(&maps.y, y, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK) return rc;
-  if (pre_act != nullptr &&
-      (rc = make_map_2d(&maps.h, pre_act, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK)
-    return rc;
-  const int sms = device_sm_count();
-  if (sms <= 0) return fail(CSB200_ERR_CUDA, "csb200_linear_fwd: cannot query the SM count");
-  int per_n = sms / p.n_tiles;              // CTAs per n-tile
-  if (per_n < 1) per_n = 1;
-  if (per_n > p.m_tiles) per_n = p.m_tiles;
-  p.m_stride = per_n;
-  const int grid = per_n * p.n_tiles;
-  const int smem = fixed + p.stages * A_STAGE_BYTES;
-  const void* fn = epilogue == EPI_BIAS ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_BIAS>)
-                   : epilogue == EPI_GELU ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU>)
-                                          : reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU_SAVE>);
-  CSB200_CUDA(opt_in_smem(fn, SMEM_LIMIT));
-  if (epilogue == EPI_BIAS) linear_tc_kernel<EPI_BIAS><<<grid, THREADS, smem, st>>>(maps, p);
-  else if (epilogue == EPI_GELU) linear_tc_kernel<EPI_GELU><<<grid, THREADS, smem, st>>>(maps, p);
-  else linear_tc_kernel<EPI_GELU_SAVE><<<grid, THREADS, smem, st>>>(maps, p);
-  return check_launch("linear_tc_kernel");
+  float* partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
+  int rows = 0;
+  int rc = launch_linear(EPI_DGELU, true, grad_y, weight, nullptr, grad_h, const_cast<void*>(pre_act), partial, &rows,
+                         M, N, K, ldg, st);
+  if (rc != CSB200_OK) return rc;
+  if (rows > MAX_PARTIAL_ROWS) return fail(CSB200_ERR_WORKSPACE, "csb200_linear_dgelu_bwd: %d partial rows", rows);
+  linear_colsum_final<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(partial, rows, (int)N, grad_bias);
+  return check_launch("linear_colsum_final");
 }
 
 }  // extern "C"

@@ -513,6 +513,83 @@ class _LinearGeluFn(torch.autograd.Function):
         return gx, gw, (gb.to(b_dtype) if ctx.needs_input_grad[2] else None), None
 
 
+def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor):
+    """(grad_h, grad_bias) = csb200_linear_dgelu_bwd: grad_h = (g W2) * GELU'(h) in one tcgen05 GEMM."""
+    M, K = g2.shape
+    N = w2c.shape[1]
+    lib = capi.lib()
+    dh = torch.empty((M, N), dtype=torch.bfloat16, device=g2.device)
+    gb = torch.empty(N, dtype=torch.float32, device=g2.device)
+    nws = lib.csb200_linear_dgelu_workspace_bytes(N)
+    wsp = torch.empty(nws, dtype=torch.uint8, device=g2.device)
+    nbytes = 2 * (M * K + N * K + 2 * M * N)
+    with torch.cuda.device(g2.device), _span("linear_tc", nbytes, 2 * M * N * K, f"M{M}xN{N}xK{K}dgelu"):
+        capi.check(lib.csb200_linear_dgelu_bwd(_ptr(g2), _ptr(w2c), _ptr(h2), _ptr(dh), _ptr(gb), _ptr(wsp), nws, M, N, K,
+                                               g2.stride(0), capi.BF16, _vp(capi.stream_of(g2))),
+                   "csb200_linear_dgelu_bwd")
+    return dh, gb
+
+
+class _MlpFn(torch.autograd.Function):
+    """y = fc2(GELU(fc1(x))) — Mlp.forward, C:188-196 (dropout 0) — with the activation inside the GEMMs that
+    surround it: forward = tcgen05 fc1 whose epilogue stores h and GELU(h), then fc2 on cuBLAS; backward =
+    ONE tcgen05 GEMM for grad_h = (grad_y W2) * GELU'(h) that also emits the fc1 bias gradient, then the
+    weight gradients and the fc1 input gradient on cuBLAS.  Neither flat GELU pass runs."""
+
+    @staticmethod
+    @torch.amp.custom_fwd(device_type="cuda")
+    def forward(ctx, x, w1, b1, w2, b2):
+        xc = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
+        w1c, w2c = cast_param(w1, torch.bfloat16), cast_param(w2, torch.bfloat16)
+        x2 = xc.reshape(-1, xc.shape[-1])
+        a, h = _tc_linear(x2, w1c, b1, capi.EPI_GELU_SAVE)
+        y = torch.nn.functional.linear(a, w2c, cast_param(b2, torch.bfloat16))
+        ctx.save_for_backward(x2, w1c, w2c, h, a)
+        ctx.meta = (x.dtype, x.shape, w1.dtype, b1.dtype, w2.dtype, None if b2 is None else b2.dtype)
+        return y.view(*x.shape[:-1], w2c.shape[0])
+
+    @staticmethod
+    @torch.amp.custom_bwd(device_type="cuda")
+    def backward(ctx, gy):
+        x2, w1c, w2c, h, a = ctx.saved_tensors
+        x_dtype, x_shape, w1_dtype, b1_dtype, w2_dtype, b2_dtype = ctx.meta
+        g2 = gy.reshape(-1, w2c.shape[0])
+        if g2.dtype != torch.bfloat16 or not g2.is_contiguous():
+            g2 = g2.to(torch.bfloat16).contiguous()
+        dh, gb1 = _tc_dgelu(g2, w2c, h)
+        gx = gw1 = gw2 = gb2 = None
+        if ctx.needs_input_grad[0]:
+            gx = torch.mm(dh, w1c).view(x_shape).to(x_dtype)
+        if ctx.needs_input_grad[1]:
+            gw1 = _wgrad(dh, x2, w1_dtype)
+        if ctx.needs_input_grad[3]:
+            gw2 = _wgrad(g2, a, w2_dtype)
+        if b2_dtype is not None and ctx.needs_input_grad[4]:
+            gb2 = _bias_grad(g2, g2.shape[1]).to(b2_dtype)
+        return gx, gw1, (gb1.to(b1_dtype) if ctx.needs_input_grad[2] else None), gw2, gb2
+
+
+def mlp_fused_supported(x: torch.Tensor, w1: torch.Tensor, b1, w2: torch.Tensor) -> bool:
+    """bf16 autocast (or bf16 input), K = C in {64, 128, 256}, hidden width a multiple of 64, and the fused path
+    switched on (TC_LINEAR["gelu"])."""
+    if not TC_LINEAR["gelu"] or b1 is None or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
+        return False
+    dt = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled("cuda") else x.dtype
+    if dt != torch.bfloat16 or w2.shape[1] != w1.shape[0] or w2.shape[0] != w1.shape[1]:
+        return False
+    M = x.numel() // x.shape[-1]
+    N, K = w1.shape
+    lib = capi.lib()
+    return bool(lib.csb200_linear_supported(M, N, K, capi.BF16)) and bool(lib.csb200_linear_dgelu_supported(M, N, K, capi.BF16))
+
+
+def mlp_fused(x, w1, b1, w2, b2, defer_fc2_bias_grad: bool = False) -> torch.Tensor:
+    """fc2(GELU(fc1(x))) through _MlpFn.  ``defer_fc2_bias_grad``: as in ``linear``."""
+    if defer_fc2_bias_grad and b2 is not None:
+        b2 = b2.detach()
+    return _MlpFn.apply(x, w1, b1, w2, b2)
+
+
 def linear_gelu_supported(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
     if bias is None or not x.is_cuda or x.dtype not in (torch.float32, torch.bfloat16):
         return False

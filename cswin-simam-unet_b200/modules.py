@@ -155,7 +155,14 @@ class Mlp(nn.Module):
         self.drop = nn.Dropout(drop)
 
     def forward(self, x, defer_fc2_bias_grad: bool = False):
-        if type(self.fc1) is nn.Linear and type(self.act) is nn.GELU and self.act.approximate == "none" \
+        exact_gelu = type(self.act) is nn.GELU and self.act.approximate == "none"
+        if exact_gelu and type(self.fc1) is nn.Linear and type(self.fc2) is nn.Linear \
+                and (self.drop.p == 0.0 or not self.training) \
+                and csbF.mlp_fused_supported(x, self.fc1.weight, self.fc1.bias, self.fc2.weight):
+            # the activation rides in the epilogues of the tcgen05 GEMMs on both sides of it (C:188-196)
+            return csbF.mlp_fused(x, self.fc1.weight, self.fc1.bias, self.fc2.weight, self.fc2.bias,
+                                  defer_fc2_bias_grad)
+        if type(self.fc1) is nn.Linear and exact_gelu \
                 and csbF.linear_gelu_supported(x, self.fc1.weight, self.fc1.bias):
             hidden = csbF.linear_gelu(x, self.fc1.weight, self.fc1.bias)  # fc1 + GELU, fused passes
         else:

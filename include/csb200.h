@@ -161,6 +161,18 @@ CSB200_API int csb200_linear_supported(int64_t M, int64_t N, int64_t K, int dtyp
 CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float* bias, void* y, void* pre_act,
                                  int64_t M, int64_t N, int64_t K, int64_t ldx, int dtype, int epilogue,
                                  void* stream);
+/* Backward of `Mlp.fc2(act(h))` with respect to h (C:190-195) as ONE tcgen05 GEMM with the GELU' factor and
+ * the fc1 bias gradient in its epilogue:
+ *     grad_h = (grad_y W2) * GELU'(pre_act),     grad_bias[n] = sum_m grad_h[m][n]   (of the ROUNDED grad_h)
+ * grad_y: [M][K] (row stride ldg), weight = fc2.weight: [K][N] (nn.Linear(N, K).weight, read in place as the
+ * MN-major operand: no transposed copy), pre_act / grad_h: [M][N], grad_bias: fp32 [N].  Replaces the cuBLAS
+ * input-gradient GEMM + the flat csb200_gelu_bwd pass (1 write + 1 read of the 4C-wide tensor less).
+ * Supported: bf16, K in {64, 128, 256}, N a multiple of 64.  workspace: csb200_linear_dgelu_workspace_bytes(N). */
+CSB200_API int csb200_linear_dgelu_supported(int64_t M, int64_t N, int64_t K, int dtype);
+CSB200_API size_t csb200_linear_dgelu_workspace_bytes(int64_t N);
+CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
+                                       float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
+                                       int64_t N, int64_t K, int64_t ldg, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step for every parameter tensor of the model in one launch — `optimizer.step()` of the

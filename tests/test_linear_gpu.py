@@ -91,3 +91,35 @@ def test_mlp_through_the_fused_path_matches_the_two_pass_path():
     csbF.set_tc_linear(gelu=True)
     for a, b in zip(outs[True], outs[False]):
         assert rel_err(a, b) < 2 ** -6
+
+
+@pytest.mark.parametrize("shape", [(4096, 64, 256), (2048, 128, 512), (1024, 256, 1024), (1000, 64, 128), (77, 128, 256),
+                                   (300 * 128 + 5, 64, 256), (19000, 256, 512)])
+def test_dgelu_backward_gemm_matches_fp32_reference(shape):
+    """csb200_linear_dgelu_bwd: grad_h = (grad_y W2) * GELU'(h) and its column sums against fp32 torch on the same
+    bf16 operands (GELU' by autograd of the exact-erf GELU), and against the two-pass path it replaces."""
+    M, K, N = shape
+    g = torch.Generator().manual_seed(M + 3 * N)
+    gy = torch.randn((M, K), generator=g).to(torch.bfloat16).cuda()
+    w2 = (torch.randn((K, N), generator=g) / K ** 0.5).to(torch.bfloat16).cuda()   # fc2.weight: (out = K, in = N)
+    h = (torch.randn((M, N), generator=g) * 1.5).to(torch.bfloat16).cuda()
+    assert capi.lib().csb200_linear_dgelu_supported(M, N, K, capi.BF16)
+    dh, gb = csbF._tc_dgelu(gy, w2, h)
+    hf = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).backward(gy.float() @ w2.float())
+    ref = hf.grad
+    assert rel_err(dh.float(), ref) < 2 ** -8
+    # the bias gradient sums the fp32 values before their bf16 rounding: close to the fp32 reference, and within
+    # the rounding noise (2^-9 per term) of a sum over the stored tensor
+    assert rel_err(gb, ref.sum(0)) < 1e-3
+    assert rel_err(gb, dh.float().sum(0)) < 1e-2
+    # the two-pass path: cuBLAS input gradient (rounded to bf16) + flat GELU' pass
+    da = torch.mm(gy, w2)
+    flat = torch.empty_like(da)
+    gb2 = torch.empty(N, dtype=torch.float32, device="cuda")
+    lib = capi.lib()
+    nws = lib.csb200_gelu_bwd_workspace_bytes(N)
+    wsp = torch.empty(nws, dtype=torch.uint8, device="cuda")
+    capi.check(lib.csb200_gelu_bwd(csbF._ptr(da), csbF._ptr(h), csbF._ptr(flat), csbF._ptr(gb2), csbF._ptr(wsp), nws, M, N,
+                                   capi.BF16, csbF._vp(capi.stream_of(h))), "csb200_gelu_bwd")
+    assert rel_err(dh.float(), ref) <= rel_err(flat.float(), ref) + 2 ** -10
