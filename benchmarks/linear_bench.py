@@ -95,5 +95,37 @@ def main():
         del xs
 
 
+def wgrad_bench(only):
+    """csb200_linear_wgrad (+ bias gradient) vs cuBLAS split-K wgrad + csb200 column-sum pass."""
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.isfile(
+        os.path.join(ROOT, "MEASURED_PEAKS.json")) else {"hbm_gbs": 6650.0}
+    shapes = {}
+    for st, (tok, C) in {"s1": (524288, 64), "s2": (131072, 128), "s3": (32768, 256), "s4": (8192, 512)}.items():
+        shapes.update({f"{st}.qkv": (tok, 3 * C, C), f"{st}.proj": (tok, C, C), f"{st}.fc1": (tok, 4 * C, C),
+                       f"{st}.fc2": (tok, C, 4 * C)})
+    for name, (M, N, K) in shapes.items():
+        if only and only not in name:
+            continue
+        nbuf = max(2, int(300e6 // (2 * M * (K + N))) + 1)
+        gs = [torch.randn(M, N, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+        xs = [torch.randn(M, K, device="cuda").to(torch.bfloat16) for _ in range(nbuf)]
+        us = timed(lambda i: csbF._tc_wgrad(gs[i], xs[i], True), nbuf)
+
+        def cublas(i):
+            return torch.mm(gs[i].t(), xs[i], out_dtype=torch.float32), csbF._bias_grad(gs[i], N)
+        base = timed(cublas, nbuf)
+        base_nobias = timed(lambda i: torch.mm(gs[i].t(), xs[i], out_dtype=torch.float32), nbuf)
+        nbytes = 2 * M * (N + K) + 4 * N * K
+        print(json.dumps({"shape": name + ".wgrad", "M": M, "N": N, "K": K, "csb200_us": round(us, 2),
+                          "cublas_plus_colsum_us": round(base, 2), "cublas_wgrad_only_us": round(base_nobias, 2),
+                          "speedup": round(base / us, 3), "alg_gbs": round(nbytes / us / 1e3, 1),
+                          "hbm_frac": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3),
+                          "tflops": round(2 * M * N * K / us / 1e6, 1)}), flush=True)
+        del gs, xs
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "wgrad":
+        wgrad_bench(sys.argv[2] if len(sys.argv) > 2 else "")
+        sys.exit(0)
     main()

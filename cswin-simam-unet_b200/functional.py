@@ -351,14 +351,14 @@ def cast_param(p: Optional[torch.Tensor], dtype: torch.dtype) -> Optional[torch.
 
 # Which Linear layers run on the csb200 tcgen05 GEMM (csb200_linear_fwd, K = C in {64, 128, 256}, bf16):
 # "gelu": Mlp.fc1 + GELU with the activation in the epilogue; "plain": qkv / proj (bias-only epilogue).
-TC_LINEAR = {"gelu": True, "plain": True}
+# "wgrad": the weight (+ bias) gradients of those layers in one streaming tcgen05 pass (csb200_linear_wgrad).
+TC_LINEAR = {"gelu": True, "plain": True, "wgrad": True}
 
 
-def set_tc_linear(gelu: Optional[bool] = None, plain: Optional[bool] = None):
-    if gelu is not None:
-        TC_LINEAR["gelu"] = bool(gelu)
-    if plain is not None:
-        TC_LINEAR["plain"] = bool(plain)
+def set_tc_linear(gelu: Optional[bool] = None, plain: Optional[bool] = None, wgrad: Optional[bool] = None):
+    for key, val in (("gelu", gelu), ("plain", plain), ("wgrad", wgrad)):
+        if val is not None:
+            TC_LINEAR[key] = val if val == "always" else bool(val)  # wgrad="always": ignore the token-count policy
 
 
 def _tc_linear_ok(x2: torch.Tensor, wc: torch.Tensor, bias: Optional[torch.Tensor]) -> bool:
@@ -414,10 +414,15 @@ class _LinearFn(torch.autograd.Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.mm(g2, wc).reshape(xc.shape).to(x_dtype)
-        if ctx.needs_input_grad[1]:
-            gw = _wgrad(g2, x2, w_dtype)
-        if b_dtype is not None and ctx.needs_input_grad[2]:
-            gb = _bias_grad(g2, n).to(b_dtype)
+        want_b = b_dtype is not None and ctx.needs_input_grad[2]
+        if ctx.needs_input_grad[1] and _tc_wgrad_ok(g2, x2, w_dtype, want_b):
+            gw, gb = _tc_wgrad(g2, x2, want_b)  # the bias gradient rides in the same streaming pass
+            gb = None if gb is None else gb.to(b_dtype)
+        else:
+            if ctx.needs_input_grad[1]:
+                gw = _wgrad(g2, x2, w_dtype)
+            if want_b:
+                gb = _bias_grad(g2, n).to(b_dtype)
         return gx, gw, gb, None
 
 
@@ -436,9 +441,41 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
     return _LinearFn.apply(x, weight, bias, dt)
 
 
+# Measured (profiles/r2_wgrad_bench.jsonl): csb200_linear_wgrad runs at 0.87-0.89 of the HBM roofline on the
+# stage-1 token counts (= cuBLAS split-K) and always beats cuBLAS + a column-sum pass when the bias gradient is
+# wanted (1.2-1.9x); on the short token counts of stages 2-4 cuBLAS alone is 10-25 % faster (fixed costs: two
+# memsets, 24-deep vector reductions on an output of a few hundred KB), so those stay on cuBLAS.
+WGRAD_MIN_TOKENS = 262144
+
+
+def _tc_wgrad_ok(g2: torch.Tensor, x2: torch.Tensor, w_dtype: torch.dtype, want_bias: bool = True) -> bool:
+    if not TC_LINEAR["wgrad"] or w_dtype != torch.float32 or g2.dtype != torch.bfloat16 or x2.dtype != torch.bfloat16:
+        return False
+    if not want_bias and g2.shape[0] < WGRAD_MIN_TOKENS and TC_LINEAR["wgrad"] != "always":
+        return False
+    if g2.stride(1) != 1 or x2.stride(1) != 1 or g2.data_ptr() % 16 or x2.data_ptr() % 16 \
+            or (g2.stride(0) * 2) % 16 or (x2.stride(0) * 2) % 16:
+        return False
+    return bool(capi.lib().csb200_linear_wgrad_supported(g2.shape[0], g2.shape[1], x2.shape[1], capi.BF16))
+
+
+def _tc_wgrad(g2: torch.Tensor, x2: torch.Tensor, want_bias: bool):
+    """(grad_W fp32 [N][K], grad_b fp32 [N] or None) = csb200_linear_wgrad(g2 [M][N], x2 [M][K])."""
+    M, N = g2.shape
+    K = x2.shape[1]
+    gw = torch.empty((N, K), dtype=torch.float32, device=g2.device)
+    gb = torch.empty(N, dtype=torch.float32, device=g2.device) if want_bias else None
+    with torch.cuda.device(g2.device), _span("wgrad_tc", 2 * M * (N + K) + 4 * N * K, 2 * M * N * K, f"M{M}xN{N}xK{K}"):
+        capi.check(capi.lib().csb200_linear_wgrad(_ptr(g2), _ptr(x2), _ptr(gw), _ptr(gb), M, N, K, g2.stride(0),
+                                                  x2.stride(0), capi.BF16, _vp(capi.stream_of(g2))), "csb200_linear_wgrad")
+    return gw, gb
+
+
 def _wgrad(g2: torch.Tensor, x2: torch.Tensor, w_dtype: torch.dtype) -> torch.Tensor:
     """grad_W = g^T x with the output written in the master-weight dtype by the GEMM itself (fp32
     accumulators stored unrounded; no bf16 -> fp32 cast kernel per layer)."""
+    if _tc_wgrad_ok(g2, x2, w_dtype, want_bias=False):
+        return _tc_wgrad(g2, x2, False)[0]
     if g2.is_cuda and g2.dtype == torch.bfloat16 and w_dtype == torch.float32:
         return torch.mm(g2.t(), x2, out_dtype=torch.float32)
     return torch.mm(g2.t(), x2).to(w_dtype)
@@ -562,10 +599,15 @@ class _MlpFn(torch.autograd.Function):
             gx = torch.mm(dh, w1c).view(x_shape).to(x_dtype)
         if ctx.needs_input_grad[1]:
             gw1 = _wgrad(dh, x2, w1_dtype)
-        if ctx.needs_input_grad[3]:
-            gw2 = _wgrad(g2, a, w2_dtype)
-        if b2_dtype is not None and ctx.needs_input_grad[4]:
-            gb2 = _bias_grad(g2, g2.shape[1]).to(b2_dtype)
+        want_b2 = b2_dtype is not None and ctx.needs_input_grad[4]
+        if ctx.needs_input_grad[3] and _tc_wgrad_ok(g2, a, w2_dtype, want_b2):
+            gw2, gb2 = _tc_wgrad(g2, a, want_b2)
+            gb2 = None if gb2 is None else gb2.to(b2_dtype)
+        else:
+            if ctx.needs_input_grad[3]:
+                gw2 = _wgrad(g2, a, w2_dtype)
+            if want_b2:
+                gb2 = _bias_grad(g2, g2.shape[1]).to(b2_dtype)
         return gx, gw1, (gb1.to(b1_dtype) if ctx.needs_input_grad[2] else None), gw2, gb2
 
 

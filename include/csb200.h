@@ -174,6 +174,16 @@ CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, c
                                        float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
                                        int64_t N, int64_t K, int64_t ldg, int dtype, void* stream);
 
+/* Parameter gradients of a token-path nn.Linear (backward of C:357-358, C:366, C:188-196 w.r.t. weight / bias):
+ *     grad_w[N][K] = grad_y[M][N]^T x[M][K],      grad_bias[n] = sum_m grad_y[m][n]   (nullable)
+ * bf16 operands (row strides ldg / ldx elements), fp32 outputs, OVERWRITTEN (zeroed inside, then accumulated by
+ * vector reductions: the summation order over the token splits is not fixed).  One streaming tcgen05 pass
+ * over both operands, the bias gradient included; replaces the split-K GEMM + reduce kernel + column-sum pass.
+ * Supported: bf16, N a multiple of 8, K a multiple of 64. */
+CSB200_API int csb200_linear_wgrad_supported(int64_t M, int64_t N, int64_t K, int dtype);
+CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M,
+                                   int64_t N, int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream);
+
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step for every parameter tensor of the model in one launch — `optimizer.step()` of the
  * reference train loop (C:786) with torch.optim.AdamW (C:937-941, decoupled decay) or torch.optim.Adam

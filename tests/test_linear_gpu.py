@@ -123,3 +123,41 @@ def test_dgelu_backward_gemm_matches_fp32_reference(shape):
     capi.check(lib.csb200_gelu_bwd(csbF._ptr(da), csbF._ptr(h), csbF._ptr(flat), csbF._ptr(gb2), csbF._ptr(wsp), nws, M, N,
                                    capi.BF16, csbF._vp(capi.stream_of(h))), "csb200_gelu_bwd")
     assert rel_err(dh.float(), ref) <= rel_err(flat.float(), ref) + 2 ** -10
+
+
+# (M, N, K): the four Linear layers of a CSWinBlock at the config-3 widths (stage 1-4 geometry, token counts
+# reduced), ragged token counts, N below one tile, K spanning several column tiles
+WGRAD_SHAPES = [(8192, 192, 64), (8192, 64, 64), (8192, 256, 64), (8192, 64, 256), (4096, 384, 128), (4096, 128, 512),
+                (4096, 768, 256), (2048, 256, 1024), (1024, 1536, 512), (1024, 512, 2048), (1000, 64, 64),
+                (77, 128, 128), (300 * 128 + 5, 192, 64), (19000, 1024, 256), (4096, 8, 64)]
+
+
+@pytest.mark.parametrize("shape", WGRAD_SHAPES)
+def test_wgrad_and_bias_gradient_match_fp32_reference(shape):
+    """csb200_linear_wgrad: grad_W = g^T x and grad_b = column sums of g, fp32 accumulation of bf16 operands,
+    against fp64 torch on the same operands; tolerance 1e-4 of the largest entry (fp32 summation noise over
+    up to 38 405 tokens; the operands themselves are exact)."""
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(M + N + K)
+    g = torch.randn((M, N), generator=gen).to(torch.bfloat16).cuda()
+    x = torch.randn((M, K), generator=gen).to(torch.bfloat16).cuda()
+    assert csbF._tc_wgrad_ok(g, x, torch.float32)
+    gw, gb = csbF._tc_wgrad(g, x, True)
+    ref_w = g.double().t() @ x.double()
+    ref_b = g.double().sum(0)
+    assert rel_err(gw, ref_w) < 1e-4
+    assert rel_err(gb, ref_b) < 1e-4
+    gw2, none = csbF._tc_wgrad(g, x, False)
+    assert none is None and rel_err(gw2, ref_w) < 1e-4
+    cublas = torch.mm(g.t(), x, out_dtype=torch.float32)
+    assert rel_err(gw, ref_w) <= rel_err(cublas, ref_w) + 1e-5
+
+
+def test_wgrad_on_strided_operands():
+    """Channel slices of wider token matrices (row stride > width), as the backward of a packed qkv sees them."""
+    gen = torch.Generator().manual_seed(5)
+    big_g = torch.randn((3000, 320), generator=gen).to(torch.bfloat16).cuda()
+    big_x = torch.randn((3000, 256), generator=gen).to(torch.bfloat16).cuda()
+    g, x = big_g[:, 64:256], big_x[:, 128:]
+    gw, gb = csbF._tc_wgrad(g, x, True)
+    assert rel_err(gw, g.double().t() @ x.double()) < 1e-4 and rel_err(gb, g.double().sum(0)) < 1e-4
