@@ -243,7 +243,11 @@ def run_ours(args, rank, local_rank, world):
         opt = pkg.FusedAdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
     else:
         opt = torch.optim.AdamW(net.parameters(), lr=1e-4, weight_decay=1e-4, fused=True, capturable=use_graph)
-    reducer = pkg.GradientAllReducer(net.parameters()) if world > 1 else None
+    # Data parallel: ONE flat bucket (94 MB fp32), all-reduced after backward INSIDE the captured graph.  Measured on
+    # 2 GPUs (profiles/r2_dp_overlap_experiment.txt): overlapping the all-reduce with backward costs more than it
+    # hides here — NCCL's CTAs take SMs away from the persistent one-CTA-per-SM kernels, whose last CTAs then run as
+    # a second wave (step +1.08 ms) — while one exposed all-reduce on NVLink / NVSwitch is ~0.3 ms.
+    reducer = pkg.GradientAllReducer(net.parameters(), bucket_bytes=1 << 30, overlap=False) if world > 1 else None
     step = pkg.TrainStep(net, opt, precision="bf16", reducer=reducer, cuda_graph=use_graph)
     # the roofline needs CUDA events around individual kernels, which a graph replay cannot give:
     # an eager twin of the step (same model, same optimizer) is timed in a separate pass
@@ -341,8 +345,7 @@ def run_ours(args, rank, local_rank, world):
             raise RuntimeError(f"replicas diverged: parameter checksums {vals}")
 
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
+        finish_distributed(world)
         return
     pk, pk_src = peaks()
     roof_all = {}
@@ -413,6 +416,10 @@ def run_ours(args, rank, local_rank, world):
                    "precision": "autocast bf16, fp32 master weights, fp32 sigmoid+BCE", "optimizer": "AdamW, one csb200_adam_step launch" if args.optimizer == "csb200" else "AdamW (torch fused)",
                    "dropout": 0.0, "parallelism": f"dp{world}", "attn_engine": args.attn_engine,
                    "cuda_graph": bool(use_graph),
+                   "dp_allreduce": (None if world == 1 else
+                                    ("NCCL AVG, one fp32 bucket, captured in the graph after backward"
+                                     if getattr(step, "_reduce_in_graph", False) else
+                                     "NCCL AVG, fp32 buckets, issued eagerly between the two graphs")),
                    "l2": "no explicit flush: one step streams several GB of activations (>> 126 MB L2)",
                    "peak_mem_gib": round(mem_gb, 2)},
         "e2e": {"value": B * world * args.steps / (ms_e2e / 1e3), "unit": UNIT, "h2d_bytes_per_step": h2d,
@@ -429,8 +436,22 @@ def run_ours(args, rank, local_rank, world):
     if gpu_ref is not None:
         line["gpu_eager_baseline"] = gpu_ref
     print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    finish_distributed(world)
+
+
+def finish_distributed(world):
+    """End of a rank.  CUDA graphs that captured NCCL kernels are still alive here and tearing the communicator
+    down under them can block (observed: destroy_process_group() never returned after the JSON line was printed),
+    so after a last barrier every rank leaves without running destructors."""
+    if world <= 1:
+        return
+    try:
+        dist.barrier()
+        torch.cuda.synchronize()
+    finally:
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 def main():

@@ -203,11 +203,11 @@ class TrainStep:
             with torch.cuda.graph(self._graph_opt, pool=self._graph.pool()):
                 self._optimizer_step()
             return
-        # Data parallel: graph 1 = forward + backward with the bucket all-reduces CAPTURED as backward produces
-        # them (NCCL's stream is forked from / joined to the capture by events), so on replay the gradient
-        # exchange overlaps the rest of backward exactly as in the eager step and nothing is issued from the
-        # host between the graphs; graph 2 = optimizer step.  If the process group cannot be captured (gloo, an
-        # old NCCL) the all-reduces stay eager between the two graphs.
+        # Data parallel: graph 1 = forward + backward + the bucket all-reduces, CAPTURED (NCCL's stream is forked
+        # from / joined to the capture by events), so nothing is issued from the host between the graphs; graph 2 =
+        # optimizer step.  With ``reducer.overlap`` the all-reduce of a bucket is recorded as soon as backward has
+        # produced its last gradient (it then runs under the rest of backward), otherwise after backward.  If the
+        # process group cannot be captured (gloo, an old NCCL) the all-reduces stay eager between the two graphs.
         self._reduce_in_graph = self.reducer.world > 1 and self.reducer.capturable and self.capture_collectives
         try:
             self._capture_dp_graph(in_graph=self._reduce_in_graph)
@@ -226,7 +226,8 @@ class TrainStep:
             self._optimizer_step()
 
     def _capture_dp_graph(self, in_graph: bool):
-        self.reducer.overlap = in_graph
+        if not in_graph:
+            self.reducer.overlap = False  # the hooks must not launch eager collectives inside a capture
         with torch.cuda.graph(self._graph):
             self.reducer.begin_step()
             loss = self.forward_loss(self._x, self._y)

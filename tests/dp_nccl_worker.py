@@ -53,7 +53,9 @@ def main():
     # ---- 2. three captured data-parallel AdamW steps (all-reduce inside the graph) == global-batch steps ----
     for capture in (True, False):
         net = make_net(dev)
-        red = pkg.GradientAllReducer(net.parameters())
+        # captured: ONE bucket all-reduced after backward (what bench.py runs); eager: bucketed + overlapped
+        red = pkg.GradientAllReducer(net.parameters(), bucket_bytes=1 << 30, overlap=False) if capture \
+            else pkg.GradientAllReducer(net.parameters())
         opt = pkg.FusedAdamW(net.parameters(), lr=1e-3, weight_decay=1e-4)
         step = pkg.TrainStep(net, opt, precision="fp32", reducer=red, cuda_graph=True, capture_collectives=capture)
         for s in range(3):
