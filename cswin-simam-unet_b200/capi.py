@@ -24,7 +24,9 @@ class StripeDesc(ctypes.Structure):
                 ("heads", ctypes.c_int32), ("head_dim", ctypes.c_int32), ("scale", ctypes.c_float),
                 ("engine", ctypes.c_int32)] + [
         (n, ctypes.c_int64) for n in ("q_sb", "q_sl", "k_sb", "k_sl", "v_sb", "v_sl", "o_sb", "o_sl",
-                                      "dq_sb", "dq_sl", "dk_sb", "dk_sl", "dv_sb", "dv_sl")]
+                                      "dq_sb", "dq_sl", "dk_sb", "dk_sl", "dv_sb", "dv_sl")] + [
+        ("drop_p", ctypes.c_float), ("drop_salt", ctypes.c_int32), ("rng_state", ctypes.c_void_p),
+        ("drop_mask", ctypes.c_void_p)]
 
 
 class BranchIO(ctypes.Structure):
@@ -136,7 +138,7 @@ def lib() -> ctypes.CDLL:
         for fn in ("csb200_simam_fwd", "csb200_simam_bwd", "csb200_stripe_attn_engine",
                    "csb200_stripe_attn_fwd", "csb200_stripe_attn_bwd"):
             getattr(L, fn).restype = ctypes.c_int
-        if L.csb200_abi_version() != 1:
+        if L.csb200_abi_version() != 2:
             raise RuntimeError("libcsb200.so ABI version mismatch; rebuild")
         _lib = L
     return _lib

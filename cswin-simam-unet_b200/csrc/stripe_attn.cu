@@ -108,6 +108,25 @@ int make_geom(const csb200_stripe_desc* d, bool backward, StripeGeom* g) {
   g->dq_sb = d->dq_sb; g->dq_sl = d->dq_sl;
   g->dk_sb = d->dk_sb; g->dk_sl = d->dk_sl;
   g->dv_sb = d->dv_sb; g->dv_sl = d->dv_sl;
+  g->drop_thr = 0;
+  g->keep_scale = 1.f;
+  g->mask_words = (g->N + 31) / 32;
+  g->drop_salt = (uint32_t)d->drop_salt;
+  g->rng = nullptr;
+  g->drop_mask = nullptr;
+  if (d->drop_p != 0.f) {
+    if (!(d->drop_p > 0.f) || !(d->drop_p < 1.f))
+      return fail(CSB200_ERR_INVALID, "stripe_attn: drop_p must be in [0, 1), got %g", (double)d->drop_p);
+    const int thr = (int)(d->drop_p * 256.f + 0.5f);
+    if (thr > 0) {
+      if (d->drop_mask == nullptr || (!backward && d->rng_state == nullptr))
+        return fail(CSB200_ERR_INVALID, "stripe_attn: drop_p > 0 needs drop_mask (and rng_state in forward)");
+      g->drop_thr = (uint32_t)(thr > 255 ? 255 : thr);
+      g->keep_scale = 256.f / (256.f - (float)g->drop_thr);
+      g->rng = reinterpret_cast<const unsigned long long*>(d->rng_state);
+      g->drop_mask = d->drop_mask;
+    }
+  }
   return CSB200_OK;
 }
 
@@ -217,7 +236,7 @@ bool mergeable(const csb200_stripe_desc* d, const StripeGeom* g, int n, bool bac
   for (int i = 0; i < 2; ++i)
     if (pick_engine(&d[i], g[i], backward) != CSB200_ENGINE_TCGEN05) return false;
   return g[0].N == g[1].N && g[0].B == g[1].B && g[0].H == g[1].H && g[0].W == g[1].W &&
-         g[0].scale == g[1].scale && d[0].dtype == d[1].dtype;
+         g[0].scale == g[1].scale && d[0].dtype == d[1].dtype && g[0].drop_thr == g[1].drop_thr;
 }
 }  // namespace
 

@@ -13,6 +13,13 @@ struct StripeGeom {
   float scale;
   int64_t q_sb, q_sl, k_sb, k_sl, v_sb, v_sl, o_sb, o_sl;
   int64_t dq_sb, dq_sl, dk_sb, dk_sl, dv_sb, dv_sl;
+  // attention dropout (csb200_stripe_desc.drop_p): a probability is DROPPED when its random byte < drop_thr
+  uint32_t drop_thr;        // 0 = off; p = drop_thr / 256
+  float keep_scale;         // 1 / (1 - p)
+  int mask_words;           // ceil(N / 32)
+  uint32_t drop_salt;
+  const unsigned long long* rng;  // device [2]: seed, call counter (forward)
+  uint32_t* drop_mask;      // [B][heads][L][mask_words] transposed keep bits
 };
 
 // ---- CUDA-core engine (stripe_attn_simt.cu) ---------------------------------------------------

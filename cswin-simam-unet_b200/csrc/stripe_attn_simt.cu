@@ -16,6 +16,7 @@
 #include <cstring>
 #include <type_traits>
 
+#include "philox.cuh"
 #include "stripe_attn.cuh"
 
 namespace csb200 {
@@ -214,6 +215,18 @@ __global__ void __launch_bounds__(ROWS)
 #pragma unroll
   for (int c = 0; c < HD; ++c) acc[c] = 0.f;
   float m = -INFINITY, l = 0.f;
+  // attention dropout (C:290): keep decisions per (query, key) from Philox, 16 keys per call; the warp's 32
+  // decisions for a key are one ballot word of the TRANSPOSED mask the backward kernels read back
+  const bool drop = g.drop_thr != 0;
+  DropRng rng;
+  uint32_t unit = 0;
+  uint4 rb = make_uint4(0u, 0u, 0u, 0u);
+  if (drop) {
+    rng = drop_rng_load(g.rng);
+    unit = drop_unit(g, w.b, w.wy, w.wx, w.head);
+  }
+  const int iw = (w.tile * ROWS + (int)threadIdx.x) >> 5;  // mask word of this warp's 32 query rows
+  uint32_t* mrow = drop ? g.drop_mask + ((int64_t)w.b * g.heads + w.head) * g.L * g.mask_words + iw : nullptr;
 
   for (int j0 = 0; j0 < g.N; j0 += CHUNK) {
     const int cnt = min(CHUNK, g.N - j0);
@@ -222,6 +235,7 @@ __global__ void __launch_bounds__(ROWS)
     load_chunk<T>(s_v, vb, g.v_sl, g, w, j0, cnt, 1.f);
     __syncthreads();
     for (int j = 0; j < cnt; j += 8) {
+      if (drop && ((j & 15) == 0)) rb = drop_bytes(rng, unit, (uint32_t)n, (uint32_t)((j0 + j) >> 4));
       float s[8];
       float mx = m;
 #pragma unroll
@@ -237,15 +251,22 @@ __global__ void __launch_bounds__(ROWS)
       for (int u = 0; u < 8; ++u) {
         if (j + u < cnt) {
           const float p = Exp<T>::f(s[u] - mx);
-          l += p;
-          axpy_smem(acc, p, s_v + (j + u) * HD);
+          l += p;  // the softmax normalisation is over ALL probabilities; dropout acts on the normalised ones
+          bool keep = true;
+          if (drop) {
+            keep = drop_byte(rb, j + u) >= g.drop_thr;
+            const uint32_t bits = __ballot_sync(0xffffffffu, keep);
+            if ((threadIdx.x & 31) == 0 && iw < g.mask_words)
+              mrow[(int64_t)token_of(g, w, j0 + j + u) * g.mask_words] = bits;
+          }
+          if (keep) axpy_smem(acc, p, s_v + (j + u) * HD);
         }
       }
       m = mx;
     }
   }
   if (!valid) return;
-  const float inv_l = 1.f / l;
+  const float inv_l = g.keep_scale / l;  // survivors are scaled by 1 / (1 - p)
   float o[HD];
 #pragma unroll
   for (int c = 0; c < HD; ++c) o[c] = s_b[c];
@@ -291,6 +312,11 @@ __global__ void __launch_bounds__(ROWS)
   }
   const T* kb = k + (int64_t)w.b * g.k_sb + co;
   const T* vb = v + (int64_t)w.b * g.v_sb + co;
+  // dropout: bit (query % 32) of the forward pass's mask word [key token][query / 32]
+  const bool drop = g.drop_thr != 0;
+  const int iw = (w.tile * ROWS + (int)threadIdx.x) >> 5, lane = threadIdx.x & 31;
+  const uint32_t* mrow = drop && iw < g.mask_words
+                             ? g.drop_mask + ((int64_t)w.b * g.heads + w.head) * g.L * g.mask_words + iw : nullptr;
   for (int j0 = 0; j0 < g.N; j0 += CHUNK) {
     const int cnt = min(CHUNK, g.N - j0);
     __syncthreads();
@@ -300,7 +326,11 @@ __global__ void __launch_bounds__(ROWS)
     for (int j = 0; j < cnt; ++j) {
       const float s = dot_smem(qs, s_k + j * HD);
       const float p = Exp<T>::f(s - lse_i);
-      const float dp = dot_smem(go, s_v + j * HD);
+      float dp = dot_smem(go, s_v + j * HD);
+      if (mrow != nullptr) {  // d(dropped P) / dP = keep / (1 - p)
+        const uint32_t bits = __ldg(mrow + (int64_t)token_of(g, w, j0 + j) * g.mask_words);
+        dp = ((bits >> lane) & 1u) ? dp * g.keep_scale : 0.f;
+      }
       axpy_smem(acc, p * (dp - delta_i), s_k + j * HD);
     }
   }
@@ -355,11 +385,21 @@ __global__ void __launch_bounds__(ROWS)
       s_delta[threadIdx.x] = delta[sbase + t];
     }
     __syncthreads();
+    // dropout: this key's own mask row holds the keep bits of all queries (CHUNK = 64 queries = 2 words)
+    uint32_t m0 = 0xffffffffu, m1 = 0xffffffffu;
+    if (g.drop_thr != 0 && valid) {
+      const uint32_t* mrow = g.drop_mask + (sbase + tok) * g.mask_words + (i0 >> 5);
+      m0 = __ldg(mrow);
+      if ((i0 >> 5) + 1 < g.mask_words) m1 = __ldg(mrow + 1);
+    }
+    const float ks = g.keep_scale;
     for (int i = 0; i < cnt; ++i) {
       const float s = dot_smem(kr, s_q + i * HD);
       const float p = Exp<T>::f(s - s_lse[i]);
-      axpy_smem(av, p, s_g + i * HD);
-      const float dp = dot_smem(vr, s_g + i * HD);
+      const bool keep = (((i < 32 ? m0 : m1) >> (i & 31)) & 1u) != 0;
+      float dp = dot_smem(vr, s_g + i * HD);
+      if (keep) axpy_smem(av, p * ks, s_g + i * HD);  // dV = (dropped P)^T dO
+      dp = keep ? dp * ks : 0.f;
       axpy_smem(ak, p * (dp - s_delta[i]), s_q + i * HD);
     }
   }

@@ -26,6 +26,7 @@
 #include <cstring>
 #include <mutex>
 
+#include "philox.cuh"
 #include "stripe_attn.cuh"
 #include "tc_common.cuh"
 
@@ -108,6 +109,8 @@ struct FwdBranch {
   __nv_bfloat16* out;
   int64_t o_sb, o_sl;
   float* lse;
+  uint32_t* drop_mask;  // attention dropout: [B][heads][L][N / 32] transposed keep bits (written here)
+  uint32_t drop_salt;
 };
 struct FwdParams {
   int B, W, L;
@@ -115,6 +118,9 @@ struct FwdParams {
   int groups;          // B * gpi
   float scale_log2;    // scale * log2(e)
   float scale;
+  uint32_t drop_thr;   // attention dropout (stripe_attn.cuh); 0 in the <.., false> instantiation
+  float keep_scale;
+  const unsigned long long* rng;
   FwdBranch br[2];
 };
 struct FwdMaps {
@@ -175,7 +181,7 @@ __device__ __forceinline__ GroupCoord decode_group(const FwdParams& p, int g) {
   return c;
 }
 
-template <int NK>
+template <int NK, bool DROP>
 __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     stripe_fwd_tc(const __grid_constant__ FwdMaps maps, const __grid_constant__ FwdParams p) {
   constexpr int T = NK / TILE;          // query tiles per group
@@ -351,17 +357,63 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       const float neg_m = -m * p.scale_log2;
       PROF_T(t2);
       float l0 = 0.f, l1 = 0.f;
+      // attention dropout (C:290): the stripe coordinates of the group are needed before the epilogue
+      DropRng rng;
+      uint32_t unit = 0;
+      uint32_t* mask_row = nullptr;  // this group's mask rows, offset to the word of this warp's 32 queries
+      int d_tok0 = 0, d_wsl = 0, d_ws1 = 0, d_nw = 0;
+      if constexpr (DROP) {
+        mbar_wait(&sm.v_full[vs], (gi / VS) & 1);  // sm.coord rides on the V barrier
+        const int4 gc = sm.coord[vs];
+        const FwdBranch& bg = p.br[gc.w];
+        rng = drop_rng_load(p.rng);
+        const int y0 = gc.y / p.W, x0 = gc.y - y0 * p.W;
+        unit = ((uint32_t)(((gc.x * bg.nwy + y0 / bg.hs) * bg.nwx + x0 / bg.ws) * bg.heads + gc.z) << 1) |
+               (bg.drop_salt & 1u);
+        d_nw = NK / 32;
+        mask_row = bg.drop_mask + ((int64_t)gc.x * bg.heads + gc.z) * p.L * d_nw + (t * TILE + ((warp & 3) << 5)) / 32;
+        d_tok0 = gc.y; d_wsl = bg.ws_log2; d_ws1 = bg.ws - 1;
+      }
       auto exp_chunk = [&](const uint32_t (&r)[32], int ch) {
         uint32_t pk[16];
+        uint32_t kw = 0xffffffffu;  // keep bits of keys 32 ch .. 32 ch + 31 for this query row
+        if constexpr (DROP) {
+          const uint32_t thr4 = p.drop_thr * 0x01010101u;
+          kw = 0u;
+#pragma unroll
+          for (int hb = 0; hb < 2; ++hb) {
+            const uint4 rb = drop_bytes(rng, unit, (uint32_t)(t * TILE + row), (uint32_t)(2 * ch + hb));
+            const uint32_t wds[4] = {rb.x, rb.y, rb.z, rb.w};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)  // byte >= threshold -> one keep bit per byte, gathered into a nibble
+              kw |= ((((__vcmpgeu4(wds[q], thr4) & 0x01010101u) * 0x01020408u) >> 24) & 0xfu) << (16 * hb + 4 * q);
+          }
+        }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
-          const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
-          l0 += p0;
+          float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
+          float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+          l0 += p0;  // the normalisation runs over ALL probabilities
           l1 += p1;
+          if constexpr (DROP) {
+            p0 = (kw >> (2 * i)) & 1u ? p0 : 0.f;
+            p1 = (kw >> (2 * i + 1)) & 1u ? p1 : 0.f;
+          }
           pk[i] = pack_bf16x2(p0, p1);
         }
         tmem_st16(lane_base + P_COL + ch * 16, pk);  // P over S columns that were already consumed
+        if constexpr (DROP) {
+          // transposed mask for the backward pass: the warp's 32 decisions for key j are one ballot word
+          uint32_t mine = 0u;
+#pragma unroll
+          for (int jl = 0; jl < 32; ++jl) {
+            const uint32_t bal = __ballot_sync(0xffffffffu, (kw >> jl) & 1u);
+            mine = lane == jl ? bal : mine;
+          }
+          const int j = ch * 32 + lane;
+          const int tokj = d_tok0 + (j >> d_wsl) * p.W + (j & d_ws1);
+          mask_row[(int64_t)tokj * d_nw] = mine;
+        }
       };
       tmem_ld32(lane_base, ra);
       tmem_wait_ld();
@@ -396,7 +448,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
       const int4 gc = sm.coord[vs];  // image, first token of the stripe, head, branch
       const FwdBranch& bg = p.br[gc.w];
-      const float inv_l = 1.f / l;
+      const float inv_l = (DROP ? p.keep_scale : 1.f) / l;  // survivors are scaled by 1 / (1 - p)
       PROF_T(t4a);
       const int n = t * TILE + row;  // in-stripe index
       const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
@@ -484,19 +536,30 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
     b.out = static_cast<__nv_bfloat16*>(io[i].out);
     b.o_sb = g[i].o_sb; b.o_sl = g[i].o_sl;
     b.lse = io[i].lse;
+    b.drop_mask = g[i].drop_mask;
+    b.drop_salt = g[i].drop_salt;
     if (i == 0) p.g0 = g[i].nwy * g[i].nwx * g[i].heads;
     gpi += g[i].nwy * g[i].nwx * g[i].heads;
   }
   p.gpi = gpi;
   p.groups = p.B * gpi;
+  p.drop_thr = g[0].drop_thr;
+  p.keep_scale = g[0].keep_scale;
+  p.rng = g[0].rng;
+  const bool drop = p.drop_thr != 0;
 
   // > half of the 227 KB so that exactly one CTA (which owns all 512 TMEM columns) fits per SM
   const int smem = (int)sizeof(Smem<NK>) + 1024 > 120 * 1024 ? (int)sizeof(Smem<NK>) + 1024 : 120 * 1024;
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return fail(CSB200_ERR_CUDA, "stripe_fwd_tc: cannot query the SM count");
-  CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK>), smem));
   const int grid = p.groups < sm_count ? p.groups : sm_count;
-  stripe_fwd_tc<NK><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
+  if (drop) {
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, true>), smem));
+    stripe_fwd_tc<NK, true><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
+  } else {
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, false>), smem));
+    stripe_fwd_tc<NK, false><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
+  }
   return check_launch("stripe_fwd_tc");
 }
 

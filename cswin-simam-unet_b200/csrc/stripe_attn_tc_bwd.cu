@@ -61,11 +61,13 @@ struct BwdBranch {
   const float* delta;   // [B][heads][L]
   __nv_bfloat16 *dq, *dk, *dv;
   int64_t dq_sb, dq_sl, dk_sb, dk_sl, dv_sb, dv_sl;
+  const uint32_t* drop_mask;  // attention dropout: the forward pass's transposed keep bits
 };
 struct BwdParams {
   int B, W, L;
   int g0, gpi, groups;  // groups per image of branch 0 / of both; B * gpi
   float scale, scale_log2;
+  float keep_scale;     // 1 / (1 - p) of the attention dropout (1 in the <.., false> instantiation)
   BwdBranch br[2];
 };
 struct BwdMaps {
@@ -106,7 +108,7 @@ __device__ __forceinline__ const uint4* sw64_chunk(const uint8_t* tile, int n, i
   return reinterpret_cast<const uint4*>(tile + n * ROW_BYTES + ((chunk ^ ((n >> 1) & 3)) << 4));
 }
 
-template <int NK>
+template <int NK, bool DROP>
 __global__ void __launch_bounds__(THREADS, 1)
     stripe_bwd_tc(const __grid_constant__ BwdMaps maps, const __grid_constant__ BwdParams p) {
   constexpr int T = NK / TILE;      // key tiles (and 128-query blocks) per group
@@ -298,6 +300,16 @@ __global__ void __launch_bounds__(THREADS, 1)
       const int qbc = (gi * T + kt) * T + (qh >> 1), dsb = qbc & 1;
       PROF_T(c0);
       mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);   // lse / delta visibility (already complete)
+      // attention dropout: this key's mask row holds the keep bits of the 64 queries of the half-block
+      uint2 mw = make_uint2(0xffffffffu, 0xffffffffu);
+      if constexpr (DROP) {
+        const int4 gc = sm.coord[gs];
+        const BwdBranch& bg = p.br[gc.w];
+        const int nj = kt * TILE + j;
+        const int tokj = gc.y + (nj >> bg.ws_log2) * p.W + (nj & (bg.ws - 1));
+        mw = __ldg(reinterpret_cast<const uint2*>(
+            bg.drop_mask + (((int64_t)gc.x * bg.heads + gc.z) * p.L + tokj) * (NK / 32) + qh * 2));
+      }
       mbar_wait(&sm.ds_free[dsb], ((qbc >> 1) & 1) ^ 1);
       PROF_T(c1);
       mbar_wait(&sm.sdp_full[wg], (x >> 1) & 1);
@@ -321,6 +333,21 @@ __global__ void __launch_bounds__(THREADS, 1)
           const float p1 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 1]), p.scale_log2, -l4.y));
           const float p2 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 2]), p.scale_log2, -l4.z));
           const float p3 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 3]), p.scale_log2, -l4.w));
+          if constexpr (DROP) {
+            // dropped P (the A operand of dV) = keep / (1 - p) * P, and dP reaches P through the same factor
+            const uint32_t kb = (c == 0 ? mw.x : mw.y) >> (4 * e4);
+            const float k0 = kb & 1u ? p.keep_scale : 0.f, k1 = kb & 2u ? p.keep_scale : 0.f;
+            const float k2 = kb & 4u ? p.keep_scale : 0.f, k3 = kb & 8u ? p.keep_scale : 0.f;
+            const float s0 = p0 * p.scale * (__uint_as_float(rd[4 * e4 + 0]) * k0 - d4.x);
+            const float s1 = p1 * p.scale * (__uint_as_float(rd[4 * e4 + 1]) * k1 - d4.y);
+            const float s2 = p2 * p.scale * (__uint_as_float(rd[4 * e4 + 2]) * k2 - d4.z);
+            const float s3 = p3 * p.scale * (__uint_as_float(rd[4 * e4 + 3]) * k3 - d4.w);
+            pp[2 * e4] = pack_bf16x2(p0 * k0, p1 * k1);
+            pp[2 * e4 + 1] = pack_bf16x2(p2 * k2, p3 * k3);
+            pd[2 * e4] = pack_bf16x2(s0, s1);
+            pd[2 * e4 + 1] = pack_bf16x2(s2, s3);
+            continue;
+          }
           const float s0 = p0 * p.scale * (__uint_as_float(rd[4 * e4 + 0]) - d4.x);
           const float s1 = p1 * p.scale * (__uint_as_float(rd[4 * e4 + 1]) - d4.y);
           const float s2 = p2 * p.scale * (__uint_as_float(rd[4 * e4 + 2]) - d4.z);
@@ -491,17 +518,25 @@ int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st)
     b.dv = static_cast<__nv_bfloat16*>(io[i].dv);
     b.dq_sb = g[i].dq_sb; b.dq_sl = g[i].dq_sl; b.dk_sb = g[i].dk_sb; b.dk_sl = g[i].dk_sl;
     b.dv_sb = g[i].dv_sb; b.dv_sl = g[i].dv_sl;
+    b.drop_mask = g[i].drop_mask;
     if (i == 0) p.g0 = g[i].nwy * g[i].nwx * g[i].heads;
     gpi += g[i].nwy * g[i].nwx * g[i].heads;
   }
   p.gpi = gpi;
   p.groups = p.B * gpi;
+  p.keep_scale = g[0].keep_scale;
+  const bool drop = g[0].drop_thr != 0;
   const int smem = (int)sizeof(BSmem<NK>) + 1024;  // > 113 KB: one CTA (all 512 TMEM columns) per SM
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return fail(CSB200_ERR_CUDA, "stripe_bwd_tc: cannot query the SM count");
-  CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_bwd_tc<NK>), smem));
   const int grid = p.groups < sm_count ? p.groups : sm_count;
-  stripe_bwd_tc<NK><<<grid, THREADS, smem, st>>>(maps, p);
+  if (drop) {
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_bwd_tc<NK, true>), smem));
+    stripe_bwd_tc<NK, true><<<grid, THREADS, smem, st>>>(maps, p);
+  } else {
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_bwd_tc<NK, false>), smem));
+    stripe_bwd_tc<NK, false><<<grid, THREADS, smem, st>>>(maps, p);
+  }
   return check_launch("stripe_bwd_tc");
 }
 

@@ -799,7 +799,34 @@ class Branch:
         self.h_sp, self.w_sp, self.heads, self.chan0, self.chans = h_sp, w_sp, heads, chan0, chans
 
 
-def _desc(dtype_code, B, H, W, br: Branch, scale, engine, qkv_strides, o_strides, g_strides=None):
+# ---- attention dropout (`attn = self.attn_drop(attn)`, C:290) -------------------------------------------------
+# The keep decisions are generated INSIDE the forward kernels (Philox4x32-10) from a device-resident
+# (seed, call counter) pair, so a captured CUDA graph draws a fresh mask on every replay; the forward kernel
+# writes the mask as bits and the backward kernels read it back (include/csb200.h, csb200_stripe_desc.drop_p).
+_drop_state = {}
+KEEP_LAST_DROP_MASKS = False   # tests: keep the masks of the last forward call in `last_drop_masks`
+last_drop_masks = None
+
+
+def attention_dropout_state(device) -> torch.Tensor:
+    """int64 [2] on `device`: seed, number of attention calls drawn so far."""
+    dev = torch.device(device)
+    idx = dev.index if dev.index is not None else torch.cuda.current_device()
+    st = _drop_state.get(idx)
+    if st is None:
+        st = _drop_state[idx] = torch.tensor([torch.initial_seed() & (2 ** 62 - 1), 0], dtype=torch.int64,
+                                             device=torch.device("cuda", idx))
+    return st
+
+
+def seed_attention_dropout(seed: int, device=None, counter: int = 0) -> None:
+    """(Re)seed the attention-dropout generator of `device` (default: the current CUDA device)."""
+    st = attention_dropout_state(device if device is not None else torch.device("cuda", torch.cuda.current_device()))
+    st.copy_(torch.tensor([seed & (2 ** 62 - 1), counter], dtype=torch.int64))
+
+
+def _desc(dtype_code, B, H, W, br: Branch, scale, engine, qkv_strides, o_strides, g_strides=None,
+          drop=None):
     d = capi.StripeDesc()
     d.dtype, d.batch, d.height, d.width = dtype_code, B, H, W
     d.h_sp, d.w_sp, d.heads, d.head_dim = br.h_sp, br.w_sp, br.heads, br.chans // br.heads
@@ -808,6 +835,10 @@ def _desc(dtype_code, B, H, W, br: Branch, scale, engine, qkv_strides, o_strides
     d.o_sb, d.o_sl = o_strides
     if g_strides is not None:
         (d.dq_sb, d.dq_sl), (d.dk_sb, d.dk_sl), (d.dv_sb, d.dv_sl) = g_strides
+    if drop is not None:  # (p, salt, rng state tensor or None, mask tensor)
+        d.drop_p, d.drop_salt = float(drop[0]), int(drop[1])
+        d.rng_state = None if drop[2] is None else drop[2].data_ptr()
+        d.drop_mask = drop[3].data_ptr()
     return d
 
 
@@ -836,7 +867,8 @@ class _CrossStripeFn(torch.autograd.Function):
 
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
-    def forward(ctx, qkv, H, W, branches, scale, engine, *wb):
+    def forward(ctx, qkv, H, W, branches, scale, engine, drop_p, *wb):
+        global last_drop_masks
         capi.require_cuda(qkv)
         qkv = qkv.contiguous()
         B, L, C3 = qkv.shape
@@ -853,8 +885,18 @@ class _CrossStripeFn(torch.autograd.Function):
         descs = (capi.StripeDesc * n)()
         ios = (capi.BranchIO * n)()
         nbytes = flops = 0
+        masks, used = [], None
+        if drop_p > 0:  # one call counter per attention call, advanced on the device (graph-capturable)
+            state = attention_dropout_state(qkv.device)
+            used = state.clone()
+            state[1:].add_(1)
+            masks = [torch.empty((B, b.heads, L, (b.h_sp * b.w_sp + 31) // 32), dtype=torch.int32, device=qkv.device)
+                     for b in branches]
+            if KEEP_LAST_DROP_MASKS:
+                last_drop_masks = masks
         for i, br in enumerate(branches):
-            descs[i] = _desc(code, B, H, W, br, scale, engine, [(L * C3, C3)] * 3, (L * C, C))
+            descs[i] = _desc(code, B, H, W, br, scale, engine, [(L * C3, C3)] * 3, (L * C, C),
+                             drop=(drop_p, i, used, masks[i]) if drop_p > 0 else None)
             io = ios[i]
             io.q, io.k, io.v = (_ptr(qkv, br.chan0).value, _ptr(qkv, C + br.chan0).value,
                                 _ptr(qkv, 2 * C + br.chan0).value)
@@ -864,16 +906,17 @@ class _CrossStripeFn(torch.autograd.Function):
             nbytes, flops = nbytes + w_[0], flops + w_[1]
         with torch.cuda.device(qkv.device), _span("attn_fwd", nbytes, flops, _attn_tag(B, L, C, branches)):
             capi.check(lib.csb200_cross_stripe_attn_fwd(n, descs, ios, st), "csb200_cross_stripe_attn_fwd")
-        ctx.save_for_backward(qkv, out, *lses, *ws)
-        ctx.cfg = (H, W, branches, scale, engine)
+        ctx.save_for_backward(qkv, out, *lses, *ws, *masks)
+        ctx.cfg = (H, W, branches, scale, engine, drop_p)
         return out
 
     @staticmethod
     @torch.amp.custom_bwd(device_type="cuda")
     def backward(ctx, gout):
-        H, W, branches, scale, engine = ctx.cfg
+        H, W, branches, scale, engine, drop_p = ctx.cfg
         qkv, out, *rest = ctx.saved_tensors
-        lses, ws = rest[:len(branches)], rest[len(branches):]
+        nb = len(branches)
+        lses, ws, masks = rest[:nb], rest[nb:3 * nb], rest[3 * nb:]
         B, L, C3 = qkv.shape
         C = C3 // 3
         code = capi.dtype_code(qkv)
@@ -890,7 +933,8 @@ class _CrossStripeFn(torch.autograd.Function):
         nbytes = flops = 0
         for i, br in enumerate(branches):
             s3 = [(L * C3, C3)] * 3
-            descs[i] = _desc(code, B, H, W, br, scale, engine, s3, (L * C, C), s3)
+            descs[i] = _desc(code, B, H, W, br, scale, engine, s3, (L * C, C), s3,
+                             drop=(drop_p, i, None, masks[i]) if drop_p > 0 else None)
             nws = lib.csb200_stripe_attn_bwd_workspace_bytes(ctypes.byref(descs[i]))
             wsp = torch.empty(max(nws, 16), dtype=torch.uint8, device=qkv.device)
             gw, gb = torch.empty_like(ws[2 * i]), torch.empty_like(ws[2 * i + 1])
@@ -910,23 +954,28 @@ class _CrossStripeFn(torch.autograd.Function):
             nbytes, flops = nbytes + w_[0], flops + w_[1]
         with torch.cuda.device(qkv.device), _span("attn_bwd", nbytes, flops, _attn_tag(B, L, C, branches)):
             capi.check(lib.csb200_cross_stripe_attn_bwd(n, descs, ios, st), "csb200_cross_stripe_attn_bwd")
-        return (gqkv, None, None, None, None, None, *grads)
+        return (gqkv, None, None, None, None, None, None, *grads)
 
 
 def cross_stripe_attention(qkv: torch.Tensor, H: int, W: int, branches: Sequence[Branch], scale: float,
-                           weights_and_biases: Sequence[torch.Tensor], engine: str = "auto") -> torch.Tensor:
+                           weights_and_biases: Sequence[torch.Tensor], engine: str = "auto",
+                           drop_p: float = 0.0) -> torch.Tensor:
     """qkv: (B, L, 3C) packed as [q | k | v] along channels (the output of CSWinBlock.qkv, C:358).
 
     ``branches`` partition the C channels; ``weights_and_biases`` = [w0, b0, w1, b1, ...] are the
-    get_v parameters ((C',1,3,3), (C',)) of each branch.  Returns (B, L, C).
+    get_v parameters ((C',1,3,3), (C',)) of each branch.  ``drop_p``: attention dropout on the softmax
+    probabilities (C:290), generated inside the kernels (quantised to k/256).  Returns (B, L, C).
     """
-    out = _CrossStripeFn.apply(qkv, H, W, tuple(branches), scale, _ENGINE[engine], *weights_and_biases)
+    if not 0.0 <= drop_p < 1.0:
+        raise ValueError(f"dropout probability has to be in [0, 1), got {drop_p}")
+    out = _CrossStripeFn.apply(qkv, H, W, tuple(branches), scale, _ENGINE[engine], float(drop_p), *weights_and_biases)
     return out
 
 
-def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, h_sp, w_sp, heads, scale=None, engine="auto"):
+def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, h_sp, w_sp, heads, scale=None, engine="auto", drop_p=0.0):
     """One branch on separate (B, L, C') q, k, v (any strides) — LePEAttention.forward, C:271-298."""
     Cb = q.shape[-1]
     scale = (Cb // heads) ** -0.5 if scale is None else scale
     qkv = torch.cat([q, k, v], dim=-1)  # generic-stride entry: one packing copy, then the fused path
-    return cross_stripe_attention(qkv, H, W, [Branch(h_sp, w_sp, heads, 0, Cb)], scale, [lepe_w, lepe_b], engine)
+    return cross_stripe_attention(qkv, H, W, [Branch(h_sp, w_sp, heads, 0, Cb)], scale, [lepe_w, lepe_b], engine,
+                                  drop_p)

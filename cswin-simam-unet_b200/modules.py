@@ -199,11 +199,10 @@ class LePEAttention(nn.Module):
         self.attn_drop = nn.Dropout(attn_drop)
         self.engine = "auto"
 
-    def check_dropout(self):
-        if self.training and self.attn_drop.p > 0:
-            raise NotImplementedError(
-                "attn_drop > 0 in training mode is not implemented by the fused stripe-attention kernel; "
-                "use attn_drop_rate=0 (the constructor default, C:495)")
+    def drop_p(self) -> float:
+        """attn_drop (C:246, applied at C:290) is evaluated inside the attention kernels (Philox mask on the
+        softmax probabilities, same mask in backward); the nn.Dropout module only carries p."""
+        return float(self.attn_drop.p) if self.training else 0.0
 
     def branch(self, chan0: int) -> csbF.Branch:
         return csbF.Branch(self.H_sp, self.W_sp, self.num_heads, chan0, self.dim)
@@ -213,9 +212,8 @@ class LePEAttention(nn.Module):
         B, L, C = q.shape
         if L != self.resolution * self.resolution:
             raise AssertionError("flatten img_tokens has wrong size")
-        self.check_dropout()
         return csbF.stripe_attention(q, k, v, self.get_v.weight, self.get_v.bias, self.resolution, self.resolution,
-                                     self.H_sp, self.W_sp, self.num_heads, self.scale, self.engine)
+                                     self.H_sp, self.W_sp, self.num_heads, self.scale, self.engine, self.drop_p())
 
 
 class CSWinBlock(nn.Module):
@@ -254,10 +252,10 @@ class CSWinBlock(nn.Module):
         width = self.dim // self.branch_num
         branches, params = [], []
         for i, att in enumerate(self.attns):
-            att.check_dropout()
             branches.append(att.branch(i * width))
             params += [att.get_v.weight, att.get_v.bias]
-        return csbF.cross_stripe_attention(qkv, reso, reso, branches, self._scale, params, self.attns[0].engine)
+        return csbF.cross_stripe_attention(qkv, reso, reso, branches, self._scale, params, self.attns[0].engine,
+                                           self.attns[0].drop_p())
 
     def forward_fused(self, x, pending=None, pending_bias=None):
         """The block with its LAST residual add left pending: returns (x', delta, delta_bias) with

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define CSB200_ABI_VERSION 1
+#define CSB200_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define CSB200_API __attribute__((visibility("default")))
@@ -257,6 +257,17 @@ typedef struct csb200_stripe_desc {
   int64_t dq_sb, dq_sl;   /* gradients (backward only) */
   int64_t dk_sb, dk_sl;
   int64_t dv_sb, dv_sl;
+  /* Attention dropout (`attn = self.attn_drop(attn)`, C:290; the reference trains with attn_drop_rate 0.3,
+   * C:930-932).  drop_p == 0: off, the three fields below are ignored.  Otherwise every softmax probability is
+   * zeroed with probability p = round(256 drop_p) / 256 and the survivors are scaled by 1 / (1 - p); the keep
+   * decisions come from Philox4x32-10 keyed by rng_state[0] (seed) at counter (key block, query, stripe-and-head
+   * unit, rng_state[1] = call counter) and are written by the FORWARD call to drop_mask as transposed bit rows —
+   * word [((b * heads + head) * L + key token) * ceil(N / 32) + query / 32], bit query % 32 — which the
+   * BACKWARD call reads back (same mask by construction, and a test can read it too). */
+  float drop_p;
+  int32_t drop_salt;            /* distinguishes the branches of one block that share a call counter */
+  const uint64_t* rng_state;    /* device, [2]: seed, call counter (forward only) */
+  uint32_t* drop_mask;          /* device, uint32[B][heads][L][ceil(N / 32)] */
 } csb200_stripe_desc;
 
 /* Which engine a descriptor resolves to (CSB200_ENGINE_SIMT / _TCGEN05), or a negative status. */

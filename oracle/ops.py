@@ -83,8 +83,10 @@ def lepe(v: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, H: int, W: i
     return out.reshape(B, L, C)
 
 
-def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, hs, ws, heads, scale=None, return_lse=False):
-    """LePEAttention.forward, C:271-298, on token-major q, k, v of shape (B, L, C')."""
+def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, hs, ws, heads, scale=None, return_lse=False, prob_mask=None):
+    """LePEAttention.forward, C:271-298, on token-major q, k, v of shape (B, L, C').
+    ``prob_mask``: (B * nW, heads, N, N) multiplier applied to the softmax probabilities — attn_drop (C:290) with
+    a GIVEN mask (keep / (1 - p)), so a kernel's own Philox mask can be replayed here."""
     B, L, C = q.shape
     hd = C // heads
     scale = scale if scale is not None else hd ** -0.5  # C:231
@@ -93,6 +95,8 @@ def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, hs, ws, heads, scale=None, r
     vs = tokens_to_stripes(v, H, W, hs, ws, heads)
     scores = qs @ ks.transpose(-2, -1)  # C:288
     prob = torch.softmax(scores, dim=-1)  # C:289
+    if prob_mask is not None:
+        prob = prob * prob_mask  # C:290
     ctx = stripes_to_tokens(prob @ vs, B, H, W, hs, ws)  # C:292-296
     out = ctx + lepe(v, lepe_w, lepe_b, H, W, hs, ws)
     if return_lse:
@@ -100,6 +104,18 @@ def stripe_attention(q, k, v, lepe_w, lepe_b, H, W, hs, ws, heads, scale=None, r
         lse = stripes_to_tokens(lse.unsqueeze(-1), B, H, W, hs, ws)  # (B, L, heads)
         return out, lse.permute(0, 2, 1).contiguous()  # (B, heads, L)
     return out
+
+
+def dense_drop_mask(words: torch.Tensor, H: int, W: int, hs: int, ws: int, keep_scale: float) -> torch.Tensor:
+    """The kernels' attention-dropout mask — int32 [B][heads][L (key token)][ceil(N / 32)], bit (query % 32) of
+    word (query / 32) — as the dense (B * nW, heads, N query, N key) multiplier `keep * keep_scale`."""
+    B, heads, L, NW = words.shape
+    N = hs * ws
+    w = words.to(torch.int64) & 0xFFFFFFFF
+    bits = ((w.unsqueeze(-1) >> torch.arange(32, dtype=torch.int64)) & 1).reshape(B, heads, L, NW * 32)[..., :N]
+    as_tokens = bits.permute(0, 2, 1, 3).reshape(B, L, heads * N).to(torch.float64)   # "channels" = (head, query)
+    per_key = tokens_to_stripes(as_tokens, H, W, hs, ws, heads)                        # (B nW, heads, N key, N query)
+    return per_key.transpose(-2, -1).contiguous() * keep_scale
 
 
 def branch_geometry(resolution: int, idx: int, split_size: int):

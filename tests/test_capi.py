@@ -23,13 +23,15 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(capi.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert capi.lib().csb200_abi_version() == 1
+    assert capi.lib().csb200_abi_version() == 2
 
 
 def test_descriptor_layout_matches_header():
-    # 10 x 4-byte fields then 14 x int64 (the first int64 is 8-byte aligned: 40 bytes in)
-    assert ctypes.sizeof(capi.StripeDesc) == 40 + 14 * 8
+    # 10 x 4-byte fields, 14 x int64 (the first int64 is 8-byte aligned: 40 bytes in), then the dropout block:
+    # float + int32 + two pointers
+    assert ctypes.sizeof(capi.StripeDesc) == 40 + 14 * 8 + 8 + 16
     assert capi.StripeDesc.q_sb.offset == 40
+    assert capi.StripeDesc.drop_p.offset == 152 and capi.StripeDesc.rng_state.offset == 160
 
 
 def test_adam_tensor_layout_and_cpu_refusal():

@@ -19,7 +19,7 @@ from oracle import models as om, ops
 
 @pytest.fixture
 def oracle_kernels(monkeypatch):
-    def cross(qkv, H, W, branches, scale, wb, engine="auto"):
+    def cross(qkv, H, W, branches, scale, wb, engine="auto", drop_p=0.0):
         C = qkv.shape[-1] // 3
         outs = []
         for i, br in enumerate(branches):
@@ -122,12 +122,16 @@ def test_default_split_fails_at_512_like_the_reference(oracle_kernels):
         net(torch.rand(1, 3, 512, 512))
 
 
-def test_attn_dropout_in_training_is_refused_not_ignored():
+def test_attn_dropout_is_passed_to_the_kernels_in_training_only():
+    """attn_drop (C:246, C:290): the module hands p to the fused kernels in training mode and 0 in eval mode
+    (nn.Dropout semantics); the reference's training hyper-parameters (C:930-932) construct without error."""
     att = pkg.LePEAttention(32, 8, 0, 2, num_heads=1, attn_drop=0.3)
-    with pytest.raises(NotImplementedError):
-        att.check_dropout()
+    assert att.drop_p() == pytest.approx(0.3)
     att.eval()
-    att.check_dropout()
+    assert att.drop_p() == 0.0
+    net = pkg.CSWinTransformer(img_size=64, split_size=[1, 2, 2, 2], drop_rate=0.3, attn_drop_rate=0.3,
+                               drop_path_rate=0.3)
+    assert all(a.drop_p() == pytest.approx(0.3) for m in net.modules() if isinstance(m, pkg.CSWinBlock) for a in m.attns)
 
 
 def test_synthetic_batch_is_shard_invariant():
