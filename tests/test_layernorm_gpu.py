@@ -195,3 +195,45 @@ def test_stage_runner_equals_block_by_block(no_tf32):
     assert rel_err(ya, yb) < 1e-5 and rel_err(xa.grad, xb.grad) < 2e-5
     for g1, p in zip(ga, blocks.parameters()):
         assert rel_err(g1, p.grad) < 5e-5
+
+
+# (rows, C) of the all-bf16 path of the autocast train step at config-3-like sizes: ragged row counts, fewer row
+# groups than resident warps, the stage shapes scaled down in rows
+STREAM_SHAPES = [(4096, 64), (4096 + 34, 64), (8192 + 2, 128), (32768, 256), (4100, 256), (65536, 64), (20000, 128)]
+
+
+@pytest.mark.parametrize("with_residual", [False, True])
+@pytest.mark.parametrize("shape", STREAM_SHAPES)
+def test_bf16_layernorm_and_fused_add_at_large_row_counts(shape, with_residual):
+    """The all-bf16 path of the autocast train step against F.layer_norm in fp64: y, s = x + r, grad_x (with the
+    residual-stream gradient summed inside), gamma / beta gradients and the deferred residual bias gradient."""
+    rows, C = shape
+    torch.manual_seed(rows + C)
+    x = (torch.randn(rows, C) * 2 + 0.3).to(torch.bfloat16)
+    r = torch.randn(rows, C).to(torch.bfloat16)
+    w, b = torch.randn(C) * 0.5 + 1, torch.randn(C) * 0.2
+    rb = torch.randn(C)
+    gy, gs = torch.randn(rows, C).to(torch.bfloat16), torch.randn(rows, C).to(torch.bfloat16)
+    xd, rd = x.cuda().requires_grad_(True), r.cuda().requires_grad_(True)
+    wd, bd, rbd = w.cuda().requires_grad_(True), b.cuda().requires_grad_(True), rb.cuda().requires_grad_(True)
+    x64, r64 = x.double().requires_grad_(True), r.double().requires_grad_(True)
+    w64, b64 = w.double().requires_grad_(True), b.double().requires_grad_(True)
+    if with_residual:
+        s, y = csbF.add_layer_norm(xd, rd, wd, bd, 1e-5, torch.bfloat16, rbd)
+        torch.autograd.backward([s, y], [gs.cuda(), gy.cuda()])
+        s64 = (x64 + r64).to(torch.bfloat16).double()  # the statistics are taken from the ROUNDED sum
+        s_ref = x64 + r64
+        y64 = F.layer_norm(s_ref, (C,), w64, b64, 1e-5)
+        torch.autograd.backward([s_ref, y64], [gs.double(), gy.double()])
+        assert rel_err(s.float().cpu(), s64) < 2 ** -8
+        assert rel_err(rd.grad.float().cpu(), r64.grad) < 2 ** -7
+        assert rel_err(rbd.grad.cpu(), r64.grad.sum(0)) < 3e-3  # column sums of the rounded gradient
+    else:
+        y = csbF.layer_norm(xd, wd, bd, 1e-5, torch.bfloat16)
+        y.backward(gy.cuda())
+        y64 = F.layer_norm(x64, (C,), w64, b64, 1e-5)
+        y64.backward(gy.double())
+    assert rel_err(y.float().cpu(), y64.detach()) < 2 ** -7
+    assert rel_err(xd.grad.float().cpu(), x64.grad) < 2 ** -7
+    # gamma / beta gradients: fp32 sums of bf16-rounded terms over >= 4096 rows
+    assert rel_err(wd.grad.cpu(), w64.grad) < 2 ** -7 and rel_err(bd.grad.cpu(), b64.grad) < 2 ** -7
