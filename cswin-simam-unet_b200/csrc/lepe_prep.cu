@@ -49,22 +49,27 @@ struct PrepTMaps {
   CUtensorMap v[2], g[2], o[2];
 };
 
-// 4 consecutive channels of one token from shared memory (explicit 32-bit shared address: a generic
-// pointer into the dynamic ring makes the compiler emit generic loads with 64-bit address math)
+// 4 consecutive channels of one token from shared memory as two packed fp32 PAIRS (explicit 32-bit shared
+// address: a generic pointer into the dynamic ring makes the compiler emit generic loads with 64-bit address
+// math).  The whole per-token chain below runs on pairs (fma.rn.f32x2): the kernel is bound by instruction
+// issue at the stage-3 / stage-4 shapes (ncu: issue-active 50 %, no DRAM pressure), and 72 scalar FMAs per
+// (token, 4 channels) become 36.
+struct P4 {
+  f2_t a, b;  // channels (0, 1) and (2, 3)
+};
 template <typename T>
-__device__ __forceinline__ float4 lds4(uint32_t addr);
+__device__ __forceinline__ P4 lds4(uint32_t addr);
 template <>
-__device__ __forceinline__ float4 lds4<float>(uint32_t addr) {
-  float4 v;
-  asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+__device__ __forceinline__ P4 lds4<float>(uint32_t addr) {
+  P4 v;
+  asm volatile("ld.shared.v2.b64 {%0,%1}, [%2];" : "=l"(v.a), "=l"(v.b) : "r"(addr));
   return v;
 }
 template <>
-__device__ __forceinline__ float4 lds4<__nv_bfloat16>(uint32_t addr) {
+__device__ __forceinline__ P4 lds4<__nv_bfloat16>(uint32_t addr) {
   uint2 u;
   asm volatile("ld.shared.v2.u32 {%0,%1}, [%2];" : "=r"(u.x), "=r"(u.y) : "r"(addr));
-  return make_float4(__uint_as_float(u.x << 16), __uint_as_float(u.x & 0xffff0000u),
-                     __uint_as_float(u.y << 16), __uint_as_float(u.y & 0xffff0000u));
+  return P4{f2_from_bf16x2(u.x), f2_from_bf16x2(u.y)};
 }
 
 struct Walk {        // per-thread constants of the token walk inside a tile
@@ -77,11 +82,12 @@ struct Walk {        // per-thread constants of the token walk inside a tile
 // HAS_X / HAS_Y: the stripe is wider / taller than one token (else those taps never exist).
 template <typename T, bool HAS_X, bool HAS_Y>
 __device__ __forceinline__ float prep_token(uint32_t va, uint32_t ga, uint32_t oa, const Walk& wk, int mx,
-                                            int my, const float4 (&w)[10], float4 (&acc)[10]) {
-  const float4 go = lds4<T>(ga);
-  const float4 o = lds4<T>(oa);
-  float4 lp = w[9];
-  acc[9].x += go.x; acc[9].y += go.y; acc[9].z += go.z; acc[9].w += go.w;
+                                            int my, const P4 (&w)[10], P4 (&acc)[10]) {
+  const P4 go = lds4<T>(ga);
+  const P4 o = lds4<T>(oa);
+  P4 lp = w[9];
+  acc[9].a = f2_add(acc[9].a, go.a);
+  acc[9].b = f2_add(acc[9].b, go.b);
 #pragma unroll
   for (int ky = 0; ky < 3; ++ky) {
     if (!HAS_Y && ky != 1) continue;
@@ -90,16 +96,21 @@ __device__ __forceinline__ float prep_token(uint32_t va, uint32_t ga, uint32_t o
     for (int kx = 0; kx < 3; ++kx) {
       if (!HAS_X && kx != 1) continue;
       if (HAS_X && ((kx == 0 && !(mx & 1)) || (kx == 2 && !(mx & 2)))) continue;
-      const float4 vn = lds4<T>(va + ky * wk.row_bytes + kx * wk.tok_bytes);  // va: tap (0,0)
-      const float4 wt = w[ky * 3 + kx];
-      lp.x = fmaf(wt.x, vn.x, lp.x); lp.y = fmaf(wt.y, vn.y, lp.y);
-      lp.z = fmaf(wt.z, vn.z, lp.z); lp.w = fmaf(wt.w, vn.w, lp.w);
-      float4& a = acc[ky * 3 + kx];
-      a.x = fmaf(go.x, vn.x, a.x); a.y = fmaf(go.y, vn.y, a.y);
-      a.z = fmaf(go.z, vn.z, a.z); a.w = fmaf(go.w, vn.w, a.w);
+      const P4 vn = lds4<T>(va + ky * wk.row_bytes + kx * wk.tok_bytes);  // va: tap (0,0)
+      const P4 wt = w[ky * 3 + kx];
+      lp.a = f2_fma(wt.a, vn.a, lp.a);
+      lp.b = f2_fma(wt.b, vn.b, lp.b);
+      P4& a = acc[ky * 3 + kx];
+      a.a = f2_fma(go.a, vn.a, a.a);
+      a.b = f2_fma(go.b, vn.b, a.b);
     }
   }
-  return go.x * (o.x - lp.x) + go.y * (o.y - lp.y) + go.z * (o.z - lp.z) + go.w * (o.w - lp.w);
+  // go . (o - lp)
+  const f2_t m1 = f2_splat(-1.f);
+  const f2_t d = f2_fma(go.b, f2_fma(lp.b, m1, o.b), f2_mul(go.a, f2_fma(lp.a, m1, o.a)));
+  float d0, d1;
+  f2_split(d, d0, d1);
+  return d0 + d1;
 }
 
 __device__ __forceinline__ float head_sum(float d) {  // 8 adjacent lanes = the 32 channels of a head
@@ -115,7 +126,7 @@ template <typename T, bool HAS_X, bool HAS_Y>
 __device__ __forceinline__ void prep_items(const PrepTParams& p, const PrepTBranch& bg, uint32_t ring,
                                            uint64_t* full, uint64_t* empty, const uint8_t* s_my,
                                            const uint8_t* s_mx, const Walk& wk, int my_items, int head,
-                                           bool writer, const float4 (&w)[10], float4 (&acc)[10]) {
+                                           bool writer, const P4 (&w)[10], P4 (&acc)[10]) {
   const int stage_bytes = bg.v_bytes + 2 * bg.t_bytes;
   const int tokens = bg.R * p.W;
   const int lane = threadIdx.x & 31;
@@ -227,7 +238,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const int walker = (int)threadIdx.x / cgn, walkers = CONSUMERS / cgn;
   const int ch = c0 + cg * 4, head = ch / HD;    // channel inside the branch
 
-  float4 w[10];  // [tap] for this thread's 4 channels, bias last
+  P4 w[10];  // [tap] for this thread's 4 channels, bias last
   {
     float t[4][10];
 #pragma unroll
@@ -237,11 +248,11 @@ __global__ void __launch_bounds__(THREADS, 1)
       t[e][9] = __ldg(bg.lepe_b + ch + e);
     }
 #pragma unroll
-    for (int k = 0; k < 10; ++k) w[k] = make_float4(t[0][k], t[1][k], t[2][k], t[3][k]);
+    for (int k = 0; k < 10; ++k) w[k] = P4{f2_make(t[0][k], t[1][k]), f2_make(t[2][k], t[3][k])};
   }
-  float4 acc[10];
+  P4 accp[10];
 #pragma unroll
-  for (int k = 0; k < 10; ++k) acc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < 10; ++k) accp[k] = P4{f2_splat(0.f), f2_splat(0.f)};
 
   Walk wk;
   wk.t0 = walker; wk.dt = walkers;
@@ -253,14 +264,20 @@ __global__ void __launch_bounds__(THREADS, 1)
   const bool writer = (cg & 7) == 0;
   const bool has_x = bg.ws > 1, has_y = bg.hs > 1;
   if (has_x && has_y)
-    prep_items<T, true, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+    prep_items<T, true, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
   else if (has_y)
-    prep_items<T, false, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+    prep_items<T, false, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
   else if (has_x)
-    prep_items<T, true, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+    prep_items<T, true, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
   else
-    prep_items<T, false, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, acc);
+    prep_items<T, false, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
 
+  float4 acc[10];
+#pragma unroll
+  for (int k = 0; k < 10; ++k) {
+    f2_split(accp[k].a, acc[k].x, acc[k].y);
+    f2_split(accp[k].b, acc[k].z, acc[k].w);
+  }
   // ---- reduce the 40 accumulators over the walkers of this CTA (fixed order) ----
   for (int off = cgn; off < 32; off <<= 1) {
 #pragma unroll

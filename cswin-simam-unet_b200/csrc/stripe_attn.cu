@@ -295,12 +295,16 @@ extern "C" int csb200_cross_stripe_attn_bwd(int n, const csb200_stripe_desc* d,
           align_up((size_t)g[i].B * g[i].heads * g[i].L * sizeof(float), 256));
       pio[i] = PrepIO{b.v, b.out, b.grad_out, b.lepe_w, b.lepe_b, delta, partial, b.grad_lepe_w,
                       b.grad_lepe_b};
-      tio[i] = TcBwdIO{b.q, b.k, b.v, b.grad_out, b.lepe_w, b.lse, delta, b.dq, b.dk, b.dv};
+      tio[i] = TcBwdIO{b.q, b.k, b.v, b.grad_out, b.lepe_w, b.lse, delta, b.dq, b.dk, b.dv, partial,
+                       b.grad_lepe_w, b.grad_lepe_b};
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int rc = lepe_bwd_prep_multi(2, g, d[0].dtype, pio, st);
+    // the per-CTA partials of the depthwise gradients are summed by the prologue of the backward kernel itself
+    // (one launch less per call: the separate final-sum kernel was 6 us of launch latency for 10 KB of output)
+    int wg_blocks = 0;
+    int rc = lepe_bwd_prep_multi(2, g, d[0].dtype, pio, st, &wg_blocks);
     if (rc != CSB200_OK) return rc;
-    return tc_bwd_multi(2, g, tio, st);
+    return tc_bwd_multi(2, g, tio, st, wg_blocks);
   }
   for (int i = 0; i < n; ++i) {
     int rc = csb200_stripe_attn_bwd(&d[i], io[i].q, io[i].k, io[i].v, io[i].lepe_w, io[i].lepe_b,

@@ -42,8 +42,11 @@ struct PrepIO {
 int lepe_prep_tma_max_blocks();
 int lepe_prep_tma_launch(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, int* blocks,
                          cudaStream_t st);
-// up to two branches of equal (B, L) in one launch
-int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st);
+// up to two branches of equal (B, L) in one launch.  final_blocks == nullptr: gw / gb are complete on return
+// (lepe_wgrad_final launched).  Otherwise the per-CTA partials are left in io[i].partial, *final_blocks is
+// their count per output, and the CALLER sums them (the tcgen05 backward kernel does, in its prologue).
+int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st,
+                        int* final_blocks = nullptr);
 int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,
                   const float* lepe_b, const void* out, const void* gout, float* delta,
                   float* partial, float* gw, float* gb, cudaStream_t st);
@@ -65,8 +68,12 @@ struct TcBwdIO {
   const void *q, *k, *v, *gout;
   const float *lepe_w, *lse, *delta;
   void *dq, *dk, *dv;
+  // optional: per-CTA partials of the LePE weight / bias gradients ([blocks][C'][10], lepe_bwd_prep_multi) to be
+  // summed into gw [C'][9] / gb [C'] by the kernel's prologue (nullptr: nothing to do)
+  const float* wg_partial;
+  float *gw, *gb;
 };
-int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st);
+int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st, int wg_blocks = 0);
 // dq, dk, dv from q, k, v, grad_out, lse and delta (stripe_attn_tc_bwd.cu)
 int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
                 const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,

@@ -601,7 +601,7 @@ int wgrad_blocks(const StripeGeom& g) {
 }
 
 template <typename T>
-int lepe_bwd_prep_multi_t(int nbr, const StripeGeom* g, const PrepIO* io, cudaStream_t st) {
+int lepe_bwd_prep_multi_t(int nbr, const StripeGeom* g, const PrepIO* io, cudaStream_t st, int* final_blocks) {
   PrepArgs<T> a;
   memset(&a, 0, sizeof(a));
   int heads = 0, cp_max = 0;
@@ -629,6 +629,10 @@ int lepe_bwd_prep_multi_t(int nbr, const StripeGeom* g, const PrepIO* io, cudaSt
     rc = check_launch("lepe_bwd_prep");
   }
   if (rc != CSB200_OK) return rc;
+  if (final_blocks != nullptr) {  // the caller's next kernel sums the partials in its prologue
+    *final_blocks = blocks;
+    return CSB200_OK;
+  }
   WgradFinal f[2];
   for (int i = 0; i < 2; ++i) {
     const int j = i < nbr ? i : 0;
@@ -638,9 +642,10 @@ int lepe_bwd_prep_multi_t(int nbr, const StripeGeom* g, const PrepIO* io, cudaSt
   return check_launch("lepe_wgrad_final");
 }
 
-int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st) {
-  return dtype == CSB200_F32 ? lepe_bwd_prep_multi_t<float>(nbr, g, io, st)
-                             : lepe_bwd_prep_multi_t<__nv_bfloat16>(nbr, g, io, st);
+int lepe_bwd_prep_multi(int nbr, const StripeGeom* g, int dtype, const PrepIO* io, cudaStream_t st,
+                        int* final_blocks) {
+  return dtype == CSB200_F32 ? lepe_bwd_prep_multi_t<float>(nbr, g, io, st, final_blocks)
+                             : lepe_bwd_prep_multi_t<__nv_bfloat16>(nbr, g, io, st, final_blocks);
 }
 
 template <typename T>
@@ -648,7 +653,7 @@ int lepe_bwd_prep_t(const StripeGeom& g, const T* v, const float* lepe_w, const 
                     const T* out, const T* gout, float* delta, float* partial, float* gw, float* gb,
                     cudaStream_t st) {
   const PrepIO io{v, out, gout, lepe_w, lepe_b, delta, partial, gw, gb};
-  return lepe_bwd_prep_multi_t<T>(1, &g, &io, st);
+  return lepe_bwd_prep_multi_t<T>(1, &g, &io, st, nullptr);
 }
 
 int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* lepe_w,

@@ -138,10 +138,14 @@ struct Cfg<128> {
 #define CSB_QS128 5
 #endif
   static constexpr int NWG = 3, KS = CSB_KS128, VS = CSB_VS128, QS = CSB_QS128;
+  static constexpr int LWG = 0, LB = 1;   // N = 128 is bound by the operand loads, not by the softmax warps
 };
 template <>
 struct Cfg<256> {
-  static constexpr int NWG = 2, KS = 3, VS = 5, QS = 6;
+  // LWG: a fifth warpgroup evaluates the LePE stencil (3 100 of the 3 900 epilogue cycles of a softmax
+  // warpgroup at N = 256) into shared memory while the softmax warpgroups run their exponentials; LB buffers
+  static constexpr int NWG = 2, KS = 3, VS = 4, QS = 6;
+  static constexpr int LWG = 1, LB = 2;
 };
 
 template <int NK>
@@ -156,7 +160,13 @@ struct Smem {
   alignas(8) uint64_t q_full[QS], q_empty[QS];
   uint64_t k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];
   uint64_t s_full[NWG], p_full[NWG], o_full[NWG], buf_empty[NWG];
+  uint64_t l_full[Cfg<NK>::LB], l_empty[Cfg<NK>::LB];
   uint32_t tmem_base;
+  // LePE warpgroup -> epilogue: bias + depthwise 3x3 of V for the 128 rows of a tile, fp32, row-major with the
+  // 16-byte chunks of row r rotated by r (a thread writes / reads its own row: conflict-free), and the tile's
+  // group coordinates (the V stage may be recycled before the epilogue runs)
+  alignas(16) float lepe_out[Cfg<NK>::LWG ? Cfg<NK>::LB : 1][Cfg<NK>::LWG ? TILE * HD : 4];
+  alignas(16) int4 lcoord[Cfg<NK>::LB];
 };
 
 // address of 16-byte chunk `chunk` (0..3) of row n inside a 64B-swizzled tile
@@ -181,12 +191,20 @@ __device__ __forceinline__ GroupCoord decode_group(const FwdParams& p, int g) {
   return c;
 }
 
+template <int A, int B>
+__device__ __forceinline__ void setmaxnreg() {  // A = 1: grow to B registers per thread, A = 0: shrink
+  if constexpr (A) asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(B));
+  else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B));
+}
+
 template <int NK, bool DROP>
-__global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
+__global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
     stripe_fwd_tc(const __grid_constant__ FwdMaps maps, const __grid_constant__ FwdParams p) {
   constexpr int T = NK / TILE;          // query tiles per group
   constexpr int NBOX = NK / TILE;       // TMA boxes per K (or V) load
   constexpr int NWG = Cfg<NK>::NWG, KS = Cfg<NK>::KS, VS = Cfg<NK>::VS, QS = Cfg<NK>::QS;
+  constexpr bool LWG = Cfg<NK>::LWG != 0;
+  constexpr int LB = Cfg<NK>::LB;
   constexpr uint32_t P_COL = 0, O_COL = NK / 2, BUF_COLS = NK;
   extern __shared__ uint8_t smem_raw[];
   // align inside the shared window: pointer + integer offset keeps the shared address space (an
@@ -213,7 +231,13 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
     }
     for (int i = 0; i < VS; ++i) {
       mbar_init(&sm.v_full[i], 2);        // expect_tx arrival (before the TMA) + one after the LePE taps
-      mbar_init(&sm.v_empty[i], 4 * T);   // one arrival per softmax warp per tile of the group
+      // readers of a V stage: the warps that evaluate the stencil (one arrival per warp per tile of the group)
+      // and, with a LePE warpgroup, the P V MMAs themselves (a tcgen05.commit after the last tile's)
+      mbar_init(&sm.v_empty[i], 4 * T + (LWG ? 1 : 0));
+    }
+    for (int i = 0; i < LB; ++i) {
+      mbar_init(&sm.l_full[i], 4);
+      mbar_init(&sm.l_empty[i], 4);
     }
     for (int i = 0; i < NWG; ++i) {
       mbar_init(&sm.s_full[i], 1);
@@ -229,7 +253,12 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
   PROF_T(k0);
-
+  // With a LePE warpgroup the CTA has 512 threads, i.e. 128 registers each at launch: the copy / issue warps and
+  // the stencil warpgroup hand registers to the softmax warpgroups (two 32-word TMEM chunks in flight plus the
+  // output row need ~170).  Each role's code is DOMINATED by its setmaxnreg (ptxas budgets a region by the
+  // setmaxnreg that dominates it) and each warpgroup executes one common instruction.
+  if (warp < 4) {
+    if constexpr (LWG) setmaxnreg<0, 40>();
   if (warp == 0) {
     // ===================================== TMA producer =====================================
     int it = 0;
@@ -322,10 +351,69 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
         for (int k = 0; k < NK / 16; ++k)  // 16 keys per step: 8 TMEM columns of P, 1024 B of V
           umma_ts2(d, a + 8 * k, v_lo + k * (1024 >> 4), DESC_HI_SW64, idesc_pv, k > 0);
         umma_commit(&sm.o_full[buf]);
+        if (LWG && it % T == T - 1) umma_commit(&sm.v_empty[vs]);  // every P V of the group has read V
       }
       __syncwarp();
     }
-  } else if (warp >= 4) {
+  }
+  } else if (LWG && warp >= 4 + 4 * NWG) {
+    if constexpr (LWG) setmaxnreg<0, 96>();
+    // ================================== LePE warpgroup ==================================
+    // bias + depthwise 3x3 of V (zero padding at the stripe border, C:244,263-265) for the 128 rows of every
+    // tile, from the V tile in shared memory into lepe_out[it % LB]
+    const int row = ((warp & 3) << 5) | lane;
+    for (int it = 0; it < my_tiles; ++it) {
+      const int gi = it / T, t = it % T, vs = gi % VS, lb = it % LB;
+      mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
+      mbar_wait(&sm.l_empty[lb], ((it / LB) & 1) ^ 1);
+      const int4 gc = sm.coord[vs];
+      const FwdBranch& bg = p.br[gc.w];
+      const int n = t * TILE + row;
+      const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
+      float o[HD];
+      const float* lw = sm.lepe[vs];
+#pragma unroll
+      for (int cc = 0; cc < HD; ++cc) o[cc] = lw[9 * HD + cc];
+      const uint8_t* vt = sm.v[vs];
+#pragma unroll
+      for (int ky = 0; ky < 3; ++ky) {
+        const int ny = yy + ky - 1;
+        if (ny < 0 || ny >= bg.hs) continue;
+#pragma unroll
+        for (int kx = 0; kx < 3; ++kx) {
+          const int nx = xx + kx - 1;
+          if (nx < 0 || nx >= bg.ws) continue;
+          const int nn = (ny << bg.ws_log2) + nx;
+          const float* wt = lw + (ky * 3 + kx) * HD;
+#pragma unroll
+          for (int q4 = 0; q4 < 4; ++q4) {
+            float f[8];
+            unpack<__nv_bfloat16>(*sw64_chunk(vt, nn, q4), f);
+            const float4 w0 = *reinterpret_cast<const float4*>(wt + q4 * 8);
+            const float4 w1 = *reinterpret_cast<const float4*>(wt + q4 * 8 + 4);
+            o[q4 * 8 + 0] = fmaf(w0.x, f[0], o[q4 * 8 + 0]);
+            o[q4 * 8 + 1] = fmaf(w0.y, f[1], o[q4 * 8 + 1]);
+            o[q4 * 8 + 2] = fmaf(w0.z, f[2], o[q4 * 8 + 2]);
+            o[q4 * 8 + 3] = fmaf(w0.w, f[3], o[q4 * 8 + 3]);
+            o[q4 * 8 + 4] = fmaf(w1.x, f[4], o[q4 * 8 + 4]);
+            o[q4 * 8 + 5] = fmaf(w1.y, f[5], o[q4 * 8 + 5]);
+            o[q4 * 8 + 6] = fmaf(w1.z, f[6], o[q4 * 8 + 6]);
+            o[q4 * 8 + 7] = fmaf(w1.w, f[7], o[q4 * 8 + 7]);
+          }
+        }
+      }
+      float4* dst = reinterpret_cast<float4*>(sm.lepe_out[lb] + row * HD);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) dst[(c + row) & 7] = make_float4(o[4 * c], o[4 * c + 1], o[4 * c + 2], o[4 * c + 3]);
+      if (row == 0) sm.lcoord[lb] = gc;
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&sm.l_full[lb]);
+        mbar_arrive(&sm.v_empty[vs]);  // this warp is done with V / the taps of the group's tile
+      }
+    }
+  } else {
+    if constexpr (LWG) setmaxnreg<1, 184>();
     // ============================ softmax + epilogue warpgroups ============================
     const int wg = (warp - 4) >> 2;                  // warpgroup == TMEM buffer
     const int row = ((warp & 3) << 5) | lane;        // query row inside the tile == TMEM lane
@@ -443,16 +531,34 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.buf_empty[wg]);  // S(it+2) may now overwrite this buffer
 
+      float o[HD];
+      int4 gc;
+      const float inv_l = (DROP ? p.keep_scale : 1.f) / l;  // dropout: survivors are scaled by 1 / (1 - p)
+      PROF_T(t4a);
+      const int n = t * TILE + row;  // in-stripe index
+      if constexpr (LWG) {
+        // the LePE term of this tile comes from the LePE warpgroup (chunks of row r rotated by r)
+        const int lb = it % LB;
+        mbar_wait(&sm.l_full[lb], (it / LB) & 1);
+        gc = sm.lcoord[lb];
+        const float4* src = reinterpret_cast<const float4*>(sm.lepe_out[lb] + row * HD);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float4 lp = src[(c + row) & 7];
+          o[4 * c + 0] = fmaf(__uint_as_float(r[4 * c + 0]), inv_l, lp.x);
+          o[4 * c + 1] = fmaf(__uint_as_float(r[4 * c + 1]), inv_l, lp.y);
+          o[4 * c + 2] = fmaf(__uint_as_float(r[4 * c + 2]), inv_l, lp.z);
+          o[4 * c + 3] = fmaf(__uint_as_float(r[4 * c + 3]), inv_l, lp.w);
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.l_empty[lb]);
+      } else {
       // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
       // barrier the PV issuer used (already complete; cannot advance before this warp's v_empty)
       mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
-      const int4 gc = sm.coord[vs];  // image, first token of the stripe, head, branch
-      const FwdBranch& bg = p.br[gc.w];
-      const float inv_l = (DROP ? p.keep_scale : 1.f) / l;  // survivors are scaled by 1 / (1 - p)
-      PROF_T(t4a);
-      const int n = t * TILE + row;  // in-stripe index
-      const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
-      float o[HD];
+      gc = sm.coord[vs];  // image, first token of the stripe, head, branch
+      const FwdBranch& bgl = p.br[gc.w];
+      const int yy = n >> bgl.ws_log2, xx = n & (bgl.ws - 1);
       const float* lw = sm.lepe[vs];
 #pragma unroll
       for (int cc = 0; cc < HD; ++cc) o[cc] = fmaf(__uint_as_float(r[cc]), inv_l, lw[9 * HD + cc]);
@@ -460,12 +566,12 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
 #pragma unroll
       for (int ky = 0; ky < 3; ++ky) {
         const int ny = yy + ky - 1;
-        if (ny < 0 || ny >= bg.hs) continue;
+        if (ny < 0 || ny >= bgl.hs) continue;
 #pragma unroll
         for (int kx = 0; kx < 3; ++kx) {
           const int nx = xx + kx - 1;
-          if (nx < 0 || nx >= bg.ws) continue;
-          const int nn = (ny << bg.ws_log2) + nx;
+          if (nx < 0 || nx >= bgl.ws) continue;
+          const int nn = (ny << bgl.ws_log2) + nx;
           const float* wt = lw + (ky * 3 + kx) * HD;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -484,6 +590,9 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
           }
         }
       }
+      }
+      const FwdBranch& bg = p.br[gc.w];
+      const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
       PROF_T(t4b);
       const int tok = gc.y + yy * p.W + xx;
       uint4* dst = reinterpret_cast<uint4*>(bg.out + (int64_t)gc.x * bg.o_sb + (int64_t)tok * bg.o_sl +
@@ -497,7 +606,7 @@ __global__ void __launch_bounds__(128 + 128 * Cfg<NK>::NWG, 1)
       }
       bg.lse[((int64_t)gc.x * bg.heads + gc.z) * p.L + tok] = m * p.scale + __logf(l);
       __syncwarp();
-      if (lane == 0) mbar_arrive(&sm.v_empty[vs]);  // this warp is done with V / LePE of the group
+      if (!LWG && lane == 0) mbar_arrive(&sm.v_empty[vs]);  // this warp is done with V / LePE of the group
       PROF_T(t5);
       PROF_ADD(0, t0, t1); PROF_ADD(1, t1, t2); PROF_ADD(2, t2, t3); PROF_ADD(3, t3, t4); PROF_ADD(4, t4, t5);
       PROF_ADD(5, t0, t0 + 1);
@@ -555,10 +664,10 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
   const int grid = p.groups < sm_count ? p.groups : sm_count;
   if (drop) {
     CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, true>), smem));
-    stripe_fwd_tc<NK, true><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
+    stripe_fwd_tc<NK, true><<<grid, 128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), smem, st>>>(maps, p);
   } else {
     CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, false>), smem));
-    stripe_fwd_tc<NK, false><<<grid, 128 + 128 * Cfg<NK>::NWG, smem, st>>>(maps, p);
+    stripe_fwd_tc<NK, false><<<grid, 128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), smem, st>>>(maps, p);
   }
   return check_launch("stripe_fwd_tc");
 }

@@ -62,12 +62,15 @@ struct BwdBranch {
   __nv_bfloat16 *dq, *dk, *dv;
   int64_t dq_sb, dq_sl, dk_sb, dk_sl, dv_sb, dv_sl;
   const uint32_t* drop_mask;  // attention dropout: the forward pass's transposed keep bits
+  const float* wg_partial;    // [wg_blocks][C'][10] partial LePE gradients of lepe_prep (nullptr: already summed)
+  float *gw, *gb;             // [C'][9], [C']
 };
 struct BwdParams {
   int B, W, L;
   int g0, gpi, groups;  // groups per image of branch 0 / of both; B * gpi
   float scale, scale_log2;
   float keep_scale;     // 1 / (1 - p) of the attention dropout (1 in the <.., false> instantiation)
+  int wg_blocks, nbr;
   BwdBranch br[2];
 };
 struct BwdMaps {
@@ -377,6 +380,24 @@ __global__ void __launch_bounds__(THREADS, 1)
     // ================================== epilogue warpgroup ==================================
     const int row = ((warp & 3) << 5) | lane;
     const uint32_t lane_base = tmem + (static_cast<uint32_t>((warp & 3) << 5) << 16);
+    // Prologue: the depthwise weight / bias gradients of get_v (C:244) — fixed-order sums of the per-CTA partials
+    // that lepe_prep left behind, one warp per output, the outputs dealt round-robin to the CTAs.  Runs while
+    // the first group's tiles are still in flight (this warpgroup has nothing to drain yet).
+    if (p.wg_blocks > 0) {
+      for (int br = 0; br < p.nbr; ++br) {
+        const BwdBranch& bw = p.br[br];
+        if (bw.wg_partial == nullptr) continue;
+        const int outs = bw.heads * HD * 10;
+        for (int o = (int)blockIdx.x * 4 + (warp & 3); o < outs; o += (int)gridDim.x * 4) {
+          const float a = strided_partial_sum(bw.wg_partial + o, p.wg_blocks, outs, lane);
+          if (lane == 0) {
+            const int c = o / 10, tap = o % 10;
+            if (tap == 9) bw.gb[c] = a;
+            else bw.gw[c * 9 + tap] = a;
+          }
+        }
+      }
+    }
     for (int gi = 0; gi < my_groups; ++gi) {
       const int gs = gi % GS;
       mbar_wait(&sm.grp_full[gs], (gi / GS) & 1);
@@ -492,7 +513,7 @@ __global__ void __launch_bounds__(THREADS, 1)
 }
 
 template <int NK>
-int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st) {
+int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st, int wg_blocks) {
   BwdMaps maps;
   BwdParams p;
   memset(&maps, 0, sizeof(maps));
@@ -519,12 +540,16 @@ int launch_bwd(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st)
     b.dq_sb = g[i].dq_sb; b.dq_sl = g[i].dq_sl; b.dk_sb = g[i].dk_sb; b.dk_sl = g[i].dk_sl;
     b.dv_sb = g[i].dv_sb; b.dv_sl = g[i].dv_sl;
     b.drop_mask = g[i].drop_mask;
+    b.wg_partial = wg_blocks > 0 ? io[i].wg_partial : nullptr;
+    b.gw = io[i].gw; b.gb = io[i].gb;
     if (i == 0) p.g0 = g[i].nwy * g[i].nwx * g[i].heads;
     gpi += g[i].nwy * g[i].nwx * g[i].heads;
   }
   p.gpi = gpi;
   p.groups = p.B * gpi;
   p.keep_scale = g[0].keep_scale;
+  p.wg_blocks = wg_blocks;
+  p.nbr = nbr;
   const bool drop = g[0].drop_thr != 0;
   const int smem = (int)sizeof(BSmem<NK>) + 1024;  // > 113 KB: one CTA (all 512 TMEM columns) per SM
   const int sm_count = device_sm_count();
@@ -554,19 +579,19 @@ extern "C" __attribute__((visibility("default"))) int csb200_debug_prof_bwd(unsi
 }
 #endif
 
-int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st) {
+int tc_bwd_multi(int nbr, const StripeGeom* g, const TcBwdIO* io, cudaStream_t st, int wg_blocks) {
   static_assert(sizeof(BSmem<128>) + 1024 > 114 * 1024 && sizeof(BSmem<256>) + 1024 > 114 * 1024,
                 "two CTAs must not fit one SM");
   static_assert(sizeof(BSmem<128>) + 1024 <= 227 * 1024 && sizeof(BSmem<256>) + 1024 <= 227 * 1024,
                 "shared memory budget");
-  return g[0].N == 128 ? launch_bwd<128>(nbr, g, io, st) : launch_bwd<256>(nbr, g, io, st);
+  return g[0].N == 128 ? launch_bwd<128>(nbr, g, io, st, wg_blocks) : launch_bwd<256>(nbr, g, io, st, wg_blocks);
 }
 
 int tc_bwd_core(const StripeGeom& g, const void* q, const void* k, const void* v, const void* gout,
                 const float* lepe_w, const float* lse, const float* delta, void* dq, void* dk,
                 void* dv, cudaStream_t st) {
-  const TcBwdIO io{q, k, v, gout, lepe_w, lse, delta, dq, dk, dv};
-  return tc_bwd_multi(1, &g, &io, st);
+  const TcBwdIO io{q, k, v, gout, lepe_w, lse, delta, dq, dk, dv, nullptr, nullptr, nullptr};
+  return tc_bwd_multi(1, &g, &io, st, 0);
 }
 
 }  // namespace csb200
