@@ -344,6 +344,27 @@ def run_ours(args, rank, local_rank, world):
         if spread > 1e-7:  # a skipped all-reduce drifts by 1e-4 and more; identical updates give exactly 0
             raise RuntimeError(f"replicas diverged: parameter checksums {vals}")
 
+    # BASELINE config 4 is a GLOBAL batch of 256: at N = 8 that is the weak-scaling point above (32 per GPU); at
+    # N = 2 / 4 it is 128 / 64 images per GPU — measured here as an extra key (strong-scaling points)
+    config4 = None
+    if world in (2, 4) and not args.no_config4:
+        try:
+            b4 = 256 // world
+            step = eager = None
+            torch.cuda.empty_cache()
+            opt4 = pkg.FusedAdamW(net.parameters(), lr=1e-4, weight_decay=1e-4)
+            red4 = pkg.GradientAllReducer(net.parameters(), bucket_bytes=1 << 30, overlap=False)
+            step4 = pkg.TrainStep(net, opt4, precision="bf16", reducer=red4, cuda_graph=use_graph)
+            sh4 = pkg.shard_of_global_batch(256, rank, world)
+            x4, y4 = pkg.synthetic_batch(b4, IMG, dev, seed=0, first_index=sh4.start)
+            for _ in range(3):
+                step4(x4, y4)
+            n4 = max(5, args.steps // 2)
+            ms4 = timed(lambda i: step4(x4, y4), n4)
+            config4 = {"global_batch": 256, "batch_per_gpu": b4, "steps": n4, "ms_per_step": ms4 / n4,
+                       "value": 256 * n4 / (ms4 / 1e3), "unit": UNIT, "scaling": "strong"}
+        except Exception as e:  # never lose the headline line to the extra measurement
+            config4 = {"error": str(e)[:200]}
     if rank != 0:
         finish_distributed(world)
         return
@@ -435,6 +456,8 @@ def run_ours(args, rank, local_rank, world):
         line["cpu_baseline"] = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample")}
     if gpu_ref is not None:
         line["gpu_eager_baseline"] = gpu_ref
+    if config4 is not None:
+        line["config4_global_batch_256"] = config4
     print(json.dumps(line), flush=True)
     finish_distributed(world)
 
@@ -463,6 +486,7 @@ def main():
     ap.add_argument("--batch-per-gpu", type=int, default=BATCH_PER_GPU)
     ap.add_argument("--attn-engine", default="auto", choices=["auto", "simt", "tcgen05"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-config4", action="store_true", help="skip the global-batch-256 point at N = 2 / 4")
     ap.add_argument("--no-gpu-baseline", action="store_true",
                     help="skip the reference-in-stock-PyTorch-eager leg on the same GPU (gpu_eager_baseline)")
     ap.add_argument("--optimizer", default="csb200", choices=["csb200", "torch"])
