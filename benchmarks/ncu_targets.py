@@ -67,4 +67,23 @@ elif what == "carafe":
     enc = torch.randn(B, 9 * up * up, H, H, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last).requires_grad_(True)
     g = torch.randn(B, C, H * up, H * up, device="cuda").bfloat16().contiguous(memory_format=torch.channels_last)
     profiled(lambda: torch.autograd.grad(csbF.carafe_reassemble(low, enc, up), [low, enc], g))
+elif what == "linear":
+    # the tcgen05 token-path GEMMs at a config-3 stage: arg = s1 | s2 | s3 (fc1 + GELU forward, dgelu backward, the
+    # qkv Linear, and the qkv weight + bias gradient)
+    from cswin_simam_unet_b200 import capi
+    M, C = {"s1": (524288, 64), "s2": (131072, 128), "s3": (32768, 256)}[arg]
+    x = torch.randn(M, C, device="cuda").bfloat16()
+    w1 = (torch.randn(4 * C, C, device="cuda") / C ** 0.5).bfloat16()
+    b1 = torch.randn(4 * C, device="cuda")
+    w2 = (torch.randn(C, 4 * C, device="cuda") / C ** 0.5).bfloat16()
+    wq = (torch.randn(3 * C, C, device="cuda") / C ** 0.5).bfloat16()
+    bq = torch.randn(3 * C, device="cuda")
+    g3 = torch.randn(M, 3 * C, device="cuda").bfloat16()
+
+    def f():
+        a, h = csbF._tc_linear(x, w1, b1, capi.EPI_GELU_SAVE)
+        csbF._tc_dgelu(x, w2, h)
+        csbF._tc_linear(x, wq, bq, capi.EPI_BIAS)
+        csbF._tc_wgrad(g3, x, True)
+    profiled(f)
 print("done", what, arg)
