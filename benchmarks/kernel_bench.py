@@ -173,9 +173,40 @@ def bench_attn(engine):
             del qs, outs
 
 
+def bench_attn_long(engine):
+    """BASELINE config 5 per-call shapes (1024^2 inference, batch 8): forward only, the long stripes of split 8
+    and the 32 x 32 full window of the last stage (stripe_fwd_tc_kv), plus split 2 stage 1."""
+    # (name, reso, split, heads, C, last_stage)
+    stages = [("sw8_s1", 256, 8, 2, 64, False), ("sw8_s2", 128, 8, 4, 128, False), ("sw8_s3", 64, 8, 8, 256, False),
+              ("s4_full", 32, 32, 16, 512, True), ("sw2_s1", 256, 2, 2, 64, False)]
+    B, dtype = 8, torch.bfloat16
+    for name, reso, split, heads, C, last in stages:
+        blk = pkg.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, last_stage=last).cuda()
+        for a in blk.attns:
+            a.engine = engine
+        L = reso * reso
+        nbytes = B * L * 3 * C * 2
+        nbuf = max(2, -(-2 * L2_BYTES // nbytes))
+        qs = [(torch.randn(B, L, 3 * C, device="cuda")).to(dtype) for _ in range(nbuf)]
+
+        def fwd_nograd(i):
+            with torch.no_grad():
+                blk.attend(qs[i])
+        ms = time_ms(fwd_nograd, nbuf)
+        N = blk.attns[0].H_sp * blk.attns[0].W_sp
+        fl = 4.0 * N * 32 * B * L * heads
+        by = 4.0 * B * L * C * 2
+        print(json.dumps({"kernel": "attn_fwd", "stage": name, "N": N, "B": B, "L": L, "C": C, "engine": engine,
+                          "us": round(ms * 1e3, 1), "TFLOPs": round(fl / ms / 1e9, 2),
+                          "frac_of_bf16_sustained": round(fl / ms / 1e9 / PEAKS["bf16_tflops_sustained"], 4),
+                          "algorithmic_GBps": round(by / ms / 1e6, 1),
+                          "attainable_tensor_frac": round(min(1.0, (fl / by) / 210.0), 3)}), flush=True)
+        del qs
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("what", choices=["simam", "attn", "layernorm"])
+    ap.add_argument("what", choices=["simam", "attn", "attn_long", "layernorm"])
     ap.add_argument("--engine", default="auto")
     ap.add_argument("--layout", default=None, choices=["NCHW", "NLC"])
     ap.add_argument("--dtype", default=None, choices=["bfloat16", "float32"])
@@ -185,5 +216,7 @@ if __name__ == "__main__":
         bench_simam(a.layout, a.dtype, a.first)
     elif a.what == "layernorm":
         bench_layernorm()
+    elif a.what == "attn_long":
+        bench_attn_long(a.engine)
     else:
         bench_attn(a.engine)

@@ -235,6 +235,7 @@ bool mergeable(const csb200_stripe_desc* d, const StripeGeom* g, int n, bool bac
   if (n != 2) return false;
   for (int i = 0; i < 2; ++i)
     if (pick_engine(&d[i], g[i], backward) != CSB200_ENGINE_TCGEN05) return false;
+  if (g[0].N != 128 && g[0].N != 256) return false;  // long stripes: one launch per branch (key/value-tiled kernel)
   return g[0].N == g[1].N && g[0].B == g[1].B && g[0].H == g[1].H && g[0].W == g[1].W &&
          g[0].scale == g[1].scale && d[0].dtype == d[1].dtype && g[0].drop_thr == g[1].drop_thr;
 }

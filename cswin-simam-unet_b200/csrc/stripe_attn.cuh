@@ -53,6 +53,10 @@ int lepe_bwd_prep(const StripeGeom& g, int dtype, const void* v, const float* le
 
 // ---- tcgen05 engine (stripe_attn_tc.cu) -------------------------------------------------------
 bool tc_fwd_supported(const StripeGeom& g, int dtype);
+// long stripes (N = 128 T, T >= 3): key/value-tiled online-softmax forward kernel (stripe_attn_tc_kv.cu)
+bool tc_fwd_kv_supported(const StripeGeom& g, int dtype);
+int tc_fwd_kv(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
+              const float* lepe_b, void* out, float* lse, cudaStream_t st);
 bool tc_bwd_supported(const StripeGeom& g, int dtype);
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st);

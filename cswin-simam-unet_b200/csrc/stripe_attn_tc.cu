@@ -23,6 +23,7 @@
 //
 // TMEM map per buffer (N columns): S fp32 [0,N) -> P bf16 [0,N/2) -> O fp32 [N/2, N/2+32).
 
+#include <cstdlib>
 #include <cstring>
 #include <mutex>
 
@@ -56,6 +57,14 @@ void ensure_context() {
 }
 
 constexpr int HD_ = 32;
+static CUtensorMapL2promotion l2_promotion(int heads) {
+  static const int forced = [] {
+    const char* e = getenv("CSB_L2PROMO");  // experiment knob: 0 none, 1 64 B, 2 128 B, 3 256 B
+    return e ? atoi(e) : -1;
+  }();
+  if (forced >= 0) return static_cast<CUtensorMapL2promotion>(forced);
+  return heads >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B;
+}
 // A token row of one head is 64 B.  With >= 2 heads the other half of the 128-B line is the
 // neighbouring head, which the neighbouring CTA wants at the same moment: promote to 128 B.  With a
 // single head it belongs to the other branch / operand: promoting would double the DRAM traffic.
@@ -71,8 +80,7 @@ int tc_make_map(CUtensorMap* m, const void* base, const StripeGeom& g, int64_t s
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides,
                    box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
-                   g.heads >= 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B : CU_TENSOR_MAP_L2_PROMOTION_L2_64B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                   l2_promotion(g.heads), CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(CSB200_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
   return CSB200_OK;
 }
@@ -676,14 +684,18 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
 
 // Shapes the tcgen05 engine tiles: bf16, stripes of exactly 128 or 256 tokens whose width divides
 // (or is a multiple of) 128, so that a 128-row tile is a rectangular TMA box.
-bool tc_fwd_supported(const StripeGeom& g, int dtype) {
+bool tc_single_pass_supported(const StripeGeom& g, int dtype) {
   if (dtype != CSB200_BF16) return false;
   if (g.N != 128 && g.N != 256) return false;
   if (!((g.ws <= TILE && TILE % g.ws == 0) || (g.ws % TILE == 0))) return false;
   if (g.ws > 256 || g.hs > 256) return false;
   return true;
 }
-bool tc_bwd_supported(const StripeGeom& g, int dtype) { return tc_fwd_supported(g, dtype); }
+// forward: the single-pass kernels here, or the key/value-tiled kernel for long stripes (stripe_attn_tc_kv.cu)
+bool tc_fwd_supported(const StripeGeom& g, int dtype) {
+  return tc_single_pass_supported(g, dtype) || tc_fwd_kv_supported(g, dtype);
+}
+bool tc_bwd_supported(const StripeGeom& g, int dtype) { return tc_single_pass_supported(g, dtype); }
 
 #ifdef CSB_PROF
 extern "C" __attribute__((visibility("default"))) int csb200_debug_prof_fwd(unsigned long long* out, int reset) {
@@ -703,6 +715,7 @@ int tc_fwd_multi(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t s
 
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st) {
+  if (g.N != 128 && g.N != 256) return tc_fwd_kv(g, q, k, v, lepe_w, lepe_b, out, lse, st);
   const TcFwdIO io{q, k, v, lepe_w, lepe_b, out, lse};
   return tc_fwd_multi(1, &g, &io, st);
 }

@@ -857,6 +857,18 @@ def _attn_tag(B, L, C, branches) -> str:
 _ENGINE = {"auto": capi.ENGINE_AUTO, "simt": capi.ENGINE_SIMT, "tcgen05": capi.ENGINE_TCGEN05}
 
 
+def stripe_engine(dtype: torch.dtype, B, H, W, br: Branch, backward=False, engine="auto") -> str:
+    """Which engine csb200_stripe_attn_fwd / _bwd runs for this shape (csb200_stripe_attn_engine): "simt" or
+    "tcgen05".  Raises like the launch would for an invalid / untileable request."""
+    C = br.chans
+    d = _desc(0 if dtype == torch.float32 else 1, B, H, W, br, 1.0, _ENGINE[engine], [(H * W * 3 * C, 3 * C)] * 3,
+              (H * W * C, C), [(H * W * 3 * C, 3 * C)] * 3)
+    rc = capi.lib().csb200_stripe_attn_engine(ctypes.byref(d), int(backward))
+    if rc < 0:
+        raise RuntimeError(capi.last_error())
+    return {capi.ENGINE_SIMT: "simt", capi.ENGINE_TCGEN05: "tcgen05"}[rc]
+
+
 class _CrossStripeFn(torch.autograd.Function):
     """All branches of one CSWinBlock on the packed (B, L, 3C) qkv buffer -> (B, L, C).
 

@@ -253,3 +253,41 @@ def test_backward_at_benchmarked_launch_geometry(stage):
     out2.backward(gout.cuda())
     assert _per_image_rel(got_out, out2.detach().float().cpu()) < 2 ** -6
     assert _per_image_rel(got_dqkv, q2.grad.float().cpu()) < 2 * BWD_TOL[torch.bfloat16]
+
+
+# Long stripes of BASELINE config 5 (1024^2: C:232-242 geometry at split 8 -> N = 2048, 1024, 512; the 32 x 32
+# full window of the last stage -> N = 1024) plus a T = 3 case: (B, H, W, hs, ws, heads).
+LONG_STRIPES = [(1, 256, 256, 256, 8, 2), (1, 16, 256, 8, 256, 1), (1, 128, 128, 128, 8, 2), (1, 64, 64, 8, 64, 4),
+                (2, 32, 32, 32, 32, 8), (1, 48, 16, 48, 8, 1), (3, 64, 16, 64, 16, 2)]
+
+
+@pytest.mark.parametrize("case", LONG_STRIPES)
+def test_long_stripes_run_on_the_key_value_tiled_tcgen05_kernel(case):
+    """N = 128 T (3 <= T <= 16): forward on stripe_fwd_tc_kv (online softmax over key/value blocks), backward on
+    the CUDA-core engine, both against the fp64 oracle of LePEAttention.forward (C:271-298)."""
+    B, H, W, hs, ws, heads = case
+    C = heads * 32
+    br = csbF.Branch(hs, ws, heads, 0, C)
+    assert csbF.stripe_engine(torch.bfloat16, B, H, W, br) == "tcgen05"
+    assert csbF.stripe_engine(torch.bfloat16, B, H, W, br, backward=True) == "simt"
+    assert csbF.stripe_engine(torch.float32, B, H, W, br) == "simt"
+    gen = torch.Generator().manual_seed(sum(case))
+    qkv = torch.randn((3, B, H * W, C), generator=gen)
+    qkv[:2] *= 1.5  # block maxima that differ, so the running-max rescale matters
+    qkv = qkv.to(torch.bfloat16).double()
+    w = (torch.randn((C, 1, 3, 3), generator=gen) * 0.3).float().double()
+    b = (torch.randn((C,), generator=gen) * 0.1).float().double()
+    gout = torch.randn((B, H * W, C), generator=gen).to(torch.bfloat16).double()
+    out, dqkv, dw, db = _run(qkv, w, b, gout, (H, W), hs, ws, heads, torch.bfloat16)
+    q64 = qkv.clone().requires_grad_(True)
+    w64, b64 = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = ops.stripe_attention(q64[0], q64[1], q64[2], w64, b64, H, W, hs, ws, heads)
+    ref.backward(gout)
+    assert _per_image_rel(out, ref.detach()) < FWD_TOL[torch.bfloat16]
+    assert rel_err(dqkv, q64.grad) < BWD_TOL[torch.bfloat16]  # uses the lse the tiled forward wrote
+    assert rel_err(dw, w64.grad) < BWD_TOL[torch.bfloat16] and rel_err(db, b64.grad) < BWD_TOL[torch.bfloat16]
+    # the CUDA-core engine on the same inputs: the two forwards agree
+    packed = torch.cat([qkv[0], qkv[1], qkv[2]], dim=-1).to(torch.bfloat16).cuda()
+    with torch.no_grad():
+        o_simt = csbF.cross_stripe_attention(packed, H, W, [br], 32 ** -0.5, [w.float().cuda(), b.float().cuda()], "simt")
+    assert _per_image_rel(out, o_simt.float().cpu()) < 2 ** -6
