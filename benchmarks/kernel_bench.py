@@ -50,7 +50,7 @@ def time_ms(fn, nbuf, reps=20, warmup=3):
     return a.elapsed_time(b) / reps
 
 
-def bench_simam(only_layout=None, only_dtype=None, first=None):
+def bench_simam(only_layout=None, only_dtype=None, first=None, workspace=True):
     # config 2 (UNet 256^2, B=16): DoubleConv outputs, NCHW; config 3 (CSWin 512^2, B=32): skips, NLC
     cases = [("NCHW", (16, 64, 256, 256)), ("NCHW", (16, 128, 128, 128)), ("NCHW", (16, 256, 64, 64)),
              ("NCHW", (16, 512, 32, 32)), ("NCHW", (16, 1024, 16, 16)),
@@ -73,24 +73,31 @@ def bench_simam(only_layout=None, only_dtype=None, first=None):
             lib, vp = pkg.capi.lib(), ctypes.c_void_p
             lay = pkg.capi.NCHW if layout == "NCHW" else pkg.capi.NLC
             code = pkg.capi.dtype_code(xs[0])
+            # the caller-owned workspace of csb200_simam_*_ws (zeroed once): large NLC tensors then take the
+            # grid-resident kernels; --no-workspace times the cluster kernels of the plain entry points
+            need = lib.csb200_simam_workspace_bytes(B, C, S, lay, code) if workspace else 0
+            ws = torch.zeros(max(need, 16), dtype=torch.uint8, device="cuda")
+            wsp, wsn = (vp(ws.data_ptr()), need) if need else (None, 0)
 
             def fwd(i):  # straight through the C ABI, on torch's current stream
                 st = vp(torch.cuda.current_stream().cuda_stream)
-                pkg.capi.check(lib.csb200_simam_fwd(vp(xs[i].data_ptr()), vp(ys[i].data_ptr()),
-                                                    vp(stats[i].data_ptr()), B, C, S, lay, code, 1e-4, st), "fwd")
+                pkg.capi.check(lib.csb200_simam_fwd_ws(vp(xs[i].data_ptr()), vp(ys[i].data_ptr()),
+                                                       vp(stats[i].data_ptr()), B, C, S, lay, code, 1e-4, wsp, wsn, st),
+                               "fwd")
 
             def bwd(i):
                 st = vp(torch.cuda.current_stream().cuda_stream)
-                pkg.capi.check(lib.csb200_simam_bwd(vp(xs[i].data_ptr()), vp(gs[i].data_ptr()),
-                                                    vp(stats[i].data_ptr()), vp(ys[i].data_ptr()), B, C, S, lay,
-                                                    code, 1e-4, st), "bwd")
+                pkg.capi.check(lib.csb200_simam_bwd_ws(vp(xs[i].data_ptr()), vp(gs[i].data_ptr()),
+                                                       vp(stats[i].data_ptr()), vp(ys[i].data_ptr()), B, C, S, lay,
+                                                       code, 1e-4, wsp, wsn, st), "bwd")
             ms_f = time_ms(fwd, nbuf)
             ms_b = time_ms(bwd, nbuf)
             for name, ms, mult in (("simam_fwd", ms_f, 2), ("simam_bwd", ms_b, 3)):
                 gbs = mult * nbytes / ms / 1e6
                 print(json.dumps({"kernel": name, "layout": layout, "shape": shape, "dtype": str(dtype)[6:],
                                   "us": round(ms * 1e3, 2), "algorithmic_GBps": round(gbs, 1),
-                                  "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3), "buffers": nbuf}),
+                                  "frac_of_measured_hbm": round(gbs / PEAKS["hbm_gbs"], 3), "buffers": nbuf,
+                                  "grid_resident_kernels": bool(need)}),
                       flush=True)
             del xs, gs, ys, stats
 
@@ -211,9 +218,10 @@ if __name__ == "__main__":
     ap.add_argument("--layout", default=None, choices=["NCHW", "NLC"])
     ap.add_argument("--dtype", default=None, choices=["bfloat16", "float32"])
     ap.add_argument("--first", type=int, default=None, help="only the first K SimAM shapes")
+    ap.add_argument("--no-workspace", action="store_true", help="SimAM: plain entry points (cluster kernels)")
     a = ap.parse_args()
     if a.what == "simam":
-        bench_simam(a.layout, a.dtype, a.first)
+        bench_simam(a.layout, a.dtype, a.first, not a.no_workspace)
     elif a.what == "layernorm":
         bench_layernorm()
     elif a.what == "attn_long":

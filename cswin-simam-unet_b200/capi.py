@@ -40,7 +40,8 @@ _lib = None
 _lock = threading.Lock()
 
 EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_count", "csb200_simam_fwd",
-           "csb200_simam_bwd", "csb200_layernorm_supported", "csb200_layernorm_fwd",
+           "csb200_simam_bwd", "csb200_simam_workspace_bytes", "csb200_simam_fwd_ws", "csb200_simam_bwd_ws",
+           "csb200_layernorm_supported", "csb200_layernorm_fwd",
            "csb200_layernorm_bwd_workspace_bytes", "csb200_layernorm_bwd", "csb200_add_layernorm_fwd",
            "csb200_add_layernorm_bwd", "csb200_add_layernorm_bwd_rb", "csb200_colsum_supported",
            "csb200_colsum_workspace_bytes", "csb200_colsum", "csb200_add_row_bias", "csb200_gelu_supported", "csb200_gelu_fwd",
@@ -72,6 +73,13 @@ def lib() -> ctypes.CDLL:
         L.csb200_launch_count.restype = ctypes.c_uint64
         L.csb200_simam_fwd.argtypes = [vp, vp, f32p, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp]
         L.csb200_simam_bwd.argtypes = [vp, vp, f32p, vp, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp]
+        L.csb200_simam_workspace_bytes.argtypes = [i64, i64, i64, ctypes.c_int, ctypes.c_int]
+        L.csb200_simam_workspace_bytes.restype = ctypes.c_size_t
+        L.csb200_simam_fwd_ws.argtypes = [vp, vp, f32p, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp,
+                                          ctypes.c_size_t, vp]
+        L.csb200_simam_bwd_ws.argtypes = [vp, vp, f32p, vp, i64, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp,
+                                          ctypes.c_size_t, vp]
+        L.csb200_simam_fwd_ws.restype = L.csb200_simam_bwd_ws.restype = ctypes.c_int
         L.csb200_layernorm_supported.argtypes = [i64, ctypes.c_int]
         L.csb200_layernorm_supported.restype = ctypes.c_int
         L.csb200_layernorm_fwd.argtypes = [vp, vp, vp, vp, vp, i64, i64, ctypes.c_int, ctypes.c_int, ctypes.c_float, vp]

@@ -1992,6 +1992,8 @@ int nlc_stream(const T* x, const T* gy, float* stats_out, const float* stats_in,
   return -1;
 }
 
+#include "simam_grid.cuh"
+
 // ------------------------------------------------------------------------------------------------
 // launch helpers
 // ------------------------------------------------------------------------------------------------
@@ -2162,10 +2164,14 @@ int nlc_resident(const T* x, const T* gy, float* stats_out, const float* stats_i
 template <typename T, bool BWD>
 int simam_dispatch(const void* x_, const void* gy_, float* stats_out, const float* stats_in,
                    void* out_, int64_t B, int64_t C, int64_t S, int layout, float e_lambda,
-                   cudaStream_t st) {
+                   cudaStream_t st, void* ws = nullptr, size_t ws_bytes = 0) {
   const T* x = static_cast<const T*>(x_);
   const T* gy = static_cast<const T*>(gy_);
   T* out = static_cast<T*>(out_);
+  if (layout == CSB200_NLC && ws != nullptr) {
+    const int rs = nlc_grid<T, BWD>(x, gy, stats_out, stats_in, out, B, C, S, e_lambda, ws, ws_bytes, st);
+    if (rs >= 0) return rs;
+  }
   if (layout == CSB200_NCHW) {
     int rs;
     if constexpr (BWD) rs = nchw_bwd_stream<T>(x, gy, stats_in, out, B * C, S, st);
@@ -2204,23 +2210,58 @@ int simam_check(const void* x, const void* out, int64_t B, int64_t C, int64_t S,
 
 using namespace csb200;
 
-extern "C" int csb200_simam_fwd(const void* x, void* y, float* stats, int64_t batch,
-                                int64_t channels, int64_t spatial, int layout, int dtype,
-                                float e_lambda, void* stream) {
+#ifdef CSB_PROF
+extern "C" __attribute__((visibility("default"))) int csb200_debug_prof_simam(unsigned long long* out, int reset) {
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(out, g_simam_prof, sizeof(g_simam_prof));
+  if (reset) {
+    unsigned long long z[16] = {0};
+    cudaMemcpyToSymbol(g_simam_prof, z, sizeof(z));
+  }
+  return 0;
+}
+#endif
+
+extern "C" size_t csb200_simam_workspace_bytes(int64_t batch, int64_t channels, int64_t spatial, int layout,
+                                               int dtype) {
+  if (layout != CSB200_NLC || batch <= 0 || channels <= 0 || spatial <= 0) return 0;
+  const int sms = device_sm_count();
+  if (sms <= 0) return 0;
+  GridPlan plan;
+  size_t fwd = 0, bwd = 0;
+  if (dtype == CSB200_F32) {
+    if (!grid_plan<float, false>(batch, channels, spatial, sms, &plan, &fwd)) fwd = 0;
+    if (!grid_plan<float, true>(batch, channels, spatial, sms, &plan, &bwd)) bwd = 0;
+  } else if (dtype == CSB200_BF16) {
+    if (!grid_plan<__nv_bfloat16, false>(batch, channels, spatial, sms, &plan, &fwd)) fwd = 0;
+    if (!grid_plan<__nv_bfloat16, true>(batch, channels, spatial, sms, &plan, &bwd)) bwd = 0;
+  }
+  return fwd > bwd ? fwd : bwd;
+}
+
+extern "C" int csb200_simam_fwd_ws(const void* x, void* y, float* stats, int64_t batch, int64_t channels,
+                                   int64_t spatial, int layout, int dtype, float e_lambda, void* workspace,
+                                   size_t workspace_bytes, void* stream) {
   int rc = simam_check(x, y, batch, channels, spatial, layout, dtype);
   if (rc != CSB200_OK) return rc;
   if (batch * channels * spatial == 0) return CSB200_OK;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CSB200_F32)
     return simam_dispatch<float, false>(x, nullptr, stats, nullptr, y, batch, channels, spatial,
-                                        layout, e_lambda, st);
+                                        layout, e_lambda, st, workspace, workspace_bytes);
   return simam_dispatch<__nv_bfloat16, false>(x, nullptr, stats, nullptr, y, batch, channels,
-                                              spatial, layout, e_lambda, st);
+                                              spatial, layout, e_lambda, st, workspace, workspace_bytes);
 }
 
-extern "C" int csb200_simam_bwd(const void* x, const void* grad_y, const float* stats,
-                                void* grad_x, int64_t batch, int64_t channels, int64_t spatial,
-                                int layout, int dtype, float e_lambda, void* stream) {
+extern "C" int csb200_simam_fwd(const void* x, void* y, float* stats, int64_t batch,
+                                int64_t channels, int64_t spatial, int layout, int dtype,
+                                float e_lambda, void* stream) {
+  return csb200_simam_fwd_ws(x, y, stats, batch, channels, spatial, layout, dtype, e_lambda, nullptr, 0, stream);
+}
+
+extern "C" int csb200_simam_bwd_ws(const void* x, const void* grad_y, const float* stats, void* grad_x,
+                                   int64_t batch, int64_t channels, int64_t spatial, int layout, int dtype,
+                                   float e_lambda, void* workspace, size_t workspace_bytes, void* stream) {
   int rc = simam_check(x, grad_x, batch, channels, spatial, layout, dtype);
   if (rc != CSB200_OK) return rc;
   if (batch * channels * spatial == 0) return CSB200_OK;
@@ -2229,7 +2270,14 @@ extern "C" int csb200_simam_bwd(const void* x, const void* grad_y, const float* 
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (dtype == CSB200_F32)
     return simam_dispatch<float, true>(x, grad_y, nullptr, stats, grad_x, batch, channels, spatial,
-                                       layout, e_lambda, st);
+                                       layout, e_lambda, st, workspace, workspace_bytes);
   return simam_dispatch<__nv_bfloat16, true>(x, grad_y, nullptr, stats, grad_x, batch, channels,
-                                             spatial, layout, e_lambda, st);
+                                             spatial, layout, e_lambda, st, workspace, workspace_bytes);
+}
+
+extern "C" int csb200_simam_bwd(const void* x, const void* grad_y, const float* stats,
+                                void* grad_x, int64_t batch, int64_t channels, int64_t spatial,
+                                int layout, int dtype, float e_lambda, void* stream) {
+  return csb200_simam_bwd_ws(x, grad_y, stats, grad_x, batch, channels, spatial, layout, dtype, e_lambda, nullptr, 0,
+                             stream);
 }

@@ -158,49 +158,81 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t tmem = sm.tmem_base;
   PROF_T(kbeg);
 
-  if (warp == 0) {
-    // ===================================== producer =========================================
-    for (int gi = 0; gi < my_groups; ++gi) {
+  if (warp == 0 || warp == 2) {
+    // ============================== producers (two warps) ===================================
+    // warp 0 takes the even groups of this CTA, warp 2 the odd ones.  One thread gets an 8-KB box of 64-byte rows
+    // through every ~800 cycles whatever the ring depth, two warps together reach what the access pattern
+    // sustains (benchmarks/debug/tma_rows.cu: 2.6 -> 4.3 TB/s); with all boxes on one warp the MMA warps waited
+    // ~3 300 cycles per group for data at N = 128.  The four boxes of a group stay on one warp, back to back
+    // (q | k | v of a token share a DRAM page).
+    // The lse / delta / LePE-tap gathers are fetched ONE GROUP AHEAD into registers (an L2 / DRAM round trip that
+    // would otherwise sit between the TMA issues of consecutive groups).
+    const int first = warp >> 1;
+    constexpr int PER_LANE = NK / 32;
+    float r_lse[PER_LANE], r_delta[PER_LANE], r_tap[9];
+    struct GC {
+      int b, br, head, wx, wy, tok0;
+    };
+    auto decode = [&](int gi) {
+      GC c;
       const int g = (int)blockIdx.x + gi * (int)gridDim.x;
-      const int b = g / p.gpi;
-      int r = g - b * p.gpi;
-      const int br = r >= p.g0 ? 1 : 0;
-      r -= br ? p.g0 : 0;
-      const BwdBranch& bg = p.br[br];
-      const int head = r % bg.heads;
+      c.b = g / p.gpi;
+      int r = g - c.b * p.gpi;
+      c.br = r >= p.g0 ? 1 : 0;
+      r -= c.br ? p.g0 : 0;
+      const BwdBranch& bg = p.br[c.br];
+      c.head = r % bg.heads;
       r /= bg.heads;
-      const int wx = r % bg.nwx, wy = r / bg.nwx;
+      c.wx = r % bg.nwx;
+      c.wy = r / bg.nwx;
+      c.tok0 = (c.wy * bg.hs) * p.W + c.wx * bg.ws;
+      return c;
+    };
+    auto gather = [&](const GC& c) {
+      const BwdBranch& bg = p.br[c.br];
+      const float* lse = bg.lse + ((int64_t)c.b * bg.heads + c.head) * p.L;
+      const float* dl = bg.delta + ((int64_t)c.b * bg.heads + c.head) * p.L;
+#pragma unroll
+      for (int j = 0; j < PER_LANE; ++j) {
+        const int i = lane + 32 * j;
+        const int tok = c.tok0 + (i >> bg.ws_log2) * p.W + (i & (bg.ws - 1));
+        r_lse[j] = __ldg(lse + tok);
+        r_delta[j] = __ldg(dl + tok);
+      }
+#pragma unroll
+      for (int j = 0; j < 9; ++j) r_tap[j] = __ldg(bg.lepe_w + (c.head * HD + lane) * 9 + j);  // [tap j][c = lane]
+    };
+    if (first < my_groups) gather(decode(first));
+    for (int gi = first; gi < my_groups; gi += 2) {
+      const GC c = decode(gi);
+      const BwdBranch& bg = p.br[c.br];
       const int gs = gi % GS;
       mbar_wait(&sm.grp_empty[gs], ((gi / GS) & 1) ^ 1);
-      const int tok0 = (wy * bg.hs) * p.W + wx * bg.ws;
-      // the four tile copies first: the lse / delta gathers below are an L2 / DRAM round trip that
-      // used to sit in front of every group's TMA issue
       if (lane == 0) {
         mbar_expect_tx(&sm.grp_full[gs], 4 * BSmem<NK>::OP_BYTES);
-        const int x0 = wx * bg.ws, y0 = wy * bg.hs;
+        const int x0 = c.wx * bg.ws, y0 = c.wy * bg.hs;
 #pragma unroll
         for (int bxi = 0; bxi < T; ++bxi) {
           const int dx = (bg.ws > TILE) ? (bxi * TILE) % bg.ws : 0;
           const int dy = (bg.ws > TILE) ? (bxi * TILE) / bg.ws : bxi * bg.by;
           const int off = bxi * TILE_BYTES;
-          tma_load_4d(sm.k[gs] + off, &maps.k[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
-          tma_load_4d(sm.q[gs] + off, &maps.q[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
-          tma_load_4d(sm.v[gs] + off, &maps.v[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
-          tma_load_4d(sm.go[gs] + off, &maps.go[br], &sm.grp_full[gs], head * HD, x0 + dx, y0 + dy, b);
+          tma_load_4d(sm.k[gs] + off, &maps.k[c.br], &sm.grp_full[gs], c.head * HD, x0 + dx, y0 + dy, c.b);
+          tma_load_4d(sm.q[gs] + off, &maps.q[c.br], &sm.grp_full[gs], c.head * HD, x0 + dx, y0 + dy, c.b);
+          tma_load_4d(sm.v[gs] + off, &maps.v[c.br], &sm.grp_full[gs], c.head * HD, x0 + dx, y0 + dy, c.b);
+          tma_load_4d(sm.go[gs] + off, &maps.go[c.br], &sm.grp_full[gs], c.head * HD, x0 + dx, y0 + dy, c.b);
         }
       }
-      const float* lse = bg.lse + ((int64_t)b * bg.heads + head) * p.L;
-      const float* dl = bg.delta + ((int64_t)b * bg.heads + head) * p.L;
-      for (int i = lane; i < NK; i += 32) {
-        const int tok = tok0 + (i >> bg.ws_log2) * p.W + (i & (bg.ws - 1));
-        sm.lse2[gs][i] = __ldg(lse + tok) * 1.4426950408889634f;
-        sm.delta[gs][i] = __ldg(dl + tok);
+#pragma unroll
+      for (int j = 0; j < PER_LANE; ++j) {
+        sm.lse2[gs][lane + 32 * j] = r_lse[j] * 1.4426950408889634f;
+        sm.delta[gs][lane + 32 * j] = r_delta[j];
       }
-      for (int i = lane; i < 9 * HD; i += 32)
-        sm.lepe[gs][i] = __ldg(bg.lepe_w + (head * HD + i % HD) * 9 + i / HD);
-      if (lane == 0) sm.coord[gs] = make_int4(b, tok0, head, br);
+#pragma unroll
+      for (int j = 0; j < 9; ++j) sm.lepe[gs][lane + 32 * j] = r_tap[j];
+      if (lane == 0) sm.coord[gs] = make_int4(c.b, c.tok0, c.head, c.br);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.grp_full[gs]);  // second arrival: the plain stores above are done
+      if (gi + 2 < my_groups) gather(decode(gi + 2));
     }
   } else if (warp == 1) {
     // ============================ MMA issuer 1: S^T and dP^T ================================

@@ -7,9 +7,9 @@
 // stream through shared memory and the softmax is the online form (running row max m, running sum l, the
 // 32-column fp32 output accumulator in TMEM rescaled by exp(m_old - m_new) before each P V):
 //
-//   warp 0      TMA producer: Q once per item, K and V once per (item, block), in the issue order below
+//   warp 0      TMA producer: Q once per item, K and V once per (item, block), in the issue order below (even entries)
 //   warp 1      tcgen05.mma issuer   S = Q K_j^T   (M128 x N128 x K32)
-//   warp 2      TMEM allocator
+//   warp 2      TMEM allocator, then the second TMA producer (odd entries)
 //   warp 3      tcgen05.mma issuer   O (+)= P_j V_j (M128 x N32 x K128, P read from TMEM)
 //   warps 4..15 three softmax warpgroups; warpgroup w owns TMEM columns [160 w, 160 w + 160): S / P in
 //               [0, 128), O in [128, 160), and takes every third item; the two issuing warps serve the
@@ -127,33 +127,39 @@ __global__ void __launch_bounds__(THREADS, 1)
   fence_after_sync();
   const uint32_t tmem = sm.tmem_base;
 
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
+  if (warp == 0 || warp == 2) {
+    // ================================ TMA producers (two warps) ================================
+    // warp 0 takes the even (item, block) entries, warp 2 the odd ones: one thread moves an 8-KB box of 64-byte
+    // rows every ~800 cycles whatever the ring depth (benchmarks/debug/tma_rows.cu); the K and V boxes of an entry
+    // stay together on one warp (k | v of a token share a DRAM page)
     if (lane == 0) {
-      int e = 0, qn = 0;  // entries (K / V blocks) and Q tiles issued so far
+      const int mine = warp >> 1;
+      int e = 0, qn = 0;  // entries (K / V blocks) and Q tiles so far (both warps count all of them)
       for (int r = 0; r < rounds; ++r) {
         const int j = r % T;
         for (int w = 0; w < NWG; ++w) {
           const int li = w + NWG * (r / T);
           if (li >= my_items) continue;
-          const Item c = decode_item(p, (int)blockIdx.x + li * (int)gridDim.x);
-          int x, y;
-          if (j == 0) {
-            const int qs = qn % QS;
-            mbar_wait(&sm.q_empty[qs], ((qn / QS) & 1) ^ 1);
-            mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
-            tile_xy(p, c, c.qt, x, y);
-            tma_load_4d(sm.q[qs], &maps.q, &sm.q_full[qs], c.head * HD, x, y, c.b);
-            ++qn;
+          if ((e & 1) == mine) {
+            const Item c = decode_item(p, (int)blockIdx.x + li * (int)gridDim.x);
+            int x, y;
+            if (j == 0) {
+              const int qs = qn % QS;
+              mbar_wait(&sm.q_empty[qs], ((qn / QS) & 1) ^ 1);
+              mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
+              tile_xy(p, c, c.qt, x, y);
+              tma_load_4d(sm.q[qs], &maps.q, &sm.q_full[qs], c.head * HD, x, y, c.b);
+            }
+            const int ks = e % KS, vs = e % VS;
+            tile_xy(p, c, j, x, y);
+            mbar_wait(&sm.k_empty[ks], ((e / KS) & 1) ^ 1);
+            mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
+            tma_load_4d(sm.k[ks], &maps.k, &sm.k_full[ks], c.head * HD, x, y, c.b);
+            mbar_wait(&sm.v_empty[vs], ((e / VS) & 1) ^ 1);
+            mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
+            tma_load_4d(sm.v[vs], &maps.v, &sm.v_full[vs], c.head * HD, x, y, c.b);
           }
-          const int ks = e % KS, vs = e % VS;
-          tile_xy(p, c, j, x, y);
-          mbar_wait(&sm.k_empty[ks], ((e / KS) & 1) ^ 1);
-          mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
-          tma_load_4d(sm.k[ks], &maps.k, &sm.k_full[ks], c.head * HD, x, y, c.b);
-          mbar_wait(&sm.v_empty[vs], ((e / VS) & 1) ^ 1);
-          mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
-          tma_load_4d(sm.v[vs], &maps.v, &sm.v_full[vs], c.head * HD, x, y, c.b);
+          if (j == 0) ++qn;
           ++e;
         }
       }

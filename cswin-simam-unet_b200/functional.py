@@ -7,6 +7,7 @@ CPU or ATen stand-in.  What deliberately stays on library code is said where it 
 sums / bias adds of widths that are not a multiple of the 16-byte vector (``_bias_grad``, ``add_row_bias``).
 """
 import ctypes
+import os
 from typing import Optional, Sequence, Tuple
 
 import torch
@@ -100,6 +101,28 @@ def _simam_plan(x: torch.Tensor, layout: str):
     return x, _simam_dims(x, layout), torch.contiguous_format
 
 
+_simam_ws = {}  # device index -> zero-initialised workspace of the grid-resident kernels (csb200_simam_*_ws)
+# The grid-resident SimAM kernels (csrc/simam_grid.cuh) are correct but, as measured on B200, slower than the
+# cluster kernels on every config-3 shape: off unless CSB200_SIMAM_GRID=1.
+SIMAM_GRID_KERNELS = os.environ.get("CSB200_SIMAM_GRID", "0") == "1"
+
+
+def _simam_workspace(x: torch.Tensor, B, C, S, lay):
+    """(pointer, bytes) of this device's SimAM workspace, grown on demand; (None, 0) when the grid-resident
+    kernels do not apply to the shape.  The library keeps it clean between calls (include/csb200.h), so it is
+    zeroed only when (re)allocated; calls on one device are expected to be stream-ordered."""
+    if not SIMAM_GRID_KERNELS:
+        return None, 0
+    need = capi.lib().csb200_simam_workspace_bytes(B, C, S, lay, capi.dtype_code(x))
+    if need == 0:
+        return None, 0
+    idx = x.device.index if x.device.index is not None else torch.cuda.current_device()
+    ws = _simam_ws.get(idx)
+    if ws is None or ws.numel() < need:
+        ws = _simam_ws[idx] = torch.zeros(need, dtype=torch.uint8, device=x.device)
+    return ws.data_ptr(), ws.numel()
+
+
 class _SimAMFn(torch.autograd.Function):
     @staticmethod
     @torch.amp.custom_fwd(device_type="cuda")
@@ -109,9 +132,11 @@ class _SimAMFn(torch.autograd.Function):
         y = torch.empty_like(x, memory_format=fmt)
         stats = torch.empty((B * C, 2), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device), _span("simam_fwd", 2 * x.numel() * x.element_size()):
-            capi.check(capi.lib().csb200_simam_fwd(_ptr(x), _ptr(y), _ptr(stats), B, C, S, lay,
-                                                   capi.dtype_code(x), float(e_lambda), _vp(capi.stream_of(x))),
-                       "csb200_simam_fwd")
+            ws, ws_bytes = _simam_workspace(x, B, C, S, lay)
+            capi.check(capi.lib().csb200_simam_fwd_ws(_ptr(x), _ptr(y), _ptr(stats), B, C, S, lay,
+                                                      capi.dtype_code(x), float(e_lambda), ws, ws_bytes,
+                                                      _vp(capi.stream_of(x))),
+                       "csb200_simam_fwd_ws")
         ctx.save_for_backward(x, stats)
         ctx.cfg = (B, C, S, lay, float(e_lambda), fmt)
         return y
@@ -126,9 +151,11 @@ class _SimAMFn(torch.autograd.Function):
             gy = gy.to(x.dtype)
         gx = torch.empty_like(x, memory_format=fmt)
         with torch.cuda.device(x.device), _span("simam_bwd", 3 * x.numel() * x.element_size()):
-            capi.check(capi.lib().csb200_simam_bwd(_ptr(x), _ptr(gy), _ptr(stats), _ptr(gx), B, C, S, lay,
-                                                   capi.dtype_code(x), e_lambda, _vp(capi.stream_of(x))),
-                       "csb200_simam_bwd")
+            ws, ws_bytes = _simam_workspace(x, B, C, S, lay)
+            capi.check(capi.lib().csb200_simam_bwd_ws(_ptr(x), _ptr(gy), _ptr(stats), _ptr(gx), B, C, S, lay,
+                                                      capi.dtype_code(x), e_lambda, ws, ws_bytes,
+                                                      _vp(capi.stream_of(x))),
+                       "csb200_simam_bwd_ws")
         return gx, None, None
 
 

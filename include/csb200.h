@@ -75,6 +75,21 @@ CSB200_API int csb200_simam_fwd(const void* x, void* y, float* stats, int64_t ba
 CSB200_API int csb200_simam_bwd(const void* x, const void* grad_y, const float* stats, void* grad_x,
                      int64_t batch, int64_t channels, int64_t spatial, int layout, int dtype,
                      float e_lambda, void* stream);
+/* The same two passes with a caller-owned workspace, which lets large token-layout (NLC) tensors take the
+ * grid-resident kernels (csrc/simam_grid.cuh: all SMs work on a few images at a time, every byte crosses HBM once,
+ * reads of the next images overlap the writes of the current ones).  csb200_simam_workspace_bytes returns the
+ * size to allocate for a shape (0: these kernels do not apply to it; the _ws calls then behave like the plain ones,
+ * as they do with workspace == NULL or a workspace that is too small).
+ * CONTRACT: the workspace must be zero-filled ONCE, when it is allocated; every call leaves it ready for the
+ * next call of any shape.  Calls that share a workspace must be ordered on one stream. */
+CSB200_API size_t csb200_simam_workspace_bytes(int64_t batch, int64_t channels, int64_t spatial, int layout,
+                     int dtype);
+CSB200_API int csb200_simam_fwd_ws(const void* x, void* y, float* stats, int64_t batch, int64_t channels,
+                     int64_t spatial, int layout, int dtype, float e_lambda, void* workspace,
+                     size_t workspace_bytes, void* stream);
+CSB200_API int csb200_simam_bwd_ws(const void* x, const void* grad_y, const float* stats, void* grad_x,
+                     int64_t batch, int64_t channels, int64_t spatial, int layout, int dtype,
+                     float e_lambda, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Token-major LayerNorm over the last dimension — the pre-norms at the CSWinBlock call site (C:357,

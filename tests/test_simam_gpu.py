@@ -112,3 +112,49 @@ def test_simam_full_size_config2_plane_samples(dtype):
     # per-plane independence: permuting planes permutes the output bit-for-bit
     perm = torch.randperm(64, device="cuda")
     assert torch.equal(pkg.simam(x[:, perm].contiguous()), y[:, perm])
+
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.bfloat16])
+@pytest.mark.parametrize("shape", [(32, 16384, 64), (32, 4096, 128), (32, 1024, 256), (12, 3000, 128)])
+def test_simam_grid_resident_kernels(shape, dtype, monkeypatch):
+    """The three CSWin skips of BASELINE config 3 (and a ragged shape) through csb200_simam_fwd_ws / _bwd_ws with a
+    workspace: the grid-resident kernels (csrc/simam_grid.cuh).  Checked against the fp64 oracle on sampled images,
+    against the cluster kernels of the plain entry points on the whole batch, for bit-reproducibility, and for the
+    workspace contract (counters left zero, so calls of different shapes can share it)."""
+    from cswin_simam_unet_b200 import capi, functional as csbF
+    monkeypatch.setattr(csbF, "SIMAM_GRID_KERNELS", True)  # off by default: slower than the cluster kernels so far
+    B, L, C = shape
+    assert capi.lib().csb200_simam_workspace_bytes(B, C, L, capi.NLC, capi._DTYPES[dtype]) > 0
+    torch.manual_seed(L)
+    x = (torch.randn(shape, device="cuda") * 2 + 0.5).to(dtype)
+    gy = torch.randn(shape, device="cuda").to(dtype)
+    xd = x.clone().requires_grad_(True)
+    y = pkg.simam(xd, 1e-4, "NLC")
+    y.backward(gy)
+    # plain entry points (no workspace): the cluster kernels
+    lib, vp = capi.lib(), lambda t: __import__("ctypes").c_void_p(t.data_ptr())
+    y2, gx2 = torch.empty_like(x), torch.empty_like(x)
+    stats = torch.empty(B * C, 2, device="cuda")
+    st = __import__("ctypes").c_void_p(torch.cuda.current_stream().cuda_stream)
+    code = capi._DTYPES[dtype]
+    capi.check(lib.csb200_simam_fwd(vp(x), vp(y2), vp(stats), B, C, L, capi.NLC, code, 1e-4, st), "fwd")
+    capi.check(lib.csb200_simam_bwd(vp(x), vp(gy), vp(stats), vp(gx2), B, C, L, capi.NLC, code, 1e-4, st), "bwd")
+    tol = 2e-6 if dtype == torch.float32 else 2 ** -8  # two summation orders; bf16: at most one output ulp
+    assert rel_err(y.float(), y2.float()) < tol and rel_err(xd.grad.float(), gx2.float()) < tol
+    for b in sorted({0, B // 2, B - 1}):
+        x64 = x[b:b + 1].double().cpu().requires_grad_(True)
+        y64 = ops.simam(x64, 1e-4, "NLC")
+        y64.backward(gy[b:b + 1].double().cpu())
+        assert rel_err(y[b:b + 1].float().cpu(), y64.detach()) < TOL[dtype]
+        assert rel_err(xd.grad[b:b + 1].float().cpu(), x64.grad) < TOL[dtype]
+    # deterministic, and independent of an image's place in the batch
+    xr = x.clone().requires_grad_(True)
+    yr = pkg.simam(xr, 1e-4, "NLC")
+    yr.backward(gy)
+    assert torch.equal(yr, y) and torch.equal(xr.grad, xd.grad)
+    perm = torch.randperm(B, device="cuda")
+    assert torch.equal(pkg.simam(x[perm].contiguous(), 1e-4, "NLC"), y[perm])
+    # the workspace is left clean: every per-image counter is zero again
+    ws = csbF._simam_ws[x.device.index]
+    torch.cuda.synchronize()
+    assert int(ws[:32768].view(torch.int32).abs().sum()) == 0
