@@ -24,8 +24,11 @@ namespace {
 using namespace tc;
 
 constexpr int HD = 32;
-constexpr int CONSUMERS = 384;  // 12 warps: with the producer warp 416 threads -> 128 registers each
-constexpr int THREADS = CONSUMERS + 32;
+constexpr int CONSUMERS = 384;  // 12 warps = 3 warpgroups
+// + one warpgroup for the producer warp (its other three warps only hand their registers over): 512 threads start
+// with 128 registers each, the producer warpgroup drops to 40 and the consumers grow to 152 (setmaxnreg) — with
+// 128 the sliding-window walk (40 weights + 40 accumulators + a 36-register window per thread) spilled
+constexpr int THREADS = CONSUMERS + 128;
 constexpr int MAX_STAGES = 3;
 constexpr int STAGE_BUDGET = 88 * 1024;  // 3 rows of 8 KB per tile: tokens divisible by the 3 * 2^k walkers
 constexpr int SMEM_BUDGET = 200 * 1024;
@@ -176,13 +179,98 @@ __device__ __forceinline__ void prep_items(const PrepTParams& p, const PrepTBran
   }
 }
 
-template <typename T>
+// Sliding-window walk (the config-3 tile shapes: R * W * (cb / 4) == 8 * CONSUMERS, stripe width 1 or a multiple
+// of 8): a thread owns 4 channels of a RUN of 8 consecutive tokens of one tile row and keeps the three v columns
+// (x - 1, x, x + 1) x three rows of the 3x3 window in registers, so a token costs ONE new column (3 shared-memory
+// loads) instead of 9, and there is no per-tap branching: a neighbour outside the stripe (or the image, or the rows
+// a partial tile lacks) is read from a block of zeros — zero padding, C:244,263-265 — by selecting the ADDRESS.
+// The generic walk above executed ~300 instructions per (token, 4 channels) at the stage-3 shape (ncu: issue-bound,
+// 35 us for 50 MB); this one ~85.
+constexpr int SEG = 8;
+template <typename T, bool HAS_X, bool HAS_Y>
+__device__ __forceinline__ void prep_items_slide(const PrepTParams& p, const PrepTBranch& bg, uint32_t ring,
+                                                 uint32_t zaddr, uint64_t* full, uint64_t* empty, int cg, int walker,
+                                                 int my_items, int head, bool writer, const P4 (&w)[10],
+                                                 P4 (&acc)[10]) {
+  constexpr int NX = HAS_X ? 3 : 1, NY = HAS_Y ? 3 : 1;
+  const int stage_bytes = bg.v_bytes + 2 * bg.t_bytes;
+  const int lane = threadIdx.x & 31;
+  const int segs = p.W / SEG;
+  const int r = walker / segs, xs = (walker - r * segs) * SEG;  // tile row and first token of this thread's run
+  const uint32_t tok_bytes = (uint32_t)(bg.cb * (int)sizeof(T)), row_bytes = tok_bytes * (uint32_t)p.W;
+  const bool left_ok = HAS_X && (xs % bg.ws) != 0, right_ok = HAS_X && ((xs + SEG) % bg.ws) != 0;
+  const f2_t m1 = f2_splat(-1.f);
+  for (int i = 0; i < my_items; ++i) {
+    const int item = (int)blockIdx.x + i * (int)gridDim.x;
+    const int b = item / bg.nrb, y0 = (item - b * bg.nrb) * bg.R;
+    const int s = i % bg.stages;
+    const int rows = p.H - y0 < bg.R ? p.H - y0 : bg.R;
+    const bool row_in = r < rows;
+    const int yy = (y0 + r) % bg.hs;
+    // which of the three window rows exist for this thread's tile row (ky = 1 is the row itself)
+    const bool rok[3] = {HAS_Y && row_in && yy != 0, row_in, HAS_Y && row_in && yy != bg.hs - 1};
+    mbar_wait(&full[s], (i / bg.stages) & 1);
+    // v tile row 0 is image row y0 - 1: window row ky of tile row r is v tile row r + ky
+    const uint32_t vrow = ring + (uint32_t)(s * stage_bytes) + (uint32_t)r * row_bytes + (uint32_t)xs * tok_bytes;
+    const uint32_t grow = ring + (uint32_t)(s * stage_bytes + bg.v_bytes) + (uint32_t)r * row_bytes + (uint32_t)xs * tok_bytes;
+    const uint32_t orow = grow + (uint32_t)bg.t_bytes;
+    float* drow = bg.delta + ((int64_t)b * bg.heads + head) * p.L + (int64_t)(y0 + r) * p.W + xs;
+    P4 col[NY][3];  // [window row][slot]; slot (j + kx) % 3 holds column xs + j + kx - 1 while token j is computed
+    auto load_col = [&](int slot, int dxs, bool ok) {  // column xs + dxs of the window rows
+#pragma unroll
+      for (int ky = 0; ky < NY; ++ky) {
+        const int kr = HAS_Y ? ky : 1;
+        const bool use = ok && rok[kr];
+        col[ky][slot] = lds4<T>(use ? vrow + (uint32_t)kr * row_bytes + (uint32_t)(dxs * (int)tok_bytes) : zaddr);
+      }
+    };
+    if (HAS_X) {
+      load_col(0, -1, left_ok);
+      load_col(1, 0, true);
+    }
+#pragma unroll
+    for (int j = 0; j < SEG; ++j) {
+      if (HAS_X) load_col((j + 2) % 3, j + 1, j + 1 < SEG ? true : right_ok);
+      else load_col(0, j, true);
+      const P4 go = lds4<T>(row_in ? grow + (uint32_t)j * tok_bytes : zaddr);
+      const P4 o = lds4<T>(row_in ? orow + (uint32_t)j * tok_bytes : zaddr);
+      P4 lp = w[9];
+      acc[9].a = f2_add(acc[9].a, go.a);
+      acc[9].b = f2_add(acc[9].b, go.b);
+#pragma unroll
+      for (int ky = 0; ky < NY; ++ky) {
+#pragma unroll
+        for (int kx = 0; kx < NX; ++kx) {
+          const P4 vn = col[ky][HAS_X ? (j + kx) % 3 : 0];
+          const int tap = (HAS_Y ? ky : 1) * 3 + (HAS_X ? kx : 1);
+          const P4 wt = w[tap];
+          lp.a = f2_fma(wt.a, vn.a, lp.a);
+          lp.b = f2_fma(wt.b, vn.b, lp.b);
+          P4& a = acc[tap];
+          a.a = f2_fma(go.a, vn.a, a.a);
+          a.b = f2_fma(go.b, vn.b, a.b);
+        }
+      }
+      // go . (o - lp), summed over the 32 channels of the head (8 adjacent lanes)
+      const f2_t d = f2_fma(go.b, f2_fma(lp.b, m1, o.b), f2_mul(go.a, f2_fma(lp.a, m1, o.a)));
+      float d0, d1;
+      f2_split(d, d0, d1);
+      const float dsum = head_sum(d0 + d1);
+      if (writer && row_in) drow[j] = dsum;
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&empty[s]);
+  }
+}
+
+template <typename T, bool SLIDE>
 __global__ void __launch_bounds__(THREADS, 1)
     lepe_prep_tma(const __grid_constant__ PrepTMaps maps, const __grid_constant__ PrepTParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* ring = smem_raw + ((128u - (smem_u32(smem_raw) & 127u)) & 127u);
   __shared__ uint64_t full[MAX_STAGES], empty[MAX_STAGES];
   __shared__ uint8_t s_my[256 + 256], s_mx[256];  // s_my: slack for the rows a partial tile lacks
+  __shared__ __align__(16) uint8_t s_zero[16];    // what a neighbour outside the stripe reads as (sliding-window walk)
 
   const int which = (int)blockIdx.y >= p.ncb0 ? 1 : 0;
   const PrepTBranch& bg = p.br[which];
@@ -201,6 +289,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const int xx = i % bg.ws;
     s_mx[i] = (uint8_t)((xx > 0 ? 1 : 0) | (xx < bg.ws - 1 ? 2 : 0));
   }
+  if (threadIdx.x < 16) s_zero[threadIdx.x] = 0;
   if (threadIdx.x == 0) {
     for (int i = 0; i < MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
@@ -210,9 +299,10 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
   __syncthreads();
 
-  if (warp == CONSUMERS / 32) {
+  if (warp >= CONSUMERS / 32) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (warp == CONSUMERS / 32 && lane == 0) {
       prefetch_tensormap(&maps.v[which]);
       prefetch_tensormap(&maps.g[which]);
       prefetch_tensormap(&maps.o[which]);
@@ -232,6 +322,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   }
 
   // ======================================= consumers ========================================
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 152;");
   constexpr int ES = (int)sizeof(T);
   const int cgn = bg.cb >> 2;                    // channel groups (of 4) per token: 8, 16, 32 or 64
   const int cg = (int)threadIdx.x % cgn;
@@ -254,23 +345,35 @@ __global__ void __launch_bounds__(THREADS, 1)
 #pragma unroll
   for (int k = 0; k < 10; ++k) accp[k] = P4{f2_splat(0.f), f2_splat(0.f)};
 
-  Walk wk;
-  wk.t0 = walker; wk.dt = walkers;
-  wk.ry0 = walker / p.W; wk.x0 = walker - wk.ry0 * p.W;
-  wk.dry = walkers / p.W; wk.dx = walkers - wk.dry * p.W;
-  wk.tok_bytes = (uint32_t)(bg.cb * ES);
-  wk.row_bytes = wk.tok_bytes * (uint32_t)p.W;
-  const uint32_t ring_a = smem_u32(ring) + (uint32_t)(cg * 4 * ES);
   const bool writer = (cg & 7) == 0;
   const bool has_x = bg.ws > 1, has_y = bg.hs > 1;
-  if (has_x && has_y)
-    prep_items<T, true, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
-  else if (has_y)
-    prep_items<T, false, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
-  else if (has_x)
-    prep_items<T, true, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
-  else
-    prep_items<T, false, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
+  if constexpr (SLIDE) {  // the host has checked slide_ok() for every branch of the launch
+    const uint32_t ring_c = smem_u32(ring) + (uint32_t)(cg * 4 * ES), zaddr = smem_u32(s_zero);
+    if (has_x && has_y)
+      prep_items_slide<T, true, true>(p, bg, ring_c, zaddr, full, empty, cg, walker, my_items, head, writer, w, accp);
+    else if (has_y)
+      prep_items_slide<T, false, true>(p, bg, ring_c, zaddr, full, empty, cg, walker, my_items, head, writer, w, accp);
+    else if (has_x)
+      prep_items_slide<T, true, false>(p, bg, ring_c, zaddr, full, empty, cg, walker, my_items, head, writer, w, accp);
+    else
+      prep_items_slide<T, false, false>(p, bg, ring_c, zaddr, full, empty, cg, walker, my_items, head, writer, w, accp);
+  } else {
+    Walk wk;
+    wk.t0 = walker; wk.dt = walkers;
+    wk.ry0 = walker / p.W; wk.x0 = walker - wk.ry0 * p.W;
+    wk.dry = walkers / p.W; wk.dx = walkers - wk.dry * p.W;
+    wk.tok_bytes = (uint32_t)(bg.cb * ES);
+    wk.row_bytes = wk.tok_bytes * (uint32_t)p.W;
+    const uint32_t ring_a = smem_u32(ring) + (uint32_t)(cg * 4 * ES);
+    if (has_x && has_y)
+      prep_items<T, true, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
+    else if (has_y)
+      prep_items<T, false, true>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
+    else if (has_x)
+      prep_items<T, true, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
+    else
+      prep_items<T, false, false>(p, bg, ring_a, full, empty, s_my, s_mx, wk, my_items, head, writer, w, accp);
+  }
 
   float4 acc[10];
 #pragma unroll
@@ -401,15 +504,26 @@ int lepe_prep_tma_launch(int nbr, const StripeGeom* g, int dtype, const PrepIO* 
     if ((rc = make_tok_map(&maps.o[i], io[i].out, dtype, cp, p.W, p.H, p.B, g[i].o_sb, g[i].o_sl, b.cb, b.R)) != CSB200_OK) return rc;
   }
   smem += 128;
-  const int ti = dtype == CSB200_F32 ? 0 : 1;
-  if (ti == 0)
-    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&lepe_prep_tma<float>), SMEM_BUDGET + 128));
-  else
-    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&lepe_prep_tma<__nv_bfloat16>), SMEM_BUDGET + 128));
-  if (ti == 0)
-    lepe_prep_tma<float><<<dim3(gx, ncb), THREADS, smem, st>>>(maps, p);
-  else
-    lepe_prep_tma<__nv_bfloat16><<<dim3(gx, ncb), THREADS, smem, st>>>(maps, p);
+  // sliding-window walk: every branch's tile is 8 tokens per consumer thread and stripe widths are 1 or 8 k
+  bool slide = true;
+  for (int i = 0; i < nbr; ++i) {
+    const PrepTBranch& b = p.br[i];
+    slide = slide && b.R * p.W * (b.cb / 4) == CONSUMERS * SEG && p.W % SEG == 0 && (b.ws == 1 || b.ws % SEG == 0);
+  }
+  const dim3 grid(gx, ncb);
+#define CSB_PREP_LAUNCH(TT, SL)                                                                              \
+  do {                                                                                                       \
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&lepe_prep_tma<TT, SL>), SMEM_BUDGET + 128));      \
+    lepe_prep_tma<TT, SL><<<grid, THREADS, smem, st>>>(maps, p);                                             \
+  } while (0)
+  if (dtype == CSB200_F32) {
+    if (slide) CSB_PREP_LAUNCH(float, true);
+    else CSB_PREP_LAUNCH(float, false);
+  } else {
+    if (slide) CSB_PREP_LAUNCH(__nv_bfloat16, true);
+    else CSB_PREP_LAUNCH(__nv_bfloat16, false);
+  }
+#undef CSB_PREP_LAUNCH
   *blocks = gx;
   return check_launch("lepe_prep_tma");
 }

@@ -267,17 +267,15 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
   // setmaxnreg that dominates it) and each warpgroup executes one common instruction.
   if (warp < 4) {
     if constexpr (LWG) setmaxnreg<0, 40>();
-  if (warp == 0 || warp == 2) {
-    // ============================ TMA producers (two warps) ============================
-    // warp 0 takes the even groups of this CTA, warp 2 the odd ones: one thread gets an 8-KB box of 64-byte rows
-    // through every ~800 cycles however deep the rings are, two warps together reach the ~4.3 TB/s this access
-    // pattern sustains (benchmarks/debug/tma_rows.cu: 2.6 -> 4.3 TB/s).  The three boxes of a group stay on ONE
-    // warp, back to back: q | k | v of a token share a DRAM page.
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    // ONE producer warp: unlike the backward kernel (four boxes per group: two producer warps help there), the
+    // forward pass measured slower with a second producer, whether the warps split the operands (97 us at the
+    // stage-1 shape) or alternate groups (90 us) — 85 us with one.
     // K lives only until its S = Q K^T has been issued and completed; V (with the LePE taps) until the epilogue:
     // separate rings, so K and Q run far ahead of the tiles still in the softmax warpgroups.
     // LePE taps of a head ([tap][c], bias last): 10 values per lane, fetched ONE GROUP AHEAD — the loads are an
-    // L2 round trip that used to sit, un-overlapped, between the TMA issues of consecutive groups
-    const int first = warp >> 1;
+    // L2 round trip that used to sit, un-overlapped, between the TMA issues of consecutive groups (101 -> 85 us).
     constexpr int TAPS_PER_LANE = LEPE_FLOATS / 32;
     float taps[TAPS_PER_LANE];
     auto fetch_taps = [&](const GroupCoord& gc) {
@@ -286,15 +284,18 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       for (int j = 0; j < TAPS_PER_LANE; ++j)  // element lane + 32 j: tap j (HD == 32), channel = lane
         taps[j] = j < 9 ? __ldg(b2.lepe_w + (gc.head * HD + lane) * 9 + j) : __ldg(b2.lepe_b + gc.head * HD + lane);
     };
-    if (first < my_groups) fetch_taps(decode_group(p, (int)blockIdx.x + first * (int)gridDim.x));
-    for (int gi = first; gi < my_groups; gi += 2) {
+    if (my_groups > 0) fetch_taps(decode_group(p, (int)blockIdx.x));
+    int it = 0;
+    for (int gi = 0; gi < my_groups; ++gi) {
       const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
       const FwdBranch& bg = p.br[c.br];
       const int ks = gi % KS, vs = gi % VS;
       mbar_wait(&sm.k_empty[ks], ((gi / KS) & 1) ^ 1);
+      mbar_wait(&sm.v_empty[vs], ((gi / VS) & 1) ^ 1);
       if (lane == 0) {
-        const int x0 = c.wx * bg.ws, y0 = c.wy * bg.hs;
         mbar_expect_tx(&sm.k_full[ks], Smem<NK>::KV_BYTES);
+        mbar_expect_tx(&sm.v_full[vs], Smem<NK>::KV_BYTES);
+        const int x0 = c.wx * bg.ws, y0 = c.wy * bg.hs;
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) {
           // box `bx` covers in-stripe rows [128 bx, 128 bx + 128)
@@ -302,26 +303,18 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
           const int dy = (bg.ws > TILE) ? (bx * TILE) / bg.ws : bx * bg.by;
           tma_load_4d(sm.k[ks] + bx * TILE_BYTES, &maps.k[c.br], &sm.k_full[ks], c.head * HD,
                       x0 + dx, y0 + dy, c.b);
+          tma_load_4d(sm.v[vs] + bx * TILE_BYTES, &maps.v[c.br], &sm.v_full[vs], c.head * HD,
+                      x0 + dx, y0 + dy, c.b);
         }
-        for (int t = 0; t < T; ++t) {
-          const int it = gi * T + t, qs = it % QS;
+        for (int t = 0; t < T; ++t, ++it) {
+          const int qs = it % QS;
           mbar_wait(&sm.q_empty[qs], ((it / QS) & 1) ^ 1);
           mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
           const int dx = (bg.ws > TILE) ? (t * TILE) % bg.ws : 0;
           const int dy = (bg.ws > TILE) ? (t * TILE) / bg.ws : t * bg.by;
           tma_load_4d(sm.q[qs], &maps.q[c.br], &sm.q_full[qs], c.head * HD, x0 + dx, y0 + dy, c.b);
         }
-        mbar_wait(&sm.v_empty[vs], ((gi / VS) & 1) ^ 1);
-        mbar_expect_tx(&sm.v_full[vs], Smem<NK>::KV_BYTES);
-#pragma unroll
-        for (int bx = 0; bx < NBOX; ++bx) {
-          const int dx = (bg.ws > TILE) ? (bx * TILE) % bg.ws : 0;
-          const int dy = (bg.ws > TILE) ? (bx * TILE) / bg.ws : bx * bg.by;
-          tma_load_4d(sm.v[vs] + bx * TILE_BYTES, &maps.v[c.br], &sm.v_full[vs], c.head * HD,
-                      x0 + dx, y0 + dy, c.b);
-        }
       }
-      __syncwarp();  // lane 0 has seen v_empty: the stage's previous readers are done with sm.lepe / sm.coord
       // taps of this head -> smem; plain stores, released by the second arrival on v_full
 #pragma unroll
       for (int j = 0; j < TAPS_PER_LANE; ++j) sm.lepe[vs][lane + 32 * j] = taps[j];
@@ -329,7 +322,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
         sm.coord[vs] = make_int4(c.b, (c.wy * bg.hs) * p.W + c.wx * bg.ws, c.head, c.br);
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.v_full[vs]);
-      if (gi + 2 < my_groups) fetch_taps(decode_group(p, (int)blockIdx.x + (gi + 2) * (int)gridDim.x));
+      if (gi + 1 < my_groups) fetch_taps(decode_group(p, (int)blockIdx.x + (gi + 1) * (int)gridDim.x));
     }
   } else if (warp == 1) {
     // ================================ MMA issuer 1: S = Q K^T ================================
