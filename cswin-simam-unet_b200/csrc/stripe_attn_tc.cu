@@ -101,6 +101,15 @@ namespace {
 using namespace tc;
 
 constexpr int HD = 32;
+// Every POLY_MOD-th pair of exponentials can run on the FMA pipes instead of MUFU (tc_common.cuh: ex2_poly_pair).
+// Measured here: no gain at N = 128 / 256 (45.5 -> 45.1 us at the stage-3 shape) — the sweep is bound by the ISSUE
+// slots of the two softmax warps per scheduler (~4 instructions per element with MUFU, ~8 with the polynomial), not
+// by the MUFU pipe — so it is off; the key/value-tiled kernel (stripe_attn_tc_kv.cu, three softmax warpgroups,
+// compute-bound) keeps it (+4 %).
+#ifndef CSB_POLY_MOD
+#define CSB_POLY_MOD 0
+#endif
+constexpr int POLY_MOD = CSB_POLY_MOD;
 constexpr int TILE = 128;                   // query rows per tile == TMEM lanes
 constexpr int ROW_BYTES = HD * 2;           // 64 B per token row of one head
 constexpr int TILE_BYTES = TILE * ROW_BYTES;  // 8 KB
@@ -461,6 +470,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
         tmem_wait_ld();
       }
       const float neg_m = -m * p.scale_log2;
+      const f2_t scale2 = f2_splat(p.scale_log2), negm2 = f2_splat(neg_m);
       PROF_T(t2);
       float l0 = 0.f, l1 = 0.f;
       // attention dropout (C:290): the stripe coordinates of the group are needed before the epilogue
@@ -497,8 +507,17 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
         }
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
-          float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+          // x = s * scale * log2(e) - max, as a packed pair; every POLY_MOD-th pair takes the FMA-pipe 2^x
+          const f2_t x2 = f2_fma(f2_make(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
+          float p0, p1;
+          if (POLY_MOD > 0 && i % POLY_MOD == POLY_MOD - 1) {
+            ex2_poly_pair(x2, p0, p1);
+          } else {
+            float x0, x1;
+            f2_split(x2, x0, x1);
+            p0 = ex2(x0);
+            p1 = ex2(x1);
+          }
           l0 += p0;  // the normalisation runs over ALL probabilities
           l1 += p1;
           if constexpr (DROP) {

@@ -31,6 +31,10 @@ namespace {
 using namespace tc;
 
 constexpr int HD = 32;
+#ifndef CSB_POLY_MOD
+#define CSB_POLY_MOD 2
+#endif
+constexpr int POLY_MOD = CSB_POLY_MOD;        // every POLY_MOD-th pair of exponentials on the FMA pipes (0: none)
 constexpr int TILE = 128;
 constexpr int ROW_BYTES = HD * 2;
 constexpr int TILE_BYTES = TILE * ROW_BYTES;  // 8 KB
@@ -286,13 +290,22 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         m_run = m_new;
         const float neg_m = -m_new * p.scale_log2;
+        const f2_t scale2 = f2_splat(p.scale_log2), negm2 = f2_splat(neg_m);
         float l0 = 0.f, l1 = 0.f;
         auto exp_chunk = [&](const uint32_t (&r)[32], int ch) {
           uint32_t pk[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
-            const float p0 = ex2(fmaf(__uint_as_float(r[2 * i]), p.scale_log2, neg_m));
-            const float p1 = ex2(fmaf(__uint_as_float(r[2 * i + 1]), p.scale_log2, neg_m));
+            const f2_t x2 = f2_fma(f2_make(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
+            float p0, p1;
+            if (POLY_MOD > 0 && i % POLY_MOD == POLY_MOD - 1) {  // FMA-pipe 2^x (tc_common.cuh)
+              ex2_poly_pair(x2, p0, p1);
+            } else {
+              float x0, x1;
+              f2_split(x2, x0, x1);
+              p0 = ex2(x0);
+              p1 = ex2(x1);
+            }
             l0 += p0;
             l1 += p1;
             pk[i] = pack_bf16x2(p0, p1);

@@ -29,17 +29,24 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
                "r"(bytes)
                : "memory");
 }
+// suspendTimeHint of try_wait: how long the thread may stay suspended inside ONE try_wait before it returns false
+// and the loop retries (it wakes as soon as the phase completes).  A warp that retries at the default, short limit
+// takes issue slots from the math warps of its scheduler (three of the 16 warps of the attention kernels are
+// waiting on barriers almost all the time).
+#ifndef CSB_MBAR_HINT_NS
+#define CSB_MBAR_HINT_NS 2000u
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n\t"
       ".reg .pred p;\n\t"
       "WAIT_%=:\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
       "@p bra DONE_%=;\n\t"
       "bra WAIT_%=;\n\t"
       "DONE_%=:\n\t"
       "}" ::"r"(smem_u32(bar)),
-      "r"(parity)
+      "r"(parity), "r"(CSB_MBAR_HINT_NS)
       : "memory");
 }
 
@@ -218,6 +225,27 @@ __device__ __forceinline__ float ex2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x for a PAIR of non-positive arguments on the FMA pipes (no MUFU): the softmax sweeps issue one ex2 per 128
+// tensor-core FLOPs at head dimension 32, and MUFU runs 16 lanes per clock per SM — a quarter of the tensor peak —
+// so part of the exponentials go through here instead.  Cody-Waite: x = n + f with n = round(x) (magic-number add),
+// 2^f on [-0.5, 0.5] by a cubic (max relative error 7.5e-5, 25x below the rounding of the bf16 probabilities),
+// 2^n by adding n to the exponent field.  ~10 issue slots per pair on packed fp32 (fma.rn.f32x2).
+__device__ __forceinline__ void ex2_poly_pair(f2_t x, float& p0, float& p1) {
+  float x0, x1;
+  f2_split(x, x0, x1);
+  x = f2_make(fmaxf(x0, -125.f), fmaxf(x1, -125.f));  // 2^-125 ~ 0; keeps the exponent arithmetic in range
+  const f2_t t = f2_add(x, f2_splat(12582912.f));     // 1.5 * 2^23: the low mantissa bits of t are round(x)
+  const f2_t f = f2_add(x, f2_fma(t, f2_splat(-1.f), f2_splat(12582912.f)));  // x - round(x)
+  f2_t p = f2_fma(f, f2_splat(0.05517164617776871f), f2_splat(0.2426111251115799f));
+  p = f2_fma(p, f, f2_splat(0.6932609677314758f));
+  p = f2_fma(p, f, f2_splat(0.9999280571937561f));
+  float t0, t1, q0, q1;
+  f2_split(t, t0, t1);
+  f2_split(p, q0, q1);
+  p0 = __int_as_float(__float_as_int(q0) + (__float_as_int(t0) << 23));
+  p1 = __int_as_float(__float_as_int(q1) + (__float_as_int(t1) << 23));
 }
 
 }  // namespace tc

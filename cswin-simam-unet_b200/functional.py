@@ -131,7 +131,7 @@ class _SimAMFn(torch.autograd.Function):
         x, (B, C, S, lay), fmt = _simam_plan(x, layout)
         y = torch.empty_like(x, memory_format=fmt)
         stats = torch.empty((B * C, 2), dtype=torch.float32, device=x.device)
-        with torch.cuda.device(x.device), _span("simam_fwd", 2 * x.numel() * x.element_size()):
+        with torch.cuda.device(x.device), _span("simam_fwd", 2 * x.numel() * x.element_size(), 0, f"B{B}xC{C}xS{S}"):
             ws, ws_bytes = _simam_workspace(x, B, C, S, lay)
             capi.check(capi.lib().csb200_simam_fwd_ws(_ptr(x), _ptr(y), _ptr(stats), B, C, S, lay,
                                                       capi.dtype_code(x), float(e_lambda), ws, ws_bytes,
@@ -150,7 +150,7 @@ class _SimAMFn(torch.autograd.Function):
         if gy.dtype != x.dtype:
             gy = gy.to(x.dtype)
         gx = torch.empty_like(x, memory_format=fmt)
-        with torch.cuda.device(x.device), _span("simam_bwd", 3 * x.numel() * x.element_size()):
+        with torch.cuda.device(x.device), _span("simam_bwd", 3 * x.numel() * x.element_size(), 0, f"B{B}xC{C}xS{S}"):
             ws, ws_bytes = _simam_workspace(x, B, C, S, lay)
             capi.check(capi.lib().csb200_simam_bwd_ws(_ptr(x), _ptr(gy), _ptr(stats), _ptr(gx), B, C, S, lay,
                                                       capi.dtype_code(x), e_lambda, ws, ws_bytes,
@@ -182,7 +182,7 @@ class _LayerNormFn(torch.autograd.Function):
         y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
         nbytes = x.numel() * (x.element_size() + y.element_size())
-        with torch.cuda.device(x.device), _span("layernorm_fwd", nbytes):
+        with torch.cuda.device(x.device), _span("layernorm_fwd", nbytes, 0, f"{rows}x{C}"):
             capi.check(capi.lib().csb200_layernorm_fwd(_ptr(x), _ptr(w), _ptr(b), _ptr(y), _ptr(stats), rows, C,
                                                        capi.dtype_code(x), capi.dtype_code(y), float(eps),
                                                        _vp(capi.stream_of(x))), "csb200_layernorm_fwd")
@@ -202,7 +202,7 @@ class _LayerNormFn(torch.autograd.Function):
         nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
         wsp = torch.empty(nws, dtype=torch.uint8, device=x.device)
         nbytes = x.numel() * (2 * x.element_size() + gy.element_size())
-        with torch.cuda.device(x.device), _span("layernorm_bwd", nbytes):
+        with torch.cuda.device(x.device), _span("layernorm_bwd", nbytes, 0, f"{rows}x{C}"):
             capi.check(lib.csb200_layernorm_bwd(_ptr(x), _ptr(gy), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb),
                                                 _ptr(wsp), nws, rows, C, capi.dtype_code(x), capi.dtype_code(gy),
                                                 _vp(capi.stream_of(x))), "csb200_layernorm_bwd")
@@ -230,7 +230,7 @@ class _AddLayerNormFn(torch.autograd.Function):
         y = torch.empty(x.shape, dtype=out_dtype, device=x.device)
         stats = torch.empty((rows, 2), dtype=torch.float32, device=x.device)
         nbytes = x.numel() * (3 * x.element_size() + y.element_size())
-        with torch.cuda.device(x.device), _span("layernorm_fwd", nbytes):
+        with torch.cuda.device(x.device), _span("layernorm_fwd", nbytes, 0, f"{rows}x{C}"):
             capi.check(capi.lib().csb200_add_layernorm_fwd(
                 _ptr(x), _ptr(r), _ptr(s), _ptr(w), _ptr(b), _ptr(y), _ptr(stats), rows, C, capi.dtype_code(x),
                 capi.dtype_code(y), float(eps), _vp(capi.stream_of(x))), "csb200_add_layernorm_fwd")
@@ -259,7 +259,7 @@ class _AddLayerNormFn(torch.autograd.Function):
         nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
         wsp = torch.empty(nws, dtype=torch.uint8, device=s.device)
         nbytes = s.numel() * ((2 + (gres is not None)) * s.element_size() + gy.element_size())
-        with torch.cuda.device(s.device), _span("layernorm_bwd", nbytes):
+        with torch.cuda.device(s.device), _span("layernorm_bwd", nbytes, 0, f"{rows}x{C}"):
             if want_rb:
                 capi.check(lib.csb200_add_layernorm_bwd_rb(
                     _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(grb),
@@ -325,7 +325,7 @@ def column_sum(x2d: torch.Tensor) -> torch.Tensor:
     out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
     nws = lib.csb200_colsum_workspace_bytes(cols)
     wsp = torch.empty(nws, dtype=torch.uint8, device=x2d.device)
-    with torch.cuda.device(x2d.device), _span("colsum", x2d.numel() * x2d.element_size()):
+    with torch.cuda.device(x2d.device), _span("colsum", x2d.numel() * x2d.element_size(), 0, f"{rows}x{cols}"):
         capi.check(lib.csb200_colsum(_ptr(x2d), _ptr(out), _ptr(wsp), nws, rows, cols, capi.dtype_code(x2d),
                                      _vp(capi.stream_of(x2d))), "csb200_colsum")
     return out
