@@ -51,10 +51,11 @@ def main():
         w = (torch.randn(N, K, device="cuda") / K ** 0.5).to(torch.bfloat16)
         b = torch.randn(N, device="cuda")
         bb = b.to(torch.bfloat16)
-        modes = [("bias", capi.EPI_BIAS)] + ([("gelu+h", capi.EPI_GELU_SAVE), ("gelu", capi.EPI_GELU)] if "fc1" in name else [])
+        modes = [("bias", capi.EPI_BIAS)] + ([("gelu+h", capi.EPI_GELU_SAVE), ("gelu+gelu'", capi.EPI_GELU_SAVE_DERIV),
+                                              ("gelu", capi.EPI_GELU)] if "fc1" in name else [])
         for label, epi in modes:
             us = timed(lambda i: csbF._tc_linear(xs[i], w, b, epi), nbuf)
-            outs = 2 if epi == capi.EPI_GELU_SAVE else 1
+            outs = 2 if epi in (capi.EPI_GELU_SAVE, capi.EPI_GELU_SAVE_DERIV) else 1
             if epi == capi.EPI_BIAS:
                 base = timed(lambda i: torch.nn.functional.linear(xs[i], w, bb), nbuf)
             else:
@@ -88,6 +89,12 @@ def main():
             base = timed(two_pass_bwd, nbuf)
             nbytes = 2 * (M * K + N * K + 2 * M * N)
             print(json.dumps({"shape": name, "M": M, "K": K, "N": N, "epilogue": "dgelu (backward)", "csb200_us": round(us, 2),
+                              "cublas_path_us": round(base, 2), "speedup": round(base / us, 3),
+                              "alg_gbs": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3),
+                              "tflops": round(2 * M * N * K / us / 1e6, 1)}), flush=True)
+            # the pair that saved GELU'(h) in forward: the backward epilogue is one multiplication
+            us = timed(lambda i: csbF._tc_dgelu(xs[i], w2, hs[i], deriv=True), nbuf)
+            print(json.dumps({"shape": name, "M": M, "K": K, "N": N, "epilogue": "dact (backward, saved GELU')", "csb200_us": round(us, 2),
                               "cublas_path_us": round(base, 2), "speedup": round(base / us, 3),
                               "alg_gbs": round(nbytes / us / 1e3, 1), "hbm_frac": round(nbytes / us / 1e3 / peaks["hbm_gbs"], 3),
                               "tflops": round(2 * M * N * K / us / 1e6, 1)}), flush=True)

@@ -50,9 +50,10 @@ EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_coun
            "csb200_stripe_attn_bwd_workspace_bytes", "csb200_stripe_attn_bwd", "csb200_cross_stripe_attn_fwd",
            "csb200_cross_stripe_attn_bwd", "csb200_adam_chunk_elems", "csb200_adam_step",
            "csb200_linear_supported", "csb200_linear_fwd", "csb200_linear_dgelu_supported",
-           "csb200_linear_dgelu_workspace_bytes", "csb200_linear_dgelu_bwd", "csb200_linear_wgrad_supported",
+           "csb200_linear_dgelu_workspace_bytes", "csb200_linear_dgelu_bwd", "csb200_linear_dact_bwd",
+           "csb200_linear_wgrad_supported",
            "csb200_linear_wgrad")
-EPI_BIAS, EPI_GELU, EPI_GELU_SAVE = 0, 1, 2
+EPI_BIAS, EPI_GELU, EPI_GELU_SAVE, EPI_GELU_SAVE_DERIV = 0, 1, 2, 3
 
 
 def lib() -> ctypes.CDLL:
@@ -123,6 +124,8 @@ def lib() -> ctypes.CDLL:
         L.csb200_linear_dgelu_workspace_bytes.restype = ctypes.c_size_t
         L.csb200_linear_dgelu_bwd.argtypes = [vp, vp, vp, vp, vp, vp, ctypes.c_size_t, i64, i64, i64, i64, ctypes.c_int, vp]
         L.csb200_linear_dgelu_bwd.restype = ctypes.c_int
+        L.csb200_linear_dact_bwd.argtypes = L.csb200_linear_dgelu_bwd.argtypes
+        L.csb200_linear_dact_bwd.restype = ctypes.c_int
         L.csb200_linear_wgrad_supported.argtypes = [i64, i64, i64, ctypes.c_int]
         L.csb200_linear_wgrad_supported.restype = ctypes.c_int
         L.csb200_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, ctypes.c_int, vp]

@@ -43,6 +43,20 @@ __device__ __forceinline__ uint32_t gelu_fwd2(uint32_t w) {
   f2_split(f2_fma(hx, g.erf, hx), lo, hi);
   return pack_bf16x2(lo, hi);
 }
+// GELU(x) and GELU'(x) = Phi(x) + x phi(x) of a packed bf16 pair in one go: the derivative costs three more packed
+// operations once erf and the Gaussian are there.  The fused Mlp (linear_tc.cu) stores GELU'(h) instead of h in
+// forward, so that its backward epilogue is one multiplication per element instead of a second erf + exponential.
+__device__ __forceinline__ uint32_t gelu_fwd_deriv2(uint32_t w, uint32_t& deriv) {
+  const f2_t x = f2_from_bf16x2(w);
+  const GeluPair g = erf_and_gauss2(x);
+  const f2_t hx = f2_mul(x, f2_splat(0.5f));
+  const f2_t cdf = f2_fma(g.erf, f2_splat(0.5f), f2_splat(0.5f));
+  float lo, hi;
+  f2_split(f2_fma(f2_mul(x, g.gauss), f2_splat(kInvSqrt2Pi), cdf), lo, hi);
+  deriv = pack_bf16x2(lo, hi);
+  f2_split(f2_fma(hx, g.erf, hx), lo, hi);
+  return pack_bf16x2(lo, hi);
+}
 __device__ __forceinline__ uint32_t gelu_bwd2(uint32_t wg, uint32_t wh) {
   const f2_t g = f2_from_bf16x2(wg), x = f2_from_bf16x2(wh);
   const GeluPair r = erf_and_gauss2(x);

@@ -59,7 +59,8 @@ struct LinMaps {
   CUtensorMap y, h;        // stores: box 32 columns x 32 rows, 64-byte swizzle (rows past M are clipped)
 };
 
-enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_GELU_SAVE = 2, EPI_DGELU = 3 };
+// EPI_GELU_SAVE_D / EPI_DMUL: the pair that stores GELU'(h) (bf16) in forward and multiplies by it in backward
+enum { EPI_BIAS = 0, EPI_GELU = 1, EPI_GELU_SAVE = 2, EPI_DGELU = 3, EPI_GELU_SAVE_D = 4, EPI_DMUL = 5 };
 
 // shared -> global tile store (bulk async group of the issuing thread)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src, int c0, int c1) {
@@ -100,6 +101,8 @@ struct Bars {
 template <int EPI>
 __global__ void __launch_bounds__(THREADS, 1)
     linear_tc_kernel(const __grid_constant__ LinMaps maps, const __grid_constant__ LinParams p) {
+  constexpr bool SAVE = EPI == EPI_GELU_SAVE || EPI == EPI_GELU_SAVE_D;  // forward: a second output tensor
+  constexpr bool DG = EPI == EPI_DGELU || EPI == EPI_DMUL;               // input-gradient form of the Mlp
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = smem_u32(smem_raw) + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* base_ptr = smem_raw + (base - smem_u32(smem_raw));
@@ -107,7 +110,7 @@ __global__ void __launch_bounds__(THREADS, 1)
   const uint32_t stg_off = p.w_bytes + p.stages * A_STAGE_BYTES;
   // 16 epilogue warps x stage_bufs output boxes, then (EPI_DGELU) 16 pre-activation boxes
   const uint32_t hstg_off = stg_off + (uint32_t)(4 * NUM_EPI_WG * p.stage_bufs * STG_BYTES);
-  const uint32_t misc_off = hstg_off + (EPI == EPI_DGELU ? 4 * NUM_EPI_WG * STG_BYTES : 0);
+  const uint32_t misc_off = hstg_off + (DG ? 4 * NUM_EPI_WG * STG_BYTES : 0);
   float* bias_sm = reinterpret_cast<float*>(base_ptr + misc_off);
   Bars& bar = *reinterpret_cast<Bars*>(base_ptr + misc_off + 256 * sizeof(float));
 
@@ -120,7 +123,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     prefetch_tensormap(&maps.a);
     prefetch_tensormap(&maps.w);
     prefetch_tensormap(&maps.y);
-    if (EPI == EPI_GELU_SAVE || EPI == EPI_DGELU) prefetch_tensormap(&maps.h);
+    if (SAVE || DG) prefetch_tensormap(&maps.h);
     mbar_init(&bar.w_full, 1);
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&bar.a_full[i], 1);
@@ -212,7 +215,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     const uint32_t hstg = base + hstg_off + (uint32_t)(warp - 4) * STG_BYTES;
     uint64_t* hbar = &bar.h_full[warp - 4];
     uint32_t hphase = 0;
-    if (EPI == EPI_DGELU && lane == 0 && buf < my_tiles && c_lo < c_hi) {
+    if (DG && lane == 0 && buf < my_tiles && c_lo < c_hi) {
       mbar_expect_tx(hbar, STG_BYTES);
       tma_load_2d(hstg, &maps.h, hbar, n0 + c_lo * 32, (m0 + buf * p.m_stride) * BM + ((warp & 3) << 5));
     }
@@ -227,7 +230,7 @@ __global__ void __launch_bounds__(THREADS, 1)
         uint4 hv[4];
         uint32_t r[32];
         tmem_ld32(lane_base + c * 32, r);
-        if (EPI == EPI_DGELU) {  // this row's 32 pre-activations out of the staged box, then prefetch the next box
+        if (DG) {  // this row's 32 pre-activations out of the staged box, then prefetch the next box
           mbar_wait(hbar, hphase);
           hphase ^= 1;
 #pragma unroll
@@ -247,12 +250,14 @@ __global__ void __launch_bounds__(THREADS, 1)
         }
         tmem_wait_ld();
         uint32_t outw[16], hw[16];
-        if (EPI == EPI_DGELU) {
+        if (DG) {
           const uint32_t* hwv = reinterpret_cast<const uint32_t*>(hv);
           float d[32];
 #pragma unroll
           for (int j2 = 0; j2 < 16; ++j2) {
-            const f2_t v = gelu_bwd2_f32(f2_make(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1])), hwv[j2]);
+            const f2_t g2 = f2_make(__uint_as_float(r[2 * j2]), __uint_as_float(r[2 * j2 + 1]));
+            // EPI_DMUL: the staged box holds GELU'(h) itself (forward saved it): one multiplication
+            const f2_t v = EPI == EPI_DMUL ? f2_mul(g2, f2_from_bf16x2(hwv[j2])) : gelu_bwd2_f32(g2, hwv[j2]);
             f2_split(v, d[2 * j2], d[2 * j2 + 1]);
             outw[j2] = pack_bf16x2(d[2 * j2], d[2 * j2 + 1]);
           }
@@ -283,17 +288,22 @@ __global__ void __launch_bounds__(THREADS, 1)
             } else {
               // GELU of the bf16-ROUNDED pre-activation: what nn.GELU sees after a bf16 Linear under autocast,
               // and exactly what the flat csb200_gelu_fwd pass computes from the stored h
-              hw[2 * q] = w0;
-              hw[2 * q + 1] = w1;
-              outw[2 * q] = gelu_fwd2(w0);
-              outw[2 * q + 1] = gelu_fwd2(w1);
+              if (EPI == EPI_GELU_SAVE_D) {  // second output: GELU'(h) instead of h
+                outw[2 * q] = gelu_fwd_deriv2(w0, hw[2 * q]);
+                outw[2 * q + 1] = gelu_fwd_deriv2(w1, hw[2 * q + 1]);
+              } else {
+                hw[2 * q] = w0;
+                hw[2 * q + 1] = w1;
+                outw[2 * q] = gelu_fwd2(w0);
+                outw[2 * q + 1] = gelu_fwd2(w1);
+              }
             }
           }
         }
         // registers -> staging (conflict-free: 8 rows cover the 32 banks) -> one TMA store per 32 x 32 box
 #pragma unroll
-        for (int v = 0; v < (EPI == EPI_GELU_SAVE ? 2 : 1); ++v) {
-          const uint32_t (&src)[16] = (v == 0 || EPI != EPI_GELU_SAVE) ? outw : hw;
+        for (int v = 0; v < (SAVE ? 2 : 1); ++v) {
+          const uint32_t (&src)[16] = (v == 0 || !SAVE) ? outw : hw;
           if (lane == 0) {
             if (p.stage_bufs == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
           }
@@ -316,7 +326,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       if (lane == 0) mbar_arrive(&bar.acc_empty[buf]);
     }
     if (lane == 0) bulk_wait_all();  // the staged boxes have been read AND written before the CTA retires
-    if (EPI == EPI_DGELU) {
+    if (DG) {
       // per-CTA column sums: 16 warps x 4 chunks x 32 lanes through the (now idle) staging area, added in a
       // fixed order; the per-CTA rows are summed by linear_colsum_final (deterministic)
       __syncwarp();
@@ -403,7 +413,7 @@ int launch_linear(int epilogue, bool w_mn, const void* x, const void* weight, co
   p.w_mn = w_mn ? 1 : 0;
   // two staging buffers per epilogue warp when that still leaves >= 4 ring stages
   const int misc = 256 * (int)sizeof(float) + (int)sizeof(Bars) + 1024 +
-                   (epilogue == EPI_DGELU ? 4 * NUM_EPI_WG * STG_BYTES : 0);
+                   (epilogue == EPI_DGELU || epilogue == EPI_DMUL ? 4 * NUM_EPI_WG * STG_BYTES : 0);
   p.stage_bufs = (SMEM_LIMIT - (int)p.w_bytes - misc - 2 * 4 * NUM_EPI_WG * STG_BYTES) / A_STAGE_BYTES >= 5 ? 2 : 1;
   const int fixed = (int)p.w_bytes + misc + p.stage_bufs * 4 * NUM_EPI_WG * STG_BYTES;
   p.stages = (SMEM_LIMIT - fixed) / A_STAGE_BYTES;
@@ -419,7 +429,7 @@ int launch_linear(int epilogue, bool w_mn, const void* x, const void* weight, co
   else rc = make_map_2d(&maps.w, weight, N, K, N, (int)K);  // box: 64 output columns x all K rows
   if (rc != CSB200_OK) return rc;
   if ((rc = make_map_2d(&maps.y, y, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK) return rc;
-  if ((epilogue == EPI_GELU_SAVE || epilogue == EPI_DGELU) &&
+  if ((epilogue == EPI_GELU_SAVE || epilogue == EPI_DGELU || epilogue == EPI_GELU_SAVE_D || epilogue == EPI_DMUL) &&
       (rc = make_map_2d(&maps.h, pre_act, N, M, N, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B)) != CSB200_OK)
     return rc;
   const int sms = device_sm_count();
@@ -431,15 +441,22 @@ int launch_linear(int epilogue, bool w_mn, const void* x, const void* weight, co
   if (partial_rows != nullptr) *partial_rows = per_n;
   const int grid = per_n * p.n_tiles;
   const int smem = fixed + p.stages * A_STAGE_BYTES;
-  const void* fn = epilogue == EPI_BIAS ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_BIAS>)
-                   : epilogue == EPI_GELU ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU>)
-                   : epilogue == EPI_GELU_SAVE ? reinterpret_cast<const void*>(&linear_tc_kernel<EPI_GELU_SAVE>)
-                                               : reinterpret_cast<const void*>(&linear_tc_kernel<EPI_DGELU>);
-  CSB200_CUDA(opt_in_smem(fn, SMEM_LIMIT));
-  if (epilogue == EPI_BIAS) linear_tc_kernel<EPI_BIAS><<<grid, THREADS, smem, st>>>(maps, p);
-  else if (epilogue == EPI_GELU) linear_tc_kernel<EPI_GELU><<<grid, THREADS, smem, st>>>(maps, p);
-  else if (epilogue == EPI_GELU_SAVE) linear_tc_kernel<EPI_GELU_SAVE><<<grid, THREADS, smem, st>>>(maps, p);
-  else linear_tc_kernel<EPI_DGELU><<<grid, THREADS, smem, st>>>(maps, p);
+#define CSB_LIN_LAUNCH(E)                                                                        \
+  case E:                                                                                         \
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&linear_tc_kernel<E>), SMEM_LIMIT));    \
+    linear_tc_kernel<E><<<grid, THREADS, smem, st>>>(maps, p);                                    \
+    break;
+  switch (epilogue) {
+    CSB_LIN_LAUNCH(EPI_BIAS)
+    CSB_LIN_LAUNCH(EPI_GELU)
+    CSB_LIN_LAUNCH(EPI_GELU_SAVE)
+    CSB_LIN_LAUNCH(EPI_DGELU)
+    CSB_LIN_LAUNCH(EPI_GELU_SAVE_D)
+    CSB_LIN_LAUNCH(EPI_DMUL)
+    default:
+      return fail(CSB200_ERR_INVALID, "csb200_linear: unknown epilogue %d", epilogue);
+  }
+#undef CSB_LIN_LAUNCH
   return check_launch("linear_tc_kernel");
 }
 
@@ -461,8 +478,10 @@ CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float*
   if (M == 0) return CSB200_OK;
   if (x == nullptr || weight == nullptr || y == nullptr)
     return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: null pointer");
-  if (epilogue < 0 || epilogue > 2 || (epilogue == EPI_GELU_SAVE && pre_act == nullptr))
+  // public codes: 0 bias, 1 GELU, 2 GELU + pre-activation h, 3 GELU + GELU'(h) (CSB200_EPI_GELU_SAVE_DERIV)
+  if (epilogue < 0 || epilogue > 3 || (epilogue >= 2 && pre_act == nullptr))
     return fail(CSB200_ERR_INVALID, "csb200_linear_fwd: bad epilogue %d", epilogue);
+  if (epilogue == 3) epilogue = EPI_GELU_SAVE_D;
   if (!shape_ok(M, N, K, dtype, 32))
     return fail(CSB200_ERR_UNSUPPORTED, "csb200_linear_fwd: bf16 with K in {64,128,256} and N a multiple of 32 only "
                 "(M %lld, N %lld, K %lld)", (long long)M, (long long)N, (long long)K);
@@ -481,9 +500,9 @@ CSB200_API size_t csb200_linear_dgelu_workspace_bytes(int64_t N) {
   return (size_t)MAX_PARTIAL_ROWS * (size_t)N * sizeof(float) + 256;
 }
 
-CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
-                                       float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
-                                       int64_t N, int64_t K, int64_t ldg, int dtype, void* stream) {
+static int linear_dact_impl(int epi, const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
+                            float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M, int64_t N,
+                            int64_t K, int64_t ldg, int dtype, void* stream) {
   if (M == 0) return CSB200_OK;
   if (grad_y == nullptr || weight == nullptr || pre_act == nullptr || grad_h == nullptr || grad_bias == nullptr ||
       workspace == nullptr)
@@ -500,12 +519,26 @@ CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partial = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(workspace) + 255) & ~uintptr_t(255));
   int rows = 0;
-  int rc = launch_linear(EPI_DGELU, true, grad_y, weight, nullptr, grad_h, const_cast<void*>(pre_act), partial, &rows,
+  int rc = launch_linear(epi, true, grad_y, weight, nullptr, grad_h, const_cast<void*>(pre_act), partial, &rows,
                          M, N, K, ldg, st);
   if (rc != CSB200_OK) return rc;
   if (rows > MAX_PARTIAL_ROWS) return fail(CSB200_ERR_WORKSPACE, "csb200_linear_dgelu_bwd: %d partial rows", rows);
   linear_colsum_final<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(partial, rows, (int)N, grad_bias);
   return check_launch("linear_colsum_final");
+}
+
+CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
+                                       float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
+                                       int64_t N, int64_t K, int64_t ldg, int dtype, void* stream) {
+  return linear_dact_impl(EPI_DGELU, grad_y, weight, pre_act, grad_h, grad_bias, workspace, workspace_bytes, M, N, K,
+                          ldg, dtype, stream);
+}
+
+CSB200_API int csb200_linear_dact_bwd(const void* grad_y, const void* weight, const void* act_deriv, void* grad_h,
+                                      float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
+                                      int64_t N, int64_t K, int64_t ldg, int dtype, void* stream) {
+  return linear_dact_impl(EPI_DMUL, grad_y, weight, act_deriv, grad_h, grad_bias, workspace, workspace_bytes, M, N, K,
+                          ldg, dtype, stream);
 }
 
 }  // extern "C"

@@ -510,7 +510,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
           // x = s * scale * log2(e) - max, as a packed pair; every POLY_MOD-th pair takes the FMA-pipe 2^x
           const f2_t x2 = f2_fma(f2_make(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
           float p0, p1;
-          if (POLY_MOD > 0 && i % POLY_MOD == POLY_MOD - 1) {
+          if (POLY_MOD > 0 && i % (POLY_MOD > 0 ? POLY_MOD : 1) == POLY_MOD - 1) {
             ex2_poly_pair(x2, p0, p1);
           } else {
             float x0, x1;

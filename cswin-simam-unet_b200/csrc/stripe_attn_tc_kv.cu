@@ -298,7 +298,7 @@ __global__ void __launch_bounds__(THREADS, 1)
           for (int i = 0; i < 16; ++i) {
             const f2_t x2 = f2_fma(f2_make(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
             float p0, p1;
-            if (POLY_MOD > 0 && i % POLY_MOD == POLY_MOD - 1) {  // FMA-pipe 2^x (tc_common.cuh)
+            if (POLY_MOD > 0 && i % (POLY_MOD > 0 ? POLY_MOD : 1) == POLY_MOD - 1) {  // FMA-pipe 2^x (tc_common.cuh)
               ex2_poly_pair(x2, p0, p1);
             } else {
               float x0, x1;

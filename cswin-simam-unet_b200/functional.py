@@ -401,7 +401,8 @@ def _tc_linear(x2: torch.Tensor, wc: torch.Tensor, bias: Optional[torch.Tensor],
     M, K = x2.shape
     N = wc.shape[0]
     y = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device)
-    h = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device) if epilogue == capi.EPI_GELU_SAVE else None
+    saves = epilogue in (capi.EPI_GELU_SAVE, capi.EPI_GELU_SAVE_DERIV)  # second output: h, or GELU'(h)
+    h = torch.empty((M, N), dtype=torch.bfloat16, device=x2.device) if saves else None
     b32 = None if bias is None else bias.detach().float().contiguous()
     nbytes = 2 * (M * K + N * K + M * N * (2 if h is not None else 1))
     with torch.cuda.device(x2.device), _span("linear_tc", nbytes, 2 * M * N * K, f"M{M}xN{N}xK{K}e{epilogue}"):
@@ -577,8 +578,10 @@ class _LinearGeluFn(torch.autograd.Function):
         return gx, gw, (gb.to(b_dtype) if ctx.needs_input_grad[2] else None), None
 
 
-def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor):
-    """(grad_h, grad_bias) = csb200_linear_dgelu_bwd: grad_h = (g W2) * GELU'(h) in one tcgen05 GEMM."""
+def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor, deriv: bool = False):
+    """(grad_h, grad_bias) = csb200_linear_dgelu_bwd: grad_h = (g W2) * GELU'(h) in one tcgen05 GEMM.
+    ``deriv``: ``h2`` already holds GELU'(h) (forward epilogue EPI_GELU_SAVE_DERIV) -> csb200_linear_dact_bwd,
+    whose epilogue is one multiplication per element."""
     M, K = g2.shape
     N = w2c.shape[1]
     lib = capi.lib()
@@ -587,16 +590,22 @@ def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor):
     nws = lib.csb200_linear_dgelu_workspace_bytes(N)
     wsp = torch.empty(nws, dtype=torch.uint8, device=g2.device)
     nbytes = 2 * (M * K + N * K + 2 * M * N)
-    with torch.cuda.device(g2.device), _span("linear_tc", nbytes, 2 * M * N * K, f"M{M}xN{N}xK{K}dgelu"):
-        capi.check(lib.csb200_linear_dgelu_bwd(_ptr(g2), _ptr(w2c), _ptr(h2), _ptr(dh), _ptr(gb), _ptr(wsp), nws, M, N, K,
-                                               g2.stride(0), capi.BF16, _vp(capi.stream_of(g2))),
-                   "csb200_linear_dgelu_bwd")
+    fn = lib.csb200_linear_dact_bwd if deriv else lib.csb200_linear_dgelu_bwd
+    with torch.cuda.device(g2.device), _span("linear_tc", nbytes, 2 * M * N * K,
+                                             f"M{M}xN{N}xK{K}{'dact' if deriv else 'dgelu'}"):
+        capi.check(fn(_ptr(g2), _ptr(w2c), _ptr(h2), _ptr(dh), _ptr(gb), _ptr(wsp), nws, M, N, K,
+                      g2.stride(0), capi.BF16, _vp(capi.stream_of(g2))),
+                   "csb200_linear_dact_bwd" if deriv else "csb200_linear_dgelu_bwd")
     return dh, gb
+
+
+# fused Mlp: save GELU'(h) in forward (True) or h (False: the backward epilogue re-evaluates erf and exp)
+MLP_SAVE_DERIV = True
 
 
 class _MlpFn(torch.autograd.Function):
     """y = fc2(GELU(fc1(x))) — Mlp.forward, C:188-196 (dropout 0) — with the activation inside the GEMMs that
-    surround it: forward = tcgen05 fc1 whose epilogue stores h and GELU(h), then fc2 on cuBLAS; backward =
+    surround it: forward = tcgen05 fc1 whose epilogue stores GELU(h) and GELU'(h), then fc2 on cuBLAS; backward =
     ONE tcgen05 GEMM for grad_h = (grad_y W2) * GELU'(h) that also emits the fc1 bias gradient, then the
     weight gradients and the fc1 input gradient on cuBLAS.  Neither flat GELU pass runs."""
 
@@ -606,9 +615,11 @@ class _MlpFn(torch.autograd.Function):
         xc = x if x.dtype == torch.bfloat16 else x.to(torch.bfloat16)
         w1c, w2c = cast_param(w1, torch.bfloat16), cast_param(w2, torch.bfloat16)
         x2 = xc.reshape(-1, xc.shape[-1])
-        a, h = _tc_linear(x2, w1c, b1, capi.EPI_GELU_SAVE)
+        # the second output is GELU'(h), not h: backward multiplies instead of evaluating erf + exp again
+        a, h = _tc_linear(x2, w1c, b1, capi.EPI_GELU_SAVE_DERIV if MLP_SAVE_DERIV else capi.EPI_GELU_SAVE)
         y = torch.nn.functional.linear(a, w2c, cast_param(b2, torch.bfloat16))
         ctx.save_for_backward(x2, w1c, w2c, h, a)
+        ctx.deriv = MLP_SAVE_DERIV
         ctx.meta = (x.dtype, x.shape, w1.dtype, b1.dtype, w2.dtype, None if b2 is None else b2.dtype)
         return y.view(*x.shape[:-1], w2c.shape[0])
 
@@ -620,7 +631,7 @@ class _MlpFn(torch.autograd.Function):
         g2 = gy.reshape(-1, w2c.shape[0])
         if g2.dtype != torch.bfloat16 or not g2.is_contiguous():
             g2 = g2.to(torch.bfloat16).contiguous()
-        dh, gb1 = _tc_dgelu(g2, w2c, h)
+        dh, gb1 = _tc_dgelu(g2, w2c, h, ctx.deriv)
         gx = gw1 = gw2 = gb2 = None
         if ctx.needs_input_grad[0]:
             gx = torch.mm(dh, w1c).view(x_shape).to(x_dtype)

@@ -167,11 +167,14 @@ CSB200_API int csb200_gelu_bwd(const void* grad_out, const void* h, void* grad_h
  * epilogue: CSB200_EPI_BIAS       y = x W^T + b
  *           CSB200_EPI_GELU       y = GELU(bf16(x W^T + b))   exact erf form, nn.GELU()
  *           CSB200_EPI_GELU_SAVE  as above and pre_act = bf16(x W^T + b)  (what GELU' needs in backward)
+ *           CSB200_EPI_GELU_SAVE_DERIV  as CSB200_EPI_GELU and pre_act = bf16(GELU'(bf16(x W^T + b))): the
+ *                                 derivative itself, for csb200_linear_dact_bwd
  * Supported (csb200_linear_supported): bf16, K in {64, 128, 256}, N a multiple of 32.
  * ---------------------------------------------------------------------------------------------- */
 #define CSB200_EPI_BIAS 0
 #define CSB200_EPI_GELU 1
 #define CSB200_EPI_GELU_SAVE 2
+#define CSB200_EPI_GELU_SAVE_DERIV 3
 CSB200_API int csb200_linear_supported(int64_t M, int64_t N, int64_t K, int dtype);
 CSB200_API int csb200_linear_fwd(const void* x, const void* weight, const float* bias, void* y, void* pre_act,
                                  int64_t M, int64_t N, int64_t K, int64_t ldx, int dtype, int epilogue,
@@ -188,6 +191,14 @@ CSB200_API size_t csb200_linear_dgelu_workspace_bytes(int64_t N);
 CSB200_API int csb200_linear_dgelu_bwd(const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
                                        float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
                                        int64_t N, int64_t K, int64_t ldg, int dtype, void* stream);
+/* The same input-gradient GEMM for a forward pass that saved the activation's DERIVATIVE instead of the
+ * pre-activation (csb200_linear_fwd with CSB200_EPI_GELU_SAVE_DERIV writes GELU'(h), bf16, into `pre_act`):
+ *     grad_h = (grad_y W2) * act_deriv,   grad_bias[n] = sum_m grad_h[m][n]
+ * The epilogue is one multiplication per element instead of a second erf + exponential (C:190 backward), which
+ * is what bounds csb200_linear_dgelu_bwd.  Same shapes, workspace and alignment rules. */
+CSB200_API int csb200_linear_dact_bwd(const void* grad_y, const void* weight, const void* act_deriv, void* grad_h,
+                                      float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
+                                      int64_t N, int64_t K, int64_t ldg, int dtype, void* stream);
 
 /* Parameter gradients of a token-path nn.Linear (backward of C:357-358, C:366, C:188-196 w.r.t. weight / bias):
  *     grad_w[N][K] = grad_y[M][N]^T x[M][K],      grad_bias[n] = sum_m grad_y[m][n]   (nullable)

@@ -74,8 +74,8 @@ def test_strided_rows_no_bias_and_rejections():
 
 
 def test_mlp_through_the_fused_path_matches_the_two_pass_path():
-    """Mlp.forward (C:188-196) under bf16 autocast: tcgen05 fc1 + GELU vs cuBLAS fc1 + flat GELU pass —
-    same h is saved, so the gradients are computed by the same backward kernels."""
+    """Mlp.forward (C:188-196) under bf16 autocast: tcgen05 fc1 + GELU (saving GELU'(h)) vs cuBLAS fc1 + flat GELU
+    pass (saving h): outputs and gradients agree to bf16 rounding."""
     torch.manual_seed(0)
     mlp = pkg.modules.Mlp(128, 512).cuda()
     x = torch.randn(4, 1024, 128, device="cuda").to(torch.bfloat16)
@@ -123,6 +123,32 @@ def test_dgelu_backward_gemm_matches_fp32_reference(shape):
     capi.check(lib.csb200_gelu_bwd(csbF._ptr(da), csbF._ptr(h), csbF._ptr(flat), csbF._ptr(gb2), csbF._ptr(wsp), nws, M, N,
                                    capi.BF16, csbF._vp(capi.stream_of(h))), "csb200_gelu_bwd")
     assert rel_err(dh.float(), ref) <= rel_err(flat.float(), ref) + 2 ** -10
+
+
+@pytest.mark.parametrize("shape", [(4096, 64, 256), (2048, 128, 512), (1024, 256, 1024), (1000, 64, 128),
+                                   (300 * 128 + 5, 64, 256)])
+def test_saved_derivative_pair_matches_fp32_reference(shape):
+    """csb200_linear_fwd with CSB200_EPI_GELU_SAVE_DERIV stores GELU'(h) (exact-erf form, C:190) instead of h, and
+    csb200_linear_dact_bwd multiplies by it: same GELU output as the h-saving epilogue bit for bit, derivative and
+    input gradient against fp32 torch autograd, and against the erf-recomputing csb200_linear_dgelu_bwd."""
+    M, K, N = shape
+    x, w, b = _operands(M, K, N, M + 5 * N)
+    a, d = csbF._tc_linear(x, w, b, capi.EPI_GELU_SAVE_DERIV)
+    a_ref, h = csbF._tc_linear(x, w, b, capi.EPI_GELU_SAVE)
+    assert torch.equal(a, a_ref)
+    hf = h.float().requires_grad_(True)
+    torch.nn.functional.gelu(hf).sum().backward()
+    assert (d.float() - hf.grad).abs().max() < 2 ** -7      # |GELU'| <= 1.13: one bf16 rounding (half an ulp of [1, 2) is 2^-8)
+    g = torch.Generator().manual_seed(N)
+    gy = torch.randn((M, K), generator=g).to(torch.bfloat16).cuda()
+    w2 = (torch.randn((K, N), generator=g) / K ** 0.5).to(torch.bfloat16).cuda()
+    dh, gb = csbF._tc_dgelu(gy, w2, d, deriv=True)
+    ref = (gy.float() @ w2.float()) * hf.grad
+    assert rel_err(dh.float(), ref) < 2 ** -7                # bf16 derivative x bf16 output rounding
+    # column sums of thousands of signed terms, each carrying the 2^-9 rounding of the stored derivative
+    assert rel_err(gb, ref.sum(0)) < 5e-3
+    dh2, gb2 = csbF._tc_dgelu(gy, w2, h)
+    assert rel_err(dh.float(), dh2.float()) < 2 ** -7 and rel_err(gb, gb2) < 5e-3
 
 
 # (M, N, K): the four Linear layers of a CSWinBlock at the config-3 widths (stage 1-4 geometry, token counts
