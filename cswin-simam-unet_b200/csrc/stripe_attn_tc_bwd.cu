@@ -97,8 +97,8 @@ struct BSmem {
   alignas(1024) uint8_t v[GS][OP_BYTES];
   alignas(1024) uint8_t go[GS][OP_BYTES];
   alignas(1024) uint8_t ds[2][2 * DS_BLOCK_BYTES];  // dS^T of one 128-query block, two 64-blocks
-  alignas(16) float lse2[GS][NK];                   // lse * log2(e)
-  alignas(16) float delta[GS][NK];
+  alignas(16) float lse2[GS][NK];                   // -lse * log2(e)
+  alignas(16) float delta[GS][NK];                  // -scale * delta
   alignas(16) float lepe[GS][9 * HD];               // [tap][c]
   alignas(16) int4 coord[GS];                       // image, first token of the stripe, head
   alignas(8) uint64_t grp_full[GS], grp_empty[GS];
@@ -224,8 +224,10 @@ __global__ void __launch_bounds__(THREADS, 1)
       }
 #pragma unroll
       for (int j = 0; j < PER_LANE; ++j) {
-        sm.lse2[gs][lane + 32 * j] = r_lse[j] * 1.4426950408889634f;
-        sm.delta[gs][lane + 32 * j] = r_delta[j];
+        // stored NEGATED and pre-scaled, so that the convert warps form  x = s * scale * log2(e) - lse * log2(e)  and
+        // scale * (dP - delta)  as one packed FMA each
+        sm.lse2[gs][lane + 32 * j] = r_lse[j] * -1.4426950408889634f;
+        sm.delta[gs][lane + 32 * j] = r_delta[j] * -p.scale;
       }
 #pragma unroll
       for (int j = 0; j < 9; ++j) sm.lepe[gs][lane + 32 * j] = r_tap[j];
@@ -353,6 +355,7 @@ __global__ void __launch_bounds__(THREADS, 1)
       uint8_t* ds_row = sm.ds[dsb] + (qh & 1) * DS_BLOCK_BYTES + j * 128;
       const float* lse2 = sm.lse2[gs] + qh * HALF;
       const float* dlt = sm.delta[gs] + qh * HALF;
+      const f2_t sl2 = f2_splat(p.scale_log2), sc2 = f2_splat(p.scale);
 #pragma unroll
       for (int c = 0; c < 2; ++c) {  // 32 query columns at a time
         uint32_t rs[32], rd[32];
@@ -362,31 +365,40 @@ __global__ void __launch_bounds__(THREADS, 1)
         uint32_t pp[16], pd[16];
 #pragma unroll
         for (int e4 = 0; e4 < 8; ++e4) {
-          const float4 l4 = *reinterpret_cast<const float4*>(lse2 + 32 * c + 4 * e4);  // broadcast
-          const float4 d4 = *reinterpret_cast<const float4*>(dlt + 32 * c + 4 * e4);
-          const float p0 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 0]), p.scale_log2, -l4.x));
-          const float p1 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 1]), p.scale_log2, -l4.y));
-          const float p2 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 2]), p.scale_log2, -l4.z));
-          const float p3 = ex2(fmaf(__uint_as_float(rs[4 * e4 + 3]), p.scale_log2, -l4.w));
+          // four queries at a time, as two packed fp32 pairs (the warps are bound by instruction issue):
+          // P = 2^(s scale log2e - lse log2e),  dS = P * (scale dP - scale delta)
+          const ulonglong2 l4 = *reinterpret_cast<const ulonglong2*>(lse2 + 32 * c + 4 * e4);  // broadcast: -lse log2e
+          const ulonglong2 d4 = *reinterpret_cast<const ulonglong2*>(dlt + 32 * c + 4 * e4);   // -scale delta
+          const f2_t xa = f2_fma(f2_make(__uint_as_float(rs[4 * e4 + 0]), __uint_as_float(rs[4 * e4 + 1])), sl2, l4.x);
+          const f2_t xb = f2_fma(f2_make(__uint_as_float(rs[4 * e4 + 2]), __uint_as_float(rs[4 * e4 + 3])), sl2, l4.y);
+          float x0, x1, x2, x3;
+          f2_split(xa, x0, x1);
+          f2_split(xb, x2, x3);
+          const float p0 = ex2(x0), p1 = ex2(x1), p2 = ex2(x2), p3 = ex2(x3);
           if constexpr (DROP) {
             // dropped P (the A operand of dV) = keep / (1 - p) * P, and dP reaches P through the same factor
             const uint32_t kb = (c == 0 ? mw.x : mw.y) >> (4 * e4);
             const float k0 = kb & 1u ? p.keep_scale : 0.f, k1 = kb & 2u ? p.keep_scale : 0.f;
             const float k2 = kb & 4u ? p.keep_scale : 0.f, k3 = kb & 8u ? p.keep_scale : 0.f;
-            const float s0 = p0 * p.scale * (__uint_as_float(rd[4 * e4 + 0]) * k0 - d4.x);
-            const float s1 = p1 * p.scale * (__uint_as_float(rd[4 * e4 + 1]) * k1 - d4.y);
-            const float s2 = p2 * p.scale * (__uint_as_float(rd[4 * e4 + 2]) * k2 - d4.z);
-            const float s3 = p3 * p.scale * (__uint_as_float(rd[4 * e4 + 3]) * k3 - d4.w);
+            const f2_t ka = f2_make(k0, k1), kb2 = f2_make(k2, k3);
+            const f2_t da = f2_mul(f2_make(__uint_as_float(rd[4 * e4 + 0]), __uint_as_float(rd[4 * e4 + 1])), ka);
+            const f2_t db = f2_mul(f2_make(__uint_as_float(rd[4 * e4 + 2]), __uint_as_float(rd[4 * e4 + 3])), kb2);
+            float s0, s1, s2, s3;
+            f2_split(f2_mul(f2_make(p0, p1), f2_fma(da, sc2, d4.x)), s0, s1);
+            f2_split(f2_mul(f2_make(p2, p3), f2_fma(db, sc2, d4.y)), s2, s3);
             pp[2 * e4] = pack_bf16x2(p0 * k0, p1 * k1);
             pp[2 * e4 + 1] = pack_bf16x2(p2 * k2, p3 * k3);
             pd[2 * e4] = pack_bf16x2(s0, s1);
             pd[2 * e4 + 1] = pack_bf16x2(s2, s3);
             continue;
           }
-          const float s0 = p0 * p.scale * (__uint_as_float(rd[4 * e4 + 0]) - d4.x);
-          const float s1 = p1 * p.scale * (__uint_as_float(rd[4 * e4 + 1]) - d4.y);
-          const float s2 = p2 * p.scale * (__uint_as_float(rd[4 * e4 + 2]) - d4.z);
-          const float s3 = p3 * p.scale * (__uint_as_float(rd[4 * e4 + 3]) - d4.w);
+          float s0, s1, s2, s3;
+          f2_split(f2_mul(f2_make(p0, p1),
+                          f2_fma(f2_make(__uint_as_float(rd[4 * e4 + 0]), __uint_as_float(rd[4 * e4 + 1])), sc2, d4.x)),
+                   s0, s1);
+          f2_split(f2_mul(f2_make(p2, p3),
+                          f2_fma(f2_make(__uint_as_float(rd[4 * e4 + 2]), __uint_as_float(rd[4 * e4 + 3])), sc2, d4.y)),
+                   s2, s3);
           pp[2 * e4] = pack_bf16x2(p0, p1);
           pp[2 * e4 + 1] = pack_bf16x2(p2, p3);
           pd[2 * e4] = pack_bf16x2(s0, s1);
