@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """One profiled call of each hot kernel, bracketed by cudaProfilerStart/Stop, for
     ncu --set full --import-source on --clock-control none --profile-from-start off -o <rep> \\
-        python benchmarks/ncu_targets.py attn s3        # or: simam nchw | simam nlc | gelu | layernorm | carafe up3 | carafe x4
+        python benchmarks/ncu_targets.py attn s3        # or: simam nchw | simam nlc | gelu | layernorm | carafe up3 | carafe x4 | linear s3 | attn_long
 Shapes are BASELINE config 3 (512^2, batch 32, bf16) call sites; config 2 for SimAM NCHW."""
 import os
 import sys
@@ -81,9 +81,18 @@ elif what == "linear":
     g3 = torch.randn(M, 3 * C, device="cuda").bfloat16()
 
     def f():
-        a, h = csbF._tc_linear(x, w1, b1, capi.EPI_GELU_SAVE)
-        csbF._tc_dgelu(x, w2, h)
+        a, d = csbF._tc_linear(x, w1, b1, capi.EPI_GELU_SAVE_DERIV)   # what _MlpFn runs: GELU and GELU'(h)
+        csbF._tc_dgelu(x, w2, d, deriv=True)
         csbF._tc_linear(x, wq, bq, capi.EPI_BIAS)
         csbF._tc_wgrad(g3, x, True)
+    profiled(f)
+elif what == "attn_long":
+    # BASELINE config 5, split 8, stage 1: N = 2048 -> the key/value-tiled forward kernel (stripe_fwd_tc_kv)
+    blk = pkg.CSWinBlock(dim=64, reso=256, num_heads=2, split_size=8).cuda()
+    q = torch.randn(8, 256 * 256, 192, device="cuda").bfloat16()
+
+    def f():
+        with torch.no_grad():
+            blk.attend(q)
     profiled(f)
 print("done", what, arg)
