@@ -185,7 +185,7 @@ def bench_attn_long(engine):
     and the 32 x 32 full window of the last stage (stripe_fwd_tc_kv), plus split 2 stage 1."""
     # (name, reso, split, heads, C, last_stage)
     stages = [("sw8_s1", 256, 8, 2, 64, False), ("sw8_s2", 128, 8, 4, 128, False), ("sw8_s3", 64, 8, 8, 256, False),
-              ("s4_full", 32, 32, 16, 512, True), ("sw2_s1", 256, 2, 2, 64, False)]
+              ("s4_full", 32, 32, 16, 512, True), ("sw2_s1", 256, 2, 2, 64, False), ("sw1_s3", 64, 1, 8, 256, False)]
     B, dtype = 8, torch.bfloat16
     for name, reso, split, heads, C, last in stages:
         blk = pkg.CSWinBlock(dim=C, reso=reso, num_heads=heads, split_size=split, last_stage=last).cuda()

@@ -132,7 +132,8 @@ struct FwdBranch {
 struct FwdParams {
   int B, W, L;
   int g0, gpi;         // groups per image of branch 0 / of both branches
-  int groups;          // B * gpi
+  int groups;          // B * gpi (pair mode: the number of TILES, two groups each)
+  int real_groups;     // B * gpi
   float scale_log2;    // scale * log2(e)
   float scale;
   uint32_t drop_thr;   // attention dropout (stripe_attn.cuh); 0 in the <.., false> instantiation
@@ -172,8 +173,9 @@ struct Smem {
   alignas(1024) uint8_t q[QS][TILE_BYTES];
   alignas(1024) uint8_t k[KS][KV_BYTES];
   alignas(1024) uint8_t v[VS][KV_BYTES];
-  alignas(16) float lepe[VS][LEPE_FLOATS];   // [tap][c] then bias[c]
-  alignas(16) int4 coord[VS];                // (image, first token of the stripe, head, branch) per V stage
+  // [half][tap][c] then bias[c]; half 1 only in the pair mode (two 64-token stripes per tile)
+  alignas(16) float lepe[VS][2][LEPE_FLOATS];
+  alignas(16) int4 coord[VS][2];             // (image, first token of the stripe, head, branch) per V stage (and half)
   alignas(8) uint64_t q_full[QS], q_empty[QS];
   uint64_t k_full[KS], k_empty[KS], v_full[VS], v_empty[VS];
   uint64_t s_full[NWG], p_full[NWG], o_full[NWG], buf_empty[NWG];
@@ -214,9 +216,15 @@ __device__ __forceinline__ void setmaxnreg() {  // A = 1: grow to B registers pe
   else asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(B));
 }
 
-template <int NK, bool DROP>
+// PAIR (NK = 128 only): stripes of 64 tokens, TWO (stripe, head) groups per 128-row tile — rows / keys 0..63 are
+// group 2P, 64..127 group 2P + 1 (any two groups: coordinates, taps and tensor maps are per half).  S = Q K^T is
+// computed for the whole tile and only its two diagonal 64 x 64 blocks are used: a row's softmax runs over the
+// two 32-column chunks of its own half, the other half of its P row is written as zeros, so O = P V needs no
+// change.  (BASELINE config 5, 1024^2 at stripe width 1: stage 3 has N = 64.)
+template <int NK, bool DROP, bool PAIR = false>
 __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
     stripe_fwd_tc(const __grid_constant__ FwdMaps maps, const __grid_constant__ FwdParams p) {
+  static_assert(!PAIR || (NK == TILE && !DROP), "pair mode: one 128-row tile, no dropout");
   constexpr int T = NK / TILE;          // query tiles per group
   constexpr int NBOX = NK / TILE;       // TMA boxes per K (or V) load
   constexpr int NWG = Cfg<NK>::NWG, KS = Cfg<NK>::KS, VS = Cfg<NK>::VS, QS = Cfg<NK>::QS;
@@ -293,10 +301,32 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       for (int j = 0; j < TAPS_PER_LANE; ++j)  // element lane + 32 j: tap j (HD == 32), channel = lane
         taps[j] = j < 9 ? __ldg(b2.lepe_w + (gc.head * HD + lane) * 9 + j) : __ldg(b2.lepe_b + gc.head * HD + lane);
     };
-    if (my_groups > 0) fetch_taps(decode_group(p, (int)blockIdx.x));
+    // pair mode: tile index P holds groups 2P and 2P + 1 (the last tile of an odd count holds its group twice:
+    // both halves then compute and store the same values)
+    auto half_group = [&](int tile, int h) {
+      const int g = 2 * tile + h;
+      return decode_group(p, g < p.real_groups ? g : p.real_groups - 1);
+    };
+    float taps1[PAIR ? TAPS_PER_LANE : 1];
+    auto fetch_taps1 = [&](const GroupCoord& gc) {
+      const FwdBranch& b2 = p.br[gc.br];
+#pragma unroll
+      for (int j = 0; j < (PAIR ? TAPS_PER_LANE : 1); ++j)
+        taps1[j] = j < 9 ? __ldg(b2.lepe_w + (gc.head * HD + lane) * 9 + j) : __ldg(b2.lepe_b + gc.head * HD + lane);
+    };
+    if (my_groups > 0) {
+      if constexpr (PAIR) {
+        fetch_taps(half_group((int)blockIdx.x, 0));
+        fetch_taps1(half_group((int)blockIdx.x, 1));
+      } else {
+        fetch_taps(decode_group(p, (int)blockIdx.x));
+      }
+    }
     int it = 0;
     for (int gi = 0; gi < my_groups; ++gi) {
-      const GroupCoord c = decode_group(p, (int)blockIdx.x + gi * (int)gridDim.x);
+      const int tile = (int)blockIdx.x + gi * (int)gridDim.x;
+      const GroupCoord c = PAIR ? half_group(tile, 0) : decode_group(p, tile);
+      const GroupCoord c1 = PAIR ? half_group(tile, 1) : c;
       const FwdBranch& bg = p.br[c.br];
       const int ks = gi % KS, vs = gi % VS;
       mbar_wait(&sm.k_empty[ks], ((gi / KS) & 1) ^ 1);
@@ -304,6 +334,21 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       if (lane == 0) {
         mbar_expect_tx(&sm.k_full[ks], Smem<NK>::KV_BYTES);
         mbar_expect_tx(&sm.v_full[vs], Smem<NK>::KV_BYTES);
+        if constexpr (PAIR) {
+          const int qs = it % QS;
+          mbar_wait(&sm.q_empty[qs], ((it / QS) & 1) ^ 1);
+          mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {  // 64-row boxes: the whole stripe of each half
+            const GroupCoord& ch = h ? c1 : c;
+            const FwdBranch& bh = p.br[ch.br];
+            const int x0 = ch.wx * bh.ws, y0 = ch.wy * bh.hs, off = h * (TILE_BYTES / 2);
+            tma_load_4d(sm.k[ks] + off, &maps.k[ch.br], &sm.k_full[ks], ch.head * HD, x0, y0, ch.b);
+            tma_load_4d(sm.v[vs] + off, &maps.v[ch.br], &sm.v_full[vs], ch.head * HD, x0, y0, ch.b);
+            tma_load_4d(sm.q[qs] + off, &maps.q[ch.br], &sm.q_full[qs], ch.head * HD, x0, y0, ch.b);
+          }
+          ++it;
+        } else {
         const int x0 = c.wx * bg.ws, y0 = c.wy * bg.hs;
 #pragma unroll
         for (int bx = 0; bx < NBOX; ++bx) {
@@ -323,15 +368,33 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
           const int dy = (bg.ws > TILE) ? (t * TILE) / bg.ws : t * bg.by;
           tma_load_4d(sm.q[qs], &maps.q[c.br], &sm.q_full[qs], c.head * HD, x0 + dx, y0 + dy, c.b);
         }
+        }
       }
       // taps of this head -> smem; plain stores, released by the second arrival on v_full
 #pragma unroll
-      for (int j = 0; j < TAPS_PER_LANE; ++j) sm.lepe[vs][lane + 32 * j] = taps[j];
-      if (lane == 0)
-        sm.coord[vs] = make_int4(c.b, (c.wy * bg.hs) * p.W + c.wx * bg.ws, c.head, c.br);
+      for (int j = 0; j < TAPS_PER_LANE; ++j) sm.lepe[vs][0][lane + 32 * j] = taps[j];
+      if constexpr (PAIR) {
+#pragma unroll
+        for (int j = 0; j < TAPS_PER_LANE; ++j) sm.lepe[vs][1][lane + 32 * j] = taps1[j];
+      }
+      if (lane == 0) {
+        sm.coord[vs][0] = make_int4(c.b, (c.wy * bg.hs) * p.W + c.wx * bg.ws, c.head, c.br);
+        if constexpr (PAIR) {
+          const FwdBranch& b1 = p.br[c1.br];
+          sm.coord[vs][1] = make_int4(c1.b, (c1.wy * b1.hs) * p.W + c1.wx * b1.ws, c1.head, c1.br);
+        }
+      }
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.v_full[vs]);
-      if (gi + 1 < my_groups) fetch_taps(decode_group(p, (int)blockIdx.x + (gi + 1) * (int)gridDim.x));
+      if (gi + 1 < my_groups) {
+        const int nt = (int)blockIdx.x + (gi + 1) * (int)gridDim.x;
+        if constexpr (PAIR) {
+          fetch_taps(half_group(nt, 0));
+          fetch_taps1(half_group(nt, 1));
+        } else {
+          fetch_taps(decode_group(p, nt));
+        }
+      }
     }
   } else if (warp == 1) {
     // ================================ MMA issuer 1: S = Q K^T ================================
@@ -393,12 +456,12 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       const int gi = it / T, t = it % T, vs = gi % VS, lb = it % LB;
       mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
       mbar_wait(&sm.l_empty[lb], ((it / LB) & 1) ^ 1);
-      const int4 gc = sm.coord[vs];
+      const int4 gc = sm.coord[vs][0];
       const FwdBranch& bg = p.br[gc.w];
       const int n = t * TILE + row;
       const int yy = n >> bg.ws_log2, xx = n & (bg.ws - 1);
       float o[HD];
-      const float* lw = sm.lepe[vs];
+      const float* lw = sm.lepe[vs][0];
 #pragma unroll
       for (int cc = 0; cc < HD; ++cc) o[cc] = lw[9 * HD + cc];
       const uint8_t* vt = sm.v[vs];
@@ -456,17 +519,24 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       // Both sweeps double-buffer the TMEM reads: chunk ch+1 is in flight while chunk ch is consumed.
       uint32_t ra[32], rb[32];
       float m = -INFINITY;
+      // pair mode: this row belongs to half `hh` of the tile and attends to the keys of that half only — the
+      // two 32-column chunks 2 hh, 2 hh + 1 (warp-uniform: a warp's 32 rows lie in one half)
+      const int hh = PAIR ? (row >> 6) : 0;
       tmem_ld32(lane_base, ra);
       tmem_wait_ld();
 #pragma unroll
       for (int ch = 0; ch < NCH; ch += 2) {
         tmem_ld32(lane_base + (ch + 1) * 32, rb);
+        if (!PAIR || (ch >> 1) == hh) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(ra[i]));
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(ra[i]));
+        }
         tmem_wait_ld();
         if (ch + 2 < NCH) tmem_ld32(lane_base + (ch + 2) * 32, ra);
+        if (!PAIR || (ch >> 1) == hh) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rb[i]));
+          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rb[i]));
+        }
         tmem_wait_ld();
       }
       const float neg_m = -m * p.scale_log2;
@@ -480,7 +550,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       int d_tok0 = 0, d_wsl = 0, d_ws1 = 0, d_nw = 0;
       if constexpr (DROP) {
         mbar_wait(&sm.v_full[vs], (gi / VS) & 1);  // sm.coord rides on the V barrier
-        const int4 gc = sm.coord[vs];
+        const int4 gc = sm.coord[vs][0];
         const FwdBranch& bg = p.br[gc.w];
         rng = drop_rng_load(p.rng);
         const int y0 = gc.y / p.W, x0 = gc.y - y0 * p.W;
@@ -492,6 +562,12 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       }
       auto exp_chunk = [&](const uint32_t (&r)[32], int ch) {
         uint32_t pk[16];
+        if (PAIR && (ch >> 1) != hh) {  // keys of the other stripe: P = 0
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = 0u;
+          tmem_st16(lane_base + P_COL + ch * 16, pk);
+          return;
+        }
         uint32_t kw = 0xffffffffu;  // keep bits of keys 32 ch .. 32 ch + 31 for this query row
         if constexpr (DROP) {
           const uint32_t thr4 = p.drop_thr * 0x01010101u;
@@ -572,7 +648,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       int4 gc;
       const float inv_l = (DROP ? p.keep_scale : 1.f) / l;  // dropout: survivors are scaled by 1 / (1 - p)
       PROF_T(t4a);
-      const int n = t * TILE + row;  // in-stripe index
+      const int n = PAIR ? (row & 63) : t * TILE + row;  // in-stripe index
       if constexpr (LWG) {
         // the LePE term of this tile comes from the LePE warpgroup (chunks of row r rotated by r)
         const int lb = it % LB;
@@ -593,10 +669,10 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       // V and the LePE taps were written by TMA / the producer warp: acquire them through the same
       // barrier the PV issuer used (already complete; cannot advance before this warp's v_empty)
       mbar_wait(&sm.v_full[vs], (gi / VS) & 1);
-      gc = sm.coord[vs];  // image, first token of the stripe, head, branch
+      gc = sm.coord[vs][hh];  // image, first token of the stripe, head, branch
       const FwdBranch& bgl = p.br[gc.w];
       const int yy = n >> bgl.ws_log2, xx = n & (bgl.ws - 1);
-      const float* lw = sm.lepe[vs];
+      const float* lw = sm.lepe[vs][hh];
 #pragma unroll
       for (int cc = 0; cc < HD; ++cc) o[cc] = fmaf(__uint_as_float(r[cc]), inv_l, lw[9 * HD + cc]);
       const uint8_t* vt = sm.v[vs];
@@ -608,7 +684,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
         for (int kx = 0; kx < 3; ++kx) {
           const int nx = xx + kx - 1;
           if (nx < 0 || nx >= bgl.ws) continue;
-          const int nn = (ny << bgl.ws_log2) + nx;
+          const int nn = (ny << bgl.ws_log2) + nx + (PAIR ? 64 * hh : 0);  // row of the V tile
           const float* wt = lw + (ky * 3 + kx) * HD;
 #pragma unroll
           for (int q4 = 0; q4 < 4; ++q4) {
@@ -658,8 +734,9 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
   if (warp == 2) tmem_dealloc(tmem, 512);
 }
 
-template <int NK>
+template <int NK, bool PAIR = false>
 int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st) {
+  constexpr int ROWS = PAIR ? TILE / 2 : TILE;  // token rows of one TMA box
   FwdMaps maps;
   FwdParams p;
   memset(&maps, 0, sizeof(maps));
@@ -669,7 +746,7 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
   p.scale_log2 = g[0].scale * 1.4426950408889634f;
   int gpi = 0;
   for (int i = 0; i < nbr; ++i) {
-    const int bx = g[i].ws < TILE ? g[i].ws : TILE, by = TILE / bx;
+    const int bx = g[i].ws < ROWS ? g[i].ws : ROWS, by = ROWS / bx;
     int rc;
     if ((rc = tc_make_map(&maps.q[i], io[i].q, g[i], g[i].q_sb, g[i].q_sl, bx, by)) != CSB200_OK) return rc;
     if ((rc = tc_make_map(&maps.k[i], io[i].k, g[i], g[i].k_sb, g[i].k_sl, bx, by)) != CSB200_OK) return rc;
@@ -688,7 +765,8 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
     gpi += g[i].nwy * g[i].nwx * g[i].heads;
   }
   p.gpi = gpi;
-  p.groups = p.B * gpi;
+  p.real_groups = p.B * gpi;
+  p.groups = PAIR ? (p.real_groups + 1) / 2 : p.real_groups;
   p.drop_thr = g[0].drop_thr;
   p.keep_scale = g[0].keep_scale;
   p.rng = g[0].rng;
@@ -699,12 +777,17 @@ int launch_fwd(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t st)
   const int sm_count = device_sm_count();
   if (sm_count <= 0) return fail(CSB200_ERR_CUDA, "stripe_fwd_tc: cannot query the SM count");
   const int grid = p.groups < sm_count ? p.groups : sm_count;
-  if (drop) {
+  constexpr int THREADS_FWD = 128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG);
+  if constexpr (PAIR) {
+    if (drop) return fail(CSB200_ERR_UNSUPPORTED, "stripe_fwd_tc: no attention dropout in the pair mode");
+    CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, false, true>), smem));
+    stripe_fwd_tc<NK, false, true><<<grid, THREADS_FWD, smem, st>>>(maps, p);
+  } else if (drop) {
     CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, true>), smem));
-    stripe_fwd_tc<NK, true><<<grid, 128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), smem, st>>>(maps, p);
+    stripe_fwd_tc<NK, true><<<grid, THREADS_FWD, smem, st>>>(maps, p);
   } else {
     CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&stripe_fwd_tc<NK, false>), smem));
-    stripe_fwd_tc<NK, false><<<grid, 128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), smem, st>>>(maps, p);
+    stripe_fwd_tc<NK, false><<<grid, THREADS_FWD, smem, st>>>(maps, p);
   }
   return check_launch("stripe_fwd_tc");
 }
@@ -720,9 +803,15 @@ bool tc_single_pass_supported(const StripeGeom& g, int dtype) {
   if (g.ws > 256 || g.hs > 256) return false;
   return true;
 }
-// forward: the single-pass kernels here, or the key/value-tiled kernel for long stripes (stripe_attn_tc_kv.cu)
+// stripes of 64 tokens (two per tile, forward only, no dropout): the stripe is one 64-row TMA box
+bool tc_fwd_pair_supported(const StripeGeom& g, int dtype) {
+  if (dtype != CSB200_BF16 || g.N != 64 || g.drop_thr != 0) return false;
+  return g.ws <= 64 && 64 % g.ws == 0 && g.hs <= 256;
+}
+// forward: the single-pass kernels here (incl. the pair mode), or the key/value-tiled kernel for long stripes
+// (stripe_attn_tc_kv.cu)
 bool tc_fwd_supported(const StripeGeom& g, int dtype) {
-  return tc_single_pass_supported(g, dtype) || tc_fwd_kv_supported(g, dtype);
+  return tc_single_pass_supported(g, dtype) || tc_fwd_pair_supported(g, dtype) || tc_fwd_kv_supported(g, dtype);
 }
 bool tc_bwd_supported(const StripeGeom& g, int dtype) { return tc_single_pass_supported(g, dtype); }
 
@@ -744,8 +833,9 @@ int tc_fwd_multi(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t s
 
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st) {
-  if (g.N != 128 && g.N != 256) return tc_fwd_kv(g, q, k, v, lepe_w, lepe_b, out, lse, st);
   const TcFwdIO io{q, k, v, lepe_w, lepe_b, out, lse};
+  if (g.N == 64) return launch_fwd<128, true>(1, &g, &io, st);
+  if (g.N != 128 && g.N != 256) return tc_fwd_kv(g, q, k, v, lepe_w, lepe_b, out, lse, st);
   return tc_fwd_multi(1, &g, &io, st);
 }
 

@@ -291,3 +291,38 @@ def test_long_stripes_run_on_the_key_value_tiled_tcgen05_kernel(case):
     with torch.no_grad():
         o_simt = csbF.cross_stripe_attention(packed, H, W, [br], 32 ** -0.5, [w.float().cuda(), b.float().cuda()], "simt")
     assert _per_image_rel(out, o_simt.float().cpu()) < 2 ** -6
+
+
+# Stripes of 64 tokens (BASELINE config 5 at stripe width 1: stage 3 of a 1024^2 input) — two (stripe, head) groups
+# per 128-row tile of the single-pass tcgen05 forward kernel ("pair mode"): (B, H, W, hs, ws, heads); the last two
+# have an ODD number of groups (the final tile holds its group twice).
+PAIR_STRIPES = [(2, 64, 64, 64, 1, 2), (1, 16, 64, 1, 64, 4), (3, 32, 32, 8, 8, 2), (2, 64, 32, 2, 32, 1),
+                (1, 64, 3, 64, 1, 1), (1, 8, 8, 8, 8, 5)]
+
+
+@pytest.mark.parametrize("case", PAIR_STRIPES)
+def test_stripes_of_64_tokens_run_two_per_tile_on_the_tcgen05_forward_kernel(case):
+    B, H, W, hs, ws, heads = case
+    C = heads * 32
+    br = csbF.Branch(hs, ws, heads, 0, C)
+    assert csbF.stripe_engine(torch.bfloat16, B, H, W, br) == "tcgen05"
+    assert csbF.stripe_engine(torch.bfloat16, B, H, W, br, backward=True) == "simt"
+    gen = torch.Generator().manual_seed(sum(case))
+    qkv = torch.randn((3, B, H * W, C), generator=gen)
+    qkv[:2] *= 1.5
+    qkv = qkv.to(torch.bfloat16).double()
+    w = (torch.randn((C, 1, 3, 3), generator=gen) * 0.3).float().double()
+    b = (torch.randn((C,), generator=gen) * 0.1).float().double()
+    gout = torch.randn((B, H * W, C), generator=gen).to(torch.bfloat16).double()
+    out, dqkv, dw, db = _run(qkv, w, b, gout, (H, W), hs, ws, heads, torch.bfloat16)
+    q64 = qkv.clone().requires_grad_(True)
+    w64, b64 = w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    ref = ops.stripe_attention(q64[0], q64[1], q64[2], w64, b64, H, W, hs, ws, heads)
+    ref.backward(gout)
+    assert _per_image_rel(out, ref.detach()) < FWD_TOL[torch.bfloat16]
+    assert rel_err(dqkv, q64.grad) < BWD_TOL[torch.bfloat16]  # CUDA-core backward from the lse the pair kernel wrote
+    assert rel_err(dw, w64.grad) < BWD_TOL[torch.bfloat16] and rel_err(db, b64.grad) < BWD_TOL[torch.bfloat16]
+    packed = torch.cat([qkv[0], qkv[1], qkv[2]], dim=-1).to(torch.bfloat16).cuda()
+    with torch.no_grad():
+        o_simt = csbF.cross_stripe_attention(packed, H, W, [br], 32 ** -0.5, [w.float().cuda(), b.float().cuda()], "simt")
+    assert _per_image_rel(out, o_simt.float().cpu()) < 2 ** -6
