@@ -211,9 +211,12 @@ class TrainStep:
         self._reduce_in_graph = self.reducer.world > 1 and self.reducer.capturable and self.capture_collectives
         try:
             self._capture_dp_graph(in_graph=self._reduce_in_graph)
-        except RuntimeError:
+        except RuntimeError as e:
             if not self._reduce_in_graph:
                 raise
+            import warnings
+            warnings.warn("the NCCL all-reduce could not be captured into the backward graph "
+                          f"({str(e).splitlines()[0][:200]}); it is issued eagerly between the two graphs instead")
             torch.cuda.synchronize(dev)
             self._reduce_in_graph = False
             self._graph = torch.cuda.CUDAGraph()
