@@ -518,7 +518,7 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
       PROF_T(t1);
       // Both sweeps double-buffer the TMEM reads: chunk ch+1 is in flight while chunk ch is consumed.
       uint32_t ra[32], rb[32];
-      float m = -INFINITY;
+      float mm[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // four independent chains (one was 16 dependent FMNMX3 per chunk)
       // pair mode: this row belongs to half `hh` of the tile and attends to the keys of that half only — the
       // two 32-column chunks 2 hh, 2 hh + 1 (warp-uniform: a warp's 32 rows lie in one half)
       const int hh = PAIR ? (row >> 6) : 0;
@@ -529,16 +529,17 @@ __global__ void __launch_bounds__(128 + 128 * (Cfg<NK>::NWG + Cfg<NK>::LWG), 1)
         tmem_ld32(lane_base + (ch + 1) * 32, rb);
         if (!PAIR || (ch >> 1) == hh) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(ra[i]));
+          for (int i = 0; i < 32; ++i) mm[i & 3] = fmaxf(mm[i & 3], __uint_as_float(ra[i]));
         }
         tmem_wait_ld();
         if (ch + 2 < NCH) tmem_ld32(lane_base + (ch + 2) * 32, ra);
         if (!PAIR || (ch >> 1) == hh) {
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m = fmaxf(m, __uint_as_float(rb[i]));
+          for (int i = 0; i < 32; ++i) mm[i & 3] = fmaxf(mm[i & 3], __uint_as_float(rb[i]));
         }
         tmem_wait_ld();
       }
+      const float m = fmaxf(fmaxf(mm[0], mm[1]), fmaxf(mm[2], mm[3]));
       const float neg_m = -m * p.scale_log2;
       const f2_t scale2 = f2_splat(p.scale_log2), negm2 = f2_splat(neg_m);
       PROF_T(t2);

@@ -253,20 +253,21 @@ __global__ void __launch_bounds__(THREADS, 1)
         mbar_wait(&sm.s_full[wg], nblk & 1);
         fence_after_sync();
         uint32_t ra[32], rb[32];
-        float m_blk = -INFINITY;
+        float mb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains
         tmem_ld32(lane_base, ra);
         tmem_wait_ld();
 #pragma unroll
         for (int ch = 0; ch < 4; ch += 2) {
           tmem_ld32(lane_base + (ch + 1) * 32, rb);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(ra[i]));
+          for (int i = 0; i < 32; ++i) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(ra[i]));
           tmem_wait_ld();
           if (ch + 2 < 4) tmem_ld32(lane_base + (ch + 2) * 32, ra);
 #pragma unroll
-          for (int i = 0; i < 32; ++i) m_blk = fmaxf(m_blk, __uint_as_float(rb[i]));
+          for (int i = 0; i < 32; ++i) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(rb[i]));
           tmem_wait_ld();
         }
+        const float m_blk = fmaxf(fmaxf(mb[0], mb[1]), fmaxf(mb[2], mb[3]));
         const float m_new = fmaxf(m_run, m_blk);
         if (j > 0) {
           // online softmax: everything accumulated so far is relative to m_run
