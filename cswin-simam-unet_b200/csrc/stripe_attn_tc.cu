@@ -835,9 +835,9 @@ int tc_fwd_multi(int nbr, const StripeGeom* g, const TcFwdIO* io, cudaStream_t s
 int tc_fwd(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
            const float* lepe_b, void* out, float* lse, cudaStream_t st) {
   const TcFwdIO io{q, k, v, lepe_w, lepe_b, out, lse};
+  if (tc_single_pass_supported(g, CSB200_BF16)) return tc_fwd_multi(1, &g, &io, st);
   if (g.N == 64) return launch_fwd<128, true>(1, &g, &io, st);
-  if (g.N != 128 && g.N != 256) return tc_fwd_kv(g, q, k, v, lepe_w, lepe_b, out, lse, st);
-  return tc_fwd_multi(1, &g, &io, st);
+  return tc_fwd_kv(g, q, k, v, lepe_w, lepe_b, out, lse, st);
 }
 
 }  // namespace csb200

@@ -45,7 +45,10 @@ constexpr int THREADS = 128 + 128 * NWG;
 
 struct KvParams {
   int B, W, L;
-  int hs, ws, ws_log2, nwy, nwx, heads, by;
+  int hs, ws, nwy, nwx, heads;
+  int by;                   // ws <= 128: stripe rows per tile (floor(128 / ws)); the TMA box is (32, ws, by)
+  int tpr;                  // ws > 128: tiles per stripe row (ceil(ws / 128)); the TMA box is (32, 128, 1)
+  int box_bytes;            // bytes one box delivers (tile rows the box does not cover are never written)
   int T;                    // query tiles == key/value blocks per group
   int items;                // groups * T
   float scale, scale_log2;
@@ -84,10 +87,40 @@ __device__ __forceinline__ Item decode_item(const KvParams& p, int it) {
   c.b = g / p.nwy;
   return c;
 }
-// TMA coordinates of in-stripe rows [128 t, 128 t + 128)
+// Tile t of a stripe (h_sp x w_sp tokens, row-major): w_sp <= 128 -> `by` whole stripe rows (by * w_sp <= 128 token
+// rows of the tile are used), w_sp > 128 -> 128 consecutive tokens of one stripe row.  Tokens of the box that lie
+// outside the stripe (below it, or to its right) are loaded like any others — or zero-filled outside the image —
+// and MASKED: tile rows [vcount, 128) never take part (keys: S columns set to -inf; queries: not stored).  Stripe
+// shapes that are not powers of two (w_sp = 7: BASELINE config 5 at 896^2, config 1) therefore tile like the rest.
 __device__ __forceinline__ void tile_xy(const KvParams& p, const Item& c, int t, int& x, int& y) {
-  x = c.wx * p.ws + ((p.ws > TILE) ? (t * TILE) % p.ws : 0);
-  y = c.wy * p.hs + ((p.ws > TILE) ? (t * TILE) / p.ws : t * p.by);
+  x = c.wx * p.ws + (p.ws > TILE ? (t % p.tpr) * TILE : 0);
+  y = c.wy * p.hs + (p.ws > TILE ? t / p.tpr : t * p.by);
+}
+__device__ __forceinline__ int tile_vcount(const KvParams& p, int t) {  // valid token rows of tile t (a prefix)
+  if (p.ws > TILE) {
+    const int left = p.ws - (t % p.tpr) * TILE;
+    return left < TILE ? left : TILE;
+  }
+  const int rows = p.hs - t * p.by;
+  return (rows < p.by ? rows : p.by) * p.ws;
+}
+// in-stripe (row, column) of token row r of tile t
+__device__ __forceinline__ void tile_pos(const KvParams& p, int t, int r, int& yy, int& xx) {
+  if (p.ws > TILE) {
+    yy = t / p.tpr;
+    xx = (t % p.tpr) * TILE + r;
+  } else {
+    const int q = r / p.ws;
+    yy = t * p.by + q;
+    xx = r - q * p.ws;
+  }
+}
+// keys [32 ch, 32 ch + 32) of a block with `vk` valid keys: the others become -inf
+__device__ __forceinline__ void mask_keys(uint32_t (&r)[32], int ch, int vk) {
+  const int left = vk - 32 * ch;
+  if (left >= 32) return;
+#pragma unroll
+  for (int i = 0; i < 32; ++i) r[i] = i < left ? r[i] : 0xff800000u;
 }
 
 __global__ void __launch_bounds__(THREADS, 1)
@@ -126,6 +159,12 @@ __global__ void __launch_bounds__(THREADS, 1)
     fence_barrier_init();
   }
   if (warp == 2) tmem_alloc(&sm.tmem_base, 512);
+  if (p.box_bytes < TILE_BYTES) {
+    // tile rows the boxes never write must read as ZERO in V (their probabilities are zero, but 0 x NaN is NaN)
+    uint4* vz = reinterpret_cast<uint4*>(&sm.v[0][0]);
+    for (int i = threadIdx.x; i < VS * TILE_BYTES / 16; i += THREADS) vz[i] = make_uint4(0u, 0u, 0u, 0u);
+    fence_proxy_async_smem();
+  }
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -150,17 +189,17 @@ __global__ void __launch_bounds__(THREADS, 1)
             if (j == 0) {
               const int qs = qn % QS;
               mbar_wait(&sm.q_empty[qs], ((qn / QS) & 1) ^ 1);
-              mbar_expect_tx(&sm.q_full[qs], TILE_BYTES);
+              mbar_expect_tx(&sm.q_full[qs], p.box_bytes);
               tile_xy(p, c, c.qt, x, y);
               tma_load_4d(sm.q[qs], &maps.q, &sm.q_full[qs], c.head * HD, x, y, c.b);
             }
             const int ks = e % KS, vs = e % VS;
             tile_xy(p, c, j, x, y);
             mbar_wait(&sm.k_empty[ks], ((e / KS) & 1) ^ 1);
-            mbar_expect_tx(&sm.k_full[ks], TILE_BYTES);
+            mbar_expect_tx(&sm.k_full[ks], p.box_bytes);
             tma_load_4d(sm.k[ks], &maps.k, &sm.k_full[ks], c.head * HD, x, y, c.b);
             mbar_wait(&sm.v_empty[vs], ((e / VS) & 1) ^ 1);
-            mbar_expect_tx(&sm.v_full[vs], TILE_BYTES);
+            mbar_expect_tx(&sm.v_full[vs], p.box_bytes);
             tma_load_4d(sm.v[vs], &maps.v, &sm.v_full[vs], c.head * HD, x, y, c.b);
           }
           if (j == 0) ++qn;
@@ -254,15 +293,18 @@ __global__ void __launch_bounds__(THREADS, 1)
         fence_after_sync();
         uint32_t ra[32], rb[32];
         float mb[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // independent chains
+        const int vk = tile_vcount(p, j);  // valid keys of this block (128 unless the stripe shape leaves a ragged tile)
         tmem_ld32(lane_base, ra);
         tmem_wait_ld();
 #pragma unroll
         for (int ch = 0; ch < 4; ch += 2) {
           tmem_ld32(lane_base + (ch + 1) * 32, rb);
+          if (vk < TILE) mask_keys(ra, ch, vk);
 #pragma unroll
           for (int i = 0; i < 32; ++i) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(ra[i]));
           tmem_wait_ld();
           if (ch + 2 < 4) tmem_ld32(lane_base + (ch + 2) * 32, ra);
+          if (vk < TILE) mask_keys(rb, ch + 1, vk);
 #pragma unroll
           for (int i = 0; i < 32; ++i) mb[i & 3] = fmaxf(mb[i & 3], __uint_as_float(rb[i]));
           tmem_wait_ld();
@@ -293,8 +335,9 @@ __global__ void __launch_bounds__(THREADS, 1)
         const float neg_m = -m_new * p.scale_log2;
         const f2_t scale2 = f2_splat(p.scale_log2), negm2 = f2_splat(neg_m);
         float l0 = 0.f, l1 = 0.f;
-        auto exp_chunk = [&](const uint32_t (&r)[32], int ch) {
+        auto exp_chunk = [&](uint32_t (&r)[32], int ch) {
           uint32_t pk[16];
+          if (vk < TILE) mask_keys(r, ch, vk);  // 2^(-inf) = 0: masked keys get no probability
 #pragma unroll
           for (int i = 0; i < 16; ++i) {
             const f2_t x2 = f2_fma(f2_make(__uint_as_float(r[2 * i]), __uint_as_float(r[2 * i + 1])), scale2, negm2);
@@ -339,8 +382,9 @@ __global__ void __launch_bounds__(THREADS, 1)
       __syncwarp();
       if (lane == 0) mbar_arrive(&sm.buf_empty[wg]);  // the next item's first S may overwrite this buffer
       const float inv_l = 1.f / l_run;
-      const int n = c.qt * TILE + row;  // in-stripe index
-      const int yy = n >> p.ws_log2, xx = n & (p.ws - 1);
+      if (row >= tile_vcount(p, c.qt)) continue;  // token rows of the tile that are not queries of this stripe
+      int yy, xx;
+      tile_pos(p, c.qt, row, yy, xx);
       const int y0 = c.wy * p.hs, x0 = c.wx * p.ws;
       float o[HD];
 #pragma unroll
@@ -385,14 +429,27 @@ __global__ void __launch_bounds__(THREADS, 1)
 
 }  // namespace
 
-// Long stripes: bf16, N a multiple of 128 with 3 <= N / 128 <= 32, stripe width dividing (or a multiple of) 128,
-// no attention dropout.  Forward only (inference; a backward pass for these lengths uses the CUDA-core engine).
+// Stripes of more than 128 tokens that the single-pass kernels do not take: bf16, stripe width <= 256, at most 64
+// tiles per stripe, no attention dropout.  ANY stripe shape — tiles that a stripe does not fill are masked.  Forward
+// only (inference; a backward pass for these shapes uses the CUDA-core engine).
+static void kv_tiling(const StripeGeom& g, int* bx, int* by, int* tpr, int* T) {
+  if (g.ws > TILE) {
+    *bx = TILE; *by = 1;
+    *tpr = (g.ws + TILE - 1) / TILE;
+    *T = g.hs * *tpr;
+  } else {
+    *bx = g.ws; *by = TILE / g.ws;
+    if (*by > g.hs) *by = g.hs;
+    *tpr = 1;
+    *T = (g.hs + *by - 1) / *by;
+  }
+}
 bool tc_fwd_kv_supported(const StripeGeom& g, int dtype) {
   if (dtype != CSB200_BF16 || g.drop_thr != 0) return false;
-  if (g.N % TILE != 0 || g.N / TILE < 3 || g.N / TILE > 32) return false;
-  if (!((g.ws <= TILE && TILE % g.ws == 0) || (g.ws % TILE == 0))) return false;
-  if (g.ws > 256 || g.hs > 256) return false;
-  return true;
+  if (g.N <= TILE || g.ws > 256 || g.hs > 256) return false;
+  int bx, by, tpr, T;
+  kv_tiling(g, &bx, &by, &tpr, &T);
+  return T >= 2 && T <= 64;
 }
 
 int tc_fwd_kv(const StripeGeom& g, const void* q, const void* k, const void* v, const float* lepe_w,
@@ -401,16 +458,16 @@ int tc_fwd_kv(const StripeGeom& g, const void* q, const void* k, const void* v, 
   KvParams p;
   memset(&maps, 0, sizeof(maps));
   memset(&p, 0, sizeof(p));
-  const int bx = g.ws < TILE ? g.ws : TILE, by = TILE / bx;
+  int bx, by, tpr, T;
+  kv_tiling(g, &bx, &by, &tpr, &T);
   int rc;
   if ((rc = tc_make_map(&maps.q, q, g, g.q_sb, g.q_sl, bx, by)) != CSB200_OK) return rc;
   if ((rc = tc_make_map(&maps.k, k, g, g.k_sb, g.k_sl, bx, by)) != CSB200_OK) return rc;
   if ((rc = tc_make_map(&maps.v, v, g, g.v_sb, g.v_sl, bx, by)) != CSB200_OK) return rc;
   p.B = g.B; p.W = g.W; p.L = g.L;
-  p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx; p.heads = g.heads; p.by = by;
-  p.ws_log2 = 0;
-  while ((1 << p.ws_log2) < g.ws) ++p.ws_log2;
-  p.T = g.N / TILE;
+  p.hs = g.hs; p.ws = g.ws; p.nwy = g.nwy; p.nwx = g.nwx; p.heads = g.heads;
+  p.by = by; p.tpr = tpr; p.T = T;
+  p.box_bytes = bx * by * ROW_BYTES;
   const int64_t items = (int64_t)g.B * g.nwy * g.nwx * g.heads * p.T;
   if (items > 0x7fffffff) return fail(CSB200_ERR_INVALID, "stripe_fwd_tc_kv: too many work items");
   p.items = (int)items;

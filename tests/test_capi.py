@@ -106,6 +106,36 @@ def test_engine_selection():
     assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_SIMT
 
 
+def test_engine_selection_for_config5_stripes():
+    """BASELINE config 5 (1024^2 inference, C:232-242 geometry): stripes of 64 tokens (two per tile) and of
+    512 / 1024 / 2048 tokens (key/value-tiled kernel) take the tcgen05 engine in FORWARD only; so does width 7."""
+    lib = capi.lib()
+    cases = (dict(height=64, width=64, h_sp=64, w_sp=1),      # split 1, stage 3: N = 64
+             dict(height=64, width=64, h_sp=1, w_sp=64),
+             dict(height=256, width=256, h_sp=256, w_sp=2),   # split 2, stage 1: N = 512
+             dict(height=256, width=256, h_sp=8, w_sp=256),   # split 8, stage 1: N = 2048
+             dict(height=32, width=32, h_sp=32, w_sp=32))     # last stage, full window: N = 1024
+    for kw in cases:
+        L = kw["height"] * kw["width"]
+        d = _desc(dtype=capi.BF16, q_sb=L * 96, k_sb=L * 96, v_sb=L * 96, o_sb=L * 32, **kw)
+        assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_TCGEN05, kw
+        assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 1) == capi.ENGINE_SIMT, kw   # backward: CUDA cores
+        d.engine = capi.ENGINE_TCGEN05
+        assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 1) == -capi.ERR_UNSUPPORTED  # forced: refused
+        d.dtype = capi.F32
+        d.engine = capi.ENGINE_AUTO
+        assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_SIMT
+    L = 224 * 224   # 896^2, split 7: N = 1568 — ragged tiles, masked: still the tcgen05 engine in forward
+    d = _desc(dtype=capi.BF16, height=224, width=224, h_sp=224, w_sp=7, q_sb=L * 96, k_sb=L * 96, v_sb=L * 96, o_sb=L * 32)
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_TCGEN05
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 1) == capi.ENGINE_SIMT
+    # config 1 (224^2, split [1, 2, 7, 7]): stripes of <= 128 tokens that are not 64 or 128 stay on the CUDA cores
+    d = _desc(dtype=capi.BF16, height=14, width=14, h_sp=14, w_sp=7, q_sb=196 * 96, k_sb=196 * 96, v_sb=196 * 96, o_sb=196 * 32)
+    assert lib.csb200_stripe_attn_engine(ctypes.byref(d), 0) == capi.ENGINE_SIMT
+    # the SimAM workspace query never fails: 0 = "the grid-resident kernels do not apply" (here: no GPU, or NCHW)
+    assert lib.csb200_simam_workspace_bytes(32, 64, 16384, capi.NCHW, capi.BF16) == 0
+
+
 def test_simam_argument_validation():
     lib = capi.lib()
     one = ctypes.c_void_p(16)

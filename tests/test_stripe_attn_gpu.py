@@ -258,13 +258,18 @@ def test_backward_at_benchmarked_launch_geometry(stage):
 # Long stripes of BASELINE config 5 (1024^2: C:232-242 geometry at split 8 -> N = 2048, 1024, 512; the 32 x 32
 # full window of the last stage -> N = 1024) plus a T = 3 case: (B, H, W, hs, ws, heads).
 LONG_STRIPES = [(1, 256, 256, 256, 8, 2), (1, 16, 256, 8, 256, 1), (1, 128, 128, 128, 8, 2), (1, 64, 64, 8, 64, 4),
-                (2, 32, 32, 32, 32, 8), (1, 48, 16, 48, 8, 1), (3, 64, 16, 64, 16, 2)]
+                (2, 32, 32, 32, 32, 8), (1, 48, 16, 48, 8, 1), (3, 64, 16, 64, 16, 2),
+                # stripe shapes that are not powers of two (width 7: config 5 at 896^2, config 1): tiles the stripe
+                # does not fill are masked — N = 1568 (224 x 7 and 7 x 224), 392, 196 (14 x 14, 28 x 7, 7 x 28), 144
+                (1, 224, 14, 224, 7, 2), (1, 7, 224, 7, 224, 1), (2, 56, 56, 56, 7, 2), (1, 28, 28, 14, 14, 2),
+                (1, 28, 28, 28, 7, 1), (2, 28, 28, 7, 28, 1), (1, 12, 24, 12, 12, 3)]
 
 
 @pytest.mark.parametrize("case", LONG_STRIPES)
 def test_long_stripes_run_on_the_key_value_tiled_tcgen05_kernel(case):
-    """N = 128 T (3 <= T <= 16): forward on stripe_fwd_tc_kv (online softmax over key/value blocks), backward on
-    the CUDA-core engine, both against the fp64 oracle of LePEAttention.forward (C:271-298)."""
+    """More than 128 tokens per stripe, any stripe shape: forward on stripe_fwd_tc_kv (online softmax over key/value
+    blocks, ragged tiles masked), backward on the CUDA-core engine, both against the fp64 oracle of
+    LePEAttention.forward (C:271-298)."""
     B, H, W, hs, ws, heads = case
     C = heads * 32
     br = csbF.Branch(hs, ws, heads, 0, C)
