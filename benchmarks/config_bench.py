@@ -69,26 +69,18 @@ def config5():
             with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16):
                 net(x)
         ms = timed_ms(f, 10)
-        # the same forward captured into a CUDA graph: eager issue of the ~1 000 launches costs more than the kernels
-        # take at split 1 / 2 (6.8 ms of device time against 13.7 ms per eager batch)
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(2):
-                f()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            f()
-        ms_graph = timed_ms(g.replay, 10)
+        # the same forward replayed from a CUDA graph (pkg.InferStep): eager issue of the ~1 000 launches costs more
+        # than the kernels take at split 1 / 2 (6.8 ms of device time against 13.7 ms per eager batch)
+        infer = pkg.InferStep(net, precision="bf16", cuda_graph=True)
+        infer(x)
+        ms_graph = timed_ms(lambda: infer(x), 10)
         engines = sorted({a.engine for m in net.modules() if isinstance(m, pkg.CSWinBlock) for a in m.attns})
         print(json.dumps({"config": f"5: CSWin-SimAM-UNet {size}^2 inference batch 8 bf16, split {[sw] * 4}",
                           "ms_per_batch": round(ms_graph, 2), "img_per_s": round(8 / ms_graph * 1e3, 1),
                           "eager_ms_per_batch": round(ms, 2), "eager_img_per_s": round(8 / ms * 1e3, 1),
-                          "mode": "forward captured in a CUDA graph (eager numbers beside it)",
+                          "mode": "pkg.InferStep: forward replayed from a CUDA graph (eager numbers beside it)",
                           "engine_setting": engines}), flush=True)
-        del g
+        del infer
         del net, x
         torch.cuda.empty_cache()
 

@@ -13,7 +13,7 @@ from .functional import cross_stripe_attention, simam, stripe_attention  # noqa:
 from .models import CSWinTransformer, DoubleConv, Down, UNet, Up  # noqa: F401
 from .modules import (CARAFE, CARAFE4, CSWinBlock, DropPath, LePEAttention, Merge_Block, Mlp,  # noqa: F401
                       SimAM)
-from .train import TrainStep, bce_from_logits_as_probabilities, synthetic_batch  # noqa: F401
+from .train import InferStep, TrainStep, bce_from_logits_as_probabilities, synthetic_batch  # noqa: F401
 from .data_parallel import GradientAllReducer, shard_of_global_batch  # noqa: F401
 from .optim import FusedAdamW, fused_adam  # noqa: F401
 

@@ -263,3 +263,25 @@ def test_config5_high_res_inference_stripe_width_sweep(size, sw):
     if sw == 7:
         with pytest.raises(RuntimeError):  # 1024/16 = 64 is not divisible by 7, exactly like the reference
             pkg.CSWinTransformer(img_size=1024, split_size=[7] * 4).cuda()(torch.rand(1, 3, 1024, 1024, device="cuda"))
+
+
+def test_infer_step_replays_a_cuda_graph_and_matches_eager():
+    """pkg.InferStep: eval-mode forward under no_grad, replayed from a CUDA graph (config 5 is host-bound in eager
+    mode).  Same bits as the eager forward, a new input really reaches the static buffer, training mode is refused.
+    448^2 with stripe width 7: stripes of 784 / 392 / 196 / 196 tokens -> the tiled tcgen05 kernel with masked tiles."""
+    torch.manual_seed(0)
+    net = pkg.CSWinTransformer(img_size=448, split_size=[7] * 4, simam=True).cuda().eval()
+    infer = pkg.InferStep(net, precision="bf16", cuda_graph=True)
+    eager = pkg.InferStep(net, precision="bf16", cuda_graph=False)
+    x1, x2 = torch.rand(2, 3, 448, 448, device="cuda"), torch.rand(2, 3, 448, 448, device="cuda")
+    n0 = pkg.capi.launch_count()
+    y1 = infer(x1).clone()
+    assert pkg.capi.launch_count() > n0
+    y2 = infer(x2).clone()
+    assert torch.equal(y1, eager(x1)) and torch.equal(y2, eager(x2)) and not torch.equal(y1, y2)
+    with torch.no_grad():
+        ref = net(x1)  # fp32, CUDA-core attention
+    assert (y1.float() - ref).abs().max().item() <= 2e-2
+    net.train()
+    with pytest.raises(RuntimeError, match="eval"):
+        infer(x1)
