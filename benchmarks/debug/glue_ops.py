@@ -24,10 +24,11 @@ ops = sorted(prof.key_averages(group_by_input_shape=True, group_by_stack_n=8), k
 want = ("aten::copy_", "aten::add", "aten::cat", "aten::_to_copy", "aten::sum", "aten::mul", "aten::clone", "aten::fill_",
         "aten::zero_", "aten::sigmoid", "aten::binary_cross", "aten::div", "aten::sub", "aten::neg", "aten::where")
 tot = 0.0
+ALL = len(sys.argv) > 1 and sys.argv[1] == "all"
 for e in ops:
-    if e.self_device_time_total < 5 or not e.key.startswith(want):
+    if e.self_device_time_total < 5 or not (e.key.startswith(want) or (ALL and e.key.startswith("aten::"))):
         continue
     tot += e.self_device_time_total
-    frames = [f for f in e.stack if "cswin" in f or "bench" in f][:3]
+    frames = [f for f in e.stack if "cswin" in f or "bench" in f][:4]
     print(f"{e.self_device_time_total / 1e3:7.3f} ms n={e.count:3d} {e.key[:24]:24s} {str(e.input_shapes)[:70]:70s} {' <- '.join(s.split('/')[-1][:60] for s in frames)}")
 print(f"total glue {tot / 1e3:.3f} ms")
