@@ -50,6 +50,19 @@ def main():
         res["grad_rel_l2"] = (num / den) ** 0.5
     red.close()
 
+    # ---- 1b. the same with a bf16 wire (reduce_dtype): half the bytes, the average rounded to bf16 ----
+    net2 = make_net(dev)
+    red = pkg.GradientAllReducer(net2.parameters(), reduce_dtype=torch.bfloat16)
+    step = pkg.TrainStep(net2, torch.optim.SGD(net2.parameters(), lr=0.0), precision="fp32", reducer=red)
+    red.begin_step()
+    step.forward_loss(x, y).backward()
+    red.finish_step()
+    res["bf16_wire_bytes_ratio"] = red.gradient_bytes() / sum(p.numel() * 4 for p in net2.parameters())
+    if rank == 0:
+        num = sum(float((p.grad.double() - q.grad.double()).pow(2).sum()) for p, q in zip(net2.parameters(), ref.parameters()))
+        res["bf16_wire_grad_rel_l2"] = (num / den) ** 0.5
+    red.close()
+
     # ---- 2. three captured data-parallel AdamW steps (all-reduce inside the graph) == global-batch steps ----
     for capture in (True, False):
         net = make_net(dev)

@@ -26,6 +26,7 @@ def test_nccl_gradients_match_the_global_batch(tmp_path):
     # per-tensor max error relative to that tensor's largest gradient, and the global L2 error
     assert res["grad_rel"] <= 1e-5 * 5, res       # tensors with tiny gradients carry fp32 summation-order noise
     assert res["grad_rel_l2"] <= 1e-5, res
+    assert res["bf16_wire_bytes_ratio"] == 0.5 and res["bf16_wire_grad_rel_l2"] <= 4e-3, res  # 2 roundings of 2^-9
     for key in ("in_graph", "between_graphs"):
         assert res[key + "_replicas_identical"], res
         assert res[key + "_weights_rel_l2"] <= 1e-5, res

@@ -154,13 +154,14 @@ def _tiny_model():
                                torch.nn.Sigmoid())
 
 
-def _dp_worker(rank, world, port, overlap, q):
+def _dp_worker(rank, world, port, overlap, q, reduce_dtype=None):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     model = _tiny_model()
-    red = data_parallel.GradientAllReducer(model.parameters(), bucket_bytes=256, overlap=overlap)
-    assert len(red.buckets) > 1
+    red = data_parallel.GradientAllReducer(model.parameters(), bucket_bytes=256, overlap=overlap,
+                                           reduce_dtype=reduce_dtype)
+    assert len(red.buckets) > 1 and all((b.wire is None) == (reduce_dtype is None) for b in red.buckets)
     opt = torch.optim.SGD(model.parameters(), lr=0.1)
     step = pkg.TrainStep(model, opt, precision="fp32", reducer=red)
     shard = data_parallel.shard_of_global_batch(8, rank, world)
@@ -172,8 +173,8 @@ def _dp_worker(rank, world, port, overlap, q):
     # again, finish_step() must still average (it used to wait on the finished all-reduce of the step before)
     replay_ok = True
     for it in range(2):
-        for b in red.buckets:
-            b.flat.fill_(float(rank + 1 + it))
+        for b in red.buckets:  # (with reduce_dtype the replayed pack copy writes the wire image of the bucket)
+            (b.flat if b.wire is None else b.wire).fill_(float(rank + 1 + it))
         red.finish_step()
         replay_ok &= all(torch.allclose(b.flat, torch.full_like(b.flat, (1 + world) / 2 + it)) for b in red.buckets)
     q.put((rank, params, grads, replay_ok))
@@ -181,14 +182,15 @@ def _dp_worker(rank, world, port, overlap, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("overlap", [True, False])
-def test_gradient_allreduce_matches_global_batch(overlap):
+@pytest.mark.parametrize("overlap,reduce_dtype", [(True, None), (False, None), (True, torch.bfloat16),
+                                                  (False, torch.bfloat16)])
+def test_gradient_allreduce_matches_global_batch(overlap, reduce_dtype):
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     ctx = __import__("multiprocessing").get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, overlap, q)) for r in range(2)]
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, overlap, q, reduce_dtype)) for r in range(2)]
     for p in procs:
         p.start()
     results = sorted([q.get(timeout=120) for _ in procs], key=lambda t: t[0])
@@ -205,8 +207,9 @@ def test_gradient_allreduce_matches_global_batch(overlap):
     for (_, params, grads, replay_ok) in results:
         assert replay_ok
         for p, g, ref in zip(params, grads, model.parameters()):
-            assert rel_err(p, ref.detach()) < 1e-5
-            assert rel_err(g, ref.grad) < 1e-5
+            # fp32 wire: SURVEY.md 8(e)'s 1e-5; bf16 wire: each rank's gradient and the average are rounded to bf16 (2^-9 each)
+            assert rel_err(p, ref.detach()) < (1e-5 if reduce_dtype is None else 1e-2)
+            assert rel_err(g, ref.grad) < (1e-5 if reduce_dtype is None else 1e-2)
     for a, b in zip(results[0][1], results[1][1]):
         assert np.array_equal(a, b)  # replicas stay bit-identical
 
