@@ -10,13 +10,19 @@
 //   * the contraction runs over TOKENS, so both operands are MN-major for the tensor core: 128-token x
 //     64-column TMA boxes (128-byte swizzle) of grad_y and x are consumed in place — no transposes;
 //   * a CTA owns one 128 x (<= 256) tile of grad_W and one contiguous range of tokens (the grid is
-//     tiles x splits ~ one CTA per SM); warp 0 = TMA producer, warp 1 = tcgen05.mma issuer (M128 x N{<=256}
-//     x K16, accumulators in TMEM), warp 2 = TMEM allocator, warps 4-7 = epilogue;
+//     tiles x splits ~ one CTA per SM); warps 0, 2, 3 = TMA producers (the 3-6 boxes of a pipeline step are dealt
+//     round-robin to them), warp 1 = tcgen05.mma issuer (M128 x N{<=256} x K16, accumulators in TMEM), warp 2
+//     also allocates TMEM, warp 3 also writes the ones block, warps 4-7 = epilogue.  Measured with 1 / 2 / 3
+//     producers (profiles/r2i_wgrad_producers.txt): no change at the stage-1..3 shapes, 3-6 % at stage 4 — the
+//     kernel is NOT bound by the box-issue rate of one thread; at the short token counts of stages 3-4 the
+//     time is launch + ramp, ~13 us of streaming and then ~9 us in which every CTA dumps its 128 x 256 fp32
+//     partial tile through red.global.add at once (18-24 splits per output element, 19 MB of reductions);
 //   * the bias gradient is one more MMA per step against a constant block of ones (N = 16): grad_y^T 1;
 //   * partial tiles are added into the zeroed fp32 gradient with 16-byte vector reductions
 //     (red.global.add.v4.f32): no partial buffers, no reduce kernel.  The order of those additions is not
 //     fixed, so the last bits of grad_W can differ from run to run (as with any atomic reduction).
 
+#include <cstdlib>
 #include <cstring>
 
 #include "tc_common.cuh"
@@ -38,6 +44,7 @@ struct WgParams {
   int n_tiles, k_tiles, splits, chunks, per_split;
   int bk;                  // columns of this launch's tiles (multiple of 64, <= 256)
   int stages, stage_bytes;
+  int nprod;               // TMA-issuing warps (1..3)
   uint32_t idesc, idesc_bias;
   float* gw;               // [N][K]
   float* gb;               // [N] or nullptr
@@ -85,7 +92,7 @@ __global__ void __launch_bounds__(THREADS, 1)
     prefetch_tensormap(&maps.g);
     prefetch_tensormap(&maps.x);
     for (int i = 0; i < p.stages; ++i) {
-      mbar_init(&bar.full[i], 1);
+      mbar_init(&bar.full[i], (uint32_t)p.nprod);  // every producer arrives with the bytes of its own boxes
       mbar_init(&bar.empty[i], 1);
     }
     mbar_init(&bar.acc_full, 1);
@@ -102,18 +109,25 @@ __global__ void __launch_bounds__(THREADS, 1)
   fence_after_sync();
   const uint32_t tmem = bar.tmem_base;
 
-  if (warp == 0) {
-    // ===================================== TMA producer =====================================
-    if (lane == 0) {
+  const int prod = warp == 0 ? 0 : warp == 2 ? 1 : warp == 3 ? 2 : -1;
+  if (prod >= 0) {
+    // ===================================== TMA producers ====================================
+    // box b of a step: b < 2 -> grad_y columns n0 + 64 b (columns past N: zero-filled), else x columns
+    // k0 + 64 (b - 2); producer j issues the boxes b == j (mod nprod)
+    const int nboxes = 2 + xboxes;  // 3..6 >= nprod
+    if (lane == 0 && prod < p.nprod) {
+      const uint32_t my_bytes = (uint32_t)((nboxes - prod + p.nprod - 1) / p.nprod) * BOX_BYTES;
       for (int i = 0; i < my_chunks; ++i) {
         const int s = i % p.stages, tok0 = (c_begin + i) * TOK;
         mbar_wait(&bar.empty[s], ((i / p.stages) & 1) ^ 1);
-        mbar_expect_tx(&bar.full[s], (uint32_t)p.stage_bytes);
+        mbar_expect_tx(&bar.full[s], my_bytes);
         const uint32_t st = ring + s * p.stage_bytes;
-        tma_load_2d(st, &maps.g, &bar.full[s], n0, tok0);                  // columns past N: zero-filled
-        tma_load_2d(st + BOX_BYTES, &maps.g, &bar.full[s], n0 + 64, tok0);
-        for (int j = 0; j < xboxes; ++j)
-          tma_load_2d(st + (2 + j) * BOX_BYTES, &maps.x, &bar.full[s], k0 + j * 64, tok0);
+        for (int b = prod; b < nboxes; b += p.nprod) {
+          if (b < 2)
+            tma_load_2d(st + b * BOX_BYTES, &maps.g, &bar.full[s], n0 + 64 * b, tok0);
+          else
+            tma_load_2d(st + b * BOX_BYTES, &maps.x, &bar.full[s], k0 + (b - 2) * 64, tok0);
+        }
       }
     }
   } else if (warp == 1) {
@@ -185,6 +199,16 @@ int make_map(CUtensorMap* m, const void* base, int64_t inner, int64_t rows, int6
   return CSB200_OK;
 }
 
+// CSB200_WGRAD_PRODUCERS=1|2|3 (experiments; default 3)
+int wgrad_producers() {
+  static const int n = [] {
+    const char* e = getenv("CSB200_WGRAD_PRODUCERS");
+    const int v = e != nullptr ? atoi(e) : 3;
+    return v < 1 ? 1 : v > 3 ? 3 : v;
+  }();
+  return n;
+}
+
 bool shape_ok(int64_t M, int64_t N, int64_t K, int dtype) {
   if (dtype != CSB200_BF16) return false;
   if (M < 1 || M > 0x7fffffff / 2 || N < 8 || N > 65536 || K < 64 || K > 65536) return false;
@@ -240,6 +264,7 @@ CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* gra
   const int fixed = BOX_BYTES + (int)sizeof(WgBars) + 1024;
   p.stages = (SMEM_LIMIT - fixed) / p.stage_bytes;
   if (p.stages > MAX_STAGES) p.stages = MAX_STAGES;
+  p.nprod = wgrad_producers();
   p.idesc = umma_idesc_bf16(p.bk, true, true);
   p.idesc_bias = umma_idesc_bf16(16, true, true);
   p.gw = grad_w;
