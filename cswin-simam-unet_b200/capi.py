@@ -52,7 +52,9 @@ EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_coun
            "csb200_linear_supported", "csb200_linear_fwd", "csb200_linear_dgelu_supported",
            "csb200_linear_dgelu_workspace_bytes", "csb200_linear_dgelu_bwd", "csb200_linear_dact_bwd",
            "csb200_linear_wgrad_supported",
-           "csb200_linear_wgrad")
+           "csb200_linear_wgrad", "csb200_layernorm_bwd_partials", "csb200_colsum_partials",
+           "csb200_linear_dact_bwd_partials", "csb200_sum_rows_deferred", "csb200_sum_rows_pending",
+           "csb200_sum_rows_flush", "csb200_sum_rows_discard")
 EPI_BIAS, EPI_GELU, EPI_GELU_SAVE, EPI_GELU_SAVE_DERIV = 0, 1, 2, 3
 
 
@@ -130,6 +132,18 @@ def lib() -> ctypes.CDLL:
         L.csb200_linear_wgrad_supported.restype = ctypes.c_int
         L.csb200_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, ctypes.c_int, vp]
         L.csb200_linear_wgrad.restype = ctypes.c_int
+        pp, ip = ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32)
+        L.csb200_layernorm_bwd_partials.argtypes = [vp] * 6 + [ctypes.c_int, vp, ctypes.c_size_t, i64, i64, ctypes.c_int,
+                                                    ctypes.c_int, pp, ip, vp]
+        L.csb200_colsum_partials.argtypes = [vp, vp, ctypes.c_size_t, i64, i64, ctypes.c_int, pp, ip, vp]
+        L.csb200_linear_dact_bwd_partials.argtypes = [vp, vp, vp, vp, vp, ctypes.c_size_t, i64, i64, i64, i64,
+                                                      ctypes.c_int, ctypes.c_int, pp, ip, vp]
+        L.csb200_sum_rows_deferred.argtypes = [vp, i64, i64, i64, vp]
+        L.csb200_sum_rows_flush.argtypes = [vp]
+        L.csb200_sum_rows_pending.restype = ctypes.c_int64
+        for fn in ("csb200_layernorm_bwd_partials", "csb200_colsum_partials", "csb200_linear_dact_bwd_partials",
+                   "csb200_sum_rows_deferred", "csb200_sum_rows_flush", "csb200_sum_rows_discard"):
+            getattr(L, fn).restype = ctypes.c_int
         L.csb200_carafe_supported.argtypes = [i64]
         L.csb200_carafe_supported.restype = ctypes.c_int
         L.csb200_carafe_fwd.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, ctypes.c_int, ctypes.c_int, vp]

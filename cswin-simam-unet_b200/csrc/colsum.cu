@@ -118,7 +118,8 @@ int add_row_bias_t(const void* x, const float* bias, void* y, int64_t rows, int6
 }
 
 template <typename T>
-int colsum_t(const void* x, float* out, float* partial, int64_t rows, int64_t cols, cudaStream_t st) {
+int colsum_t(const void* x, float* out, float* partial, int64_t rows, int64_t cols, cudaStream_t st,
+             int32_t* partial_rows = nullptr) {
   constexpr int VE = Vec16<T>::N;
   const int cvn = (int)(cols / VE);
   const int tpb = 256 / cvn * cvn;
@@ -128,6 +129,10 @@ int colsum_t(const void* x, float* out, float* partial, int64_t rows, int64_t co
   colsum_partial<T><<<(int)grid, tpb, 0, st>>>(static_cast<const T*>(x), partial, nvec, cvn);
   int rc = check_launch("colsum_partial");
   if (rc != CSB200_OK) return rc;
+  if (partial_rows != nullptr) {  // deferred final sum (csb200_sum_rows_deferred / _flush, sum_rows.cu)
+    *partial_rows = (int32_t)grid;
+    return CSB200_OK;
+  }
   colsum_final<<<(int)((cols * 32 + 255) / 256), 256, 0, st>>>(partial, (int)grid, (int)cols, out);
   return check_launch("colsum_final");
 }
@@ -162,6 +167,25 @@ extern "C" int csb200_colsum(const void* x, float* out, void* workspace, size_t 
   float* partial = static_cast<float*>(workspace);
   return dtype == CSB200_F32 ? colsum_t<float>(x, out, partial, rows, cols, st)
                              : colsum_t<__nv_bfloat16>(x, out, partial, rows, cols, st);
+}
+
+// csb200_colsum without its last launch: float[*partial_rows][cols] stays in the workspace.
+extern "C" int csb200_colsum_partials(const void* x, void* workspace, size_t workspace_bytes, int64_t rows,
+                                      int64_t cols, int dtype, const float** partials, int32_t* partial_rows,
+                                      void* stream) {
+  if (rows < 1 || !csb200_colsum_supported(cols, dtype))
+    return fail(CSB200_ERR_UNSUPPORTED, "colsum_partials: rows=%lld cols=%lld dtype=%d", (long long)rows,
+                (long long)cols, dtype);
+  if (!x || !workspace || !partials || !partial_rows) return fail(CSB200_ERR_INVALID, "colsum_partials: null pointer");
+  if (workspace_bytes < csb200_colsum_workspace_bytes(cols))
+    return fail(CSB200_ERR_WORKSPACE, "colsum_partials: workspace too small");
+  if ((reinterpret_cast<uintptr_t>(x) & 15) != 0)
+    return fail(CSB200_ERR_INVALID, "colsum_partials: x must be 16-byte aligned");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  float* partial = static_cast<float*>(workspace);
+  *partials = partial;
+  return dtype == CSB200_F32 ? colsum_t<float>(x, nullptr, partial, rows, cols, st, partial_rows)
+                             : colsum_t<__nv_bfloat16>(x, nullptr, partial, rows, cols, st, partial_rows);
 }
 
 extern "C" int csb200_add_row_bias(const void* x, const float* bias, void* y, int64_t rows, int64_t cols,

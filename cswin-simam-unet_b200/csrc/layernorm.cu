@@ -417,7 +417,7 @@ int ln_fwd_t(const void* x, const void* res, void* sum_out, const float* gamma, 
 template <typename TIn, typename TGy, typename TGx>
 int ln_bwd_t(const void* x, const void* gy, const void* gres, const float* gamma, const float* stats,
              void* gx, float* ggamma, float* gbeta, float* grbias, float* partial, int64_t rows, int64_t C,
-             cudaStream_t st) {
+             cudaStream_t st, bool rb, int32_t* partial_rows) {
   constexpr int NE = 16 / sizeof(TIn);
   int lpr, cpl;
   if (!ln_shape<TIn>(C, &lpr, &cpl))
@@ -425,7 +425,7 @@ int ln_bwd_t(const void* x, const void* gy, const void* gres, const float* gamma
   const int grid = ln_grid(rows, 32 / lpr, cpl == 1 ? LN_MAX_GRID_BWD : 148);  // wide rows: 150+ registers, 1 CTA / SM
 #define CALL(L, P)                                                                       \
   do {                                                                                   \
-    if (grbias != nullptr)                                                               \
+    if (rb)                                                                              \
       layernorm_bwd_kernel<TIn, TGy, TGx, L, P, NE, true><<<grid, LN_THREADS, 0, st>>>(  \
           static_cast<const TIn*>(x), static_cast<const TGy*>(gy), gamma, stats,         \
           static_cast<const TGx*>(gres), static_cast<TGx*>(gx), partial, rows);          \
@@ -438,7 +438,11 @@ int ln_bwd_t(const void* x, const void* gy, const void* gres, const float* gamma
 #undef CALL
   int rc = check_launch("layernorm_bwd_kernel");
   if (rc != CSB200_OK) return rc;
-  const int K = grbias != nullptr ? 3 : 2;
+  if (partial_rows != nullptr) {  // deferred: the caller records the final sums (csb200_sum_rows_deferred)
+    *partial_rows = grid;
+    return CSB200_OK;
+  }
+  const int K = rb ? 3 : 2;
   layernorm_param_grad_final<<<(int)((K * C * 32 + 255) / 256), 256, 0, st>>>(partial, grid, (int)C, K,
                                                                          ggamma, gbeta, grbias);
   return check_launch("layernorm_param_grad_final");
@@ -501,11 +505,15 @@ extern "C" size_t csb200_layernorm_bwd_workspace_bytes(int64_t rows, int64_t cha
 static int ln_bwd_dispatch(const void* x, const void* grad_y, const void* grad_res, const float* gamma,
                            const float* stats, void* grad_x, float* grad_gamma, float* grad_beta,
                            float* grad_res_bias, void* workspace, size_t workspace_bytes, int64_t rows,
-                           int64_t channels, int x_dtype, int gy_dtype, void* stream) {
+                           int64_t channels, int x_dtype, int gy_dtype, void* stream, bool rb = false,
+                           int32_t* partial_rows = nullptr) {
   if (rows < 0 || channels <= 0 || !ok_dtype(x_dtype) || !ok_dtype(gy_dtype))
     return fail(CSB200_ERR_INVALID, "layernorm_bwd: bad size or dtype");
-  if (!x || !grad_y || !gamma || !stats || !grad_x || !grad_gamma || !grad_beta || !workspace)
+  const bool deferred = partial_rows != nullptr;
+  if (!deferred) rb = grad_res_bias != nullptr;
+  if (!x || !grad_y || !gamma || !stats || !grad_x || (!deferred && (!grad_gamma || !grad_beta)) || !workspace)
     return fail(CSB200_ERR_INVALID, "layernorm_bwd: null pointer");
+  if (deferred && rows == 0) return fail(CSB200_ERR_INVALID, "layernorm_bwd_partials: rows == 0 has no partial rows");
   if (workspace_bytes < csb200_layernorm_bwd_workspace_bytes(rows, channels))
     return fail(CSB200_ERR_WORKSPACE, "layernorm_bwd: workspace too small");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -520,14 +528,14 @@ static int ln_bwd_dispatch(const void* x, const void* grad_y, const void* grad_r
   if (x_dtype == CSB200_F32)
     return gy_dtype == CSB200_F32
                ? ln_bwd_t<float, float, float>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma,
-                                               grad_beta, grad_res_bias, partial, rows, channels, st)
+                                               grad_beta, grad_res_bias, partial, rows, channels, st, rb, partial_rows)
                : ln_bwd_t<float, bf16, float>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma,
-                                              grad_beta, grad_res_bias, partial, rows, channels, st);
+                                              grad_beta, grad_res_bias, partial, rows, channels, st, rb, partial_rows);
   return gy_dtype == CSB200_F32
              ? ln_bwd_t<bf16, float, bf16>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma, grad_beta,
-                                           grad_res_bias, partial, rows, channels, st)
+                                           grad_res_bias, partial, rows, channels, st, rb, partial_rows)
              : ln_bwd_t<bf16, bf16, bf16>(x, grad_y, grad_res, gamma, stats, grad_x, grad_gamma, grad_beta,
-                                          grad_res_bias, partial, rows, channels, st);
+                                          grad_res_bias, partial, rows, channels, st, rb, partial_rows);
 }
 
 extern "C" int csb200_layernorm_bwd(const void* x, const void* grad_y, const float* gamma,
@@ -556,4 +564,18 @@ extern "C" int csb200_add_layernorm_bwd_rb(const void* sum, const void* grad_y, 
   if (!grad_res_bias) return fail(CSB200_ERR_INVALID, "add_layernorm_bwd_rb: null pointer");
   return ln_bwd_dispatch(sum, grad_y, grad_sum, gamma, stats, grad_x, grad_gamma, grad_beta, grad_res_bias,
                          workspace, workspace_bytes, rows, channels, x_dtype, gy_dtype, stream);
+}
+
+// The same pass without its last launch: the per-CTA partial sums stay in the workspace as
+// float[*partial_rows][(2 + with_res_bias) * channels] for csb200_sum_rows_deferred / _flush (sum_rows.cu).
+extern "C" int csb200_layernorm_bwd_partials(const void* sum_or_x, const void* grad_y, const void* grad_sum,
+                                             const float* gamma, const float* stats, void* grad_x,
+                                             int with_res_bias, void* workspace, size_t workspace_bytes,
+                                             int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
+                                             const float** partials, int32_t* partial_rows, void* stream) {
+  if (!partials || !partial_rows) return fail(CSB200_ERR_INVALID, "layernorm_bwd_partials: null pointer");
+  *partials = static_cast<const float*>(workspace);
+  *partial_rows = 0;
+  return ln_bwd_dispatch(sum_or_x, grad_y, grad_sum, gamma, stats, grad_x, nullptr, nullptr, nullptr, workspace,
+                         workspace_bytes, rows, channels, x_dtype, gy_dtype, stream, with_res_bias != 0, partial_rows);
 }

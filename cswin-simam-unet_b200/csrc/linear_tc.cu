@@ -502,10 +502,12 @@ CSB200_API size_t csb200_linear_dgelu_workspace_bytes(int64_t N) {
 
 static int linear_dact_impl(int epi, const void* grad_y, const void* weight, const void* pre_act, void* grad_h,
                             float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M, int64_t N,
-                            int64_t K, int64_t ldg, int dtype, void* stream) {
-  if (M == 0) return CSB200_OK;
-  if (grad_y == nullptr || weight == nullptr || pre_act == nullptr || grad_h == nullptr || grad_bias == nullptr ||
-      workspace == nullptr)
+                            int64_t K, int64_t ldg, int dtype, void* stream, const float** partials = nullptr,
+                            int32_t* partial_rows = nullptr) {
+  const bool deferred = partial_rows != nullptr;
+  if (M == 0) return deferred ? fail(CSB200_ERR_INVALID, "csb200_linear_dact_bwd_partials: M == 0") : CSB200_OK;
+  if (grad_y == nullptr || weight == nullptr || pre_act == nullptr || grad_h == nullptr ||
+      (!deferred && grad_bias == nullptr) || workspace == nullptr)
     return fail(CSB200_ERR_INVALID, "csb200_linear_dgelu_bwd: null pointer");
   if (!shape_ok(M, N, K, dtype, 64))
     return fail(CSB200_ERR_UNSUPPORTED, "csb200_linear_dgelu_bwd: bf16 with K in {64,128,256} and N a multiple of 64 "
@@ -523,6 +525,11 @@ static int linear_dact_impl(int epi, const void* grad_y, const void* weight, con
                          M, N, K, ldg, st);
   if (rc != CSB200_OK) return rc;
   if (rows > MAX_PARTIAL_ROWS) return fail(CSB200_ERR_WORKSPACE, "csb200_linear_dgelu_bwd: %d partial rows", rows);
+  if (deferred) {  // the caller records the final sum (csb200_sum_rows_deferred / _flush, sum_rows.cu)
+    *partials = partial;
+    *partial_rows = rows;
+    return CSB200_OK;
+  }
   linear_colsum_final<<<(int)((N * 32 + 255) / 256), 256, 0, st>>>(partial, rows, (int)N, grad_bias);
   return check_launch("linear_colsum_final");
 }
@@ -539,6 +546,18 @@ CSB200_API int csb200_linear_dact_bwd(const void* grad_y, const void* weight, co
                                       int64_t N, int64_t K, int64_t ldg, int dtype, void* stream) {
   return linear_dact_impl(EPI_DMUL, grad_y, weight, act_deriv, grad_h, grad_bias, workspace, workspace_bytes, M, N, K,
                           ldg, dtype, stream);
+}
+
+// Both input-gradient GEMMs without their last launch: the per-CTA column sums of grad_h stay in the workspace
+// as float[*partial_rows][N] at *partials.
+CSB200_API int csb200_linear_dact_bwd_partials(const void* grad_y, const void* weight, const void* act, void* grad_h,
+                                               void* workspace, size_t workspace_bytes, int64_t M, int64_t N,
+                                               int64_t K, int64_t ldg, int dtype, int use_saved_derivative,
+                                               const float** partials, int32_t* partial_rows, void* stream) {
+  if (partials == nullptr || partial_rows == nullptr)
+    return fail(CSB200_ERR_INVALID, "csb200_linear_dact_bwd_partials: null pointer");
+  return linear_dact_impl(use_saved_derivative ? EPI_DMUL : EPI_DGELU, grad_y, weight, act, grad_h, nullptr, workspace,
+                          workspace_bytes, M, N, K, ldg, dtype, stream, partials, partial_rows);
 }
 
 }  // extern "C"

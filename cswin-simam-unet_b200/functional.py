@@ -76,6 +76,102 @@ def _ptr(t: Optional[torch.Tensor], elem_offset: int = 0):
 # ------------------------------------------------------------------------------------------------
 # SimAM
 # ------------------------------------------------------------------------------------------------
+# ---- deferred final sums (include/csb200.h "Deferred final sums", csrc/sum_rows.cu) ---------------------------
+# The LayerNorm parameter gradients, the column-sum bias gradients and the fc1 bias gradient of the fused Mlp all
+# end with a 4-5 us "sum the per-CTA partial rows" launch: 106 of them on the critical path of one 512^2 backward
+# pass, for vectors nobody reads before the optimizer step.  Inside ``with deferred_sums(device):`` those call
+# sites stop after their main kernel, record the sum, and ONE launch per 120 records performs them all when the
+# block exits — the gradient tensors autograd hands to the parameters are filled at that point.
+# Only valid when (TrainStep guarantees all three): every ``.grad`` is None when backward starts (a second
+# contribution would be ADDED to a vector that is not filled yet), nothing reads the gradients before the block
+# exits (no post-accumulate hooks launching all-reduces), and backward runs on the current stream.
+_deferred: Optional[list] = None  # off: None; on: tensors that must stay allocated until the flush
+_deferred_outs: list = []         # the sum vectors among them (checked at the flush: were they adopted?)
+
+
+class deferred_sums:
+    def __init__(self, device):
+        self.device = torch.device(device)
+
+    def __enter__(self):
+        global _deferred
+        if _deferred is not None:
+            raise RuntimeError("deferred_sums blocks do not nest")
+        capi.lib().csb200_sum_rows_discard()
+        _deferred = []
+        del _deferred_outs[:]
+        return self
+
+    def __exit__(self, etype, evalue, tb):
+        global _deferred
+        keep, _deferred = _deferred, None
+        outs = list(_deferred_outs)
+        del _deferred_outs[:]
+        lib = capi.lib()
+        if etype is not None:
+            lib.csb200_sum_rows_discard()
+            return False
+        # Every recorded vector went to autograd as a view; if that view is gone, AccumulateGrad did not adopt it
+        # but cloned it (before it was filled) or the gradient was dropped: refuse loudly rather than train on
+        # garbage.  (storage use count: this list's tensor + the handle below = 2, an adopted view makes 3)
+        for out in outs:
+            if torch._C._storage_Use_Count(out.untyped_storage()._cdata) <= 2:
+                lib.csb200_sum_rows_discard()
+                raise RuntimeError("deferred_sums: a deferred gradient vector was not adopted by autograd (gradient "
+                                   "accumulation into an existing .grad, or a copy): use the immediate sums")
+        with torch.cuda.device(self.device):
+            capi.check(lib.csb200_sum_rows_flush(_vp(torch.cuda.current_stream(self.device).cuda_stream)),
+                       "csb200_sum_rows_flush")
+        keep.clear()  # freed in stream order: after the flush kernel
+        return False
+
+
+def _defer_sum(partials: int, partial_rows: int, cols: int, out: torch.Tensor, *keep: torch.Tensor) -> torch.Tensor:
+    """Record out[c] = sum of the partial rows; returns a VIEW of ``out`` for the caller to hand to autograd.
+    ``out`` itself stays referenced here until the flush (its storage must not be recycled if autograd drops the
+    gradient), and AccumulateGrad only adopts a gradient tensor nobody else references — a tensor that is also
+    held here would be CLONED at accumulation time, before the flush has filled it; a view is adopted as it is."""
+    capi.check(capi.lib().csb200_sum_rows_deferred(partials, partial_rows, cols, cols, _ptr(out)),
+               "csb200_sum_rows_deferred")
+    _deferred.extend(keep)
+    _deferred.append(out)
+    _deferred_outs.append(out)
+    return out.view(-1)
+
+
+def _layernorm_bwd_call(lib, s, gy, gres, w, stats, gx, want_rb: bool, rows: int, C: int, defer_ok: bool = True):
+    """LayerNorm backward (plain when gres is None and not want_rb); returns (grad_gamma, grad_beta,
+    grad_res_bias or None) — immediate, or views of one vector filled at the deferred flush."""
+    nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
+    wsp = torch.empty(nws, dtype=torch.uint8, device=s.device)
+    st = _vp(capi.stream_of(s))
+    xc, gc = capi.dtype_code(s), capi.dtype_code(gy)
+    if _deferred is not None and defer_ok and rows > 0:
+        K = 3 if want_rb else 2
+        out = torch.empty(K * C, dtype=torch.float32, device=s.device)
+        pp, pr = ctypes.c_void_p(), ctypes.c_int32()
+        capi.check(lib.csb200_layernorm_bwd_partials(_ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx),
+                                                     int(want_rb), _ptr(wsp), nws, rows, C, xc, gc, ctypes.byref(pp),
+                                                     ctypes.byref(pr), st), "csb200_layernorm_bwd_partials")
+        out = _defer_sum(pp.value, pr.value, K * C, out, wsp)
+        return out[:C], out[C:2 * C], (out[2 * C:] if want_rb else None)
+    gw, gb = torch.empty_like(w), torch.empty_like(w)
+    if want_rb:
+        grb = torch.empty_like(w)
+        capi.check(lib.csb200_add_layernorm_bwd_rb(_ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx),
+                                                   _ptr(gw), _ptr(gb), _ptr(grb), _ptr(wsp), nws, rows, C, xc, gc, st),
+                   "csb200_add_layernorm_bwd_rb")
+        return gw, gb, grb
+    if gres is None:
+        capi.check(lib.csb200_layernorm_bwd(_ptr(s), _ptr(gy), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb),
+                                            _ptr(wsp), nws, rows, C, xc, gc, st), "csb200_layernorm_bwd")
+    else:
+        capi.check(lib.csb200_add_layernorm_bwd(_ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx),
+                                                _ptr(gw), _ptr(gb), _ptr(wsp), nws, rows, C, xc, gc, st),
+                   "csb200_add_layernorm_bwd")
+    return gw, gb, None
+
+
 def _simam_dims(x: torch.Tensor, layout: str) -> Tuple[int, int, int, int]:
     if layout == "NCHW":
         if x.dim() != 4:
@@ -197,15 +293,10 @@ class _LayerNormFn(torch.autograd.Function):
         rows = x.numel() // C
         gy = gy.contiguous()
         gx = torch.empty_like(x)
-        gw, gb = torch.empty_like(w), torch.empty_like(w)
-        lib = capi.lib()
-        nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
-        wsp = torch.empty(nws, dtype=torch.uint8, device=x.device)
         nbytes = x.numel() * (2 * x.element_size() + gy.element_size())
         with torch.cuda.device(x.device), _span("layernorm_bwd", nbytes, 0, f"{rows}x{C}"):
-            capi.check(lib.csb200_layernorm_bwd(_ptr(x), _ptr(gy), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb),
-                                                _ptr(wsp), nws, rows, C, capi.dtype_code(x), capi.dtype_code(gy),
-                                                _vp(capi.stream_of(x))), "csb200_layernorm_bwd")
+            gw, gb, _ = _layernorm_bwd_call(capi.lib(), x, gy, None, w, stats, gx, False, rows, C,
+                                            defer_ok=ctx.needs_input_grad[1] and ctx.needs_input_grad[2])
         return gx, gw, gb, None, None
 
 
@@ -248,28 +339,16 @@ class _AddLayerNormFn(torch.autograd.Function):
         if gy is None:  # the normalised branch was unused: only the residual stream carries gradient
             grb = None
             if want_rb and gs is not None:
-                grb = _bias_grad(gs.reshape(rows, C).contiguous(), C).to(ctx.rb_dtype)
+                grb = _bias_grad(gs.reshape(rows, C).contiguous(), C, ctx.rb_dtype)
             return gs, gs, None, None, None, None, grb
         gy = gy.contiguous()
         gres = None if gs is None else gs.to(s.dtype).contiguous()
         gx = torch.empty_like(s)
-        gw, gb = torch.empty_like(w), torch.empty_like(w)
-        grb = torch.empty_like(w) if want_rb else None
-        lib = capi.lib()
-        nws = lib.csb200_layernorm_bwd_workspace_bytes(rows, C)
-        wsp = torch.empty(nws, dtype=torch.uint8, device=s.device)
         nbytes = s.numel() * ((2 + (gres is not None)) * s.element_size() + gy.element_size())
         with torch.cuda.device(s.device), _span("layernorm_bwd", nbytes, 0, f"{rows}x{C}"):
-            if want_rb:
-                capi.check(lib.csb200_add_layernorm_bwd_rb(
-                    _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(grb),
-                    _ptr(wsp), nws, rows, C, capi.dtype_code(s), capi.dtype_code(gy), _vp(capi.stream_of(s))),
-                    "csb200_add_layernorm_bwd_rb")
-            else:
-                capi.check(lib.csb200_add_layernorm_bwd(
-                    _ptr(s), _ptr(gy), _ptr(gres), _ptr(w), _ptr(stats), _ptr(gx), _ptr(gw), _ptr(gb), _ptr(wsp),
-                    nws, rows, C, capi.dtype_code(s), capi.dtype_code(gy), _vp(capi.stream_of(s))),
-                    "csb200_add_layernorm_bwd")
+            # (deferred only when all the vectors go to autograd as they are: wanted, and no cast of grad_res_bias)
+            ok = ctx.needs_input_grad[2] and ctx.needs_input_grad[3] and (not want_rb or ctx.rb_dtype == torch.float32)
+            gw, gb, grb = _layernorm_bwd_call(capi.lib(), s, gy, gres, w, stats, gx, want_rb, rows, C, defer_ok=ok)
         return gx, gx, gw, gb, None, None, None if grb is None else grb.to(ctx.rb_dtype)
 
 
@@ -296,7 +375,9 @@ class _RouteBiasGradFn(torch.autograd.Function):
         g2 = g.reshape(-1, n)
         if not g2.is_contiguous():
             g2 = g2.contiguous()
-        return g, _bias_grad(g2, n).to(ctx.b_dtype)
+        if not ctx.needs_input_grad[1]:
+            return g, None
+        return g, _bias_grad(g2, n, ctx.b_dtype)
 
 
 def route_bias_grad(delta: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
@@ -318,16 +399,24 @@ def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: f
 # ------------------------------------------------------------------------------------------------
 # Linear with a one-pass bias gradient
 # ------------------------------------------------------------------------------------------------
-def column_sum(x2d: torch.Tensor) -> torch.Tensor:
-    """fp32 column sums of a contiguous (rows, cols) CUDA matrix in one flat HBM pass."""
+def column_sum(x2d: torch.Tensor, deferrable: bool = False) -> torch.Tensor:
+    """fp32 column sums of a contiguous (rows, cols) CUDA matrix in one flat HBM pass.  ``deferrable``: inside a
+    ``deferred_sums`` block the result may be filled at the end of the block (the caller must not read it)."""
     rows, cols = x2d.shape
     lib = capi.lib()
     out = torch.empty(cols, dtype=torch.float32, device=x2d.device)
     nws = lib.csb200_colsum_workspace_bytes(cols)
     wsp = torch.empty(nws, dtype=torch.uint8, device=x2d.device)
     with torch.cuda.device(x2d.device), _span("colsum", x2d.numel() * x2d.element_size(), 0, f"{rows}x{cols}"):
-        capi.check(lib.csb200_colsum(_ptr(x2d), _ptr(out), _ptr(wsp), nws, rows, cols, capi.dtype_code(x2d),
-                                     _vp(capi.stream_of(x2d))), "csb200_colsum")
+        if deferrable and _deferred is not None and rows > 0:
+            pp, pr = ctypes.c_void_p(), ctypes.c_int32()
+            capi.check(lib.csb200_colsum_partials(_ptr(x2d), _ptr(wsp), nws, rows, cols, capi.dtype_code(x2d),
+                                                  ctypes.byref(pp), ctypes.byref(pr), _vp(capi.stream_of(x2d))),
+                       "csb200_colsum_partials")
+            out = _defer_sum(pp.value, pr.value, cols, out, wsp)
+        else:
+            capi.check(lib.csb200_colsum(_ptr(x2d), _ptr(out), _ptr(wsp), nws, rows, cols, capi.dtype_code(x2d),
+                                         _vp(capi.stream_of(x2d))), "csb200_colsum")
     return out
 
 
@@ -450,7 +539,7 @@ class _LinearFn(torch.autograd.Function):
             if ctx.needs_input_grad[1]:
                 gw = _wgrad(g2, x2, w_dtype)
             if want_b:
-                gb = _bias_grad(g2, n).to(b_dtype)
+                gb = _bias_grad(g2, n, b_dtype)
         return gx, gw, gb, None
 
 
@@ -509,8 +598,15 @@ def _wgrad(g2: torch.Tensor, x2: torch.Tensor, w_dtype: torch.dtype) -> torch.Te
     return torch.mm(g2.t(), x2).to(w_dtype)
 
 
-def _bias_grad(g2: torch.Tensor, n: int) -> torch.Tensor:
-    """fp32 column sums of a (rows, n) gradient: csb200_colsum when the width tiles, else ATen."""
+def _bias_grad(g2: torch.Tensor, n: int, final_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """Column sums of a (rows, n) gradient, accumulated in fp32 and returned as ``final_dtype`` (None: fp32):
+    csb200_colsum when the width tiles, else ATen.  A caller that passes ``final_dtype`` promises to hand the
+    result to autograd unread, so the fp32 case may be deferred (``deferred_sums``)."""
+    if final_dtype is not None:
+        if final_dtype == torch.float32 and g2.is_contiguous() and g2.data_ptr() % 16 == 0 \
+                and capi.lib().csb200_colsum_supported(n, capi.dtype_code(g2)):
+            return column_sum(g2, deferrable=True)
+        return _bias_grad(g2, n).to(final_dtype)
     if g2.is_contiguous() and g2.data_ptr() % 16 == 0:
         code, rows = capi.dtype_code(g2), g2.shape[0]
         if capi.lib().csb200_colsum_supported(n, code):
@@ -578,7 +674,7 @@ class _LinearGeluFn(torch.autograd.Function):
         return gx, gw, (gb.to(b_dtype) if ctx.needs_input_grad[2] else None), None
 
 
-def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor, deriv: bool = False):
+def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor, deriv: bool = False, defer_bias: bool = False):
     """(grad_h, grad_bias) = csb200_linear_dgelu_bwd: grad_h = (g W2) * GELU'(h) in one tcgen05 GEMM.
     ``deriv``: ``h2`` already holds GELU'(h) (forward epilogue EPI_GELU_SAVE_DERIV) -> csb200_linear_dact_bwd,
     whose epilogue is one multiplication per element."""
@@ -593,9 +689,17 @@ def _tc_dgelu(g2: torch.Tensor, w2c: torch.Tensor, h2: torch.Tensor, deriv: bool
     fn = lib.csb200_linear_dact_bwd if deriv else lib.csb200_linear_dgelu_bwd
     with torch.cuda.device(g2.device), _span("linear_tc", nbytes, 2 * M * N * K,
                                              f"M{M}xN{N}xK{K}{'dact' if deriv else 'dgelu'}"):
-        capi.check(fn(_ptr(g2), _ptr(w2c), _ptr(h2), _ptr(dh), _ptr(gb), _ptr(wsp), nws, M, N, K,
-                      g2.stride(0), capi.BF16, _vp(capi.stream_of(g2))),
-                   "csb200_linear_dact_bwd" if deriv else "csb200_linear_dgelu_bwd")
+        if defer_bias and _deferred is not None and M > 0:  # gb is filled when the deferred_sums block exits
+            pp, pr = ctypes.c_void_p(), ctypes.c_int32()
+            capi.check(lib.csb200_linear_dact_bwd_partials(_ptr(g2), _ptr(w2c), _ptr(h2), _ptr(dh), _ptr(wsp), nws, M, N,
+                                                           K, g2.stride(0), capi.BF16, int(deriv), ctypes.byref(pp),
+                                                           ctypes.byref(pr), _vp(capi.stream_of(g2))),
+                       "csb200_linear_dact_bwd_partials")
+            gb = _defer_sum(pp.value, pr.value, N, gb, wsp)
+        else:
+            capi.check(fn(_ptr(g2), _ptr(w2c), _ptr(h2), _ptr(dh), _ptr(gb), _ptr(wsp), nws, M, N, K,
+                          g2.stride(0), capi.BF16, _vp(capi.stream_of(g2))),
+                       "csb200_linear_dact_bwd" if deriv else "csb200_linear_dgelu_bwd")
     return dh, gb
 
 
@@ -631,7 +735,8 @@ class _MlpFn(torch.autograd.Function):
         g2 = gy.reshape(-1, w2c.shape[0])
         if g2.dtype != torch.bfloat16 or not g2.is_contiguous():
             g2 = g2.to(torch.bfloat16).contiguous()
-        dh, gb1 = _tc_dgelu(g2, w2c, h, ctx.deriv)
+        # (the fc1 bias gradient may be deferred when it goes to autograd as it is: fp32 parameter)
+        dh, gb1 = _tc_dgelu(g2, w2c, h, ctx.deriv, defer_bias=b1_dtype == torch.float32 and ctx.needs_input_grad[2])
         gx = gw1 = gw2 = gb2 = None
         if ctx.needs_input_grad[0]:
             gx = torch.mm(dh, w1c).view(x_shape).to(x_dtype)
@@ -645,7 +750,7 @@ class _MlpFn(torch.autograd.Function):
             if ctx.needs_input_grad[3]:
                 gw2 = _wgrad(g2, a, w2_dtype)
             if want_b2:
-                gb2 = _bias_grad(g2, g2.shape[1]).to(b2_dtype)
+                gb2 = _bias_grad(g2, g2.shape[1], b2_dtype)
         return gx, gw1, (gb1.to(b1_dtype) if ctx.needs_input_grad[2] else None), gw2, gb2
 
 
@@ -711,12 +816,13 @@ class _Conv2dFn(torch.autograd.Function):
             [ctx.needs_input_grad[0], ctx.needs_input_grad[1], False])
         gb = None
         if b_dtype is not None and ctx.needs_input_grad[2]:
-            gb = channel_sum(gy).to(b_dtype)
+            gb = channel_sum(gy, b_dtype)
         return (None if gx is None else gx.to(x_dtype)), (None if gw is None else gw.to(w_dtype)), gb, None, None, None
 
 
-def channel_sum(g: torch.Tensor) -> torch.Tensor:
-    """fp32 sum over (B, H, W) of a (B, C, H, W) tensor; one flat csb200 pass when it is channels-last."""
+def channel_sum(g: torch.Tensor, final_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """fp32 sum over (B, H, W) of a (B, C, H, W) tensor; one flat csb200 pass when it is channels-last.
+    ``final_dtype``: as in ``_bias_grad`` (the result goes to autograd unread)."""
     B, C, H, W = g.shape
     if g.dtype in (torch.float32, torch.bfloat16) and g.is_cuda:
         if not g.is_contiguous(memory_format=torch.channels_last) and g.stride(1) == 1:
@@ -724,8 +830,9 @@ def channel_sum(g: torch.Tensor) -> torch.Tensor:
             # C:657): one compacting copy + a flat column sum beats ATen's strided reduction 5x
             g = g.contiguous(memory_format=torch.channels_last)
         if g.is_contiguous(memory_format=torch.channels_last):
-            return _bias_grad(g.permute(0, 2, 3, 1).reshape(B * H * W, C), C)
-    return g.sum((0, 2, 3), dtype=torch.float32)
+            return _bias_grad(g.permute(0, 2, 3, 1).reshape(B * H * W, C), C, final_dtype)
+    out = g.sum((0, 2, 3), dtype=torch.float32)
+    return out if final_dtype is None else out.to(final_dtype)
 
 
 def conv2d(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor], stride=1, padding=0) -> torch.Tensor:
@@ -767,7 +874,7 @@ class _ChannelBiasFn(torch.autograd.Function):
 
     @staticmethod
     def backward(ctx, g):
-        return g, (channel_sum(g).to(ctx.b_dtype) if ctx.needs_input_grad[1] else None)
+        return g, (channel_sum(g, ctx.b_dtype) if ctx.needs_input_grad[1] else None)
 
 
 def add_channel_bias(x: torch.Tensor, bias: torch.Tensor) -> torch.Tensor:

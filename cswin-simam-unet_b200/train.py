@@ -10,6 +10,7 @@ BCELoss on probabilities).  No ``.item()`` is called here: the reference's five 
 (C:797-806) are the caller's choice, not the step's.
 """
 import contextlib
+import os
 from typing import Tuple
 
 import torch
@@ -109,6 +110,7 @@ class TrainStep:
         self.model, self.optimizer, self.precision, self.reducer = model, optimizer, precision, reducer
         self.cuda_graph = cuda_graph
         self.capture_collectives = capture_collectives  # data parallel: NCCL all-reduces inside the captured backward
+        self.defer_sums = os.environ.get("CSB200_DEFER_SUMS", "1") != "0"  # see _backward
         self._reduce_in_graph = False
         self._graph = self._graph_opt = None
         self._shadow = None  # (fp32 masters, bf16 shadows): see functional.shadow_params
@@ -134,6 +136,19 @@ class TrainStep:
         if self.precision == "bf16":
             return torch.autocast(device_type=device_type, dtype=torch.bfloat16)
         return contextlib.nullcontext()
+
+    def _backward(self, loss: torch.Tensor) -> None:
+        """loss.backward() with the ~100 "sum the per-CTA partials" launches of the pass (LayerNorm parameter
+        gradients, bias column sums) batched into one at its end (``functional.deferred_sums``).  The conditions
+        hold here: every ``.grad`` was just set to None, the gradients are first read after this returns (the
+        reducer's hooks only launch collectives mid-backward in overlap mode, which therefore keeps the immediate
+        sums), and the whole step runs on the current stream."""
+        overlapped = self.reducer is not None and self.reducer.world > 1 and self.reducer.overlap
+        if loss.is_cuda and self.defer_sums and not overlapped:
+            with csbF.deferred_sums(loss.device):
+                loss.backward()
+        else:
+            loss.backward()
 
     def forward_loss(self, images: torch.Tensor, masks: torch.Tensor) -> torch.Tensor:
         with self._autocast(images.device.type):
@@ -244,7 +259,7 @@ class TrainStep:
             self.optimizer.zero_grad(set_to_none=True)
             with torch.cuda.graph(self._graph):
                 loss = self.forward_loss(self._x, self._y)
-                loss.backward()
+                self._backward(loss)
                 self._loss = loss.detach()
             self.optimizer.prepare(freeze=True)
             torch.cuda.synchronize(dev)
@@ -283,7 +298,7 @@ class TrainStep:
         with torch.cuda.graph(self._graph):
             self.reducer.begin_step()
             loss = self.forward_loss(self._x, self._y)
-            loss.backward()
+            self._backward(loss)
             if in_graph:
                 self.reducer.finish_step()  # launches what the hooks have not, joins NCCL's stream to the capture
             else:
@@ -322,7 +337,7 @@ class TrainStep:
         else:
             self.optimizer.zero_grad(set_to_none=True)
         loss = self.forward_loss(images, masks)
-        loss.backward()
+        self._backward(loss)
         if self.reducer is not None:
             self.reducer.finish_step()  # wait for the bucketed all-reduces
         self._optimizer_step()

@@ -200,6 +200,41 @@ CSB200_API int csb200_linear_dact_bwd(const void* grad_y, const void* weight, co
                                       float* grad_bias, void* workspace, size_t workspace_bytes, int64_t M,
                                       int64_t N, int64_t K, int64_t ldg, int dtype, void* stream);
 
+/* ------------------------------------------------------------------------------------------------
+ * Deferred final sums.  csb200_layernorm_bwd / _add_layernorm_bwd(_rb), csb200_colsum and
+ * csb200_linear_dgelu_bwd / _dact_bwd all end with the same tiny launch: out[c] = sum over the per-CTA partial
+ * rows of partial[r][c] (fixed order).  One backward pass of the 512^2 model issues 106 of them, ~4-5 us each
+ * on the critical path of the stream, for results nobody reads before the optimizer step.  The `_partials`
+ * twins below stop after the main kernel and hand back where the partial rows are; the caller records the sums
+ * it wants with csb200_sum_rows_deferred and ONE launch per 120 records performs them all at
+ * csb200_sum_rows_flush (same summation order as the immediate kernels: bit-identical results).
+ * CONTRACT: the workspace holding the partial rows and the `out` vectors must stay allocated and untouched
+ * until the flush; the record list is process-wide (one deferring client at a time), guarded by a mutex;
+ * records and flush must be issued in stream order on the same stream (or a stream ordered after it).
+ *   *partials      : float[*partial_rows][row_stride], inside `workspace`
+ *   layernorm      : row_stride = (2 + with_res_bias) * channels: grad_gamma | grad_beta | grad_res_bias
+ *   colsum         : row_stride = cols
+ *   linear dact    : row_stride = N (fc1 bias gradient); use_saved_derivative selects _dact_ (1) or _dgelu_ (0)
+ * ---------------------------------------------------------------------------------------------- */
+CSB200_API int csb200_layernorm_bwd_partials(const void* sum_or_x, const void* grad_y, const void* grad_sum,
+                                             const float* gamma, const float* stats, void* grad_x,
+                                             int with_res_bias, void* workspace, size_t workspace_bytes,
+                                             int64_t rows, int64_t channels, int x_dtype, int gy_dtype,
+                                             const float** partials, int32_t* partial_rows, void* stream);
+CSB200_API int csb200_colsum_partials(const void* x, void* workspace, size_t workspace_bytes, int64_t rows,
+                                      int64_t cols, int dtype, const float** partials, int32_t* partial_rows,
+                                      void* stream);
+CSB200_API int csb200_linear_dact_bwd_partials(const void* grad_y, const void* weight, const void* act, void* grad_h,
+                                               void* workspace, size_t workspace_bytes, int64_t M, int64_t N,
+                                               int64_t K, int64_t ldg, int dtype, int use_saved_derivative,
+                                               const float** partials, int32_t* partial_rows, void* stream);
+/* record: out[c] = sum_{r < rows} partial[r * row_stride + c] for c < cols (performed at the next flush) */
+CSB200_API int csb200_sum_rows_deferred(const float* partial, int64_t rows, int64_t cols, int64_t row_stride,
+                                        float* out);
+CSB200_API int64_t csb200_sum_rows_pending(void);
+CSB200_API int csb200_sum_rows_flush(void* stream);  /* performs and clears the records */
+CSB200_API int csb200_sum_rows_discard(void);        /* clears them without performing (error paths) */
+
 /* Parameter gradients of a token-path nn.Linear (backward of C:357-358, C:366, C:188-196 w.r.t. weight / bias):
  *     grad_w[N][K] = grad_y[M][N]^T x[M][K],      grad_bias[n] = sum_m grad_y[m][n]   (nullable)
  * bf16 operands (row strides ldg / ldx elements), fp32 outputs, OVERWRITTEN (zeroed inside, then accumulated by

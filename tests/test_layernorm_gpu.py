@@ -237,3 +237,53 @@ def test_bf16_layernorm_and_fused_add_at_large_row_counts(shape, with_residual):
     assert rel_err(xd.grad.float().cpu(), x64.grad) < 2 ** -7
     # gamma / beta gradients: fp32 sums of bf16-rounded terms over >= 4096 rows
     assert rel_err(wd.grad.cpu(), w64.grad) < 2 ** -7 and rel_err(bd.grad.cpu(), b64.grad) < 2 ** -7
+
+
+def test_deferred_final_sums_equal_the_immediate_ones_bit_for_bit():
+    """csb200_sum_rows_deferred / _flush (one launch per 120 recorded sums) against the immediate final kernels:
+    LayerNorm parameter gradients (plain, fused add, with the residual-bias gradient), bias column sums and
+    the raw entry point with more than 120 records of ragged sizes."""
+    lib = pkg.capi.lib()
+    torch.manual_seed(3)
+    # raw records: 130 jobs -> two launches
+    parts = [torch.randn(r, c, device="cuda") for r, c in [(1 + (7 * i) % 40, 8 * (1 + i % 9)) for i in range(130)]]
+    outs = [torch.full((p.shape[1],), float("nan"), device="cuda") for p in parts]
+    assert lib.csb200_sum_rows_discard() == 0 and lib.csb200_sum_rows_pending() == 0
+    for p, o in zip(parts, outs):
+        pkg.capi.check(lib.csb200_sum_rows_deferred(p.data_ptr(), p.shape[0], p.shape[1], p.shape[1], o.data_ptr()), "rec")
+    assert lib.csb200_sum_rows_pending() == 130
+    n0 = pkg.capi.launch_count()
+    pkg.capi.check(lib.csb200_sum_rows_flush(torch.cuda.current_stream().cuda_stream), "flush")
+    assert pkg.capi.launch_count() - n0 == 2 and lib.csb200_sum_rows_pending() == 0
+    for p, o in zip(parts, outs):
+        assert rel_err(o.cpu(), p.double().sum(0).cpu()) < 1e-5
+    assert lib.csb200_sum_rows_deferred(0, 1, 8, 8, outs[0].data_ptr()) != 0  # null partials are refused
+
+    # through autograd: the same ops inside / outside a deferred_sums block
+    x = torch.randn(4, 3000, 256, device="cuda", dtype=torch.bfloat16)
+    r = torch.randn_like(x)
+    # (every parameter is used ONCE: a second contribution would be added to a vector that is not filled yet —
+    # the documented precondition of deferred_sums)
+    ps = [torch.randn(256, device="cuda", requires_grad=True) for _ in range(6)]
+    w0, b0, w1, b1, rb, cb = ps
+    g = torch.randn_like(x)
+
+    def run(deferred):
+        for p in ps:
+            p.grad = None
+        ctx = csbF.deferred_sums("cuda") if deferred else __import__("contextlib").nullcontext()
+        n0 = pkg.capi.launch_count()
+        with ctx:
+            y0 = csbF.layer_norm(x, w0, b0, out_dtype=torch.bfloat16)
+            s, y1 = csbF.add_layer_norm(x, r, w1, b1, out_dtype=torch.bfloat16, residual_bias=rb)
+            y2 = csbF.route_bias_grad(x, cb)
+            torch.autograd.backward([y0, s, y1, y2], [g, g, g, g])
+        return [p.grad.clone() for p in ps], pkg.capi.launch_count() - n0
+
+    now, n_now = run(False)
+    later, n_later = run(True)
+    assert all(torch.equal(a, c) for a, c in zip(now, later))
+    assert n_later == n_now - 2  # three final launches became one
+    with pytest.raises(RuntimeError, match="nest"):
+        with csbF.deferred_sums("cuda"), csbF.deferred_sums("cuda"):
+            pass

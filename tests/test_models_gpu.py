@@ -206,6 +206,32 @@ def test_cuda_graph_step_matches_eager_step():
     assert losses[True][-1] != losses[True][0]
 
 
+def test_train_step_with_deferred_final_sums_equals_the_immediate_step():
+    """TrainStep batches the ~100 "sum the per-CTA partials" launches of backward into one
+    (functional.deferred_sums): gradients identical to the step that launches each sum at once — bit for bit
+    for the LayerNorm parameters and the biases (same summation order), and fewer csb200 launches."""
+    grads, launches = {}, {}
+    for defer in (False, True):
+        torch.manual_seed(0)
+        net = pkg.CSWinTransformer(img_size=128, split_size=[1, 2, 4, 4], simam=True).cuda()
+        step = pkg.TrainStep(net, torch.optim.SGD(net.parameters(), lr=0.0), precision="bf16")
+        step.defer_sums = defer
+        x, y = pkg.synthetic_batch(2, 128, "cuda", seed=5)
+        step(x, y)
+        n0 = pkg.capi.launch_count()
+        step(x, y)
+        launches[defer] = pkg.capi.launch_count() - n0
+        grads[defer] = {k: p.grad.clone() for k, p in net.named_parameters()}
+        assert pkg.capi.lib().csb200_sum_rows_pending() == 0
+    assert launches[True] < launches[False] - 40, launches
+    for k, g in grads[False].items():
+        assert torch.isfinite(grads[True][k]).all(), k
+        if "norm" in k or k.endswith(".bias"):
+            assert torch.equal(grads[True][k], g), k
+        else:
+            assert rel_err(grads[True][k].cpu(), g.cpu()) < 1e-5, k
+
+
 def test_cuda_graph_step_with_reducer_single_rank():
     """The data-parallel graph path (two graphs around the bucket all-reduce) on one rank: same
     trajectory as the plain eager step; gradients live in the reducer's flat buckets."""
