@@ -52,7 +52,7 @@ EXPORTS = ("csb200_abi_version", "csb200_last_error_string", "csb200_launch_coun
            "csb200_linear_supported", "csb200_linear_fwd", "csb200_linear_dgelu_supported",
            "csb200_linear_dgelu_workspace_bytes", "csb200_linear_dgelu_bwd", "csb200_linear_dact_bwd",
            "csb200_linear_wgrad_supported",
-           "csb200_linear_wgrad", "csb200_layernorm_bwd_partials", "csb200_colsum_partials",
+           "csb200_linear_wgrad", "csb200_linear_wgrad_acc", "csb200_layernorm_bwd_partials", "csb200_colsum_partials",
            "csb200_linear_dact_bwd_partials", "csb200_sum_rows_deferred", "csb200_sum_rows_pending",
            "csb200_sum_rows_flush", "csb200_sum_rows_discard")
 EPI_BIAS, EPI_GELU, EPI_GELU_SAVE, EPI_GELU_SAVE_DERIV = 0, 1, 2, 3
@@ -132,6 +132,8 @@ def lib() -> ctypes.CDLL:
         L.csb200_linear_wgrad_supported.restype = ctypes.c_int
         L.csb200_linear_wgrad.argtypes = [vp, vp, vp, vp, i64, i64, i64, i64, i64, ctypes.c_int, vp]
         L.csb200_linear_wgrad.restype = ctypes.c_int
+        L.csb200_linear_wgrad_acc.argtypes = L.csb200_linear_wgrad.argtypes
+        L.csb200_linear_wgrad_acc.restype = ctypes.c_int
         pp, ip = ctypes.POINTER(ctypes.c_void_p), ctypes.POINTER(ctypes.c_int32)
         L.csb200_layernorm_bwd_partials.argtypes = [vp] * 6 + [ctypes.c_int, vp, ctypes.c_size_t, i64, i64, ctypes.c_int,
                                                     ctypes.c_int, pp, ip, vp]

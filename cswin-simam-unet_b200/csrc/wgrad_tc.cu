@@ -226,8 +226,8 @@ CSB200_API int csb200_linear_wgrad_supported(int64_t M, int64_t N, int64_t K, in
   return shape_ok(M, N, K, dtype) ? 1 : 0;
 }
 
-CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M,
-                                   int64_t N, int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream) {
+static int wgrad_impl(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M, int64_t N,
+                      int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream, bool zero_outputs) {
   if (grad_y == nullptr || x == nullptr || grad_w == nullptr)
     return fail(CSB200_ERR_INVALID, "csb200_linear_wgrad: null pointer");
   if (!shape_ok(M, N, K, dtype))
@@ -237,8 +237,10 @@ CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* gra
       (reinterpret_cast<uintptr_t>(x) & 15) || (reinterpret_cast<uintptr_t>(grad_w) & 15))
     return fail(CSB200_ERR_INVALID, "csb200_linear_wgrad: operands must be 16-byte aligned");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  CSB200_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)N * K * sizeof(float), st));
-  if (grad_bias != nullptr) CSB200_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)N * sizeof(float), st));
+  if (zero_outputs) {
+    CSB200_CUDA(cudaMemsetAsync(grad_w, 0, (size_t)N * K * sizeof(float), st));
+    if (grad_bias != nullptr) CSB200_CUDA(cudaMemsetAsync(grad_bias, 0, (size_t)N * sizeof(float), st));
+  }
   WgMaps maps;
   WgParams p;
   memset(&maps, 0, sizeof(maps));
@@ -278,6 +280,19 @@ CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* gra
   CSB200_CUDA(opt_in_smem(reinterpret_cast<const void*>(&wgrad_tc_kernel), SMEM_LIMIT));
   wgrad_tc_kernel<<<tiles * p.splits, THREADS, smem, st>>>(maps, p);
   return check_launch("wgrad_tc_kernel");
+}
+
+CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M,
+                                   int64_t N, int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream) {
+  return wgrad_impl(grad_y, x, grad_w, grad_bias, M, N, K, ldg, ldx, dtype, stream, true);
+}
+
+// The same pass ADDING into grad_w / grad_bias (no memsets): the caller hands over zero-filled outputs — one
+// arena zeroed by ONE memset per backward pass instead of two memset nodes in front of every call — or partial
+// gradients to accumulate into.
+CSB200_API int csb200_linear_wgrad_acc(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M,
+                                       int64_t N, int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream) {
+  return wgrad_impl(grad_y, x, grad_w, grad_bias, M, N, K, ldg, ldx, dtype, stream, false);
 }
 
 }  // extern "C"

@@ -89,9 +89,18 @@ _deferred: Optional[list] = None  # off: None; on: tensors that must stay alloca
 _deferred_outs: list = []         # the sum vectors among them (checked at the flush: were they adopted?)
 
 
+_zero_arena = None  # [buffer or None, offset, demand]: see deferred_sums(zero_arena_numel=...)
+
+
 class deferred_sums:
-    def __init__(self, device):
+    """``zero_arena_numel``: also serve the accumulate-into outputs of the pass (csb200_linear_wgrad's grad_w /
+    grad_b, two memset nodes in front of each of the 35 calls of a 512^2 backward) from ONE fp32 buffer zeroed
+    once on entry; ``arena_demand`` afterwards = the elements the pass asked for (size the next arena with it)."""
+
+    def __init__(self, device, zero_arena_numel: int = 0):
         self.device = torch.device(device)
+        self.zero_arena_numel = int(zero_arena_numel)
+        self.arena_demand = 0
 
     def __enter__(self):
         global _deferred
@@ -100,10 +109,18 @@ class deferred_sums:
         capi.lib().csb200_sum_rows_discard()
         _deferred = []
         del _deferred_outs[:]
+        global _zero_arena
+        buf = None
+        if self.zero_arena_numel > 0:
+            with torch.cuda.device(self.device):
+                buf = torch.zeros(self.zero_arena_numel, dtype=torch.float32, device=self.device)
+        _zero_arena = [buf, 0, 0]
         return self
 
     def __exit__(self, etype, evalue, tb):
         global _deferred
+        global _zero_arena
+        self.arena_demand, _zero_arena = _zero_arena[2], None
         keep, _deferred = _deferred, None
         outs = list(_deferred_outs)
         del _deferred_outs[:]
@@ -124,6 +141,20 @@ class deferred_sums:
                        "csb200_sum_rows_flush")
         keep.clear()  # freed in stream order: after the flush kernel
         return False
+
+
+def _zeroed(numel: int, device) -> Optional[torch.Tensor]:
+    """``numel`` zero-filled fp32 elements out of the arena of the enclosing deferred_sums block (256-byte
+    aligned), or None (no block, no arena yet, or the arena is exhausted: the caller zeroes its own buffer)."""
+    if _zero_arena is None:
+        return None
+    need = (numel + 63) // 64 * 64
+    buf, off, _ = _zero_arena
+    _zero_arena[2] += need
+    if buf is None or buf.device != torch.device(device) or off + need > buf.numel():
+        return None
+    _zero_arena[1] = off + need
+    return buf[off:off + numel]
 
 
 def _defer_sum(partials: int, partial_rows: int, cols: int, out: torch.Tensor, *keep: torch.Tensor) -> torch.Tensor:
@@ -580,11 +611,18 @@ def _tc_wgrad(g2: torch.Tensor, x2: torch.Tensor, want_bias: bool):
     """(grad_W fp32 [N][K], grad_b fp32 [N] or None) = csb200_linear_wgrad(g2 [M][N], x2 [M][K])."""
     M, N = g2.shape
     K = x2.shape[1]
-    gw = torch.empty((N, K), dtype=torch.float32, device=g2.device)
-    gb = torch.empty(N, dtype=torch.float32, device=g2.device) if want_bias else None
+    lib = capi.lib()
+    arena = _zeroed(N * K + (N if want_bias else 0), g2.device)  # both outputs from one zero-filled slice, or None
+    if arena is not None:
+        gw, gb, fn, name = arena[:N * K].view(N, K), (arena[N * K:] if want_bias else None), lib.csb200_linear_wgrad_acc, \
+            "csb200_linear_wgrad_acc"
+    else:
+        gw = torch.empty((N, K), dtype=torch.float32, device=g2.device)
+        gb = torch.empty(N, dtype=torch.float32, device=g2.device) if want_bias else None
+        fn, name = lib.csb200_linear_wgrad, "csb200_linear_wgrad"
     with torch.cuda.device(g2.device), _span("wgrad_tc", 2 * M * (N + K) + 4 * N * K, 2 * M * N * K, f"M{M}xN{N}xK{K}"):
-        capi.check(capi.lib().csb200_linear_wgrad(_ptr(g2), _ptr(x2), _ptr(gw), _ptr(gb), M, N, K, g2.stride(0),
-                                                  x2.stride(0), capi.BF16, _vp(capi.stream_of(g2))), "csb200_linear_wgrad")
+        capi.check(fn(_ptr(g2), _ptr(x2), _ptr(gw), _ptr(gb), M, N, K, g2.stride(0), x2.stride(0), capi.BF16,
+                      _vp(capi.stream_of(g2))), name)
     return gw, gb
 
 

@@ -111,6 +111,7 @@ class TrainStep:
         self.cuda_graph = cuda_graph
         self.capture_collectives = capture_collectives  # data parallel: NCCL all-reduces inside the captured backward
         self.defer_sums = os.environ.get("CSB200_DEFER_SUMS", "1") != "0"  # see _backward
+        self._zero_arena_numel = 0
         self._reduce_in_graph = False
         self._graph = self._graph_opt = None
         self._shadow = None  # (fp32 masters, bf16 shadows): see functional.shadow_params
@@ -145,8 +146,11 @@ class TrainStep:
         sums), and the whole step runs on the current stream."""
         overlapped = self.reducer is not None and self.reducer.world > 1 and self.reducer.overlap
         if loss.is_cuda and self.defer_sums and not overlapped:
-            with csbF.deferred_sums(loss.device):
+            # the weight-gradient kernels accumulate into zeroed outputs: one arena, zeroed once, sized by what
+            # the previous pass asked for (the first pass zeroes per call)
+            with csbF.deferred_sums(loss.device, zero_arena_numel=self._zero_arena_numel) as block:
                 loss.backward()
+            self._zero_arena_numel = block.arena_demand
         else:
             loss.backward()
 

@@ -244,6 +244,10 @@ CSB200_API int csb200_sum_rows_discard(void);        /* clears them without perf
 CSB200_API int csb200_linear_wgrad_supported(int64_t M, int64_t N, int64_t K, int dtype);
 CSB200_API int csb200_linear_wgrad(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M,
                                    int64_t N, int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream);
+/* The same pass ADDING into grad_w / grad_bias instead of overwriting them (no memsets inside): for outputs carved
+ * from an arena the caller zeroed once for the whole backward pass, or for gradient accumulation. */
+CSB200_API int csb200_linear_wgrad_acc(const void* grad_y, const void* x, float* grad_w, float* grad_bias, int64_t M,
+                                   int64_t N, int64_t K, int64_t ldg, int64_t ldx, int dtype, void* stream);
 
 /* ------------------------------------------------------------------------------------------------
  * Optimizer step for every parameter tensor of the model in one launch — `optimizer.step()` of the

@@ -187,3 +187,26 @@ def test_wgrad_on_strided_operands():
     g, x = big_g[:, 64:256], big_x[:, 128:]
     gw, gb = csbF._tc_wgrad(g, x, True)
     assert rel_err(gw, g.double().t() @ x.double()) < 1e-4 and rel_err(gb, g.double().sum(0)) < 1e-4
+
+
+def test_wgrad_into_the_zero_arena_of_a_deferred_block():
+    """csb200_linear_wgrad_acc: inside ``deferred_sums(zero_arena_numel=...)`` grad_W / grad_b are slices of ONE buffer
+    zeroed once (no memset nodes per call); a first block without an arena measures the demand, an exhausted arena
+    falls back to the self-zeroing call."""
+    gen = torch.Generator().manual_seed(11)
+    g = torch.randn((4096, 192), generator=gen).to(torch.bfloat16).cuda()
+    x = torch.randn((4096, 64), generator=gen).to(torch.bfloat16).cuda()
+    ref_w, ref_b = g.double().t() @ x.double(), g.double().sum(0)
+    with csbF.deferred_sums("cuda") as first:
+        gw, gb = csbF._tc_wgrad(g, x, True)
+    assert first.arena_demand >= 192 * 64 + 192 and rel_err(gw, ref_w) < 1e-4
+    n0 = pkg.capi.launch_count()
+    with csbF.deferred_sums("cuda", zero_arena_numel=first.arena_demand) as block:
+        gw1, gb1 = csbF._tc_wgrad(g, x, True)      # served by the arena
+        gw2, gb2 = csbF._tc_wgrad(g, x, True)      # arena exhausted: standalone buffers
+    assert block.arena_demand == 2 * first.arena_demand
+    assert gw1.untyped_storage().data_ptr() == gb1.untyped_storage().data_ptr()
+    assert gw2.untyped_storage().data_ptr() != gb2.untyped_storage().data_ptr()
+    for a, b in ((gw1, gb1), (gw2, gb2)):
+        assert rel_err(a, ref_w) < 1e-4 and rel_err(b, ref_b) < 1e-4
+    assert pkg.capi.launch_count() - n0 == 2

@@ -223,10 +223,12 @@ def test_train_step_with_deferred_final_sums_equals_the_immediate_step():
         launches[defer] = pkg.capi.launch_count() - n0
         grads[defer] = {k: p.grad.clone() for k, p in net.named_parameters()}
         assert pkg.capi.lib().csb200_sum_rows_pending() == 0
+        assert (step._zero_arena_numel > 0) == defer  # the second step's weight-gradient outputs came from the arena
     assert launches[True] < launches[False] - 40, launches
     for k, g in grads[False].items():
         assert torch.isfinite(grads[True][k]).all(), k
-        if "norm" in k or k.endswith(".bias"):
+        # (qkv.bias rides in csb200_linear_wgrad, whose atomic accumulation order is not fixed)
+        if "norm" in k or (k.endswith(".bias") and "qkv" not in k):
             assert torch.equal(grads[True][k], g), k
         else:
             assert rel_err(grads[True][k].cpu(), g.cpu()) < 1e-5, k
