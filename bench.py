@@ -305,6 +305,8 @@ def run_ours(args, rank, local_rank, world):
     launches = pkg.capi.launch_count() - n0
     host_issue_ms = timed.host_ms
     csbF.set_kernel_timer(None)
+    # (read now: `step` is released further down, before the other legs allocate)
+    reduce_in_graph, defer_sums = bool(getattr(step, "_reduce_in_graph", False)), bool(step.defer_sums)
     roofline_pass = "CUDA events inside the timed steps"
     if use_graph:
         # a replay launches the csb200 kernels recorded at capture: count them in one eager step and
@@ -437,9 +439,11 @@ def run_ours(args, rank, local_rank, world):
                    "precision": "autocast bf16, fp32 master weights, fp32 sigmoid+BCE", "optimizer": "AdamW, one csb200_adam_step launch" if args.optimizer == "csb200" else "AdamW (torch fused)",
                    "dropout": 0.0, "parallelism": f"dp{world}", "attn_engine": args.attn_engine,
                    "cuda_graph": bool(use_graph),
+                   "backward_final_sums": ("deferred: one csb200_sum_rows_flush launch per backward pass, weight-gradient "
+                                           "outputs from one zeroed arena" if defer_sums else "immediate"),
                    "dp_allreduce": (None if world == 1 else
                                     ("NCCL AVG, one fp32 bucket, captured in the graph after backward"
-                                     if getattr(step, "_reduce_in_graph", False) else
+                                     if reduce_in_graph else
                                      "NCCL AVG, fp32 buckets, issued eagerly between the two graphs")),
                    "l2": "no explicit flush: one step streams several GB of activations (>> 126 MB L2)",
                    "peak_mem_gib": round(mem_gb, 2)},
