@@ -166,3 +166,30 @@ def test_product_package_does_not_import_the_oracle():
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 assert not pat.search(open(os.path.join(dirpath, f)).read()), f
+
+
+def test_deferred_sum_recorder_is_host_side_bookkeeping():
+    """csb200_sum_rows_deferred only RECORDS (no device work until the flush): arguments are validated, the list
+    is process-wide and can be dropped; functional.deferred_sums refuses to nest and drops its records when the
+    block raises (no flush, hence nothing a CPU-only box could not do)."""
+    lib = capi.lib()
+    assert lib.csb200_sum_rows_discard() == capi.OK and lib.csb200_sum_rows_pending() == 0
+    buf = (ctypes.c_float * 64)()
+    p = ctypes.addressof(buf)
+    assert lib.csb200_sum_rows_deferred(p, 4, 8, 8, p) == capi.OK
+    assert lib.csb200_sum_rows_deferred(p, 2, 8, 16, p) == capi.OK
+    assert lib.csb200_sum_rows_pending() == 2
+    for bad in ((None, 4, 8, 8, p), (p, 4, 8, 8, None), (p, 0, 8, 8, p), (p, 4, 0, 8, p), (p, 4, 8, 4, p)):
+        assert lib.csb200_sum_rows_deferred(*bad) == capi.ERR_INVALID
+        assert "csb200_sum_rows_deferred" in capi.last_error()
+    assert lib.csb200_sum_rows_pending() == 2
+    assert lib.csb200_sum_rows_discard() == capi.OK and lib.csb200_sum_rows_pending() == 0
+    with pytest.raises(ZeroDivisionError):
+        with F_.deferred_sums("cpu") as block:
+            assert lib.csb200_sum_rows_deferred(p, 4, 8, 8, p) == capi.OK
+            with pytest.raises(RuntimeError, match="nest"):
+                F_.deferred_sums("cpu").__enter__()
+            assert F_._zeroed(100, "cpu") is None and block.zero_arena_numel == 0  # no arena: callers zero their own
+            1 / 0
+    assert lib.csb200_sum_rows_pending() == 0 and F_._deferred is None and F_._zero_arena is None
+    assert block.arena_demand == 128  # what the block was asked for, rounded to 256-byte slices
