@@ -226,3 +226,56 @@ def test_reducer_single_process_manages_flat_grads():
     for p in model.parameters():
         assert flat.data_ptr() <= p.grad.data_ptr() < flat.data_ptr() + flat.numel() * 4
     assert red.gradient_bytes() == sum(p.numel() for p in model.parameters()) * 4
+
+
+def test_train_step_defers_the_final_sums_only_when_it_is_safe(monkeypatch):
+    """TrainStep._backward wraps loss.backward() in functional.deferred_sums only for CUDA losses, when enabled, and
+    never while a multi-rank reducer launches all-reduces from its gradient hooks (those read the gradients before
+    the block would have filled them)."""
+    from cswin_simam_unet_b200 import functional as csbF
+    used = []
+
+    class FakeBlock:
+        arena_demand = 123
+
+        def __init__(self, device, zero_arena_numel=0):
+            used.append(zero_arena_numel)
+
+        def __enter__(self):
+            return self
+
+        def __exit__(self, *exc):
+            return False
+
+    class FakeLoss:
+        is_cuda, device = True, "cuda:0"
+
+        def backward(self):
+            pass
+
+    class FakeReducer:
+        def __init__(self, world, overlap):
+            self.world, self.overlap = world, overlap
+
+    monkeypatch.setattr(csbF, "deferred_sums", FakeBlock)
+    model = _tiny_model()
+    step = pkg.TrainStep(model, torch.optim.SGD(model.parameters(), lr=0.1), precision="fp32")
+    step.defer_sums = True
+    step._backward(FakeLoss())
+    step._backward(FakeLoss())
+    assert used == [0, 123]  # the second pass sizes its zero arena with what the first one asked for
+    step.reducer = FakeReducer(world=2, overlap=True)
+    step._backward(FakeLoss())
+    assert used == [0, 123]
+    step.reducer = FakeReducer(world=2, overlap=False)  # bench.py: one bucket reduced after backward
+    step._backward(FakeLoss())
+    step.reducer = FakeReducer(world=1, overlap=True)   # a single rank launches nothing from its hooks
+    step._backward(FakeLoss())
+    assert len(used) == 4
+    step.defer_sums = False
+    step._backward(FakeLoss())
+    cpu_loss = FakeLoss()
+    cpu_loss.is_cuda = False
+    step.defer_sums = True
+    step._backward(cpu_loss)
+    assert len(used) == 4
