@@ -435,7 +435,7 @@ def run_ours(args, rank, local_rank, world):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
         "config": {"workload": f"CSWin-SimAM-UNet train step {IMG}x{IMG} (BASELINE configs[2]; configs[3] at N=8)",
-                   "global_batch": B * world, "batch_per_gpu": B, "split_size": SPLIT, "simam": "3 skip tensors (NLC)",
+                   "global_batch": B * world, "batch_per_gpu": B, "split_size": SPLIT, "simam": "3 skip tensors (NLC); parity UNPINNED by the reference (its checkout has no SimAM code): checked against the public simam_module restated in oracle/ops.py",
                    "precision": "autocast bf16, fp32 master weights, fp32 sigmoid+BCE", "optimizer": "AdamW, one csb200_adam_step launch" if args.optimizer == "csb200" else "AdamW (torch fused)",
                    "dropout": 0.0, "parallelism": f"dp{world}", "attn_engine": args.attn_engine,
                    "cuda_graph": bool(use_graph),
